@@ -1,0 +1,101 @@
+"""Categorical embed / decode, training-step loss and EMA (TEST INFRASTRUCTURE).
+
+Restates the parts of ``Geo3DStochInterp`` (a LightningModule, not importable here:
+lightning / geogen are absent) that sit on the hot path:
+  project/geodata-3d-unconditional/model_train_inference.py
+    _initialize_embedding :330-356, embed :361-370, decode :373-404, training_step :417-457
+  project/geodata-3d-conditional/callbacks.py  EMACallback.on_train_batch_end :238-268
+
+``decode_numpy`` spells out the fp32 operation ORDER that torch's CPU kernels use for the
+reference decode (verified bit-for-bit on logits in the build container,
+tests/golden/make_golden.py): sequential sum of squares without FMA -> sqrt -> clamp 1e-12
+-> divide; 15 sequential dot products without FMA; first-max argmax.  The CUDA decode
+kernel follows the same order so the integer output is bit-exact.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import interp as _interp
+
+
+def simplex_embedding(n_cats: int, n_dims: int) -> torch.Tensor:
+    """_initialize_embedding :330-356 — centred simplex, unit rows."""
+    m = torch.zeros(n_cats, n_dims)
+    m[:, :n_cats] = torch.eye(n_cats)
+    centroid = torch.ones(n_cats) / n_cats
+    centroid = torch.cat([centroid, torch.zeros(n_dims - n_cats)])
+    m[:, :n_cats] -= centroid[:n_cats].unsqueeze(0)
+    return m / m.norm(dim=1, keepdim=True)
+
+
+def embed(weight: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """embed :361-370 — [B,1,X,Y,Z] categories (-1..n-2) -> [B,E,X,Y,Z]."""
+    idx = x.squeeze(1).long() + 1
+    e = F.embedding(idx, weight)
+    return e.permute(0, 4, 1, 2, 3).contiguous()
+
+
+def decode_torch(weight: torch.Tensor, x: torch.Tensor, return_logits=False):
+    """decode :373-404, same op sequence as the reference (incl. the broadcast temp)."""
+    n_cat, E = weight.shape
+    xn = F.normalize(x, dim=1)
+    en = F.normalize(weight, dim=1)
+    logits = (xn.unsqueeze(1) * en.view(1, n_cat, E, 1, 1, 1)).sum(dim=2)
+    return logits if return_logits else torch.argmax(logits, dim=1)
+
+
+def normalized_embedding(weight: torch.Tensor) -> torch.Tensor:
+    """F.normalize(embedding.weight, dim=1) (:384) on CPU fp32 — 270 numbers, host side."""
+    return F.normalize(weight.detach().float().cpu(), dim=1)
+
+
+def decode_numpy(en: np.ndarray, x: np.ndarray, return_logits=False):
+    """Explicit-order fp32 decode.  en: [n_cat,E] already normalised; x: [B,E,...]."""
+    f32 = np.float32
+    x = np.ascontiguousarray(x, dtype=f32)
+    en = np.ascontiguousarray(en, dtype=f32)
+    E = x.shape[1]
+    ss = np.zeros_like(x[:, 0])
+    for e in range(E):
+        ss = (ss + (x[:, e] * x[:, e]).astype(f32)).astype(f32)
+    nrm = np.maximum(np.sqrt(ss).astype(f32), f32(1e-12))
+    xn = [(x[:, e] / nrm).astype(f32) for e in range(E)]
+    n_cat = en.shape[0]
+    logits = np.zeros((x.shape[0], n_cat) + x.shape[2:], f32)
+    for c in range(n_cat):
+        acc = np.zeros_like(ss)
+        for e in range(E):
+            acc = (acc + (xn[e] * en[c, e]).astype(f32)).astype(f32)
+        logits[:, c] = acc
+    if return_logits:
+        return logits
+    return np.argmax(logits, axis=1).astype(np.int64)  # first max, like torch.argmax
+
+
+def flow_loss(VT: torch.Tensor, VT_hat: torch.Tensor) -> torch.Tensor:
+    """training_step :443 — mse(VT, VT_hat) / mse(VT, 0)."""
+    return F.mse_loss(VT, VT_hat) / F.mse_loss(VT, torch.zeros_like(VT))
+
+
+def training_step_loss(net, weight, batch, noise1, X0, T, kind="linear", one_sided=True):
+    """training_step :417-457 with all random draws passed in:
+    X1 = embed(batch) + 1e-3*noise1 ; XT,VT = flow_objective(T,X0,X1) ; loss."""
+    X1 = embed(weight, batch)
+    X1 = X1 + 1e-3 * noise1
+    XT, VT = _interp.flow_objective(kind, T, X0, X1, one_sided=one_sided)
+    VT_hat = net(XT, T)
+    return flow_loss(VT, VT_hat), (XT, VT, VT_hat)
+
+
+def ema_update(shadow: torch.Tensor, param: torch.Tensor, decay: float) -> torch.Tensor:
+    """EMACallback.on_train_batch_end :263-266 — shadow = a*shadow + (1-a)*param."""
+    return decay * shadow + (1.0 - decay) * param
+
+
+def vote_probabilities(decoded: torch.Tensor, n_cat: int) -> torch.Tensor:
+    """inference_demo.ipynb cell 21 — one-hot vote over the ensemble axis (dim 0)."""
+    oh = F.one_hot(decoded.long(), n_cat).float()
+    return oh.mean(dim=0).movedim(-1, 0)
