@@ -112,7 +112,7 @@ def test_solvers_golden(golden_dir):
     np.testing.assert_array_equal(solvers.ode_sol_rk4(x0, _toy, 10, 1.0).numpy(), g["rk4_n10"])
     f = solvers.make_denoise_func(_toy, "linear", True)
     tr = solvers.integrate(f, x0, 0.05, 0.95, 9, "euler")
-    np.testing.assert_allclose(tr.numpy(), g["denoise_ode_n9"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(tr.numpy(), g["denoise_ode_n9"], rtol=2e-6, atol=2e-6)
     # SDE: replay the reference's randn_like draws (one per ode_func call, heun = 2 per step)
     torch.manual_seed(1234)
     f = solvers.make_denoise_func(_toy, "linear", True, epsilon=torch.tensor(0.1),
