@@ -1,0 +1,22 @@
+"""flowtrain-b200: the B200-native (sm_100a) hot path of flowtrain_stochastic_interpolation —
+the Unet3D velocity field v_theta(x_t, t), the interpolant construction, the fixed-grid ODE/SDE
+samplers and the categorical embed/decode — behind flowtrain's own Python API.
+
+Importing this package loads ``csrc/libftb.so`` (built by ``__graft_entry__.build()``); there is
+no PyTorch or CPU fallback for any of the math.
+"""
+from . import _lib  # noqa: F401  (fails loudly when the CUDA library is missing)
+from .interpolation import (BaseInterpolant, EncDecInterpolant, LinearInterpolant, MirrorInterpolant,
+                            SBDMInterpolant, StochasticInterpolator, TrigInterpolant)
+from .solvers import (ODEFlowSolver, ODEOneSidedDenoisingSolver, SDEOneSidedDenoisingSolver,
+                      integrate_fixed, odeSol_RK4)
+from .task import (EMAShadow, Geo3DStochInterp, decode, ema_update_, embed, flow_loss,
+                   simplex_embedding)
+from .unet3d import Unet3D
+
+__all__ = [
+    "Unet3D", "StochasticInterpolator", "BaseInterpolant", "LinearInterpolant", "TrigInterpolant",
+    "EncDecInterpolant", "SBDMInterpolant", "MirrorInterpolant", "ODEFlowSolver",
+    "ODEOneSidedDenoisingSolver", "SDEOneSidedDenoisingSolver", "odeSol_RK4", "integrate_fixed",
+    "Geo3DStochInterp", "EMAShadow", "embed", "decode", "flow_loss", "ema_update_", "simplex_embedding",
+]

@@ -1,0 +1,343 @@
+// Attention cores on the blocked bf16 qkv tensor (q | k | v channel thirds).
+//
+// LinearAttention (unet_attn_3d.py:308-341): q is already softmax_d(q)*scale (fused into the
+// to_qkv conv epilogue).  Here: k softmax over all voxels + memory tokens and the per-head
+// context ctx[d][e] = sum_n softmax_n(k)[d,n] v[e,n], as max -> partial sums -> combine.
+// The combine step folds the context into the output projection:
+//     to_out.0(W) . (ctx^T q)  ==  M_b . q   with  M_b[c, h*dh+d] = sum_e W[c, h*dh+e] ctx[h,d,e]
+// and writes M_b as a per-sample packed 1x1 conv weight, so "context x q", the output
+// projection, its bias, the trailing RMSNorm and the residual are ONE tensor-core conv launch.
+//
+// Attention (:357-373, :436-465): softmax(q k^T * dh^-0.5) v over n tokens + memory kv, tiled
+// over keys with an online softmax; one warp per query.
+#include "ops.h"
+
+namespace ftb {
+
+namespace {
+
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  if (v >= 0.f)
+    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else
+    atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__global__ void fill_kernel(float* p, float v, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// grid (nsplit, kcg, B): per-channel max of k over a voxel slice
+__global__ void __launch_bounds__(256)
+kmax_kernel(const bf16* __restrict__ qkv, int cgtot, int kcg0, size_t vox, int nsplit,
+            float* __restrict__ kmax, int hd) {
+  const int s = blockIdx.x, cgi = blockIdx.y, b = blockIdx.z;
+  const size_t per = (vox + nsplit - 1) / nsplit;
+  const size_t lo = (size_t)s * per, hi = min(vox, lo + per);
+  const bf16* base = qkv + ((size_t)b * cgtot + kcg0 + cgi) * vox * 8;
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+  for (size_t v = lo + threadIdx.x; v < hi; v += blockDim.x) {
+    float f[8];
+    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(base + v * 8)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+  }
+  __shared__ float red[8][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = warp_max(m[j]);
+  if ((threadIdx.x & 31) == 0)
+    for (int j = 0; j < 8; ++j) red[threadIdx.x >> 5][j] = m[j];
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float r = red[0][threadIdx.x];
+    for (int w = 1; w < 8; ++w) r = fmaxf(r, red[w][threadIdx.x]);
+    atomic_max_float(kmax + (size_t)b * hd + cgi * 8 + threadIdx.x, r);
+  }
+}
+
+// grid (nsplit, heads, B); partial ctx[d][e] = sum_n exp(k[d,n]-kmax[d]) v[e,n], s[d] = sum_n exp(.)
+template <int DH>
+__global__ void __launch_bounds__(256)
+ctx_partial_kernel(const bf16* __restrict__ qkv, int cgtot, int heads, size_t vox, int nsplit,
+                   const float* __restrict__ kmax, float* __restrict__ part) {
+  constexpr int T = 128;                    // voxels per tile
+  constexpr int EPT = DH * DH / 256;        // outputs per thread (consecutive e)
+  constexpr int CGH = DH / 8;               // channel groups per head
+  __shared__ __align__(16) float sp[T][DH];
+  __shared__ __align__(16) float sv[T][DH];
+  const int s = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int hd = heads * DH;
+  const size_t per = (vox + nsplit - 1) / nsplit;
+  const size_t lo = (size_t)s * per, hi = min(vox, lo + per);
+  const bf16* kbase = qkv + ((size_t)b * cgtot + (hd + h * DH) / 8) * vox * 8;
+  const bf16* vbase = qkv + ((size_t)b * cgtot + (2 * hd + h * DH) / 8) * vox * 8;
+  const float* km = kmax + (size_t)b * hd + h * DH;
+  const int d = (threadIdx.x * EPT) / DH, e0 = (threadIdx.x * EPT) % DH;
+  float acc[EPT];
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) acc[i] = 0.f;
+  float ssum = 0.f;
+  for (size_t t0 = lo; t0 < hi; t0 += T) {
+    const int nt = (int)min((size_t)T, hi - t0);
+    for (int idx = threadIdx.x; idx < T * CGH; idx += blockDim.x) {
+      const int n = idx % T, cgi = idx / T;
+      float fk[8], fv[8];
+      if (n < nt) {
+        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(kbase + ((size_t)cgi * vox + t0 + n) * 8)), fk);
+        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(vbase + ((size_t)cgi * vox + t0 + n) * 8)), fv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) fk[j] = __expf(fk[j] - __ldg(km + cgi * 8 + j));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { fk[j] = 0.f; fv[j] = 0.f; }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sp[n][cgi * 8 + j] = fk[j]; sv[n][cgi * 8 + j] = fv[j]; }
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int n = 0; n < T; ++n) {
+      const float pv = sp[n][d];
+#pragma unroll
+      for (int i = 0; i < EPT; ++i) acc[i] += pv * sv[n][e0 + i];
+      if (e0 == 0) ssum += pv;
+    }
+    __syncthreads();
+  }
+  float* out = part + (((size_t)b * heads + h) * nsplit + s) * (DH * DH + DH);
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) out[d * DH + e0 + i] = acc[i];
+  if (e0 == 0) out[DH * DH + d] = ssum;
+}
+
+// grid (B): merge partials + memory kv -> ctx; fold W_out -> packed per-sample weights
+__global__ void __launch_bounds__(256)
+combine_kernel(const float* __restrict__ part, int nsplit, const float* __restrict__ kmax, int heads,
+               int dh, const float* __restrict__ mem_kv, int n_mem, const float* __restrict__ w_out,
+               int C, float q_scale, bf16* __restrict__ wpack, float* __restrict__ ctx_dbg) {
+  extern __shared__ float sctx[];  // [heads][dh][dh]
+  const int b = blockIdx.x;
+  const int hd = heads * dh;
+  const int per = dh * dh + dh;
+  for (int o = threadIdx.x; o < heads * dh * dh; o += blockDim.x) {
+    const int e = o % dh, d = (o / dh) % dh, h = o / (dh * dh);
+    const float* pp = part + ((size_t)b * heads + h) * nsplit * per;
+    float c = 0.f, s = 0.f;
+    for (int sp = 0; sp < nsplit; ++sp) {
+      c += pp[(size_t)sp * per + d * dh + e];
+      s += pp[(size_t)sp * per + dh * dh + d];
+    }
+    // memory tokens (mem_kv[2][heads][dh][n_mem], :300,:320-323) join the softmax over n
+    const float m0 = kmax[(size_t)b * hd + h * dh + d];
+    const float* mk = mem_kv + ((size_t)h * dh + d) * n_mem;
+    const float* mv = mem_kv + ((size_t)heads * dh + (size_t)h * dh + e) * n_mem;
+    float m = m0;
+    for (int j = 0; j < n_mem; ++j) m = fmaxf(m, mk[j]);
+    const float r = __expf(m0 - m);
+    c *= r;
+    s *= r;
+    for (int j = 0; j < n_mem; ++j) {
+      const float pj = __expf(mk[j] - m);
+      c += pj * mv[j];
+      s += pj;
+    }
+    const float v = c / s;
+    sctx[o] = v;
+    if (ctx_dbg) ctx_dbg[(size_t)b * heads * dh * dh + o] = v;
+  }
+  __syncthreads();
+  // M_b[c][k = h*dh+d] = q_scale * sum_e W[c][h*dh+e] * ctx[h][d][e]; packed [ks][C/8][2][8][8]
+  bf16* dst = wpack + (size_t)b * C * hd;
+  for (int o = threadIdx.x; o < C * hd; o += blockDim.x) {
+    const int k = o % hd, c = o / hd;
+    const int h = k / dh, d = k % dh;
+    const float* wr = w_out + (size_t)c * hd + h * dh;
+    const float* cx = sctx + ((size_t)h * dh + d) * dh;
+    float a = 0.f;
+    for (int e = 0; e < dh; ++e) a += wr[e] * cx[e];
+    const int ks = k >> 4, kc = (k >> 3) & 1, k8 = k & 7;
+    dst[((((size_t)ks * (C / 8) + (c >> 3)) * 2 + kc) * 8 + (c & 7)) * 8 + k8] = __float2bfloat16(a * q_scale);
+  }
+}
+
+// ------------------------------------------------------------------ softmax attention
+// grid (B*heads, query tiles of 64); 4 warps; one warp per query; keys tiled by KT with
+// online softmax.  q/k/v of token n, head h, dim d: channel part*hd + h*dh + d of voxel n.
+template <int DH>
+__global__ void __launch_bounds__(128)
+full_attn_kernel(const bf16* __restrict__ qkv, int cgtot, int heads, int n,
+                 const float* __restrict__ mem_kv, int n_mem, bf16* __restrict__ out, int out_cgtot,
+                 float scale) {
+  constexpr int KT = 128;
+  constexpr int CGH = DH / 8;
+  constexpr int DPL = (DH + 31) / 32;  // output dims per lane
+  __shared__ float sk[KT][DH + 1];
+  __shared__ float sv[KT][DH + 1];
+  __shared__ float sq[4][DH];
+  __shared__ float spj[4][KT];
+  const int bh = blockIdx.x, b = bh / heads, h = bh % heads;
+  const int hd = heads * DH;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bf16* qb = qkv + ((size_t)b * cgtot + (h * DH) / 8) * (size_t)n * 8;
+  const bf16* kb = qkv + ((size_t)b * cgtot + (hd + h * DH) / 8) * (size_t)n * 8;
+  const bf16* vb = qkv + ((size_t)b * cgtot + (2 * hd + h * DH) / 8) * (size_t)n * 8;
+  const int nk = n + n_mem;
+  const int q0 = blockIdx.y * 64;
+  // each warp walks queries q0+warp, q0+warp+4, ...; all warps share the key tiles, so the
+  // loops are organised tile-outer and the per-query state lives in registers (16 queries/warp).
+  constexpr int QPW = 16;
+  float m_run[QPW], l_run[QPW], o_run[QPW][DPL];
+#pragma unroll
+  for (int i = 0; i < QPW; ++i) {
+    m_run[i] = -INFINITY;
+    l_run[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) o_run[i][j] = 0.f;
+  }
+  for (int k0 = 0; k0 < nk; k0 += KT) {
+    const int kt = min(KT, nk - k0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < KT * CGH; idx += blockDim.x) {
+      const int j = idx % KT, cgi = idx / KT;
+      const int key = k0 + j;
+      float fk[8], fv[8];
+      if (j < kt && key >= n_mem) {
+        const size_t tok = (size_t)(key - n_mem);
+        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(kb + ((size_t)cgi * n + tok) * 8)), fk);
+        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(vb + ((size_t)cgi * n + tok) * 8)), fv);
+      } else if (j < kt) {  // memory kv: mem_kv[2][heads][n_mem][dh] (:353,:367-368)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          fk[c] = mem_kv[(((size_t)h) * n_mem + key) * DH + cgi * 8 + c];
+          fv[c] = mem_kv[(((size_t)heads + h) * n_mem + key) * DH + cgi * 8 + c];
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { fk[c] = 0.f; fv[c] = 0.f; }
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { sk[j][cgi * 8 + c] = fk[c]; sv[j][cgi * 8 + c] = fv[c]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int qi = 0; qi < QPW; ++qi) {
+      const int qidx = q0 + warp + qi * 4;
+      if (qidx >= n) continue;  // warp-uniform
+      // stage q (scaled) for this warp
+      for (int dd = lane; dd < DH; dd += 32) {
+        const int cgi = dd >> 3;
+        sq[warp][dd] = __bfloat162float(qb[((size_t)cgi * n + qidx) * 8 + (dd & 7)]) * scale;
+      }
+      __syncwarp();
+      float sc[KT / 32];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int r = 0; r < KT / 32; ++r) {
+        const int j = lane + r * 32;
+        float s = -INFINITY;
+        if (j < kt) {
+          s = 0.f;
+#pragma unroll
+          for (int dd = 0; dd < DH; ++dd) s += sq[warp][dd] * sk[j][dd];
+        }
+        sc[r] = s;
+        mx = fmaxf(mx, s);
+      }
+      mx = warp_max(mx);
+      const float mnew = fmaxf(m_run[qi], mx);
+      const float corr = __expf(m_run[qi] - mnew);
+      float psum = 0.f;
+#pragma unroll
+      for (int r = 0; r < KT / 32; ++r) {
+        const int j = lane + r * 32;
+        const float pj = j < kt ? __expf(sc[r] - mnew) : 0.f;
+        spj[warp][j] = pj;
+        psum += pj;
+      }
+      psum = warp_sum(psum);
+      __syncwarp();
+      l_run[qi] = l_run[qi] * corr + psum;
+      m_run[qi] = mnew;
+#pragma unroll
+      for (int jj = 0; jj < DPL; ++jj) {
+        const int dd = lane + jj * 32;
+        float a = 0.f;
+        if (dd < DH)
+          for (int j = 0; j < kt; ++j) a += spj[warp][j] * sv[j][dd];
+        o_run[qi][jj] = o_run[qi][jj] * corr + a;
+      }
+      __syncwarp();
+    }
+  }
+#pragma unroll
+  for (int qi = 0; qi < QPW; ++qi) {
+    const int qidx = q0 + warp + qi * 4;
+    if (qidx >= n) continue;
+#pragma unroll
+    for (int jj = 0; jj < DPL; ++jj) {
+      const int dd = lane + jj * 32;
+      if (dd < DH) {
+        const int ch = h * DH + dd;
+        out[(((size_t)b * out_cgtot + (ch >> 3)) * (size_t)n + qidx) * 8 + (ch & 7)] =
+            __float2bfloat16(o_run[qi][jj] / l_run[qi]);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+int linattn_kmax(const Act& qkv, int heads, int dh, int nsplit, float* kmax, cudaStream_t st) {
+  const int hd = heads * dh;
+  FTB_CHECK(qkv.C == 3 * hd, "linattn: qkv must have 3*heads*dim_head channels");
+  fill_kernel<<<1, 256, 0, st>>>(kmax, -INFINITY, (size_t)qkv.B * hd);
+  dim3 grid(nsplit, hd / 8, qkv.B);
+  kmax_kernel<<<grid, 256, 0, st>>>(qkv.p, qkv.cg(), hd / 8, qkv.voxels(), nsplit, kmax, hd);
+  FTB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int linattn_context_partial(const Act& qkv, int heads, int dh, int nsplit, const float* kmax,
+                            float* part, cudaStream_t st) {
+  dim3 grid(nsplit, heads, qkv.B);
+  if (dh == 32)
+    ctx_partial_kernel<32><<<grid, 256, 0, st>>>(qkv.p, qkv.cg(), heads, qkv.voxels(), nsplit, kmax, part);
+  else if (dh == 16)
+    ctx_partial_kernel<16><<<grid, 256, 0, st>>>(qkv.p, qkv.cg(), heads, qkv.voxels(), nsplit, kmax, part);
+  else
+    FTB_FAIL("linattn: dim_head must be 16 or 32");
+  FTB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int linattn_combine(const float* part, int nsplit, const float* kmax, int B, int heads, int dh,
+                    const float* mem_kv, int n_mem, const float* w_out, int C, float q_scale,
+                    bf16* wpack_out, float* ctx_dbg, cudaStream_t st) {
+  FTB_CHECK(C % 16 == 0 && (heads * dh) % 16 == 0, "linattn: C and heads*dim_head must be multiples of 16");
+  const size_t smem = (size_t)heads * dh * dh * sizeof(float);
+  FTB_CHECK(smem <= 48 * 1024, "linattn: context does not fit shared memory");
+  combine_kernel<<<B, 256, smem, st>>>(part, nsplit, kmax, heads, dh, mem_kv, n_mem, w_out, C, q_scale, wpack_out, ctx_dbg);
+  FTB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int full_attention(const Act& qkv, int heads, int dh, const float* mem_kv, int n_mem, Act& out,
+                   cudaStream_t st) {
+  const int n = (int)qkv.voxels();
+  FTB_CHECK(qkv.C == 3 * heads * dh && out.C == heads * dh, "attention: channel counts");
+  FTB_CHECK(n_mem <= 128, "attention: too many memory kv");
+  dim3 grid(qkv.B * heads, cdiv(n, 64));
+  const float scale = 1.0f / sqrtf((float)dh);
+  if (dh == 32)
+    full_attn_kernel<32><<<grid, 128, 0, st>>>(qkv.p, qkv.cg(), heads, n, mem_kv, n_mem, out.p, out.cg(), scale);
+  else if (dh == 16)
+    full_attn_kernel<16><<<grid, 128, 0, st>>>(qkv.p, qkv.cg(), heads, n, mem_kv, n_mem, out.p, out.cg(), scale);
+  else
+    FTB_FAIL("attention: dim_head must be 16 or 32");
+  FTB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace ftb

@@ -1,0 +1,563 @@
+// 3-D convolution as implicit GEMM on tcgen05 tensor cores (sm_100a).
+//
+// Replaces every nn.Conv3d on the Unet3D path (reference src/flowtrain/models/unet_attn_3d.py:
+// stem :535, Block.proj :227, Upsample.conv :83, stage-last :614/:657, Downsample.conv :103,
+// res_conv :263, to_qkv :303/:354, to_out :306/:355, final_conv :667) and fuses what follows it
+// in the reference into the epilogue: bias, channel RMSNorm (:127-128), FiLM (:241), SiLU (:243),
+// the residual add (:278, :695), the pre-attention RMSNorm (:311, as a per-row scale) and the
+// q softmax of LinearAttention (:326,:329).
+//
+// Data flow per CTA (persistent, 192 threads = TMA warp | MMA warp | 4 epilogue warps):
+//   * activations live in HBM as [B][C/8][D][H][W][8] bf16.  One TMA box = one halo PLANE
+//     (BH x BW voxels x all input channels) and lands in shared memory as [cg][h][w][8], which is
+//     exactly the no-swizzle K-major UMMA operand layout: 8 consecutive voxels along W form a
+//     core matrix, LBO = channel-group pitch, SBO = halo-row pitch.  A filter tap (kd,kh,kw) is
+//     therefore just a start-address shift of the A descriptor: no im2col, every plane is read
+//     from L2 once and reused by all K^3 taps; zero padding comes from TMA out-of-bounds fill.
+//   * an output tile is M = 128 voxels = 16 rows (H) x 8 columns (W) of one depth plane; the CTA
+//     marches along D through a ring of plane slots, so each plane is loaded once per column.
+//   * weights are pre-packed per (tap, k-step) as N x 16 K-major tiles; they stay resident in
+//     shared memory when all taps fit, else they stream through a small ring.
+//   * accumulators sit in TMEM (double-buffered: the epilogue of group g overlaps the MMAs of g+1);
+//     each epilogue thread owns one voxel row, so the channel reduction of RMSNorm is thread-local.
+#include "ops.h"
+
+namespace ftb {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kMaxSlots = 12;
+constexpr int kMaxWSlots = 32;
+
+enum : int { F_SILU = 1, F_QSOFTMAX = 2 };
+
+struct IgemmParams {
+  int B, D, H, W;
+  int K, pad, taps;
+  int cg0, cg1, KS0, KS;
+  int s0_cgtot, s0_cgoff, s1_cgtot, s1_cgoff;
+  int N;
+  int TH, BH, BW;
+  int nHt, nWt, nSeg, LZ, NZ;
+  int n_items;
+  int nslot, wslot, w_resident;
+  uint32_t cg_pitch, row_pitch, src1_off, slot_stride, plane_tx_bytes, wtap_bytes;
+  uint32_t off_w, off_bar;
+  uint32_t tmem_cols;
+  const bf16* wpack;
+  long long w_batch_stride;
+  bf16* out;
+  int out_cgtot, out_cgoff;
+  float* out_f32;
+  int out_f32_c;
+  const float *bias, *gs, *scale, *shift;
+  int film_stride;
+  const bf16* resid;
+  int resid_cgtot, resid_cgoff;
+  const bf16* pre_src;
+  int pre_cgtot, pre_cgoff, pre_cg;
+  int flags, q_dh;
+  float q_scale;
+};
+
+struct ItemCoord {
+  int b, d0, lz, h0, w0;
+};
+
+__device__ __forceinline__ ItemCoord decode_item(const IgemmParams& p, int item) {
+  ItemCoord c;
+  int wt = item % p.nWt;
+  int r = item / p.nWt;
+  int ht = r % p.nHt;
+  r /= p.nHt;
+  int seg = r % p.nSeg;
+  c.b = r / p.nSeg;
+  c.d0 = seg * p.LZ;
+  c.lz = min(p.LZ, p.D - c.d0);
+  c.h0 = ht * p.TH;
+  c.w0 = wt * 8;
+  return c;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
+                  const IgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* s_planes = smem;
+  uint8_t* s_w = smem + p.off_w;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint64_t* plane_full = bars;
+  uint64_t* plane_empty = bars + kMaxSlots;
+  uint64_t* w_full = bars + 2 * kMaxSlots;
+  uint64_t* w_empty = w_full + kMaxWSlots;
+  uint64_t* acc_full = w_empty + kMaxWSlots;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.nslot; ++i) {
+      mbar_init(&plane_full[i], 1);
+      mbar_init(&plane_empty[i], 1);
+    }
+    for (int i = 0; i < p.wslot; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);
+    }
+    fence_barrier_init();
+    prefetch_tmap(&tm0);
+    if (p.cg1 > 0) prefetch_tmap(&tm1);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      uint32_t pctr = 0;  // planes issued so far (ring position)
+      uint32_t wctr = 0;  // weight taps issued so far
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const ItemCoord c = decode_item(p, item);
+        const int npl = c.lz + 2 * p.pad;
+        const int ngroups = (c.lz + p.NZ - 1) / p.NZ;
+        int issued = 0;
+        for (int g = 0; g < ngroups; ++g) {
+          const int nze = min(p.NZ, c.lz - g * p.NZ);
+          const int need = min(npl, g * p.NZ + nze + 2 * p.pad);
+          for (; issued < need; ++issued, ++pctr) {
+            const uint32_t slot = pctr % p.nslot;
+            const uint32_t par = (pctr / p.nslot) & 1;
+            mbar_wait(&plane_empty[slot], par ^ 1);
+            mbar_expect_tx(&plane_full[slot], p.plane_tx_bytes);
+            uint8_t* dst = s_planes + (size_t)slot * p.slot_stride;
+            const int dz = c.d0 - p.pad + issued;
+            tma_load_4d(dst, &tm0, &plane_full[slot], (c.w0 - p.pad) * 8, c.h0 - p.pad, dz,
+                        c.b * p.s0_cgtot + p.s0_cgoff);
+            if (p.cg1 > 0)
+              tma_load_4d(dst + p.src1_off, &tm1, &plane_full[slot], (c.w0 - p.pad) * 8,
+                          c.h0 - p.pad, dz, c.b * p.s1_cgtot + p.s1_cgoff);
+          }
+          if (!p.w_resident || wctr == 0) {
+            const bf16* wsrc = p.wpack + (long long)c.b * p.w_batch_stride;
+            for (int t = 0; t < p.taps; ++t, ++wctr) {
+              const uint32_t slot = wctr % p.wslot;
+              const uint32_t par = (wctr / p.wslot) & 1;
+              mbar_wait(&w_empty[slot], par ^ 1);
+              mbar_expect_tx(&w_full[slot], p.wtap_bytes);
+              bulk_load(s_w + (size_t)slot * p.wtap_bytes,
+                        reinterpret_cast<const uint8_t*>(wsrc) + (size_t)t * p.wtap_bytes,
+                        p.wtap_bytes, &w_full[slot]);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16_f32(128, p.N);
+      const uint32_t planes_addr = smem_u32(s_planes);
+      const uint32_t w_addr = smem_u32(s_w);
+      uint32_t pbase = 0, wctr = 0, gctr = 0;
+      bool w_waited = false;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const ItemCoord c = decode_item(p, item);
+        const int npl = c.lz + 2 * p.pad;
+        const int ngroups = (c.lz + p.NZ - 1) / p.NZ;
+        int ready = 0;
+        for (int g = 0; g < ngroups; ++g, ++gctr) {
+          const int nze = min(p.NZ, c.lz - g * p.NZ);
+          const uint32_t ab = gctr & 1;
+          mbar_wait(&acc_empty[ab], ((gctr >> 1) & 1) ^ 1);
+          const int need = min(npl, g * p.NZ + nze + 2 * p.pad);
+          for (; ready < need; ++ready) {
+            const uint32_t pc = pbase + ready;
+            mbar_wait(&plane_full[pc % p.nslot], (pc / p.nslot) & 1);
+          }
+          tc_fence_after();
+          const bool stream_w = !p.w_resident;
+          int t = 0;
+          for (int kd = 0; kd < p.K; ++kd)
+            for (int kh = 0; kh < p.K; ++kh)
+              for (int kw = 0; kw < p.K; ++kw, ++t) {
+                uint32_t wslot_i;
+                if (stream_w) {
+                  wslot_i = wctr % p.wslot;
+                  mbar_wait(&w_full[wslot_i], (wctr / p.wslot) & 1);
+                  tc_fence_after();
+                } else {
+                  wslot_i = t;
+                  if (!w_waited) {
+                    mbar_wait(&w_full[wslot_i], 0);
+                    tc_fence_after();
+                  }
+                }
+                const uint32_t wb = w_addr + wslot_i * p.wtap_bytes;
+                for (int zi = 0; zi < nze; ++zi) {
+                  const uint32_t pc = pbase + g * p.NZ + zi + kd;
+                  const uint32_t abase = planes_addr + (pc % p.nslot) * p.slot_stride +
+                                         kh * p.row_pitch + kw * 16;
+                  const uint32_t dcol = tmem_base + (ab * p.NZ + zi) * p.N;
+                  for (int ks = 0; ks < p.KS; ++ks) {
+                    const uint32_t aoff = ks < p.KS0 ? ks * 2 * p.cg_pitch
+                                                     : p.src1_off + (ks - p.KS0) * 2 * p.cg_pitch;
+                    const uint64_t da = umma_desc_kmajor_noswz(abase + aoff, p.cg_pitch, p.row_pitch);
+                    const uint64_t db = umma_desc_kmajor_noswz(wb + ks * p.N * 32, 128, 256);
+                    umma_bf16(dcol, da, db, idesc, (t | ks) != 0);
+                  }
+                }
+                if (stream_w) {
+                  umma_commit(&w_empty[wslot_i]);
+                  ++wctr;
+                }
+              }
+          w_waited = true;
+          // planes that leave the window: the NZ oldest, or everything at the end of the item
+          const int rel_lo = g * p.NZ;
+          const int rel_hi = (g == ngroups - 1) ? npl : rel_lo + nze;
+          for (int i = rel_lo; i < rel_hi; ++i) umma_commit(&plane_empty[(pbase + i) % p.nslot]);
+          umma_commit(&acc_full[ab]);
+        }
+        pbase += npl;
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (4 warps)
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int m = q * 32 + lane;
+    const int hl = m >> 3, wl = m & 7;
+    const size_t plane_vox = (size_t)p.H * p.W;
+    uint32_t gctr = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const ItemCoord c = decode_item(p, item);
+      const int ngroups = (c.lz + p.NZ - 1) / p.NZ;
+      const int h = c.h0 + hl, w = c.w0 + wl;
+      const bool valid = (hl < p.TH) && (h < p.H) && (w < p.W);
+      const float* scale = p.scale ? p.scale + (size_t)c.b * p.film_stride : nullptr;
+      const float* shift = p.shift ? p.shift + (size_t)c.b * p.film_stride : nullptr;
+      for (int g = 0; g < ngroups; ++g, ++gctr) {
+        const int nze = min(p.NZ, c.lz - g * p.NZ);
+        const uint32_t ab = gctr & 1;
+        mbar_wait(&acc_full[ab], (gctr >> 1) & 1);
+        tc_fence_after();
+        for (int zi = 0; zi < nze; ++zi) {
+          const int d = c.d0 + g * p.NZ + zi;
+          const size_t vox = (size_t)d * plane_vox + (size_t)h * p.W + w;  // within one (b, cg)
+          const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (ab * p.NZ + zi) * p.N;
+          float rs = 1.f;
+          if (p.pre_src && valid) {
+            float ss = 0.f;
+            const size_t cgs = (size_t)p.D * plane_vox;
+            const bf16* src = p.pre_src + (((size_t)c.b * p.pre_cgtot + p.pre_cgoff) * cgs + vox) * 8;
+            for (int cgi = 0; cgi < p.pre_cg; ++cgi) {
+              float f[8];
+              unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(src + (size_t)cgi * cgs * 8)), f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+            }
+            rs = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+          }
+          __syncwarp();
+          float rinv = 1.f;
+          if (p.gs) {
+            float ss = 0.f;
+            for (int c0 = 0; c0 < p.N; c0 += 16) {
+              uint32_t r[16];
+              tmem_ld16(trow + c0, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float v = __uint_as_float(r[j]) * rs + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
+                ss += v * v;
+              }
+            }
+            rinv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+          }
+          const size_t cgs = (size_t)p.D * plane_vox;
+          if (p.flags & F_QSOFTMAX) {
+            // softmax over each dim_head group of this voxel's q, times dim_head^-0.5 (:326,:329)
+            const int nch = p.q_dh >> 4;
+            for (int hd = 0; hd < p.N / p.q_dh; ++hd) {
+              float v[64];
+              float mx = -INFINITY;
+#pragma unroll
+              for (int ch = 0; ch < 4; ++ch) {
+                if (ch < nch) {
+                  uint32_t r[16];
+                  tmem_ld16(trow + hd * p.q_dh + ch * 16, r);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    v[ch * 16 + j] = __uint_as_float(r[j]) * rs;
+                    mx = fmaxf(mx, v[ch * 16 + j]);
+                  }
+                }
+              }
+              float sum = 0.f;
+#pragma unroll
+              for (int ch = 0; ch < 4; ++ch)
+                if (ch < nch) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    v[ch * 16 + j] = __expf(v[ch * 16 + j] - mx);
+                    sum += v[ch * 16 + j];
+                  }
+                }
+              const float inv = p.q_scale / sum;
+              if (valid) {
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch)
+                  if (ch < nch) {
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                      float f[8];
+#pragma unroll
+                      for (int j = 0; j < 8; ++j) f[j] = v[ch * 16 + half * 8 + j] * inv;
+                      const int cg = p.out_cgoff + ((hd * p.q_dh + ch * 16) >> 3) + half;
+                      bf16* dst = p.out + (((size_t)c.b * p.out_cgtot + cg) * cgs + vox) * 8;
+                      *reinterpret_cast<uint4*>(dst) = pack_bf16x8(f);
+                    }
+                  }
+              }
+              __syncwarp();
+            }
+            continue;
+          }
+          for (int c0 = 0; c0 < p.N; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(trow + c0, r);
+            tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float x = __uint_as_float(r[j]) * rs + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
+              if (p.gs) x = x * rinv * __ldg(p.gs + c0 + j);
+              if (scale) x = x * (__ldg(scale + c0 + j) + 1.f) + __ldg(shift + c0 + j);
+              if (p.flags & F_SILU) x = silu_f(x);
+              v[j] = x;
+            }
+            if (valid) {
+            if (p.resid) {
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                const int cg = p.resid_cgoff + (c0 >> 3) + half;
+                const bf16* rp = p.resid + (((size_t)c.b * p.resid_cgtot + cg) * cgs + vox) * 8;
+                float f[8];
+                unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(rp)), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[half * 8 + j] += f[j];
+              }
+            }
+            if (p.out_f32) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int ch = c0 + j;
+                if (ch < p.out_f32_c)
+                  p.out_f32[((size_t)c.b * p.out_f32_c + ch) * cgs + vox] = v[j];
+              }
+            } else {
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = v[half * 8 + j];
+                const int cg = p.out_cgoff + (c0 >> 3) + half;
+                bf16* dst = p.out + (((size_t)c.b * p.out_cgtot + cg) * cgs + vox) * 8;
+                *reinterpret_cast<uint4*>(dst) = pack_bf16x8(f);
+              }
+            }
+            }  // valid
+            __syncwarp();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[ab]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 4-D view of a blocked activation: (W*8, H, D, B*CG) bf16; box = (BW*8, BH, 1, cg)
+int make_plane_tmap(CUtensorMap* tm, const Act& a, int BW, int BH, int cg) {
+  PFN_encodeTiled enc = get_encode();
+  FTB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[4] = {(cuuint64_t)a.W * 8, (cuuint64_t)a.H, (cuuint64_t)a.D,
+                        (cuuint64_t)a.B * a.cg()};
+  cuuint64_t gstr[3] = {(cuuint64_t)a.W * 16, (cuuint64_t)a.W * a.H * 16,
+                        (cuuint64_t)a.W * a.H * a.D * 16};
+  cuuint32_t box[4] = {(cuuint32_t)BW * 8, (cuuint32_t)BH, 1u, (cuuint32_t)cg};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.p, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FTB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  return 0;
+}
+
+constexpr uint32_t kSmemLimit = 227 * 1024 - 128;  // 227 KB opt-in maximum minus the alignment pad
+
+}  // namespace
+
+int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const ConvEpilogue& e,
+               Act& out, int out_cgoff, cudaStream_t st) {
+  const Act& a0 = *s0.t;
+  FTB_CHECK(s0.cg > 0 && (s0.cg % 2) == 0, "conv: src0 channel groups must be a positive multiple of 2");
+  FTB_CHECK(s1.cg % 2 == 0, "conv: src1 channel groups must be a multiple of 2");
+  FTB_CHECK((s0.cg + s1.cg) * 8 == w.cin, "conv: weight K extent does not match the sources");
+  FTB_CHECK(w.n % 16 == 0 && w.n >= 16 && w.n <= 256, "conv: N tile must be a multiple of 16 in [16,256]");
+  FTB_CHECK(w.ksize == 1 || w.ksize == 3 || w.ksize == 5 || w.ksize == 7, "conv: ksize");
+  FTB_CHECK(out.B == a0.B && out.D == a0.D && out.H == a0.H && out.W == a0.W, "conv: out dims");
+  if (s1.t) FTB_CHECK(s1.t->B == a0.B && s1.t->D == a0.D && s1.t->H == a0.H && s1.t->W == a0.W, "conv: src1 dims");
+  FTB_CHECK(!e.q_softmax_heads || (e.q_dim_head % 16 == 0 && e.q_dim_head <= 64 && w.n % e.q_dim_head == 0),
+            "conv: q softmax needs dim_head in {16,32,48,64} dividing N");
+
+  IgemmParams p{};
+  p.B = a0.B; p.D = a0.D; p.H = a0.H; p.W = a0.W;
+  p.K = w.ksize; p.pad = (w.ksize - 1) / 2; p.taps = w.ksize * w.ksize * w.ksize;
+  p.cg0 = s0.cg; p.cg1 = s1.t ? s1.cg : 0;
+  p.KS0 = p.cg0 / 2; p.KS = (p.cg0 + p.cg1) / 2;
+  p.s0_cgtot = a0.cg(); p.s0_cgoff = s0.cgoff;
+  p.s1_cgtot = s1.t ? s1.t->cg() : 0; p.s1_cgoff = s1.cgoff;
+  p.N = w.n;
+  p.TH = a0.H >= 16 ? 16 : a0.H;
+  p.BH = p.TH + 2 * p.pad;
+  p.BW = 8 + 2 * p.pad;
+  p.nHt = cdiv(a0.H, p.TH);
+  p.nWt = cdiv(a0.W, 8);
+  p.row_pitch = p.BW * 16;
+  p.cg_pitch = p.BH * p.row_pitch;
+  p.src1_off = (uint32_t)round_up(p.cg0 * (int)p.cg_pitch, 128);
+  const uint32_t plane_bytes = p.src1_off + p.cg1 * p.cg_pitch;
+  p.plane_tx_bytes = (p.cg0 + p.cg1) * p.cg_pitch;
+  p.slot_stride = (uint32_t)round_up((int)plane_bytes, 128);
+  p.wtap_bytes = (uint32_t)p.KS * p.N * 32;
+
+  // ---- tiling along D and ring sizing against the 227 KB shared-memory budget
+  const int sms = num_sms();
+  const int cols = a0.B * p.nHt * p.nWt;
+  const uint32_t slack = (uint32_t)(16 - p.TH + 2) * p.row_pitch + 512;  // A rows of a partial tile over-read
+  const uint32_t bar_bytes = (2 * kMaxSlots + 2 * kMaxWSlots + 4) * 8 + 16;
+  const uint32_t fixed = slack + bar_bytes + 256;
+  const size_t all_w = (size_t)p.taps * p.wtap_bytes;
+  const int win1 = 1 + 2 * p.pad;
+  p.w_resident = 0;
+  p.NZ = 1;
+  if (w.batch_stride == 0 && p.taps <= kMaxWSlots &&
+      all_w + (size_t)(win1 + 1) * p.slot_stride + fixed <= kSmemLimit) {
+    p.w_resident = 1;
+    p.wslot = p.taps;
+  } else {
+    p.wslot = p.taps == 1 ? 1 : (p.wtap_bytes <= 8192 ? 6 : (p.wtap_bytes <= 16384 ? 4 : 2));
+    // amortise the streamed weights over NZ output planes (one accumulator each)
+    int nz = 1;
+    while (nz < 4 && nz * 2 <= a0.D && 2 * (nz * 2) * p.N <= 512 &&
+           (size_t)p.wslot * p.wtap_bytes + (size_t)(nz * 2 + 2 * p.pad + 1) * p.slot_stride + fixed <= kSmemLimit)
+      nz *= 2;
+    if (p.taps > 1) p.NZ = nz;
+  }
+  const size_t w_region = (size_t)p.wslot * p.wtap_bytes;
+  const int win = p.NZ + 2 * p.pad;
+  FTB_CHECK(w_region + (size_t)win * p.slot_stride + fixed <= kSmemLimit,
+            "conv: one plane window + weights exceed shared memory (Cin too large for this tile)");
+  int nslot = (int)((kSmemLimit - fixed - w_region) / p.slot_stride);
+  nslot = nslot > kMaxSlots ? kMaxSlots : nslot;
+  p.nslot = nslot;
+  // segment length along D: minimise (rounds of items over the SMs) x (planes per item, halo
+  // planes counted at half weight: they cost loads but no MMAs)
+  int lz = a0.D;
+  {
+    double best = 1e30;
+    for (int cand = a0.D; cand >= p.NZ; cand = cdiv(cand, 2)) {
+      const int cl = round_up(cand, p.NZ) > a0.D ? a0.D : round_up(cand, p.NZ);
+      const double cost = (double)cdiv(cols * cdiv(a0.D, cl), sms) * (cl + p.pad);
+      if (cost < best - 1e-9) { best = cost; lz = cl; }
+      if (cand == 1) break;
+    }
+  }
+  p.LZ = lz;
+  p.nSeg = cdiv(a0.D, lz);
+  p.n_items = cols * p.nSeg;
+  p.off_w = (uint32_t)round_up((int)(p.nslot * p.slot_stride + slack), 128);
+  p.off_bar = (uint32_t)round_up((int)(p.off_w + w_region), 16);
+  const uint32_t smem_bytes = p.off_bar + bar_bytes + 128;
+  FTB_CHECK(smem_bytes <= kSmemLimit + 128, "conv: smem budget");
+  uint32_t cols_needed = 2u * p.NZ * p.N;
+  uint32_t tc = 32;
+  while (tc < cols_needed) tc <<= 1;
+  FTB_CHECK(tc <= 512, "conv: accumulators exceed TMEM");
+  p.tmem_cols = tc;
+
+  p.wpack = w.w;
+  p.w_batch_stride = w.batch_stride;
+  p.out = out.p; p.out_cgtot = out.cg();
+  p.out_f32 = e.out_f32; p.out_f32_c = e.out_f32_c;
+  p.gs = e.gs; p.scale = e.scale; p.shift = e.shift; p.film_stride = e.film_stride;
+  p.resid = e.resid ? e.resid->p : nullptr;
+  p.resid_cgtot = e.resid ? e.resid->cg() : 0; p.resid_cgoff = e.resid_cgoff;
+  if (e.prenorm) { p.pre_src = a0.p; p.pre_cgtot = a0.cg(); p.pre_cgoff = s0.cgoff; p.pre_cg = s0.cg; }
+  p.q_dh = e.q_dim_head; p.q_scale = e.q_scale;
+
+  CUtensorMap tm0, tm1;
+  FTB_TRY(make_plane_tmap(&tm0, a0, p.BW, p.BH, p.cg0));
+  if (s1.t) FTB_TRY(make_plane_tmap(&tm1, *s1.t, p.BW, p.BH, p.cg1)); else tm1 = tm0;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    FTB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(kSmemLimit + 128)));
+    attr_set = true;
+  }
+  const int grid = p.n_items < sms ? p.n_items : sms;
+  for (int nt = 0; nt < w.ntiles; ++nt) {
+    IgemmParams q = p;
+    q.wpack = w.w + (size_t)nt * w.tile_elems();
+    q.bias = e.bias ? e.bias + (size_t)nt * w.n : nullptr;
+    q.out_cgoff = out_cgoff + nt * (w.n / 8);
+    q.flags = (e.silu ? F_SILU : 0) | ((e.q_softmax_heads && nt == 0) ? F_QSOFTMAX : 0);
+    conv_igemm_kernel<<<grid, kThreads, smem_bytes, st>>>(tm0, tm1, q);
+    FTB_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // namespace ftb

@@ -1,0 +1,235 @@
+// Direct (CUDA-core) convolution with the same operands, layouts and fused epilogue as
+// conv_igemm.cu.  It exists to validate the tensor-core kernel on the device and to bisect
+// failures (FTB_CONV_IMPL=naive routes the whole network through it); it is GPU code, not a
+// CPU fallback, and is never the timed path.  Also holds the weight packer.
+#include <cstdlib>
+#include <cstring>
+
+#include "ops.h"
+
+namespace ftb {
+
+namespace {
+
+struct NaiveParams {
+  int B, D, H, W, K, pad;
+  int cg0, cg1, s0_cgtot, s0_cgoff, s1_cgtot, s1_cgoff;
+  int N, KS;
+  const bf16 *src0, *src1, *wpack;
+  long long w_batch_stride;
+  bf16* out;
+  int out_cgtot, out_cgoff;
+  float* out_f32;
+  int out_f32_c;
+  const float *bias, *gs, *scale, *shift;
+  int film_stride;
+  const bf16* resid;
+  int resid_cgtot, resid_cgoff;
+  int prenorm, silu, qsoftmax, q_dh;
+  float q_scale;
+};
+
+// one thread = one output voxel x 16 output channels (chunk c0)
+__device__ void naive_chunk(const NaiveParams& p, int b, int d, int h, int w, int c0, float (&acc)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  const size_t cgs = (size_t)p.D * p.H * p.W;
+  const bf16* wb = p.wpack + (long long)b * p.w_batch_stride;
+  int t = 0;
+  for (int kd = 0; kd < p.K; ++kd)
+    for (int kh = 0; kh < p.K; ++kh)
+      for (int kw = 0; kw < p.K; ++kw, ++t) {
+        const int dz = d + kd - p.pad, hy = h + kh - p.pad, wx = w + kw - p.pad;
+        if (dz < 0 || dz >= p.D || hy < 0 || hy >= p.H || wx < 0 || wx >= p.W) continue;
+        const size_t vox = ((size_t)dz * p.H + hy) * p.W + wx;
+        for (int ks = 0; ks < p.KS; ++ks) {
+          float a[16];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int cgk = ks * 2 + half;
+            const bf16* sp = cgk < p.cg0
+                                 ? p.src0 + (((size_t)b * p.s0_cgtot + p.s0_cgoff + cgk) * cgs + vox) * 8
+                                 : p.src1 + (((size_t)b * p.s1_cgtot + p.s1_cgoff + cgk - p.cg0) * cgs + vox) * 8;
+            float f[8];
+            unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(sp)), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[half * 8 + j] = f[j];
+          }
+          // packed tile [N/8][2][8][8] for (t, ks)
+          const bf16* wt = wb + ((size_t)t * p.KS + ks) * p.N * 16;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = c0 + j;
+            const bf16* wr = wt + (n >> 3) * 128 + (n & 7) * 8;
+            float f0[8], f1[8];
+            unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(wr)), f0);
+            unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(wr + 64)), f1);
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += a[k] * f0[k] + a[8 + k] * f1[k];
+            acc[j] += s;
+          }
+        }
+      }
+}
+
+__global__ void conv_naive_kernel(const NaiveParams p) {
+  const size_t cgs = (size_t)p.D * p.H * p.W;
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (size_t)p.B * cgs) return;
+  const int b = (int)(gid / cgs);
+  const size_t vox = gid % cgs;
+  const int w = (int)(vox % p.W);
+  const int h = (int)((vox / p.W) % p.H);
+  const int d = (int)(vox / ((size_t)p.W * p.H));
+
+  float rs = 1.f;
+  if (p.prenorm) {
+    float ss = 0.f;
+    for (int cgi = 0; cgi < p.cg0; ++cgi) {
+      float f[8];
+      unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(
+                        p.src0 + (((size_t)b * p.s0_cgtot + p.s0_cgoff + cgi) * cgs + vox) * 8)), f);
+      for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+    }
+    rs = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  }
+  float acc[16];
+  float rinv = 1.f;
+  if (p.gs) {
+    float ss = 0.f;
+    for (int c0 = 0; c0 < p.N; c0 += 16) {
+      naive_chunk(p, b, d, h, w, c0, acc);
+      for (int j = 0; j < 16; ++j) {
+        float v = acc[j] * rs + (p.bias ? p.bias[c0 + j] : 0.f);
+        ss += v * v;
+      }
+    }
+    rinv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  }
+  if (p.qsoftmax) {
+    for (int hd = 0; hd < p.N / p.q_dh; ++hd) {
+      float v[64];
+      float mx = -INFINITY;
+      for (int ch = 0; ch < p.q_dh / 16; ++ch) {
+        naive_chunk(p, b, d, h, w, hd * p.q_dh + ch * 16, acc);
+        for (int j = 0; j < 16; ++j) { v[ch * 16 + j] = acc[j] * rs; mx = fmaxf(mx, v[ch * 16 + j]); }
+      }
+      float sum = 0.f;
+      for (int i = 0; i < p.q_dh; ++i) { v[i] = __expf(v[i] - mx); sum += v[i]; }
+      const float inv = p.q_scale / sum;
+      for (int i = 0; i < p.q_dh; ++i) {
+        const int ch = hd * p.q_dh + i;
+        p.out[(((size_t)b * p.out_cgtot + p.out_cgoff + (ch >> 3)) * cgs + vox) * 8 + (ch & 7)] =
+            __float2bfloat16(v[i] * inv);
+      }
+    }
+    return;
+  }
+  const float* scale = p.scale ? p.scale + (size_t)b * p.film_stride : nullptr;
+  const float* shift = p.shift ? p.shift + (size_t)b * p.film_stride : nullptr;
+  for (int c0 = 0; c0 < p.N; c0 += 16) {
+    naive_chunk(p, b, d, h, w, c0, acc);
+    for (int j = 0; j < 16; ++j) {
+      const int ch = c0 + j;
+      float x = acc[j] * rs + (p.bias ? p.bias[ch] : 0.f);
+      if (p.gs) x = x * rinv * p.gs[ch];
+      if (scale) x = x * (scale[ch] + 1.f) + shift[ch];
+      if (p.silu) x = silu_f(x);
+      if (p.resid)
+        x += __bfloat162float(
+            p.resid[(((size_t)b * p.resid_cgtot + p.resid_cgoff + (ch >> 3)) * cgs + vox) * 8 + (ch & 7)]);
+      if (p.out_f32) {
+        if (ch < p.out_f32_c) p.out_f32[((size_t)b * p.out_f32_c + ch) * cgs + vox] = x;
+      } else {
+        p.out[(((size_t)b * p.out_cgtot + p.out_cgoff + (ch >> 3)) * cgs + vox) * 8 + (ch & 7)] =
+            __float2bfloat16(x);
+      }
+    }
+  }
+}
+
+// fp32 [Cout][Cin][k^3] -> bf16 [ntile][tap][ks][n/8][2][8][8]
+__global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int cin_real, int taps,
+                                    int cin_pad, int n, int ntiles, const float* __restrict__ in_scale,
+                                    bf16* __restrict__ dst) {
+  const size_t total = (size_t)ntiles * taps * cin_pad * n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    size_t r = i;
+    const int k8 = r % 8; r /= 8;
+    const int n8 = r % 8; r /= 8;
+    const int kc = r % 2; r /= 2;
+    const int ng = r % (n / 8); r /= (n / 8);
+    const int ks = r % (cin_pad / 16); r /= (cin_pad / 16);
+    const int t = r % taps; r /= taps;
+    const int nt = (int)r;
+    const int co = nt * n + ng * 8 + n8;
+    const int ci = ks * 16 + kc * 8 + k8;
+    float v = 0.f;
+    if (co < cout && ci < cin_real) {
+      v = w[((size_t)co * cin_real + ci) * taps + t];
+      if (in_scale) v *= in_scale[ci];
+    }
+    dst[i] = __float2bfloat16(v);
+  }
+}
+
+}  // namespace
+
+int pack_conv_weights(const float* w, int cout, int cin_real, int ksize, int cin_pad, int ntile_n,
+                      int ntiles, const float* in_scale, bf16* dst, cudaStream_t st) {
+  FTB_CHECK(cin_pad % 16 == 0 && ntile_n % 16 == 0, "pack: padded extents must be multiples of 16");
+  FTB_CHECK(ntile_n * ntiles >= cout && cin_pad >= cin_real, "pack: tile does not cover the weight");
+  const int taps = ksize * ksize * ksize;
+  const size_t total = (size_t)ntiles * taps * cin_pad * ntile_n;
+  const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  pack_weights_kernel<<<blocks, 256, 0, st>>>(w, cout, cin_real, taps, cin_pad, ntile_n, ntiles, in_scale, dst);
+  FTB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int conv_naive(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const ConvEpilogue& e,
+               Act& out, int out_cgoff, cudaStream_t st) {
+  const Act& a0 = *s0.t;
+  FTB_CHECK((s0.cg + s1.cg) * 8 == w.cin, "conv_naive: weight K extent does not match the sources");
+  NaiveParams p{};
+  p.B = a0.B; p.D = a0.D; p.H = a0.H; p.W = a0.W; p.K = w.ksize; p.pad = (w.ksize - 1) / 2;
+  p.cg0 = s0.cg; p.cg1 = s1.t ? s1.cg : 0;
+  p.s0_cgtot = a0.cg(); p.s0_cgoff = s0.cgoff;
+  p.s1_cgtot = s1.t ? s1.t->cg() : 0; p.s1_cgoff = s1.cgoff;
+  p.N = w.n; p.KS = w.cin / 16;
+  p.src0 = a0.p; p.src1 = s1.t ? s1.t->p : nullptr;
+  p.w_batch_stride = w.batch_stride;
+  p.out = out.p; p.out_cgtot = out.cg();
+  p.out_f32 = e.out_f32; p.out_f32_c = e.out_f32_c;
+  p.gs = e.gs; p.scale = e.scale; p.shift = e.shift; p.film_stride = e.film_stride;
+  p.resid = e.resid ? e.resid->p : nullptr;
+  p.resid_cgtot = e.resid ? e.resid->cg() : 0; p.resid_cgoff = e.resid_cgoff;
+  p.prenorm = e.prenorm; p.silu = e.silu; p.q_dh = e.q_dim_head; p.q_scale = e.q_scale;
+  const size_t nthreads = (size_t)a0.B * a0.voxels();
+  const int blocks = (int)((nthreads + 127) / 128);
+  for (int nt = 0; nt < w.ntiles; ++nt) {
+    NaiveParams q = p;
+    q.wpack = w.w + (size_t)nt * w.tile_elems();
+    q.bias = e.bias ? e.bias + (size_t)nt * w.n : nullptr;
+    q.out_cgoff = out_cgoff + nt * (w.n / 8);
+    q.qsoftmax = (e.q_softmax_heads && nt == 0) ? 1 : 0;
+    conv_naive_kernel<<<blocks, 128, 0, st>>>(q);
+    FTB_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+int conv_dispatch(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const ConvEpilogue& e,
+                  Act& out, int out_cgoff, cudaStream_t st) {
+  static int naive = -1;
+  if (naive < 0) {
+    const char* v = getenv("FTB_CONV_IMPL");
+    naive = (v && strcmp(v, "naive") == 0) ? 1 : 0;
+  }
+  return naive ? conv_naive(s0, s1, w, e, out, out_cgoff, st)
+               : conv_igemm(s0, s1, w, e, out, out_cgoff, st);
+}
+
+}  // namespace ftb

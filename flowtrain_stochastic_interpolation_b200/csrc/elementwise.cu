@@ -1,0 +1,431 @@
+// Bandwidth kernels: layout conversion, trilinear resample, interpolant construction,
+// integrator updates, eq-6.7 drift, categorical decode/embed, EMA, loss partials.
+// All are coalesced, 16-byte vectorised where the layout allows, grid-stride over
+// (a multiple of) the SM count.  Reference lines are cited at each kernel.
+#include "ops.h"
+
+namespace ftb {
+
+namespace {
+
+inline int grid_for(size_t work_items, int threads) {
+  size_t blocks = (work_items + threads - 1) / threads;
+  const size_t cap = (size_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ------------------------------------------------------------------ NCDHW fp32 <-> blocked bf16
+__global__ void pack_kernel(const float* __restrict__ x, int B, int C, size_t vox, int CG,
+                            bf16* __restrict__ out) {
+  const size_t total = (size_t)B * CG * vox;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t v = i % vox;
+    const int cg = (int)((i / vox) % CG);
+    const int b = (int)(i / (vox * CG));
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cg * 8 + j;
+      f[j] = c < C ? __ldg(x + ((size_t)b * C + c) * vox + v) : 0.f;
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = pack_bf16x8(f);
+  }
+}
+
+__global__ void unpack_kernel(const bf16* __restrict__ in, int B, int cgtot, int cgoff, int C,
+                              size_t vox, float* __restrict__ out) {
+  const int CG = (C + 7) / 8;
+  const size_t total = (size_t)B * CG * vox;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t v = i % vox;
+    const int cg = (int)((i / vox) % CG);
+    const int b = (int)(i / (vox * CG));
+    float f[8];
+    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(in + (((size_t)b * cgtot + cgoff + cg) * vox + v) * 8)), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = cg * 8 + j;
+      if (c < C) out[((size_t)b * C + c) * vox + v] = f[j];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ trilinear, align_corners=True
+// F.interpolate(..., mode="trilinear", align_corners=True) — unet_attn_3d.py:86,:106.
+// Index rule as ATen: scale = (in-1)/(out-1) (0 if out==1) in fp32, src = scale*dst,
+// i0 = (int)src, i1 = i0 + (i0 < in-1), lambda1 = src - i0, lambda0 = 1 - lambda1.
+struct Lerp {
+  int i0, i1;
+  float l0, l1;
+};
+__device__ __forceinline__ Lerp lerp_idx(int o, int in, int out) {
+  const float scale = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+  const float src = scale * (float)o;
+  Lerp r;
+  r.i0 = (int)src;
+  r.i1 = r.i0 + (r.i0 < in - 1 ? 1 : 0);
+  r.l1 = src - (float)r.i0;
+  r.l0 = 1.f - r.l1;
+  return r;
+}
+
+__global__ void trilinear_kernel(const bf16* __restrict__ in, int B, int CG, int Di, int Hi, int Wi,
+                                 int Do, int Ho, int Wo, bf16* __restrict__ out) {
+  const size_t vo = (size_t)Do * Ho * Wo, vi = (size_t)Di * Hi * Wi;
+  const size_t total = (size_t)B * CG * vo;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % Wo);
+    const int h = (int)((i / Wo) % Ho);
+    const int d = (int)((i / ((size_t)Wo * Ho)) % Do);
+    const size_t bc = i / vo;
+    const Lerp ld = lerp_idx(d, Di, Do), lh = lerp_idx(h, Hi, Ho), lw = lerp_idx(w, Wi, Wo);
+    const bf16* base = in + bc * vi * 8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int dd = a ? ld.i1 : ld.i0;
+      const float wd = a ? ld.l1 : ld.l0;
+      float accd[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) accd[j] = 0.f;
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb) {
+        const int hh = bb ? lh.i1 : lh.i0;
+        const float wh = bb ? lh.l1 : lh.l0;
+        float f0[8], f1[8];
+        const size_t row = ((size_t)dd * Hi + hh) * Wi;
+        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(base + (row + lw.i0) * 8)), f0);
+        unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(base + (row + lw.i1) * 8)), f1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) accd[j] += wh * (lw.l0 * f0[j] + lw.l1 * f1[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += wd * accd[j];
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = pack_bf16x8(acc);
+  }
+}
+
+// ------------------------------------------------------------------ interpolant (interpolation.py:156-216, :379-546)
+struct Coef {
+  float a, b, g, ad, bd, gd;
+};
+__device__ Coef interp_coef(int kind, int one_sided, float ga, float t) {
+  const float pi = 3.14159265358979323846f;
+  Coef c;
+  c.g = 0.f;
+  c.gd = 0.f;
+  const float gam = sqrtf(__fmul_rn(__fmul_rn(ga, t), 1.f - t));
+  const float gamd = __fmul_rn(__fmul_rn(0.5f, ga), 1.f - __fmul_rn(2.f, t)) / gam;
+  switch (kind) {
+    case 0:  // linear
+      c.a = 1.f - t; c.b = t; c.ad = -1.f; c.bd = 1.f;
+      if (!one_sided) { c.g = gam; c.gd = gamd; }
+      break;
+    case 1: {  // trig
+      const float ph = __fmul_rn(pi, t) / 2.f;
+      c.a = cosf(ph); c.b = sinf(ph);
+      c.ad = __fmul_rn(-pi / 2.f, sinf(ph)); c.bd = __fmul_rn(pi / 2.f, cosf(ph));
+      if (!one_sided) { c.g = gam; c.gd = gamd; }
+    } break;
+    case 2: {  // enc-dec
+      const float cs = cosf(__fmul_rn(pi, t));
+      const float c2 = __fmul_rn(cs, cs);
+      const float s2 = __fmul_rn(-pi, sinf(__fmul_rn(__fmul_rn(2.f, pi), t)));
+      c.a = t < 0.5f ? c2 : 0.f; c.b = t > 0.5f ? c2 : 0.f;
+      const float sn = sinf(__fmul_rn(pi, t));
+      c.g = __fmul_rn(sn, sn);
+      c.ad = t < 0.5f ? s2 : 0.f; c.bd = t > 0.5f ? s2 : 0.f;
+      c.gd = -s2;
+    } break;
+    case 3:  // SBDM
+      c.a = sqrtf(1.f - __fmul_rn(t, t)); c.b = t;
+      c.ad = -t / sqrtf(1.f - __fmul_rn(t, t)); c.bd = 1.f;
+      break;
+    default:  // mirror
+      c.a = 0.f; c.b = 1.f; c.ad = 0.f; c.bd = 0.f; c.g = gam; c.gd = gamd;
+      break;
+  }
+  return c;
+}
+
+__global__ void interp_kernel(int kind, int one_sided, float ga, const float4* __restrict__ x0,
+                              const float4* __restrict__ x1, const float4* __restrict__ z,
+                              const float* __restrict__ t, float4* __restrict__ xt,
+                              float4* __restrict__ bt, int B, size_t n4) {
+  const size_t total = (size_t)B * n4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / n4);
+    const Coef c = interp_coef(kind, one_sided, ga, __ldg(t + b));
+    const float4 u = __ldg(x0 + i), v = __ldg(x1 + i);
+    float4 zz = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (z) zz = __ldg(z + i);
+    float4 o, d;
+#define FTB_XT(f)                                                                  \
+  o.f = __fadd_rn(__fmul_rn(c.a, u.f), __fmul_rn(c.b, v.f));                       \
+  d.f = __fadd_rn(__fmul_rn(c.ad, u.f), __fmul_rn(c.bd, v.f));                     \
+  if (z) {                                                                         \
+    o.f = __fadd_rn(o.f, __fmul_rn(c.g, zz.f));                                    \
+    d.f = __fadd_rn(d.f, __fmul_rn(c.gd, zz.f));                                   \
+  }
+    FTB_XT(x) FTB_XT(y) FTB_XT(z) FTB_XT(w)
+#undef FTB_XT
+    xt[i] = o;
+    if (bt) bt[i] = d;
+  }
+}
+
+// ------------------------------------------------------------------ integrator updates (solvers.py:236-240; fixed grid)
+__global__ void axpy_kernel(float* __restrict__ out, const float* __restrict__ x,
+                            const float* __restrict__ k, float h, size_t n,
+                            const unsigned char* __restrict__ frozen, size_t inner) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    float kv = __ldg(k + i);
+    if (frozen && frozen[i % inner]) kv = 0.f;  // dxdt[..., frozen_mask] = 0 (solvers.py:73)
+    out[i] = __fadd_rn(__ldg(x + i), __fmul_rn(h, kv));
+  }
+}
+__global__ void axpy4_kernel(float4* __restrict__ out, const float4* __restrict__ x,
+                             const float4* __restrict__ k, float h, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(x + i), b = __ldg(k + i);
+    float4 o;
+    o.x = __fadd_rn(a.x, __fmul_rn(h, b.x));
+    o.y = __fadd_rn(a.y, __fmul_rn(h, b.y));
+    o.z = __fadd_rn(a.z, __fmul_rn(h, b.z));
+    o.w = __fadd_rn(a.w, __fmul_rn(h, b.w));
+    out[i] = o;
+  }
+}
+__global__ void heun_kernel(float4* __restrict__ out, const float4* __restrict__ x,
+                            const float4* __restrict__ k1, const float4* __restrict__ k2, float hh,
+                            size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(x + i), p = __ldg(k1 + i), q = __ldg(k2 + i);
+    float4 o;
+    o.x = __fadd_rn(a.x, __fmul_rn(hh, __fadd_rn(p.x, q.x)));
+    o.y = __fadd_rn(a.y, __fmul_rn(hh, __fadd_rn(p.y, q.y)));
+    o.z = __fadd_rn(a.z, __fmul_rn(hh, __fadd_rn(p.z, q.z)));
+    o.w = __fadd_rn(a.w, __fmul_rn(hh, __fadd_rn(p.w, q.w)));
+    out[i] = o;
+  }
+}
+__device__ __forceinline__ float rk4_1(float x, float a, float b, float c, float d, float h6) {
+  float t = __fadd_rn(a, __fmul_rn(2.f, b));
+  t = __fadd_rn(t, __fmul_rn(2.f, c));
+  t = __fadd_rn(t, d);
+  return __fadd_rn(x, __fmul_rn(h6, t));
+}
+__global__ void rk4_kernel(float4* __restrict__ out, const float4* __restrict__ x,
+                           const float4* __restrict__ k1, const float4* __restrict__ k2,
+                           const float4* __restrict__ k3, const float4* __restrict__ k4, float h6,
+                           size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = __ldg(x + i), p = __ldg(k1 + i), q = __ldg(k2 + i), r = __ldg(k3 + i),
+                 s = __ldg(k4 + i);
+    float4 o;
+    o.x = rk4_1(a.x, p.x, q.x, r.x, s.x, h6);
+    o.y = rk4_1(a.y, p.y, q.y, r.y, s.y, h6);
+    o.z = rk4_1(a.z, p.z, q.z, r.z, s.z, h6);
+    o.w = rk4_1(a.w, p.w, q.w, r.w, s.w, h6);
+    out[i] = o;
+  }
+}
+// eq. 6.7 drift from a denoiser (solvers.py:130-143) + SDE term (:205-216)
+__global__ void drift_kernel(float* __restrict__ out, const float* __restrict__ x,
+                             const float* __restrict__ eta, const float* __restrict__ noise, float a,
+                             float b, float ad, float bd, float eps, int use_sde, size_t n) {
+  const float bdb = bd / b;
+  const float sq = use_sde ? sqrtf(__fmul_rn(2.f, eps)) : 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float e = __ldg(eta + i), xv = __ldg(x + i);
+    float d = __fadd_rn(__fmul_rn(ad, e), __fmul_rn(bdb, __fsub_rn(xv, __fmul_rn(a, e))));
+    if (use_sde) {
+      const float score = -e / a;
+      const float st = __fadd_rn(__fmul_rn(eps, score), __fmul_rn(__ldg(noise + i), sq));
+      d = __fadd_rn(d, st);
+    }
+    out[i] = d;
+  }
+}
+
+// ------------------------------------------------------------------ decode (model_train_inference.py:373-404)
+// One thread per voxel; fp32 op ORDER fixed (no FMA contraction): sequential sum of squares,
+// sqrt, clamp 1e-12, divide, ncat sequential dot products, first-max argmax -> int64.
+__global__ void decode_kernel(const float* __restrict__ x, const float* __restrict__ en,
+                              long long* __restrict__ out, int B, int E, int ncat, size_t n) {
+  extern __shared__ float s_en[];
+  for (int i = threadIdx.x; i < ncat * E; i += blockDim.x) s_en[i] = en[i];
+  __syncthreads();
+  const size_t total = (size_t)B * n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / n);
+    const size_t v = i % n;
+    const float* xp = x + (size_t)b * E * n + v;
+    float xv[32];
+    float ss = 0.f;
+    for (int e = 0; e < E; ++e) {
+      xv[e] = __ldg(xp + (size_t)e * n);
+      ss = __fadd_rn(ss, __fmul_rn(xv[e], xv[e]));
+    }
+    const float nrm = fmaxf(__fsqrt_rn(ss), 1e-12f);
+    for (int e = 0; e < E; ++e) xv[e] = __fdiv_rn(xv[e], nrm);
+    float best = -INFINITY;
+    int arg = 0;
+    for (int c = 0; c < ncat; ++c) {
+      float acc = 0.f;
+      for (int e = 0; e < E; ++e) acc = __fadd_rn(acc, __fmul_rn(xv[e], s_en[c * E + e]));
+      // strictly-greater keeps the FIRST maximum; a NaN logit wins like torch.argmax
+      if (c == 0 || acc > best || (acc != acc && best == best)) { best = acc; arg = c; }
+    }
+    out[i] = arg;
+  }
+}
+
+__global__ void embed_kernel(const long long* __restrict__ cats, const float* __restrict__ w,
+                             float* __restrict__ out, int B, int E, int ncat, size_t n, int shift) {
+  const size_t total = (size_t)B * E * n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t v = i % n;
+    const int e = (int)((i / n) % E);
+    const int b = (int)(i / (n * E));
+    long long c = cats[(size_t)b * n + v] + shift;  // embed(): indices = x + 1 (:366)
+    c = c < 0 ? 0 : (c >= ncat ? ncat - 1 : c);
+    out[i] = __ldg(w + c * E + e);
+  }
+}
+
+// EMACallback.on_train_batch_end (project/geodata-3d-conditional/callbacks.py:263-266)
+__global__ void ema_kernel(float* __restrict__ shadow, const float* __restrict__ param, size_t n,
+                           float decay, float omd) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    shadow[i] = __fadd_rn(__fmul_rn(decay, shadow[i]), __fmul_rn(omd, __ldg(param + i)));
+}
+
+// training_step loss partials (model_train_inference.py:443): sum (v-vhat)^2 and sum v^2
+__global__ void mse_kernel(const float* __restrict__ v, const float* __restrict__ vh, size_t n,
+                           double* __restrict__ acc2) {
+  double s0 = 0.0, s1 = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const float a = __ldg(v + i), d = a - __ldg(vh + i);
+    s0 += (double)d * d;
+    s1 += (double)a * a;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(acc2, s0);
+    atomicAdd(acc2 + 1, s1);
+  }
+}
+
+}  // namespace
+
+int pack_ncdhw_to_blocked(const float* x, int B, int C, int D, int H, int W, Act& out, cudaStream_t st) {
+  FTB_CHECK(out.B == B && out.D == D && out.H == H && out.W == W && out.C >= C && out.C % 16 == 0,
+            "pack: output activation shape");
+  const size_t vox = (size_t)D * H * W;
+  pack_kernel<<<grid_for((size_t)B * out.cg() * vox, 256), 256, 0, st>>>(x, B, C, vox, out.cg(), out.p);
+  FTB_CUDA(cudaGetLastError());
+  return 0;
+}
+int unpack_blocked_to_ncdhw(const Act& in, int cgoff, int C, float* out, cudaStream_t st) {
+  const size_t vox = in.voxels();
+  unpack_kernel<<<grid_for((size_t)in.B * ((C + 7) / 8) * vox, 256), 256, 0, st>>>(in.p, in.B, in.cg(), cgoff, C, vox, out);
+  FTB_CUDA(cudaGetLastError());
+  return 0;
+}
+int trilinear_resample(const Act& in, Act& out, cudaStream_t st) {
+  FTB_CHECK(in.B == out.B && in.C == out.C, "trilinear: batch/channels must match");
+  trilinear_kernel<<<grid_for((size_t)out.B * out.cg() * out.voxels(), 256), 256, 0, st>>>(
+      in.p, in.B, in.cg(), in.D, in.H, in.W, out.D, out.H, out.W, out.p);
+  FTB_CUDA(cudaGetLastError());
+  return 0;
+}
+int interp_xt_bt(int kind, int one_sided, float gamma_a, const float* x0, const float* x1,
+                 const float* z, const float* t, float* xt, float* bt, int B, long long n,
+                 cudaStream_t st) {
+  FTB_CHECK(kind >= 0 && kind <= 4, "interp: unknown interpolant kind");
+  FTB_CHECK(n % 4 == 0, "interp: per-sample element count must be a multiple of 4");
+  const size_t n4 = (size_t)n / 4;
+  interp_kernel<<<grid_for((size_t)B * n4, 256), 256, 0, st>>>(
+      kind, one_sided, gamma_a, (const float4*)x0, (const float4*)x1, (const float4*)z, t,
+      (float4*)xt, (float4*)bt, B, n4);
+  FTB_CUDA(cudaGetLastError());
+  return 0;
+}
+int axpy_out(float* out, const float* x, const float* k, float h, long long n,
+             const unsigned char* frozen, long long inner, cudaStream_t st) {
+  if (!frozen && n % 4 == 0) {
+    axpy4_kernel<<<grid_for((size_t)n / 4, 256), 256, 0, st>>>((float4*)out, (const float4*)x, (const float4*)k, h, (size_t)n / 4);
+  } else {
+    axpy_kernel<<<grid_for((size_t)n, 256), 256, 0, st>>>(out, x, k, h, (size_t)n, frozen, (size_t)(inner > 0 ? inner : 1));
+  }
+  FTB_CUDA(cudaGetLastError());
+  return 0;
+}
+int heun_combine(float* out, const float* x, const float* k1, const float* k2, double h, long long n, cudaStream_t st) {
+  FTB_CHECK(n % 4 == 0, "heun: n must be a multiple of 4");
+  heun_kernel<<<grid_for((size_t)n / 4, 256), 256, 0, st>>>((float4*)out, (const float4*)x, (const float4*)k1, (const float4*)k2, (float)(h / 2.0), (size_t)n / 4);
+  FTB_CUDA(cudaGetLastError());
+  return 0;
+}
+int rk4_combine(float* out, const float* x, const float* k1, const float* k2, const float* k3,
+                const float* k4, double h, long long n, cudaStream_t st) {
+  FTB_CHECK(n % 4 == 0, "rk4: n must be a multiple of 4");
+  rk4_kernel<<<grid_for((size_t)n / 4, 256), 256, 0, st>>>((float4*)out, (const float4*)x, (const float4*)k1, (const float4*)k2, (const float4*)k3, (const float4*)k4, (float)(h / 6.0), (size_t)n / 4);
+  FTB_CUDA(cudaGetLastError());
+  return 0;
+}
+int denoise_drift(float* out, const float* x, const float* eta, const float* noise, float a, float b,
+                  float ad, float bd, float eps, int use_sde, long long n, cudaStream_t st) {
+  FTB_CHECK(!use_sde || noise != nullptr, "drift: SDE term needs a noise tensor");
+  drift_kernel<<<grid_for((size_t)n, 256), 256, 0, st>>>(out, x, eta, noise, a, b, ad, bd, eps, use_sde, (size_t)n);
+  FTB_CUDA(cudaGetLastError());
+  return 0;
+}
+int decode_argmax(const float* x, const float* en, long long* out, int B, int E, int ncat,
+                  long long n, cudaStream_t st) {
+  FTB_CHECK(E >= 1 && E <= 32, "decode: embedding dim must be in [1,32]");
+  FTB_CHECK(ncat >= 1 && ncat <= 256, "decode: category count");
+  decode_kernel<<<grid_for((size_t)B * n, 128), 128, (size_t)ncat * E * sizeof(float), st>>>(x, en, out, B, E, ncat, (size_t)n);
+  FTB_CUDA(cudaGetLastError());
+  return 0;
+}
+int embed_lookup(const long long* cats, const float* w, float* out, int B, int E, int ncat,
+                 long long n, int shift, cudaStream_t st) {
+  embed_kernel<<<grid_for((size_t)B * E * n, 256), 256, 0, st>>>(cats, w, out, B, E, ncat, (size_t)n, shift);
+  FTB_CUDA(cudaGetLastError());
+  return 0;
+}
+int ema_update(float* shadow, const float* param, long long n, double decay, cudaStream_t st) {
+  ema_kernel<<<grid_for((size_t)n, 256), 256, 0, st>>>(shadow, param, (size_t)n, (float)decay, (float)(1.0 - decay));
+  FTB_CUDA(cudaGetLastError());
+  return 0;
+}
+int mse_ratio_partial(const float* v, const float* vhat, long long n, double* acc2, cudaStream_t st) {
+  mse_kernel<<<grid_for((size_t)n, 256), 256, 0, st>>>(v, vhat, (size_t)n, acc2);
+  FTB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace ftb

@@ -1,0 +1,114 @@
+// Host-side launch API of the flowtrain-b200 kernels (internal; the public C ABI is include/ftb.h).
+#pragma once
+#include "ftb_common.cuh"
+
+namespace ftb {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------- conv (implicit GEMM)
+// Packed weights: [ntile][tap][kstep][N/8][2][8][8] bf16 — per (tap,kstep) an N x 16 B-operand
+// tile in the no-swizzle K-major core-matrix layout (LBO = 128 B, SBO = 256 B).
+struct ConvWeights {
+  const bf16* w = nullptr;
+  int ksize = 1;        // 1, 3, 5, 7 (cubic, stride 1, "same" zero padding)
+  int cin = 0;          // padded K extent (multiple of 16) = channels of src0 (+ src1)
+  int n = 0;            // output channels of one N tile (multiple of 16, <= 256)
+  int ntiles = 1;       // number of N tiles packed back to back
+  long long batch_stride = 0;  // elements between per-sample weight sets (0 = shared)
+  size_t tile_elems() const { return (size_t)ksize * ksize * ksize * cin * n; }
+};
+
+struct ConvEpilogue {
+  const float* bias = nullptr;   // [ntiles*n]
+  const float* gs = nullptr;     // [n]  RMSNorm gain * sqrt(C) (enables the norm)
+  const float* scale = nullptr;  // FiLM scale [B][film_stride] (enables x*(scale+1)+shift)
+  const float* shift = nullptr;
+  int film_stride = 0;
+  bool silu = false;
+  const Act* resid = nullptr;    // residual added last (blocked bf16, same spatial dims)
+  int resid_cgoff = 0;
+  bool prenorm = false;          // row scale 1/max(||src0 voxel||_2, 1e-12) (fused pre-RMSNorm)
+  int q_softmax_heads = 0;       // >0: softmax over each dim_head group of the first N tile
+  int q_dim_head = 0;
+  float q_scale = 1.f;
+  float* out_f32 = nullptr;      // NCDHW fp32 output (final conv) instead of blocked bf16
+  int out_f32_c = 0;
+};
+
+struct ConvSrc {
+  const Act* t = nullptr;
+  int cgoff = 0;   // first channel group used
+  int cg = 0;      // channel groups used (multiple of 2)
+};
+
+// out channels [out_cgoff*8, out_cgoff*8 + ntiles*n) of `out` are written.
+int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const ConvEpilogue& e,
+               Act& out, int out_cgoff, cudaStream_t st);
+// Same contract, plain CUDA-core direct convolution (validation / FTB_CONV_IMPL=naive).
+int conv_naive(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const ConvEpilogue& e,
+               Act& out, int out_cgoff, cudaStream_t st);
+int conv_dispatch(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const ConvEpilogue& e,
+                  Act& out, int out_cgoff, cudaStream_t st);
+
+// fp32 [Cout][Cin][k^3] -> packed bf16 tiles.  cin_map: K index -> source Cin index is
+// identity for k < cin_real, zero beyond.  in_scale (optional, [cin_real]) folds a per-input-
+// channel factor (pre-norm gain * sqrt(C)) into the weights.
+int pack_conv_weights(const float* w, int cout, int cin_real, int ksize, int cin_pad, int ntile_n,
+                      int ntiles, const float* in_scale, bf16* dst, cudaStream_t st);
+
+// ---------------------------------------------------------------- layout / resample
+int pack_ncdhw_to_blocked(const float* x, int B, int C, int D, int H, int W, Act& out, cudaStream_t st);
+int unpack_blocked_to_ncdhw(const Act& in, int cgoff, int C, float* out, cudaStream_t st);
+int trilinear_resample(const Act& in, Act& out, cudaStream_t st);  // align_corners=True
+
+// ---------------------------------------------------------------- time path
+struct TimeMlpParams {
+  const float *freqs, *phases, *w1, *b1, *w2, *b2;  // Fourier + Linear(tr->td) + Linear(td->td)
+  int time_res, time_dim;
+};
+int time_embed(const TimeMlpParams& p, const float* t, int B, float* temb, float* temb_silu,
+               cudaStream_t st);
+// all per-block FiLM MLPs in one launch: out[b][off_j + o] = W_j[o,:] . silu(temb[b]) + b_j[o]
+struct FilmTable {
+  const float* const* w;  // device array of weight pointers [nblk] (each [rows_j][time_dim])
+  const float* const* b;  // device array of bias pointers
+  const int* row_off;     // device prefix offsets [nblk+1]
+  int nblk, total_rows, time_dim;
+};
+int film_mlps(const FilmTable& ft, const float* temb_silu, int B, float* out, cudaStream_t st);
+
+// ---------------------------------------------------------------- attention
+// qkv: blocked tensor with 3*heads*dh channels (q | k | v).  Linear attention, phase A:
+// per-(b,head,split) online-softmax partials of k over voxels and ctx = softmax(k) v^T.
+int linattn_kmax(const Act& qkv, int heads, int dh, int nsplit, float* kmax, cudaStream_t st);
+int linattn_context_partial(const Act& qkv, int heads, int dh, int nsplit, const float* kmax,
+                            float* part, cudaStream_t st);
+// phase A2: merge partials + memory kv, fold W_out -> per-sample packed 1x1 weights M_b[C][heads*dh]
+int linattn_combine(const float* part, int nsplit, const float* kmax, int B, int heads, int dh,
+                    const float* mem_kv, int n_mem, const float* w_out, int C, float q_scale,
+                    bf16* wpack_out, float* ctx_dbg, cudaStream_t st);
+// softmax attention over n tokens (+ n_mem memory kv), one CTA per (b, head, query tile)
+int full_attention(const Act& qkv, int heads, int dh, const float* mem_kv, int n_mem, Act& out,
+                   cudaStream_t st);
+
+// ---------------------------------------------------------------- sampler / task kernels (fp32, NCDHW flat)
+int interp_xt_bt(int kind, int one_sided, float gamma_a, const float* x0, const float* x1,
+                 const float* z, const float* t, float* xt, float* bt, int B, long long n,
+                 cudaStream_t st);
+int axpy_out(float* out, const float* x, const float* k, float h, long long n, const unsigned char* frozen,
+             long long inner, cudaStream_t st);  // out = x + h*k   (Euler / RK stage input)
+int heun_combine(float* out, const float* x, const float* k1, const float* k2, double h, long long n,
+                 cudaStream_t st);
+int rk4_combine(float* out, const float* x, const float* k1, const float* k2, const float* k3,
+                const float* k4, double h, long long n, cudaStream_t st);
+int denoise_drift(float* out, const float* x, const float* eta, const float* noise, float a, float b,
+                  float ad, float bd, float eps, int use_sde, long long n, cudaStream_t st);
+int decode_argmax(const float* x, const float* en, long long* out, int B, int E, int ncat,
+                  long long n, cudaStream_t st);
+int embed_lookup(const long long* cats, const float* w, float* out, int B, int E, int ncat,
+                 long long n, int shift, cudaStream_t st);
+int ema_update(float* shadow, const float* param, long long n, double decay, cudaStream_t st);
+int mse_ratio_partial(const float* v, const float* vhat, long long n, double* acc2, cudaStream_t st);
+
+}  // namespace ftb

@@ -1,0 +1,244 @@
+"""``Unet3D`` — drop-in for flowtrain.models.Unet3D (src/flowtrain/models/unet_attn_3d.py:469-719)
+whose forward runs entirely in the sm_100a kernels behind the C ABI (include/ftb.h).
+
+Same constructor kwargs (:509-525), same ``forward(x, time, x_self_cond=None)`` (:673) and the
+same ``state_dict()`` keys, shapes and order, so a reference state dict / Lightning ``.ckpt``
+``net.*`` entries load unchanged.  The parameter tree is generated from the plan the C library
+reports (one source of truth), not from a copy of the reference module code.
+
+There is no PyTorch implementation of the math in here: on a machine without the library or
+without a GPU, ``forward`` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+from torch import nn
+
+from . import _lib
+
+
+class _Node(nn.Module):
+    """Container node of the parameter tree (mirrors the reference's module nesting)."""
+
+
+def _cfg_struct(dim, dim_mults, data_channels, time_resolution, attn_heads, attn_dim_head, full_attn):
+    n = len(dim_mults)
+    if n > _lib.FTB_MAX_STAGES:
+        raise ValueError(f"at most {_lib.FTB_MAX_STAGES} stages")
+    cfg = _lib.FtbUnetCfg()
+    cfg.dim = dim
+    cfg.n_stages = n
+    for i, m in enumerate(dim_mults):
+        cfg.dim_mults[i] = int(m)
+    cfg.data_channels = data_channels
+    cfg.time_resolution = time_resolution
+    cfg.attn_heads = attn_heads
+    cfg.attn_dim_head = attn_dim_head
+    for i, f in enumerate(full_attn):
+        cfg.full_attn[i] = 1 if f else 0
+    cfg.num_mem_kv = 4
+    return cfg
+
+
+class Unet3D(nn.Module):
+    def __init__(
+        self,
+        dim,
+        dim_mults=(1, 2, 4, 8),
+        data_channels=3,
+        dropout=0.0,
+        self_condition=False,
+        time_resolution=64,
+        time_sin_pos=False,
+        time_bandwidth=100.0,
+        time_learned_emb=False,
+        attn_enabled=True,
+        attn_dim_head=64,
+        attn_heads=4,
+        full_attn=None,
+        flash_attn=False,
+    ):
+        super().__init__()
+        if self_condition:
+            raise NotImplementedError("self_condition=True is not on the B200 hot path (no shipped config uses it)")
+        if time_sin_pos:
+            raise NotImplementedError("time_sin_pos=True: only the Fourier time embeddings are implemented")
+        if not attn_enabled:
+            raise NotImplementedError("attn_enabled=False is not implemented")
+        dim_mults = tuple(dim_mults)
+        if not full_attn:  # unet_attn_3d.py:559-560
+            full_attn = (False,) * (len(dim_mults) - 1) + (True,)
+        elif not isinstance(full_attn, tuple):
+            full_attn = (full_attn,) * len(dim_mults)
+        if isinstance(attn_heads, tuple) or isinstance(attn_dim_head, tuple):
+            if len(set(attn_heads if isinstance(attn_heads, tuple) else (attn_heads,))) != 1 or \
+               len(set(attn_dim_head if isinstance(attn_dim_head, tuple) else (attn_dim_head,))) != 1:
+                raise NotImplementedError("per-stage attention head counts are not implemented")
+            attn_heads = attn_heads[0] if isinstance(attn_heads, tuple) else attn_heads
+            attn_dim_head = attn_dim_head[0] if isinstance(attn_dim_head, tuple) else attn_dim_head
+        assert len(full_attn) == len(dim_mults)
+        self.channels = data_channels
+        self.out_dim = data_channels
+        self.self_condition = False
+        self.attn_enabled = True
+        self.dropout_p = float(dropout)  # eval/sampling path: dropout is the identity
+        self.time_learned_emb = bool(time_learned_emb)
+        self._time_bandwidth = float(time_bandwidth)
+        self._n_stages = len(dim_mults)
+        self.config = dict(
+            dim=dim, dim_mults=dim_mults, data_channels=data_channels, dropout=dropout,
+            self_condition=False, time_resolution=time_resolution, time_sin_pos=False,
+            time_bandwidth=time_bandwidth, time_learned_emb=time_learned_emb, attn_enabled=True,
+            attn_dim_head=attn_dim_head, attn_heads=attn_heads, full_attn=tuple(full_attn),
+            flash_attn=flash_attn,
+        )
+        self._cfg = _cfg_struct(dim, dim_mults, data_channels, time_resolution, attn_heads,
+                                attn_dim_head, full_attn)
+        self._handle = C.c_void_p()
+        _lib.check(_lib.lib.ftb_unet3d_create(C.byref(self._cfg), C.byref(self._handle)))
+        self._names = []
+        self._build_tree()
+        self._synced = {}      # name -> (data_ptr, version) last pushed to the engine
+        self._workspace = {}   # (device, B, X, Y, Z) -> uint8 tensor
+        self.last_launches = 0
+
+    # ------------------------------------------------------------------ parameter tree
+    def _plan(self):
+        h = self._handle
+        n = _lib.lib.ftb_unet3d_num_params(h)
+        dims = (C.c_int * 8)()
+        for i in range(n):
+            name = _lib.lib.ftb_unet3d_param_name(h, i).decode()
+            nd = _lib.lib.ftb_unet3d_param_shape(h, i, dims, 8)
+            yield name, tuple(dims[k] for k in range(nd))
+
+    def _build_tree(self):
+        for name, shape in self._plan():
+            parts = name.split(".")
+            node = self
+            for p in parts[:-1]:
+                if p not in node._modules:
+                    node.add_module(p, _Node())
+                node = node._modules[p]
+            t = torch.empty(shape, dtype=torch.float32)
+            leaf = parts[-1]
+            frozen = leaf in ("freqs", "phases") and not self.time_learned_emb  # :198-201 vs :217-218
+            node.register_parameter(leaf, nn.Parameter(t, requires_grad=not frozen))
+            self._names.append(name)
+        self.reset_parameters()
+
+    @torch.no_grad()
+    def reset_parameters(self):
+        """torch-default initial statistics of the reference ctor (kaiming-uniform(a=sqrt 5) conv /
+        linear weights, bias ~ U(+-1/sqrt(fan_in)), g = 1, mem_kv ~ N(0,1), freqs ~ N(0,1)*bandwidth,
+        phases ~ U(0,1))."""
+        sd = dict(self.named_parameters())
+        for name, p in sd.items():
+            leaf = name.rsplit(".", 1)[-1]
+            if leaf == "g":
+                p.fill_(1.0)
+            elif leaf == "mem_kv":
+                p.normal_()
+            elif leaf == "freqs":
+                p.normal_().mul_(self._time_bandwidth)
+            elif leaf == "phases":
+                p.uniform_(0, 1)
+            elif leaf == "weight":
+                fan_in = p[0].numel()
+                bound = 1.0 / math.sqrt(fan_in)
+                p.uniform_(-bound, bound)
+            elif leaf == "bias":
+                w = sd[name[: -len("bias")] + "weight"]
+                bound = 1.0 / math.sqrt(w[0].numel())
+                p.uniform_(-bound, bound)
+
+    @property
+    def downsample_factor(self):
+        return 2 ** (self._n_stages - 1)
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _sync_params(self, device):
+        st = _lib.stream_ptr()
+        for name, p in self.named_parameters():
+            if p.device != device:
+                raise RuntimeError(f"parameter {name} is on {p.device}, input on {device}: call .to(device)")
+            key = (p.data_ptr(), p._version)
+            if self._synced.get(name) == key:
+                continue
+            d = p.detach()
+            if d.dtype != torch.float32 or not d.is_contiguous():
+                d = d.float().contiguous()
+            _lib.check(_lib.lib.ftb_unet3d_set_param(self._handle, name.encode(), _lib.ptr(d),
+                                                     d.numel(), st))
+            self._synced[name] = key
+
+    def _get_workspace(self, device, B, X, Y, Z):
+        key = (str(device), B, X, Y, Z)
+        ws = self._workspace.get(key)
+        if ws is None:
+            nbytes = _lib.lib.ftb_unet3d_workspace_bytes(self._handle, B, X, Y, Z)
+            if nbytes == 0:
+                raise _lib.FtbError(_lib.last_error())
+            self._workspace.clear()  # one resident workspace; shapes rarely alternate
+            ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+            self._workspace[key] = ws
+        return ws
+
+    def forward(self, x, time, x_self_cond=None):
+        if x_self_cond is not None:
+            raise NotImplementedError("self conditioning is not implemented")
+        if not x.is_cuda:
+            raise RuntimeError("flowtrain_stochastic_interpolation_b200.Unet3D runs on CUDA (sm_100a) only; "
+                               "there is no CPU fallback")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            if x.requires_grad or self.training:
+                raise NotImplementedError(
+                    "backward through the B200 Unet3D is not implemented yet (sampling / no_grad only); "
+                    "wrap the call in torch.no_grad()")
+        if x.dim() != 5 or x.shape[1] != self.channels:
+            raise ValueError(f"expected x of shape [B,{self.channels},X,Y,Z], got {tuple(x.shape)}")
+        B, _, X, Y, Z = x.shape
+        f = self.downsample_factor
+        # the reference asserts only the last two dims (unet_attn_3d.py:674-676); all three matter
+        if any(d % f for d in (X, Y, Z)):
+            raise AssertionError(f"your input dimensions {(X, Y, Z)} need to be divisible by {f}, given the unet")
+        if time.dim() != 1 or time.shape[0] != B:
+            raise ValueError(f"expected time of shape [{B}], got {tuple(time.shape)}")
+        with torch.cuda.device(x.device):
+            xin = x.detach()
+            if xin.dtype != torch.float32 or not xin.is_contiguous():
+                xin = xin.float().contiguous()
+            tin = time.detach().to(device=x.device, dtype=torch.float32).contiguous()
+            self._sync_params(x.device)
+            ws = self._get_workspace(x.device, B, X, Y, Z)
+            base = (ws.data_ptr() + 255) // 256 * 256
+            out = torch.empty_like(xin)
+            _lib.check(_lib.lib.ftb_unet3d_forward(
+                self._handle, _lib.ptr(xin), _lib.ptr(tin), _lib.ptr(out), B, X, Y, Z,
+                C.c_void_p(base), ws.numel() - (base - ws.data_ptr()), _lib.stream_ptr()))
+            self.last_launches = _lib.lib.ftb_unet3d_last_launches(self._handle)
+        return out if x.dtype == torch.float32 else out.to(x.dtype)
+
+    # ------------------------------------------------------------------ debugging taps
+    def get_tap(self, name: str) -> torch.Tensor:
+        """NCDHW fp32 copy of a named intermediate of the LAST forward (names as oracle/unet3d.py)."""
+        c, x, y, z = (C.c_int() for _ in range(4))
+        _lib.check(_lib.lib.ftb_unet3d_tap_channels(self._handle, name.encode(), C.byref(c), C.byref(x),
+                                                    C.byref(y), C.byref(z)))
+        ws = next(iter(self._workspace.values()))
+        B = next(iter(self._workspace.keys()))[1]
+        out = torch.empty((B, c.value, x.value, y.value, z.value), dtype=torch.float32, device=ws.device)
+        with torch.cuda.device(ws.device):
+            _lib.check(_lib.lib.ftb_unet3d_get_tap(self._handle, name.encode(), _lib.ptr(out), _lib.stream_ptr()))
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None and self._handle.value:
+                _lib.lib.ftb_unet3d_destroy(self._handle)
+                self._handle = C.c_void_p()
+        except Exception:
+            pass

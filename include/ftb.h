@@ -1,0 +1,120 @@
+/* flowtrain-b200 C ABI — the drop-in boundary of the B200-native hot path.
+ *
+ * The reference (chipnbits/flowtrain_stochastic_interpolation) is pure Python and has no FFI;
+ * its seam is the Python calling convention `model(XT, T)` (src/flowtrain/solvers/solvers.py:70,
+ * :136, :198, :235-238) / `self.net(XT, T)` (project/geodata-3d-unconditional/
+ * model_train_inference.py:440).  Each entry point below replaces the reference code cited at
+ * it; the Python host (flowtrain_stochastic_interpolation_b200/) binds them with ctypes.
+ *
+ * Conventions: every pointer is a DEVICE pointer unless stated; tensors are contiguous,
+ * fp32, in the reference's NCDHW order ([B,C,X,Y,Z], Z fastest); `stream` is a cudaStream_t
+ * passed as void*; calls enqueue work and return without synchronising.  Return value 0 = ok,
+ * negative = error (ftb_last_error() gives a thread-local message).  Nothing throws across the
+ * ABI.  Ownership: the caller owns every tensor and the workspace; a handle owns only its
+ * packed weights.  A handle is bound to the device current at creation; calls on one handle must
+ * be serialised by the caller (one host thread per rank), distinct handles are independent.
+ * There is no CPU fallback: without a CUDA device every compute entry returns an error.
+ */
+#ifndef FTB_H_
+#define FTB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FTB_MAX_STAGES 8
+
+/* Constructor arguments of Unet3D (src/flowtrain/models/unet_attn_3d.py:509-525). */
+typedef struct ftb_unet_cfg {
+  int dim;                          /* base channels (multiple of 16) */
+  int n_stages;                     /* len(dim_mults) */
+  int dim_mults[FTB_MAX_STAGES];
+  int data_channels;                /* embedding dim E (18 unconditional) */
+  int time_resolution;              /* Fourier features */
+  int attn_heads;
+  int attn_dim_head;                /* 16 or 32 */
+  int full_attn[FTB_MAX_STAGES];    /* per stage: 1 = softmax Attention, 0 = LinearAttention */
+  int num_mem_kv;                   /* 4 in the reference (:290, :345) */
+} ftb_unet_cfg;
+
+typedef struct ftb_unet ftb_unet;
+
+const char* ftb_last_error(void);
+int ftb_version(void);
+int ftb_device_sm_count(void);
+
+/* ---- Unet3D velocity field v_theta(x, t): replaces Unet3D.forward (unet_attn_3d.py:673-719) */
+/* create() only builds the plan (works without a GPU, so names/shapes can be queried);
+ * device storage is allocated on the first set_param()/forward() on the current device. */
+int ftb_unet3d_create(const ftb_unet_cfg* cfg, ftb_unet** out);
+int ftb_unet3d_destroy(ftb_unet* h);
+int ftb_unet3d_num_params(const ftb_unet* h);
+const char* ftb_unet3d_param_name(const ftb_unet* h, int i);   /* state_dict() key order */
+int64_t ftb_unet3d_param_numel(const ftb_unet* h, int i);
+/* writes the shape into dims[0..ndim) and returns ndim (or -1) */
+int ftb_unet3d_param_shape(const ftb_unet* h, int i, int* dims, int max_dims);
+/* copy one fp32 parameter (device pointer) into the handle; repacked lazily before forward */
+int ftb_unet3d_set_param(ftb_unet* h, const char* name, const float* data, int64_t numel, void* stream);
+size_t ftb_unet3d_workspace_bytes(ftb_unet* h, int B, int X, int Y, int Z);
+/* x [B,C,X,Y,Z] fp32, t [B] fp32 -> out [B,C,X,Y,Z] fp32.  bf16 tensor-core path. */
+int ftb_unet3d_forward(ftb_unet* h, const float* x, const float* t, float* out, int B, int X, int Y,
+                       int Z, void* workspace, size_t workspace_bytes, void* stream);
+/* after a forward: copy a named intermediate (same names as oracle/unet3d.py taps) as NCDHW fp32 */
+int ftb_unet3d_tap_channels(ftb_unet* h, const char* name, int* C, int* X, int* Y, int* Z);
+int ftb_unet3d_get_tap(ftb_unet* h, const char* name, float* out, void* stream);
+/* number of kernels the last forward launched (for bench.py "gpu_launches") */
+int ftb_unet3d_last_launches(const ftb_unet* h);
+
+/* ---- interpolant: replaces StochasticInterpolator.get_XT / get_BT / flow_objective
+ *      (src/flowtrain/interpolation/interpolation.py:78-117, :156-216).
+ *      kind: 0 linear, 1 trig, 2 enc-dec, 3 SBDM, 4 mirror (:379-546).  z and bt may be NULL. */
+int ftb_interp_xt_bt(int kind, int one_sided, float gamma_a, const float* x0, const float* x1,
+                     const float* z, const float* t, float* xt, float* bt, int B, int64_t n_per_sample,
+                     void* stream);
+
+/* ---- fixed-grid integrator updates around model(x,t) (solvers.py:66-77, odeSol_RK4 :235-240) */
+/* h is a double on the host; the kernels use float(h), float(h/2), float(h/6) like torch
+ * does for `tensor * python_float`.  out = x + h*k ; frozen (optional, bytes, length `inner`) zeroes k where frozen[i % inner] (:73) */
+int ftb_ode_axpy(float* out, const float* x, const float* k, double h, int64_t n,
+                 const unsigned char* frozen, int64_t inner, void* stream);
+int ftb_ode_heun_combine(float* out, const float* x, const float* k1, const float* k2, double h,
+                         int64_t n, void* stream);
+int ftb_ode_rk4_combine(float* out, const float* x, const float* k1, const float* k2, const float* k3,
+                        const float* k4, double h, int64_t n, void* stream);
+/* eq. 6.7 drift from a denoiser eta (solvers.py:130-143); SDE term (:205-216) when use_sde */
+int ftb_denoise_drift(float* out, const float* x, const float* eta, const float* noise, float alpha,
+                      float beta, float alpha_dot, float beta_dot, float eps, int use_sde, int64_t n,
+                      void* stream);
+
+/* ---- categorical embedding (model_train_inference.py:361-370, :373-404) */
+/* x [B,E,n] fp32, en [ncat,E] = F.normalize(embedding.weight) -> out [B,n] int64, bit-exact order */
+int ftb_decode(const float* x, const float* en, int64_t* out, int B, int E, int ncat, int64_t n,
+               void* stream);
+/* cats [B,n] int64 (+shift, :366) , w [ncat,E] -> out [B,E,n] */
+int ftb_embed(const int64_t* cats, const float* w, float* out, int B, int E, int ncat, int64_t n,
+              int shift, void* stream);
+
+/* ---- training-step pieces (model_train_inference.py:443; callbacks.py:263-266) */
+int ftb_ema_update(float* shadow, const float* param, int64_t n, double decay, void* stream);
+/* acc2[0] += sum (v-vhat)^2, acc2[1] += sum v^2 (device doubles; loss = acc2[0]/acc2[1]) */
+int ftb_mse_ratio_accumulate(const float* v, const float* vhat, int64_t n, double* acc2, void* stream);
+
+/* ---- single-op test hooks (allocate scratch internally; not for hot paths) */
+/* conv3d "same", stride 1, on NCDHW fp32 tensors through the blocked bf16 kernels.
+ * impl: 0 = tcgen05 implicit GEMM, 1 = direct CUDA-core kernel.  x2/resid/bias/g/scale/shift may
+ * be NULL.  flags: bit0 SiLU, bit1 pre-norm row scale.  Epilogue: bias -> RMSNorm(g) -> FiLM -> SiLU
+ * -> +resid. */
+int ftb_test_conv3d(const float* x, int c1, const float* x2, int c2, const float* w, const float* bias,
+                    int cout, int ksize, const float* g, const float* scale, const float* shift,
+                    const float* resid, int flags, float* out, int B, int X, int Y, int Z, int impl,
+                    void* stream);
+int ftb_test_trilinear(const float* x, int B, int C, int X, int Y, int Z, int Xo, int Yo, int Zo,
+                       float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FTB_H_ */
