@@ -49,6 +49,9 @@ _SIGS = {
     "ftb_last_error": (C.c_char_p, []),
     "ftb_version": (_i, []),
     "ftb_device_sm_count": (_i, []),
+    "ftb_launch_count": (_i64, []),
+    "ftb_profile_enable": (_i, [_i]),
+    "ftb_profile_collect": (_i, [C.POINTER(_d), C.POINTER(_d), C.POINTER(_d), _ip, _i]),
     "ftb_unet3d_create": (_i, [C.POINTER(FtbUnetCfg), C.POINTER(_vp)]),
     "ftb_unet3d_destroy": (_i, [_vp]),
     "ftb_unet3d_num_params": (_i, [_vp]),

@@ -295,7 +295,7 @@ int linattn_kmax(const Act& qkv, int heads, int dh, int nsplit, float* kmax, cud
   fill_kernel<<<1, 256, 0, st>>>(kmax, -INFINITY, (size_t)qkv.B * hd);
   dim3 grid(nsplit, hd / 8, qkv.B);
   kmax_kernel<<<grid, 256, 0, st>>>(qkv.p, qkv.cg(), hd / 8, qkv.voxels(), nsplit, kmax, hd);
-  FTB_CUDA(cudaGetLastError());
+  FTB_LAUNCH_OK();
   return 0;
 }
 
@@ -308,7 +308,7 @@ int linattn_context_partial(const Act& qkv, int heads, int dh, int nsplit, const
     ctx_partial_kernel<16><<<grid, 256, 0, st>>>(qkv.p, qkv.cg(), heads, qkv.voxels(), nsplit, kmax, part);
   else
     FTB_FAIL("linattn: dim_head must be 16 or 32");
-  FTB_CUDA(cudaGetLastError());
+  FTB_LAUNCH_OK();
   return 0;
 }
 
@@ -319,7 +319,7 @@ int linattn_combine(const float* part, int nsplit, const float* kmax, int B, int
   const size_t smem = (size_t)heads * dh * dh * sizeof(float);
   FTB_CHECK(smem <= 48 * 1024, "linattn: context does not fit shared memory");
   combine_kernel<<<B, 256, smem, st>>>(part, nsplit, kmax, heads, dh, mem_kv, n_mem, w_out, C, q_scale, wpack_out, ctx_dbg);
-  FTB_CUDA(cudaGetLastError());
+  FTB_LAUNCH_OK();
   return 0;
 }
 
@@ -336,7 +336,7 @@ int full_attention(const Act& qkv, int heads, int dh, const float* mem_kv, int n
     full_attn_kernel<16><<<grid, 128, 0, st>>>(qkv.p, qkv.cg(), heads, n, mem_kv, n_mem, out.p, out.cg(), scale);
   else
     FTB_FAIL("attention: dim_head must be 16 or 32");
-  FTB_CUDA(cudaGetLastError());
+  FTB_LAUNCH_OK();
   return 0;
 }
 

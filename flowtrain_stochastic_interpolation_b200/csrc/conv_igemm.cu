@@ -43,6 +43,8 @@ struct IgemmParams {
   int n_items;
   int nslot, wslot, w_resident;
   uint32_t cg_pitch, row_pitch, src1_off, slot_stride, plane_tx_bytes, wtap_bytes;
+  int KC, nkc;              // k-steps per weight chunk, chunks per tap (ring unit = one chunk)
+  uint32_t wchunk_bytes;    // KC * N * 32 (ring slot stride)
   uint32_t off_w, off_bar;
   uint32_t tmem_cols;
   const bf16* wpack;
@@ -153,15 +155,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
           }
           if (!p.w_resident || wctr == 0) {
             const bf16* wsrc = p.wpack + (long long)c.b * p.w_batch_stride;
-            for (int t = 0; t < p.taps; ++t, ++wctr) {
-              const uint32_t slot = wctr % p.wslot;
-              const uint32_t par = (wctr / p.wslot) & 1;
-              mbar_wait(&w_empty[slot], par ^ 1);
-              mbar_expect_tx(&w_full[slot], p.wtap_bytes);
-              bulk_load(s_w + (size_t)slot * p.wtap_bytes,
-                        reinterpret_cast<const uint8_t*>(wsrc) + (size_t)t * p.wtap_bytes,
-                        p.wtap_bytes, &w_full[slot]);
-            }
+            for (int t = 0; t < p.taps; ++t)
+              for (int kc = 0; kc < p.nkc; ++kc, ++wctr) {
+                const uint32_t slot = wctr % p.wslot;
+                const uint32_t par = (wctr / p.wslot) & 1;
+                const uint32_t nks = min(p.KC, p.KS - kc * p.KC);
+                const uint32_t bytes = nks * p.N * 32;
+                mbar_wait(&w_empty[slot], par ^ 1);
+                mbar_expect_tx(&w_full[slot], bytes);
+                bulk_load(s_w + (size_t)slot * p.wchunk_bytes,
+                          reinterpret_cast<const uint8_t*>(wsrc) + (size_t)t * p.wtap_bytes +
+                              (size_t)kc * p.wchunk_bytes,
+                          bytes, &w_full[slot]);
+              }
           }
         }
       }
@@ -193,38 +199,40 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
           int t = 0;
           for (int kd = 0; kd < p.K; ++kd)
             for (int kh = 0; kh < p.K; ++kh)
-              for (int kw = 0; kw < p.K; ++kw, ++t) {
-                uint32_t wslot_i;
-                if (stream_w) {
-                  wslot_i = wctr % p.wslot;
-                  mbar_wait(&w_full[wslot_i], (wctr / p.wslot) & 1);
-                  tc_fence_after();
-                } else {
-                  wslot_i = t;
-                  if (!w_waited) {
-                    mbar_wait(&w_full[wslot_i], 0);
+              for (int kw = 0; kw < p.K; ++kw, ++t)
+                for (int kc = 0; kc < p.nkc; ++kc) {
+                  uint32_t wslot_i;
+                  if (stream_w) {
+                    wslot_i = wctr % p.wslot;
+                    mbar_wait(&w_full[wslot_i], (wctr / p.wslot) & 1);
                     tc_fence_after();
+                  } else {
+                    wslot_i = t * p.nkc + kc;
+                    if (!w_waited) {
+                      mbar_wait(&w_full[wslot_i], 0);
+                      tc_fence_after();
+                    }
+                  }
+                  const uint32_t wb = w_addr + wslot_i * p.wchunk_bytes;
+                  const int ks_lo = kc * p.KC, ks_hi = min(p.KS, ks_lo + p.KC);
+                  for (int zi = 0; zi < nze; ++zi) {
+                    const uint32_t pc = pbase + g * p.NZ + zi + kd;
+                    const uint32_t abase = planes_addr + (pc % p.nslot) * p.slot_stride +
+                                           kh * p.row_pitch + kw * 16;
+                    const uint32_t dcol = tmem_base + (ab * p.NZ + zi) * p.N;
+                    for (int ks = ks_lo; ks < ks_hi; ++ks) {
+                      const uint32_t aoff = ks < p.KS0 ? ks * 2 * p.cg_pitch
+                                                       : p.src1_off + (ks - p.KS0) * 2 * p.cg_pitch;
+                      const uint64_t da = umma_desc_kmajor_noswz(abase + aoff, p.cg_pitch, p.row_pitch);
+                      const uint64_t db = umma_desc_kmajor_noswz(wb + (ks - ks_lo) * p.N * 32, 128, 256);
+                      umma_bf16(dcol, da, db, idesc, (t | ks) != 0);
+                    }
+                  }
+                  if (stream_w) {
+                    umma_commit(&w_empty[wslot_i]);
+                    ++wctr;
                   }
                 }
-                const uint32_t wb = w_addr + wslot_i * p.wtap_bytes;
-                for (int zi = 0; zi < nze; ++zi) {
-                  const uint32_t pc = pbase + g * p.NZ + zi + kd;
-                  const uint32_t abase = planes_addr + (pc % p.nslot) * p.slot_stride +
-                                         kh * p.row_pitch + kw * 16;
-                  const uint32_t dcol = tmem_base + (ab * p.NZ + zi) * p.N;
-                  for (int ks = 0; ks < p.KS; ++ks) {
-                    const uint32_t aoff = ks < p.KS0 ? ks * 2 * p.cg_pitch
-                                                     : p.src1_off + (ks - p.KS0) * 2 * p.cg_pitch;
-                    const uint64_t da = umma_desc_kmajor_noswz(abase + aoff, p.cg_pitch, p.row_pitch);
-                    const uint64_t db = umma_desc_kmajor_noswz(wb + ks * p.N * 32, 128, 256);
-                    umma_bf16(dcol, da, db, idesc, (t | ks) != 0);
-                  }
-                }
-                if (stream_w) {
-                  umma_commit(&w_empty[wslot_i]);
-                  ++wctr;
-                }
-              }
           w_waited = true;
           // planes that leave the window: the NZ oldest, or everything at the end of the item
           const int rel_lo = g * p.NZ;
@@ -459,46 +467,61 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   p.s0_cgtot = a0.cg(); p.s0_cgoff = s0.cgoff;
   p.s1_cgtot = s1.t ? s1.t->cg() : 0; p.s1_cgoff = s1.cgoff;
   p.N = w.n;
-  p.TH = a0.H >= 16 ? 16 : a0.H;
-  p.BH = p.TH + 2 * p.pad;
   p.BW = 8 + 2 * p.pad;
-  p.nHt = cdiv(a0.H, p.TH);
   p.nWt = cdiv(a0.W, 8);
   p.row_pitch = p.BW * 16;
-  p.cg_pitch = p.BH * p.row_pitch;
-  p.src1_off = (uint32_t)round_up(p.cg0 * (int)p.cg_pitch, 128);
-  const uint32_t plane_bytes = p.src1_off + p.cg1 * p.cg_pitch;
-  p.plane_tx_bytes = (p.cg0 + p.cg1) * p.cg_pitch;
-  p.slot_stride = (uint32_t)round_up((int)plane_bytes, 128);
   p.wtap_bytes = (uint32_t)p.KS * p.N * 32;
-
-  // ---- tiling along D and ring sizing against the 227 KB shared-memory budget
+  // weight ring unit: a chunk of KC k-steps of one tap, at most 24 KB
+  p.KC = p.KS;
+  while (p.KC > 1 && (uint32_t)p.KC * p.N * 32 > 24 * 1024) --p.KC;
+  p.nkc = cdiv(p.KS, p.KC);
+  p.wchunk_bytes = (uint32_t)p.KC * p.N * 32;
+  const int nchunks = p.taps * p.nkc;
   const int sms = num_sms();
-  const int cols = a0.B * p.nHt * p.nWt;
-  const uint32_t slack = (uint32_t)(16 - p.TH + 2) * p.row_pitch + 512;  // A rows of a partial tile over-read
   const uint32_t bar_bytes = (2 * kMaxSlots + 2 * kMaxWSlots + 4) * 8 + 16;
-  const uint32_t fixed = slack + bar_bytes + 256;
   const size_t all_w = (size_t)p.taps * p.wtap_bytes;
   const int win1 = 1 + 2 * p.pad;
-  p.w_resident = 0;
-  p.NZ = 1;
-  if (w.batch_stride == 0 && p.taps <= kMaxWSlots &&
-      all_w + (size_t)(win1 + 1) * p.slot_stride + fixed <= kSmemLimit) {
-    p.w_resident = 1;
-    p.wslot = p.taps;
-  } else {
-    p.wslot = p.taps == 1 ? 1 : (p.wtap_bytes <= 8192 ? 6 : (p.wtap_bytes <= 16384 ? 4 : 2));
-    // amortise the streamed weights over NZ output planes (one accumulator each)
-    int nz = 1;
-    while (nz < 4 && nz * 2 <= a0.D && 2 * (nz * 2) * p.N <= 512 &&
-           (size_t)p.wslot * p.wtap_bytes + (size_t)(nz * 2 + 2 * p.pad + 1) * p.slot_stride + fixed <= kSmemLimit)
-      nz *= 2;
-    if (p.taps > 1) p.NZ = nz;
+
+  // ---- tile height, tiling along D and ring sizing against the 227 KB shared-memory budget.
+  // The tile is 8 (W) x TH (H) voxels in the 128-row MMA; TH = 16 unless a plane window of that
+  // height does not fit (very wide inputs), then rows are traded for capacity.
+  uint32_t slack = 0, fixed = 0;
+  size_t w_region = 0;
+  int win = 0;
+  bool fits = false;
+  for (int th = a0.H >= 16 ? 16 : a0.H; th >= 1; th = th / 2) {
+    p.TH = th;
+    p.BH = p.TH + 2 * p.pad;
+    p.nHt = cdiv(a0.H, p.TH);
+    p.cg_pitch = p.BH * p.row_pitch;
+    p.src1_off = (uint32_t)round_up(p.cg0 * (int)p.cg_pitch, 128);
+    const uint32_t plane_bytes = p.src1_off + p.cg1 * p.cg_pitch;
+    p.plane_tx_bytes = (p.cg0 + p.cg1) * p.cg_pitch;
+    p.slot_stride = (uint32_t)round_up((int)plane_bytes, 128);
+    slack = (uint32_t)(16 - p.TH + 2) * p.row_pitch + 512;  // A rows of a partial tile over-read
+    fixed = slack + bar_bytes + 256;
+    p.w_resident = 0;
+    p.NZ = 1;
+    if (w.batch_stride == 0 && nchunks <= kMaxWSlots && p.nkc == 1 &&
+        all_w + (size_t)(win1 + 1) * p.slot_stride + fixed <= kSmemLimit) {
+      p.w_resident = 1;
+      p.wslot = nchunks;
+    } else {
+      p.wslot = nchunks == 1 ? 2 : (p.wchunk_bytes <= 8192 ? 6 : (p.wchunk_bytes <= 16384 ? 4 : 3));
+      // amortise the streamed weights over NZ output planes (one accumulator each)
+      int nz = 1;
+      while (nz < 4 && nz * 2 <= a0.D && 2 * (nz * 2) * p.N <= 512 &&
+             (size_t)p.wslot * p.wchunk_bytes + (size_t)(nz * 2 + 2 * p.pad + 1) * p.slot_stride + fixed <= kSmemLimit)
+        nz *= 2;
+      if (p.taps > 1) p.NZ = nz;
+    }
+    w_region = (size_t)p.wslot * p.wchunk_bytes;
+    win = p.NZ + 2 * p.pad;
+    if (w_region + (size_t)(win + 1) * p.slot_stride + fixed <= kSmemLimit) { fits = true; break; }
+    if (th == 1) break;
   }
-  const size_t w_region = (size_t)p.wslot * p.wtap_bytes;
-  const int win = p.NZ + 2 * p.pad;
-  FTB_CHECK(w_region + (size_t)win * p.slot_stride + fixed <= kSmemLimit,
-            "conv: one plane window + weights exceed shared memory (Cin too large for this tile)");
+  FTB_CHECK(fits, "conv: one plane window + weights exceed shared memory (Cin too large)");
+  const int cols = a0.B * p.nHt * p.nWt;
   int nslot = (int)((kSmemLimit - fixed - w_region) / p.slot_stride);
   nslot = nslot > kMaxSlots ? kMaxSlots : nslot;
   p.nslot = nslot;
@@ -554,8 +577,20 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
     q.bias = e.bias ? e.bias + (size_t)nt * w.n : nullptr;
     q.out_cgoff = out_cgoff + nt * (w.n / 8);
     q.flags = (e.silu ? F_SILU : 0) | ((e.q_softmax_heads && nt == 0) ? F_QSOFTMAX : 0);
+    int prof = -1;
+    if (prof_enabled()) {
+      // algorithmic work of this launch: real (unpadded) channel counts
+      const double vox = (double)a0.B * a0.voxels();
+      const double cin = w.cin_real > 0 ? w.cin_real : w.cin;
+      const double cout_all = w.cout_real > 0 ? w.cout_real : (double)w.n * w.ntiles;
+      const double cout = cout_all / w.ntiles;
+      const double flops = 2.0 * vox * cin * cout * p.taps;
+      const double bytes = vox * (cin + cout) * 2.0;  // read input once, write output once (bf16)
+      prof = prof_begin(st, flops, bytes, w.ksize > 1 ? 0 : 1);
+    }
     conv_igemm_kernel<<<grid, kThreads, smem_bytes, st>>>(tm0, tm1, q);
-    FTB_CUDA(cudaGetLastError());
+    prof_end(prof, st);
+    FTB_LAUNCH_OK();
   }
   return 0;
 }

@@ -185,7 +185,7 @@ int pack_conv_weights(const float* w, int cout, int cin_real, int ksize, int cin
   const size_t total = (size_t)ntiles * taps * cin_pad * ntile_n;
   const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
   pack_weights_kernel<<<blocks, 256, 0, st>>>(w, cout, cin_real, taps, cin_pad, ntile_n, ntiles, in_scale, dst);
-  FTB_CUDA(cudaGetLastError());
+  FTB_LAUNCH_OK();
   return 0;
 }
 
@@ -216,7 +216,7 @@ int conv_naive(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
     q.out_cgoff = out_cgoff + nt * (w.n / 8);
     q.qsoftmax = (e.q_softmax_heads && nt == 0) ? 1 : 0;
     conv_naive_kernel<<<blocks, 128, 0, st>>>(q);
-    FTB_CUDA(cudaGetLastError());
+    FTB_LAUNCH_OK();
   }
   return 0;
 }

@@ -345,20 +345,20 @@ int pack_ncdhw_to_blocked(const float* x, int B, int C, int D, int H, int W, Act
             "pack: output activation shape");
   const size_t vox = (size_t)D * H * W;
   pack_kernel<<<grid_for((size_t)B * out.cg() * vox, 256), 256, 0, st>>>(x, B, C, vox, out.cg(), out.p);
-  FTB_CUDA(cudaGetLastError());
+  FTB_LAUNCH_OK();
   return 0;
 }
 int unpack_blocked_to_ncdhw(const Act& in, int cgoff, int C, float* out, cudaStream_t st) {
   const size_t vox = in.voxels();
   unpack_kernel<<<grid_for((size_t)in.B * ((C + 7) / 8) * vox, 256), 256, 0, st>>>(in.p, in.B, in.cg(), cgoff, C, vox, out);
-  FTB_CUDA(cudaGetLastError());
+  FTB_LAUNCH_OK();
   return 0;
 }
 int trilinear_resample(const Act& in, Act& out, cudaStream_t st) {
   FTB_CHECK(in.B == out.B && in.C == out.C, "trilinear: batch/channels must match");
   trilinear_kernel<<<grid_for((size_t)out.B * out.cg() * out.voxels(), 256), 256, 0, st>>>(
       in.p, in.B, in.cg(), in.D, in.H, in.W, out.D, out.H, out.W, out.p);
-  FTB_CUDA(cudaGetLastError());
+  FTB_LAUNCH_OK();
   return 0;
 }
 int interp_xt_bt(int kind, int one_sided, float gamma_a, const float* x0, const float* x1,
@@ -370,7 +370,7 @@ int interp_xt_bt(int kind, int one_sided, float gamma_a, const float* x0, const 
   interp_kernel<<<grid_for((size_t)B * n4, 256), 256, 0, st>>>(
       kind, one_sided, gamma_a, (const float4*)x0, (const float4*)x1, (const float4*)z, t,
       (float4*)xt, (float4*)bt, B, n4);
-  FTB_CUDA(cudaGetLastError());
+  FTB_LAUNCH_OK();
   return 0;
 }
 int axpy_out(float* out, const float* x, const float* k, float h, long long n,
@@ -380,27 +380,27 @@ int axpy_out(float* out, const float* x, const float* k, float h, long long n,
   } else {
     axpy_kernel<<<grid_for((size_t)n, 256), 256, 0, st>>>(out, x, k, h, (size_t)n, frozen, (size_t)(inner > 0 ? inner : 1));
   }
-  FTB_CUDA(cudaGetLastError());
+  FTB_LAUNCH_OK();
   return 0;
 }
 int heun_combine(float* out, const float* x, const float* k1, const float* k2, double h, long long n, cudaStream_t st) {
   FTB_CHECK(n % 4 == 0, "heun: n must be a multiple of 4");
   heun_kernel<<<grid_for((size_t)n / 4, 256), 256, 0, st>>>((float4*)out, (const float4*)x, (const float4*)k1, (const float4*)k2, (float)(h / 2.0), (size_t)n / 4);
-  FTB_CUDA(cudaGetLastError());
+  FTB_LAUNCH_OK();
   return 0;
 }
 int rk4_combine(float* out, const float* x, const float* k1, const float* k2, const float* k3,
                 const float* k4, double h, long long n, cudaStream_t st) {
   FTB_CHECK(n % 4 == 0, "rk4: n must be a multiple of 4");
   rk4_kernel<<<grid_for((size_t)n / 4, 256), 256, 0, st>>>((float4*)out, (const float4*)x, (const float4*)k1, (const float4*)k2, (const float4*)k3, (const float4*)k4, (float)(h / 6.0), (size_t)n / 4);
-  FTB_CUDA(cudaGetLastError());
+  FTB_LAUNCH_OK();
   return 0;
 }
 int denoise_drift(float* out, const float* x, const float* eta, const float* noise, float a, float b,
                   float ad, float bd, float eps, int use_sde, long long n, cudaStream_t st) {
   FTB_CHECK(!use_sde || noise != nullptr, "drift: SDE term needs a noise tensor");
   drift_kernel<<<grid_for((size_t)n, 256), 256, 0, st>>>(out, x, eta, noise, a, b, ad, bd, eps, use_sde, (size_t)n);
-  FTB_CUDA(cudaGetLastError());
+  FTB_LAUNCH_OK();
   return 0;
 }
 int decode_argmax(const float* x, const float* en, long long* out, int B, int E, int ncat,
@@ -408,23 +408,23 @@ int decode_argmax(const float* x, const float* en, long long* out, int B, int E,
   FTB_CHECK(E >= 1 && E <= 32, "decode: embedding dim must be in [1,32]");
   FTB_CHECK(ncat >= 1 && ncat <= 256, "decode: category count");
   decode_kernel<<<grid_for((size_t)B * n, 128), 128, (size_t)ncat * E * sizeof(float), st>>>(x, en, out, B, E, ncat, (size_t)n);
-  FTB_CUDA(cudaGetLastError());
+  FTB_LAUNCH_OK();
   return 0;
 }
 int embed_lookup(const long long* cats, const float* w, float* out, int B, int E, int ncat,
                  long long n, int shift, cudaStream_t st) {
   embed_kernel<<<grid_for((size_t)B * E * n, 256), 256, 0, st>>>(cats, w, out, B, E, ncat, (size_t)n, shift);
-  FTB_CUDA(cudaGetLastError());
+  FTB_LAUNCH_OK();
   return 0;
 }
 int ema_update(float* shadow, const float* param, long long n, double decay, cudaStream_t st) {
   ema_kernel<<<grid_for((size_t)n, 256), 256, 0, st>>>(shadow, param, (size_t)n, (float)decay, (float)(1.0 - decay));
-  FTB_CUDA(cudaGetLastError());
+  FTB_LAUNCH_OK();
   return 0;
 }
 int mse_ratio_partial(const float* v, const float* vhat, long long n, double* acc2, cudaStream_t st) {
   mse_kernel<<<grid_for((size_t)n, 256), 256, 0, st>>>(v, vhat, (size_t)n, acc2);
-  FTB_CUDA(cudaGetLastError());
+  FTB_LAUNCH_OK();
   return 0;
 }
 

@@ -36,6 +36,64 @@ int num_sms() {
   return n;
 }
 
+// ---- launch counter and optional per-launch event timing of the conv kernel
+static long long g_launches = 0;
+void count_launch(int n) { g_launches += n; }
+long long launch_count() { return g_launches; }
+
+namespace {
+struct ProfRec {
+  cudaEvent_t e0, e1;
+  double flops, bytes;
+  int kind;
+};
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_event_pool;
+cudaEvent_t pool_event() {
+  if (!g_event_pool.empty()) {
+    cudaEvent_t e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+bool prof_enabled() { return g_prof_on; }
+int prof_begin(cudaStream_t st, double flops, double bytes, int kind) {
+  if (!g_prof_on) return -1;
+  ProfRec r{pool_event(), pool_event(), flops, bytes, kind};
+  cudaEventRecord(r.e0, st);
+  g_prof.push_back(r);
+  return (int)g_prof.size() - 1;
+}
+void prof_end(int idx, cudaStream_t st) {
+  if (idx >= 0 && idx < (int)g_prof.size()) cudaEventRecord(g_prof[idx].e1, st);
+}
+void prof_set(bool on) { g_prof_on = on; }
+// sums per kind (0: conv k>=3, 1: conv 1x1); returns number of records consumed
+int prof_collect(double* flops, double* bytes, double* ms, int* launches, int nkinds) {
+  for (int k = 0; k < nkinds; ++k) { flops[k] = 0; bytes[k] = 0; ms[k] = 0; launches[k] = 0; }
+  int n = 0;
+  for (ProfRec& r : g_prof) {
+    float t = 0.f;
+    if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess &&
+        r.kind >= 0 && r.kind < nkinds) {
+      flops[r.kind] += r.flops;
+      bytes[r.kind] += r.bytes;
+      ms[r.kind] += t;
+      launches[r.kind] += 1;
+      ++n;
+    }
+    g_event_pool.push_back(r.e0);
+    g_event_pool.push_back(r.e1);
+  }
+  g_prof.clear();
+  return n;
+}
+
 namespace eng {
 
 struct Param {
@@ -346,6 +404,7 @@ struct Fwd {
     const ConvLayer& cl = U->convs.at(name);
     ConvWeights w;
     w.w = cl.packed; w.ksize = cl.k; w.cin = cl.cin_pad; w.n = cl.n_tile; w.ntiles = cl.ntiles;
+    w.cin_real = cl.cin; w.cout_real = cl.cout;
     if (!cl.bname.empty()) e.bias = cl.bias;
     if (dry) return 0;
     U->launches += cl.ntiles;
@@ -533,6 +592,15 @@ extern "C" {
 const char* ftb_last_error(void) { return g_err.c_str(); }
 int ftb_version(void) { return 100; }
 int ftb_device_sm_count(void) { return num_sms(); }
+int64_t ftb_launch_count(void) { return launch_count(); }
+int ftb_profile_enable(int on) {
+  prof_set(on != 0);
+  return 0;
+}
+int ftb_profile_collect(double* flops, double* bytes, double* ms, int* launches, int nkinds) {
+  FTB_CHECK(flops && bytes && ms && launches && nkinds >= 1, "null argument");
+  return prof_collect(flops, bytes, ms, launches, nkinds) >= 0 ? 0 : -1;
+}
 
 int ftb_unet3d_create(const ftb_unet_cfg* cfg, ftb_unet** out) {
   FTB_CHECK(cfg && out, "null argument");

@@ -27,6 +27,12 @@ int fail(const char* file, int line, const std::string& msg);
     if (_e != cudaSuccess)                                                               \
       return ::ftb::fail(__FILE__, __LINE__, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
   } while (0)
+// after a kernel launch: surface launch errors and count the launch (bench.py "gpu_launches")
+#define FTB_LAUNCH_OK()                \
+  do {                                 \
+    FTB_CUDA(cudaGetLastError());      \
+    ::ftb::count_launch(1);            \
+  } while (0)
 #define FTB_TRY(expr)          \
   do {                         \
     int _r = (expr);           \
@@ -53,6 +59,11 @@ static inline size_t round_up_sz(size_t x, size_t m) { return (x + m - 1) / m * 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 int num_sms();
+void count_launch(int n);
+// optional per-launch CUDA-event timing of the conv kernel (bench.py roofline leg)
+bool prof_enabled();
+int prof_begin(cudaStream_t st, double flops, double bytes, int kind);
+void prof_end(int idx, cudaStream_t st);
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------

@@ -16,6 +16,7 @@ struct ConvWeights {
   int n = 0;            // output channels of one N tile (multiple of 16, <= 256)
   int ntiles = 1;       // number of N tiles packed back to back
   long long batch_stride = 0;  // elements between per-sample weight sets (0 = shared)
+  int cin_real = 0, cout_real = 0;  // unpadded channel counts (algorithmic-FLOP accounting only)
   size_t tile_elems() const { return (size_t)ksize * ksize * ksize * cin * n; }
 };
 

@@ -77,14 +77,14 @@ int time_embed(const TimeMlpParams& p, const float* t, int B, float* temb, float
   const size_t smem = (size_t)(p.time_res + p.time_dim) * sizeof(float);
   FTB_CHECK(smem <= 48 * 1024, "time_embed: time_resolution + time_dim too large for shared memory");
   time_embed_kernel<<<B, 256, smem, st>>>(p, t, temb, temb_silu);
-  FTB_CUDA(cudaGetLastError());
+  FTB_LAUNCH_OK();
   return 0;
 }
 
 int film_mlps(const FilmTable& ft, const float* temb_silu, int B, float* out, cudaStream_t st) {
   const int warps_per_block = 8;
   film_kernel<<<cdiv(ft.total_rows, warps_per_block), 256, 0, st>>>(ft, temb_silu, B, out);
-  FTB_CUDA(cudaGetLastError());
+  FTB_LAUNCH_OK();
   return 0;
 }
 

@@ -45,6 +45,13 @@ typedef struct ftb_unet ftb_unet;
 const char* ftb_last_error(void);
 int ftb_version(void);
 int ftb_device_sm_count(void);
+/* kernels launched by this library in this process so far (bench.py "gpu_launches") */
+int64_t ftb_launch_count(void);
+/* optional CUDA-event timing around every conv_igemm launch on its own stream (roofline leg of
+ * bench.py).  collect() synchronises the recorded events and sums, per kind (0: 3x3x3/5^3/7^3
+ * convs, 1: 1x1x1 convs), algorithmic FLOPs, algorithmic bytes, milliseconds and launches. */
+int ftb_profile_enable(int on);
+int ftb_profile_collect(double* flops, double* bytes, double* ms, int* launches, int nkinds);
 
 /* ---- Unet3D velocity field v_theta(x, t): replaces Unet3D.forward (unet_attn_3d.py:673-719) */
 /* create() only builds the plan (works without a GPU, so names/shapes can be queried);

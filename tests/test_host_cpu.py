@@ -1,0 +1,127 @@
+"""CPU: the C-ABI library loads and exports every symbol include/ftb.h declares, the host-side
+mirror of the reference API (parameter tree, schedules, error behaviour) is right, and the
+sample-sharding logic works under a world_size-2 gloo group.  No compute kernels run here."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import flowtrain_stochastic_interpolation_b200 as ftb
+from flowtrain_stochastic_interpolation_b200 import _lib, sharding
+from oracle import interp, ref_loader, synth, task
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    syms = _lib.header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(_lib.lib, s), f"libftb.so does not export {s}"
+        assert s in _lib._SIGS, f"{s} has no ctypes signature"
+    assert _lib.lib.ftb_version() >= 100
+
+
+def test_no_cpu_fallback():
+    net = ftb.Unet3D(**synth.make_cfg(dim=32, dim_mults=(1, 2), attn_heads=2, attn_dim_head=16, time_resolution=64))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(torch.zeros(1, 18, 8, 8, 8), torch.zeros(1))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ftb.decode(task.simplex_embedding(15, 18), torch.zeros(1, 18, 2, 2, 2))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ftb.StochasticInterpolator(ftb.LinearInterpolant(True)).flow_objective(
+            torch.rand(2), torch.zeros(2, 4, 2, 2, 2), torch.zeros(2, 4, 2, 2, 2))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ftb.ODEFlowSolver(lambda x, t: x).solve(torch.zeros(1, 4, 2, 2, 2))
+    # the product package never imports the oracle
+    for mod in list(sys.modules):
+        if mod.startswith("flowtrain_stochastic_interpolation_b200"):
+            src = getattr(sys.modules[mod], "__file__", None)
+            if src and src.endswith(".py"):
+                assert "oracle" not in open(src).read().replace("oracle/unet3d.py", ""), mod
+
+
+@pytest.mark.parametrize("cfg", [synth.make_cfg(),
+                                 synth.make_cfg(dim=32, dim_mults=(1, 2), attn_heads=2, attn_dim_head=16,
+                                                time_resolution=64, time_learned_emb=False)])
+def test_param_tree_matches_reference_keys(cfg):
+    net = ftb.Unet3D(**cfg)
+    specs = synth.unet3d_param_specs(cfg)
+    sd = net.state_dict()
+    assert list(sd.keys()) == list(specs.keys())
+    assert all(tuple(sd[k].shape) == tuple(specs[k]) for k in sd)
+    # learned vs random Fourier features: requires_grad of freqs/phases (unet_attn_3d.py:198-218)
+    assert net.time_mlp._modules["0"].freqs.requires_grad == bool(cfg["time_learned_emb"])
+    if ref_loader.available():
+        ref = ref_loader.unet3d_module().Unet3D(**cfg)
+        assert list(ref.state_dict().keys()) == list(sd.keys())
+        assert [n for n, p in ref.named_parameters() if p.requires_grad] == \
+               [n for n, p in net.named_parameters() if p.requires_grad]
+        net.load_state_dict(ref.state_dict())  # strict
+
+
+def test_ctor_rejects_unsupported_and_bad_dims():
+    with pytest.raises(NotImplementedError):
+        ftb.Unet3D(dim=32, self_condition=True)
+    with pytest.raises(NotImplementedError):
+        ftb.Unet3D(dim=32, time_sin_pos=True)
+    with pytest.raises(_lib.FtbError):
+        ftb.Unet3D(dim=20)  # not a multiple of 16
+
+
+def test_init_statistics_like_reference():
+    torch.manual_seed(0)
+    net = ftb.Unet3D(**synth.make_cfg())
+    sd = net.state_dict()
+    w = sd["downs.0.0.block1.proj.weight"]
+    bound = 1 / (48 * 27) ** 0.5
+    assert w.abs().max() <= bound and w.abs().max() > 0.9 * bound
+    assert torch.all(sd["downs.0.0.block1.norm.g"] == 1)
+    assert 800 < sd["time_mlp.0.freqs"].std() < 1200
+    assert 0 <= sd["time_mlp.0.phases"].min() and sd["time_mlp.0.phases"].max() <= 1
+
+
+def test_schedules_match_oracle_and_reference():
+    t = torch.linspace(0.01, 0.99, 50)
+    cases = [(ftb.LinearInterpolant(False), "linear", False), (ftb.LinearInterpolant(True), "linear", True),
+             (ftb.TrigInterpolant(False), "trig", False), (ftb.TrigInterpolant(True), "trig", True),
+             (ftb.EncDecInterpolant(), "encdec", False), (ftb.SBDMInterpolant(), "sbdm", True),
+             (ftb.MirrorInterpolant(), "mirror", False)]
+    for ip, kind, one in cases:
+        mine = torch.stack([ip.alpha(t), ip.beta(t), ip.gamma(t), ip.alpha_dot(t), ip.beta_dot(t), ip.gamma_dot(t)])
+        want = torch.stack(interp.coeffs(kind, t, one))
+        assert torch.equal(mine, want), kind
+        assert ip.is_one_sided() == interp.is_one_sided(kind, one)
+    si = ftb.StochasticInterpolator(ftb.LinearInterpolant(False))
+    with pytest.raises(ValueError, match="Z must be provided"):
+        si.flow_objective(torch.rand(2), torch.zeros(2, 4), torch.zeros(2, 4))
+    assert repr(si) == "StochasticInterpolator(LinearInterpolant(one_sided=False))"
+
+
+def test_simplex_embedding_matches_oracle():
+    assert torch.equal(ftb.simplex_embedding(15, 18), task.simplex_embedding(15, 18))
+    assert torch.equal(ftb.simplex_embedding(15, 15), task.simplex_embedding(15, 15))
+
+
+def test_shard_indices_cover_everything_once():
+    for n, world in ((64, 1), (64, 8), (10, 4), (3, 8)):
+        seen = []
+        for r in range(world):
+            seen += list(sharding.shard_indices(n, r, world))
+        assert sorted(seen) == list(range(n))
+    assert list(sharding.shard_indices(10, 1, 4)) == [1, 5, 9]
+
+
+def test_sharded_ensemble_gloo_world2():
+    """world_size-2 gloo run of the N>1 host path: shard sample indices, run a (CPU stand-in)
+    per-sample function, gather the decoded volumes and the vote histogram on rank 0."""
+    script = os.path.join(ROOT, "tests", "_gloo_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29613")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29613", script],
+                       capture_output=True, text=True, timeout=240, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "GLOO_OK" in r.stdout
