@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 hot path (contract: task prompt, section 4).
+
+Metric (BASELINE.json): 64^3 samples/s for a 100-step ODE solve of the unconditional Unet3D
+(base 48, mults 1,2,2,3,4, 18-d embedding).  Workload at every N: BASELINE configs[1] —
+batch 8 per GPU, Heun integrator (2 velocity evaluations per step), bf16 tensor-core convs with
+fp32 state.  One bench "step" = ONE integrator step of the whole batch (the hot path once over one
+batch: 2 x v_theta(x,t) + the fused stage kernels); the metric follows as
+
+    samples/s = n_gpus * B / (100 * step_seconds + decode_seconds)
+
+with the decode of the final state (one kernel, timed separately, in the same run) included.
+Inputs larger than L2 (B=8 fp32 state 151 MB, every 64^3 activation 201 MB > 126 MB L2), so no
+explicit L2 flush between iterations.
+
+`value`  : device-resident state, CUDA events, barrier + synchronize on both sides, max over ranks.
+`e2e`    : the same metric through the public API a flowtrain user calls
+           (ODEFlowSolver(net).solve -> decode) starting from PINNED HOST noise and ending with the
+           decoded int64 volume back on the host, for the FULL 100-step solve; "step" bytes are
+           the solve's H2D/D2H bytes.
+`roofline`: dominant kernel = conv_igemm (3^3/5^3/7^3 implicit-GEMM convs): algorithmic FLOPs of
+           its launches / their CUDA-event durations, measured in a profile pass of the same step
+           right after the timed region (events per launch on the launching stream).
+`cpu_baseline` / `--impl reference`: the oracle port of the reference's CPU path (torch CPU ops,
+           all host threads) on a bounded sample: single velocity evaluations at B=1.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "samples_per_sec_64cubed_100step_ode"
+UNIT = "samples/s"
+N_ODE_STEPS = 100
+T0, TF = 0.001, 1.0                      # model_train_inference.py:618
+GF_PER_EVAL = 872.7                      # algorithmic GFLOP per velocity evaluation per sample @64^3
+EVALS_PER_STEP = {"euler": 1, "heun": 2, "rk4": 4}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--size", type=int, default=64)
+    ap.add_argument("--method", default="heun", choices=list(EVALS_PER_STEP))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-evals", type=int, default=2, help="timed CPU velocity evaluations in the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"configs[1]: unconditional {a.size}^3 sampling, batch {a.batch}/GPU, {a.method} integrator, "
+            f"{N_ODE_STEPS}-step ODE, bf16 (Unet3D dim 48 mults 1,2,2,3,4, 18 ch)")
+
+
+# ---------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "bf16_burst": d["bf16_tflops"], "src": "MEASURED_PEAKS.json (sustained bf16: kernel timed inside a long step)"}
+    return {"hbm_gbs": 6650.0, "bf16": 1590.0, "bf16_burst": 1590.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return None
+
+
+# ---------------------------------------------------------------------------- CPU baseline (oracle port)
+def cpu_velocity_evals(n_timed, size, threads=None):
+    """Times the oracle's CPU restatement of Unet3D.forward (the reference's CPU path) at B=1."""
+    import torch
+    from oracle import synth, unet3d
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = synth.make_cfg()
+    params = synth.synth_unet3d_params(cfg, 0)
+    x = synth.synth_input((1, 18, size, size, size), 100)
+    t = torch.tensor([0.5])
+    times = []
+    with torch.no_grad():
+        unet3d.unet3d_forward(params, cfg, x, t)  # warm-up (oneDNN primitive creation)
+        for _ in range(n_timed):
+            t0 = time.perf_counter()
+            unet3d.unet3d_forward(params, cfg, x, t)
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), cores
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import synth, unet3d
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = synth.make_cfg()
+    params = synth.synth_unet3d_params(cfg, 0)
+    x = synth.synth_input((1, 18, a.size, a.size, a.size), 100)
+    t = torch.tensor([0.5])
+    per = EVALS_PER_STEP[a.method]
+    with torch.no_grad():
+        for _ in range(a.warmup):
+            unet3d.unet3d_forward(params, cfg, x, t)
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            unet3d.unet3d_forward(params, cfg, x, t)
+        dt = (time.perf_counter() - t0) / a.steps
+    # one bench step of the reference arm = ONE velocity evaluation at B=1 (bounded sample of the
+    # 100 x `per` evaluations of a solve); integrator axpys and decode are < 0.1% on the CPU
+    value = 1.0 / (N_ODE_STEPS * per * dt)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "reference_step": "one CPU velocity evaluation, B=1"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{a.steps} velocity evaluations at B=1 {a.size}^3 fp32 (oracle port of "
+                                   f"Unet3D.forward on torch CPU ops); samples/s = 1/({N_ODE_STEPS}*{per}*s_per_eval)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------- B200 arm
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert torch.cuda.is_available(), "bench.py needs a B200 (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    import flowtrain_stochastic_interpolation_b200 as ftb
+    from flowtrain_stochastic_interpolation_b200 import _lib
+    from oracle import synth  # synthetic weights/inputs only (no oracle compute on this arm's timed path)
+
+    cfg = synth.make_cfg()
+    net = ftb.Unet3D(**cfg).to(dev).eval()
+    net.load_state_dict(synth.synth_unet3d_params(cfg, 0))
+    B, S = a.batch, a.size
+    per = EVALS_PER_STEP[a.method]
+    W = ftb.simplex_embedding(15, 18).to(dev)
+    # per-rank noise: sample index i -> seed 100 + i (independent samples, no communication)
+    g = torch.Generator("cpu").manual_seed(100 + rank)
+    x_host = torch.randn(B, 18, S, S, S, generator=g).pin_memory()
+    x_dev = x_host.to(dev)
+    solver = ftb.ODEFlowSolver(net, method=a.method)
+    h = (TF - T0) / N_ODE_STEPS
+
+    def run_steps(k, x):
+        return solver.solve(x, t0=T0, tf=T0 + k * h, n_steps=k + 1, return_trajectory=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        run_steps(max(a.warmup, 1), x_dev)
+        barrier()
+        clocks = ClockSampler(local_rank)
+        if rank == 0:
+            clocks.start()
+        l0 = _lib.lib.ftb_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        x_end = run_steps(a.steps, x_dev)
+        e1.record()
+        barrier()
+        step_ms = e0.elapsed_time(e1) / a.steps
+        launches = _lib.lib.ftb_launch_count() - l0
+        clk = clocks.stop() if rank == 0 else None
+        # decode of the final state (part of the metric)
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ftb.decode(W, x_end)
+        torch.cuda.synchronize()
+        d0.record()
+        dec = ftb.decode(W, x_end)
+        d1.record()
+        torch.cuda.synchronize()
+        decode_ms = d0.elapsed_time(d1)
+
+        # ---- roofline leg: per-launch CUDA events around every conv_igemm launch of one more step
+        _lib.lib.ftb_profile_enable(1)
+        run_steps(1, x_dev)
+        torch.cuda.synchronize()
+        import ctypes as C
+        nk = 2
+        fl, by, ms = (C.c_double * nk)(), (C.c_double * nk)(), (C.c_double * nk)()
+        ln = (C.c_int * nk)()
+        _lib.check(_lib.lib.ftb_profile_collect(fl, by, ms, ln, nk))
+        _lib.lib.ftb_profile_enable(0)
+        t1, t2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t1.record()
+        run_steps(1, x_dev)
+        t2.record()
+        torch.cuda.synchronize()
+        one_step_ms = t1.elapsed_time(t2)
+
+        # ---- e2e: full solve through the public API from pinned host noise to host categories
+        e2e = None
+        if not a.no_e2e:
+            barrier()
+            w0 = time.perf_counter()
+            xd = x_host.to(dev, non_blocking=True)
+            xe = solver.solve(xd, t0=T0, tf=TF, n_steps=N_ODE_STEPS + 1, return_trajectory=False)
+            out_host = ftb.decode(W, xe).cpu()
+            torch.cuda.synchronize()
+            e2e_s = time.perf_counter() - w0
+            e2e = (e2e_s, x_host.numel() * 4, out_host.numel() * 8)
+
+    tot_s = (N_ODE_STEPS * step_ms + decode_ms) / 1e3
+    stats = torch.tensor([step_ms, decode_ms, tot_s, e2e[0] if e2e else 0.0, float(launches)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    step_ms, decode_ms, tot_s, e2e_s, launches = stats.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    conv_tf = fl[0] / (ms[0] * 1e-3) / 1e12 if ms[0] > 0 else 0.0
+    traffic = ncu_traffic()
+    roof = {
+        "bound": "tensor", "kernel": "conv_igemm_kernel (k>=3 convs)", "achieved": conv_tf, "peak": peaks["bf16"],
+        "unit": "TFLOP/s", "frac": conv_tf / peaks["bf16"], "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+        "peak_source": peaks["src"], "launches_per_step": int(ln[0]), "avg_launch_ms": ms[0] / max(ln[0], 1),
+        "algorithmic_gflop_per_launch": fl[0] / max(ln[0], 1) / 1e9,
+        "share_of_step": ms[0] / one_step_ms if one_step_ms > 0 else None,
+        "conv1x1": {"ms": ms[1], "launches": int(ln[1]), "achieved_gbs": by[1] / (ms[1] * 1e-3) / 1e9 if ms[1] > 0 else None,
+                    "hbm_peak_gbs": peaks["hbm_gbs"]},
+        "whole_step_tflops": GF_PER_EVAL * per * B / step_ms / 1e3,
+        "whole_step_frac": GF_PER_EVAL * per * B / step_ms / 1e3 / peaks["bf16"],
+    }
+    line = {
+        "metric": METRIC, "value": world * B / tot_s, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": workload_name(a), "global_batch": world * B, "volume": [S, S, S],
+                   "ode_steps": N_ODE_STEPS, "evals_per_step": per, "decode_ms": decode_ms,
+                   "step": "one integrator step of the whole batch; value = n_gpus*B/(100*step+decode)",
+                   "l2": "inputs larger than L2 (fp32 state 151 MB, activations 201 MB each at B=8); no flush",
+                   "parallelism": f"independent samples, {world} rank(s), no data-path collective",
+                   "weights": "synthetic random-init (oracle/synth.py seed 0)"},
+        "clocks": clk, "gpu_launches": int(launches), "roofline": roof,
+    }
+    if e2e:
+        line["e2e"] = {"value": world * B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": e2e[1], "d2h_bytes_per_step": e2e[2],
+                       "seconds_per_solve": e2e_s,
+                       "what": "ODEFlowSolver.solve (full 100 steps) + decode, pinned-host X0 in, host int64 volume out; "
+                               "bytes are per solve"}
+    if not a.no_cpu_baseline:
+        s_per_eval, cores = cpu_velocity_evals(a.cpu_evals, S)
+        line["cpu_baseline"] = {
+            "value": 1.0 / (N_ODE_STEPS * per * s_per_eval), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{a.cpu_evals} velocity evaluations at B=1 {S}^3 fp32 on the host ({s_per_eval:.2f} s each, oracle "
+                      f"port of the reference CPU path); samples/s = 1/({N_ODE_STEPS}*{per}*s_per_eval)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()
