@@ -311,8 +311,8 @@ def run_b200(a):
         "share_of_step": ms[0] / one_step_ms if one_step_ms > 0 else None,
         "conv1x1": {"ms": ms[1], "launches": int(ln[1]), "achieved_gbs": by[1] / (ms[1] * 1e-3) / 1e9 if ms[1] > 0 else None,
                     "hbm_peak_gbs": peaks["hbm_gbs"]},
-        "whole_step_tflops": GF_PER_EVAL * per * B / step_ms / 1e3,
-        "whole_step_frac": GF_PER_EVAL * per * B / step_ms / 1e3 / peaks["bf16"],
+        "whole_step_tflops": GF_PER_EVAL * per * B / step_ms,
+        "whole_step_frac": GF_PER_EVAL * per * B / step_ms / peaks["bf16"],
     }
     line = {
         "metric": METRIC, "value": world * B / tot_s, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,

@@ -16,10 +16,19 @@
 //     from L2 once and reused by all K^3 taps; zero padding comes from TMA out-of-bounds fill.
 //   * an output tile is M = 128 voxels = 16 rows (H) x 8 columns (W) of one depth plane; the CTA
 //     marches along D through a ring of plane slots, so each plane is loaded once per column.
-//   * weights are pre-packed per (tap, k-step) as N x 16 K-major tiles; they stay resident in
-//     shared memory when all taps fit, else they stream through a small ring.
-//   * accumulators sit in TMEM (double-buffered: the epilogue of group g overlaps the MMAs of g+1);
-//     each epilogue thread owns one voxel row, so the channel reduction of RMSNorm is thread-local.
+//   * a group of NZ consecutive output planes is accumulated at once (NZ TMEM accumulators of N
+//     columns, side by side).  Weights are packed per (kh, kw, k-step) as a (K*N) x 16 K-major
+//     tile whose row blocks are the K depth taps in DESCENDING kd order: an input plane q of the
+//     window feeds output planes q-kd, i.e. ADJACENT accumulators, so one tcgen05.mma with
+//     N_mma = (#depth taps) * N covers them all ("depth-tap stacking").  A-operand reads from
+//     shared memory (128 rows x 32 B per MMA whatever N is) are what bounds narrow layers
+//     (Cout = 48: 4 KB of A for 1.5 KB of B); stacking divides them by up to K.
+//   * weights stay resident in shared memory when everything fits, else they stream through a
+//     small ring, once per group of NZ planes.
+//   * accumulators are double-buffered (the epilogue of group g overlaps the MMAs of g+1); each
+//     epilogue thread owns one voxel row, so the channel reduction of RMSNorm is thread-local.
+//   * the MMA issuer is one elected lane of warp 1; everything it needs per instruction is one
+//     16-byte table entry (built per group by the whole warp) plus two adds.
 #include "ops.h"
 
 namespace ftb {
@@ -29,22 +38,25 @@ namespace {
 constexpr int kThreads = 192;
 constexpr int kMaxSlots = 12;
 constexpr int kMaxWSlots = 32;
+constexpr int kMaxEnt = 96;   // MMA table entries per group (first-step pairs + stacked runs)
+constexpr int kMaxKS = 32;    // k-steps (Cin_pad / 16)
 
 enum : int { F_SILU = 1, F_QSOFTMAX = 2 };
 
 struct IgemmParams {
   int B, D, H, W;
-  int K, pad, taps;
+  int K, pad, taps;            // taps = K*K (kh, kw) positions; the K depth taps are stacked along N
   int cg0, cg1, KS0, KS;
   int s0_cgtot, s0_cgoff, s1_cgtot, s1_cgoff;
-  int N;
+  int N, smax;                 // smax: adjacent accumulators one MMA may cover (smax*N <= 256)
   int TH, BH, BW;
   int nHt, nWt, nSeg, LZ, NZ;
   int n_items;
   int nslot, wslot, w_resident;
   uint32_t cg_pitch, row_pitch, src1_off, slot_stride, plane_tx_bytes, wtap_bytes;
   int KC, nkc;              // k-steps per weight chunk, chunks per tap (ring unit = one chunk)
-  uint32_t wchunk_bytes;    // KC * N * 32 (ring slot stride)
+  uint32_t wchunk_bytes;    // KC * K * N * 32 (ring slot stride)
+  uint32_t kstep_bytes;     // K * N * 32: one k-step of one (kh,kw) position, all depth taps
   uint32_t off_w, off_bar;
   uint32_t tmem_cols;
   const bf16* wpack;
@@ -97,6 +109,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
   uint64_t* acc_full = w_empty + kMaxWSlots;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint32_t* s_koff = tmem_ptr + 4;                                   // [kMaxKS]
+  uint4* s_tab = reinterpret_cast<uint4*>(s_koff + kMaxKS);          // [kMaxEnt]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -160,7 +174,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
                 const uint32_t slot = wctr % p.wslot;
                 const uint32_t par = (wctr / p.wslot) & 1;
                 const uint32_t nks = min(p.KC, p.KS - kc * p.KC);
-                const uint32_t bytes = nks * p.N * 32;
+                const uint32_t bytes = nks * p.kstep_bytes;
                 mbar_wait(&w_empty[slot], par ^ 1);
                 mbar_expect_tx(&w_full[slot], bytes);
                 bulk_load(s_w + (size_t)slot * p.wchunk_bytes,
@@ -174,74 +188,128 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16_f32(128, p.N);
-      const uint32_t planes_addr = smem_u32(s_planes);
-      const uint32_t w_addr = smem_u32(s_w);
-      uint32_t pbase = 0, wctr = 0, gctr = 0;
-      bool w_waited = false;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const ItemCoord c = decode_item(p, item);
-        const int npl = c.lz + 2 * p.pad;
-        const int ngroups = (c.lz + p.NZ - 1) / p.NZ;
-        int ready = 0;
-        for (int g = 0; g < ngroups; ++g, ++gctr) {
-          const int nze = min(p.NZ, c.lz - g * p.NZ);
-          const uint32_t ab = gctr & 1;
-          mbar_wait(&acc_empty[ab], ((gctr >> 1) & 1) ^ 1);
-          const int need = min(npl, g * p.NZ + nze + 2 * p.pad);
-          for (; ready < need; ++ready) {
-            const uint32_t pc = pbase + ready;
-            mbar_wait(&plane_full[pc % p.nslot], (pc / p.nslot) & 1);
+    // The whole warp runs the loops (uniform control flow keeps addresses in uniform registers);
+    // one elected lane issues tcgen05.mma / tcgen05.commit.
+    const bool leader = elect_one();
+    if (lane < p.KS)
+      s_koff[lane] = (lane < p.KS0 ? lane * 2 * p.cg_pitch
+                                   : p.src1_off + (lane - p.KS0) * 2 * p.cg_pitch) >> 4;
+    __syncwarp();
+    const uint32_t a_hi = ((p.row_pitch >> 4) & 0x3FFFu) | (1u << 14);     // SBO | descriptor version
+    const uint32_t a_lbo = ((p.cg_pitch >> 4) & 0x3FFFu) << 16;
+    const uint32_t b_hi = (256u >> 4) | (1u << 14);
+    const uint32_t planes_enc = smem_u32(s_planes) >> 4;
+    const uint32_t slot_enc = p.slot_stride >> 4;
+    const uint32_t w_enc = (smem_u32(s_w) >> 4) | ((128u >> 4) << 16);
+    const uint32_t kstep_enc = p.kstep_bytes >> 4;
+    const uint32_t wchunk_enc = p.wchunk_bytes >> 4;
+    const uint32_t rowp_enc = p.row_pitch >> 4;
+    const bool stream_w = !p.w_resident;
+    uint32_t pbase = 0, wctr = 0, gctr = 0;
+    bool w_waited = false;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const ItemCoord c = decode_item(p, item);
+      const int npl = c.lz + 2 * p.pad;
+      const int ngroups = (c.lz + p.NZ - 1) / p.NZ;
+      int ready = 0;
+      for (int g = 0; g < ngroups; ++g, ++gctr) {
+        const int nze = min(p.NZ, c.lz - g * p.NZ);
+        const uint32_t ab = gctr & 1;
+        // ---- per-group MMA table.  Lane q owns window plane q, which feeds the accumulators
+        // zi = q - kd for kd in [kd_lo, kd_hi]: adjacent TMEM column blocks, and adjacent row
+        // blocks j = K-1-kd of the packed weight tile.  "first" entries (one per (q,kd) pair,
+        // accumulate = kd > 0) serve the very first k-step, where each accumulator's first
+        // touch must overwrite; "main" entries cover up to smax accumulators per instruction.
+        const int win = nze + 2 * p.pad;
+        int cnt = 0, kd_hi = 0, nruns = 0;
+        if (lane < win) {
+          const int kd_lo = max(0, lane - (nze - 1));
+          kd_hi = min(2 * p.pad, lane);
+          cnt = kd_hi - kd_lo + 1;
+          nruns = (cnt + p.smax - 1) / p.smax;
+        }
+        int sf = cnt, sm = nruns;  // inclusive scans
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int tf = __shfl_up_sync(0xffffffffu, sf, o), tm = __shfl_up_sync(0xffffffffu, sm, o);
+          if (lane >= o) { sf += tf; sm += tm; }
+        }
+        const int n_first = __shfl_sync(0xffffffffu, sf, 31), n_main = __shfl_sync(0xffffffffu, sm, 31);
+        if (lane < win) {
+          const uint32_t pc = pbase + g * p.NZ + lane;
+          const uint32_t a_q = (planes_enc + (pc % p.nslot) * slot_enc) | a_lbo;
+          const uint32_t acc0 = tmem_base + ab * p.NZ * p.N;
+          const uint32_t id1 = umma_idesc_bf16_f32(128, p.N);
+          for (int i = 0; i < cnt; ++i) {
+            const int kd = kd_hi - i, zi = lane - kd, j = p.K - 1 - kd;
+            s_tab[sf - cnt + i] = make_uint4(a_q, (uint32_t)(j * p.N * 2) | (kd > 0 ? 0x80000000u : 0u),
+                                             acc0 + zi * p.N, id1);
           }
-          tc_fence_after();
-          const bool stream_w = !p.w_resident;
-          int t = 0;
-          for (int kd = 0; kd < p.K; ++kd)
-            for (int kh = 0; kh < p.K; ++kh)
-              for (int kw = 0; kw < p.K; ++kw, ++t)
-                for (int kc = 0; kc < p.nkc; ++kc) {
-                  uint32_t wslot_i;
-                  if (stream_w) {
-                    wslot_i = wctr % p.wslot;
-                    mbar_wait(&w_full[wslot_i], (wctr / p.wslot) & 1);
-                    tc_fence_after();
-                  } else {
-                    wslot_i = t * p.nkc + kc;
-                    if (!w_waited) {
-                      mbar_wait(&w_full[wslot_i], 0);
-                      tc_fence_after();
-                    }
-                  }
-                  const uint32_t wb = w_addr + wslot_i * p.wchunk_bytes;
-                  const int ks_lo = kc * p.KC, ks_hi = min(p.KS, ks_lo + p.KC);
-                  for (int zi = 0; zi < nze; ++zi) {
-                    const uint32_t pc = pbase + g * p.NZ + zi + kd;
-                    const uint32_t abase = planes_addr + (pc % p.nslot) * p.slot_stride +
-                                           kh * p.row_pitch + kw * 16;
-                    const uint32_t dcol = tmem_base + (ab * p.NZ + zi) * p.N;
-                    for (int ks = ks_lo; ks < ks_hi; ++ks) {
-                      const uint32_t aoff = ks < p.KS0 ? ks * 2 * p.cg_pitch
-                                                       : p.src1_off + (ks - p.KS0) * 2 * p.cg_pitch;
-                      const uint64_t da = umma_desc_kmajor_noswz(abase + aoff, p.cg_pitch, p.row_pitch);
-                      const uint64_t db = umma_desc_kmajor_noswz(wb + (ks - ks_lo) * p.N * 32, 128, 256);
-                      umma_bf16(dcol, da, db, idesc, (t | ks) != 0);
-                    }
-                  }
-                  if (stream_w) {
-                    umma_commit(&w_empty[wslot_i]);
-                    ++wctr;
-                  }
+          for (int r = 0; r < nruns; ++r) {
+            const int z0 = lane - kd_hi + r * p.smax, j0 = p.K - 1 - kd_hi + r * p.smax;
+            const int ns = min(p.smax, cnt - r * p.smax);
+            s_tab[n_first + sm - nruns + r] =
+                make_uint4(a_q, (uint32_t)(j0 * p.N * 2) | 0x80000000u, acc0 + z0 * p.N,
+                           umma_idesc_bf16_f32(128, ns * p.N));
+          }
+        }
+        __syncwarp();
+        mbar_wait(&acc_empty[ab], ((gctr >> 1) & 1) ^ 1);
+        const int need = min(npl, g * p.NZ + nze + 2 * p.pad);
+        for (; ready < need; ++ready) {
+          const uint32_t pc = pbase + ready;
+          mbar_wait(&plane_full[pc % p.nslot], (pc / p.nslot) & 1);
+        }
+        tc_fence_after();
+        int t = 0;
+        for (int kh = 0; kh < p.K; ++kh)
+          for (int kw = 0; kw < p.K; ++kw, ++t) {
+            const uint32_t tapoff = kh * rowp_enc + kw;
+            for (int kc = 0; kc < p.nkc; ++kc) {
+              uint32_t wslot_i;
+              if (stream_w) {
+                wslot_i = wctr % p.wslot;
+                mbar_wait(&w_full[wslot_i], (wctr / p.wslot) & 1);
+                tc_fence_after();
+              } else {
+                wslot_i = t * p.nkc + kc;
+                if (!w_waited) {
+                  mbar_wait(&w_full[wslot_i], 0);
+                  tc_fence_after();
                 }
-          w_waited = true;
-          // planes that leave the window: the NZ oldest, or everything at the end of the item
-          const int rel_lo = g * p.NZ;
-          const int rel_hi = (g == ngroups - 1) ? npl : rel_lo + nze;
+              }
+              const uint32_t wb = w_enc + wslot_i * wchunk_enc;
+              const int ks_lo = kc * p.KC, ks_hi = min(p.KS, ks_lo + p.KC);
+              for (int ks = ks_lo; ks < ks_hi; ++ks) {
+                const uint32_t aoff = tapoff + s_koff[ks];
+                const uint32_t bks = wb + (ks - ks_lo) * kstep_enc;
+                const bool first = (t | ks) == 0;
+                const int e0 = first ? 0 : n_first, e1 = first ? n_first : n_first + n_main;
+#pragma unroll 4
+                for (int e = e0; e < e1; ++e) {
+                  const uint4 en = s_tab[e];
+                  if (leader)
+                    umma_bf16_lohi(en.z, en.x + aoff, a_hi, bks + (en.y & 0x7FFFFFFFu), b_hi, en.w,
+                                   en.y >> 31);
+                }
+              }
+              if (stream_w) {
+                if (leader) umma_commit(&w_empty[wslot_i]);
+                ++wctr;
+              }
+            }
+          }
+        w_waited = true;
+        // planes that leave the window: the NZ oldest, or everything at the end of the item
+        const int rel_lo = g * p.NZ;
+        const int rel_hi = (g == ngroups - 1) ? npl : rel_lo + nze;
+        if (leader) {
           for (int i = rel_lo; i < rel_hi; ++i) umma_commit(&plane_empty[(pbase + i) % p.nslot]);
           umma_commit(&acc_full[ab]);
         }
-        pbase += npl;
+        __syncwarp();  // s_tab is rewritten for the next group
       }
+      pbase += npl;
     }
   } else {
     // ===================================================================== epilogue (4 warps)
@@ -461,35 +529,44 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
 
   IgemmParams p{};
   p.B = a0.B; p.D = a0.D; p.H = a0.H; p.W = a0.W;
-  p.K = w.ksize; p.pad = (w.ksize - 1) / 2; p.taps = w.ksize * w.ksize * w.ksize;
+  p.K = w.ksize; p.pad = (w.ksize - 1) / 2; p.taps = w.ksize * w.ksize;
   p.cg0 = s0.cg; p.cg1 = s1.t ? s1.cg : 0;
   p.KS0 = p.cg0 / 2; p.KS = (p.cg0 + p.cg1) / 2;
+  FTB_CHECK(p.KS <= kMaxKS, "conv: more than 512 input channels");
   p.s0_cgtot = a0.cg(); p.s0_cgoff = s0.cgoff;
   p.s1_cgtot = s1.t ? s1.t->cg() : 0; p.s1_cgoff = s1.cgoff;
   p.N = w.n;
+  p.smax = 256 / p.N < 1 ? 1 : 256 / p.N;
   p.BW = 8 + 2 * p.pad;
   p.nWt = cdiv(a0.W, 8);
   p.row_pitch = p.BW * 16;
-  p.wtap_bytes = (uint32_t)p.KS * p.N * 32;
-  // weight ring unit: a chunk of KC k-steps of one tap, at most 24 KB
+  p.kstep_bytes = (uint32_t)p.K * p.N * 32;
+  p.wtap_bytes = (uint32_t)p.KS * p.kstep_bytes;
+  // weight ring unit: a chunk of KC k-steps of one (kh,kw) position (all depth taps), <= 24 KB
   p.KC = p.KS;
-  while (p.KC > 1 && (uint32_t)p.KC * p.N * 32 > 24 * 1024) --p.KC;
+  while (p.KC > 1 && (uint32_t)p.KC * p.kstep_bytes > 24 * 1024) --p.KC;
   p.nkc = cdiv(p.KS, p.KC);
-  p.wchunk_bytes = (uint32_t)p.KC * p.N * 32;
+  p.wchunk_bytes = (uint32_t)p.KC * p.kstep_bytes;
   const int nchunks = p.taps * p.nkc;
   const int sms = num_sms();
-  const uint32_t bar_bytes = (2 * kMaxSlots + 2 * kMaxWSlots + 4) * 8 + 16;
+  const uint32_t bar_bytes = (2 * kMaxSlots + 2 * kMaxWSlots + 4) * 8 + 16 + kMaxKS * 4 + kMaxEnt * 16;
   const size_t all_w = (size_t)p.taps * p.wtap_bytes;
-  const int win1 = 1 + 2 * p.pad;
 
-  // ---- tile height, tiling along D and ring sizing against the 227 KB shared-memory budget.
-  // The tile is 8 (W) x TH (H) voxels in the 128-row MMA; TH = 16 unless a plane window of that
-  // height does not fit (very wide inputs), then rows are traded for capacity.
+  // ---- tile height, planes per group (NZ) and ring sizing against the 227 KB shared-memory
+  // budget.  The tile is 8 (W) x TH (H) voxels in the 128-row MMA; TH = 16 unless a plane window
+  // of that height does not fit (very wide inputs), then rows are traded for capacity.  NZ output
+  // planes share one pass over the weights and one TMEM buffer (2 buffers x NZ x N <= 512
+  // columns); larger NZ means more depth-tap stacking per MMA and fewer weight passes.
   uint32_t slack = 0, fixed = 0;
   size_t w_region = 0;
-  int win = 0;
   bool fits = false;
-  for (int th = a0.H >= 16 ? 16 : a0.H; th >= 1; th = th / 2) {
+  int nz_cap = 512 / (2 * p.N);
+  if (nz_cap > 8) nz_cap = 8;
+  if (nz_cap > a0.D) nz_cap = a0.D;
+  if (p.K == 1 && nz_cap > 2) nz_cap = 2;
+  while (nz_cap > 1 && (nz_cap * p.K > kMaxEnt / 2 || nz_cap + 2 * p.pad > 32)) --nz_cap;
+  FTB_CHECK(nz_cap >= 1, "conv: N tile too wide for a double-buffered accumulator");
+  for (int th = a0.H >= 16 ? 16 : a0.H; th >= 1 && !fits; th = th / 2) {
     p.TH = th;
     p.BH = p.TH + 2 * p.pad;
     p.nHt = cdiv(a0.H, p.TH);
@@ -500,27 +577,26 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
     p.slot_stride = (uint32_t)round_up((int)plane_bytes, 128);
     slack = (uint32_t)(16 - p.TH + 2) * p.row_pitch + 512;  // A rows of a partial tile over-read
     fixed = slack + bar_bytes + 256;
-    p.w_resident = 0;
-    p.NZ = 1;
-    if (w.batch_stride == 0 && nchunks <= kMaxWSlots && p.nkc == 1 &&
-        all_w + (size_t)(win1 + 1) * p.slot_stride + fixed <= kSmemLimit) {
-      p.w_resident = 1;
-      p.wslot = nchunks;
-    } else {
-      p.wslot = nchunks == 1 ? 2 : (p.wchunk_bytes <= 8192 ? 6 : (p.wchunk_bytes <= 16384 ? 4 : 3));
-      // amortise the streamed weights over NZ output planes (one accumulator each)
-      int nz = 1;
-      while (nz < 4 && nz * 2 <= a0.D && 2 * (nz * 2) * p.N <= 512 &&
-             (size_t)p.wslot * p.wchunk_bytes + (size_t)(nz * 2 + 2 * p.pad + 1) * p.slot_stride + fixed <= kSmemLimit)
-        nz *= 2;
-      if (p.taps > 1) p.NZ = nz;
+    for (int nz = nz_cap; nz >= 1 && !fits; --nz) {
+      const size_t planes = (size_t)(nz + 2 * p.pad + 1) * p.slot_stride;  // window + 1 prefetch
+      p.NZ = nz;
+      if (w.batch_stride == 0 && nchunks <= kMaxWSlots && all_w + planes + fixed <= kSmemLimit) {
+        p.w_resident = 1;
+        p.wslot = nchunks;
+        fits = true;
+      } else {
+        p.w_resident = 0;
+        int ws = nchunks == 1 ? 2 : (p.wchunk_bytes <= 8192 ? 6 : (p.wchunk_bytes <= 16384 ? 4 : 3));
+        for (; ws >= 2 && !fits; --ws) {
+          p.wslot = ws;
+          if ((size_t)ws * p.wchunk_bytes + planes + fixed <= kSmemLimit) fits = true;
+        }
+      }
     }
-    w_region = (size_t)p.wslot * p.wchunk_bytes;
-    win = p.NZ + 2 * p.pad;
-    if (w_region + (size_t)(win + 1) * p.slot_stride + fixed <= kSmemLimit) { fits = true; break; }
     if (th == 1) break;
   }
   FTB_CHECK(fits, "conv: one plane window + weights exceed shared memory (Cin too large)");
+  w_region = (size_t)p.wslot * p.wchunk_bytes;
   const int cols = a0.B * p.nHt * p.nWt;
   int nslot = (int)((kSmemLimit - fixed - w_region) / p.slot_stride);
   nslot = nslot > kMaxSlots ? kMaxSlots : nslot;
@@ -584,7 +660,7 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
       const double cin = w.cin_real > 0 ? w.cin_real : w.cin;
       const double cout_all = w.cout_real > 0 ? w.cout_real : (double)w.n * w.ntiles;
       const double cout = cout_all / w.ntiles;
-      const double flops = 2.0 * vox * cin * cout * p.taps;
+      const double flops = 2.0 * vox * cin * cout * p.taps * p.K;
       const double bytes = vox * (cin + cout) * 2.0;  // read input once, write output once (bf16)
       prof = prof_begin(st, flops, bytes, w.ksize > 1 ? 0 : 1);
     }

@@ -55,8 +55,8 @@ __device__ void naive_chunk(const NaiveParams& p, int b, int d, int h, int w, in
 #pragma unroll
             for (int j = 0; j < 8; ++j) a[half * 8 + j] = f[j];
           }
-          // packed tile [N/8][2][8][8] for (t, ks)
-          const bf16* wt = wb + ((size_t)t * p.KS + ks) * p.N * 16;
+          // packed tile [N/8][2][8][8] for (kh, kw, ks, j = K-1-kd)
+          const bf16* wt = wb + ((((size_t)(kh * p.K + kw) * p.KS + ks) * p.K + (p.K - 1 - kd)) * p.N) * 16;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int n = c0 + j;
@@ -149,10 +149,11 @@ __global__ void conv_naive_kernel(const NaiveParams p) {
   }
 }
 
-// fp32 [Cout][Cin][k^3] -> bf16 [ntile][tap][ks][n/8][2][8][8]
-__global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int cin_real, int taps,
+// fp32 [Cout][Cin][kd][kh][kw] -> bf16 [ntile][kh][kw][ks][j = K-1-kd][n/8][2][8][8]
+__global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int cin_real, int K,
                                     int cin_pad, int n, int ntiles, const float* __restrict__ in_scale,
                                     bf16* __restrict__ dst) {
+  const int taps = K * K * K;
   const size_t total = (size_t)ntiles * taps * cin_pad * n;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
@@ -161,9 +162,11 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int c
     const int n8 = r % 8; r /= 8;
     const int kc = r % 2; r /= 2;
     const int ng = r % (n / 8); r /= (n / 8);
+    const int j = r % K; r /= K;
     const int ks = r % (cin_pad / 16); r /= (cin_pad / 16);
-    const int t = r % taps; r /= taps;
+    const int khw = r % (K * K); r /= (K * K);
     const int nt = (int)r;
+    const int t = (K - 1 - j) * K * K + khw;
     const int co = nt * n + ng * 8 + n8;
     const int ci = ks * 16 + kc * 8 + k8;
     float v = 0.f;
@@ -184,7 +187,7 @@ int pack_conv_weights(const float* w, int cout, int cin_real, int ksize, int cin
   const int taps = ksize * ksize * ksize;
   const size_t total = (size_t)ntiles * taps * cin_pad * ntile_n;
   const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  pack_weights_kernel<<<blocks, 256, 0, st>>>(w, cout, cin_real, taps, cin_pad, ntile_n, ntiles, in_scale, dst);
+  pack_weights_kernel<<<blocks, 256, 0, st>>>(w, cout, cin_real, ksize, cin_pad, ntile_n, ntiles, in_scale, dst);
   FTB_LAUNCH_OK();
   return 0;
 }

@@ -7,8 +7,9 @@ namespace ftb {
 typedef __nv_bfloat16 bf16;
 
 // ---------------------------------------------------------------- conv (implicit GEMM)
-// Packed weights: [ntile][tap][kstep][N/8][2][8][8] bf16 — per (tap,kstep) an N x 16 B-operand
-// tile in the no-swizzle K-major core-matrix layout (LBO = 128 B, SBO = 256 B).
+// Packed weights: [ntile][kh][kw][kstep][j][N/8][2][8][8] bf16, j = K-1-kd — per (kh,kw,kstep) a
+// (K*N) x 16 B-operand tile in the no-swizzle K-major core-matrix layout (LBO = 128 B,
+// SBO = 256 B) whose K row blocks are the depth taps in descending kd (depth-tap stacking).
 struct ConvWeights {
   const bf16* w = nullptr;
   int ksize = 1;        // 1, 3, 5, 7 (cubic, stride 1, "same" zero padding)
