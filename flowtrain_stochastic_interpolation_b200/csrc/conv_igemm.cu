@@ -35,7 +35,8 @@ namespace ftb {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // TMA warp | MMA warp | 8 epilogue warps
+constexpr int kMaxN = 256;
 constexpr int kMaxSlots = 12;
 constexpr int kMaxWSlots = 32;
 constexpr int kMaxEnt = 96;   // MMA table entries per group (first-step pairs + stacked runs)
@@ -65,8 +66,8 @@ struct IgemmParams {
   int out_cgtot, out_cgoff;
   float* out_f32;
   int out_f32_c;
-  const float *bias, *gs, *scale, *shift;
-  int film_stride;
+  const float *bias, *mul, *add;
+  int mul_stride, add_stride, norm;
   const bf16* resid;
   int resid_cgtot, resid_cgoff;
   const bf16* pre_src;
@@ -94,6 +95,231 @@ __device__ __forceinline__ ItemCoord decode_item(const IgemmParams& p, int item)
   return c;
 }
 
+
+// ------------------------------------------------------------------------------ epilogue helpers
+struct EpiCtx {
+  const float *bias, *mul, *add;   // shared memory, this half's copy for the current sample
+  bf16* out_b;                     // output base of sample b
+  const bf16* res_b;               // residual base of sample b (or null)
+  float* f32_b;                    // NCDHW fp32 output base of sample b (or null)
+  size_t cgs;                      // voxels per channel-group plane (D*H*W)
+  bool valid;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+
+// finish 16 consecutive channels [c0, c0+16) of one voxel: SiLU, + residual, store
+__device__ __forceinline__ void epi_store16(const IgemmParams& p, const EpiCtx& ec, int c0, size_t vox,
+                                            float (&v)[16]) {
+  if (p.flags & F_SILU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = silu_fast(v[j]);
+  }
+  if (!ec.valid) return;
+  if (ec.res_b) {
+    const bf16* rp = ec.res_b + ((size_t)(p.resid_cgoff + (c0 >> 3)) * ec.cgs + vox) * 8;
+    const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(rp));
+    const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(rp + ec.cgs * 8));
+    float f[8];
+    unpack_bf16x8(u0, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += f[j];
+    unpack_bf16x8(u1, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[8 + j] += f[j];
+  }
+  if (ec.f32_b) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (c0 + j < p.out_f32_c) ec.f32_b[(size_t)(c0 + j) * ec.cgs + vox] = v[j];
+    return;
+  }
+  bf16* dst = ec.out_b + ((size_t)(p.out_cgoff + (c0 >> 3)) * ec.cgs + vox) * 8;
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = v[j];
+  *reinterpret_cast<uint4*>(dst) = pack_bf16x8(f);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = v[8 + j];
+  *reinterpret_cast<uint4*>(dst + ec.cgs * 8) = pack_bf16x8(f);
+}
+
+// y = (acc * rs) * mul + add'   (no norm; bias already folded into add')
+__device__ __forceinline__ void epi_affine(const IgemmParams& p, const EpiCtx& ec, uint32_t trow,
+                                           size_t vox, float rs) {
+  for (int c0 = 0; c0 < p.N; c0 += 32) {
+    uint32_t r0[16], r1[16];
+    const bool two = c0 + 16 < p.N;
+    tmem_ld16(trow + c0, r0);
+    if (two) tmem_ld16(trow + c0 + 16, r1);
+    tmem_ld_wait();
+    float v[16];
+#pragma unroll
+    for (int j4 = 0; j4 < 16; j4 += 4) {
+      const float4 mu = *reinterpret_cast<const float4*>(ec.mul + c0 + j4);
+      const float4 ad = *reinterpret_cast<const float4*>(ec.add + c0 + j4);
+      v[j4 + 0] = fmaf(__uint_as_float(r0[j4 + 0]) * rs, mu.x, ad.x);
+      v[j4 + 1] = fmaf(__uint_as_float(r0[j4 + 1]) * rs, mu.y, ad.y);
+      v[j4 + 2] = fmaf(__uint_as_float(r0[j4 + 2]) * rs, mu.z, ad.z);
+      v[j4 + 3] = fmaf(__uint_as_float(r0[j4 + 3]) * rs, mu.w, ad.w);
+    }
+    epi_store16(p, ec, c0, vox, v);
+    if (two) {
+#pragma unroll
+      for (int j4 = 0; j4 < 16; j4 += 4) {
+        const float4 mu = *reinterpret_cast<const float4*>(ec.mul + c0 + 16 + j4);
+        const float4 ad = *reinterpret_cast<const float4*>(ec.add + c0 + 16 + j4);
+        v[j4 + 0] = fmaf(__uint_as_float(r1[j4 + 0]) * rs, mu.x, ad.x);
+        v[j4 + 1] = fmaf(__uint_as_float(r1[j4 + 1]) * rs, mu.y, ad.y);
+        v[j4 + 2] = fmaf(__uint_as_float(r1[j4 + 2]) * rs, mu.z, ad.z);
+        v[j4 + 3] = fmaf(__uint_as_float(r1[j4 + 3]) * rs, mu.w, ad.w);
+      }
+      epi_store16(p, ec, c0 + 16, vox, v);
+    }
+  }
+}
+
+// channel RMSNorm (unet_attn_3d.py:127-128) with the whole voxel row held in registers:
+// v = acc*rs + bias; y = v / max(||v||, 1e-12) * mul + add
+template <int NCH>
+__device__ __forceinline__ void epi_norm_regs(const IgemmParams& p, const EpiCtx& ec, uint32_t trow,
+                                              size_t vox, float rs) {
+  uint32_t r[NCH][16];
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) tmem_ld16(trow + ch * 16, r[ch]);
+  tmem_ld_wait();
+  float ss[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+    for (int j4 = 0; j4 < 16; j4 += 4) {
+      const float4 bi = *reinterpret_cast<const float4*>(ec.bias + ch * 16 + j4);
+      const float a0 = fmaf(__uint_as_float(r[ch][j4 + 0]), rs, bi.x);
+      const float a1 = fmaf(__uint_as_float(r[ch][j4 + 1]), rs, bi.y);
+      const float a2 = fmaf(__uint_as_float(r[ch][j4 + 2]), rs, bi.z);
+      const float a3 = fmaf(__uint_as_float(r[ch][j4 + 3]), rs, bi.w);
+      ss[0] = fmaf(a0, a0, ss[0]); ss[1] = fmaf(a1, a1, ss[1]);
+      ss[2] = fmaf(a2, a2, ss[2]); ss[3] = fmaf(a3, a3, ss[3]);
+      r[ch][j4 + 0] = __float_as_uint(a0); r[ch][j4 + 1] = __float_as_uint(a1);
+      r[ch][j4 + 2] = __float_as_uint(a2); r[ch][j4 + 3] = __float_as_uint(a3);
+    }
+  const float rinv = 1.f / fmaxf(sqrtf((ss[0] + ss[1]) + (ss[2] + ss[3])), 1e-12f);
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    float v[16];
+#pragma unroll
+    for (int j4 = 0; j4 < 16; j4 += 4) {
+      const float4 mu = *reinterpret_cast<const float4*>(ec.mul + ch * 16 + j4);
+      const float4 ad = *reinterpret_cast<const float4*>(ec.add + ch * 16 + j4);
+      v[j4 + 0] = fmaf(__uint_as_float(r[ch][j4 + 0]) * rinv, mu.x, ad.x);
+      v[j4 + 1] = fmaf(__uint_as_float(r[ch][j4 + 1]) * rinv, mu.y, ad.y);
+      v[j4 + 2] = fmaf(__uint_as_float(r[ch][j4 + 2]) * rinv, mu.z, ad.z);
+      v[j4 + 3] = fmaf(__uint_as_float(r[ch][j4 + 3]) * rinv, mu.w, ad.w);
+    }
+    epi_store16(p, ec, ch * 16, vox, v);
+  }
+}
+
+// same, any N: one TMEM pass for the norm, a second for the output
+__device__ __forceinline__ void epi_norm_2pass(const IgemmParams& p, const EpiCtx& ec, uint32_t trow,
+                                               size_t vox, float rs) {
+  float ss[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c0 = 0; c0 < p.N; c0 += 32) {
+    uint32_t r0[16], r1[16];
+    const bool two = c0 + 16 < p.N;
+    tmem_ld16(trow + c0, r0);
+    if (two) tmem_ld16(trow + c0 + 16, r1);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j4 = 0; j4 < 16; j4 += 4) {
+      const float4 bi = *reinterpret_cast<const float4*>(ec.bias + c0 + j4);
+      const float a0 = fmaf(__uint_as_float(r0[j4 + 0]), rs, bi.x);
+      const float a1 = fmaf(__uint_as_float(r0[j4 + 1]), rs, bi.y);
+      const float a2 = fmaf(__uint_as_float(r0[j4 + 2]), rs, bi.z);
+      const float a3 = fmaf(__uint_as_float(r0[j4 + 3]), rs, bi.w);
+      ss[0] = fmaf(a0, a0, ss[0]); ss[1] = fmaf(a1, a1, ss[1]);
+      ss[2] = fmaf(a2, a2, ss[2]); ss[3] = fmaf(a3, a3, ss[3]);
+    }
+    if (two) {
+#pragma unroll
+      for (int j4 = 0; j4 < 16; j4 += 4) {
+        const float4 bi = *reinterpret_cast<const float4*>(ec.bias + c0 + 16 + j4);
+        const float a0 = fmaf(__uint_as_float(r1[j4 + 0]), rs, bi.x);
+        const float a1 = fmaf(__uint_as_float(r1[j4 + 1]), rs, bi.y);
+        const float a2 = fmaf(__uint_as_float(r1[j4 + 2]), rs, bi.z);
+        const float a3 = fmaf(__uint_as_float(r1[j4 + 3]), rs, bi.w);
+        ss[0] = fmaf(a0, a0, ss[0]); ss[1] = fmaf(a1, a1, ss[1]);
+        ss[2] = fmaf(a2, a2, ss[2]); ss[3] = fmaf(a3, a3, ss[3]);
+      }
+    }
+  }
+  const float rinv = 1.f / fmaxf(sqrtf((ss[0] + ss[1]) + (ss[2] + ss[3])), 1e-12f);
+  for (int c0 = 0; c0 < p.N; c0 += 16) {
+    uint32_t r0[16];
+    tmem_ld16(trow + c0, r0);
+    tmem_ld_wait();
+    float v[16];
+#pragma unroll
+    for (int j4 = 0; j4 < 16; j4 += 4) {
+      const float4 bi = *reinterpret_cast<const float4*>(ec.bias + c0 + j4);
+      const float4 mu = *reinterpret_cast<const float4*>(ec.mul + c0 + j4);
+      const float4 ad = *reinterpret_cast<const float4*>(ec.add + c0 + j4);
+      v[j4 + 0] = fmaf(fmaf(__uint_as_float(r0[j4 + 0]), rs, bi.x) * rinv, mu.x, ad.x);
+      v[j4 + 1] = fmaf(fmaf(__uint_as_float(r0[j4 + 1]), rs, bi.y) * rinv, mu.y, ad.y);
+      v[j4 + 2] = fmaf(fmaf(__uint_as_float(r0[j4 + 2]), rs, bi.z) * rinv, mu.z, ad.z);
+      v[j4 + 3] = fmaf(fmaf(__uint_as_float(r0[j4 + 3]), rs, bi.w) * rinv, mu.w, ad.w);
+    }
+    epi_store16(p, ec, c0, vox, v);
+  }
+}
+
+// LinearAttention q: softmax over each dim_head group of this voxel, times dim_head^-0.5
+// (unet_attn_3d.py:326,:329); no bias / affine on this path
+template <int DH>
+__device__ __forceinline__ void epi_qsoftmax(const IgemmParams& p, const EpiCtx& ec, uint32_t trow,
+                                             size_t vox, float rs) {
+  for (int hd = 0; hd < p.N / DH; ++hd) {
+    uint32_t r[DH / 16][16];
+#pragma unroll
+    for (int ch = 0; ch < DH / 16; ++ch) tmem_ld16(trow + hd * DH + ch * 16, r[ch]);
+    tmem_ld_wait();
+    float mx = -INFINITY;
+#pragma unroll
+    for (int ch = 0; ch < DH / 16; ++ch)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float v = __uint_as_float(r[ch][j]) * rs;
+        r[ch][j] = __float_as_uint(v);
+        mx = fmaxf(mx, v);
+      }
+    float sum = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < DH / 16; ++ch)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float e = __expf(__uint_as_float(r[ch][j]) - mx);
+        r[ch][j] = __float_as_uint(e);
+        sum += e;
+      }
+    const float inv = __fdividef(p.q_scale, sum);
+    if (ec.valid) {
+#pragma unroll
+      for (int ch = 0; ch < DH / 16; ++ch)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[ch][hf * 8 + j]) * inv;
+          const int cg = p.out_cgoff + ((hd * DH + ch * 16) >> 3) + hf;
+          *reinterpret_cast<uint4*>(ec.out_b + ((size_t)cg * ec.cgs + vox) * 8) = pack_bf16x8(f);
+        }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                   const IgemmParams p) {
@@ -111,6 +337,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
   uint32_t* s_koff = tmem_ptr + 4;                                   // [kMaxKS]
   uint4* s_tab = reinterpret_cast<uint4*>(s_koff + kMaxKS);          // [kMaxEnt]
+  float* s_par = reinterpret_cast<float*>(s_tab + kMaxEnt);          // [2 halves][bias|mul|add][kMaxN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -126,7 +353,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);
+      mbar_init(&acc_empty[i], 8);
     }
     fence_barrier_init();
     prefetch_tmap(&tm0);
@@ -312,152 +539,80 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
       pbase += npl;
     }
   } else {
-    // ===================================================================== epilogue (4 warps)
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    // ===================================================================== epilogue (8 warps)
+    // Two halves of four warps; a warp may only touch the TMEM lane quadrant (warp % 4), so the
+    // halves split a group's planes between them (alternating) and both see every accumulator.
+    // Thread m of a quadrant set owns voxel row m of the tile: the channel reduction of the
+    // RMSNorm is thread-local.  Per-channel parameters of the current sample sit in shared
+    // memory (one copy per half), so the inner loops are LDS.128 + FMA only.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int tid_h = (((warp - 2) & 3) << 5) | lane;  // 0..127 within the half
     const int m = q * 32 + lane;
     const int hl = m >> 3, wl = m & 7;
     const size_t plane_vox = (size_t)p.H * p.W;
+    const size_t cgs = (size_t)p.D * plane_vox;
+    float* par = s_par + half * 3 * kMaxN;
+    EpiCtx ec;
+    ec.bias = par; ec.mul = par + kMaxN; ec.add = par + 2 * kMaxN;
+    ec.cgs = cgs;
     uint32_t gctr = 0;
+    int cur_b = -1;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const ItemCoord c = decode_item(p, item);
       const int ngroups = (c.lz + p.NZ - 1) / p.NZ;
       const int h = c.h0 + hl, w = c.w0 + wl;
-      const bool valid = (hl < p.TH) && (h < p.H) && (w < p.W);
-      const float* scale = p.scale ? p.scale + (size_t)c.b * p.film_stride : nullptr;
-      const float* shift = p.shift ? p.shift + (size_t)c.b * p.film_stride : nullptr;
+      ec.valid = (hl < p.TH) && (h < p.H) && (w < p.W);
+      if (c.b != cur_b) {
+        // (bias, mul, add) of sample b; without a norm the bias folds into the affine part
+        named_bar_sync(1 + half, 128);
+        for (int ch = tid_h; ch < p.N; ch += 128) {
+          float bi = p.bias ? __ldg(p.bias + ch) : 0.f;
+          const float mu = p.mul ? __ldg(p.mul + (size_t)c.b * p.mul_stride + ch) : 1.f;
+          float ad = p.add ? __ldg(p.add + (size_t)c.b * p.add_stride + ch) : 0.f;
+          if (!p.norm) { ad = fmaf(bi, mu, ad); bi = 0.f; }
+          par[ch] = bi; par[kMaxN + ch] = mu; par[2 * kMaxN + ch] = ad;
+        }
+        named_bar_sync(1 + half, 128);
+        cur_b = c.b;
+      }
+      ec.out_b = p.out + (size_t)c.b * p.out_cgtot * cgs * 8;
+      ec.res_b = p.resid ? p.resid + (size_t)c.b * p.resid_cgtot * cgs * 8 : nullptr;
+      ec.f32_b = p.out_f32 ? p.out_f32 + (size_t)c.b * p.out_f32_c * cgs : nullptr;
       for (int g = 0; g < ngroups; ++g, ++gctr) {
         const int nze = min(p.NZ, c.lz - g * p.NZ);
         const uint32_t ab = gctr & 1;
         mbar_wait(&acc_full[ab], (gctr >> 1) & 1);
         tc_fence_after();
-        for (int zi = 0; zi < nze; ++zi) {
+        for (int zi = (half + g) & 1; zi < nze; zi += 2) {
           const int d = c.d0 + g * p.NZ + zi;
           const size_t vox = (size_t)d * plane_vox + (size_t)h * p.W + w;  // within one (b, cg)
           const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (ab * p.NZ + zi) * p.N;
           float rs = 1.f;
-          if (p.pre_src && valid) {
-            float ss = 0.f;
-            const size_t cgs = (size_t)p.D * plane_vox;
+          if (p.pre_src && ec.valid) {
+            // fused pre-attention RMSNorm: 1 / max(||x||_2, 1e-12) of this voxel of the input
             const bf16* src = p.pre_src + (((size_t)c.b * p.pre_cgtot + p.pre_cgoff) * cgs + vox) * 8;
-            for (int cgi = 0; cgi < p.pre_cg; ++cgi) {
-              float f[8];
-              unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(src + (size_t)cgi * cgs * 8)), f);
+            float ss0 = 0.f, ss1 = 0.f;
+            for (int cgi = 0; cgi < p.pre_cg; cgi += 2) {
+              float f[8], g8[8];
+              const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(src + (size_t)cgi * cgs * 8));
+              const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(cgi + 1) * cgs * 8));
+              unpack_bf16x8(u0, f);
+              unpack_bf16x8(u1, g8);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+              for (int j = 0; j < 8; ++j) { ss0 = fmaf(f[j], f[j], ss0); ss1 = fmaf(g8[j], g8[j], ss1); }
             }
-            rs = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+            rs = 1.f / fmaxf(sqrtf(ss0 + ss1), 1e-12f);
           }
-          __syncwarp();
-          float rinv = 1.f;
-          if (p.gs) {
-            float ss = 0.f;
-            for (int c0 = 0; c0 < p.N; c0 += 16) {
-              uint32_t r[16];
-              tmem_ld16(trow + c0, r);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                float v = __uint_as_float(r[j]) * rs + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
-                ss += v * v;
-              }
-            }
-            rinv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-          }
-          const size_t cgs = (size_t)p.D * plane_vox;
           if (p.flags & F_QSOFTMAX) {
-            // softmax over each dim_head group of this voxel's q, times dim_head^-0.5 (:326,:329)
-            const int nch = p.q_dh >> 4;
-            for (int hd = 0; hd < p.N / p.q_dh; ++hd) {
-              float v[64];
-              float mx = -INFINITY;
-#pragma unroll
-              for (int ch = 0; ch < 4; ++ch) {
-                if (ch < nch) {
-                  uint32_t r[16];
-                  tmem_ld16(trow + hd * p.q_dh + ch * 16, r);
-                  tmem_ld_wait();
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) {
-                    v[ch * 16 + j] = __uint_as_float(r[j]) * rs;
-                    mx = fmaxf(mx, v[ch * 16 + j]);
-                  }
-                }
-              }
-              float sum = 0.f;
-#pragma unroll
-              for (int ch = 0; ch < 4; ++ch)
-                if (ch < nch) {
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) {
-                    v[ch * 16 + j] = __expf(v[ch * 16 + j] - mx);
-                    sum += v[ch * 16 + j];
-                  }
-                }
-              const float inv = p.q_scale / sum;
-              if (valid) {
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch)
-                  if (ch < nch) {
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                      float f[8];
-#pragma unroll
-                      for (int j = 0; j < 8; ++j) f[j] = v[ch * 16 + half * 8 + j] * inv;
-                      const int cg = p.out_cgoff + ((hd * p.q_dh + ch * 16) >> 3) + half;
-                      bf16* dst = p.out + (((size_t)c.b * p.out_cgtot + cg) * cgs + vox) * 8;
-                      *reinterpret_cast<uint4*>(dst) = pack_bf16x8(f);
-                    }
-                  }
-              }
-              __syncwarp();
-            }
-            continue;
-          }
-          for (int c0 = 0; c0 < p.N; c0 += 16) {
-            uint32_t r[16];
-            tmem_ld16(trow + c0, r);
-            tmem_ld_wait();
-            float v[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float x = __uint_as_float(r[j]) * rs + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
-              if (p.gs) x = x * rinv * __ldg(p.gs + c0 + j);
-              if (scale) x = x * (__ldg(scale + c0 + j) + 1.f) + __ldg(shift + c0 + j);
-              if (p.flags & F_SILU) x = silu_f(x);
-              v[j] = x;
-            }
-            if (valid) {
-            if (p.resid) {
-#pragma unroll
-              for (int half = 0; half < 2; ++half) {
-                const int cg = p.resid_cgoff + (c0 >> 3) + half;
-                const bf16* rp = p.resid + (((size_t)c.b * p.resid_cgtot + cg) * cgs + vox) * 8;
-                float f[8];
-                unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(rp)), f);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[half * 8 + j] += f[j];
-              }
-            }
-            if (p.out_f32) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int ch = c0 + j;
-                if (ch < p.out_f32_c)
-                  p.out_f32[((size_t)c.b * p.out_f32_c + ch) * cgs + vox] = v[j];
-              }
-            } else {
-#pragma unroll
-              for (int half = 0; half < 2; ++half) {
-                float f[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = v[half * 8 + j];
-                const int cg = p.out_cgoff + (c0 >> 3) + half;
-                bf16* dst = p.out + (((size_t)c.b * p.out_cgtot + cg) * cgs + vox) * 8;
-                *reinterpret_cast<uint4*>(dst) = pack_bf16x8(f);
-              }
-            }
-            }  // valid
-            __syncwarp();
+            if (p.q_dh == 32) epi_qsoftmax<32>(p, ec, trow, vox, rs);
+            else epi_qsoftmax<16>(p, ec, trow, vox, rs);
+          } else if (p.norm) {
+            if (p.N == 48) epi_norm_regs<3>(p, ec, trow, vox, rs);
+            else if (p.N == 96) epi_norm_regs<6>(p, ec, trow, vox, rs);
+            else epi_norm_2pass(p, ec, trow, vox, rs);
+          } else {
+            epi_affine(p, ec, trow, vox, rs);
           }
         }
         tc_fence_before();
@@ -524,8 +679,8 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   FTB_CHECK(w.ksize == 1 || w.ksize == 3 || w.ksize == 5 || w.ksize == 7, "conv: ksize");
   FTB_CHECK(out.B == a0.B && out.D == a0.D && out.H == a0.H && out.W == a0.W, "conv: out dims");
   if (s1.t) FTB_CHECK(s1.t->B == a0.B && s1.t->D == a0.D && s1.t->H == a0.H && s1.t->W == a0.W, "conv: src1 dims");
-  FTB_CHECK(!e.q_softmax_heads || (e.q_dim_head % 16 == 0 && e.q_dim_head <= 64 && w.n % e.q_dim_head == 0),
-            "conv: q softmax needs dim_head in {16,32,48,64} dividing N");
+  FTB_CHECK(!e.q_softmax_heads || ((e.q_dim_head == 16 || e.q_dim_head == 32) && w.n % e.q_dim_head == 0),
+            "conv: q softmax needs dim_head 16 or 32 dividing N");
 
   IgemmParams p{};
   p.B = a0.B; p.D = a0.D; p.H = a0.H; p.W = a0.W;
@@ -549,7 +704,8 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   p.wchunk_bytes = (uint32_t)p.KC * p.kstep_bytes;
   const int nchunks = p.taps * p.nkc;
   const int sms = num_sms();
-  const uint32_t bar_bytes = (2 * kMaxSlots + 2 * kMaxWSlots + 4) * 8 + 16 + kMaxKS * 4 + kMaxEnt * 16;
+  const uint32_t bar_bytes =
+      (2 * kMaxSlots + 2 * kMaxWSlots + 4) * 8 + 16 + kMaxKS * 4 + kMaxEnt * 16 + 2 * 3 * kMaxN * 4;
   const size_t all_w = (size_t)p.taps * p.wtap_bytes;
 
   // ---- tile height, planes per group (NZ) and ring sizing against the 227 KB shared-memory
@@ -630,7 +786,8 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   p.w_batch_stride = w.batch_stride;
   p.out = out.p; p.out_cgtot = out.cg();
   p.out_f32 = e.out_f32; p.out_f32_c = e.out_f32_c;
-  p.gs = e.gs; p.scale = e.scale; p.shift = e.shift; p.film_stride = e.film_stride;
+  p.norm = e.norm ? 1 : 0;
+  p.mul = e.mul; p.add = e.add; p.mul_stride = e.mul_stride; p.add_stride = e.add_stride;
   p.resid = e.resid ? e.resid->p : nullptr;
   p.resid_cgtot = e.resid ? e.resid->cg() : 0; p.resid_cgoff = e.resid_cgoff;
   if (e.prenorm) { p.pre_src = a0.p; p.pre_cgtot = a0.cg(); p.pre_cgoff = s0.cgoff; p.pre_cg = s0.cg; }

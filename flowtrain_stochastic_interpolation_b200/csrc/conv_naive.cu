@@ -21,8 +21,8 @@ struct NaiveParams {
   int out_cgtot, out_cgoff;
   float* out_f32;
   int out_f32_c;
-  const float *bias, *gs, *scale, *shift;
-  int film_stride;
+  const float *bias, *mul, *add;
+  int mul_stride, add_stride, norm;
   const bf16* resid;
   int resid_cgtot, resid_cgoff;
   int prenorm, silu, qsoftmax, q_dh;
@@ -96,7 +96,7 @@ __global__ void conv_naive_kernel(const NaiveParams p) {
   }
   float acc[16];
   float rinv = 1.f;
-  if (p.gs) {
+  if (p.norm) {
     float ss = 0.f;
     for (int c0 = 0; c0 < p.N; c0 += 16) {
       naive_chunk(p, b, d, h, w, c0, acc);
@@ -126,15 +126,16 @@ __global__ void conv_naive_kernel(const NaiveParams p) {
     }
     return;
   }
-  const float* scale = p.scale ? p.scale + (size_t)b * p.film_stride : nullptr;
-  const float* shift = p.shift ? p.shift + (size_t)b * p.film_stride : nullptr;
+  const float* mul = p.mul ? p.mul + (size_t)b * p.mul_stride : nullptr;
+  const float* add = p.add ? p.add + (size_t)b * p.add_stride : nullptr;
   for (int c0 = 0; c0 < p.N; c0 += 16) {
     naive_chunk(p, b, d, h, w, c0, acc);
     for (int j = 0; j < 16; ++j) {
       const int ch = c0 + j;
       float x = acc[j] * rs + (p.bias ? p.bias[ch] : 0.f);
-      if (p.gs) x = x * rinv * p.gs[ch];
-      if (scale) x = x * (scale[ch] + 1.f) + shift[ch];
+      x *= rinv;
+      if (mul) x *= mul[ch];
+      if (add) x += add[ch];
       if (p.silu) x = silu_f(x);
       if (p.resid)
         x += __bfloat162float(
@@ -206,7 +207,7 @@ int conv_naive(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   p.w_batch_stride = w.batch_stride;
   p.out = out.p; p.out_cgtot = out.cg();
   p.out_f32 = e.out_f32; p.out_f32_c = e.out_f32_c;
-  p.gs = e.gs; p.scale = e.scale; p.shift = e.shift; p.film_stride = e.film_stride;
+  p.norm = e.norm; p.mul = e.mul; p.add = e.add; p.mul_stride = e.mul_stride; p.add_stride = e.add_stride;
   p.resid = e.resid ? e.resid->p : nullptr;
   p.resid_cgtot = e.resid ? e.resid->cg() : 0; p.resid_cgoff = e.resid_cgoff;
   p.prenorm = e.prenorm; p.silu = e.silu; p.q_dh = e.q_dim_head; p.q_scale = e.q_scale;

@@ -141,6 +141,7 @@ struct ftb_unet {
   int film_rows = 0;
   const float** d_film_w = nullptr;
   const float** d_film_b = nullptr;
+  const float** d_film_gs = nullptr;
   int* d_film_off = nullptr;
   bool dirty = true;
   bool on_device = false;
@@ -322,17 +323,20 @@ int ensure_device(ftb_unet* U) {
   FTB_TRY(dev_alloc(U, &U->d_film_w, (size_t)nb));
   FTB_TRY(dev_alloc(U, &U->d_film_b, (size_t)nb));
   FTB_TRY(dev_alloc(U, &U->d_film_off, (size_t)nb + 1));
-  std::vector<const float*> hw(nb), hb(nb);
+  FTB_TRY(dev_alloc(U, &U->d_film_gs, (size_t)nb));
+  std::vector<const float*> hw(nb), hb(nb), hg(nb);
   std::vector<int> ho(nb + 1);
   for (int i = 0; i < nb; ++i) {
     hw[i] = U->params[U->pindex[U->film_blocks[i] + ".mlp.1.weight"]].dev;
     hb[i] = U->params[U->pindex[U->film_blocks[i] + ".mlp.1.bias"]].dev;
     ho[i] = U->film_off[U->film_blocks[i]];
+    hg[i] = U->gains.at(U->film_blocks[i] + ".block1.norm.g").gs;
   }
   ho[nb] = U->film_rows;
   FTB_CUDA(cudaMemcpy(U->d_film_w, hw.data(), nb * sizeof(float*), cudaMemcpyHostToDevice));
   FTB_CUDA(cudaMemcpy(U->d_film_b, hb.data(), nb * sizeof(float*), cudaMemcpyHostToDevice));
   FTB_CUDA(cudaMemcpy(U->d_film_off, ho.data(), (nb + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  FTB_CUDA(cudaMemcpy(U->d_film_gs, hg.data(), nb * sizeof(float*), cudaMemcpyHostToDevice));
   U->on_device = true;
   return 0;
 }
@@ -340,6 +344,17 @@ int ensure_device(ftb_unet* U) {
 __global__ void scale_vec_kernel(const float* g, float mul, float* out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = g[i] * mul;
+}
+
+__global__ void test_affine_kernel(const float* g, const float* scale, const float* shift, float sqrt_c,
+                                   int B, int C, int stride, float* mul, float* add) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i % C;
+  float m = g ? g[c] * sqrt_c : 1.f;
+  if (scale) m *= scale[i] + 1.f;
+  mul[(size_t)b * stride + c] = m;
+  add[(size_t)b * stride + c] = shift ? shift[i] : 0.f;
 }
 
 int finalize(ftb_unet* U, cudaStream_t st) {
@@ -420,8 +435,10 @@ struct Fwd {
     const float* film_p = film ? film + U->film_off.at(p) : nullptr;
     Act h1 = act(cout, a.D, a.H, a.W);
     ConvEpilogue e1;
-    e1.gs = U->gains.at(p + ".block1.norm.g").gs;
-    e1.scale = film_p; e1.shift = film_p ? film_p + cout : nullptr; e1.film_stride = U->film_rows;
+    // Block1: RMSNorm gain and FiLM (scale+1) arrive pre-multiplied from film_mlps
+    e1.norm = true;
+    e1.mul = film_p; e1.mul_stride = U->film_rows;
+    e1.add = film_p ? film_p + cout : nullptr; e1.add_stride = U->film_rows;
     e1.silu = true;
     FTB_TRY(conv(p + ".block1.proj", s0, s1, e1, h1));
     tap(p + ".block1", h1);
@@ -434,7 +451,8 @@ struct Fwd {
     }
     *out = act(cout, a.D, a.H, a.W);
     ConvEpilogue e2;
-    e2.gs = U->gains.at(p + ".block2.norm.g").gs;
+    e2.norm = true;
+    e2.mul = U->gains.at(p + ".block2.norm.g").gs;
     e2.silu = true;
     e2.resid = resp;
     FTB_TRY(conv(p + ".block2.proj", ConvSrc{&h1, 0, h1.cg()}, ConvSrc{}, e2, *out));
@@ -479,7 +497,8 @@ struct Fwd {
         w.batch_stride = (long long)x.C * hd;
         ConvEpilogue eo;
         eo.bias = pdev(p + ".to_out.0.bias");
-        eo.gs = U->gains.at(p + ".to_out.1.g").gs;
+        eo.norm = true;
+        eo.mul = U->gains.at(p + ".to_out.1.g").gs;
         eo.resid = &x;
         FTB_TRY(conv_dispatch(ConvSrc{&qkv, 0, hd / 8}, ConvSrc{}, w, eo, *out, 0, st));
         U->launches += 1;
@@ -511,8 +530,8 @@ struct Fwd {
                        pdev("time_mlp.1.bias"), pdev("time_mlp.3.weight"), pdev("time_mlp.3.bias"),
                        c.time_resolution, U->time_dim};
       FTB_TRY(time_embed(tp, t, B, temb, temb_silu, st));
-      FilmTable ft{U->d_film_w, U->d_film_b, U->d_film_off, (int)U->film_blocks.size(), U->film_rows,
-                   U->time_dim};
+      FilmTable ft{U->d_film_w, U->d_film_b, U->d_film_gs, U->d_film_off, (int)U->film_blocks.size(),
+                   U->film_rows, U->time_dim};
       FTB_TRY(film_mlps(ft, temb_silu, B, film, st));
       FTB_TRY(pack_ncdhw_to_blocked(x, B, c.data_channels, X, Y, Z, xin, st));
       U->launches += 3;
@@ -805,24 +824,20 @@ int ftb_test_conv3d(const float* x, int c1, const float* x2, int c2, const float
   cw.w = packed; cw.ksize = ksize; cw.cin = cin_pad; cw.n = n_tile; cw.ntiles = ntiles;
   ConvEpilogue e;
   e.bias = bias_p;
-  if (g) {
-    FTB_CHECK(ntiles == 1, "norm needs a single N tile");
-    FTB_CUDA(cudaMemsetAsync(gs, 0, n_tile * sizeof(float), st));
-    scale_vec_kernel<<<cdiv(cout, 128), 128, 0, st>>>(g, sqrtf((float)cout), gs, cout);
-    e.gs = gs;
-  }
-  float *sc_p = nullptr, *sh_p = nullptr;
-  if (scale && shift) {
-    sc_p = S.get<float>((size_t)B * n_tile * ntiles);
-    sh_p = S.get<float>((size_t)B * n_tile * ntiles);
-    FTB_CHECK(sc_p && sh_p, "scratch allocation failed");
-    FTB_CUDA(cudaMemsetAsync(sc_p, 0, (size_t)B * n_tile * ntiles * sizeof(float), st));
-    FTB_CUDA(cudaMemsetAsync(sh_p, 0, (size_t)B * n_tile * ntiles * sizeof(float), st));
-    FTB_CUDA(cudaMemcpy2DAsync(sc_p, (size_t)n_tile * ntiles * sizeof(float), scale, cout * sizeof(float),
-                               cout * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
-    FTB_CUDA(cudaMemcpy2DAsync(sh_p, (size_t)n_tile * ntiles * sizeof(float), shift, cout * sizeof(float),
-                               cout * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
-    e.scale = sc_p; e.shift = sh_p; e.film_stride = n_tile * ntiles;
+  float *mul_p = nullptr, *add_p = nullptr;
+  const int pstride = n_tile * ntiles;
+  if (g) FTB_CHECK(ntiles == 1, "norm needs a single N tile");
+  if (g || (scale && shift)) {
+    // mul[b][c] = g[c]*sqrt(C) * (scale[b][c] + 1), add[b][c] = shift[b][c]
+    mul_p = S.get<float>((size_t)B * pstride);
+    add_p = S.get<float>((size_t)B * pstride);
+    FTB_CHECK(mul_p && add_p, "scratch allocation failed");
+    FTB_CUDA(cudaMemsetAsync(mul_p, 0, (size_t)B * pstride * sizeof(float), st));
+    FTB_CUDA(cudaMemsetAsync(add_p, 0, (size_t)B * pstride * sizeof(float), st));
+    test_affine_kernel<<<cdiv(B * cout, 128), 128, 0, st>>>(g, scale, shift, sqrtf((float)cout), B, cout,
+                                                            pstride, mul_p, add_p);
+    e.norm = g != nullptr;
+    e.mul = mul_p; e.add = add_p; e.mul_stride = pstride; e.add_stride = pstride;
   }
   e.silu = (flags & 1) != 0;
   e.prenorm = (flags & 2) != 0;

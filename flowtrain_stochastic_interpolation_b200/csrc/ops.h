@@ -21,12 +21,18 @@ struct ConvWeights {
   size_t tile_elems() const { return (size_t)ksize * ksize * ksize * cin * n; }
 };
 
+// y = ((acc * rs + bias) * rinv) * mul[b][c] + add[b][c], then SiLU, then + resid.
+//   rs   = 1/max(||src0 voxel||, 1e-12) when prenorm (pre-attention RMSNorm folded into a 1x1 conv)
+//   rinv = 1/max(||acc*rs + bias|| over the N channels, 1e-12) when norm (RMSNorm, :127-128)
+//   mul  = g*sqrt(C) (RMSNorm gain), for Block1 pre-multiplied by the FiLM (scale+1) (:241)
+//   add  = FiLM shift
 struct ConvEpilogue {
   const float* bias = nullptr;   // [ntiles*n]
-  const float* gs = nullptr;     // [n]  RMSNorm gain * sqrt(C) (enables the norm)
-  const float* scale = nullptr;  // FiLM scale [B][film_stride] (enables x*(scale+1)+shift)
-  const float* shift = nullptr;
-  int film_stride = 0;
+  bool norm = false;
+  const float* mul = nullptr;    // [B or 1][mul_stride]: per-channel factor (first n entries used)
+  int mul_stride = 0;            // 0: shared by all samples
+  const float* add = nullptr;    // [B or 1][add_stride]
+  int add_stride = 0;
   bool silu = false;
   const Act* resid = nullptr;    // residual added last (blocked bf16, same spatial dims)
   int resid_cgoff = 0;
@@ -72,9 +78,12 @@ struct TimeMlpParams {
 int time_embed(const TimeMlpParams& p, const float* t, int B, float* temb, float* temb_silu,
                cudaStream_t st);
 // all per-block FiLM MLPs in one launch: out[b][off_j + o] = W_j[o,:] . silu(temb[b]) + b_j[o]
+// (first half of each block = scale, emitted as (scale+1)*gs_j; second half = shift)
 struct FilmTable {
   const float* const* w;  // device array of weight pointers [nblk] (each [rows_j][time_dim])
   const float* const* b;  // device array of bias pointers
+  const float* const* gs; // device array of Block1 gain vectors g*sqrt(C) [rows_j/2] (entries may be null):
+                          // the scale half of block j is emitted as (scale + 1) * gs, ready for the conv epilogue
   const int* row_off;     // device prefix offsets [nblk+1]
   int nblk, total_rows, time_dim;
 };

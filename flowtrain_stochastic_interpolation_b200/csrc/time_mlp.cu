@@ -61,12 +61,16 @@ film_kernel(FilmTable ft, const float* __restrict__ x, int B, float* __restrict_
   const int r = row - __ldg(ft.row_off + lo);
   const float* wr = ft.w[lo] + (size_t)r * ft.time_dim;
   const float bias = __ldg(ft.b[lo] + r);
+  const int half = (__ldg(ft.row_off + lo + 1) - __ldg(ft.row_off + lo)) >> 1;
+  const float* gsp = ft.gs ? ft.gs[lo] : nullptr;
+  const bool is_scale = r < half;
+  const float gain = (is_scale && gsp) ? __ldg(gsp + r) : 1.f;
   for (int b = 0; b < B; ++b) {
     const float* xb = x + (size_t)b * ft.time_dim;
     float s = 0.f;
     for (int i = lane; i < ft.time_dim; i += 32) s += __ldg(wr + i) * __ldg(xb + i);
     s = warp_sum(s);
-    if (lane == 0) out[(size_t)b * ft.total_rows + row] = s + bias;
+    if (lane == 0) out[(size_t)b * ft.total_rows + row] = is_scale ? (s + bias + 1.f) * gain : s + bias;
   }
 }
 
