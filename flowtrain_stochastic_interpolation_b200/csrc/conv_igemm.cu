@@ -27,8 +27,8 @@
 //     small ring, once per group of NZ planes.
 //   * accumulators are double-buffered (the epilogue of group g overlaps the MMAs of g+1); each
 //     epilogue thread owns one voxel row, so the channel reduction of RMSNorm is thread-local.
-//   * the MMA issuer is one elected lane of warp 1; everything it needs per instruction is one
-//     16-byte table entry (built per group by the whole warp) plus two adds.
+//   * the MMA issuer is one elected lane of warp 1 walking a per-group table (built by the whole
+//     warp): chunk -> table entry -> k-step, two adds per instruction.
 #include "ops.h"
 
 namespace ftb {
@@ -39,7 +39,7 @@ constexpr int kThreads = 320;   // TMA warp | MMA warp | 8 epilogue warps
 constexpr int kMaxN = 256;
 constexpr int kMaxSlots = 12;
 constexpr int kMaxWSlots = 32;
-constexpr int kMaxEnt = 96;   // MMA table entries per group (first-step pairs + stacked runs)
+constexpr int kMaxEnt = 96;   // MMA table entries per group (first-chunk pairs + stacked runs)
 constexpr int kMaxKS = 32;    // k-steps (Cin_pad / 16)
 
 enum : int { F_SILU = 1, F_QSOFTMAX = 2 };
@@ -111,18 +111,25 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 __device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
-// finish 16 consecutive channels [c0, c0+16) of one voxel: SiLU, + residual, store
+// finish 16 consecutive channels [c0, c0+16) of one voxel: SiLU, + residual, store.
+// `pre` (optional) holds the residual's two 16-byte groups, loaded by the caller ahead of time.
 __device__ __forceinline__ void epi_store16(const IgemmParams& p, const EpiCtx& ec, int c0, size_t vox,
-                                            float (&v)[16]) {
+                                            float (&v)[16], uint4 pre0 = uint4(), uint4 pre1 = uint4(),
+                                            bool use_pre = false) {
   if (p.flags & F_SILU) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = silu_fast(v[j]);
   }
   if (!ec.valid) return;
   if (ec.res_b) {
-    const bf16* rp = ec.res_b + ((size_t)(p.resid_cgoff + (c0 >> 3)) * ec.cgs + vox) * 8;
-    const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(rp));
-    const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(rp + ec.cgs * 8));
+    uint4 u0, u1;
+    if (use_pre) {
+      u0 = pre0; u1 = pre1;
+    } else {
+      const bf16* rp = ec.res_b + ((size_t)(p.resid_cgoff + (c0 >> 3)) * ec.cgs + vox) * 8;
+      u0 = __ldg(reinterpret_cast<const uint4*>(rp));
+      u1 = __ldg(reinterpret_cast<const uint4*>(rp + ec.cgs * 8));
+    }
     float f[8];
     unpack_bf16x8(u0, f);
 #pragma unroll
@@ -147,9 +154,18 @@ __device__ __forceinline__ void epi_store16(const IgemmParams& p, const EpiCtx& 
   *reinterpret_cast<uint4*>(dst + ec.cgs * 8) = pack_bf16x8(f);
 }
 
+// pull this voxel's residual row towards the SM before the accumulator is read
+__device__ __forceinline__ void epi_prefetch_resid(const IgemmParams& p, const EpiCtx& ec, size_t vox) {
+  if (!ec.res_b || !ec.valid) return;
+  const bf16* rp = ec.res_b + ((size_t)p.resid_cgoff * ec.cgs + vox) * 8;
+  for (int cg = 0; cg < (p.N >> 3); ++cg)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(rp + (size_t)cg * ec.cgs * 8));
+}
+
 // y = (acc * rs) * mul + add'   (no norm; bias already folded into add')
 __device__ __forceinline__ void epi_affine(const IgemmParams& p, const EpiCtx& ec, uint32_t trow,
                                            size_t vox, float rs) {
+  epi_prefetch_resid(p, ec, vox);
   for (int c0 = 0; c0 < p.N; c0 += 32) {
     uint32_t r0[16], r1[16];
     const bool two = c0 + 16 < p.N;
@@ -187,6 +203,18 @@ __device__ __forceinline__ void epi_affine(const IgemmParams& p, const EpiCtx& e
 template <int NCH>
 __device__ __forceinline__ void epi_norm_regs(const IgemmParams& p, const EpiCtx& ec, uint32_t trow,
                                               size_t vox, float rs) {
+  constexpr bool kPre = NCH <= 3;   // residual row preloaded into registers (else L1 prefetch)
+  uint4 pre[kPre ? 2 * NCH : 2];
+  const bool has_res = ec.res_b != nullptr && ec.valid;
+  if (kPre) {
+    if (has_res) {
+      const bf16* rp = ec.res_b + ((size_t)p.resid_cgoff * ec.cgs + vox) * 8;
+#pragma unroll
+      for (int i = 0; i < 2 * NCH; ++i) pre[i] = __ldg(reinterpret_cast<const uint4*>(rp + (size_t)i * ec.cgs * 8));
+    }
+  } else {
+    epi_prefetch_resid(p, ec, vox);
+  }
   uint32_t r[NCH][16];
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) tmem_ld16(trow + ch * 16, r[ch]);
@@ -219,13 +247,15 @@ __device__ __forceinline__ void epi_norm_regs(const IgemmParams& p, const EpiCtx
       v[j4 + 2] = fmaf(__uint_as_float(r[ch][j4 + 2]) * rinv, mu.z, ad.z);
       v[j4 + 3] = fmaf(__uint_as_float(r[ch][j4 + 3]) * rinv, mu.w, ad.w);
     }
-    epi_store16(p, ec, ch * 16, vox, v);
+    if (kPre) epi_store16(p, ec, ch * 16, vox, v, pre[2 * ch], pre[2 * ch + 1], true);
+    else epi_store16(p, ec, ch * 16, vox, v);
   }
 }
 
 // same, any N: one TMEM pass for the norm, a second for the output
 __device__ __forceinline__ void epi_norm_2pass(const IgemmParams& p, const EpiCtx& ec, uint32_t trow,
                                                size_t vox, float rs) {
+  epi_prefetch_resid(p, ec, vox);
   float ss[4] = {0.f, 0.f, 0.f, 0.f};
   for (int c0 = 0; c0 < p.N; c0 += 32) {
     uint32_t r0[16], r1[16];
@@ -320,6 +350,26 @@ __device__ __forceinline__ void epi_qsoftmax(const IgemmParams& p, const EpiCtx&
   }
 }
 
+
+// Issue the MMAs of one weight chunk: table entries [ea, ea_end) x NKS k-steps.  An entry is
+// (A descriptor base of the window plane, B row-block offset | accumulate flag, TMEM address,
+// instruction descriptor); `overwrite_ok` = this is the first chunk, honour the entry's flag.
+template <int NKS>
+__device__ __forceinline__ void issue_entries(uint32_t ea, uint32_t ea_end, uint32_t aoff, uint32_t wb,
+                                              bool overwrite_ok, uint32_t a_hi, uint32_t b_hi, uint32_t kinc,
+                                              uint32_t kstep) {
+#pragma unroll 1
+  for (; ea < ea_end; ea += 16) {
+    uint32_t ex, ey, ez, ew;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ex), "=r"(ey), "=r"(ez), "=r"(ew) : "r"(ea));
+    const uint32_t a = ex + aoff;
+    const uint32_t b = (ey & 0x7FFFFFFFu) + wb;
+    umma_bf16_lohi(ez, a, a_hi, b, b_hi, ew, overwrite_ok ? (ey >> 31) : 1u);
+#pragma unroll
+    for (int i = 1; i < NKS; ++i) umma_bf16_lohi(ez, a + i * kinc, a_hi, b + i * kstep, b_hi, ew, 1u);
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                   const IgemmParams p) {
@@ -335,8 +385,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
   uint64_t* acc_full = w_empty + kMaxWSlots;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  uint32_t* s_koff = tmem_ptr + 4;                                   // [kMaxKS]
-  uint4* s_tab = reinterpret_cast<uint4*>(s_koff + kMaxKS);          // [kMaxEnt]
+  uint4* s_tab = reinterpret_cast<uint4*>(tmem_ptr + 4);             // [kMaxEnt] MMA table of the group
   float* s_par = reinterpret_cast<float*>(s_tab + kMaxEnt);          // [2 halves][bias|mul|add][kMaxN]
 
   const int warp = threadIdx.x >> 5;
@@ -415,39 +464,43 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    // The whole warp runs the loops (uniform control flow keeps addresses in uniform registers);
-    // one elected lane issues tcgen05.mma / tcgen05.commit.
+    // Window plane q of a group feeds the accumulators zi = q - kd for the depth taps
+    // kd in [kd_lo, kd_hi]: adjacent TMEM column blocks, and adjacent row blocks j = K-1-kd of
+    // the packed weight tile, so one MMA of N_mma = ns*N covers ns of them.  The warp builds a
+    // small table per group ("first" entries: one per (q, kd) pair, used on the very first weight
+    // chunk where each accumulator's first touch must overwrite; "main" entries: stacked runs
+    // of up to smax taps), then ONE elected lane walks chunk -> entry -> k-step with two adds
+    // per instruction.
     const bool leader = elect_one();
-    if (lane < p.KS)
-      s_koff[lane] = (lane < p.KS0 ? lane * 2 * p.cg_pitch
-                                   : p.src1_off + (lane - p.KS0) * 2 * p.cg_pitch) >> 4;
-    __syncwarp();
     const uint32_t a_hi = ((p.row_pitch >> 4) & 0x3FFFu) | (1u << 14);     // SBO | descriptor version
     const uint32_t a_lbo = ((p.cg_pitch >> 4) & 0x3FFFu) << 16;
     const uint32_t b_hi = (256u >> 4) | (1u << 14);
-    const uint32_t planes_enc = smem_u32(s_planes) >> 4;
+    const uint32_t planes_enc = (smem_u32(s_planes) >> 4) | a_lbo;
     const uint32_t slot_enc = p.slot_stride >> 4;
     const uint32_t w_enc = (smem_u32(s_w) >> 4) | ((128u >> 4) << 16);
     const uint32_t kstep_enc = p.kstep_bytes >> 4;
     const uint32_t wchunk_enc = p.wchunk_bytes >> 4;
     const uint32_t rowp_enc = p.row_pitch >> 4;
+    const uint32_t kinc = (2 * p.cg_pitch) >> 4;                            // one k-step = 2 channel groups
+    const uint32_t kjump = (p.src1_off >> 4) - (uint32_t)p.KS0 * kinc;      // extra offset entering src1
+    const uint32_t idesc0 = umma_idesc_bf16_f32(128, 0);
+    const uint32_t idesc_n = (uint32_t)(p.N >> 3) << 17;
+    const uint32_t nb_enc = (uint32_t)(p.N * 2);                            // one depth tap of B rows, >>4
+    const uint32_t tab_addr = smem_u32(s_tab);
     const bool stream_w = !p.w_resident;
-    uint32_t pbase = 0, wctr = 0, gctr = 0;
+    uint32_t wctr = 0, gctr = 0;
+    uint32_t pc_ready = 0;  // planes of the ring already waited for (global plane counter)
+    uint32_t pc_base = 0;   // global plane counter of the current item's plane 0
     bool w_waited = false;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const ItemCoord c = decode_item(p, item);
       const int npl = c.lz + 2 * p.pad;
       const int ngroups = (c.lz + p.NZ - 1) / p.NZ;
-      int ready = 0;
       for (int g = 0; g < ngroups; ++g, ++gctr) {
         const int nze = min(p.NZ, c.lz - g * p.NZ);
-        const uint32_t ab = gctr & 1;
-        // ---- per-group MMA table.  Lane q owns window plane q, which feeds the accumulators
-        // zi = q - kd for kd in [kd_lo, kd_hi]: adjacent TMEM column blocks, and adjacent row
-        // blocks j = K-1-kd of the packed weight tile.  "first" entries (one per (q,kd) pair,
-        // accumulate = kd > 0) serve the very first k-step, where each accumulator's first
-        // touch must overwrite; "main" entries cover up to smax accumulators per instruction.
         const int win = nze + 2 * p.pad;
+        const uint32_t ab = gctr & 1;
+        // ---- table: lane q owns window plane q
         int cnt = 0, kd_hi = 0, nruns = 0;
         if (lane < win) {
           const int kd_lo = max(0, lane - (nze - 1));
@@ -463,80 +516,85 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
         }
         const int n_first = __shfl_sync(0xffffffffu, sf, 31), n_main = __shfl_sync(0xffffffffu, sm, 31);
         if (lane < win) {
-          const uint32_t pc = pbase + g * p.NZ + lane;
-          const uint32_t a_q = (planes_enc + (pc % p.nslot) * slot_enc) | a_lbo;
+          const uint32_t pc = pc_base + g * p.NZ + lane;
+          const uint32_t a_q = planes_enc + (pc % p.nslot) * slot_enc;
           const uint32_t acc0 = tmem_base + ab * p.NZ * p.N;
-          const uint32_t id1 = umma_idesc_bf16_f32(128, p.N);
           for (int i = 0; i < cnt; ++i) {
-            const int kd = kd_hi - i, zi = lane - kd, j = p.K - 1 - kd;
-            s_tab[sf - cnt + i] = make_uint4(a_q, (uint32_t)(j * p.N * 2) | (kd > 0 ? 0x80000000u : 0u),
-                                             acc0 + zi * p.N, id1);
+            const int kd = kd_hi - i;
+            s_tab[sf - cnt + i] = make_uint4(a_q, (uint32_t)(p.K - 1 - kd) * nb_enc | (kd > 0 ? 0x80000000u : 0u),
+                                             acc0 + (lane - kd) * p.N, idesc0 + idesc_n);
           }
           for (int r = 0; r < nruns; ++r) {
-            const int z0 = lane - kd_hi + r * p.smax, j0 = p.K - 1 - kd_hi + r * p.smax;
+            const int kd = kd_hi - r * p.smax;
             const int ns = min(p.smax, cnt - r * p.smax);
             s_tab[n_first + sm - nruns + r] =
-                make_uint4(a_q, (uint32_t)(j0 * p.N * 2) | 0x80000000u, acc0 + z0 * p.N,
-                           umma_idesc_bf16_f32(128, ns * p.N));
+                make_uint4(a_q, (uint32_t)(p.K - 1 - kd) * nb_enc | 0x80000000u, acc0 + (lane - kd) * p.N,
+                           idesc0 + (uint32_t)ns * idesc_n);
           }
         }
         __syncwarp();
-        mbar_wait(&acc_empty[ab], ((gctr >> 1) & 1) ^ 1);
-        const int need = min(npl, g * p.NZ + nze + 2 * p.pad);
-        for (; ready < need; ++ready) {
-          const uint32_t pc = pbase + ready;
-          mbar_wait(&plane_full[pc % p.nslot], (pc / p.nslot) & 1);
-        }
-        tc_fence_after();
-        int t = 0;
-        for (int kh = 0; kh < p.K; ++kh)
-          for (int kw = 0; kw < p.K; ++kw, ++t) {
-            const uint32_t tapoff = kh * rowp_enc + kw;
-            for (int kc = 0; kc < p.nkc; ++kc) {
-              uint32_t wslot_i;
-              if (stream_w) {
-                wslot_i = wctr % p.wslot;
-                mbar_wait(&w_full[wslot_i], (wctr / p.wslot) & 1);
-                tc_fence_after();
-              } else {
-                wslot_i = t * p.nkc + kc;
-                if (!w_waited) {
-                  mbar_wait(&w_full[wslot_i], 0);
+        if (leader) {
+          mbar_wait(&acc_empty[ab], ((gctr >> 1) & 1) ^ 1);
+          const uint32_t need = pc_base + (uint32_t)min(npl, g * p.NZ + win);
+          for (; pc_ready < need; ++pc_ready)
+            mbar_wait(&plane_full[pc_ready % p.nslot], (pc_ready / p.nslot) & 1);
+          tc_fence_after();
+          int t = 0;
+          for (int kh = 0; kh < p.K; ++kh)
+            for (int kw = 0; kw < p.K; ++kw, ++t) {
+              const uint32_t tapoff = kh * rowp_enc + kw;
+              for (int kc = 0; kc < p.nkc; ++kc) {
+                uint32_t wslot_i;
+                if (stream_w) {
+                  wslot_i = wctr % p.wslot;
+                  mbar_wait(&w_full[wslot_i], (wctr / p.wslot) & 1);
                   tc_fence_after();
+                } else {
+                  wslot_i = t * p.nkc + kc;
+                  if (!w_waited) {
+                    mbar_wait(&w_full[wslot_i], 0);
+                    tc_fence_after();
+                  }
                 }
-              }
-              const uint32_t wb = w_enc + wslot_i * wchunk_enc;
-              const int ks_lo = kc * p.KC, ks_hi = min(p.KS, ks_lo + p.KC);
-              for (int ks = ks_lo; ks < ks_hi; ++ks) {
-                const uint32_t aoff = tapoff + s_koff[ks];
-                const uint32_t bks = wb + (ks - ks_lo) * kstep_enc;
-                const bool first = (t | ks) == 0;
-                const int e0 = first ? 0 : n_first, e1 = first ? n_first : n_first + n_main;
-#pragma unroll 4
-                for (int e = e0; e < e1; ++e) {
-                  const uint4 en = s_tab[e];
-                  if (leader)
-                    umma_bf16_lohi(en.z, en.x + aoff, a_hi, bks + (en.y & 0x7FFFFFFFu), b_hi, en.w,
-                                   en.y >> 31);
+                const uint32_t wb = w_enc + wslot_i * wchunk_enc;
+                // a chunk never straddles the src0/src1 boundary (host picks KC | KS0)
+                const int ks_lo = kc * p.KC;
+                const int nks = min(p.KS, ks_lo + p.KC) - ks_lo;
+                const bool firstc = (t | kc) == 0;
+                const uint32_t aoff = tapoff + ks_lo * kinc + (ks_lo >= p.KS0 ? kjump : 0u);
+                uint32_t ea = tab_addr + (firstc ? 0u : (uint32_t)n_first * 16u);
+                const uint32_t ea_end = ea + (uint32_t)(firstc ? n_first : n_main) * 16u;
+                switch (nks) {   // straight-line k-step issue for the common chunk lengths
+                  case 1: issue_entries<1>(ea, ea_end, aoff, wb, firstc, a_hi, b_hi, kinc, kstep_enc); break;
+                  case 2: issue_entries<2>(ea, ea_end, aoff, wb, firstc, a_hi, b_hi, kinc, kstep_enc); break;
+                  case 3: issue_entries<3>(ea, ea_end, aoff, wb, firstc, a_hi, b_hi, kinc, kstep_enc); break;
+                  case 4: issue_entries<4>(ea, ea_end, aoff, wb, firstc, a_hi, b_hi, kinc, kstep_enc); break;
+                  case 5: issue_entries<5>(ea, ea_end, aoff, wb, firstc, a_hi, b_hi, kinc, kstep_enc); break;
+                  case 6: issue_entries<6>(ea, ea_end, aoff, wb, firstc, a_hi, b_hi, kinc, kstep_enc); break;
+                  default:
+                    for (int i = 0; i < nks; ++i)
+                      issue_entries<1>(ea, ea_end, aoff + i * kinc, wb + i * kstep_enc, firstc && i == 0, a_hi,
+                                       b_hi, kinc, kstep_enc);
                 }
-              }
-              if (stream_w) {
-                if (leader) umma_commit(&w_empty[wslot_i]);
-                ++wctr;
+                if (stream_w) {
+                  umma_commit(&w_empty[wslot_i]);
+                  ++wctr;
+                }
               }
             }
+          // planes that leave the window: the NZ oldest, or everything at the end of the item
+          const int nrel = (g == ngroups - 1) ? win : nze;
+          uint32_t slot = (pc_base + g * p.NZ) % p.nslot;
+          for (int i = 0; i < nrel; ++i) {
+            umma_commit(&plane_empty[slot]);
+            slot = slot + 1 == (uint32_t)p.nslot ? 0u : slot + 1;
           }
-        w_waited = true;
-        // planes that leave the window: the NZ oldest, or everything at the end of the item
-        const int rel_lo = g * p.NZ;
-        const int rel_hi = (g == ngroups - 1) ? npl : rel_lo + nze;
-        if (leader) {
-          for (int i = rel_lo; i < rel_hi; ++i) umma_commit(&plane_empty[(pbase + i) % p.nslot]);
           umma_commit(&acc_full[ab]);
         }
+        w_waited = true;
         __syncwarp();  // s_tab is rewritten for the next group
       }
-      pbase += npl;
+      pc_base += npl;
     }
   } else {
     // ===================================================================== epilogue (8 warps)
@@ -609,7 +667,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
             else epi_qsoftmax<16>(p, ec, trow, vox, rs);
           } else if (p.norm) {
             if (p.N == 48) epi_norm_regs<3>(p, ec, trow, vox, rs);
-            else if (p.N == 96) epi_norm_regs<6>(p, ec, trow, vox, rs);
             else epi_norm_2pass(p, ec, trow, vox, rs);
           } else {
             epi_affine(p, ec, trow, vox, rs);
@@ -699,13 +756,13 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   p.wtap_bytes = (uint32_t)p.KS * p.kstep_bytes;
   // weight ring unit: a chunk of KC k-steps of one (kh,kw) position (all depth taps), <= 24 KB
   p.KC = p.KS;
-  while (p.KC > 1 && (uint32_t)p.KC * p.kstep_bytes > 24 * 1024) --p.KC;
+  while (p.KC > 1 && ((uint32_t)p.KC * p.kstep_bytes > 24 * 1024 || (p.cg1 > 0 && p.KS0 % p.KC != 0))) --p.KC;
   p.nkc = cdiv(p.KS, p.KC);
   p.wchunk_bytes = (uint32_t)p.KC * p.kstep_bytes;
   const int nchunks = p.taps * p.nkc;
   const int sms = num_sms();
   const uint32_t bar_bytes =
-      (2 * kMaxSlots + 2 * kMaxWSlots + 4) * 8 + 16 + kMaxKS * 4 + kMaxEnt * 16 + 2 * 3 * kMaxN * 4;
+      (2 * kMaxSlots + 2 * kMaxWSlots + 4) * 8 + 16 + kMaxEnt * 16 + 2 * 3 * kMaxN * 4;
   const size_t all_w = (size_t)p.taps * p.wtap_bytes;
 
   // ---- tile height, planes per group (NZ) and ring sizing against the 227 KB shared-memory
