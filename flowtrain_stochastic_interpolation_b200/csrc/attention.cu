@@ -10,6 +10,9 @@
 //
 // Attention (:357-373, :436-465): softmax(q k^T * dh^-0.5) v over n tokens + memory kv, tiled
 // over keys with an online softmax; one warp per query.
+#include <stdlib.h>
+#include <string.h>
+
 #include "ops.h"
 
 namespace ftb {
@@ -112,23 +115,194 @@ ctx_partial_kernel(const bf16* __restrict__ qkv, int cgtot, int heads, size_t vo
   if (e0 == 0) out[DH * DH + d] = ssum;
 }
 
-// grid (B): merge partials + memory kv -> ctx; fold W_out -> packed per-sample weights
+// ------------------------------------------------------------------ context on tensor cores
+// ctx[h][d][e] = sum_n P[(h,d), n] V[(h,e), n] with P = exp(k - kmax): a 128 x (128+16) x n GEMM
+// whose four diagonal 32x32 blocks are the per-head contexts (the off-diagonal blocks are
+// computed and dropped: the tensor pipe has the room, the kernel is bound by the exp pass and
+// the HBM read of k and v).  Column 128 of the B operand is a constant one, so D[:,128] is the
+// softmax denominator.  Both operands are MN-major: the blocked activation layout
+// [channel group][voxel][8 channels] IS the no-swizzle MN-major UMMA layout (core matrix = 8
+// voxels x 16 B, LBO = 128 B along voxels, SBO = channel-group pitch), so v is consumed exactly
+// as TMA delivers it and k needs only the elementwise exp in place.
+//   warp 0: TMA producer | warp 1: MMA issuer | warps 2-5: exp pass, then TMEM -> partials
+constexpr int kCtxT = 128;       // voxels per stage
+constexpr int kCtxStages = 3;
+constexpr int kCtxThreads = 192;
+
+struct CtxParams {
+  int heads, dh, hd;             // hd = heads*dh = 128
+  int cgtot;                     // channel groups of the qkv tensor
+  long long vox;                 // voxels per sample
+  int ntiles, nsplit;
+  const float* kmax;             // [B][hd]
+  float* part;                   // [B][heads][nsplit][dh*dh + dh]
+};
+
+__global__ void __launch_bounds__(kCtxThreads, 1)
+ctx_tc_kernel(const __grid_constant__ CUtensorMap tm, const CtxParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  constexpr uint32_t kBytesK = 16 * kCtxT * 16;          // 16 channel groups of k
+  constexpr uint32_t kBytesV = 18 * kCtxT * 16;          // 16 of v + 2 constant (ones column)
+  constexpr uint32_t kStage = kBytesK + kBytesV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCtxStages * kStage);
+  uint64_t* full = bars;                    // TMA landed
+  uint64_t* ready = bars + kCtxStages;      // exp pass done
+  uint64_t* empty = bars + 2 * kCtxStages;  // MMAs done reading
+  uint64_t* done = bars + 3 * kCtxStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done + 1);
+  float* s_kmax = reinterpret_cast<float*>(tmem_ptr + 4);  // [128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x, b = blockIdx.y;
+  const int tiles_per = (p.ntiles + p.nsplit - 1) / p.nsplit;
+  const int t_lo = split * tiles_per, t_hi = min(p.ntiles, t_lo + tiles_per);
+  const int nt = max(0, t_hi - t_lo);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kCtxStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&ready[i], 128);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(done, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tm);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 256);
+    tmem_relinquish();
+  }
+  if (warp >= 2) {
+    const int t = threadIdx.x - 64;
+    s_kmax[t] = __ldg(p.kmax + (size_t)b * p.hd + t);
+    // constant channel groups 16,17 of every stage's V tile: channel 128 = 1, the rest 0
+    for (int i = t; i < kCtxStages * 2 * kCtxT; i += 128) {
+      const int st = i / (2 * kCtxT), r = i % (2 * kCtxT);
+      uint4 u = make_uint4(0u, 0u, 0u, 0u);
+      if (r < kCtxT) u.x = 0x00003F80u;  // bf16 1.0 in element 0
+      *reinterpret_cast<uint4*>(smem + st * kStage + kBytesK + 16 * kCtxT * 16 + r * 16) = u;
+    }
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < nt; ++i) {
+        const int s = i % kCtxStages;
+        mbar_wait(&empty[s], ((i / kCtxStages) & 1) ^ 1);
+        mbar_expect_tx(&full[s], kBytesK + 16 * kCtxT * 16);
+        uint8_t* dst = smem + s * kStage;
+        const int v0 = (t_lo + i) * kCtxT;
+        tma_load_3d(dst, &tm, &full[s], 0, v0, b * p.cgtot + p.hd / 8);
+        tma_load_3d(dst + kBytesK, &tm, &full[s], 0, v0, b * p.cgtot + 2 * p.hd / 8);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // MN-major A and B (bits 15, 16), bf16 x bf16 -> f32, M = 128, N = 144
+      const uint32_t idesc = umma_idesc_bf16_f32(128, 144) | (1u << 15) | (1u << 16);
+      const uint32_t hi = ((kCtxT * 16u) >> 4) | (1u << 14);          // SBO = channel-group pitch
+      const uint32_t lbo = (128u >> 4) << 16;                         // LBO = 8 voxels
+      for (int i = 0; i < nt; ++i) {
+        const int s = i % kCtxStages;
+        mbar_wait(&ready[s], (i / kCtxStages) & 1);
+        tc_fence_after();
+        const uint32_t a0 = (smem_u32(smem + s * kStage) >> 4) | lbo;
+        const uint32_t b0 = (smem_u32(smem + s * kStage + kBytesK) >> 4) | lbo;
+#pragma unroll
+        for (int ks = 0; ks < kCtxT / 16; ++ks)
+          umma_bf16_lohi(tmem_base, a0 + ks * 16, hi, b0 + ks * 16, hi, idesc, (i | ks) != 0);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(done);
+    }
+    __syncwarp();
+  } else {
+    const int t = threadIdx.x - 64;  // 0..127
+    for (int i = 0; i < nt; ++i) {
+      const int s = i % kCtxStages;
+      mbar_wait(&full[s], (i / kCtxStages) & 1);
+      uint8_t* kt = smem + s * kStage;
+      const long long v = (long long)(t_lo + i) * kCtxT + t;
+      const bool in = v < p.vox;
+#pragma unroll 4
+      for (int cg = 0; cg < 16; ++cg) {
+        uint4* u = reinterpret_cast<uint4*>(kt + (cg * kCtxT + t) * 16);
+        float f[8];
+        unpack_bf16x8(*u, f);
+        const float4 m0 = *reinterpret_cast<const float4*>(s_kmax + cg * 8);
+        const float4 m1 = *reinterpret_cast<const float4*>(s_kmax + cg * 8 + 4);
+        f[0] = __expf(f[0] - m0.x); f[1] = __expf(f[1] - m0.y);
+        f[2] = __expf(f[2] - m0.z); f[3] = __expf(f[3] - m0.w);
+        f[4] = __expf(f[4] - m1.x); f[5] = __expf(f[5] - m1.y);
+        f[6] = __expf(f[6] - m1.z); f[7] = __expf(f[7] - m1.w);
+        *u = in ? pack_bf16x8(f) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      fence_proxy_async();
+      mbar_arrive(&ready[s]);
+    }
+    // ---- TMEM -> partials: row t = (head, d); own head's 32 columns + the denominator column
+    const int q = warp & 3;            // TMEM lane quadrant of this warp
+    const int row = q * 32 + lane;
+    const int h = row / p.dh, d = row % p.dh;
+    float* out = p.part + (((size_t)b * p.heads + h) * p.nsplit + split) * (p.dh * p.dh + p.dh);
+    if (nt > 0) {
+      mbar_wait(done, 0);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+      // dh is 16 or 32: head h owns columns [h*dh, h*dh + dh); warps of a quadrant may hold two
+      // heads (dh = 16), so the column base is per lane and the loads are issued per head
+      for (int hh = (q * 32) / p.dh; hh < (q * 32 + 32) / p.dh; ++hh) {
+        for (int c0 = 0; c0 < p.dh; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(trow + hh * p.dh + c0, r);
+          tmem_ld_wait();
+          if (hh == h) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) out[d * p.dh + c0 + j] = __uint_as_float(r[j]);
+          }
+        }
+      }
+      uint32_t r[16];
+      tmem_ld16(trow + 128, r);
+      tmem_ld_wait();
+      out[p.dh * p.dh + d] = __uint_as_float(r[0]);
+    } else {
+      for (int e = 0; e < p.dh; ++e) out[d * p.dh + e] = 0.f;
+      out[p.dh * p.dh + d] = 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+// grid (heads, B): merge the split partials + memory kv -> ctx[h]; then this head's 32 columns
+// of the folded projection M_b[c][h*dh + d] = q_scale * sum_e W[c][h*dh+e] ctx[h][d][e]
 __global__ void __launch_bounds__(256)
-combine_kernel(const float* __restrict__ part, int nsplit, const float* __restrict__ kmax, int heads,
-               int dh, const float* __restrict__ mem_kv, int n_mem, const float* __restrict__ w_out,
-               int C, float q_scale, bf16* __restrict__ wpack, float* __restrict__ ctx_dbg) {
-  extern __shared__ float sctx[];  // [heads][dh][dh]
-  const int b = blockIdx.x;
+combine_head_kernel(const float* __restrict__ part, int nsplit, const float* __restrict__ kmax, int heads,
+                    int dh, const float* __restrict__ mem_kv, int n_mem, const float* __restrict__ w_out,
+                    int C, float q_scale, bf16* __restrict__ wpack, float* __restrict__ ctx_dbg) {
+  __shared__ float sctx[32 * 33];
+  __shared__ float ssum[32];
+  const int h = blockIdx.x, b = blockIdx.y;
   const int hd = heads * dh;
   const int per = dh * dh + dh;
-  for (int o = threadIdx.x; o < heads * dh * dh; o += blockDim.x) {
-    const int e = o % dh, d = (o / dh) % dh, h = o / (dh * dh);
-    const float* pp = part + ((size_t)b * heads + h) * nsplit * per;
-    float c = 0.f, s = 0.f;
-    for (int sp = 0; sp < nsplit; ++sp) {
-      c += pp[(size_t)sp * per + d * dh + e];
-      s += pp[(size_t)sp * per + dh * dh + d];
-    }
+  const float* pp = part + ((size_t)b * heads + h) * nsplit * per;
+  for (int o = threadIdx.x; o < per; o += blockDim.x) {
+    float c = 0.f;
+    for (int sp = 0; sp < nsplit; ++sp) c += pp[(size_t)sp * per + o];
+    if (o < dh * dh) sctx[(o / dh) * 33 + (o % dh)] = c; else ssum[o - dh * dh] = c;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < dh * dh; o += blockDim.x) {
+    const int d = o / dh, e = o % dh;
+    float c = sctx[d * 33 + e], s = ssum[d];
     // memory tokens (mem_kv[2][heads][dh][n_mem], :300,:320-323) join the softmax over n
     const float m0 = kmax[(size_t)b * hd + h * dh + d];
     const float* mk = mem_kv + ((size_t)h * dh + d) * n_mem;
@@ -144,19 +318,17 @@ combine_kernel(const float* __restrict__ part, int nsplit, const float* __restri
       s += pj;
     }
     const float v = c / s;
-    sctx[o] = v;
-    if (ctx_dbg) ctx_dbg[(size_t)b * heads * dh * dh + o] = v;
+    sctx[d * 33 + e] = v;   // (d, e) is read and written by this thread only
+    if (ctx_dbg) ctx_dbg[((size_t)b * heads + h) * dh * dh + o] = v;
   }
   __syncthreads();
-  // M_b[c][k = h*dh+d] = q_scale * sum_e W[c][h*dh+e] * ctx[h][d][e]; packed [ks][C/8][2][8][8]
   bf16* dst = wpack + (size_t)b * C * hd;
-  for (int o = threadIdx.x; o < C * hd; o += blockDim.x) {
-    const int k = o % hd, c = o / hd;
-    const int h = k / dh, d = k % dh;
+  for (int o = threadIdx.x; o < C * dh; o += blockDim.x) {
+    const int d = o % dh, c = o / dh;
+    const int k = h * dh + d;
     const float* wr = w_out + (size_t)c * hd + h * dh;
-    const float* cx = sctx + ((size_t)h * dh + d) * dh;
     float a = 0.f;
-    for (int e = 0; e < dh; ++e) a += wr[e] * cx[e];
+    for (int e = 0; e < dh; ++e) a += __ldg(wr + e) * sctx[d * 33 + e];
     const int ks = k >> 4, kc = (k >> 3) & 1, k8 = k & 7;
     dst[((((size_t)ks * (C / 8) + (c >> 3)) * 2 + kc) * 8 + (c & 7)) * 8 + k8] = __float2bfloat16(a * q_scale);
   }
@@ -301,6 +473,28 @@ int linattn_kmax(const Act& qkv, int heads, int dh, int nsplit, float* kmax, cud
 
 int linattn_context_partial(const Act& qkv, int heads, int dh, int nsplit, const float* kmax,
                             float* part, cudaStream_t st) {
+  static const bool simt = [] { const char* e = getenv("FTB_LINATTN_IMPL"); return e && !strcmp(e, "simt"); }();
+  if (heads * dh == 128 && !simt) {
+    CUtensorMap tm;
+    FTB_TRY(make_voxel_tmap(&tm, qkv, kCtxT, 16));
+    CtxParams p;
+    p.heads = heads; p.dh = dh; p.hd = heads * dh;
+    p.cgtot = qkv.cg();
+    p.vox = (long long)qkv.voxels();
+    p.ntiles = (int)((p.vox + kCtxT - 1) / kCtxT);
+    p.nsplit = nsplit;
+    p.kmax = kmax; p.part = part;
+    constexpr int kSmem = kCtxStages * (16 + 18) * kCtxT * 16 + (3 * kCtxStages + 1) * 8 + 16 + 128 * 4 + 128;
+    static bool attr_set = false;
+    if (!attr_set) {
+      FTB_CUDA(cudaFuncSetAttribute(ctx_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+      attr_set = true;
+    }
+    dim3 grid(nsplit, qkv.B);
+    ctx_tc_kernel<<<grid, kCtxThreads, kSmem, st>>>(tm, p);
+    FTB_LAUNCH_OK();
+    return 0;
+  }
   dim3 grid(nsplit, heads, qkv.B);
   if (dh == 32)
     ctx_partial_kernel<32><<<grid, 256, 0, st>>>(qkv.p, qkv.cg(), heads, qkv.voxels(), nsplit, kmax, part);
@@ -316,9 +510,9 @@ int linattn_combine(const float* part, int nsplit, const float* kmax, int B, int
                     const float* mem_kv, int n_mem, const float* w_out, int C, float q_scale,
                     bf16* wpack_out, float* ctx_dbg, cudaStream_t st) {
   FTB_CHECK(C % 16 == 0 && (heads * dh) % 16 == 0, "linattn: C and heads*dim_head must be multiples of 16");
-  const size_t smem = (size_t)heads * dh * dh * sizeof(float);
-  FTB_CHECK(smem <= 48 * 1024, "linattn: context does not fit shared memory");
-  combine_kernel<<<B, 256, smem, st>>>(part, nsplit, kmax, heads, dh, mem_kv, n_mem, w_out, C, q_scale, wpack_out, ctx_dbg);
+  FTB_CHECK(dh <= 32, "linattn: dim_head must be at most 32");
+  combine_head_kernel<<<dim3(heads, B), 256, 0, st>>>(part, nsplit, kmax, heads, dh, mem_kv, n_mem, w_out, C,
+                                                      q_scale, wpack_out, ctx_dbg);
   FTB_LAUNCH_OK();
   return 0;
 }

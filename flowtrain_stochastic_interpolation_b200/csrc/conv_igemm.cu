@@ -29,6 +29,8 @@
 //     epilogue thread owns one voxel row, so the channel reduction of RMSNorm is thread-local.
 //   * the MMA issuer is one elected lane of warp 1 walking a per-group table (built by the whole
 //     warp): chunk -> table entry -> k-step, two adds per instruction.
+#include <stdlib.h>
+
 #include "ops.h"
 
 namespace ftb {
@@ -726,6 +728,21 @@ constexpr uint32_t kSmemLimit = 227 * 1024 - 128;  // 227 KB opt-in maximum minu
 
 }  // namespace
 
+int make_voxel_tmap(CUtensorMap* tm, const Act& a, int box_vox, int box_cg) {
+  PFN_encodeTiled enc = get_encode();
+  FTB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t vox = (cuuint64_t)a.voxels();
+  cuuint64_t gdim[3] = {8, vox, (cuuint64_t)a.B * a.cg()};
+  cuuint64_t gstr[2] = {16, vox * 16};
+  cuuint32_t box[3] = {8u, (cuuint32_t)box_vox, (cuuint32_t)box_cg};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a.p, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FTB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (voxel view) failed (" + std::to_string((int)r) + ")");
+  return 0;
+}
+
 int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const ConvEpilogue& e,
                Act& out, int out_cgoff, cudaStream_t st) {
   const Act& a0 = *s0.t;
@@ -777,6 +794,10 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   if (nz_cap > 8) nz_cap = 8;
   if (nz_cap > a0.D) nz_cap = a0.D;
   if (p.K == 1 && nz_cap > 2) nz_cap = 2;
+  if (const char* env = getenv("FTB_NZ")) {   // planner override for experiments
+    const int v = atoi(env);
+    if (v >= 1 && v < nz_cap) nz_cap = v;
+  }
   while (nz_cap > 1 && (nz_cap * p.K > kMaxEnt / 2 || nz_cap + 2 * p.pad > 32)) --nz_cap;
   FTB_CHECK(nz_cap >= 1, "conv: N tile too wide for a double-buffered accumulator");
   for (int th = a0.H >= 16 ? 16 : a0.H; th >= 1 && !fits; th = th / 2) {
@@ -800,6 +821,10 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
       } else {
         p.w_resident = 0;
         int ws = nchunks == 1 ? 2 : (p.wchunk_bytes <= 8192 ? 6 : (p.wchunk_bytes <= 16384 ? 4 : 3));
+        if (const char* env = getenv("FTB_WSLOT")) {
+          const int v = atoi(env);
+          if (v >= 2 && v <= kMaxWSlots) ws = v;
+        }
         for (; ws >= 2 && !fits; --ws) {
           p.wslot = ws;
           if ((size_t)ws * p.wchunk_bytes + planes + fixed <= kSmemLimit) fits = true;
