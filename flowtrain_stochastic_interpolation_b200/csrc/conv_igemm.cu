@@ -37,14 +37,15 @@ namespace ftb {
 
 namespace {
 
-constexpr int kThreads = 320;   // TMA warp | MMA warp | 8 epilogue warps
+constexpr int kThreads = 384;   // TMA warp | up to 2 MMA issuer warps | spare | 8 epilogue warps
+constexpr int kMaxIss = 2;
 constexpr int kMaxN = 256;
 constexpr int kMaxSlots = 12;
 constexpr int kMaxWSlots = 32;
 constexpr int kMaxEnt = 96;   // MMA table entries per group (first-chunk pairs + stacked runs)
 constexpr int kMaxKS = 32;    // k-steps (Cin_pad / 16)
 
-enum : int { F_SILU = 1, F_QSOFTMAX = 2 };
+enum : int { F_SILU = 1, F_QSOFTMAX = 2, F_NOMMA = 4 };
 
 struct IgemmParams {
   int B, D, H, W;
@@ -56,6 +57,7 @@ struct IgemmParams {
   int nHt, nWt, nSeg, LZ, NZ;
   int n_items;
   int nslot, wslot, w_resident;
+  int n_iss;                   // MMA issuer warps (each owns a contiguous share of a group's accumulators)
   uint32_t cg_pitch, row_pitch, src1_off, slot_stride, plane_tx_bytes, wtap_bytes;
   int KC, nkc;              // k-steps per weight chunk, chunks per tap (ring unit = one chunk)
   uint32_t wchunk_bytes;    // KC * K * N * 32 (ring slot stride)
@@ -73,6 +75,9 @@ struct IgemmParams {
   const bf16* resid;
   int resid_cgtot, resid_cgoff;
   const bf16* pre_src;
+  const float* ss_in;          // per-voxel ||src0||^2 (replaces reading pre_src)
+  float* ss_out;               // per-voxel sum of squares of the stored output
+  long long* dbg;              // optional [grid][8] cycle counters of the first MMA issuer (FTB_CONV_DBG)
   int pre_cgtot, pre_cgoff, pre_cg;
   int flags, q_dh;
   float q_scale;
@@ -105,6 +110,7 @@ struct EpiCtx {
   const bf16* res_b;               // residual base of sample b (or null)
   float* f32_b;                    // NCDHW fp32 output base of sample b (or null)
   size_t cgs;                      // voxels per channel-group plane (D*H*W)
+  float ssq;                       // running sum of squares of this voxel's stored outputs
   bool valid;
 };
 
@@ -115,7 +121,7 @@ __device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f 
 
 // finish 16 consecutive channels [c0, c0+16) of one voxel: SiLU, + residual, store.
 // `pre` (optional) holds the residual's two 16-byte groups, loaded by the caller ahead of time.
-__device__ __forceinline__ void epi_store16(const IgemmParams& p, const EpiCtx& ec, int c0, size_t vox,
+__device__ __forceinline__ void epi_store16(const IgemmParams& p, EpiCtx& ec, int c0, size_t vox,
                                             float (&v)[16], uint4 pre0 = uint4(), uint4 pre1 = uint4(),
                                             bool use_pre = false) {
   if (p.flags & F_SILU) {
@@ -139,6 +145,12 @@ __device__ __forceinline__ void epi_store16(const IgemmParams& p, const EpiCtx& 
     unpack_bf16x8(u1, f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[8 + j] += f[j];
+  }
+  if (p.ss_out) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s0 = fmaf(v[j], v[j], s0); s1 = fmaf(v[8 + j], v[8 + j], s1); }
+    ec.ssq += s0 + s1;
   }
   if (ec.f32_b) {
 #pragma unroll
@@ -165,7 +177,7 @@ __device__ __forceinline__ void epi_prefetch_resid(const IgemmParams& p, const E
 }
 
 // y = (acc * rs) * mul + add'   (no norm; bias already folded into add')
-__device__ __forceinline__ void epi_affine(const IgemmParams& p, const EpiCtx& ec, uint32_t trow,
+__device__ __forceinline__ void epi_affine(const IgemmParams& p, EpiCtx& ec, uint32_t trow,
                                            size_t vox, float rs) {
   epi_prefetch_resid(p, ec, vox);
   for (int c0 = 0; c0 < p.N; c0 += 32) {
@@ -203,7 +215,7 @@ __device__ __forceinline__ void epi_affine(const IgemmParams& p, const EpiCtx& e
 // channel RMSNorm (unet_attn_3d.py:127-128) with the whole voxel row held in registers:
 // v = acc*rs + bias; y = v / max(||v||, 1e-12) * mul + add
 template <int NCH>
-__device__ __forceinline__ void epi_norm_regs(const IgemmParams& p, const EpiCtx& ec, uint32_t trow,
+__device__ __forceinline__ void epi_norm_regs(const IgemmParams& p, EpiCtx& ec, uint32_t trow,
                                               size_t vox, float rs) {
   constexpr bool kPre = NCH <= 3;   // residual row preloaded into registers (else L1 prefetch)
   uint4 pre[kPre ? 2 * NCH : 2];
@@ -255,7 +267,7 @@ __device__ __forceinline__ void epi_norm_regs(const IgemmParams& p, const EpiCtx
 }
 
 // same, any N: one TMEM pass for the norm, a second for the output
-__device__ __forceinline__ void epi_norm_2pass(const IgemmParams& p, const EpiCtx& ec, uint32_t trow,
+__device__ __forceinline__ void epi_norm_2pass(const IgemmParams& p, EpiCtx& ec, uint32_t trow,
                                                size_t vox, float rs) {
   epi_prefetch_resid(p, ec, vox);
   float ss[4] = {0.f, 0.f, 0.f, 0.f};
@@ -353,22 +365,51 @@ __device__ __forceinline__ void epi_qsoftmax(const IgemmParams& p, const EpiCtx&
 }
 
 
+__device__ __forceinline__ void umma_fake(uint32_t d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                          uint32_t idesc, uint32_t accum) {   // timing experiments only
+  asm volatile("{\n\t.reg .b32 t;\n\tadd.u32 t, %0, %1;\n\tadd.u32 t, t, %2;\n\tadd.u32 t, t, %3;\n\t"
+               "add.u32 t, t, %4;\n\tadd.u32 t, t, %5;\n\tadd.u32 t, t, %6;\n\t}" ::"r"(d), "r"(a_lo), "r"(a_hi),
+               "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum));
+}
+
+struct IssueCtx {
+  uint32_t a_hi, b_hi, planes_enc, slot_enc, nslot, kinc, kstep;
+  uint32_t slot_w0, acc0;   // per group: ring slot of window plane 0, TMEM address of accumulator 0
+};
+
 // Issue the MMAs of one weight chunk: table entries [ea, ea_end) x NKS k-steps.  An entry is
-// (A descriptor base of the window plane, B row-block offset | accumulate flag, TMEM address,
-// instruction descriptor); `overwrite_ok` = this is the first chunk, honour the entry's flag.
-template <int NKS>
-__device__ __forceinline__ void issue_entries(uint32_t ea, uint32_t ea_end, uint32_t aoff, uint32_t wb,
-                                              bool overwrite_ok, uint32_t a_hi, uint32_t b_hi, uint32_t kinc,
-                                              uint32_t kstep) {
+// (window plane q, B row-block offset | accumulate flag, TMEM column offset, instruction
+// descriptor); `overwrite_ok` = this is the first chunk, honour the entry's flag.
+template <int NKS, bool FAKE = false>
+__device__ __forceinline__ void issue_entries(const IssueCtx& ic, uint32_t ea, uint32_t ea_end, uint32_t aoff,
+                                              uint32_t wb, bool overwrite_ok) {
+  if (ea >= ea_end) return;
+  uint32_t ex, ey, ez, ew;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ex), "=r"(ey), "=r"(ez), "=r"(ew) : "r"(ea));
+  const uint32_t a_base = ic.planes_enc + aoff;
 #pragma unroll 1
-  for (; ea < ea_end; ea += 16) {
-    uint32_t ex, ey, ez, ew;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ex), "=r"(ey), "=r"(ez), "=r"(ew) : "r"(ea));
-    const uint32_t a = ex + aoff;
+  while (true) {
+    ea += 16;
+    const bool more = ea < ea_end;
+    uint32_t nx = 0, ny = 0, nz = 0, nw = 0;
+    if (more)   // next entry's load overlaps this entry's issue
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(nx), "=r"(ny), "=r"(nz), "=r"(nw) : "r"(ea));
+    uint32_t slot = ic.slot_w0 + ex;            // window plane q -> ring slot
+    if (slot >= ic.nslot) slot -= ic.nslot;
+    const uint32_t a = a_base + slot * ic.slot_enc;
     const uint32_t b = (ey & 0x7FFFFFFFu) + wb;
-    umma_bf16_lohi(ez, a, a_hi, b, b_hi, ew, overwrite_ok ? (ey >> 31) : 1u);
+    const uint32_t d = ic.acc0 + ez;
+    if (FAKE) {
+      umma_fake(d, a, ic.a_hi, b, ic.b_hi, ew, overwrite_ok ? (ey >> 31) : 1u);
 #pragma unroll
-    for (int i = 1; i < NKS; ++i) umma_bf16_lohi(ez, a + i * kinc, a_hi, b + i * kstep, b_hi, ew, 1u);
+      for (int i = 1; i < NKS; ++i) umma_fake(d, a + i * ic.kinc, ic.a_hi, b + i * ic.kstep, ic.b_hi, ew, 1u);
+    } else {
+      umma_bf16_lohi(d, a, ic.a_hi, b, ic.b_hi, ew, overwrite_ok ? (ey >> 31) : 1u);
+#pragma unroll
+      for (int i = 1; i < NKS; ++i) umma_bf16_lohi(d, a + i * ic.kinc, ic.a_hi, b + i * ic.kstep, ic.b_hi, ew, 1u);
+    }
+    if (!more) break;
+    ex = nx; ey = ny; ez = nz; ew = nw;
   }
 }
 
@@ -388,7 +429,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
   uint4* s_tab = reinterpret_cast<uint4*>(tmem_ptr + 4);             // [kMaxEnt] MMA table of the group
-  float* s_par = reinterpret_cast<float*>(s_tab + kMaxEnt);          // [2 halves][bias|mul|add][kMaxN]
+  float* s_par = reinterpret_cast<float*>(s_tab + kMaxIss * kMaxEnt);          // [2 halves][bias|mul|add][kMaxN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -396,14 +437,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.nslot; ++i) {
       mbar_init(&plane_full[i], 1);
-      mbar_init(&plane_empty[i], 1);
+      mbar_init(&plane_empty[i], p.n_iss);
     }
     for (int i = 0; i < p.wslot; ++i) {
       mbar_init(&w_full[i], 1);
-      mbar_init(&w_empty[i], 1);
+      mbar_init(&w_empty[i], p.n_iss);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_full[i], p.n_iss);
       mbar_init(&acc_empty[i], 8);
     }
     fence_barrier_init();
@@ -464,36 +505,49 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
+  } else if (warp >= 1 && warp <= p.n_iss) {
+    // ===================================================================== MMA issuers
     // Window plane q of a group feeds the accumulators zi = q - kd for the depth taps
     // kd in [kd_lo, kd_hi]: adjacent TMEM column blocks, and adjacent row blocks j = K-1-kd of
     // the packed weight tile, so one MMA of N_mma = ns*N covers ns of them.  The warp builds a
     // small table per group ("first" entries: one per (q, kd) pair, used on the very first weight
     // chunk where each accumulator's first touch must overwrite; "main" entries: stacked runs
     // of up to smax taps), then ONE elected lane walks chunk -> entry -> k-step with two adds
-    // per instruction.
+    // per instruction.  A single thread cannot issue narrow MMAs (N = 48: 24 tensor cycles each)
+    // fast enough, so up to two issuer warps run side by side on DISJOINT accumulators: issuer i
+    // owns the output planes [i*nze/n_iss, (i+1)*nze/n_iss) of every group (tcgen05.mma from
+    // different threads are unordered, which is harmless when they never share an accumulator).
+    const int iss = warp - 1;
+    uint4* tab = s_tab + iss * kMaxEnt;
     const bool leader = elect_one();
-    const uint32_t a_hi = ((p.row_pitch >> 4) & 0x3FFFu) | (1u << 14);     // SBO | descriptor version
-    const uint32_t a_lbo = ((p.cg_pitch >> 4) & 0x3FFFu) << 16;
-    const uint32_t b_hi = (256u >> 4) | (1u << 14);
-    const uint32_t planes_enc = (smem_u32(s_planes) >> 4) | a_lbo;
-    const uint32_t slot_enc = p.slot_stride >> 4;
+    IssueCtx ic;
+    ic.a_hi = ((p.row_pitch >> 4) & 0x3FFFu) | (1u << 14);                 // SBO | descriptor version
+    ic.b_hi = (256u >> 4) | (1u << 14);
+    ic.planes_enc = (smem_u32(s_planes) >> 4) | (((p.cg_pitch >> 4) & 0x3FFFu) << 16);   // | LBO
+    ic.slot_enc = p.slot_stride >> 4;
+    ic.nslot = (uint32_t)p.nslot;
+    ic.kinc = (2 * p.cg_pitch) >> 4;                                       // one k-step = 2 channel groups
+    ic.kstep = p.kstep_bytes >> 4;
     const uint32_t w_enc = (smem_u32(s_w) >> 4) | ((128u >> 4) << 16);
-    const uint32_t kstep_enc = p.kstep_bytes >> 4;
     const uint32_t wchunk_enc = p.wchunk_bytes >> 4;
     const uint32_t rowp_enc = p.row_pitch >> 4;
-    const uint32_t kinc = (2 * p.cg_pitch) >> 4;                            // one k-step = 2 channel groups
-    const uint32_t kjump = (p.src1_off >> 4) - (uint32_t)p.KS0 * kinc;      // extra offset entering src1
+    const uint32_t kjump = (p.src1_off >> 4) - (uint32_t)p.KS0 * ic.kinc;   // extra offset entering src1
     const uint32_t idesc0 = umma_idesc_bf16_f32(128, 0);
     const uint32_t idesc_n = (uint32_t)(p.N >> 3) << 17;
-    const uint32_t nb_enc = (uint32_t)(p.N * 2);                            // one depth tap of B rows, >>4
-    const uint32_t tab_addr = smem_u32(s_tab);
+    const uint32_t nb_enc = (uint32_t)(p.N * 2);                           // one depth tap of B rows, >>4
+    const uint32_t tab_addr = smem_u32(tab);
     const bool stream_w = !p.w_resident;
-    uint32_t wctr = 0, gctr = 0;
-    uint32_t pc_ready = 0;  // planes of the ring already waited for (global plane counter)
-    uint32_t pc_base = 0;   // global plane counter of the current item's plane 0
+    const bool fake = (p.flags & F_NOMMA) != 0;
+    // ring cursors, advanced incrementally (no divisions on the issue path)
+    uint32_t slot_w0 = 0;                  // ring slot of the current window's plane 0
+    uint32_t rslot = 0, rphase = 0;        // next plane_full barrier to wait for
+    uint32_t planes_waited = 0, pc_base = 0;
+    uint32_t wslot = 0, wphase = 0;        // next streamed weight chunk
+    uint32_t gctr = 0;
+    int tab_nze = -1, n_first = 0, n_main = 0;
     bool w_waited = false;
+    long long dbg_acc = 0, dbg_plane = 0, dbg_w = 0, dbg_nchunk = 0, dbg_issue = 0, dbg_tab = 0;
+    const long long dbg_t0 = clock64();
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const ItemCoord c = decode_item(p, item);
       const int npl = c.lz + 2 * p.pad;
@@ -502,45 +556,59 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
         const int nze = min(p.NZ, c.lz - g * p.NZ);
         const int win = nze + 2 * p.pad;
         const uint32_t ab = gctr & 1;
-        // ---- table: lane q owns window plane q
-        int cnt = 0, kd_hi = 0, nruns = 0;
-        if (lane < win) {
-          const int kd_lo = max(0, lane - (nze - 1));
-          kd_hi = min(2 * p.pad, lane);
-          cnt = kd_hi - kd_lo + 1;
-          nruns = (cnt + p.smax - 1) / p.smax;
-        }
-        int sf = cnt, sm = nruns;  // inclusive scans
+        if (nze != tab_nze) {
+          // ---- (re)build the table for this window shape: lane q owns window plane q.  Entries
+          // are position independent: (q, B row-block offset | accumulate flag, TMEM column offset
+          // of the first accumulator, instruction descriptor).
+          long long tt0 = 0;
+          if (p.dbg) tt0 = clock64();
+          __syncwarp();
+          const int z_lo = (iss * nze) / p.n_iss, z_hi = ((iss + 1) * nze) / p.n_iss;
+          int cnt = 0, kd_hi = 0, nruns = 0;
+          if (lane < win && z_hi > z_lo) {
+            const int kd_lo = max(0, lane - (z_hi - 1));
+            kd_hi = min(2 * p.pad, lane - z_lo);
+            cnt = max(0, kd_hi - kd_lo + 1);
+            nruns = (cnt + p.smax - 1) / p.smax;
+          }
+          int sf = cnt, sm = nruns;  // inclusive scans
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int tf = __shfl_up_sync(0xffffffffu, sf, o), tm = __shfl_up_sync(0xffffffffu, sm, o);
-          if (lane >= o) { sf += tf; sm += tm; }
-        }
-        const int n_first = __shfl_sync(0xffffffffu, sf, 31), n_main = __shfl_sync(0xffffffffu, sm, 31);
-        if (lane < win) {
-          const uint32_t pc = pc_base + g * p.NZ + lane;
-          const uint32_t a_q = planes_enc + (pc % p.nslot) * slot_enc;
-          const uint32_t acc0 = tmem_base + ab * p.NZ * p.N;
+          for (int o = 1; o < 32; o <<= 1) {
+            const int tf = __shfl_up_sync(0xffffffffu, sf, o), tm = __shfl_up_sync(0xffffffffu, sm, o);
+            if (lane >= o) { sf += tf; sm += tm; }
+          }
+          n_first = __shfl_sync(0xffffffffu, sf, 31);
+          n_main = __shfl_sync(0xffffffffu, sm, 31);
           for (int i = 0; i < cnt; ++i) {
             const int kd = kd_hi - i;
-            s_tab[sf - cnt + i] = make_uint4(a_q, (uint32_t)(p.K - 1 - kd) * nb_enc | (kd > 0 ? 0x80000000u : 0u),
-                                             acc0 + (lane - kd) * p.N, idesc0 + idesc_n);
+            tab[sf - cnt + i] = make_uint4((uint32_t)lane, (uint32_t)(p.K - 1 - kd) * nb_enc | (kd > 0 ? 0x80000000u : 0u),
+                                           (uint32_t)((lane - kd) * p.N), idesc0 + idesc_n);
           }
           for (int r = 0; r < nruns; ++r) {
             const int kd = kd_hi - r * p.smax;
             const int ns = min(p.smax, cnt - r * p.smax);
-            s_tab[n_first + sm - nruns + r] =
-                make_uint4(a_q, (uint32_t)(p.K - 1 - kd) * nb_enc | 0x80000000u, acc0 + (lane - kd) * p.N,
-                           idesc0 + (uint32_t)ns * idesc_n);
+            tab[n_first + sm - nruns + r] = make_uint4((uint32_t)lane, (uint32_t)(p.K - 1 - kd) * nb_enc | 0x80000000u,
+                                                       (uint32_t)((lane - kd) * p.N), idesc0 + (uint32_t)ns * idesc_n);
           }
+          tab_nze = nze;
+          __syncwarp();
+          if (p.dbg) dbg_tab += clock64() - tt0;
         }
-        __syncwarp();
         if (leader) {
+          long long tq0 = 0;
+          if (p.dbg) tq0 = clock64();
           mbar_wait(&acc_empty[ab], ((gctr >> 1) & 1) ^ 1);
+          if (p.dbg) { const long long t = clock64(); dbg_acc += t - tq0; tq0 = t; }
           const uint32_t need = pc_base + (uint32_t)min(npl, g * p.NZ + win);
-          for (; pc_ready < need; ++pc_ready)
-            mbar_wait(&plane_full[pc_ready % p.nslot], (pc_ready / p.nslot) & 1);
+          while (planes_waited < need) {
+            mbar_wait(&plane_full[rslot], rphase);
+            ++planes_waited;
+            if (++rslot == ic.nslot) { rslot = 0; rphase ^= 1; }
+          }
+          if (p.dbg) dbg_plane += clock64() - tq0;
           tc_fence_after();
+          ic.slot_w0 = slot_w0;
+          ic.acc0 = tmem_base + ab * p.NZ * p.N;
           int t = 0;
           for (int kh = 0; kh < p.K; ++kh)
             for (int kw = 0; kw < p.K; ++kw, ++t) {
@@ -548,8 +616,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
               for (int kc = 0; kc < p.nkc; ++kc) {
                 uint32_t wslot_i;
                 if (stream_w) {
-                  wslot_i = wctr % p.wslot;
-                  mbar_wait(&w_full[wslot_i], (wctr / p.wslot) & 1);
+                  wslot_i = wslot;
+                  long long tq1 = 0;
+                  if (p.dbg) tq1 = clock64();
+                  mbar_wait(&w_full[wslot_i], wphase);
+                  if (p.dbg) { dbg_w += clock64() - tq1; ++dbg_nchunk; }
                   tc_fence_after();
                 } else {
                   wslot_i = t * p.nkc + kc;
@@ -563,42 +634,51 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
                 const int ks_lo = kc * p.KC;
                 const int nks = min(p.KS, ks_lo + p.KC) - ks_lo;
                 const bool firstc = (t | kc) == 0;
-                const uint32_t aoff = tapoff + ks_lo * kinc + (ks_lo >= p.KS0 ? kjump : 0u);
-                uint32_t ea = tab_addr + (firstc ? 0u : (uint32_t)n_first * 16u);
+                const uint32_t aoff = tapoff + ks_lo * ic.kinc + (ks_lo >= p.KS0 ? kjump : 0u);
+                const uint32_t ea = tab_addr + (firstc ? 0u : (uint32_t)n_first * 16u);
                 const uint32_t ea_end = ea + (uint32_t)(firstc ? n_first : n_main) * 16u;
-                switch (nks) {   // straight-line k-step issue for the common chunk lengths
-                  case 1: issue_entries<1>(ea, ea_end, aoff, wb, firstc, a_hi, b_hi, kinc, kstep_enc); break;
-                  case 2: issue_entries<2>(ea, ea_end, aoff, wb, firstc, a_hi, b_hi, kinc, kstep_enc); break;
-                  case 3: issue_entries<3>(ea, ea_end, aoff, wb, firstc, a_hi, b_hi, kinc, kstep_enc); break;
-                  case 4: issue_entries<4>(ea, ea_end, aoff, wb, firstc, a_hi, b_hi, kinc, kstep_enc); break;
-                  case 5: issue_entries<5>(ea, ea_end, aoff, wb, firstc, a_hi, b_hi, kinc, kstep_enc); break;
-                  case 6: issue_entries<6>(ea, ea_end, aoff, wb, firstc, a_hi, b_hi, kinc, kstep_enc); break;
-                  default:
-                    for (int i = 0; i < nks; ++i)
-                      issue_entries<1>(ea, ea_end, aoff + i * kinc, wb + i * kstep_enc, firstc && i == 0, a_hi,
-                                       b_hi, kinc, kstep_enc);
+                long long ti0 = 0;
+                if (p.dbg) ti0 = clock64();
+                if (fake) {
+                  issue_entries<3, true>(ic, ea, ea_end, aoff, wb, firstc);
+                } else {
+                  switch (nks) {   // straight-line k-step issue for the common chunk lengths
+                    case 1: issue_entries<1>(ic, ea, ea_end, aoff, wb, firstc); break;
+                    case 2: issue_entries<2>(ic, ea, ea_end, aoff, wb, firstc); break;
+                    case 3: issue_entries<3>(ic, ea, ea_end, aoff, wb, firstc); break;
+                    case 4: issue_entries<4>(ic, ea, ea_end, aoff, wb, firstc); break;
+                    case 5: issue_entries<5>(ic, ea, ea_end, aoff, wb, firstc); break;
+                    case 6: issue_entries<6>(ic, ea, ea_end, aoff, wb, firstc); break;
+                    default:
+                      for (int i = 0; i < nks; ++i)
+                        issue_entries<1>(ic, ea, ea_end, aoff + i * ic.kinc, wb + i * ic.kstep, firstc && i == 0);
+                  }
                 }
+                if (p.dbg) dbg_issue += clock64() - ti0;
                 if (stream_w) {
                   umma_commit(&w_empty[wslot_i]);
-                  ++wctr;
+                  if (++wslot == (uint32_t)p.wslot) { wslot = 0; wphase ^= 1; }
                 }
               }
             }
           // planes that leave the window: the NZ oldest, or everything at the end of the item
           const int nrel = (g == ngroups - 1) ? win : nze;
-          uint32_t slot = (pc_base + g * p.NZ) % p.nslot;
           for (int i = 0; i < nrel; ++i) {
-            umma_commit(&plane_empty[slot]);
-            slot = slot + 1 == (uint32_t)p.nslot ? 0u : slot + 1;
+            umma_commit(&plane_empty[slot_w0]);
+            if (++slot_w0 == ic.nslot) slot_w0 = 0;
           }
           umma_commit(&acc_full[ab]);
         }
         w_waited = true;
-        __syncwarp();  // s_tab is rewritten for the next group
       }
       pc_base += npl;
     }
-  } else {
+    if (p.dbg && leader && iss == 0) {
+      long long* o = p.dbg + (size_t)blockIdx.x * 8;
+      o[0] = clock64() - dbg_t0; o[1] = dbg_acc; o[2] = dbg_plane; o[3] = dbg_w; o[4] = dbg_nchunk; o[5] = dbg_issue; o[6] = dbg_tab;
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
     // ===================================================================== epilogue (8 warps)
     // Two halves of four warps; a warp may only touch the TMEM lane quadrant (warp % 4), so the
     // halves split a group's planes between them (alternating) and both see every accumulator.
@@ -606,8 +686,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     // RMSNorm is thread-local.  Per-channel parameters of the current sample sit in shared
     // memory (one copy per half), so the inner loops are LDS.128 + FMA only.
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int tid_h = (((warp - 2) & 3) << 5) | lane;  // 0..127 within the half
+    const int half = (warp - 4) >> 2;
+    const int tid_h = (((warp - 4) & 3) << 5) | lane;  // 0..127 within the half
     const int m = q * 32 + lane;
     const int hl = m >> 3, wl = m & 7;
     const size_t plane_vox = (size_t)p.H * p.W;
@@ -649,8 +729,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
           const size_t vox = (size_t)d * plane_vox + (size_t)h * p.W + w;  // within one (b, cg)
           const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (ab * p.NZ + zi) * p.N;
           float rs = 1.f;
-          if (p.pre_src && ec.valid) {
-            // fused pre-attention RMSNorm: 1 / max(||x||_2, 1e-12) of this voxel of the input
+          if (p.ss_in) {
+            // fused pre-attention RMSNorm: 1 / max(||x||_2, 1e-12); ||x||^2 came from x's producer
+            if (ec.valid) rs = 1.f / fmaxf(sqrtf(__ldg(p.ss_in + (size_t)c.b * cgs + vox)), 1e-12f);
+          } else if (p.pre_src && ec.valid) {
             const bf16* src = p.pre_src + (((size_t)c.b * p.pre_cgtot + p.pre_cgoff) * cgs + vox) * 8;
             float ss0 = 0.f, ss1 = 0.f;
             for (int cgi = 0; cgi < p.pre_cg; cgi += 2) {
@@ -664,6 +746,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
             }
             rs = 1.f / fmaxf(sqrtf(ss0 + ss1), 1e-12f);
           }
+          ec.ssq = 0.f;
           if (p.flags & F_QSOFTMAX) {
             if (p.q_dh == 32) epi_qsoftmax<32>(p, ec, trow, vox, rs);
             else epi_qsoftmax<16>(p, ec, trow, vox, rs);
@@ -673,6 +756,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
           } else {
             epi_affine(p, ec, trow, vox, rs);
           }
+          if (p.ss_out && ec.valid) p.ss_out[(size_t)c.b * cgs + vox] = ec.ssq;
         }
         tc_fence_before();
         __syncwarp();
@@ -724,9 +808,16 @@ int make_plane_tmap(CUtensorMap* tm, const Act& a, int BW, int BH, int cg) {
   return 0;
 }
 
+long long* g_conv_dbg = nullptr;
 constexpr uint32_t kSmemLimit = 227 * 1024 - 128;  // 227 KB opt-in maximum minus the alignment pad
 
 }  // namespace
+
+// debug: per-CTA cycle counters of the last instrumented launch (FTB_CONV_DBG=1): [grid][8]
+int conv_debug_read(long long* host, int n) {
+  if (!g_conv_dbg) return -1;
+  return cudaMemcpy(host, g_conv_dbg, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+}
 
 int make_voxel_tmap(CUtensorMap* tm, const Act& a, int box_vox, int box_cg) {
   PFN_encodeTiled enc = get_encode();
@@ -779,7 +870,7 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   const int nchunks = p.taps * p.nkc;
   const int sms = num_sms();
   const uint32_t bar_bytes =
-      (2 * kMaxSlots + 2 * kMaxWSlots + 4) * 8 + 16 + kMaxEnt * 16 + 2 * 3 * kMaxN * 4;
+      (2 * kMaxSlots + 2 * kMaxWSlots + 4) * 8 + 16 + kMaxIss * kMaxEnt * 16 + 2 * 3 * kMaxN * 4;
   const size_t all_w = (size_t)p.taps * p.wtap_bytes;
 
   // ---- tile height, planes per group (NZ) and ring sizing against the 227 KB shared-memory
@@ -864,6 +955,16 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   FTB_CHECK(tc <= 512, "conv: accumulators exceed TMEM");
   p.tmem_cols = tc;
 
+  p.n_iss = p.NZ >= 2 ? kMaxIss : 1;
+  if (const char* env = getenv("FTB_NISS")) { const int v = atoi(env); if (v >= 1 && v <= kMaxIss && v <= p.NZ) p.n_iss = v; }
+  p.dbg = nullptr;
+  if (getenv("FTB_CONV_DBG")) {
+    static long long* dbuf = nullptr;
+    if (!dbuf) FTB_CUDA(cudaMalloc(&dbuf, 256 * 8 * sizeof(long long)));
+    FTB_CUDA(cudaMemsetAsync(dbuf, 0, 256 * 8 * sizeof(long long), st));
+    p.dbg = dbuf;
+    g_conv_dbg = dbuf;
+  }
   p.wpack = w.w;
   p.w_batch_stride = w.batch_stride;
   p.out = out.p; p.out_cgtot = out.cg();
@@ -872,6 +973,8 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   p.mul = e.mul; p.add = e.add; p.mul_stride = e.mul_stride; p.add_stride = e.add_stride;
   p.resid = e.resid ? e.resid->p : nullptr;
   p.resid_cgtot = e.resid ? e.resid->cg() : 0; p.resid_cgoff = e.resid_cgoff;
+  p.ss_in = e.prenorm ? e.prenorm_ss : nullptr;
+  p.ss_out = e.sumsq_out;
   if (e.prenorm) { p.pre_src = a0.p; p.pre_cgtot = a0.cg(); p.pre_cgoff = s0.cgoff; p.pre_cg = s0.cg; }
   p.q_dh = e.q_dim_head; p.q_scale = e.q_scale;
 
@@ -891,7 +994,8 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
     q.wpack = w.w + (size_t)nt * w.tile_elems();
     q.bias = e.bias ? e.bias + (size_t)nt * w.n : nullptr;
     q.out_cgoff = out_cgoff + nt * (w.n / 8);
-    q.flags = (e.silu ? F_SILU : 0) | ((e.q_softmax_heads && nt == 0) ? F_QSOFTMAX : 0);
+    q.flags = (e.silu ? F_SILU : 0) | ((e.q_softmax_heads && nt == 0) ? F_QSOFTMAX : 0) |
+              (getenv("FTB_CONV_NOMMA") ? F_NOMMA : 0);
     int prof = -1;
     if (prof_enabled()) {
       // algorithmic work of this launch: real (unpadded) channel counts

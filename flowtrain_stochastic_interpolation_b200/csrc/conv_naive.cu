@@ -26,6 +26,8 @@ struct NaiveParams {
   const bf16* resid;
   int resid_cgtot, resid_cgoff;
   int prenorm, silu, qsoftmax, q_dh;
+  const float* ss_in;
+  float* ss_out;
   float q_scale;
 };
 
@@ -84,7 +86,9 @@ __global__ void conv_naive_kernel(const NaiveParams p) {
   const int d = (int)(vox / ((size_t)p.W * p.H));
 
   float rs = 1.f;
-  if (p.prenorm) {
+  if (p.prenorm && p.ss_in) {
+    rs = 1.f / fmaxf(sqrtf(p.ss_in[(size_t)b * cgs + vox]), 1e-12f);
+  } else if (p.prenorm) {
     float ss = 0.f;
     for (int cgi = 0; cgi < p.cg0; ++cgi) {
       float f[8];
@@ -128,6 +132,7 @@ __global__ void conv_naive_kernel(const NaiveParams p) {
   }
   const float* mul = p.mul ? p.mul + (size_t)b * p.mul_stride : nullptr;
   const float* add = p.add ? p.add + (size_t)b * p.add_stride : nullptr;
+  float ssq = 0.f;
   for (int c0 = 0; c0 < p.N; c0 += 16) {
     naive_chunk(p, b, d, h, w, c0, acc);
     for (int j = 0; j < 16; ++j) {
@@ -140,6 +145,7 @@ __global__ void conv_naive_kernel(const NaiveParams p) {
       if (p.resid)
         x += __bfloat162float(
             p.resid[(((size_t)b * p.resid_cgtot + p.resid_cgoff + (ch >> 3)) * cgs + vox) * 8 + (ch & 7)]);
+      ssq += x * x;
       if (p.out_f32) {
         if (ch < p.out_f32_c) p.out_f32[((size_t)b * p.out_f32_c + ch) * cgs + vox] = x;
       } else {
@@ -148,6 +154,7 @@ __global__ void conv_naive_kernel(const NaiveParams p) {
       }
     }
   }
+  if (p.ss_out) p.ss_out[(size_t)b * cgs + vox] = ssq;
 }
 
 // fp32 [Cout][Cin][kd][kh][kw] -> bf16 [ntile][kh][kw][ks][j = K-1-kd][n/8][2][8][8]
@@ -210,6 +217,7 @@ int conv_naive(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   p.norm = e.norm; p.mul = e.mul; p.add = e.add; p.mul_stride = e.mul_stride; p.add_stride = e.add_stride;
   p.resid = e.resid ? e.resid->p : nullptr;
   p.resid_cgtot = e.resid ? e.resid->cg() : 0; p.resid_cgoff = e.resid_cgoff;
+  p.ss_in = e.prenorm ? e.prenorm_ss : nullptr; p.ss_out = e.sumsq_out;
   p.prenorm = e.prenorm; p.silu = e.silu; p.q_dh = e.q_dim_head; p.q_scale = e.q_scale;
   const size_t nthreads = (size_t)a0.B * a0.voxels();
   const int blocks = (int)((nthreads + 127) / 128);

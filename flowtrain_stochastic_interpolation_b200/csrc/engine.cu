@@ -427,7 +427,8 @@ struct Fwd {
   }
 
   // ResnetBlock.forward (:265-278); input may be the channel concat of (x0, x1)
-  int resnet(const std::string& p, const Act& x0, const Act* x1, int cout, Act* out) {
+  // `sumsq` (optional, [B][voxels]) receives ||out voxel||^2 for a following attention's pre-norm
+  int resnet(const std::string& p, const Act& x0, const Act* x1, int cout, Act* out, float* sumsq = nullptr) {
     const Act& a = x0;
     ConvSrc s0{&x0, 0, x0.cg()}, s1{};
     if (x1) s1 = ConvSrc{x1, 0, x1->cg()};
@@ -455,18 +456,20 @@ struct Fwd {
     e2.mul = U->gains.at(p + ".block2.norm.g").gs;
     e2.silu = true;
     e2.resid = resp;
+    e2.sumsq_out = sumsq;
     FTB_TRY(conv(p + ".block2.proj", ConvSrc{&h1, 0, h1.cg()}, ConvSrc{}, e2, *out));
     tap(p, *out);
     return 0;
   }
 
   // x + attn(x)  (:695, :702, :712)
-  int attention(const std::string& p, const Act& x, bool full, Act* out) {
+  int attention(const std::string& p, const Act& x, const float* x_sumsq, bool full, Act* out) {
     const ftb_unet_cfg& c = U->cfg;
     const int heads = c.attn_heads, dh = c.attn_dim_head, hd = heads * dh;
     Act qkv = act(3 * hd, x.D, x.H, x.W);
     ConvEpilogue eq;
     eq.prenorm = true;
+    eq.prenorm_ss = x_sumsq;
     if (!full) { eq.q_softmax_heads = heads; eq.q_dim_head = dh; eq.q_scale = 1.f / sqrtf((float)dh); }
     FTB_TRY(conv(p + ".to_qkv", ConvSrc{&x, 0, x.cg()}, ConvSrc{}, eq, qkv));
     *out = act(x.C, x.D, x.H, x.W);
@@ -547,8 +550,9 @@ struct Fwd {
       Act a1, a2, a3, a4;
       FTB_TRY(resnet(p + ".0", cur, nullptr, din, &a1));
       skips.push_back(a1);
-      FTB_TRY(resnet(p + ".1", a1, nullptr, din, &a2));
-      FTB_TRY(attention(p + ".2", a2, c.full_attn[i] != 0, &a3));
+      float* ss = f32((size_t)B * a1.voxels());
+      FTB_TRY(resnet(p + ".1", a1, nullptr, din, &a2, ss));
+      FTB_TRY(attention(p + ".2", a2, ss, c.full_attn[i] != 0, &a3));
       skips.push_back(a3);
       if (i >= n - 1) {
         a4 = act(dout, a3.D, a3.H, a3.W);
@@ -565,8 +569,9 @@ struct Fwd {
     {
       Act m1, m2, m3;
       const int mid = U->dims.back();
-      FTB_TRY(resnet("mid_block1", cur, nullptr, mid, &m1));
-      FTB_TRY(attention("mid_attn", m1, true, &m2));
+      float* ss = f32((size_t)B * cur.voxels());
+      FTB_TRY(resnet("mid_block1", cur, nullptr, mid, &m1, ss));
+      FTB_TRY(attention("mid_attn", m1, ss, true, &m2));
       FTB_TRY(resnet("mid_block2", m2, nullptr, mid, &m3));
       cur = m3;
     }
@@ -577,8 +582,9 @@ struct Fwd {
       Act s = skips.back(); skips.pop_back();
       FTB_TRY(resnet(p + ".0", cur, &s, dout, &a1));
       s = skips.back(); skips.pop_back();
-      FTB_TRY(resnet(p + ".1", a1, &s, dout, &a2));
-      FTB_TRY(attention(p + ".2", a2, c.full_attn[n - 1 - i] != 0, &a3));
+      float* ss = f32((size_t)B * a1.voxels());
+      FTB_TRY(resnet(p + ".1", a1, &s, dout, &a2, ss));
+      FTB_TRY(attention(p + ".2", a2, ss, c.full_attn[n - 1 - i] != 0, &a3));
       if (i == n - 1) {
         a4 = act(din, a3.D, a3.H, a3.W);
         FTB_TRY(conv(p + ".3", ConvSrc{&a3, 0, a3.cg()}, ConvSrc{}, ConvEpilogue{}, a4));
@@ -855,6 +861,8 @@ int ftb_test_conv3d(const float* x, int c1, const float* x2, int c2, const float
   FTB_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
+
+int ftb_test_conv_debug(long long* host, int n) { return conv_debug_read(host, n); }
 
 int ftb_test_trilinear(const float* x, int B, int C, int X, int Y, int Z, int Xo, int Yo, int Zo,
                        float* out, void* stream) {

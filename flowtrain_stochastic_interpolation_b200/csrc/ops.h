@@ -37,6 +37,8 @@ struct ConvEpilogue {
   const Act* resid = nullptr;    // residual added last (blocked bf16, same spatial dims)
   int resid_cgoff = 0;
   bool prenorm = false;          // row scale 1/max(||src0 voxel||_2, 1e-12) (fused pre-RMSNorm)
+  const float* prenorm_ss = nullptr;  // optional [B][voxels]: ||src0 voxel||^2 from the producer's sumsq_out
+  float* sumsq_out = nullptr;    // optional [B][voxels]: sum over channels of the stored output squared
   int q_softmax_heads = 0;       // >0: softmax over each dim_head group of the first N tile
   int q_dim_head = 0;
   float q_scale = 1.f;
@@ -58,6 +60,8 @@ int conv_naive(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
                Act& out, int out_cgoff, cudaStream_t st);
 int conv_dispatch(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const ConvEpilogue& e,
                   Act& out, int out_cgoff, cudaStream_t st);
+
+int conv_debug_read(long long* host, int n);
 
 // 3-D TMA view of a blocked activation as (8 channels, voxels, B*CG); box = (8, box_vox, box_cg):
 // lands in shared memory as [cg][voxel][8], the no-swizzle MN-major UMMA operand layout.

@@ -46,5 +46,23 @@ def run(c1, c2, cout, k, n, full):
           f"{byts/best/1e6:7.1f} GB/s  [{os.environ.get('FTB_NZ','-')},{os.environ.get('FTB_WSLOT','-')}]", flush=True)
 
 
+def dbg():
+    try:
+        f = _lib.lib.ftb_test_conv_debug
+    except AttributeError:
+        return
+    buf = (C.c_longlong * (148 * 8))()
+    if f(buf, 148 * 8) != 0:
+        return
+    import statistics
+    rows = [buf[i * 8:(i + 1) * 8] for i in range(148) if buf[i * 8] > 0]
+    if rows:
+        med = [statistics.median(r[k] for r in rows) for k in range(7)]
+        print(f"    issuer0 cycles: total {med[0]:.0f}  wait acc {med[1]:.0f}  planes {med[2]:.0f}  weights {med[3]:.0f}  "
+              f"chunks {med[4]:.0f}  -> busy {med[0]-med[1]-med[2]-med[3]:.0f} (issue {med[5]:.0f}, table {med[6]:.0f})", flush=True)
+
+
 for s in SHAPES:
     run(*s)
+    if os.environ.get("FTB_CONV_DBG"):
+        dbg()
