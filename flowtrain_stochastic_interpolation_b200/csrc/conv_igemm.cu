@@ -45,7 +45,7 @@ constexpr int kMaxWSlots = 32;
 constexpr int kMaxEnt = 96;   // MMA table entries per group (first-chunk pairs + stacked runs)
 constexpr int kMaxKS = 32;    // k-steps (Cin_pad / 16)
 
-enum : int { F_SILU = 1, F_QSOFTMAX = 2, F_NOMMA = 4 };
+enum : int { F_SILU = 1, F_QSOFTMAX = 2, F_NOMMA = 4, F_PLAIN = 8 };
 
 struct IgemmParams {
   int B, D, H, W;
@@ -208,6 +208,34 @@ __device__ __forceinline__ void epi_affine(const IgemmParams& p, EpiCtx& ec, uin
         v[j4 + 3] = fmaf(__uint_as_float(r1[j4 + 3]) * rs, mu.w, ad.w);
       }
       epi_store16(p, ec, c0 + 16, vox, v);
+    }
+  }
+}
+
+// y = acc * rs: no bias, affine, activation or residual (k and v of to_qkv)
+__device__ __forceinline__ void epi_plain(const IgemmParams& p, EpiCtx& ec, uint32_t trow, size_t vox, float rs) {
+  for (int c0 = 0; c0 < p.N; c0 += 32) {
+    uint32_t r0[16], r1[16];
+    const bool two = c0 + 16 < p.N;
+    tmem_ld16(trow + c0, r0);
+    if (two) tmem_ld16(trow + c0 + 16, r1);
+    tmem_ld_wait();
+    if (!ec.valid) continue;
+    bf16* dst = ec.out_b + ((size_t)(p.out_cgoff + (c0 >> 3)) * ec.cgs + vox) * 8;
+    float f[8];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r0[hf * 8 + j]) * rs;
+      *reinterpret_cast<uint4*>(dst + (size_t)hf * ec.cgs * 8) = pack_bf16x8(f);
+    }
+    if (two) {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r1[hf * 8 + j]) * rs;
+        *reinterpret_cast<uint4*>(dst + (size_t)(2 + hf) * ec.cgs * 8) = pack_bf16x8(f);
+      }
     }
   }
 }
@@ -753,6 +781,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
           } else if (p.norm) {
             if (p.N == 48) epi_norm_regs<3>(p, ec, trow, vox, rs);
             else epi_norm_2pass(p, ec, trow, vox, rs);
+          } else if (p.flags & F_PLAIN) {
+            epi_plain(p, ec, trow, vox, rs);
           } else {
             epi_affine(p, ec, trow, vox, rs);
           }
@@ -891,7 +921,7 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   }
   while (nz_cap > 1 && (nz_cap * p.K > kMaxEnt / 2 || nz_cap + 2 * p.pad > 32)) --nz_cap;
   FTB_CHECK(nz_cap >= 1, "conv: N tile too wide for a double-buffered accumulator");
-  for (int th = a0.H >= 16 ? 16 : a0.H; th >= 1 && !fits; th = th / 2) {
+  for (int th = a0.H >= 16 ? 16 : a0.H; th >= 1 && !fits; th = th / 2) {   // first tile height that fits wins
     p.TH = th;
     p.BH = p.TH + 2 * p.pad;
     p.nHt = cdiv(a0.H, p.TH);
@@ -902,23 +932,38 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
     p.slot_stride = (uint32_t)round_up((int)plane_bytes, 128);
     slack = (uint32_t)(16 - p.TH + 2) * p.row_pitch + 512;  // A rows of a partial tile over-read
     fixed = slack + bar_bytes + 256;
-    for (int nz = nz_cap; nz >= 1 && !fits; --nz) {
-      const size_t planes = (size_t)(nz + 2 * p.pad + 1) * p.slot_stride;  // window + 1 prefetch
-      p.NZ = nz;
-      if (w.batch_stride == 0 && nchunks <= kMaxWSlots && all_w + planes + fixed <= kSmemLimit) {
-        p.w_resident = 1;
-        p.wslot = nchunks;
-        fits = true;
-      } else {
-        p.w_resident = 0;
-        int ws = nchunks == 1 ? 2 : (p.wchunk_bytes <= 8192 ? 6 : (p.wchunk_bytes <= 16384 ? 4 : 3));
-        if (const char* env = getenv("FTB_WSLOT")) {
-          const int v = atoi(env);
-          if (v >= 2 && v <= kMaxWSlots) ws = v;
-        }
-        for (; ws >= 2 && !fits; --ws) {
-          p.wslot = ws;
-          if ((size_t)ws * p.wchunk_bytes + planes + fixed <= kSmemLimit) fits = true;
+    // Candidates (NZ, weight ring): score = shared-memory A reads per output plane
+    // ((NZ + halo) / NZ, the stacking efficiency) + the share of a group's planes that cannot be
+    // prefetched while the previous group computes (ring slots beyond the window), divided by
+    // the fill of the last group of a typical depth segment.  Measured on 48->48 @64^3:
+    // (NZ 4, ring 3) 300 us < (5, 4) 347 us < (3, 4) 421 us — the score orders them the same way.
+    double best_score = 1e30;
+    const int dseg = a0.D < 16 ? a0.D : 16;
+    int ws_hi = nchunks == 1 ? 2 : (p.wchunk_bytes <= 8192 ? 6 : (p.wchunk_bytes <= 16384 ? 4 : 3));
+    int ws_lo = 2;
+    if (const char* env = getenv("FTB_WSLOT")) {
+      const int v = atoi(env);
+      if (v >= 2 && v <= kMaxWSlots) ws_hi = ws_lo = v;
+    }
+    for (int nz = nz_cap; nz >= 1; --nz) {
+      const int win = nz + 2 * p.pad;
+      const double fill = (double)dseg / (cdiv(dseg, nz) * nz);
+      for (int ws = ws_hi + 1; ws >= ws_lo; --ws) {   // ws_hi + 1 stands for "resident"
+        const bool resident = ws == ws_hi + 1;
+        if (resident && !(w.batch_stride == 0 && nchunks <= kMaxWSlots)) continue;
+        const size_t wbytes = resident ? all_w : (size_t)ws * p.wchunk_bytes;
+        if (wbytes + (size_t)(win + 1) * p.slot_stride + fixed > kSmemLimit) continue;
+        int ns = (int)((kSmemLimit - fixed - wbytes) / p.slot_stride);
+        ns = ns > kMaxSlots ? kMaxSlots : ns;
+        const int spare = ns - win;
+        double score = (double)win / nz + 0.35 * (spare >= nz ? 0.0 : (double)(nz - spare) / nz);
+        score = score / fill - (resident ? 0.1 : 0.0) + (ws == 2 && !resident && nchunks > 1 ? 0.05 : 0.0);
+        if (score < best_score - 1e-9) {
+          best_score = score;
+          p.NZ = nz;
+          p.w_resident = resident ? 1 : 0;
+          p.wslot = resident ? nchunks : ws;
+          fits = true;
         }
       }
     }
@@ -996,6 +1041,8 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
     q.out_cgoff = out_cgoff + nt * (w.n / 8);
     q.flags = (e.silu ? F_SILU : 0) | ((e.q_softmax_heads && nt == 0) ? F_QSOFTMAX : 0) |
               (getenv("FTB_CONV_NOMMA") ? F_NOMMA : 0);
+    if (!(q.flags & F_QSOFTMAX) && !q.norm && !q.bias && !q.mul && !q.add && !e.silu && !q.resid && !q.out_f32 && !q.ss_out)
+      q.flags |= F_PLAIN;
     int prof = -1;
     if (prof_enabled()) {
       // algorithmic work of this launch: real (unpadded) channel counts

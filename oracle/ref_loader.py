@@ -39,6 +39,10 @@ def unet3d_module():
     return _load("ref_unet_attn_3d", "src/flowtrain/models/unet_attn_3d.py")
 
 
+def unet3d_cond_module():
+    return _load("ref_unet_attn_3d_cond_v3", "src/flowtrain/models/unet_attn_3d_cond_v3.py")
+
+
 def interpolation_module():
     return _load("ref_interpolation", "src/flowtrain/interpolation/interpolation.py")
 
@@ -87,5 +91,12 @@ def solvers_module():
 def build_reference_unet(cfg, params):
     """Instantiate the reference Unet3D and load the given state dict (strict)."""
     m = unet3d_module().Unet3D(**cfg)
+    m.load_state_dict(params, strict=True)
+    return m.eval()
+
+
+def build_reference_unet_cond(cfg, params):
+    """Instantiate the reference Unet3DCond v3 and load the given state dict (strict)."""
+    m = unet3d_cond_module().Unet3DCond(**cfg)
     m.load_state_dict(params, strict=True)
     return m.eval()

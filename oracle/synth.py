@@ -151,6 +151,79 @@ def unet3d_param_specs(cfg) -> "OrderedDict[str, tuple]":
     return s
 
 
+def unet3d_cond_param_specs(cfg) -> "OrderedDict[str, tuple]":
+    """name -> shape in ``state_dict()`` order of the reference Unet3DCond v3
+    (src/flowtrain/models/unet_attn_3d_cond_v3.py:598-764): init_conv_x, init_conv_ATb, time_mlp,
+    per stage [EmbedATb, MixATb, ResnetBlock, ResnetBlock, attention, down/up-sample]."""
+    assert not cfg.get("self_condition", False) and not cfg.get("time_sin_pos", False)
+    dim = cfg["dim"]
+    C = cfg["data_channels"]
+    tr = cfg["time_resolution"]
+    time_dim = dim * 4
+    heads, dh = cfg["attn_heads"], cfg["attn_dim_head"]
+    dims, in_out, full_attn = stage_plan(cfg)
+    n = len(in_out)
+
+    def embed_mix(prefix, d):
+        e = OrderedDict()
+        e[f"{prefix}.0.conv1.weight"] = (d, C, 5, 5, 5)      # EmbedATb :127-129
+        e[f"{prefix}.0.conv1.bias"] = (d,)
+        e[f"{prefix}.0.conv2.weight"] = (d, d, 5, 5, 5)
+        e[f"{prefix}.0.conv2.bias"] = (d,)
+        e[f"{prefix}.1.time_mlp.1.weight"] = (4 * d, time_dim)  # MixATb :164-173
+        e[f"{prefix}.1.time_mlp.1.bias"] = (4 * d,)
+        e[f"{prefix}.1.conv1.weight"] = (d, 2 * d, 3, 3, 3)
+        e[f"{prefix}.1.conv1.bias"] = (d,)
+        e[f"{prefix}.1.norm.g"] = (1, d, 1, 1, 1)
+        e[f"{prefix}.1.conv2.weight"] = (d, d, 3, 3, 3)
+        e[f"{prefix}.1.conv2.bias"] = (d,)
+        return e
+
+    s = OrderedDict()
+    s["init_conv_x.weight"] = (dim, C, 7, 7, 7)
+    s["init_conv_x.bias"] = (dim,)
+    s["init_conv_ATb.weight"] = (C, C, 7, 7, 7)
+    s["init_conv_ATb.bias"] = (C,)
+    s["time_mlp.0.freqs"] = (tr,)
+    s["time_mlp.0.phases"] = (tr,)
+    s["time_mlp.1.weight"] = (time_dim, tr)
+    s["time_mlp.1.bias"] = (time_dim,)
+    s["time_mlp.3.weight"] = (time_dim, time_dim)
+    s["time_mlp.3.bias"] = (time_dim,)
+    for i, ((din, dout), fa) in enumerate(zip(in_out, full_attn)):
+        last = i >= n - 1
+        s.update(embed_mix(f"downs.{i}", din))
+        s.update(_resnet_specs(f"downs.{i}.2", din, din, time_dim))
+        s.update(_resnet_specs(f"downs.{i}.3", din, din, time_dim))
+        s.update(_attn_specs(f"downs.{i}.4", din, heads, dh, fa))
+        if last:
+            s[f"downs.{i}.5.weight"] = (dout, din, 3, 3, 3)
+            s[f"downs.{i}.5.bias"] = (dout,)
+        else:
+            s[f"downs.{i}.5.conv.weight"] = (dout, din, 1, 1, 1)
+            s[f"downs.{i}.5.conv.bias"] = (dout,)
+    for i, ((din, dout), fa) in enumerate(zip(reversed(in_out), reversed(full_attn))):
+        last = i == n - 1
+        s.update(embed_mix(f"ups.{i}", dout))
+        s.update(_resnet_specs(f"ups.{i}.2", dout + din, dout, time_dim))
+        s.update(_resnet_specs(f"ups.{i}.3", dout + din, dout, time_dim))
+        s.update(_attn_specs(f"ups.{i}.4", dout, heads, dh, fa))
+        if last:
+            s[f"ups.{i}.5.weight"] = (din, dout, 3, 3, 3)
+            s[f"ups.{i}.5.bias"] = (din,)
+        else:
+            s[f"ups.{i}.5.conv.weight"] = (din, dout, 3, 3, 3)
+            s[f"ups.{i}.5.conv.bias"] = (din,)
+    mid = dims[-1]
+    s.update(_resnet_specs("mid_block1", mid, mid, time_dim))
+    s.update(_attn_specs("mid_attn", mid, heads, dh, True))
+    s.update(_resnet_specs("mid_block2", mid, mid, time_dim))
+    s.update(_resnet_specs("final_res_block", dim * 2, dim, time_dim))
+    s["final_conv.weight"] = (C, dim, 1, 1, 1)
+    s["final_conv.bias"] = (C,)
+    return s
+
+
 # ---------------------------------------------------------------------------------------
 # counter-based value synthesis
 # ---------------------------------------------------------------------------------------
@@ -199,6 +272,22 @@ def synth_param(seed: int, name: str, shape, cfg) -> torch.Tensor:
 def synth_unet3d_params(cfg, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
     specs = unet3d_param_specs(cfg)
     return OrderedDict((k, synth_param(seed, k, shp, cfg)) for k, shp in specs.items())
+
+
+def synth_unet3d_cond_params(cfg, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    specs = unet3d_cond_param_specs(cfg)
+    return OrderedDict((k, synth_param(seed, k, shp, cfg)) for k, shp in specs.items())
+
+
+def synth_atb(shape, seed: int) -> torch.Tensor:
+    """Synthetic conditioning volume: a random field kept on a top slab and a few vertical
+    'boreholes', zero elsewhere (stand-in for embed(X1)*mask, boreholes.py:111-126)."""
+    B, C, X, Y, Z = shape
+    v = synth_input(shape, seed, "atb")
+    u = _uniform01(seed, "atbmask", B * X * Y).reshape(B, 1, X, Y, 1)
+    mask = torch.from_numpy((u < 0.06).astype(np.float32)).expand(B, 1, X, Y, Z).clone()
+    mask[..., : max(1, Z // 16)] = 1.0
+    return v * mask
 
 
 def synth_input(shape, seed: int, name: str = "x") -> torch.Tensor:

@@ -57,6 +57,29 @@ def gen_unet():
     np.savez_compressed(os.path.join(OUT, "unet3d_small_seed3.npz"), y=y.numpy(), t=t.numpy())
 
 
+def gen_unet_cond():
+    """Unet3DCond v3 (the conditional project's model: 15-d embedding, mults 1,2,2,3,4)."""
+    cfg = synth.make_cfg(data_channels=15)
+    p = synth.synth_unet3d_cond_params(cfg, 5)
+    m = ref_loader.build_reference_unet_cond(cfg, p)
+    out = {}
+    shape = (1, 15, 16, 16, 16)
+    x, atb, t = synth.synth_input(shape, 6), synth.synth_atb(shape, 7), torch.tensor([0.4])
+    with torch.no_grad():
+        y = m(x, atb, t)
+    out["full_b1_16.y"], out["full_b1_16.t"] = y.numpy(), t.numpy()
+    cfg2 = synth.make_cfg(dim=32, dim_mults=(1, 2), data_channels=15, time_resolution=64,
+                          time_bandwidth=100.0, attn_heads=2, attn_dim_head=16)
+    p2 = synth.synth_unet3d_cond_params(cfg2, 8)
+    m2 = ref_loader.build_reference_unet_cond(cfg2, p2)
+    shape = (2, 15, 16, 16, 16)
+    x, atb, t = synth.synth_input(shape, 9), synth.synth_atb(shape, 10), torch.tensor([0.15, 0.8])
+    with torch.no_grad():
+        y = m2(x, atb, t)
+    out["small_b2_16.y"], out["small_b2_16.t"] = y.numpy(), t.numpy()
+    np.savez_compressed(os.path.join(OUT, "unet3d_cond.npz"), **out)
+
+
 def gen_interp():
     im = ref_loader.interpolation_module()
     t = torch.linspace(0.01, 0.99, 50)
@@ -147,5 +170,6 @@ if __name__ == "__main__":
     gen_solvers()
     gen_decode()
     gen_unet()
+    gen_unet_cond()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
