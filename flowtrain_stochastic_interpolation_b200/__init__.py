@@ -12,10 +12,10 @@ from .solvers import (ODEFlowSolver, ODEOneSidedDenoisingSolver, SDEOneSidedDeno
                       integrate_fixed, odeSol_RK4)
 from .task import (EMAShadow, Geo3DStochInterp, decode, ema_update_, embed, flow_loss,
                    simplex_embedding)
-from .unet3d import Unet3D
+from .unet3d import Unet3D, Unet3DCond
 
 __all__ = [
-    "Unet3D", "StochasticInterpolator", "BaseInterpolant", "LinearInterpolant", "TrigInterpolant",
+    "Unet3D", "Unet3DCond", "StochasticInterpolator", "BaseInterpolant", "LinearInterpolant", "TrigInterpolant",
     "EncDecInterpolant", "SBDMInterpolant", "MirrorInterpolant", "ODEFlowSolver",
     "ODEOneSidedDenoisingSolver", "SDEOneSidedDenoisingSolver", "odeSol_RK4", "integrate_fixed",
     "Geo3DStochInterp", "EMAShadow", "embed", "decode", "flow_loss", "ema_update_", "simplex_embedding",

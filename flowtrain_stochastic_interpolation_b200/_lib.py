@@ -27,6 +27,7 @@ class FtbUnetCfg(C.Structure):
         ("attn_dim_head", C.c_int),
         ("full_attn", C.c_int * FTB_MAX_STAGES),
         ("num_mem_kv", C.c_int),
+        ("conditional", C.c_int),
     ]
 
 
@@ -61,6 +62,8 @@ _SIGS = {
     "ftb_unet3d_set_param": (_i, [_vp, C.c_char_p, _vp, _i64, _vp]),
     "ftb_unet3d_workspace_bytes": (_sz, [_vp, _i, _i, _i, _i]),
     "ftb_unet3d_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "ftb_unet3d_cond_workspace_bytes": (_sz, [_vp, _i, _i, _i, _i, _i]),
+    "ftb_unet3d_cond_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _i, _vp]),
     "ftb_unet3d_tap_channels": (_i, [_vp, C.c_char_p, _ip, _ip, _ip, _ip]),
     "ftb_unet3d_get_tap": (_i, [_vp, C.c_char_p, _vp, _vp]),
     "ftb_unet3d_last_launches": (_i, [_vp]),

@@ -113,6 +113,34 @@ __global__ void trilinear_kernel(const bf16* __restrict__ in, int B, int CG, int
   }
 }
 
+// ------------------------------------------------------------------ MixATb input: cat + FiLM
+// MixATb.forward (unet_attn_3d_cond_v3.py:176-182): ATb_x = cat(x, ATb); ATb_x*(scale+1)+shift.
+// The FiLM acts on the conv INPUT (the zero padding of conv1 stays zero), so it cannot fold
+// into the conv; one pass writes the 2C-channel tensor.  mul = scale+1 and add = shift come
+// from film_mlps; the ATb embedding may have batch 1 (one conditioning volume for an ensemble).
+__global__ void film_concat_kernel(const bf16* __restrict__ x, const bf16* __restrict__ a, int B, int CG,
+                                   size_t vox, size_t a_bstride, const float* __restrict__ film,
+                                   int film_stride, int C, bf16* __restrict__ out) {
+  const size_t total = (size_t)B * 2 * CG * vox;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t v = i % vox;
+    const int cg = (int)((i / vox) % (2 * CG));
+    const int b = (int)(i / (vox * 2 * CG));
+    const bool second = cg >= CG;
+    const int cgl = second ? cg - CG : cg;
+    const bf16* src = second ? a + (size_t)b * a_bstride + ((size_t)cgl * vox + v) * 8
+                             : x + (((size_t)b * CG + cgl) * vox + v) * 8;
+    float f[8];
+    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(src)), f);
+    const float* mul = film + (size_t)b * film_stride + (second ? C : 0) + cgl * 8;
+    const float* add = mul + 2 * C;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = cgl * 8 + j < C ? fmaf(f[j], __ldg(mul + j), __ldg(add + j)) : 0.f;
+    *reinterpret_cast<uint4*>(out + i * 8) = pack_bf16x8(f);
+  }
+}
+
 // ------------------------------------------------------------------ interpolant (interpolation.py:156-216, :379-546)
 struct Coef {
   float a, b, g, ad, bd, gd;
@@ -358,6 +386,19 @@ int trilinear_resample(const Act& in, Act& out, cudaStream_t st) {
   FTB_CHECK(in.B == out.B && in.C == out.C, "trilinear: batch/channels must match");
   trilinear_kernel<<<grid_for((size_t)out.B * out.cg() * out.voxels(), 256), 256, 0, st>>>(
       in.p, in.B, in.cg(), in.D, in.H, in.W, out.D, out.H, out.W, out.p);
+  FTB_LAUNCH_OK();
+  return 0;
+}
+
+int film_concat(const Act& x, const Act& atb, const float* film, int film_stride, int c_real, Act& out,
+                cudaStream_t st) {
+  FTB_CHECK(x.C == atb.C && out.C == 2 * x.C && out.B == x.B, "film_concat: channel/batch mismatch");
+  FTB_CHECK(atb.B == x.B || atb.B == 1, "film_concat: ATb batch must be 1 or B");
+  FTB_CHECK(x.voxels() == atb.voxels() && x.voxels() == out.voxels(), "film_concat: spatial mismatch");
+  const size_t total = (size_t)x.B * 2 * x.cg() * x.voxels();
+  const size_t a_bstride = atb.B == 1 ? 0 : (size_t)atb.C * atb.voxels();
+  film_concat_kernel<<<grid_for(total, 256), 256, 0, st>>>(x.p, atb.p, x.B, x.cg(), x.voxels(), a_bstride, film,
+                                                           film_stride, c_real, out.p);
   FTB_LAUNCH_OK();
   return 0;
 }

@@ -136,7 +136,8 @@ struct ftb_unet {
   std::map<std::string, int> pindex;
   std::map<std::string, ConvLayer> convs;
   std::map<std::string, GainVec> gains;
-  std::vector<std::string> film_blocks;  // resnet prefixes in FiLM-table order
+  std::vector<std::string> film_blocks;  // FiLM-table rows: prefix of the (SiLU, Linear) time MLP's Linear
+  std::map<std::string, std::string> film_gain;   // block -> gain vector folded into its scale half ("" = none)
   std::map<std::string, int> film_off;
   int film_rows = 0;
   const float** d_film_w = nullptr;
@@ -201,14 +202,31 @@ void add_gain(ftb_unet* U, const std::string& gname, int c, bool as_param = true
   U->gains[gname] = g;
 }
 
+// the reference names the block's time MLP `mlp` in unet_attn_3d.py:255 and `time_mlp` in
+// unet_attn_3d_cond_v3.py:337
+std::string resnet_mlp(const ftb_unet* U, const std::string& p) {
+  return p + (U->cfg.conditional ? ".time_mlp.1" : ".mlp.1");
+}
+
 void add_resnet(ftb_unet* U, const std::string& p, int cin, int cout) {
-  add_param(U, p + ".mlp.1.weight", {2 * cout, U->time_dim});
-  add_param(U, p + ".mlp.1.bias", {2 * cout});
+  add_param(U, resnet_mlp(U, p) + ".weight", {2 * cout, U->time_dim});
+  add_param(U, resnet_mlp(U, p) + ".bias", {2 * cout});
   add_conv(U, p + ".block1.proj", cout, cin, 3, true);
   add_gain(U, p + ".block1.norm.g", cout);
   add_conv(U, p + ".block2.proj", cout, cout, 3, true);
   add_gain(U, p + ".block2.norm.g", cout);
   if (cin != cout) add_conv(U, p + ".res_conv", cout, cin, 1, true);
+}
+
+// EmbedATb (unet_attn_3d_cond_v3.py:120-129) + MixATb (:156-173) of one stage
+void add_embed_mix(ftb_unet* U, const std::string& p, int d) {
+  add_conv(U, p + ".0.conv1", d, U->cfg.data_channels, 5, true);
+  add_conv(U, p + ".0.conv2", d, d, 5, true);
+  add_param(U, p + ".1.time_mlp.1.weight", {4 * d, U->time_dim});
+  add_param(U, p + ".1.time_mlp.1.bias", {4 * d});
+  add_conv(U, p + ".1.conv1", d, 2 * d, 3, true);
+  add_gain(U, p + ".1.norm.g", d);
+  add_conv(U, p + ".1.conv2", d, d, 3, true);
 }
 
 void add_attn(ftb_unet* U, const std::string& p, int dim, bool full) {
@@ -248,7 +266,17 @@ int build_plan(ftb_unet* U) {
   U->time_dim = c.dim * 4;
   const int n = c.n_stages;
 
-  add_conv(U, "init_conv", c.dim, c.data_channels, 7, true);
+  const bool cond = c.conditional != 0;
+  // module indices inside a stage: [resnet, resnet, attn, resample] (unet_attn_3d.py:600-611) or
+  // [EmbedATb, MixATb, resnet, resnet, attn, resample] (unet_attn_3d_cond_v3.py:702-716)
+  const int o = cond ? 2 : 0;
+  auto sub = [&](const std::string& p, int k) { return p + "." + std::to_string(k); };
+  if (cond) {
+    add_conv(U, "init_conv_x", c.dim, c.data_channels, 7, true);
+    add_conv(U, "init_conv_ATb", c.data_channels, c.data_channels, 7, true);
+  } else {
+    add_conv(U, "init_conv", c.dim, c.data_channels, 7, true);
+  }
   add_param(U, "time_mlp.0.freqs", {c.time_resolution});
   add_param(U, "time_mlp.0.phases", {c.time_resolution});
   add_param(U, "time_mlp.1.weight", {U->time_dim, c.time_resolution});
@@ -258,20 +286,22 @@ int build_plan(ftb_unet* U) {
   for (int i = 0; i < n; ++i) {
     const int din = U->in_out[i].first, dout = U->in_out[i].second;
     const std::string p = "downs." + std::to_string(i);
-    add_resnet(U, p + ".0", din, din);
-    add_resnet(U, p + ".1", din, din);
-    add_attn(U, p + ".2", din, c.full_attn[i] != 0);
-    if (i >= n - 1) add_conv(U, p + ".3", dout, din, 3, true);
-    else add_conv(U, p + ".3.conv", dout, din, 1, true);
+    if (cond) add_embed_mix(U, p, din);
+    add_resnet(U, sub(p, o), din, din);
+    add_resnet(U, sub(p, o + 1), din, din);
+    add_attn(U, sub(p, o + 2), din, c.full_attn[i] != 0);
+    if (i >= n - 1) add_conv(U, sub(p, o + 3), dout, din, 3, true);
+    else add_conv(U, sub(p, o + 3) + ".conv", dout, din, 1, true);
   }
   for (int i = 0; i < n; ++i) {
     const int din = U->in_out[n - 1 - i].first, dout = U->in_out[n - 1 - i].second;
     const std::string p = "ups." + std::to_string(i);
-    add_resnet(U, p + ".0", dout + din, dout);
-    add_resnet(U, p + ".1", dout + din, dout);
-    add_attn(U, p + ".2", dout, c.full_attn[n - 1 - i] != 0);
-    if (i == n - 1) add_conv(U, p + ".3", din, dout, 3, true);
-    else add_conv(U, p + ".3.conv", din, dout, 3, true);
+    if (cond) add_embed_mix(U, p, dout);
+    add_resnet(U, sub(p, o), dout + din, dout);
+    add_resnet(U, sub(p, o + 1), dout + din, dout);
+    add_attn(U, sub(p, o + 2), dout, c.full_attn[n - 1 - i] != 0);
+    if (i == n - 1) add_conv(U, sub(p, o + 3), din, dout, 3, true);
+    else add_conv(U, sub(p, o + 3) + ".conv", din, dout, 3, true);
   }
   const int mid = U->dims.back();
   add_resnet(U, "mid_block1", mid, mid);
@@ -280,22 +310,35 @@ int build_plan(ftb_unet* U) {
   add_resnet(U, "final_res_block", c.dim * 2, c.dim);
   add_conv(U, "final_conv", c.data_channels, c.dim, 1, true);
 
-  // FiLM table in execution order
+  // FiLM table in execution order: every (SiLU, Linear) time MLP of the network in one launch
+  auto film_resnet = [&](const std::string& b) {
+    const std::string lin = resnet_mlp(U, b);
+    U->film_blocks.push_back(lin);
+    U->film_gain[lin] = b + ".block1.norm.g";
+  };
+  auto film_mix = [&](const std::string& p) {
+    U->film_blocks.push_back(p + ".1.time_mlp.1");
+    U->film_gain[p + ".1.time_mlp.1"] = "";
+  };
   for (int i = 0; i < n; ++i) {
-    U->film_blocks.push_back("downs." + std::to_string(i) + ".0");
-    U->film_blocks.push_back("downs." + std::to_string(i) + ".1");
+    const std::string p = "downs." + std::to_string(i);
+    if (cond) film_mix(p);
+    film_resnet(sub(p, o));
+    film_resnet(sub(p, o + 1));
   }
-  U->film_blocks.push_back("mid_block1");
-  U->film_blocks.push_back("mid_block2");
+  film_resnet("mid_block1");
+  film_resnet("mid_block2");
   for (int i = 0; i < n; ++i) {
-    U->film_blocks.push_back("ups." + std::to_string(i) + ".0");
-    U->film_blocks.push_back("ups." + std::to_string(i) + ".1");
+    const std::string p = "ups." + std::to_string(i);
+    if (cond) film_mix(p);
+    film_resnet(sub(p, o));
+    film_resnet(sub(p, o + 1));
   }
-  U->film_blocks.push_back("final_res_block");
+  film_resnet("final_res_block");
   int off = 0;
   for (const std::string& b : U->film_blocks) {
     U->film_off[b] = off;
-    off += U->params[U->pindex[b + ".mlp.1.bias"]].shape[0];
+    off += U->params[U->pindex[b + ".bias"]].shape[0];
   }
   U->film_rows = off;
 
@@ -327,10 +370,11 @@ int ensure_device(ftb_unet* U) {
   std::vector<const float*> hw(nb), hb(nb), hg(nb);
   std::vector<int> ho(nb + 1);
   for (int i = 0; i < nb; ++i) {
-    hw[i] = U->params[U->pindex[U->film_blocks[i] + ".mlp.1.weight"]].dev;
-    hb[i] = U->params[U->pindex[U->film_blocks[i] + ".mlp.1.bias"]].dev;
+    hw[i] = U->params[U->pindex[U->film_blocks[i] + ".weight"]].dev;
+    hb[i] = U->params[U->pindex[U->film_blocks[i] + ".bias"]].dev;
     ho[i] = U->film_off[U->film_blocks[i]];
-    hg[i] = U->gains.at(U->film_blocks[i] + ".block1.norm.g").gs;
+    const std::string& gname = U->film_gain.at(U->film_blocks[i]);
+    hg[i] = gname.empty() ? nullptr : U->gains.at(gname).gs;
   }
   ho[nb] = U->film_rows;
   FTB_CUDA(cudaMemcpy(U->d_film_w, hw.data(), nb * sizeof(float*), cudaMemcpyHostToDevice));
@@ -395,6 +439,10 @@ struct Fwd {
   bool dry;
   int B;
   float* film = nullptr;
+  const float* atb = nullptr;   // conditional model: ATb [atb_B, C, X, Y, Z] fp32 (atb_B = 1 or B)
+  int atb_B = 0;
+  bool reuse_atb = false;       // the workspace still holds the ATb-only branch of the previous call
+  bool skip = false;            // allocate only (cached ATb branch)
 
   void* raw(size_t bytes) {
     off = round_up_sz(off, 256);
@@ -402,9 +450,9 @@ struct Fwd {
     off += bytes;
     return p;
   }
-  Act act(int C, int D, int H, int W) {
+  Act act(int C, int D, int H, int W, int batch = 0) {
     Act a;
-    a.B = B; a.C = round_up(C, 16); a.D = D; a.H = H; a.W = W;
+    a.B = batch > 0 ? batch : B; a.C = round_up(C, 16); a.D = D; a.H = H; a.W = W;
     a.p = reinterpret_cast<bf16*>(raw(a.bytes()));
     return a;
   }
@@ -421,7 +469,7 @@ struct Fwd {
     w.w = cl.packed; w.ksize = cl.k; w.cin = cl.cin_pad; w.n = cl.n_tile; w.ntiles = cl.ntiles;
     w.cin_real = cl.cin; w.cout_real = cl.cout;
     if (!cl.bname.empty()) e.bias = cl.bias;
-    if (dry) return 0;
+    if (dry || skip) return 0;
     U->launches += cl.ntiles;
     return conv_dispatch(s0, s1, w, e, out, out_cgoff, st);
   }
@@ -433,7 +481,7 @@ struct Fwd {
     ConvSrc s0{&x0, 0, x0.cg()}, s1{};
     if (x1) s1 = ConvSrc{x1, 0, x1->cg()};
     const int cin = x0.C + (x1 ? x1->C : 0);
-    const float* film_p = film ? film + U->film_off.at(p) : nullptr;
+    const float* film_p = film ? film + U->film_off.at(resnet_mlp(U, p)) : nullptr;
     Act h1 = act(cout, a.D, a.H, a.W);
     ConvEpilogue e1;
     // Block1: RMSNorm gain and FiLM (scale+1) arrive pre-multiplied from film_mlps
@@ -511,6 +559,48 @@ struct Fwd {
     return 0;
   }
 
+  // EmbedATb.forward (unet_attn_3d_cond_v3.py:131-139) on the opened ATb; depends on ATb only, so a
+  // sampler computes it once per trajectory (reuse_atb) instead of once per evaluation.
+  int embed_atb(const std::string& p, const Act& opened, int C, int D, int H, int W, Act* out) {
+    Act src = opened;
+    if (opened.D != D || opened.H != H || opened.W != W) {
+      src = act(opened.C, D, H, W, opened.B);
+      if (!dry && !skip) {
+        FTB_TRY(trilinear_resample(opened, src, st));
+        U->launches += 1;
+      }
+    }
+    Act e1 = act(C, D, H, W, opened.B);
+    ConvEpilogue a1;
+    a1.silu = true;
+    FTB_TRY(conv(p + ".conv1", ConvSrc{&src, 0, src.cg()}, ConvSrc{}, a1, e1));
+    *out = act(C, D, H, W, opened.B);
+    FTB_TRY(conv(p + ".conv2", ConvSrc{&e1, 0, e1.cg()}, ConvSrc{}, ConvEpilogue{}, *out));
+    return 0;
+  }
+
+  // MixATb.forward (unet_attn_3d_cond_v3.py:175-190)
+  int mix_atb(const std::string& p, const Act& x, const Act& emb, Act* out) {
+    const int C = x.C;
+    Act cat = act(2 * C, x.D, x.H, x.W);
+    if (!dry) {
+      FTB_TRY(film_concat(x, emb, film + U->film_off.at(p + ".time_mlp.1"), U->film_rows, C, cat, st));
+      U->launches += 1;
+    }
+    Act h1 = act(C, x.D, x.H, x.W);
+    ConvEpilogue e1;
+    e1.norm = true;
+    e1.mul = U->gains.at(p + ".norm.g").gs;
+    e1.silu = true;
+    FTB_TRY(conv(p + ".conv1", ConvSrc{&cat, 0, cat.cg()}, ConvSrc{}, e1, h1));
+    *out = act(C, x.D, x.H, x.W);
+    ConvEpilogue e2;
+    e2.resid = &x;
+    FTB_TRY(conv(p + ".conv2", ConvSrc{&h1, 0, h1.cg()}, ConvSrc{}, e2, *out));
+    tap(p, *out);
+    return 0;
+  }
+
   int resample(const Act& in, int D, int H, int W, Act* out) {
     *out = act(in.C, D, H, W);
     if (dry) return 0;
@@ -521,8 +611,38 @@ struct Fwd {
   int run(const float* x, const float* t, float* y, int X, int Y, int Z) {
     const ftb_unet_cfg& c = U->cfg;
     const int n = c.n_stages;
+    const bool cond = c.conditional != 0;
+    const int o = cond ? 2 : 0;
+    auto sub = [&](const std::string& p, int k) { return p + "." + std::to_string(k); };
     U->taps.clear();
     U->launches = 0;
+    // ---- ATb-only branch first, so that its place in the arena does not depend on anything else:
+    // init_conv_ATb (:778) and the EmbedATb of every down and up stage (:793, :812)
+    std::vector<Act> emb_down(n), emb_up(n);
+    if (cond) {
+      skip = reuse_atb;
+      Act ain = act(c.data_channels, X, Y, Z, atb_B);
+      if (!dry && !skip) {
+        FTB_TRY(pack_ncdhw_to_blocked(atb, atb_B, c.data_channels, X, Y, Z, ain, st));
+        U->launches += 1;
+      }
+      Act opened = act(c.data_channels, X, Y, Z, atb_B);
+      FTB_TRY(conv("init_conv_ATb", ConvSrc{&ain, 0, ain.cg()}, ConvSrc{}, ConvEpilogue{}, opened));
+      if (!skip) tap("init_conv_ATb", opened);
+      for (int i = 0; i < n; ++i) {
+        const int f = 1 << i;
+        FTB_TRY(embed_atb("downs." + std::to_string(i) + ".0", opened, U->in_out[i].first, X / f, Y / f, Z / f,
+                          &emb_down[i]));
+        if (!skip) tap("downs." + std::to_string(i) + ".0", emb_down[i]);
+      }
+      for (int i = 0; i < n; ++i) {
+        const int f = 1 << (n - 1 - i);
+        FTB_TRY(embed_atb("ups." + std::to_string(i) + ".0", opened, U->in_out[n - 1 - i].second, X / f, Y / f,
+                          Z / f, &emb_up[i]));
+        if (!skip) tap("ups." + std::to_string(i) + ".0", emb_up[i]);
+      }
+      skip = false;
+    }
     // time path
     float* temb = f32((size_t)B * U->time_dim);
     float* temb_silu = f32((size_t)B * U->time_dim);
@@ -540,30 +660,36 @@ struct Fwd {
       U->launches += 3;
     }
     Act r = act(c.dim, X, Y, Z);
-    FTB_TRY(conv("init_conv", ConvSrc{&xin, 0, xin.cg()}, ConvSrc{}, ConvEpilogue{}, r));
-    tap("init_conv", r);
+    const std::string init_name = cond ? "init_conv_x" : "init_conv";
+    FTB_TRY(conv(init_name, ConvSrc{&xin, 0, xin.cg()}, ConvSrc{}, ConvEpilogue{}, r));
+    tap(init_name, r);
     Act cur = r;
     std::vector<Act> skips;
     for (int i = 0; i < n; ++i) {
       const std::string p = "downs." + std::to_string(i);
       const int din = U->in_out[i].first, dout = U->in_out[i].second;
       Act a1, a2, a3, a4;
-      FTB_TRY(resnet(p + ".0", cur, nullptr, din, &a1));
+      if (cond) {
+        Act mixed;
+        FTB_TRY(mix_atb(sub(p, 1), cur, emb_down[i], &mixed));
+        cur = mixed;
+      }
+      FTB_TRY(resnet(sub(p, o), cur, nullptr, din, &a1));
       skips.push_back(a1);
       float* ss = f32((size_t)B * a1.voxels());
-      FTB_TRY(resnet(p + ".1", a1, nullptr, din, &a2, ss));
-      FTB_TRY(attention(p + ".2", a2, ss, c.full_attn[i] != 0, &a3));
+      FTB_TRY(resnet(sub(p, o + 1), a1, nullptr, din, &a2, ss));
+      FTB_TRY(attention(sub(p, o + 2), a2, ss, c.full_attn[i] != 0, &a3));
       skips.push_back(a3);
       if (i >= n - 1) {
         a4 = act(dout, a3.D, a3.H, a3.W);
-        FTB_TRY(conv(p + ".3", ConvSrc{&a3, 0, a3.cg()}, ConvSrc{}, ConvEpilogue{}, a4));
+        FTB_TRY(conv(sub(p, o + 3), ConvSrc{&a3, 0, a3.cg()}, ConvSrc{}, ConvEpilogue{}, a4));
       } else {
         Act ds;
         FTB_TRY(resample(a3, a3.D / 2, a3.H / 2, a3.W / 2, &ds));
         a4 = act(dout, ds.D, ds.H, ds.W);
-        FTB_TRY(conv(p + ".3.conv", ConvSrc{&ds, 0, ds.cg()}, ConvSrc{}, ConvEpilogue{}, a4));
+        FTB_TRY(conv(sub(p, o + 3) + ".conv", ConvSrc{&ds, 0, ds.cg()}, ConvSrc{}, ConvEpilogue{}, a4));
       }
-      tap(p + ".3", a4);
+      tap(sub(p, o + 3), a4);
       cur = a4;
     }
     {
@@ -579,22 +705,27 @@ struct Fwd {
       const std::string p = "ups." + std::to_string(i);
       const int din = U->in_out[n - 1 - i].first, dout = U->in_out[n - 1 - i].second;
       Act a1, a2, a3, a4;
+      if (cond) {
+        Act mixed;
+        FTB_TRY(mix_atb(sub(p, 1), cur, emb_up[i], &mixed));
+        cur = mixed;
+      }
       Act s = skips.back(); skips.pop_back();
-      FTB_TRY(resnet(p + ".0", cur, &s, dout, &a1));
+      FTB_TRY(resnet(sub(p, o), cur, &s, dout, &a1));
       s = skips.back(); skips.pop_back();
       float* ss = f32((size_t)B * a1.voxels());
-      FTB_TRY(resnet(p + ".1", a1, &s, dout, &a2, ss));
-      FTB_TRY(attention(p + ".2", a2, ss, c.full_attn[n - 1 - i] != 0, &a3));
+      FTB_TRY(resnet(sub(p, o + 1), a1, &s, dout, &a2, ss));
+      FTB_TRY(attention(sub(p, o + 2), a2, ss, c.full_attn[n - 1 - i] != 0, &a3));
       if (i == n - 1) {
         a4 = act(din, a3.D, a3.H, a3.W);
-        FTB_TRY(conv(p + ".3", ConvSrc{&a3, 0, a3.cg()}, ConvSrc{}, ConvEpilogue{}, a4));
+        FTB_TRY(conv(sub(p, o + 3), ConvSrc{&a3, 0, a3.cg()}, ConvSrc{}, ConvEpilogue{}, a4));
       } else {
         Act us;
         FTB_TRY(resample(a3, a3.D * 2, a3.H * 2, a3.W * 2, &us));
         a4 = act(din, us.D, us.H, us.W);
-        FTB_TRY(conv(p + ".3.conv", ConvSrc{&us, 0, us.cg()}, ConvSrc{}, ConvEpilogue{}, a4));
+        FTB_TRY(conv(sub(p, o + 3) + ".conv", ConvSrc{&us, 0, us.cg()}, ConvSrc{}, ConvEpilogue{}, a4));
       }
-      tap(p + ".3", a4);
+      tap(sub(p, o + 3), a4);
       cur = a4;
     }
     Act fin;
@@ -680,9 +811,10 @@ static int check_dims(const ftb_unet* h, int B, int X, int Y, int Z) {
   return 0;
 }
 
-size_t ftb_unet3d_workspace_bytes(ftb_unet* h, int B, int X, int Y, int Z) {
+static size_t workspace_bytes_impl(ftb_unet* h, int B, int atb_B, int X, int Y, int Z) {
   if (check_dims(h, B, X, Y, Z) != 0) return 0;
   Fwd f{h, nullptr, nullptr, 0, 0, true, B};
+  f.atb_B = atb_B;
   const bool kt = h->keep_taps;
   h->keep_taps = false;
   const int r = f.run(nullptr, nullptr, nullptr, X, Y, Z);
@@ -690,9 +822,18 @@ size_t ftb_unet3d_workspace_bytes(ftb_unet* h, int B, int X, int Y, int Z) {
   return r == 0 ? round_up_sz(f.off, 256) + 256 : 0;
 }
 
+size_t ftb_unet3d_workspace_bytes(ftb_unet* h, int B, int X, int Y, int Z) {
+  return workspace_bytes_impl(h, B, h && h->cfg.conditional ? B : 0, X, Y, Z);
+}
+size_t ftb_unet3d_cond_workspace_bytes(ftb_unet* h, int B, int atb_B, int X, int Y, int Z) {
+  if (!h || !h->cfg.conditional || !(atb_B == 1 || atb_B == B)) return 0;
+  return workspace_bytes_impl(h, B, atb_B, X, Y, Z);
+}
+
 int ftb_unet3d_forward(ftb_unet* h, const float* x, const float* t, float* out, int B, int X, int Y,
                        int Z, void* workspace, size_t workspace_bytes, void* stream) {
   FTB_TRY(check_dims(h, B, X, Y, Z));
+  FTB_CHECK(!h->cfg.conditional, "conditional model: call ftb_unet3d_cond_forward (ATb is required)");
   FTB_CHECK(x && t && out && workspace, "null argument");
   FTB_CHECK(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
   const size_t need = ftb_unet3d_workspace_bytes(h, B, X, Y, Z);
@@ -702,6 +843,28 @@ int ftb_unet3d_forward(ftb_unet* h, const float* x, const float* t, float* out, 
   FTB_TRY(ensure_device(h));
   FTB_TRY(finalize(h, st));
   Fwd f{h, st, reinterpret_cast<char*>(workspace), 0, workspace_bytes, false, B};
+  return f.run(x, t, out, X, Y, Z);
+}
+
+int ftb_unet3d_cond_forward(ftb_unet* h, const float* x, const float* atb, int atb_B, const float* t, float* out,
+                            int B, int X, int Y, int Z, void* workspace, size_t workspace_bytes, int reuse_atb,
+                            void* stream) {
+  FTB_TRY(check_dims(h, B, X, Y, Z));
+  FTB_CHECK(h->cfg.conditional, "unconditional model: call ftb_unet3d_forward");
+  FTB_CHECK(x && atb && t && out && workspace, "null argument");
+  FTB_CHECK(atb_B == 1 || atb_B == B, "ATb batch must be 1 (shared by the batch) or B");
+  FTB_CHECK(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+  const size_t need = ftb_unet3d_cond_workspace_bytes(h, B, atb_B, X, Y, Z);
+  FTB_CHECK(need > 0 && workspace_bytes >= need,
+            "workspace too small: need " + std::to_string(need) + " bytes");
+  cudaStream_t st = (cudaStream_t)stream;
+  FTB_TRY(ensure_device(h));
+  const bool was_dirty = h->dirty;
+  FTB_TRY(finalize(h, st));
+  Fwd f{h, st, reinterpret_cast<char*>(workspace), 0, workspace_bytes, false, B};
+  f.atb = atb;
+  f.atb_B = atb_B;
+  f.reuse_atb = reuse_atb != 0 && !was_dirty;   // new weights invalidate the cached branch
   return f.run(x, t, out, X, Y, Z);
 }
 

@@ -77,6 +77,9 @@ int pack_conv_weights(const float* w, int cout, int cin_real, int ksize, int cin
 int pack_ncdhw_to_blocked(const float* x, int B, int C, int D, int H, int W, Act& out, cudaStream_t st);
 int unpack_blocked_to_ncdhw(const Act& in, int cgoff, int C, float* out, cudaStream_t st);
 int trilinear_resample(const Act& in, Act& out, cudaStream_t st);  // align_corners=True
+// out[:, :C] = x*mul[:C]+add[:C]; out[:, C:] = atb*mul[C:]+add[C:], film row = [mul(2C) | add(2C)] per sample
+int film_concat(const Act& x, const Act& atb, const float* film, int film_stride, int c_real, Act& out,
+                cudaStream_t st);
 
 // ---------------------------------------------------------------- time path
 struct TimeMlpParams {

@@ -1,5 +1,7 @@
-"""``Unet3D`` — drop-in for flowtrain.models.Unet3D (src/flowtrain/models/unet_attn_3d.py:469-719)
-whose forward runs entirely in the sm_100a kernels behind the C ABI (include/ftb.h).
+"""``Unet3D`` / ``Unet3DCond`` — drop-ins for flowtrain.models.Unet3D
+(src/flowtrain/models/unet_attn_3d.py:469-719) and the conditional project's Unet3DCond v3
+(src/flowtrain/models/unet_attn_3d_cond_v3.py:537-828), whose forward runs entirely in the sm_100a
+kernels behind the C ABI (include/ftb.h).
 
 Same constructor kwargs (:509-525), same ``forward(x, time, x_self_cond=None)`` (:673) and the
 same ``state_dict()`` keys, shapes and order, so a reference state dict / Lightning ``.ckpt``
@@ -24,7 +26,8 @@ class _Node(nn.Module):
     """Container node of the parameter tree (mirrors the reference's module nesting)."""
 
 
-def _cfg_struct(dim, dim_mults, data_channels, time_resolution, attn_heads, attn_dim_head, full_attn):
+def _cfg_struct(dim, dim_mults, data_channels, time_resolution, attn_heads, attn_dim_head, full_attn,
+                conditional=False):
     n = len(dim_mults)
     if n > _lib.FTB_MAX_STAGES:
         raise ValueError(f"at most {_lib.FTB_MAX_STAGES} stages")
@@ -40,10 +43,13 @@ def _cfg_struct(dim, dim_mults, data_channels, time_resolution, attn_heads, attn
     for i, f in enumerate(full_attn):
         cfg.full_attn[i] = 1 if f else 0
     cfg.num_mem_kv = 4
+    cfg.conditional = 1 if conditional else 0
     return cfg
 
 
 class Unet3D(nn.Module):
+    _conditional = False
+
     def __init__(
         self,
         dim,
@@ -96,7 +102,7 @@ class Unet3D(nn.Module):
             flash_attn=flash_attn,
         )
         self._cfg = _cfg_struct(dim, dim_mults, data_channels, time_resolution, attn_heads,
-                                attn_dim_head, full_attn)
+                                attn_dim_head, full_attn, self._conditional)
         self._handle = C.c_void_p()
         _lib.check(_lib.lib.ftb_unet3d_create(C.byref(self._cfg), C.byref(self._handle)))
         self._names = []
@@ -187,16 +193,16 @@ class Unet3D(nn.Module):
             self._workspace[key] = ws
         return ws
 
-    def forward(self, x, time, x_self_cond=None):
+    def _check_inputs(self, x, time, x_self_cond):
         if x_self_cond is not None:
             raise NotImplementedError("self conditioning is not implemented")
         if not x.is_cuda:
-            raise RuntimeError("flowtrain_stochastic_interpolation_b200.Unet3D runs on CUDA (sm_100a) only; "
-                               "there is no CPU fallback")
+            raise RuntimeError(f"flowtrain_stochastic_interpolation_b200.{type(self).__name__} runs on CUDA "
+                               "(sm_100a) only; there is no CPU fallback")
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             if x.requires_grad or self.training:
                 raise NotImplementedError(
-                    "backward through the B200 Unet3D is not implemented yet (sampling / no_grad only); "
+                    "backward through the B200 UNet is not implemented yet (sampling / no_grad only); "
                     "wrap the call in torch.no_grad()")
         if x.dim() != 5 or x.shape[1] != self.channels:
             raise ValueError(f"expected x of shape [B,{self.channels},X,Y,Z], got {tuple(x.shape)}")
@@ -207,10 +213,17 @@ class Unet3D(nn.Module):
             raise AssertionError(f"your input dimensions {(X, Y, Z)} need to be divisible by {f}, given the unet")
         if time.dim() != 1 or time.shape[0] != B:
             raise ValueError(f"expected time of shape [{B}], got {tuple(time.shape)}")
+
+    @staticmethod
+    def _f32c(t):
+        t = t.detach()
+        return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+
+    def forward(self, x, time, x_self_cond=None):
+        self._check_inputs(x, time, x_self_cond)
+        B, _, X, Y, Z = x.shape
         with torch.cuda.device(x.device):
-            xin = x.detach()
-            if xin.dtype != torch.float32 or not xin.is_contiguous():
-                xin = xin.float().contiguous()
+            xin = self._f32c(x)
             tin = time.detach().to(device=x.device, dtype=torch.float32).contiguous()
             self._sync_params(x.device)
             ws = self._get_workspace(x.device, B, X, Y, Z)
@@ -242,3 +255,61 @@ class Unet3D(nn.Module):
                 self._handle = C.c_void_p()
         except Exception:
             pass
+
+
+class Unet3DCond(Unet3D):
+    """Drop-in for the conditional project's ``Unet3DCond`` (unet_attn_3d_cond_v3.py:537-828):
+    same constructor kwargs, ``forward(x, ATb, time, x_self_cond=None)`` (:769), same state_dict.
+
+    ``ATb`` may be ``[B,C,X,Y,Z]`` like the reference, or ``[1,C,X,Y,Z]`` when one conditioning volume
+    is shared by the whole batch (the reference expands it, model_inference_experiments.py:232).
+    ``init_conv_ATb`` and the ten ``EmbedATb`` outputs depend on ATb only; they are cached in the
+    workspace and recomputed only when ATb (storage, version or shape) or the weights change — the
+    reference recomputes them on every ODE function evaluation.
+    """
+    _conditional = True
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._atb_key = None
+
+    def _get_workspace_cond(self, device, B, atb_B, X, Y, Z):
+        key = (str(device), B, X, Y, Z, atb_B)
+        ws = self._workspace.get(key)
+        if ws is None:
+            nbytes = _lib.lib.ftb_unet3d_cond_workspace_bytes(self._handle, B, atb_B, X, Y, Z)
+            if nbytes == 0:
+                raise _lib.FtbError(_lib.last_error())
+            self._workspace.clear()
+            self._atb_key = None
+            ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+            self._workspace[key] = ws
+        return ws
+
+    def forward(self, x, ATb, time, x_self_cond=None):
+        self._check_inputs(x, time, x_self_cond)
+        B, _, X, Y, Z = x.shape
+        if ATb.dim() != 5 or tuple(ATb.shape[1:]) != tuple(x.shape[1:]) or ATb.shape[0] not in (1, B):
+            # the reference asserts x.shape == ATb.shape (:775-777); batch 1 is this build's extension
+            raise AssertionError(f"Input and ATb shapes do not match: {tuple(x.shape)} and {tuple(ATb.shape)}")
+        if ATb.device != x.device:
+            raise RuntimeError("x and ATb must be on the same device")
+        with torch.cuda.device(x.device):
+            xin = self._f32c(x)
+            ain = self._f32c(ATb)
+            tin = time.detach().to(device=x.device, dtype=torch.float32).contiguous()
+            synced_before = dict(self._synced)
+            self._sync_params(x.device)
+            ws = self._get_workspace_cond(x.device, B, ain.shape[0], X, Y, Z)
+            base = (ws.data_ptr() + 255) // 256 * 256
+            key = (ATb.data_ptr(), ATb._version, tuple(ATb.shape), ws.data_ptr())
+            reuse = self._atb_key == key and synced_before == self._synced
+            out = torch.empty_like(xin)
+            _lib.check(_lib.lib.ftb_unet3d_cond_forward(
+                self._handle, _lib.ptr(xin), _lib.ptr(ain), ain.shape[0], _lib.ptr(tin), _lib.ptr(out),
+                B, X, Y, Z, C.c_void_p(base), ws.numel() - (base - ws.data_ptr()), 1 if reuse else 0,
+                _lib.stream_ptr()))
+            self._atb_key = key
+            self._ain_keepalive = ain
+            self.last_launches = _lib.lib.ftb_unet3d_last_launches(self._handle)
+        return out if x.dtype == torch.float32 else out.to(x.dtype)

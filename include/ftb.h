@@ -38,6 +38,7 @@ typedef struct ftb_unet_cfg {
   int attn_dim_head;                /* 16 or 32 */
   int full_attn[FTB_MAX_STAGES];    /* per stage: 1 = softmax Attention, 0 = LinearAttention */
   int num_mem_kv;                   /* 4 in the reference (:290, :345) */
+  int conditional;                  /* 1: Unet3DCond v3 (unet_attn_3d_cond_v3.py:598-828), 0: Unet3D */
 } ftb_unet_cfg;
 
 typedef struct ftb_unet ftb_unet;
@@ -69,6 +70,17 @@ size_t ftb_unet3d_workspace_bytes(ftb_unet* h, int B, int X, int Y, int Z);
 /* x [B,C,X,Y,Z] fp32, t [B] fp32 -> out [B,C,X,Y,Z] fp32.  bf16 tensor-core path. */
 int ftb_unet3d_forward(ftb_unet* h, const float* x, const float* t, float* out, int B, int X, int Y,
                        int Z, void* workspace, size_t workspace_bytes, void* stream);
+/* ---- conditional velocity field: replaces Unet3DCond.forward(x, ATb, time)
+ *      (src/flowtrain/models/unet_attn_3d_cond_v3.py:769-828; handle created with cfg.conditional = 1).
+ * atb is [atb_B, C, X, Y, Z] fp32 with atb_B = B, or 1 when one conditioning volume is shared by the
+ * whole batch (the ensemble case, project/geodata-3d-conditional/model_inference_experiments.py:232).
+ * init_conv_ATb and the ten EmbedATb outputs depend on ATb only: they live at the start of the
+ * workspace, and reuse_atb != 0 skips recomputing them when the caller passes the SAME workspace,
+ * shapes and ATb as in the previous call (the reference recomputes them on every evaluation). */
+size_t ftb_unet3d_cond_workspace_bytes(ftb_unet* h, int B, int atb_B, int X, int Y, int Z);
+int ftb_unet3d_cond_forward(ftb_unet* h, const float* x, const float* atb, int atb_B, const float* t, float* out,
+                            int B, int X, int Y, int Z, void* workspace, size_t workspace_bytes, int reuse_atb,
+                            void* stream);
 /* after a forward: copy a named intermediate (same names as oracle/unet3d.py taps) as NCDHW fp32 */
 int ftb_unet3d_tap_channels(ftb_unet* h, const char* name, int* C, int* X, int* Y, int* Z);
 int ftb_unet3d_get_tap(ftb_unet* h, const char* name, float* out, void* stream);

@@ -59,10 +59,12 @@ def stage_plan(cfg):
     return dims, in_out, tuple(full_attn)
 
 
-def _resnet_specs(prefix, cin, cout, time_dim):
+def _resnet_specs(prefix, cin, cout, time_dim, mlp="mlp"):
+    """ResnetBlock parameters; the time MLP attribute is ``mlp`` in unet_attn_3d.py:255 and
+    ``time_mlp`` in unet_attn_3d_cond_v3.py:337."""
     s = OrderedDict()
-    s[f"{prefix}.mlp.1.weight"] = (2 * cout, time_dim)
-    s[f"{prefix}.mlp.1.bias"] = (2 * cout,)
+    s[f"{prefix}.{mlp}.1.weight"] = (2 * cout, time_dim)
+    s[f"{prefix}.{mlp}.1.bias"] = (2 * cout,)
     s[f"{prefix}.block1.proj.weight"] = (cout, cin, 3, 3, 3)
     s[f"{prefix}.block1.proj.bias"] = (cout,)
     s[f"{prefix}.block1.norm.g"] = (1, cout, 1, 1, 1)
@@ -193,8 +195,8 @@ def unet3d_cond_param_specs(cfg) -> "OrderedDict[str, tuple]":
     for i, ((din, dout), fa) in enumerate(zip(in_out, full_attn)):
         last = i >= n - 1
         s.update(embed_mix(f"downs.{i}", din))
-        s.update(_resnet_specs(f"downs.{i}.2", din, din, time_dim))
-        s.update(_resnet_specs(f"downs.{i}.3", din, din, time_dim))
+        s.update(_resnet_specs(f"downs.{i}.2", din, din, time_dim, "time_mlp"))
+        s.update(_resnet_specs(f"downs.{i}.3", din, din, time_dim, "time_mlp"))
         s.update(_attn_specs(f"downs.{i}.4", din, heads, dh, fa))
         if last:
             s[f"downs.{i}.5.weight"] = (dout, din, 3, 3, 3)
@@ -205,8 +207,8 @@ def unet3d_cond_param_specs(cfg) -> "OrderedDict[str, tuple]":
     for i, ((din, dout), fa) in enumerate(zip(reversed(in_out), reversed(full_attn))):
         last = i == n - 1
         s.update(embed_mix(f"ups.{i}", dout))
-        s.update(_resnet_specs(f"ups.{i}.2", dout + din, dout, time_dim))
-        s.update(_resnet_specs(f"ups.{i}.3", dout + din, dout, time_dim))
+        s.update(_resnet_specs(f"ups.{i}.2", dout + din, dout, time_dim, "time_mlp"))
+        s.update(_resnet_specs(f"ups.{i}.3", dout + din, dout, time_dim, "time_mlp"))
         s.update(_attn_specs(f"ups.{i}.4", dout, heads, dh, fa))
         if last:
             s[f"ups.{i}.5.weight"] = (din, dout, 3, 3, 3)
@@ -215,10 +217,10 @@ def unet3d_cond_param_specs(cfg) -> "OrderedDict[str, tuple]":
             s[f"ups.{i}.5.conv.weight"] = (din, dout, 3, 3, 3)
             s[f"ups.{i}.5.conv.bias"] = (din,)
     mid = dims[-1]
-    s.update(_resnet_specs("mid_block1", mid, mid, time_dim))
+    s.update(_resnet_specs("mid_block1", mid, mid, time_dim, "time_mlp"))
     s.update(_attn_specs("mid_attn", mid, heads, dh, True))
-    s.update(_resnet_specs("mid_block2", mid, mid, time_dim))
-    s.update(_resnet_specs("final_res_block", dim * 2, dim, time_dim))
+    s.update(_resnet_specs("mid_block2", mid, mid, time_dim, "time_mlp"))
+    s.update(_resnet_specs("final_res_block", dim * 2, dim, time_dim, "time_mlp"))
     s["final_conv.weight"] = (C, dim, 1, 1, 1)
     s["final_conv.bias"] = (C,)
     return s

@@ -55,9 +55,10 @@ def block(p, prefix, x, scale_shift=None):
     return F.silu(x)
 
 
-def resnet_block(p, prefix, x, temb, taps=None):
-    """ResnetBlock.forward — unet_attn_3d.py:265-278."""
-    te = F.linear(F.silu(temb), p[f"{prefix}.mlp.1.weight"], p[f"{prefix}.mlp.1.bias"])
+def resnet_block(p, prefix, x, temb, taps=None, mlp="mlp"):
+    """ResnetBlock.forward — unet_attn_3d.py:265-278 (``mlp``); the conditional file names the
+    same Sequential ``time_mlp`` (unet_attn_3d_cond_v3.py:337, :347-361)."""
+    te = F.linear(F.silu(temb), p[f"{prefix}.{mlp}.1.weight"], p[f"{prefix}.{mlp}.1.bias"])
     te = te[:, :, None, None, None]
     scale_shift = te.chunk(2, dim=1)
     h = block(p, f"{prefix}.block1", x, scale_shift)

@@ -59,9 +59,9 @@ def unet3d_cond_forward(p, cfg, x, atb, time, taps=None):
     for i in range(n):
         a = _tap(taps, f"downs.{i}.0", embed_atb(p, f"downs.{i}.0", atb_opened, 0.5 ** i))
         x = _tap(taps, f"downs.{i}.1", mix_atb(p, f"downs.{i}.1", x, a, t))
-        x = resnet_block(p, f"downs.{i}.2", x, t, taps)
+        x = resnet_block(p, f"downs.{i}.2", x, t, taps, mlp="time_mlp")
         h.append(x)
-        x = resnet_block(p, f"downs.{i}.3", x, t, taps)
+        x = resnet_block(p, f"downs.{i}.3", x, t, taps, mlp="time_mlp")
         x = attn(f"downs.{i}.4", x, full_attn[i])
         h.append(x)
         if i >= n - 1:
@@ -69,17 +69,17 @@ def unet3d_cond_forward(p, cfg, x, atb, time, taps=None):
         else:
             x = downsample(p, f"downs.{i}.5", x)
         _tap(taps, f"downs.{i}.5", x)
-    x = resnet_block(p, "mid_block1", x, t, taps)
+    x = resnet_block(p, "mid_block1", x, t, taps, mlp="time_mlp")
     x = attn("mid_attn", x, True)
-    x = resnet_block(p, "mid_block2", x, t, taps)
+    x = resnet_block(p, "mid_block2", x, t, taps, mlp="time_mlp")
     for i in range(n):
         fa = full_attn[n - 1 - i]
         a = _tap(taps, f"ups.{i}.0", embed_atb(p, f"ups.{i}.0", atb_opened, 0.5 ** (n - i - 1)))
         x = _tap(taps, f"ups.{i}.1", mix_atb(p, f"ups.{i}.1", x, a, t))
         x = torch.cat((x, h.pop()), dim=1)
-        x = resnet_block(p, f"ups.{i}.2", x, t, taps)
+        x = resnet_block(p, f"ups.{i}.2", x, t, taps, mlp="time_mlp")
         x = torch.cat((x, h.pop()), dim=1)
-        x = resnet_block(p, f"ups.{i}.3", x, t, taps)
+        x = resnet_block(p, f"ups.{i}.3", x, t, taps, mlp="time_mlp")
         x = attn(f"ups.{i}.4", x, fa)
         if i == n - 1:
             x = F.conv3d(x, p[f"ups.{i}.5.weight"], p[f"ups.{i}.5.bias"], padding=1)
@@ -87,5 +87,5 @@ def unet3d_cond_forward(p, cfg, x, atb, time, taps=None):
             x = upsample(p, f"ups.{i}.5", x)
         _tap(taps, f"ups.{i}.5", x)
     x = torch.cat((x, r), dim=1)
-    x = resnet_block(p, "final_res_block", x, t, taps)
+    x = resnet_block(p, "final_res_block", x, t, taps, mlp="time_mlp")
     return F.conv3d(x, p["final_conv.weight"], p["final_conv.bias"])

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from conftest import rel_l2
-from oracle import interp, ref_loader, solvers, synth, task, unet3d
+from oracle import interp, ref_loader, solvers, synth, task, unet3d, unet3d_cond
 
 
 def _load(golden_dir, name):
@@ -60,6 +60,43 @@ def test_unet_small_arch_golden(golden_dir):
     with torch.no_grad():
         y = unet3d.unet3d_forward(p, cfg, x, torch.from_numpy(g["t"]))
     assert rel_l2(y, g["y"]) < 1e-5
+
+
+COND_SMALL = dict(dim=32, dim_mults=(1, 2), data_channels=15, time_resolution=64, time_bandwidth=100.0,
+                  attn_heads=2, attn_dim_head=16)
+
+
+def test_cond_param_specs_count_and_size():
+    specs = synth.unet3d_cond_param_specs(synth.make_cfg(data_channels=15))
+    assert len(specs) == 411
+    assert sum(int(np.prod(s)) for s in specs.values()) == 53_049_349
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present")
+def test_cond_param_specs_match_reference_state_dict():
+    for cfg in (synth.make_cfg(data_channels=15), synth.make_cfg(**COND_SMALL)):
+        sd = ref_loader.unet3d_cond_module().Unet3DCond(**cfg).state_dict()
+        specs = synth.unet3d_cond_param_specs(cfg)
+        assert list(sd.keys()) == list(specs.keys())
+        assert all(tuple(sd[k].shape) == tuple(specs[k]) for k in sd)
+
+
+def test_unet_cond_oracle_vs_reference_golden(golden_dir):
+    g = _load(golden_dir, "unet3d_cond.npz")
+    cfg = synth.make_cfg(data_channels=15)
+    p = synth.synth_unet3d_cond_params(cfg, 5)
+    shape = (1, 15, 16, 16, 16)
+    with torch.no_grad():
+        y = unet3d_cond.unet3d_cond_forward(p, cfg, synth.synth_input(shape, 6), synth.synth_atb(shape, 7),
+                                            torch.from_numpy(g["full_b1_16.t"]))
+    assert rel_l2(y, g["full_b1_16.y"]) < 1e-5
+    cfg2 = synth.make_cfg(**COND_SMALL)
+    p2 = synth.synth_unet3d_cond_params(cfg2, 8)
+    shape = (2, 15, 16, 16, 16)
+    with torch.no_grad():
+        y = unet3d_cond.unet3d_cond_forward(p2, cfg2, synth.synth_input(shape, 9), synth.synth_atb(shape, 10),
+                                            torch.from_numpy(g["small_b2_16.t"]))
+    assert rel_l2(y, g["small_b2_16.y"]) < 1e-5
 
 
 KINDS = {
