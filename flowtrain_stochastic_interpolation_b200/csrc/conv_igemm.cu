@@ -57,6 +57,7 @@ struct IgemmParams {
   int nHt, nWt, nSeg, LZ, NZ;
   int n_items;
   int nslot, wslot, w_resident;
+  int flat, Dext;              // 1x1x1 convs: tiles are 128 CONSECUTIVE voxels (Dext tiles per sample), else Dext = D
   int n_iss;                   // MMA issuer warps (each owns a contiguous share of a group's accumulators)
   uint32_t cg_pitch, row_pitch, src1_off, slot_stride, plane_tx_bytes, wtap_bytes;
   int KC, nkc;              // k-steps per weight chunk, chunks per tap (ring unit = one chunk)
@@ -96,7 +97,7 @@ __device__ __forceinline__ ItemCoord decode_item(const IgemmParams& p, int item)
   int seg = r % p.nSeg;
   c.b = r / p.nSeg;
   c.d0 = seg * p.LZ;
-  c.lz = min(p.LZ, p.D - c.d0);
+  c.lz = min(p.LZ, p.Dext - c.d0);
   c.h0 = ht * p.TH;
   c.w0 = wt * 8;
   return c;
@@ -508,6 +509,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
             mbar_expect_tx(&plane_full[slot], p.plane_tx_bytes);
             uint8_t* dst = s_planes + (size_t)slot * p.slot_stride;
             const int dz = c.d0 - p.pad + issued;
+            if (p.flat) {
+              tma_load_3d(dst, &tm0, &plane_full[slot], 0, dz * 128, c.b * p.s0_cgtot + p.s0_cgoff);
+              if (p.cg1 > 0)
+                tma_load_3d(dst + p.src1_off, &tm1, &plane_full[slot], 0, dz * 128, c.b * p.s1_cgtot + p.s1_cgoff);
+              continue;
+            }
             tma_load_4d(dst, &tm0, &plane_full[slot], (c.w0 - p.pad) * 8, c.h0 - p.pad, dz,
                         c.b * p.s0_cgtot + p.s0_cgoff);
             if (p.cg1 > 0)
@@ -702,7 +709,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
       pc_base += npl;
     }
     if (p.dbg && leader && iss == 0) {
-      long long* o = p.dbg + (size_t)blockIdx.x * 8;
+      long long* o = p.dbg + (size_t)blockIdx.x * 16;
       o[0] = clock64() - dbg_t0; o[1] = dbg_acc; o[2] = dbg_plane; o[3] = dbg_w; o[4] = dbg_nchunk; o[5] = dbg_issue; o[6] = dbg_tab;
     }
     __syncwarp();
@@ -726,11 +733,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     ec.cgs = cgs;
     uint32_t gctr = 0;
     int cur_b = -1;
+    long long e_wait = 0, e_t0 = clock64();
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const ItemCoord c = decode_item(p, item);
       const int ngroups = (c.lz + p.NZ - 1) / p.NZ;
       const int h = c.h0 + hl, w = c.w0 + wl;
-      ec.valid = (hl < p.TH) && (h < p.H) && (w < p.W);
+      ec.valid = p.flat || ((hl < p.TH) && (h < p.H) && (w < p.W));
       if (c.b != cur_b) {
         // (bias, mul, add) of sample b; without a norm the bias folds into the affine part
         named_bar_sync(1 + half, 128);
@@ -750,11 +758,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
       for (int g = 0; g < ngroups; ++g, ++gctr) {
         const int nze = min(p.NZ, c.lz - g * p.NZ);
         const uint32_t ab = gctr & 1;
+        long long ew0 = 0;
+        if (p.dbg) ew0 = clock64();
         mbar_wait(&acc_full[ab], (gctr >> 1) & 1);
+        if (p.dbg) e_wait += clock64() - ew0;
         tc_fence_after();
         for (int zi = (half + g) & 1; zi < nze; zi += 2) {
           const int d = c.d0 + g * p.NZ + zi;
-          const size_t vox = (size_t)d * plane_vox + (size_t)h * p.W + w;  // within one (b, cg)
+          // voxel index within one (b, cg): flat tiles are 128 consecutive voxels (the last may be ragged)
+          const size_t vox = p.flat ? (size_t)d * 128 + m : (size_t)d * plane_vox + (size_t)h * p.W + w;
+          if (p.flat) ec.valid = vox < cgs;
           const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (ab * p.NZ + zi) * p.N;
           float rs = 1.f;
           if (p.ss_in) {
@@ -792,6 +805,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[ab]);
       }
+    }
+    if (p.dbg && warp == 4 && lane == 0) {
+      long long* o = p.dbg + (size_t)blockIdx.x * 16;
+      o[8] = clock64() - e_t0; o[9] = e_wait;
     }
   }
 
@@ -888,7 +905,11 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   p.N = w.n;
   p.smax = 256 / p.N < 1 ? 1 : 256 / p.N;
   p.BW = 8 + 2 * p.pad;
-  p.nWt = cdiv(a0.W, 8);
+  // 1x1x1 convs have no halo, so their tiles are free-form: 128 consecutive voxels give 2 KB
+  // contiguous runs per channel group in HBM (16 x 8 bricks: 128 B runs) for loads and stores
+  p.flat = (p.K == 1 && getenv("FTB_NOFLAT") == nullptr) ? 1 : 0;
+  p.Dext = p.flat ? (int)((a0.voxels() + 127) / 128) : a0.D;
+  p.nWt = p.flat ? 1 : cdiv(a0.W, 8);
   p.row_pitch = p.BW * 16;
   p.kstep_bytes = (uint32_t)p.K * p.N * 32;
   p.wtap_bytes = (uint32_t)p.KS * p.kstep_bytes;
@@ -913,7 +934,7 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   bool fits = false;
   int nz_cap = 512 / (2 * p.N);
   if (nz_cap > 8) nz_cap = 8;
-  if (nz_cap > a0.D) nz_cap = a0.D;
+  if (nz_cap > p.Dext) nz_cap = p.Dext;
   if (p.K == 1 && nz_cap > 2) nz_cap = 2;
   if (const char* env = getenv("FTB_NZ")) {   // planner override for experiments
     const int v = atoi(env);
@@ -921,10 +942,11 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   }
   while (nz_cap > 1 && (nz_cap * p.K > kMaxEnt / 2 || nz_cap + 2 * p.pad > 32)) --nz_cap;
   FTB_CHECK(nz_cap >= 1, "conv: N tile too wide for a double-buffered accumulator");
-  for (int th = a0.H >= 16 ? 16 : a0.H; th >= 1 && !fits; th = th / 2) {   // first tile height that fits wins
+  for (int th = (a0.H >= 16 || p.flat) ? 16 : a0.H; th >= 1 && !fits; th = th / 2) {   // first tile height that fits wins
     p.TH = th;
     p.BH = p.TH + 2 * p.pad;
-    p.nHt = cdiv(a0.H, p.TH);
+    p.nHt = p.flat ? 1 : cdiv(a0.H, p.TH);
+    if (p.flat) p.row_pitch = 128;
     p.cg_pitch = p.BH * p.row_pitch;
     p.src1_off = (uint32_t)round_up(p.cg0 * (int)p.cg_pitch, 128);
     const uint32_t plane_bytes = p.src1_off + p.cg1 * p.cg_pitch;
@@ -938,7 +960,7 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
     // the fill of the last group of a typical depth segment.  Measured on 48->48 @64^3:
     // (NZ 4, ring 3) 300 us < (5, 4) 347 us < (3, 4) 421 us — the score orders them the same way.
     double best_score = 1e30;
-    const int dseg = a0.D < 16 ? a0.D : 16;
+    const int dseg = p.Dext < 16 ? p.Dext : 16;
     int ws_hi = nchunks == 1 ? 2 : (p.wchunk_bytes <= 8192 ? 6 : (p.wchunk_bytes <= 16384 ? 4 : 3));
     int ws_lo = 2;
     if (const char* env = getenv("FTB_WSLOT")) {
@@ -977,18 +999,18 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   p.nslot = nslot;
   // segment length along D: minimise (rounds of items over the SMs) x (planes per item, halo
   // planes counted at half weight: they cost loads but no MMAs)
-  int lz = a0.D;
+  int lz = p.Dext;
   {
     double best = 1e30;
-    for (int cand = a0.D; cand >= p.NZ; cand = cdiv(cand, 2)) {
-      const int cl = round_up(cand, p.NZ) > a0.D ? a0.D : round_up(cand, p.NZ);
-      const double cost = (double)cdiv(cols * cdiv(a0.D, cl), sms) * (cl + p.pad);
+    for (int cand = p.Dext; cand >= p.NZ; cand = cdiv(cand, 2)) {
+      const int cl = round_up(cand, p.NZ) > p.Dext ? p.Dext : round_up(cand, p.NZ);
+      const double cost = (double)cdiv(cols * cdiv(p.Dext, cl), sms) * (cl + p.pad);
       if (cost < best - 1e-9) { best = cost; lz = cl; }
       if (cand == 1) break;
     }
   }
   p.LZ = lz;
-  p.nSeg = cdiv(a0.D, lz);
+  p.nSeg = cdiv(p.Dext, lz);
   p.n_items = cols * p.nSeg;
   p.off_w = (uint32_t)round_up((int)(p.nslot * p.slot_stride + slack), 128);
   p.off_bar = (uint32_t)round_up((int)(p.off_w + w_region), 16);
@@ -1005,8 +1027,8 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   p.dbg = nullptr;
   if (getenv("FTB_CONV_DBG")) {
     static long long* dbuf = nullptr;
-    if (!dbuf) FTB_CUDA(cudaMalloc(&dbuf, 256 * 8 * sizeof(long long)));
-    FTB_CUDA(cudaMemsetAsync(dbuf, 0, 256 * 8 * sizeof(long long), st));
+    if (!dbuf) FTB_CUDA(cudaMalloc(&dbuf, 256 * 16 * sizeof(long long)));
+    FTB_CUDA(cudaMemsetAsync(dbuf, 0, 256 * 16 * sizeof(long long), st));
     p.dbg = dbuf;
     g_conv_dbg = dbuf;
   }
@@ -1024,8 +1046,13 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   p.q_dh = e.q_dim_head; p.q_scale = e.q_scale;
 
   CUtensorMap tm0, tm1;
-  FTB_TRY(make_plane_tmap(&tm0, a0, p.BW, p.BH, p.cg0));
-  if (s1.t) FTB_TRY(make_plane_tmap(&tm1, *s1.t, p.BW, p.BH, p.cg1)); else tm1 = tm0;
+  if (p.flat) {
+    FTB_TRY(make_voxel_tmap(&tm0, a0, 128, p.cg0));
+    if (s1.t) FTB_TRY(make_voxel_tmap(&tm1, *s1.t, 128, p.cg1)); else tm1 = tm0;
+  } else {
+    FTB_TRY(make_plane_tmap(&tm0, a0, p.BW, p.BH, p.cg0));
+    if (s1.t) FTB_TRY(make_plane_tmap(&tm1, *s1.t, p.BW, p.BH, p.cg1)); else tm1 = tm0;
+  }
 
   static bool attr_set = false;
   if (!attr_set) {

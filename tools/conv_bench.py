@@ -51,15 +51,15 @@ def dbg():
         f = _lib.lib.ftb_test_conv_debug
     except AttributeError:
         return
-    buf = (C.c_longlong * (148 * 8))()
-    if f(buf, 148 * 8) != 0:
+    buf = (C.c_longlong * (148 * 16))()
+    if f(buf, 148 * 16) != 0:
         return
     import statistics
-    rows = [buf[i * 8:(i + 1) * 8] for i in range(148) if buf[i * 8] > 0]
+    rows = [buf[i * 16:(i + 1) * 16] for i in range(148) if buf[i * 16] > 0]
     if rows:
-        med = [statistics.median(r[k] for r in rows) for k in range(7)]
+        med = [statistics.median(r[k] for r in rows) for k in range(10)]
         print(f"    issuer0 cycles: total {med[0]:.0f}  wait acc {med[1]:.0f}  planes {med[2]:.0f}  weights {med[3]:.0f}  "
-              f"chunks {med[4]:.0f}  -> busy {med[0]-med[1]-med[2]-med[3]:.0f} (issue {med[5]:.0f}, table {med[6]:.0f})", flush=True)
+              f"chunks {med[4]:.0f}  -> busy {med[0]-med[1]-med[2]-med[3]:.0f} (issue {med[5]:.0f}, table {med[6]:.0f}); epilogue warp4: total {med[8]:.0f} wait {med[9]:.0f}", flush=True)
 
 
 for s in SHAPES:
