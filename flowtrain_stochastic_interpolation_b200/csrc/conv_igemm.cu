@@ -44,13 +44,19 @@ constexpr int kMaxSlots = 12;
 constexpr int kMaxWSlots = 32;
 constexpr int kMaxEnt = 96;   // MMA table entries per group (first-chunk pairs + stacked runs)
 constexpr int kMaxKS = 32;    // k-steps (Cin_pad / 16)
+constexpr int kMaxCC = 16;    // channel chunks (passes) per group
 
 enum : int { F_SILU = 1, F_QSOFTMAX = 2, F_NOMMA = 4, F_PLAIN = 8 };
 
 struct IgemmParams {
   int B, D, H, W;
   int K, pad, taps;            // taps = K*K (kh, kw) positions; the K depth taps are stacked along N
-  int cg0, cg1, KS0, KS;
+  int cg0, cg1, KS;
+  // Input channels are processed in chunks ("passes"): a ring slot holds ONE plane of ONE chunk (<= 64
+  // channels), so the plane window stays small for any Cin.  ncc == 1: the window slides along D and
+  // halo planes are kept between groups; ncc > 1: every (group, chunk) pass loads its own window.
+  int ncc;
+  int cc_src[kMaxCC], cc_cgoff[kMaxCC], cc_ks[kMaxCC], cc_ks0[kMaxCC];   // source, first cg, k-steps, first k-step
   int s0_cgtot, s0_cgoff, s1_cgtot, s1_cgoff;
   int N, smax;                 // smax: adjacent accumulators one MMA may cover (smax*N <= 256)
   int TH, BH, BW;
@@ -59,9 +65,8 @@ struct IgemmParams {
   int nslot, wslot, w_resident;
   int flat, Dext;              // 1x1x1 convs: tiles are 128 CONSECUTIVE voxels (Dext tiles per sample), else Dext = D
   int n_iss;                   // MMA issuer warps (each owns a contiguous share of a group's accumulators)
-  uint32_t cg_pitch, row_pitch, src1_off, slot_stride, plane_tx_bytes, wtap_bytes;
-  int KC, nkc;              // k-steps per weight chunk, chunks per tap (ring unit = one chunk)
-  uint32_t wchunk_bytes;    // KC * K * N * 32 (ring slot stride)
+  uint32_t cg_pitch, row_pitch, slot_stride, wtap_bytes;
+  uint32_t wchunk_bytes;    // weight ring slot: one (tap, channel chunk) = max cc_ks * kstep_bytes
   uint32_t kstep_bytes;     // K * N * 32: one k-step of one (kh,kw) position, all depth taps
   uint32_t off_w, off_bar;
   uint32_t tmem_cols;
@@ -492,51 +497,53 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
-      uint32_t pctr = 0;  // planes issued so far (ring position)
-      uint32_t wctr = 0;  // weight taps issued so far
+      uint32_t pslot = 0, pphase = 0;   // plane ring cursor
+      uint32_t wslot = 0, wphase = 0;   // weight ring cursor
+      bool w_loaded = false;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const ItemCoord c = decode_item(p, item);
         const int npl = c.lz + 2 * p.pad;
         const int ngroups = (c.lz + p.NZ - 1) / p.NZ;
-        int issued = 0;
+        int issued = 0;   // ncc == 1: planes of this item loaded so far
         for (int g = 0; g < ngroups; ++g) {
           const int nze = min(p.NZ, c.lz - g * p.NZ);
-          const int need = min(npl, g * p.NZ + nze + 2 * p.pad);
-          for (; issued < need; ++issued, ++pctr) {
-            const uint32_t slot = pctr % p.nslot;
-            const uint32_t par = (pctr / p.nslot) & 1;
-            mbar_wait(&plane_empty[slot], par ^ 1);
-            mbar_expect_tx(&plane_full[slot], p.plane_tx_bytes);
-            uint8_t* dst = s_planes + (size_t)slot * p.slot_stride;
-            const int dz = c.d0 - p.pad + issued;
-            if (p.flat) {
-              tma_load_3d(dst, &tm0, &plane_full[slot], 0, dz * 128, c.b * p.s0_cgtot + p.s0_cgoff);
-              if (p.cg1 > 0)
-                tma_load_3d(dst + p.src1_off, &tm1, &plane_full[slot], 0, dz * 128, c.b * p.s1_cgtot + p.s1_cgoff);
-              continue;
+          const int win = nze + 2 * p.pad;
+          for (int cc = 0; cc < p.ncc; ++cc) {
+            const bool s1 = p.cc_src[cc] != 0;
+            const CUtensorMap* tm = s1 ? &tm1 : &tm0;
+            const int cgc = c.b * (s1 ? p.s1_cgtot : p.s0_cgtot) + (s1 ? p.s1_cgoff : p.s0_cgoff) + p.cc_cgoff[cc];
+            const uint32_t bytes = (uint32_t)p.cc_ks[cc] * 2u * p.cg_pitch;
+            int q_lo, q_hi;   // item-relative planes to load for this pass
+            if (p.ncc == 1) { q_lo = issued; q_hi = min(npl, g * p.NZ + win); issued = q_hi; }
+            else { q_lo = g * p.NZ; q_hi = q_lo + win; }
+            for (int q = q_lo; q < q_hi; ++q) {
+              mbar_wait(&plane_empty[pslot], pphase ^ 1);
+              mbar_expect_tx(&plane_full[pslot], bytes);
+              uint8_t* dst = s_planes + (size_t)pslot * p.slot_stride;
+              const int dz = c.d0 - p.pad + q;
+              if (p.flat) tma_load_3d(dst, tm, &plane_full[pslot], 0, dz * 128, cgc);
+              else tma_load_4d(dst, tm, &plane_full[pslot], (c.w0 - p.pad) * 8, c.h0 - p.pad, dz, cgc);
+              if (++pslot == (uint32_t)p.nslot) { pslot = 0; pphase ^= 1; }
             }
-            tma_load_4d(dst, &tm0, &plane_full[slot], (c.w0 - p.pad) * 8, c.h0 - p.pad, dz,
-                        c.b * p.s0_cgtot + p.s0_cgoff);
-            if (p.cg1 > 0)
-              tma_load_4d(dst + p.src1_off, &tm1, &plane_full[slot], (c.w0 - p.pad) * 8,
-                          c.h0 - p.pad, dz, c.b * p.s1_cgtot + p.s1_cgoff);
-          }
-          if (!p.w_resident || wctr == 0) {
-            const bf16* wsrc = p.wpack + (long long)c.b * p.w_batch_stride;
-            for (int t = 0; t < p.taps; ++t)
-              for (int kc = 0; kc < p.nkc; ++kc, ++wctr) {
-                const uint32_t slot = wctr % p.wslot;
-                const uint32_t par = (wctr / p.wslot) & 1;
-                const uint32_t nks = min(p.KC, p.KS - kc * p.KC);
-                const uint32_t bytes = nks * p.kstep_bytes;
-                mbar_wait(&w_empty[slot], par ^ 1);
-                mbar_expect_tx(&w_full[slot], bytes);
-                bulk_load(s_w + (size_t)slot * p.wchunk_bytes,
-                          reinterpret_cast<const uint8_t*>(wsrc) + (size_t)t * p.wtap_bytes +
-                              (size_t)kc * p.wchunk_bytes,
-                          bytes, &w_full[slot]);
+            if (!p.w_resident || !w_loaded) {
+              const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack + (long long)c.b * p.w_batch_stride) +
+                                    (size_t)p.cc_ks0[cc] * p.kstep_bytes;
+              const uint32_t wbytes = (uint32_t)p.cc_ks[cc] * p.kstep_bytes;
+              for (int t = 0; t < p.taps; ++t) {
+                uint32_t slot;
+                if (p.w_resident) {
+                  slot = (uint32_t)(cc * p.taps + t);
+                } else {
+                  slot = wslot;
+                  mbar_wait(&w_empty[slot], wphase ^ 1);
+                  if (++wslot == (uint32_t)p.wslot) { wslot = 0; wphase ^= 1; }
+                }
+                mbar_expect_tx(&w_full[slot], wbytes);
+                bulk_load(s_w + (size_t)slot * p.wchunk_bytes, wsrc + (size_t)t * p.wtap_bytes, wbytes, &w_full[slot]);
               }
+            }
           }
+          w_loaded = true;
         }
       }
     }
@@ -566,7 +573,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     const uint32_t w_enc = (smem_u32(s_w) >> 4) | ((128u >> 4) << 16);
     const uint32_t wchunk_enc = p.wchunk_bytes >> 4;
     const uint32_t rowp_enc = p.row_pitch >> 4;
-    const uint32_t kjump = (p.src1_off >> 4) - (uint32_t)p.KS0 * ic.kinc;   // extra offset entering src1
     const uint32_t idesc0 = umma_idesc_bf16_f32(128, 0);
     const uint32_t idesc_n = (uint32_t)(p.N >> 3) << 17;
     const uint32_t nb_enc = (uint32_t)(p.N * 2);                           // one depth tap of B rows, >>4
@@ -576,7 +582,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     // ring cursors, advanced incrementally (no divisions on the issue path)
     uint32_t slot_w0 = 0;                  // ring slot of the current window's plane 0
     uint32_t rslot = 0, rphase = 0;        // next plane_full barrier to wait for
-    uint32_t planes_waited = 0, pc_base = 0;
     uint32_t wslot = 0, wphase = 0;        // next streamed weight chunk
     uint32_t gctr = 0;
     int tab_nze = -1, n_first = 0, n_main = 0;
@@ -587,6 +592,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
       const ItemCoord c = decode_item(p, item);
       const int npl = c.lz + 2 * p.pad;
       const int ngroups = (c.lz + p.NZ - 1) / p.NZ;
+      int waited = 0;   // ncc == 1: planes of this item already waited for
       for (int g = 0; g < ngroups; ++g, ++gctr) {
         const int nze = min(p.NZ, c.lz - g * p.NZ);
         const int win = nze + 2 * p.pad;
@@ -633,22 +639,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
           long long tq0 = 0;
           if (p.dbg) tq0 = clock64();
           mbar_wait(&acc_empty[ab], ((gctr >> 1) & 1) ^ 1);
-          if (p.dbg) { const long long t = clock64(); dbg_acc += t - tq0; tq0 = t; }
-          const uint32_t need = pc_base + (uint32_t)min(npl, g * p.NZ + win);
-          while (planes_waited < need) {
-            mbar_wait(&plane_full[rslot], rphase);
-            ++planes_waited;
-            if (++rslot == ic.nslot) { rslot = 0; rphase ^= 1; }
-          }
-          if (p.dbg) dbg_plane += clock64() - tq0;
-          tc_fence_after();
-          ic.slot_w0 = slot_w0;
+          if (p.dbg) dbg_acc += clock64() - tq0;
           ic.acc0 = tmem_base + ab * p.NZ * p.N;
-          int t = 0;
-          for (int kh = 0; kh < p.K; ++kh)
-            for (int kw = 0; kw < p.K; ++kw, ++t) {
-              const uint32_t tapoff = kh * rowp_enc + kw;
-              for (int kc = 0; kc < p.nkc; ++kc) {
+          for (int cc = 0; cc < p.ncc; ++cc) {
+            if (p.dbg) tq0 = clock64();
+            int n_new;
+            if (p.ncc == 1) { const int upto = min(npl, g * p.NZ + win); n_new = upto - waited; waited = upto; }
+            else n_new = win;
+            for (int i = 0; i < n_new; ++i) {
+              mbar_wait(&plane_full[rslot], rphase);
+              if (++rslot == ic.nslot) { rslot = 0; rphase ^= 1; }
+            }
+            if (p.dbg) dbg_plane += clock64() - tq0;
+            tc_fence_after();
+            ic.slot_w0 = slot_w0;
+            const int nks = p.cc_ks[cc];
+            int t = 0;
+            for (int kh = 0; kh < p.K; ++kh)
+              for (int kw = 0; kw < p.K; ++kw, ++t) {
+                const uint32_t aoff = kh * rowp_enc + kw;
                 uint32_t wslot_i;
                 if (stream_w) {
                   wslot_i = wslot;
@@ -658,18 +667,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
                   if (p.dbg) { dbg_w += clock64() - tq1; ++dbg_nchunk; }
                   tc_fence_after();
                 } else {
-                  wslot_i = t * p.nkc + kc;
+                  wslot_i = (uint32_t)(cc * p.taps + t);
                   if (!w_waited) {
                     mbar_wait(&w_full[wslot_i], 0);
                     tc_fence_after();
                   }
                 }
                 const uint32_t wb = w_enc + wslot_i * wchunk_enc;
-                // a chunk never straddles the src0/src1 boundary (host picks KC | KS0)
-                const int ks_lo = kc * p.KC;
-                const int nks = min(p.KS, ks_lo + p.KC) - ks_lo;
-                const bool firstc = (t | kc) == 0;
-                const uint32_t aoff = tapoff + ks_lo * ic.kinc + (ks_lo >= p.KS0 ? kjump : 0u);
+                const bool firstc = (cc | t) == 0;
                 const uint32_t ea = tab_addr + (firstc ? 0u : (uint32_t)n_first * 16u);
                 const uint32_t ea_end = ea + (uint32_t)(firstc ? n_first : n_main) * 16u;
                 long long ti0 = 0;
@@ -682,8 +687,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
                     case 2: issue_entries<2>(ic, ea, ea_end, aoff, wb, firstc); break;
                     case 3: issue_entries<3>(ic, ea, ea_end, aoff, wb, firstc); break;
                     case 4: issue_entries<4>(ic, ea, ea_end, aoff, wb, firstc); break;
-                    case 5: issue_entries<5>(ic, ea, ea_end, aoff, wb, firstc); break;
-                    case 6: issue_entries<6>(ic, ea, ea_end, aoff, wb, firstc); break;
                     default:
                       for (int i = 0; i < nks; ++i)
                         issue_entries<1>(ic, ea, ea_end, aoff + i * ic.kinc, wb + i * ic.kstep, firstc && i == 0);
@@ -695,18 +698,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
                   if (++wslot == (uint32_t)p.wslot) { wslot = 0; wphase ^= 1; }
                 }
               }
+            if (p.ncc > 1) {   // this pass's window is done: hand all its slots back
+              for (int i = 0; i < win; ++i) {
+                umma_commit(&plane_empty[slot_w0]);
+                if (++slot_w0 == ic.nslot) slot_w0 = 0;
+              }
             }
-          // planes that leave the window: the NZ oldest, or everything at the end of the item
-          const int nrel = (g == ngroups - 1) ? win : nze;
-          for (int i = 0; i < nrel; ++i) {
-            umma_commit(&plane_empty[slot_w0]);
-            if (++slot_w0 == ic.nslot) slot_w0 = 0;
+          }
+          if (p.ncc == 1) {
+            // planes that leave the sliding window: the NZ oldest, or everything at the end of the item
+            const int nrel = (g == ngroups - 1) ? win : nze;
+            for (int i = 0; i < nrel; ++i) {
+              umma_commit(&plane_empty[slot_w0]);
+              if (++slot_w0 == ic.nslot) slot_w0 = 0;
+            }
           }
           umma_commit(&acc_full[ab]);
         }
         w_waited = true;
       }
-      pc_base += npl;
     }
     if (p.dbg && leader && iss == 0) {
       long long* o = p.dbg + (size_t)blockIdx.x * 16;
@@ -898,7 +908,7 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   p.B = a0.B; p.D = a0.D; p.H = a0.H; p.W = a0.W;
   p.K = w.ksize; p.pad = (w.ksize - 1) / 2; p.taps = w.ksize * w.ksize;
   p.cg0 = s0.cg; p.cg1 = s1.t ? s1.cg : 0;
-  p.KS0 = p.cg0 / 2; p.KS = (p.cg0 + p.cg1) / 2;
+  p.KS = (p.cg0 + p.cg1) / 2;
   FTB_CHECK(p.KS <= kMaxKS, "conv: more than 512 input channels");
   p.s0_cgtot = a0.cg(); p.s0_cgoff = s0.cgoff;
   p.s1_cgtot = s1.t ? s1.t->cg() : 0; p.s1_cgoff = s1.cgoff;
@@ -913,16 +923,41 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   p.row_pitch = p.BW * 16;
   p.kstep_bytes = (uint32_t)p.K * p.N * 32;
   p.wtap_bytes = (uint32_t)p.KS * p.kstep_bytes;
-  // weight ring unit: a chunk of KC k-steps of one (kh,kw) position (all depth taps), <= 24 KB
-  p.KC = p.KS;
-  while (p.KC > 1 && ((uint32_t)p.KC * p.kstep_bytes > 24 * 1024 || (p.cg1 > 0 && p.KS0 % p.KC != 0))) --p.KC;
-  p.nkc = cdiv(p.KS, p.KC);
-  p.wchunk_bytes = (uint32_t)p.KC * p.kstep_bytes;
-  const int nchunks = p.taps * p.nkc;
+  // ---- channel chunks: each source is cut into equal chunks of `ccg` channel groups (an even
+  // divisor of its group count, <= 8 groups = 64 channels for K > 1, whose weight chunk of one
+  // (kh,kw) position stays <= 56 KB).  One source of <= 8 groups is a single chunk: the classic
+  // sliding window.
+  const int cg_cap = p.K == 1 ? 16 : 8;
+  const uint32_t kWChunkMax = 56 * 1024;
+  auto pick = [&](int cg) {
+    for (int d = cg < cg_cap ? cg : cg_cap; d > 2; d -= 2)
+      if (cg % d == 0 && (uint32_t)(d / 2) * p.kstep_bytes <= kWChunkMax) return d;
+    return 2;
+  };
+  if (const char* env = getenv("FTB_NOCHUNK")) { (void)env; }
+  p.ncc = 0;
+  int max_ccg = 0;
+  {
+    const int cgs[2] = {p.cg0, p.cg1};
+    int ks0 = 0;
+    for (int sidx = 0; sidx < 2; ++sidx) {
+      if (cgs[sidx] == 0) continue;
+      const int ccg = pick(cgs[sidx]);
+      for (int off = 0; off < cgs[sidx]; off += ccg) {
+        FTB_CHECK(p.ncc < kMaxCC, "conv: too many channel chunks (channel count with no even divisor <= 64/8?)");
+        p.cc_src[p.ncc] = sidx; p.cc_cgoff[p.ncc] = off; p.cc_ks[p.ncc] = ccg / 2; p.cc_ks0[p.ncc] = ks0;
+        ks0 += ccg / 2;
+        ++p.ncc;
+      }
+      if (ccg > max_ccg) max_ccg = ccg;
+    }
+  }
+  p.wchunk_bytes = (uint32_t)(max_ccg / 2) * p.kstep_bytes;
+  const int nchunks = p.taps * p.ncc;
   const int sms = num_sms();
   const uint32_t bar_bytes =
       (2 * kMaxSlots + 2 * kMaxWSlots + 4) * 8 + 16 + kMaxIss * kMaxEnt * 16 + 2 * 3 * kMaxN * 4;
-  const size_t all_w = (size_t)p.taps * p.wtap_bytes;
+  const size_t all_w = (size_t)nchunks * p.wchunk_bytes;   // resident layout: one ring-sized slot per (chunk, tap)
 
   // ---- tile height, planes per group (NZ) and ring sizing against the 227 KB shared-memory
   // budget.  The tile is 8 (W) x TH (H) voxels in the 128-row MMA; TH = 16 unless a plane window
@@ -948,10 +983,7 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
     p.nHt = p.flat ? 1 : cdiv(a0.H, p.TH);
     if (p.flat) p.row_pitch = 128;
     p.cg_pitch = p.BH * p.row_pitch;
-    p.src1_off = (uint32_t)round_up(p.cg0 * (int)p.cg_pitch, 128);
-    const uint32_t plane_bytes = p.src1_off + p.cg1 * p.cg_pitch;
-    p.plane_tx_bytes = (p.cg0 + p.cg1) * p.cg_pitch;
-    p.slot_stride = (uint32_t)round_up((int)plane_bytes, 128);
+    p.slot_stride = (uint32_t)round_up(max_ccg * (int)p.cg_pitch, 128);   // one plane of one channel chunk
     slack = (uint32_t)(16 - p.TH + 2) * p.row_pitch + 512;  // A rows of a partial tile over-read
     fixed = slack + bar_bytes + 256;
     // Candidates (NZ, weight ring): score = shared-memory A reads per output plane
@@ -961,7 +993,7 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
     // (NZ 4, ring 3) 300 us < (5, 4) 347 us < (3, 4) 421 us — the score orders them the same way.
     double best_score = 1e30;
     const int dseg = p.Dext < 16 ? p.Dext : 16;
-    int ws_hi = nchunks == 1 ? 2 : (p.wchunk_bytes <= 8192 ? 6 : (p.wchunk_bytes <= 16384 ? 4 : 3));
+    int ws_hi = nchunks == 1 ? 2 : (p.wchunk_bytes <= 8192 ? 6 : (p.wchunk_bytes <= 16384 ? 4 : (p.wchunk_bytes <= 32768 ? 3 : 2)));
     int ws_lo = 2;
     if (const char* env = getenv("FTB_WSLOT")) {
       const int v = atoi(env);
@@ -978,7 +1010,10 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
         int ns = (int)((kSmemLimit - fixed - wbytes) / p.slot_stride);
         ns = ns > kMaxSlots ? kMaxSlots : ns;
         const int spare = ns - win;
-        double score = (double)win / nz + 0.35 * (spare >= nz ? 0.0 : (double)(nz - spare) / nz);
+        // planes that must be fetched per group (sliding window: NZ new ones; chunked passes: a
+        // whole window per pass) and cannot be prefetched into spare slots
+        const int fetch = p.ncc == 1 ? nz : win;
+        double score = (double)win / nz + 0.35 * (spare >= fetch ? 0.0 : (double)(fetch - spare) / fetch);
         score = score / fill - (resident ? 0.1 : 0.0) + (ws == 2 && !resident && nchunks > 1 ? 0.05 : 0.0);
         if (score < best_score - 1e-9) {
           best_score = score;
@@ -1046,12 +1081,13 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   p.q_dh = e.q_dim_head; p.q_scale = e.q_scale;
 
   CUtensorMap tm0, tm1;
+  const int box0 = pick(p.cg0), box1 = s1.t ? pick(p.cg1) : 0;   // TMA box = one channel chunk
   if (p.flat) {
-    FTB_TRY(make_voxel_tmap(&tm0, a0, 128, p.cg0));
-    if (s1.t) FTB_TRY(make_voxel_tmap(&tm1, *s1.t, 128, p.cg1)); else tm1 = tm0;
+    FTB_TRY(make_voxel_tmap(&tm0, a0, 128, box0));
+    if (s1.t) FTB_TRY(make_voxel_tmap(&tm1, *s1.t, 128, box1)); else tm1 = tm0;
   } else {
-    FTB_TRY(make_plane_tmap(&tm0, a0, p.BW, p.BH, p.cg0));
-    if (s1.t) FTB_TRY(make_plane_tmap(&tm1, *s1.t, p.BW, p.BH, p.cg1)); else tm1 = tm0;
+    FTB_TRY(make_plane_tmap(&tm0, a0, p.BW, p.BH, box0));
+    if (s1.t) FTB_TRY(make_plane_tmap(&tm1, *s1.t, p.BW, p.BH, box1)); else tm1 = tm0;
   }
 
   static bool attr_set = false;
