@@ -124,10 +124,11 @@ ctx_partial_kernel(const bf16* __restrict__ qkv, int cgtot, int heads, size_t vo
 // [channel group][voxel][8 channels] IS the no-swizzle MN-major UMMA layout (core matrix = 8
 // voxels x 16 B, LBO = 128 B along voxels, SBO = channel-group pitch), so v is consumed exactly
 // as TMA delivers it and k needs only the elementwise exp in place.
-//   warp 0: TMA producer | warp 1: MMA issuer | warps 2-5: exp pass, then TMEM -> partials
+//   warp 0: TMA producer | warp 1: MMA issuer | warps 2-9: exp pass (8 channel groups each half);
+//   warps 2-5 then move TMEM -> partials
 constexpr int kCtxT = 128;       // voxels per stage
 constexpr int kCtxStages = 3;
-constexpr int kCtxThreads = 192;
+constexpr int kCtxThreads = 320;   // TMA warp | MMA warp | 8 exp warps
 
 struct CtxParams {
   int heads, dh, hd;             // hd = heads*dh = 128
@@ -162,7 +163,7 @@ ctx_tc_kernel(const __grid_constant__ CUtensorMap tm, const CtxParams p) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < kCtxStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&ready[i], 128);
+      mbar_init(&ready[i], 256);
       mbar_init(&empty[i], 1);
     }
     mbar_init(done, 1);
@@ -175,9 +176,9 @@ ctx_tc_kernel(const __grid_constant__ CUtensorMap tm, const CtxParams p) {
   }
   if (warp >= 2) {
     const int t = threadIdx.x - 64;
-    s_kmax[t] = __ldg(p.kmax + (size_t)b * p.hd + t);
+    if (t < 128) s_kmax[t] = __ldg(p.kmax + (size_t)b * p.hd + t);
     // constant channel groups 16,17 of every stage's V tile: channel 128 = 1, the rest 0
-    for (int i = t; i < kCtxStages * 2 * kCtxT; i += 128) {
+    for (int i = t; i < kCtxStages * 2 * kCtxT; i += 256) {
       const int st = i / (2 * kCtxT), r = i % (2 * kCtxT);
       uint4 u = make_uint4(0u, 0u, 0u, 0u);
       if (r < kCtxT) u.x = 0x00003F80u;  // bf16 1.0 in element 0
@@ -223,7 +224,8 @@ ctx_tc_kernel(const __grid_constant__ CUtensorMap tm, const CtxParams p) {
     }
     __syncwarp();
   } else {
-    const int t = threadIdx.x - 64;  // 0..127
+    const int t = (threadIdx.x - 64) & 127;     // voxel of the tile
+    const int cg_lo = ((threadIdx.x - 64) >> 7) * 8;   // this thread's 8 channel groups
     for (int i = 0; i < nt; ++i) {
       const int s = i % kCtxStages;
       mbar_wait(&full[s], (i / kCtxStages) & 1);
@@ -231,7 +233,7 @@ ctx_tc_kernel(const __grid_constant__ CUtensorMap tm, const CtxParams p) {
       const long long v = (long long)(t_lo + i) * kCtxT + t;
       const bool in = v < p.vox;
 #pragma unroll 4
-      for (int cg = 0; cg < 16; ++cg) {
+      for (int cg = cg_lo; cg < cg_lo + 8; ++cg) {
         uint4* u = reinterpret_cast<uint4*>(kt + (cg * kCtxT + t) * 16);
         float f[8];
         unpack_bf16x8(*u, f);
@@ -246,7 +248,8 @@ ctx_tc_kernel(const __grid_constant__ CUtensorMap tm, const CtxParams p) {
       fence_proxy_async();
       mbar_arrive(&ready[s]);
     }
-    // ---- TMEM -> partials: row t = (head, d); own head's 32 columns + the denominator column
+    // ---- TMEM -> partials (warps 2-5): row = (head, d); own head's columns + the denominator column
+    if (warp < 6) {
     const int q = warp & 3;            // TMEM lane quadrant of this warp
     const int row = q * 32 + lane;
     const int h = row / p.dh, d = row % p.dh;
@@ -275,6 +278,7 @@ ctx_tc_kernel(const __grid_constant__ CUtensorMap tm, const CtxParams p) {
     } else {
       for (int e = 0; e < p.dh; ++e) out[d * p.dh + e] = 0.f;
       out[p.dh * p.dh + d] = 0.f;
+    }
     }
   }
   tc_fence_before();

@@ -73,18 +73,24 @@ __device__ __forceinline__ Lerp lerp_idx(int o, int in, int out) {
   return r;
 }
 
-__global__ void trilinear_kernel(const bf16* __restrict__ in, int B, int CG, int Di, int Hi, int Wi,
-                                 int Do, int Ho, int Wo, bf16* __restrict__ out) {
-  const size_t vo = (size_t)Do * Ho * Wo, vi = (size_t)Di * Hi * Wi;
-  const size_t total = (size_t)B * CG * vo;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const int w = (int)(i % Wo);
-    const int h = (int)((i / Wo) % Ho);
-    const int d = (int)((i / ((size_t)Wo * Ho)) % Do);
-    const size_t bc = i / vo;
-    const Lerp ld = lerp_idx(d, Di, Do), lh = lerp_idx(h, Hi, Ho), lw = lerp_idx(w, Wi, Wo);
-    const bf16* base = in + bc * vi * 8;
+// One block per (b*cg, d, group of RH output rows): the depth/height lerp parameters are computed
+// from block-uniform values, each thread only does the W lerp of its voxel (no per-thread div/mod).
+constexpr int kTriRH = 4;
+__global__ void __launch_bounds__(256)
+trilinear_kernel(const bf16* __restrict__ in, int CG, int Di, int Hi, int Wi, int Do, int Ho, int Wo,
+                 int hgroups, bf16* __restrict__ out) {
+  int blk = blockIdx.x;
+  const int hg = blk % hgroups; blk /= hgroups;
+  const int d = blk % Do;
+  const size_t bc = blk / Do;
+  const Lerp ld = lerp_idx(d, Di, Do);
+  const bf16* base = in + bc * (size_t)Di * Hi * Wi * 8;
+  bf16* obase = out + (bc * (size_t)Do + d) * Ho * Wo * 8;
+  for (int idx = threadIdx.x; idx < kTriRH * Wo; idx += blockDim.x) {
+    const int hr = idx / Wo, w = idx - hr * Wo;
+    const int h = hg * kTriRH + hr;
+    if (h >= Ho) break;
+    const Lerp lh = lerp_idx(h, Hi, Ho), lw = lerp_idx(w, Wi, Wo);
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -109,7 +115,7 @@ __global__ void trilinear_kernel(const bf16* __restrict__ in, int B, int CG, int
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += wd * accd[j];
     }
-    *reinterpret_cast<uint4*>(out + i * 8) = pack_bf16x8(acc);
+    *reinterpret_cast<uint4*>(obase + ((size_t)h * Wo + w) * 8) = pack_bf16x8(acc);
   }
 }
 
@@ -384,8 +390,12 @@ int unpack_blocked_to_ncdhw(const Act& in, int cgoff, int C, float* out, cudaStr
 }
 int trilinear_resample(const Act& in, Act& out, cudaStream_t st) {
   FTB_CHECK(in.B == out.B && in.C == out.C, "trilinear: batch/channels must match");
-  trilinear_kernel<<<grid_for((size_t)out.B * out.cg() * out.voxels(), 256), 256, 0, st>>>(
-      in.p, in.B, in.cg(), in.D, in.H, in.W, out.D, out.H, out.W, out.p);
+  const int hgroups = cdiv(out.H, kTriRH);
+  const long long blocks = (long long)out.B * out.cg() * out.D * hgroups;
+  FTB_CHECK(blocks < (1ll << 31), "trilinear: grid too large");
+  const int threads = kTriRH * out.W >= 256 ? 256 : round_up(kTriRH * out.W, 32);
+  trilinear_kernel<<<(unsigned)blocks, threads, 0, st>>>(in.p, in.cg(), in.D, in.H, in.W, out.D, out.H, out.W,
+                                                         hgroups, out.p);
   FTB_LAUNCH_OK();
   return 0;
 }

@@ -532,7 +532,11 @@ struct Fwd {
       FTB_TRY(conv(p + ".to_out", ConvSrc{&ao, 0, ao.cg()}, ConvSrc{}, eo, *out));
     } else {
       const size_t vox = x.voxels();
-      int nsplit = (int)(vox / 2048);
+      // voxel slices per sample for the context GEMM: about two CTAs per SM over the batch, each
+      // with at least a few 128-voxel tiles
+      int nsplit = cdiv(2 * num_sms(), B);
+      const int max_split = (int)((vox + 511) / 512);
+      nsplit = nsplit > max_split ? max_split : nsplit;
       nsplit = nsplit < 1 ? 1 : (nsplit > 256 ? 256 : nsplit);
       float* kmax = f32((size_t)B * hd);
       float* part = f32((size_t)B * heads * nsplit * (dh * dh + dh));

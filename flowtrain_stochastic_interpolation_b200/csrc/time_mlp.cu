@@ -9,7 +9,7 @@ namespace ftb {
 
 namespace {
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 time_embed_kernel(TimeMlpParams p, const float* __restrict__ t, float* __restrict__ temb,
                   float* __restrict__ temb_silu) {
   extern __shared__ float sm[];
@@ -80,7 +80,7 @@ int time_embed(const TimeMlpParams& p, const float* t, int B, float* temb, float
                cudaStream_t st) {
   const size_t smem = (size_t)(p.time_res + p.time_dim) * sizeof(float);
   FTB_CHECK(smem <= 48 * 1024, "time_embed: time_resolution + time_dim too large for shared memory");
-  time_embed_kernel<<<B, 256, smem, st>>>(p, t, temb, temb_silu);
+  time_embed_kernel<<<B, 1024, smem, st>>>(p, t, temb, temb_silu);   // 32 warps: the row loops are latency-bound
   FTB_LAUNCH_OK();
   return 0;
 }
