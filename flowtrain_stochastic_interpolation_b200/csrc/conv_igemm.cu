@@ -934,7 +934,6 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
       if (cg % d == 0 && (uint32_t)(d / 2) * p.kstep_bytes <= kWChunkMax) return d;
     return 2;
   };
-  if (const char* env = getenv("FTB_NOCHUNK")) { (void)env; }
   p.ncc = 0;
   int max_ccg = 0;
   {
@@ -1097,6 +1096,10 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
     attr_set = true;
   }
   const int grid = p.n_items < sms ? p.n_items : sms;
+  if (getenv("FTB_CONV_PLAN"))
+    fprintf(stderr, "conv plan: K%d cin %d(+%d) N%d @%dx%dx%d B%d -> ncc %d NZ %d iss %d wslot %d%s nslot %d LZ %d TH %d items %d smem %u\n",
+            p.K, p.cg0 * 8, p.cg1 * 8, p.N, p.D, p.H, p.W, p.B, p.ncc, p.NZ, p.n_iss, p.wslot,
+            p.w_resident ? "(resident)" : "", p.nslot, p.LZ, p.TH, p.n_items, smem_bytes);
   for (int nt = 0; nt < w.ntiles; ++nt) {
     IgemmParams q = p;
     q.wpack = w.w + (size_t)nt * w.tile_elems();

@@ -996,7 +996,7 @@ int ftb_test_conv3d(const float* x, int c1, const float* x2, int c2, const float
   ConvWeights cw;
   cw.w = packed; cw.ksize = ksize; cw.cin = cin_pad; cw.n = n_tile; cw.ntiles = ntiles;
   ConvEpilogue e;
-  e.bias = bias_p;
+  if (bias) e.bias = bias_p;
   float *mul_p = nullptr, *add_p = nullptr;
   const int pstride = n_tile * ntiles;
   if (g) FTB_CHECK(ntiles == 1, "norm needs a single N tile");

@@ -1,22 +1,23 @@
 import ctypes as C, os, sys, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from flowtrain_stochastic_interpolation_b200 import _lib
 dev = torch.device("cuda:0")
-def run(B, n, c1, cout):
+def run(B, n, c1, cout, bias=False):
     g = torch.Generator().manual_seed(0)
     x = torch.randn(B, c1, n, n, n, generator=g).to(dev)
     w = (torch.randn(cout, c1, 1, 1, 1, generator=g) * 0.05).to(dev)
-    bias = torch.randn(cout, generator=g).to(dev)
+    bv = torch.randn(cout, generator=g).to(dev) if bias else None
     out = torch.empty(B, cout, n, n, n, device=dev)
     best = 1e9
     for it in range(3):
         _lib.lib.ftb_profile_enable(1)
-        _lib.check(_lib.lib.ftb_test_conv3d(_lib.ptr(x), c1, None, 0, _lib.ptr(w), None, cout, 1, None, None, None, None, 0, _lib.ptr(out), B, n, n, n, 0, _lib.stream_ptr()))
+        _lib.check(_lib.lib.ftb_test_conv3d(_lib.ptr(x), c1, None, 0, _lib.ptr(w), _lib.ptr(bv), cout, 1, None, None, None, None, 0, _lib.ptr(out), B, n, n, n, 0, _lib.stream_ptr()))
         torch.cuda.synchronize()
         nk = 2
         fl, by, ms, ln = (C.c_double * nk)(), (C.c_double * nk)(), (C.c_double * nk)(), (C.c_int * nk)()
         _lib.check(_lib.lib.ftb_profile_collect(fl, by, ms, ln, nk)); _lib.lib.ftb_profile_enable(0)
         best = min(best, ms[0] + ms[1])
     byts = B * n ** 3 * (c1 * ((cout + 127) // 128) + cout) * 2.0
-    print(f"B{B} {c1}->{cout} k1 @{n}^3: {best*1e3:8.1f} us  {byts/best/1e6:7.1f} GB/s (real traffic)", flush=True)
-run(8, 64, 48, 128); run(64, 32, 48, 128); run(512, 16, 48, 128); run(8, 64, 48, 48); run(8, 64, 128, 48); run(8,64,48,256); run(8, 64, 96, 48)
+    print(f"B{B} {c1}->{cout} k1 @{n}^3 bias={bias}: {best*1e3:8.1f} us  {byts/best/1e6:7.1f} GB/s (real traffic) "
+          f"[nostore={os.environ.get('FTB_DBG_NOSTORE')}, nold={os.environ.get('FTB_DBG_NOLD')}]", flush=True)
+run(8, 64, 48, 128); run(8, 64, 48, 128, True); run(8, 64, 48, 48)
