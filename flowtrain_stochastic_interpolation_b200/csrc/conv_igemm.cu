@@ -50,7 +50,8 @@ enum : int { F_SILU = 1, F_QSOFTMAX = 2, F_NOMMA = 4, F_PLAIN = 8 };
 
 struct IgemmParams {
   int B, D, H, W;
-  int K, pad, taps;            // taps = K*K (kh, kw) positions; the K depth taps are stacked along N
+  int K, pad, taps;            // taps = K*Kw (kh, kw) positions; the K depth taps are stacked along N
+  int Kw, padw;                // extent along W (= K, or 1 when the W taps were unfolded into channels)
   int cg0, cg1, KS;
   // Input channels are processed in chunks ("passes"): a ring slot holds ONE plane of ONE chunk (<= 64
   // channels), so the plane window stays small for any Cin.  ncc == 1: the window slides along D and
@@ -522,7 +523,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
               uint8_t* dst = s_planes + (size_t)pslot * p.slot_stride;
               const int dz = c.d0 - p.pad + q;
               if (p.flat) tma_load_3d(dst, tm, &plane_full[pslot], 0, dz * 128, cgc);
-              else tma_load_4d(dst, tm, &plane_full[pslot], (c.w0 - p.pad) * 8, c.h0 - p.pad, dz, cgc);
+              else tma_load_4d(dst, tm, &plane_full[pslot], (c.w0 - p.padw) * 8, c.h0 - p.pad, dz, cgc);
               if (++pslot == (uint32_t)p.nslot) { pslot = 0; pphase ^= 1; }
             }
             if (!p.w_resident || !w_loaded) {
@@ -656,7 +657,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
             const int nks = p.cc_ks[cc];
             int t = 0;
             for (int kh = 0; kh < p.K; ++kh)
-              for (int kw = 0; kw < p.K; ++kw, ++t) {
+              for (int kw = 0; kw < p.Kw; ++kw, ++t) {
                 const uint32_t aoff = kh * rowp_enc + kw;
                 uint32_t wslot_i;
                 if (stream_w) {
@@ -906,7 +907,9 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
 
   IgemmParams p{};
   p.B = a0.B; p.D = a0.D; p.H = a0.H; p.W = a0.W;
-  p.K = w.ksize; p.pad = (w.ksize - 1) / 2; p.taps = w.ksize * w.ksize;
+  p.K = w.ksize; p.pad = (w.ksize - 1) / 2;
+  p.Kw = w.kw(); p.padw = (p.Kw - 1) / 2; p.taps = p.K * p.Kw;
+  FTB_CHECK(p.Kw == p.K || p.Kw == 1, "conv: ksize_w must be ksize or 1");
   p.cg0 = s0.cg; p.cg1 = s1.t ? s1.cg : 0;
   p.KS = (p.cg0 + p.cg1) / 2;
   FTB_CHECK(p.KS <= kMaxKS, "conv: more than 512 input channels");
@@ -914,7 +917,7 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   p.s1_cgtot = s1.t ? s1.t->cg() : 0; p.s1_cgoff = s1.cgoff;
   p.N = w.n;
   p.smax = 256 / p.N < 1 ? 1 : 256 / p.N;
-  p.BW = 8 + 2 * p.pad;
+  p.BW = 8 + 2 * p.padw;
   // 1x1x1 convs have no halo, so their tiles are free-form: 128 consecutive voxels give 2 KB
   // contiguous runs per channel group in HBM (16 x 8 bricks: 128 B runs) for loads and stores
   p.flat = (p.K == 1 && getenv("FTB_NOFLAT") == nullptr) ? 1 : 0;
@@ -927,16 +930,18 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   // divisor of its group count, <= 8 groups = 64 channels for K > 1, whose weight chunk of one
   // (kh,kw) position stays <= 56 KB).  One source of <= 8 groups is a single chunk: the classic
   // sliding window.
-  const int cg_cap = p.K == 1 ? 16 : 8;
+  int cg_cap = p.K == 1 ? 16 : 8;
   const uint32_t kWChunkMax = 56 * 1024;
   auto pick = [&](int cg) {
     for (int d = cg < cg_cap ? cg : cg_cap; d > 2; d -= 2)
       if (cg % d == 0 && (uint32_t)(d / 2) * p.kstep_bytes <= kWChunkMax) return d;
     return 2;
   };
-  p.ncc = 0;
-  int max_ccg = 0;
-  {
+  int max_ccg = 0, nchunks = 0;
+  size_t all_w = 0;
+  auto build_chunks = [&]() -> int {
+    p.ncc = 0;
+    max_ccg = 0;
     const int cgs[2] = {p.cg0, p.cg1};
     int ks0 = 0;
     for (int sidx = 0; sidx < 2; ++sidx) {
@@ -950,13 +955,14 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
       }
       if (ccg > max_ccg) max_ccg = ccg;
     }
-  }
-  p.wchunk_bytes = (uint32_t)(max_ccg / 2) * p.kstep_bytes;
-  const int nchunks = p.taps * p.ncc;
+    p.wchunk_bytes = (uint32_t)(max_ccg / 2) * p.kstep_bytes;
+    nchunks = p.taps * p.ncc;
+    all_w = (size_t)nchunks * p.wchunk_bytes;   // resident layout: one ring-sized slot per (chunk, tap)
+    return 0;
+  };
   const int sms = num_sms();
   const uint32_t bar_bytes =
       (2 * kMaxSlots + 2 * kMaxWSlots + 4) * 8 + 16 + kMaxIss * kMaxEnt * 16 + 2 * 3 * kMaxN * 4;
-  const size_t all_w = (size_t)nchunks * p.wchunk_bytes;   // resident layout: one ring-sized slot per (chunk, tap)
 
   // ---- tile height, planes per group (NZ) and ring sizing against the 227 KB shared-memory
   // budget.  The tile is 8 (W) x TH (H) voxels in the 128-row MMA; TH = 16 unless a plane window
@@ -976,7 +982,13 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   }
   while (nz_cap > 1 && (nz_cap * p.K > kMaxEnt / 2 || nz_cap + 2 * p.pad > 32)) --nz_cap;
   FTB_CHECK(nz_cap >= 1, "conv: N tile too wide for a double-buffered accumulator");
-  for (int th = (a0.H >= 16 || p.flat) ? 16 : a0.H; th >= 1 && !fits; th = th / 2) {   // first tile height that fits wins
+  // Smaller channel chunks are tried before a shorter tile: a wide kernel (K = 7: window of NZ + 6
+  // planes) only fits with 32- or 16-channel chunks, and a full-height tile keeps all 128 MMA rows busy.
+  const int th0 = (a0.H >= 16 || p.flat) ? 16 : a0.H;
+  for (int attempt = 0; attempt < 4 && !fits; ++attempt) {
+  if (attempt > 0 && attempt < 3) { if (cg_cap <= 2) continue; cg_cap = cg_cap > 4 ? 4 : 2; }
+  FTB_TRY(build_chunks());
+  for (int th = th0; th >= (attempt < 3 ? th0 : 1) && !fits; th = th / 2) {   // last attempt: trade tile rows for capacity
     p.TH = th;
     p.BH = p.TH + 2 * p.pad;
     p.nHt = p.flat ? 1 : cdiv(a0.H, p.TH);
@@ -1024,6 +1036,7 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
       }
     }
     if (th == 1) break;
+  }
   }
   FTB_CHECK(fits, "conv: one plane window + weights exceed shared memory (Cin too large)");
   w_region = (size_t)p.wslot * p.wchunk_bytes;
@@ -1116,7 +1129,7 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
       const double cin = w.cin_real > 0 ? w.cin_real : w.cin;
       const double cout_all = w.cout_real > 0 ? w.cout_real : (double)w.n * w.ntiles;
       const double cout = cout_all / w.ntiles;
-      const double flops = 2.0 * vox * cin * cout * p.taps * p.K;
+      const double flops = 2.0 * vox * cin * cout * p.K * p.K * (w.ksize_w == 1 && p.K > 1 ? 1 : p.K);   // cin_real of an unfolded conv already counts the W taps
       const double bytes = vox * (cin + cout) * 2.0;  // read input once, write output once (bf16)
       prof = prof_begin(st, flops, bytes, w.ksize > 1 ? 0 : 1);
     }

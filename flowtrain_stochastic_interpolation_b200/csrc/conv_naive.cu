@@ -12,7 +12,7 @@ namespace ftb {
 namespace {
 
 struct NaiveParams {
-  int B, D, H, W, K, pad;
+  int B, D, H, W, K, pad, Kw, padw;
   int cg0, cg1, s0_cgtot, s0_cgoff, s1_cgtot, s1_cgoff;
   int N, KS;
   const bf16 *src0, *src1, *wpack;
@@ -40,8 +40,8 @@ __device__ void naive_chunk(const NaiveParams& p, int b, int d, int h, int w, in
   int t = 0;
   for (int kd = 0; kd < p.K; ++kd)
     for (int kh = 0; kh < p.K; ++kh)
-      for (int kw = 0; kw < p.K; ++kw, ++t) {
-        const int dz = d + kd - p.pad, hy = h + kh - p.pad, wx = w + kw - p.pad;
+      for (int kw = 0; kw < p.Kw; ++kw, ++t) {
+        const int dz = d + kd - p.pad, hy = h + kh - p.pad, wx = w + kw - p.padw;
         if (dz < 0 || dz >= p.D || hy < 0 || hy >= p.H || wx < 0 || wx >= p.W) continue;
         const size_t vox = ((size_t)dz * p.H + hy) * p.W + wx;
         for (int ks = 0; ks < p.KS; ++ks) {
@@ -58,7 +58,7 @@ __device__ void naive_chunk(const NaiveParams& p, int b, int d, int h, int w, in
             for (int j = 0; j < 8; ++j) a[half * 8 + j] = f[j];
           }
           // packed tile [N/8][2][8][8] for (kh, kw, ks, j = K-1-kd)
-          const bf16* wt = wb + ((((size_t)(kh * p.K + kw) * p.KS + ks) * p.K + (p.K - 1 - kd)) * p.N) * 16;
+          const bf16* wt = wb + ((((size_t)(kh * p.Kw + kw) * p.KS + ks) * p.K + (p.K - 1 - kd)) * p.N) * 16;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int n = c0 + j;
@@ -160,9 +160,10 @@ __global__ void conv_naive_kernel(const NaiveParams p) {
 // fp32 [Cout][Cin][kd][kh][kw] -> bf16 [ntile][kh][kw][ks][j = K-1-kd][n/8][2][8][8]
 __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int cin_real, int K,
                                     int cin_pad, int n, int ntiles, const float* __restrict__ in_scale,
-                                    bf16* __restrict__ dst) {
+                                    bf16* __restrict__ dst, int unfold_w) {
   const int taps = K * K * K;
-  const size_t total = (size_t)ntiles * taps * cin_pad * n;
+  const int Kw = unfold_w ? 1 : K;
+  const size_t total = (size_t)ntiles * K * K * Kw * cin_pad * n;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
     size_t r = i;
@@ -172,13 +173,20 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int c
     const int ng = r % (n / 8); r /= (n / 8);
     const int j = r % K; r /= K;
     const int ks = r % (cin_pad / 16); r /= (cin_pad / 16);
-    const int khw = r % (K * K); r /= (K * K);
+    const int khw = r % (K * Kw); r /= (K * Kw);
     const int nt = (int)r;
-    const int t = (K - 1 - j) * K * K + khw;
     const int co = nt * n + ng * 8 + n8;
-    const int ci = ks * 16 + kc * 8 + k8;
+    int ci = ks * 16 + kc * 8 + k8;
+    int t = (K - 1 - j) * K * K + khw;
+    bool ok = co < cout && ci < cin_real;
+    if (unfold_w) {   // K index kw*cin_real + ci, khw = kh
+      const int kw = ci / cin_real;
+      ci -= kw * cin_real;
+      ok = co < cout && kw < K;
+      t = (K - 1 - j) * K * K + khw * K + kw;
+    }
     float v = 0.f;
-    if (co < cout && ci < cin_real) {
+    if (ok) {
       v = w[((size_t)co * cin_real + ci) * taps + t];
       if (in_scale) v *= in_scale[ci];
     }
@@ -189,13 +197,14 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int c
 }  // namespace
 
 int pack_conv_weights(const float* w, int cout, int cin_real, int ksize, int cin_pad, int ntile_n,
-                      int ntiles, const float* in_scale, bf16* dst, cudaStream_t st) {
+                      int ntiles, const float* in_scale, bf16* dst, cudaStream_t st, bool unfold_w) {
   FTB_CHECK(cin_pad % 16 == 0 && ntile_n % 16 == 0, "pack: padded extents must be multiples of 16");
-  FTB_CHECK(ntile_n * ntiles >= cout && cin_pad >= cin_real, "pack: tile does not cover the weight");
-  const int taps = ksize * ksize * ksize;
+  FTB_CHECK(ntile_n * ntiles >= cout && cin_pad >= (unfold_w ? ksize : 1) * cin_real, "pack: tile does not cover the weight");
+  const int taps = ksize * ksize * (unfold_w ? 1 : ksize);
   const size_t total = (size_t)ntiles * taps * cin_pad * ntile_n;
   const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  pack_weights_kernel<<<blocks, 256, 0, st>>>(w, cout, cin_real, ksize, cin_pad, ntile_n, ntiles, in_scale, dst);
+  pack_weights_kernel<<<blocks, 256, 0, st>>>(w, cout, cin_real, ksize, cin_pad, ntile_n, ntiles, in_scale, dst,
+                                              unfold_w ? 1 : 0);
   FTB_LAUNCH_OK();
   return 0;
 }
@@ -206,6 +215,7 @@ int conv_naive(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   FTB_CHECK((s0.cg + s1.cg) * 8 == w.cin, "conv_naive: weight K extent does not match the sources");
   NaiveParams p{};
   p.B = a0.B; p.D = a0.D; p.H = a0.H; p.W = a0.W; p.K = w.ksize; p.pad = (w.ksize - 1) / 2;
+  p.Kw = w.kw(); p.padw = (p.Kw - 1) / 2;
   p.cg0 = s0.cg; p.cg1 = s1.t ? s1.cg : 0;
   p.s0_cgtot = a0.cg(); p.s0_cgoff = s0.cgoff;
   p.s1_cgtot = s1.t ? s1.t->cg() : 0; p.s1_cgoff = s1.cgoff;

@@ -35,6 +35,29 @@ __global__ void pack_kernel(const float* __restrict__ x, int B, int C, size_t vo
   }
 }
 
+__global__ void pack_unfold_w_kernel(const float* __restrict__ x, int B, int C, int D, int H, int W, int K,
+                                     int CG, bf16* __restrict__ out) {
+  const size_t vox = (size_t)D * H * W;
+  const size_t total = (size_t)B * CG * vox;
+  const int pad = K / 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t v = i % vox;
+    const int w = (int)(v % W);
+    const int cg = (int)((i / vox) % CG);
+    const int b = (int)(i / (vox * CG));
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int cc = cg * 8 + j;
+      const int kw = cc / C, c = cc - kw * C;
+      const int ws = w + kw - pad;
+      f[j] = (kw < K && ws >= 0 && ws < W) ? __ldg(x + ((size_t)b * C + c) * vox + v + (kw - pad)) : 0.f;
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = pack_bf16x8(f);
+  }
+}
+
 __global__ void unpack_kernel(const bf16* __restrict__ in, int B, int cgtot, int cgoff, int C,
                               size_t vox, float* __restrict__ out) {
   const int CG = (C + 7) / 8;
@@ -379,6 +402,14 @@ int pack_ncdhw_to_blocked(const float* x, int B, int C, int D, int H, int W, Act
             "pack: output activation shape");
   const size_t vox = (size_t)D * H * W;
   pack_kernel<<<grid_for((size_t)B * out.cg() * vox, 256), 256, 0, st>>>(x, B, C, vox, out.cg(), out.p);
+  FTB_LAUNCH_OK();
+  return 0;
+}
+int pack_unfold_w(const float* x, int B, int C, int D, int H, int W, int K, Act& out, cudaStream_t st) {
+  FTB_CHECK(out.B == B && out.D == D && out.H == H && out.W == W && out.C >= K * C && out.C % 16 == 0,
+            "pack_unfold_w: output activation shape");
+  const size_t vox = (size_t)D * H * W;
+  pack_unfold_w_kernel<<<grid_for((size_t)B * out.cg() * vox, 256), 256, 0, st>>>(x, B, C, D, H, W, K, out.cg(), out.p);
   FTB_LAUNCH_OK();
   return 0;
 }

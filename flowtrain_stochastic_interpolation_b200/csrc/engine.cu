@@ -108,6 +108,7 @@ struct ConvLayer {
   std::string wname, bname;  // bname empty = no bias
   int cout = 0, cin = 0, k = 1;
   int cin_pad = 0, n_tile = 0, ntiles = 1;
+  bool unfold_w = false;     // stem convs: W taps unfolded into the channels (K extent k*cin instead of k x pad16(cin))
   std::string in_scale;      // name of a gain vector folded into the input channels ("" = none)
   float in_scale_mul = 1.f;
   bf16* packed = nullptr;
@@ -186,6 +187,10 @@ void add_conv(ftb_unet* U, const std::string& prefix, int cout, int cin, int k, 
   c.bname = bias ? prefix + ".bias" : "";
   c.cout = cout; c.cin = cin; c.k = k;
   c.cin_pad = round_up(cin, 16);
+  if (k >= 5 && k * cin <= 128 && round_up(k * cin, 16) < k * c.cin_pad && getenv("FTB_NO_UNFOLD") == nullptr) {
+    c.unfold_w = true;
+    c.cin_pad = round_up(k * cin, 16);
+  }
   if (n_tile == 0) n_tile = round_up(cout, 16);
   c.n_tile = n_tile;
   c.ntiles = cdiv(cout, n_tile);
@@ -355,7 +360,7 @@ int ensure_device(ftb_unet* U) {
   for (Param& p : U->params) FTB_TRY(dev_alloc(U, &p.dev, (size_t)p.numel));
   for (auto& kv : U->convs) {
     ConvLayer& cl = kv.second;
-    const size_t elems = (size_t)cl.ntiles * cl.k * cl.k * cl.k * cl.cin_pad * cl.n_tile;
+    const size_t elems = (size_t)cl.ntiles * cl.k * cl.k * (cl.unfold_w ? 1 : cl.k) * cl.cin_pad * cl.n_tile;
     FTB_TRY(dev_alloc(U, &cl.packed, elems));
     FTB_TRY(dev_alloc(U, &cl.bias, (size_t)cl.ntiles * cl.n_tile));
     FTB_CUDA(cudaMemset(cl.bias, 0, (size_t)cl.ntiles * cl.n_tile * sizeof(float)));
@@ -420,7 +425,7 @@ int finalize(ftb_unet* U, cudaStream_t st) {
       in_scale = cl.scale_tmp;
     }
     FTB_TRY(pack_conv_weights(w, cl.cout, cl.cin, cl.k, cl.cin_pad, cl.n_tile, cl.ntiles, in_scale,
-                              cl.packed, st));
+                              cl.packed, st, cl.unfold_w));
     if (!cl.bname.empty())
       FTB_CUDA(cudaMemcpyAsync(cl.bias, U->params[U->pindex[cl.bname]].dev, cl.cout * sizeof(float),
                                cudaMemcpyDeviceToDevice, st));
@@ -467,7 +472,8 @@ struct Fwd {
     const ConvLayer& cl = U->convs.at(name);
     ConvWeights w;
     w.w = cl.packed; w.ksize = cl.k; w.cin = cl.cin_pad; w.n = cl.n_tile; w.ntiles = cl.ntiles;
-    w.cin_real = cl.cin; w.cout_real = cl.cout;
+    w.ksize_w = cl.unfold_w ? 1 : 0;
+    w.cin_real = cl.unfold_w ? cl.k * cl.cin : cl.cin; w.cout_real = cl.cout;
     if (!cl.bname.empty()) e.bias = cl.bias;
     if (dry || skip) return 0;
     U->launches += cl.ntiles;
@@ -563,6 +569,17 @@ struct Fwd {
     return 0;
   }
 
+  // NCDHW fp32 network input -> blocked bf16 operand of the stem conv `name` (W-unfolded when the
+  // stem was planned that way)
+  int pack_input(const std::string& name, const float* x, int batch, int X, int Y, int Z, Act* out) {
+    const ConvLayer& cl = U->convs.at(name);
+    *out = act(cl.unfold_w ? cl.k * cl.cin : cl.cin, X, Y, Z, batch);
+    if (dry || skip) return 0;
+    U->launches += 1;
+    if (cl.unfold_w) return pack_unfold_w(x, batch, cl.cin, X, Y, Z, cl.k, *out, st);
+    return pack_ncdhw_to_blocked(x, batch, cl.cin, X, Y, Z, *out, st);
+  }
+
   // EmbedATb.forward (unet_attn_3d_cond_v3.py:131-139) on the opened ATb; depends on ATb only, so a
   // sampler computes it once per trajectory (reuse_atb) instead of once per evaluation.
   int embed_atb(const std::string& p, const Act& opened, int C, int D, int H, int W, Act* out) {
@@ -625,11 +642,8 @@ struct Fwd {
     std::vector<Act> emb_down(n), emb_up(n);
     if (cond) {
       skip = reuse_atb;
-      Act ain = act(c.data_channels, X, Y, Z, atb_B);
-      if (!dry && !skip) {
-        FTB_TRY(pack_ncdhw_to_blocked(atb, atb_B, c.data_channels, X, Y, Z, ain, st));
-        U->launches += 1;
-      }
+      Act ain;
+      FTB_TRY(pack_input("init_conv_ATb", atb, atb_B, X, Y, Z, &ain));
       Act opened = act(c.data_channels, X, Y, Z, atb_B);
       FTB_TRY(conv("init_conv_ATb", ConvSrc{&ain, 0, ain.cg()}, ConvSrc{}, ConvEpilogue{}, opened));
       if (!skip) tap("init_conv_ATb", opened);
@@ -651,7 +665,9 @@ struct Fwd {
     float* temb = f32((size_t)B * U->time_dim);
     float* temb_silu = f32((size_t)B * U->time_dim);
     film = f32((size_t)B * U->film_rows);
-    Act xin = act(c.data_channels, X, Y, Z);
+    const std::string init_name = cond ? "init_conv_x" : "init_conv";
+    Act xin;
+    FTB_TRY(pack_input(init_name, x, B, X, Y, Z, &xin));
     if (!dry) {
       TimeMlpParams tp{pdev("time_mlp.0.freqs"), pdev("time_mlp.0.phases"), pdev("time_mlp.1.weight"),
                        pdev("time_mlp.1.bias"), pdev("time_mlp.3.weight"), pdev("time_mlp.3.bias"),
@@ -660,11 +676,9 @@ struct Fwd {
       FilmTable ft{U->d_film_w, U->d_film_b, U->d_film_gs, U->d_film_off, (int)U->film_blocks.size(),
                    U->film_rows, U->time_dim};
       FTB_TRY(film_mlps(ft, temb_silu, B, film, st));
-      FTB_TRY(pack_ncdhw_to_blocked(x, B, c.data_channels, X, Y, Z, xin, st));
-      U->launches += 3;
+      U->launches += 2;
     }
     Act r = act(c.dim, X, Y, Z);
-    const std::string init_name = cond ? "init_conv_x" : "init_conv";
     FTB_TRY(conv(init_name, ConvSrc{&xin, 0, xin.cg()}, ConvSrc{}, ConvEpilogue{}, r));
     tap(init_name, r);
     Act cur = r;
@@ -972,9 +986,13 @@ int ftb_test_conv3d(const float* x, int c1, const float* x2, int c2, const float
     a.p = S.get<bf16>(a.elems());
     return a;
   };
-  Act a0 = mk(c1), a1, ar, ao = mk(cout);
+  // like the engine, a wide-kernel / small-Cin conv runs W-unfolded (impl 2 forces the cubic kernel)
+  const bool unfold = !x2 && ksize >= 5 && ksize * c1 <= 128 && round_up(ksize * c1, 16) < ksize * round_up(c1, 16) &&
+                      impl != 2 && getenv("FTB_NO_UNFOLD") == nullptr;
+  Act a0 = mk(unfold ? ksize * c1 : c1), a1, ar, ao = mk(cout);
   FTB_CHECK(a0.p && ao.p, "scratch allocation failed");
-  FTB_TRY(pack_ncdhw_to_blocked(x, B, c1, X, Y, Z, a0, st));
+  if (unfold) FTB_TRY(pack_unfold_w(x, B, c1, X, Y, Z, ksize, a0, st));
+  else FTB_TRY(pack_ncdhw_to_blocked(x, B, c1, X, Y, Z, a0, st));
   if (x2) {
     FTB_CHECK(c1 % 16 == 0, "concat test needs c1 % 16 == 0");
     a1 = mk(c2);
@@ -985,16 +1003,17 @@ int ftb_test_conv3d(const float* x, int c1, const float* x2, int c2, const float
   const int cin_pad = a0.C + (x2 ? a1.C : 0);
   const int n_tile = round_up(cout, 16) > 256 ? 128 : round_up(cout, 16);
   const int ntiles = cdiv(cout, n_tile);
-  const int taps = ksize * ksize * ksize;
+  const int taps = ksize * ksize * (unfold ? 1 : ksize);
   bf16* packed = S.get<bf16>((size_t)ntiles * taps * cin_pad * n_tile);
   float* bias_p = S.get<float>((size_t)ntiles * n_tile);
   float* gs = S.get<float>((size_t)n_tile);
   FTB_CHECK(packed && bias_p && gs, "scratch allocation failed");
-  FTB_TRY(pack_conv_weights(w, cout, cin, ksize, cin_pad, n_tile, ntiles, nullptr, packed, st));
+  FTB_TRY(pack_conv_weights(w, cout, cin, ksize, cin_pad, n_tile, ntiles, nullptr, packed, st, unfold));
   FTB_CUDA(cudaMemsetAsync(bias_p, 0, (size_t)ntiles * n_tile * sizeof(float), st));
   if (bias) FTB_CUDA(cudaMemcpyAsync(bias_p, bias, cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
   ConvWeights cw;
   cw.w = packed; cw.ksize = ksize; cw.cin = cin_pad; cw.n = n_tile; cw.ntiles = ntiles;
+  cw.ksize_w = unfold ? 1 : 0;
   ConvEpilogue e;
   if (bias) e.bias = bias_p;
   float *mul_p = nullptr, *add_p = nullptr;
@@ -1022,7 +1041,7 @@ int ftb_test_conv3d(const float* x, int c1, const float* x2, int c2, const float
   }
   ConvSrc s0{&a0, 0, a0.cg()}, s1{};
   if (x2) s1 = ConvSrc{&a1, 0, a1.cg()};
-  if (impl == 1) FTB_TRY(conv_naive(s0, s1, cw, e, ao, 0, st));
+  if (impl == 1) FTB_TRY(conv_naive(s0, s1, cw, e, ao, 0, st));   // impl 2: tcgen05 kernel, cubic (no W-unfold)
   else FTB_TRY(conv_igemm(s0, s1, cw, e, ao, 0, st));
   FTB_TRY(unpack_blocked_to_ncdhw(ao, 0, cout, out, st));
   FTB_CUDA(cudaStreamSynchronize(st));

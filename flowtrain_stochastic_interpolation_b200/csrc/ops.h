@@ -12,13 +12,17 @@ typedef __nv_bfloat16 bf16;
 // SBO = 256 B) whose K row blocks are the depth taps in descending kd (depth-tap stacking).
 struct ConvWeights {
   const bf16* w = nullptr;
-  int ksize = 1;        // 1, 3, 5, 7 (cubic, stride 1, "same" zero padding)
+  int ksize = 1;        // 1, 3, 5, 7 (stride 1, "same" zero padding): extent along D and H
+  int ksize_w = 0;      // extent along W; 0 = cubic.  1 with ksize > 1: the W taps were unfolded into
+                        // the channels (c' = kw*Cin + ci, pack_unfold_w), so K waste of a small-Cin stem
+                        // (18 -> 32 per tap) becomes 7*18 = 126 -> 128 per (kd, kh)
+  int kw() const { return ksize_w > 0 ? ksize_w : ksize; }
   int cin = 0;          // padded K extent (multiple of 16) = channels of src0 (+ src1)
   int n = 0;            // output channels of one N tile (multiple of 16, <= 256)
   int ntiles = 1;       // number of N tiles packed back to back
   long long batch_stride = 0;  // elements between per-sample weight sets (0 = shared)
   int cin_real = 0, cout_real = 0;  // unpadded channel counts (algorithmic-FLOP accounting only)
-  size_t tile_elems() const { return (size_t)ksize * ksize * ksize * cin * n; }
+  size_t tile_elems() const { return (size_t)ksize * ksize * kw() * cin * n; }
 };
 
 // y = ((acc * rs + bias) * rinv) * mul[b][c] + add[b][c], then SiLU, then + resid.
@@ -70,11 +74,14 @@ int make_voxel_tmap(CUtensorMap* tm, const Act& a, int box_vox, int box_cg);
 // fp32 [Cout][Cin][k^3] -> packed bf16 tiles.  cin_map: K index -> source Cin index is
 // identity for k < cin_real, zero beyond.  in_scale (optional, [cin_real]) folds a per-input-
 // channel factor (pre-norm gain * sqrt(C)) into the weights.
+// unfold_w: pack for a W-unfolded input: K index c' = kw*cin_real + ci, taps (kd, kh) only.
 int pack_conv_weights(const float* w, int cout, int cin_real, int ksize, int cin_pad, int ntile_n,
-                      int ntiles, const float* in_scale, bf16* dst, cudaStream_t st);
+                      int ntiles, const float* in_scale, bf16* dst, cudaStream_t st, bool unfold_w = false);
 
 // ---------------------------------------------------------------- layout / resample
 int pack_ncdhw_to_blocked(const float* x, int B, int C, int D, int H, int W, Act& out, cudaStream_t st);
+// W-unfolded pack: out channel kw*C + c of voxel (d,h,w) = x[c][d][h][w + kw - K/2] (zero outside)
+int pack_unfold_w(const float* x, int B, int C, int D, int H, int W, int K, Act& out, cudaStream_t st);
 int unpack_blocked_to_ncdhw(const Act& in, int cgoff, int C, float* out, cudaStream_t st);
 int trilinear_resample(const Act& in, Act& out, cudaStream_t st);  // align_corners=True
 // out[:, :C] = x*mul[:C]+add[:C]; out[:, C:] = atb*mul[C:]+add[C:], film row = [mul(2C) | add(2C)] per sample
