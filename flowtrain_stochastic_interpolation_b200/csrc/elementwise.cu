@@ -35,26 +35,40 @@ __global__ void pack_kernel(const float* __restrict__ x, int B, int C, size_t vo
   }
 }
 
-__global__ void pack_unfold_w_kernel(const float* __restrict__ x, int B, int C, int D, int H, int W, int K,
-                                     int CG, bf16* __restrict__ out) {
+// One block per (b, d, h) row: the C fp32 rows are staged in shared memory with a zero halo, then
+// every (channel group, w) output reads its 8 (kw, c) taps from there (coalesced both ways).
+__global__ void __launch_bounds__(256)
+pack_unfold_w_kernel(const float* __restrict__ x, int C, int D, int H, int W, int K, int CG,
+                     bf16* __restrict__ out) {
+  extern __shared__ float s_row[];                  // [C][W + K - 1]
+  __shared__ unsigned char s_kw[256], s_c[256];     // per unfolded channel: tap and source channel
+  const int pad = K / 2, RW = W + K - 1;
+  int blk = blockIdx.x;
+  const int h = blk % H; blk /= H;
+  const int d = blk % D;
+  const int b = blk / D;
   const size_t vox = (size_t)D * H * W;
-  const size_t total = (size_t)B * CG * vox;
-  const int pad = K / 2;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const size_t v = i % vox;
-    const int w = (int)(v % W);
-    const int cg = (int)((i / vox) % CG);
-    const int b = (int)(i / (vox * CG));
+  const size_t rowoff = ((size_t)d * H + h) * W;
+  for (int i = threadIdx.x; i < CG * 8; i += blockDim.x) {
+    const int kw = i / C;
+    s_kw[i] = (unsigned char)(kw < K ? kw : 255);
+    s_c[i] = (unsigned char)(i - kw * C);
+  }
+  for (int i = threadIdx.x; i < C * RW; i += blockDim.x) {
+    const int c = i / RW, wr = i - c * RW, w = wr - pad;
+    s_row[i] = (w >= 0 && w < W) ? __ldg(x + ((size_t)b * C + c) * vox + rowoff + w) : 0.f;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < CG * W; o += blockDim.x) {
+    const int cg = o / W, w = o - cg * W;
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int cc = cg * 8 + j;
-      const int kw = cc / C, c = cc - kw * C;
-      const int ws = w + kw - pad;
-      f[j] = (kw < K && ws >= 0 && ws < W) ? __ldg(x + ((size_t)b * C + c) * vox + v + (kw - pad)) : 0.f;
+      const int kw = s_kw[cc];
+      f[j] = kw == 255 ? 0.f : s_row[s_c[cc] * RW + w + kw];
     }
-    *reinterpret_cast<uint4*>(out + i * 8) = pack_bf16x8(f);
+    *reinterpret_cast<uint4*>(out + ((((size_t)b * CG + cg) * vox) + rowoff + w) * 8) = pack_bf16x8(f);
   }
 }
 
@@ -85,8 +99,7 @@ struct Lerp {
   int i0, i1;
   float l0, l1;
 };
-__device__ __forceinline__ Lerp lerp_idx(int o, int in, int out) {
-  const float scale = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+__device__ __forceinline__ Lerp lerp_idx(int o, int in, float scale) {
   const float src = scale * (float)o;
   Lerp r;
   r.i0 = (int)src;
@@ -101,19 +114,19 @@ __device__ __forceinline__ Lerp lerp_idx(int o, int in, int out) {
 constexpr int kTriRH = 4;
 __global__ void __launch_bounds__(256)
 trilinear_kernel(const bf16* __restrict__ in, int CG, int Di, int Hi, int Wi, int Do, int Ho, int Wo,
-                 int hgroups, bf16* __restrict__ out) {
+                 int hgroups, float sd, float sh, float sw, bf16* __restrict__ out) {
   int blk = blockIdx.x;
   const int hg = blk % hgroups; blk /= hgroups;
   const int d = blk % Do;
   const size_t bc = blk / Do;
-  const Lerp ld = lerp_idx(d, Di, Do);
+  const Lerp ld = lerp_idx(d, Di, sd);
   const bf16* base = in + bc * (size_t)Di * Hi * Wi * 8;
   bf16* obase = out + (bc * (size_t)Do + d) * Ho * Wo * 8;
   for (int idx = threadIdx.x; idx < kTriRH * Wo; idx += blockDim.x) {
     const int hr = idx / Wo, w = idx - hr * Wo;
     const int h = hg * kTriRH + hr;
     if (h >= Ho) break;
-    const Lerp lh = lerp_idx(h, Hi, Ho), lw = lerp_idx(w, Wi, Wo);
+    const Lerp lh = lerp_idx(h, Hi, sh), lw = lerp_idx(w, Wi, sw);
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -408,8 +421,10 @@ int pack_ncdhw_to_blocked(const float* x, int B, int C, int D, int H, int W, Act
 int pack_unfold_w(const float* x, int B, int C, int D, int H, int W, int K, Act& out, cudaStream_t st) {
   FTB_CHECK(out.B == B && out.D == D && out.H == H && out.W == W && out.C >= K * C && out.C % 16 == 0,
             "pack_unfold_w: output activation shape");
-  const size_t vox = (size_t)D * H * W;
-  pack_unfold_w_kernel<<<grid_for((size_t)B * out.cg() * vox, 256), 256, 0, st>>>(x, B, C, D, H, W, K, out.cg(), out.p);
+  FTB_CHECK(out.cg() * 8 <= 256 && C <= 255, "pack_unfold_w: at most 256 unfolded channels");
+  const size_t smem = (size_t)C * (W + K - 1) * sizeof(float);
+  FTB_CHECK(smem <= 40 * 1024, "pack_unfold_w: row too wide for shared memory");
+  pack_unfold_w_kernel<<<(unsigned)((size_t)B * D * H), 256, smem, st>>>(x, C, D, H, W, K, out.cg(), out.p);
   FTB_LAUNCH_OK();
   return 0;
 }
@@ -425,8 +440,11 @@ int trilinear_resample(const Act& in, Act& out, cudaStream_t st) {
   const long long blocks = (long long)out.B * out.cg() * out.D * hgroups;
   FTB_CHECK(blocks < (1ll << 31), "trilinear: grid too large");
   const int threads = kTriRH * out.W >= 256 ? 256 : round_up(kTriRH * out.W, 32);
+  // ATen's align_corners scale, computed once in fp32 exactly like area_pixel_compute_scale
+  auto scale = [](int i, int o) { return o > 1 ? (float)(i - 1) / (float)(o - 1) : 0.f; };
   trilinear_kernel<<<(unsigned)blocks, threads, 0, st>>>(in.p, in.cg(), in.D, in.H, in.W, out.D, out.H, out.W,
-                                                         hgroups, out.p);
+                                                         hgroups, scale(in.D, out.D), scale(in.H, out.H),
+                                                         scale(in.W, out.W), out.p);
   FTB_LAUNCH_OK();
   return 0;
 }
