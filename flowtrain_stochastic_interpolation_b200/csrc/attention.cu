@@ -286,11 +286,248 @@ ctx_tc_kernel(const __grid_constant__ CUtensorMap tm, const CtxParams p) {
   if (warp == 1) tmem_dealloc(tmem_base, 256);
 }
 
+// ------------------------------------------------------------------ fused k/v projection + context
+// LinearAttention without ever writing k and v (unet_attn_3d.py:311-331): per 128-voxel tile
+//   GEMM1 (tcgen05, K-major): [k | v] = x_tile . [Wk | Wv]^T      -> TMEM columns [0,256)
+//   exp pass (8 warps):       P = exp(k*rs - shift), V = v*rs      -> shared memory, MN-major, bf16
+//   GEMM2 (tcgen05, MN-major): ctx += P^T [V | 1]                  -> TMEM columns [256,400)
+// rs = 1/max(||x voxel||, 1e-12) is the fused pre-attention RMSNorm (its gain is folded into the
+// weights).  `shift` replaces the softmax max: softmax is invariant to a per-channel constant, and
+// shift[d] = 1.02 * ||W_k[d,:]||_2 >= |k[d,n]| (Cauchy-Schwarz, the normalised voxel has norm 1), so
+// the exponent is never positive and no pass over k is needed to find the true maximum; the combine
+// step treats `shift` like a (loose) max.  The engine only takes this path while shift <= 60, where
+// exp(k - shift) stays far from the fp32 underflow; otherwise it runs the exact 3-kernel path.
+//   warp 0: TMA producer | warp 1: MMA issuer | warps 2-9: exp pass (k columns: 2-5, v columns: 6-9)
+constexpr int kKvT = 128;
+constexpr int kKvThreads = 320;
+
+struct KvCtxParams {
+  int heads, dh, hd;
+  int cg;                        // channel groups of x (C/8)
+  int cgtot, cgoff;
+  long long vox;
+  int ntiles, nsplit;
+  int nx, npv;                   // x stages, P/V stages
+  uint32_t x_stage, off_w, off_pv, off_bar;
+  const bf16* wk;                // packed K-major B tiles [ks][16][2][8][8] of the k rows
+  const bf16* wv;
+  const float* ss;               // [B][vox] ||x||^2
+  const float* shift;            // [hd]
+  float* part;                   // [B][heads][nsplit][dh*dh + dh]
+};
+
+__global__ void __launch_bounds__(kKvThreads, 1)
+kvctx_kernel(const __grid_constant__ CUtensorMap tm, const KvCtxParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  constexpr uint32_t kBytesP = 16 * kKvT * 16;           // 128 channels of P
+  constexpr uint32_t kBytesV = 18 * kKvT * 16;           // 128 of V + 2 constant groups (ones column)
+  constexpr uint32_t kPv = kBytesP + kBytesV;
+  uint8_t* s_w = smem + p.off_w;
+  uint8_t* s_pv = smem + p.off_pv;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint64_t* x_full = bars;            // [4]
+  uint64_t* x_empty = bars + 4;       // [4]
+  uint64_t* pv_ready = bars + 8;      // [2]
+  uint64_t* pv_empty = bars + 10;     // [2]
+  uint64_t* d1_full = bars + 12;
+  uint64_t* d1_empty = bars + 13;
+  uint64_t* w_full = bars + 14;
+  uint64_t* done = bars + 15;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
+  float* s_shift = reinterpret_cast<float*>(tmem_ptr + 4);   // [128], pre-multiplied by log2(e)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x, b = blockIdx.y;
+  const int tiles_per = (p.ntiles + p.nsplit - 1) / p.nsplit;
+  const int t_lo = split * tiles_per, t_hi = min(p.ntiles, t_lo + tiles_per);
+  const int nt = max(0, t_hi - t_lo);
+  const int KS = p.cg / 2;
+  const uint32_t wbytes = (uint32_t)KS * 4096u;           // one of Wk / Wv
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&pv_ready[i], 256); mbar_init(&pv_empty[i], 1); }
+    mbar_init(d1_full, 1);
+    mbar_init(d1_empty, 256);
+    mbar_init(w_full, 1);
+    mbar_init(done, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tm);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  if (warp >= 2) {
+    const int t = threadIdx.x - 64;
+    if (t < 128) s_shift[t] = __ldg(p.shift + t) * 1.44269504088896340736f;
+    // constant channel groups 16,17 of every stage's V tile: channel 128 = 1, the rest 0
+    for (int i = t; i < p.npv * 2 * kKvT; i += 256) {
+      const int stg = i / (2 * kKvT), r = i % (2 * kKvT);
+      uint4 u = make_uint4(0u, 0u, 0u, 0u);
+      if (r < kKvT) u.x = 0x00003F80u;  // bf16 1.0 in element 0
+      *reinterpret_cast<uint4*>(s_pv + stg * kPv + kBytesP + 16 * kKvT * 16 + r * 16) = u;
+    }
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0 && nt > 0) {
+      mbar_expect_tx(w_full, 2 * wbytes);
+      bulk_load(s_w, p.wk, wbytes, w_full);
+      bulk_load(s_w + wbytes, p.wv, wbytes, w_full);
+      for (int i = 0; i < nt; ++i) {
+        const int s = i % p.nx;
+        mbar_wait(&x_empty[s], ((i / p.nx) & 1) ^ 1);
+        mbar_expect_tx(&x_full[s], (uint32_t)p.cg * kKvT * 16);
+        tma_load_3d(smem + s * p.x_stage, &tm, &x_full[s], 0, (t_lo + i) * kKvT, b * p.cgtot + p.cgoff);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one() && nt > 0) {
+      const uint32_t idesc1 = umma_idesc_bf16_f32(128, 128);                          // K-major A and B
+      const uint32_t idesc2 = umma_idesc_bf16_f32(128, 144) | (1u << 15) | (1u << 16); // MN-major A and B
+      const uint32_t a1_hi = (128u >> 4) | (1u << 14);                 // SBO: next 8 voxels
+      const uint32_t a1_lbo = ((uint32_t)(kKvT * 16) >> 4) << 16;      // LBO: next channel group
+      const uint32_t b1_hi = (256u >> 4) | (1u << 14);
+      const uint32_t b1_lo = (smem_u32(s_w) >> 4) | ((128u >> 4) << 16);
+      const uint32_t hi2 = ((kKvT * 16u) >> 4) | (1u << 14);           // SBO = channel-group pitch
+      const uint32_t lbo2 = (128u >> 4) << 16;                         // LBO = 8 voxels
+      auto gemm2 = [&](int j) {   // ctx += P^T [V | 1] of tile j
+        const int s = j % p.npv;
+        mbar_wait(&pv_ready[s], (j / p.npv) & 1);
+        tc_fence_after();
+        const uint32_t a0 = (smem_u32(s_pv + s * kPv) >> 4) | lbo2;
+        const uint32_t b0 = (smem_u32(s_pv + s * kPv + kBytesP) >> 4) | lbo2;
+#pragma unroll
+        for (int ks = 0; ks < kKvT / 16; ++ks)
+          umma_bf16_lohi(tmem_base + 256, a0 + ks * 16, hi2, b0 + ks * 16, hi2, idesc2, (j | ks) != 0);
+        umma_commit(&pv_empty[s]);
+      };
+      mbar_wait(w_full, 0);
+      for (int i = 0; i < nt; ++i) {
+        const int s = i % p.nx;
+        mbar_wait(&x_full[s], (i / p.nx) & 1);
+        mbar_wait(d1_empty, (i & 1) ^ 1);          // exp pass of tile i-1 has drained [k | v]
+        tc_fence_after();
+        const uint32_t a0 = (smem_u32(smem + s * p.x_stage) >> 4) | a1_lbo;
+        for (int ks = 0; ks < KS; ++ks) {
+          const uint32_t a = a0 + ks * ((2u * kKvT * 16u) >> 4);
+          umma_bf16_lohi(tmem_base, a, a1_hi, b1_lo + ks * 256, b1_hi, idesc1, ks != 0);
+          umma_bf16_lohi(tmem_base + 128, a, a1_hi, b1_lo + (wbytes >> 4) + ks * 256, b1_hi, idesc1, ks != 0);
+        }
+        umma_commit(&x_empty[s]);
+        umma_commit(d1_full);
+        if (i > 0) gemm2(i - 1);                   // overlaps the exp pass of tile i
+      }
+      gemm2(nt - 1);
+      umma_commit(done);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;                        // TMEM lane quadrant
+    const int half = (warp - 2) >> 2;              // 0: k columns -> P, 1: v columns -> V
+    const int row = q * 32 + lane;                 // voxel of the tile
+    const float log2e = 1.44269504088896340736f;
+    for (int i = 0; i < nt; ++i) {
+      const long long v = (long long)(t_lo + i) * kKvT + row;
+      const bool in = v < p.vox;
+      float rs = 0.f;
+      if (in) rs = 1.f / fmaxf(sqrtf(__ldg(p.ss + (size_t)b * p.vox + v)), 1e-12f);
+      const int s = i % p.npv;
+      mbar_wait(d1_full, i & 1);
+      mbar_wait(&pv_empty[s], ((i / p.npv) & 1) ^ 1);
+      tc_fence_after();
+      uint8_t* dst = s_pv + s * kPv + (half ? kBytesP : 0);
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + half * 128;
+      const float rs2 = rs * log2e;
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t r0[16], r1[16];
+        tmem_ld16(trow + c0, r0);
+        tmem_ld16(trow + c0 + 16, r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          float f[8];
+          const uint32_t* r = g8 < 2 ? r0 + g8 * 8 : r1 + (g8 - 2) * 8;
+          if (half == 0) {
+            const float4 m0 = *reinterpret_cast<const float4*>(s_shift + c0 + g8 * 8);
+            const float4 m1 = *reinterpret_cast<const float4*>(s_shift + c0 + g8 * 8 + 4);
+            f[0] = exp2f(fmaf(__uint_as_float(r[0]), rs2, -m0.x)); f[1] = exp2f(fmaf(__uint_as_float(r[1]), rs2, -m0.y));
+            f[2] = exp2f(fmaf(__uint_as_float(r[2]), rs2, -m0.z)); f[3] = exp2f(fmaf(__uint_as_float(r[3]), rs2, -m0.w));
+            f[4] = exp2f(fmaf(__uint_as_float(r[4]), rs2, -m1.x)); f[5] = exp2f(fmaf(__uint_as_float(r[5]), rs2, -m1.y));
+            f[6] = exp2f(fmaf(__uint_as_float(r[6]), rs2, -m1.z)); f[7] = exp2f(fmaf(__uint_as_float(r[7]), rs2, -m1.w));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[j]) * rs;
+          }
+          const uint4 u = in ? pack_bf16x8(f) : make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(dst + ((size_t)((c0 >> 3) + g8) * kKvT + row) * 16) = u;
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(d1_empty);
+      mbar_arrive(&pv_ready[s]);
+    }
+    // ---- TMEM -> partials (warps 2-5): row = (head, d); own head's columns + the denominator column
+    if (warp < 6) {
+      const int h = row / p.dh, d = row % p.dh;
+      float* out = p.part + (((size_t)b * p.heads + h) * p.nsplit + split) * (p.dh * p.dh + p.dh);
+      if (nt > 0) {
+        mbar_wait(done, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + 256;
+        for (int hh = (q * 32) / p.dh; hh < (q * 32 + 32) / p.dh; ++hh) {
+          for (int c0 = 0; c0 < p.dh; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(trow + hh * p.dh + c0, r);
+            tmem_ld_wait();
+            if (hh == h) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) out[d * p.dh + c0 + j] = __uint_as_float(r[j]);
+            }
+          }
+        }
+        uint32_t r[16];
+        tmem_ld16(trow + 128, r);
+        tmem_ld_wait();
+        out[p.dh * p.dh + d] = __uint_as_float(r[0]);
+      } else {
+        for (int e = 0; e < p.dh; ++e) out[d * p.dh + e] = 0.f;
+        out[p.dh * p.dh + d] = 0.f;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// shift[d] = 1.02 * ||w[d,:] * in_scale||_2 over the k rows of to_qkv (fp32 weights [3*hd][cin])
+__global__ void kshift_kernel(const float* __restrict__ w, const float* __restrict__ in_scale, int hd, int cin,
+                              float* __restrict__ shift) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= hd) return;
+  const float* wr = w + (size_t)(hd + d) * cin;
+  float s = 0.f;
+  for (int c = 0; c < cin; ++c) {
+    const float v = wr[c] * (in_scale ? in_scale[c] : 1.f);
+    s += v * v;
+  }
+  shift[d] = 1.02f * sqrtf(s) + 1e-6f;
+}
+
 // grid (heads, B): merge the split partials + memory kv -> ctx[h]; then this head's 32 columns
 // of the folded projection M_b[c][h*dh + d] = q_scale * sum_e W[c][h*dh+e] ctx[h][d][e]
 __global__ void __launch_bounds__(256)
-combine_head_kernel(const float* __restrict__ part, int nsplit, const float* __restrict__ kmax, int heads,
-                    int dh, const float* __restrict__ mem_kv, int n_mem, const float* __restrict__ w_out,
+combine_head_kernel(const float* __restrict__ part, int nsplit, const float* __restrict__ kmax,
+                    int kmax_bstride, int heads, int dh, const float* __restrict__ mem_kv, int n_mem, const float* __restrict__ w_out,
                     int C, float q_scale, bf16* __restrict__ wpack, float* __restrict__ ctx_dbg) {
   __shared__ float sctx[32 * 33];
   __shared__ float ssum[32];
@@ -308,7 +545,7 @@ combine_head_kernel(const float* __restrict__ part, int nsplit, const float* __r
     const int d = o / dh, e = o % dh;
     float c = sctx[d * 33 + e], s = ssum[d];
     // memory tokens (mem_kv[2][heads][dh][n_mem], :300,:320-323) join the softmax over n
-    const float m0 = kmax[(size_t)b * hd + h * dh + d];
+    const float m0 = kmax[(size_t)b * kmax_bstride + h * dh + d];
     const float* mk = mem_kv + ((size_t)h * dh + d) * n_mem;
     const float* mv = mem_kv + ((size_t)heads * dh + (size_t)h * dh + e) * n_mem;
     float m = m0;
@@ -510,12 +747,55 @@ int linattn_context_partial(const Act& qkv, int heads, int dh, int nsplit, const
   return 0;
 }
 
-int linattn_combine(const float* part, int nsplit, const float* kmax, int B, int heads, int dh,
+int linattn_kshift(const float* w_qkv, const float* in_scale, int hd, int cin, float* shift, cudaStream_t st) {
+  kshift_kernel<<<cdiv(hd, 128), 128, 0, st>>>(w_qkv, in_scale, hd, cin, shift);
+  FTB_LAUNCH_OK();
+  return 0;
+}
+
+int linattn_kv_context(const Act& x, int cgoff, int cg, const float* ss, const bf16* wk, const bf16* wv,
+                       const float* shift, int heads, int dh, int nsplit, float* part, cudaStream_t st) {
+  FTB_CHECK(heads * dh == 128, "fused k/v context needs heads*dim_head == 128");
+  FTB_CHECK(cg >= 2 && cg % 2 == 0 && cg <= 16, "fused k/v context: 16..128 input channels");
+  CUtensorMap tm;
+  FTB_TRY(make_voxel_tmap(&tm, x, kKvT, cg));
+  KvCtxParams p;
+  p.heads = heads; p.dh = dh; p.hd = 128;
+  p.cg = cg; p.cgtot = x.cg(); p.cgoff = cgoff;
+  p.vox = (long long)x.voxels();
+  p.ntiles = (int)((p.vox + kKvT - 1) / kKvT);
+  p.nsplit = nsplit;
+  p.wk = wk; p.wv = wv; p.ss = ss; p.shift = shift; p.part = part;
+  p.x_stage = (uint32_t)cg * kKvT * 16;
+  const uint32_t wbytes = (uint32_t)(cg / 2) * 4096u * 2u;
+  const uint32_t pv = (16 + 18) * kKvT * 16;
+  const uint32_t fixed = 16 * 8 + 16 + 128 * 4 + 256;
+  const uint32_t limit = 227 * 1024 - 128;
+  p.npv = (2 * pv + wbytes + 2 * p.x_stage + fixed <= limit) ? 2 : 1;
+  p.nx = (int)((limit - fixed - wbytes - p.npv * pv) / p.x_stage);
+  p.nx = p.nx > 4 ? 4 : p.nx;
+  FTB_CHECK(p.nx >= 2, "fused k/v context: shared memory budget");
+  p.off_w = (uint32_t)round_up((int)(p.nx * p.x_stage), 128);
+  p.off_pv = (uint32_t)round_up((int)(p.off_w + wbytes), 128);
+  p.off_bar = (uint32_t)round_up((int)(p.off_pv + p.npv * pv), 16);
+  const int smem = (int)(p.off_bar + 16 * 8 + 16 + 128 * 4 + 128);
+  static bool attr_set = false;
+  if (!attr_set) {
+    FTB_CUDA(cudaFuncSetAttribute(kvctx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(nsplit, x.B);
+  kvctx_kernel<<<grid, kKvThreads, smem, st>>>(tm, p);
+  FTB_LAUNCH_OK();
+  return 0;
+}
+
+int linattn_combine(const float* part, int nsplit, const float* kmax, int kmax_bstride, int B, int heads, int dh,
                     const float* mem_kv, int n_mem, const float* w_out, int C, float q_scale,
                     bf16* wpack_out, float* ctx_dbg, cudaStream_t st) {
   FTB_CHECK(C % 16 == 0 && (heads * dh) % 16 == 0, "linattn: C and heads*dim_head must be multiples of 16");
   FTB_CHECK(dh <= 32, "linattn: dim_head must be at most 32");
-  combine_head_kernel<<<dim3(heads, B), 256, 0, st>>>(part, nsplit, kmax, heads, dh, mem_kv, n_mem, w_out, C,
+  combine_head_kernel<<<dim3(heads, B), 256, 0, st>>>(part, nsplit, kmax, kmax_bstride, heads, dh, mem_kv, n_mem, w_out, C,
                                                       q_scale, wpack_out, ctx_dbg);
   FTB_LAUNCH_OK();
   return 0;

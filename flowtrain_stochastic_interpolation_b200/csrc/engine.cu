@@ -137,6 +137,8 @@ struct ftb_unet {
   std::map<std::string, int> pindex;
   std::map<std::string, ConvLayer> convs;
   std::map<std::string, GainVec> gains;
+  struct KShift { float* dev = nullptr; bool ok = false; };
+  std::map<std::string, KShift> kshift;   // LinearAttention layers: softmax shift of the fused k/v-context path
   std::vector<std::string> film_blocks;  // FiLM-table rows: prefix of the (SiLU, Linear) time MLP's Linear
   std::map<std::string, std::string> film_gain;   // block -> gain vector folded into its scale half ("" = none)
   std::map<std::string, int> film_off;
@@ -247,6 +249,7 @@ void add_attn(ftb_unet* U, const std::string& p, int dim, bool full) {
   } else {
     // LinearAttention's out projection is folded into per-sample weights (attention.cu), so
     // its weight stays fp32; only the bias/gain are used by the conv epilogue.
+    U->kshift[p] = ftb_unet::KShift{};
     add_param(U, p + ".to_out.0.weight", {dim, hd, 1, 1, 1});
     add_param(U, p + ".to_out.0.bias", {dim});
     add_gain(U, p + ".to_out.1.g", dim);
@@ -367,6 +370,7 @@ int ensure_device(ftb_unet* U) {
     if (!cl.in_scale.empty()) FTB_TRY(dev_alloc(U, &cl.scale_tmp, (size_t)cl.cin));
   }
   for (auto& kv : U->gains) FTB_TRY(dev_alloc(U, &kv.second.gs, (size_t)kv.second.c));
+  for (auto& kv : U->kshift) FTB_TRY(dev_alloc(U, &kv.second.dev, (size_t)U->cfg.attn_heads * U->cfg.attn_dim_head));
   const int nb = (int)U->film_blocks.size();
   FTB_TRY(dev_alloc(U, &U->d_film_w, (size_t)nb));
   FTB_TRY(dev_alloc(U, &U->d_film_b, (size_t)nb));
@@ -429,6 +433,20 @@ int finalize(ftb_unet* U, cudaStream_t st) {
     if (!cl.bname.empty())
       FTB_CUDA(cudaMemcpyAsync(cl.bias, U->params[U->pindex[cl.bname]].dev, cl.cout * sizeof(float),
                                cudaMemcpyDeviceToDevice, st));
+  }
+  // LinearAttention: shift[d] = 1.02*||W_k[d,:] (x) g*sqrt(C)||_2 bounds |k[d,n]| for every voxel, which
+  // lets the fused k/v-context kernel skip the max pass; only trusted while it is far from underflow
+  const int hd = U->cfg.attn_heads * U->cfg.attn_dim_head;
+  std::vector<float> hshift(hd);
+  for (auto& kv : U->kshift) {
+    const ConvLayer& cl = U->convs.at(kv.first + ".to_qkv");
+    const float* w = U->params[U->pindex[cl.wname]].dev;
+    FTB_TRY(linattn_kshift(w, cl.scale_tmp, hd, cl.cin, kv.second.dev, st));
+    FTB_CUDA(cudaMemcpyAsync(hshift.data(), kv.second.dev, hd * sizeof(float), cudaMemcpyDeviceToHost, st));
+    FTB_CUDA(cudaStreamSynchronize(st));
+    float mx = 0.f;
+    for (float v : hshift) mx = v > mx || !(v == v) ? v : mx;
+    kv.second.ok = mx == mx && mx <= 60.f && hd == 128 && cl.cin_pad <= 128 && getenv("FTB_LINATTN_EXACT") == nullptr;
   }
   FTB_CUDA(cudaGetLastError());
   U->dirty = false;
@@ -520,12 +538,26 @@ struct Fwd {
   int attention(const std::string& p, const Act& x, const float* x_sumsq, bool full, Act* out) {
     const ftb_unet_cfg& c = U->cfg;
     const int heads = c.attn_heads, dh = c.attn_dim_head, hd = heads * dh;
-    Act qkv = act(3 * hd, x.D, x.H, x.W);
+    // (the dry sizing pass reserves the larger, unfused footprint)
+    const bool fused = !dry && !full && x_sumsq != nullptr && U->kshift.count(p) && U->kshift.at(p).ok;
+    // fused path: only q is materialised; k and v live in TMEM / shared memory of kvctx_kernel
+    Act qkv = act(fused ? hd : 3 * hd, x.D, x.H, x.W);
     ConvEpilogue eq;
     eq.prenorm = true;
     eq.prenorm_ss = x_sumsq;
     if (!full) { eq.q_softmax_heads = heads; eq.q_dim_head = dh; eq.q_scale = 1.f / sqrtf((float)dh); }
-    FTB_TRY(conv(p + ".to_qkv", ConvSrc{&x, 0, x.cg()}, ConvSrc{}, eq, qkv));
+    const ConvLayer& cq = U->convs.at(p + ".to_qkv");
+    if (fused) {
+      if (!dry) {
+        ConvWeights wq;
+        wq.w = cq.packed; wq.ksize = 1; wq.cin = cq.cin_pad; wq.n = cq.n_tile; wq.ntiles = 1;   // q tile only
+        wq.cin_real = cq.cin; wq.cout_real = hd;
+        FTB_TRY(conv_dispatch(ConvSrc{&x, 0, x.cg()}, ConvSrc{}, wq, eq, qkv, 0, st));
+        U->launches += 1;
+      }
+    } else {
+      FTB_TRY(conv(p + ".to_qkv", ConvSrc{&x, 0, x.cg()}, ConvSrc{}, eq, qkv));
+    }
     *out = act(x.C, x.D, x.H, x.W);
     if (full) {
       Act ao = act(hd, x.D, x.H, x.W);
@@ -548,11 +580,21 @@ struct Fwd {
       float* part = f32((size_t)B * heads * nsplit * (dh * dh + dh));
       bf16* mpack = reinterpret_cast<bf16*>(raw((size_t)B * x.C * hd * sizeof(bf16)));
       if (!dry) {
-        FTB_TRY(linattn_kmax(qkv, heads, dh, nsplit, kmax, st));
-        FTB_TRY(linattn_context_partial(qkv, heads, dh, nsplit, kmax, part, st));
-        FTB_TRY(linattn_combine(part, nsplit, kmax, B, heads, dh, pdev(p + ".mem_kv"), c.num_mem_kv,
-                                pdev(p + ".to_out.0.weight"), x.C, 1.f, mpack, nullptr, st));
-        U->launches += 4;
+        if (fused) {
+          const size_t tile = (size_t)cq.cin_pad * cq.n_tile;
+          const float* shift = U->kshift.at(p).dev;
+          FTB_TRY(linattn_kv_context(x, 0, x.cg(), x_sumsq, cq.packed + tile, cq.packed + 2 * tile, shift, heads, dh,
+                                     nsplit, part, st));
+          FTB_TRY(linattn_combine(part, nsplit, shift, 0, B, heads, dh, pdev(p + ".mem_kv"), c.num_mem_kv,
+                                  pdev(p + ".to_out.0.weight"), x.C, 1.f, mpack, nullptr, st));
+          U->launches += 2;
+        } else {
+          FTB_TRY(linattn_kmax(qkv, heads, dh, nsplit, kmax, st));
+          FTB_TRY(linattn_context_partial(qkv, heads, dh, nsplit, kmax, part, st));
+          FTB_TRY(linattn_combine(part, nsplit, kmax, hd, B, heads, dh, pdev(p + ".mem_kv"), c.num_mem_kv,
+                                  pdev(p + ".to_out.0.weight"), x.C, 1.f, mpack, nullptr, st));
+          U->launches += 4;
+        }
         ConvWeights w;
         w.w = mpack; w.ksize = 1; w.cin = hd; w.n = x.C; w.ntiles = 1;
         w.batch_stride = (long long)x.C * hd;

@@ -114,7 +114,13 @@ int linattn_kmax(const Act& qkv, int heads, int dh, int nsplit, float* kmax, cud
 int linattn_context_partial(const Act& qkv, int heads, int dh, int nsplit, const float* kmax,
                             float* part, cudaStream_t st);
 // phase A2: merge partials + memory kv, fold W_out -> per-sample packed 1x1 weights M_b[C][heads*dh]
-int linattn_combine(const float* part, int nsplit, const float* kmax, int B, int heads, int dh,
+// fused k/v projection + context (never writes k, v): x blocked bf16 (channel groups [cgoff, cgoff+cg)),
+// ss = ||x voxel||^2, wk / wv = packed K-major tiles of the k / v rows of to_qkv, shift[hd] >= |k|
+int linattn_kshift(const float* w_qkv, const float* in_scale, int hd, int cin, float* shift, cudaStream_t st);
+int linattn_kv_context(const Act& x, int cgoff, int cg, const float* ss, const bf16* wk, const bf16* wv,
+                       const float* shift, int heads, int dh, int nsplit, float* part, cudaStream_t st);
+// kmax_bstride: elements between samples of `kmax` (0: one shift vector for the whole batch)
+int linattn_combine(const float* part, int nsplit, const float* kmax, int kmax_bstride, int B, int heads, int dh,
                     const float* mem_kv, int n_mem, const float* w_out, int C, float q_scale,
                     bf16* wpack_out, float* ctx_dbg, cudaStream_t st);
 // softmax attention over n tokens (+ n_mem memory kv), one CTA per (b, head, query tile)
