@@ -316,6 +316,12 @@ struct KvCtxParams {
   float* part;                   // [B][heads][nsplit][dh*dh + dh]
 };
 
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __global__ void __launch_bounds__(kKvThreads, 1)
 kvctx_kernel(const __grid_constant__ CUtensorMap tm, const KvCtxParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -458,10 +464,10 @@ kvctx_kernel(const __grid_constant__ CUtensorMap tm, const KvCtxParams p) {
           if (half == 0) {
             const float4 m0 = *reinterpret_cast<const float4*>(s_shift + c0 + g8 * 8);
             const float4 m1 = *reinterpret_cast<const float4*>(s_shift + c0 + g8 * 8 + 4);
-            f[0] = exp2f(fmaf(__uint_as_float(r[0]), rs2, -m0.x)); f[1] = exp2f(fmaf(__uint_as_float(r[1]), rs2, -m0.y));
-            f[2] = exp2f(fmaf(__uint_as_float(r[2]), rs2, -m0.z)); f[3] = exp2f(fmaf(__uint_as_float(r[3]), rs2, -m0.w));
-            f[4] = exp2f(fmaf(__uint_as_float(r[4]), rs2, -m1.x)); f[5] = exp2f(fmaf(__uint_as_float(r[5]), rs2, -m1.y));
-            f[6] = exp2f(fmaf(__uint_as_float(r[6]), rs2, -m1.z)); f[7] = exp2f(fmaf(__uint_as_float(r[7]), rs2, -m1.w));
+            f[0] = ex2_fast(fmaf(__uint_as_float(r[0]), rs2, -m0.x)); f[1] = ex2_fast(fmaf(__uint_as_float(r[1]), rs2, -m0.y));
+            f[2] = ex2_fast(fmaf(__uint_as_float(r[2]), rs2, -m0.z)); f[3] = ex2_fast(fmaf(__uint_as_float(r[3]), rs2, -m0.w));
+            f[4] = ex2_fast(fmaf(__uint_as_float(r[4]), rs2, -m1.x)); f[5] = ex2_fast(fmaf(__uint_as_float(r[5]), rs2, -m1.y));
+            f[6] = ex2_fast(fmaf(__uint_as_float(r[6]), rs2, -m1.z)); f[7] = ex2_fast(fmaf(__uint_as_float(r[7]), rs2, -m1.w));
           } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[j]) * rs;

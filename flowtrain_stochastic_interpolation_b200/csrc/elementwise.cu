@@ -59,16 +59,23 @@ pack_unfold_w_kernel(const float* __restrict__ x, int C, int D, int H, int W, in
     s_row[i] = (w >= 0 && w < W) ? __ldg(x + ((size_t)b * C + c) * vox + rowoff + w) : 0.f;
   }
   __syncthreads();
-  for (int o = threadIdx.x; o < CG * W; o += blockDim.x) {
-    const int cg = o / W, w = o - cg * W;
-    float f[8];
+  // thread = (channel group, W lane): its 8 (kw, c) taps are loop invariant
+  const int lanes = blockDim.x / CG;            // W lanes per channel group (blockDim = CG * lanes)
+  const int cg = threadIdx.x / lanes, wl = threadIdx.x - cg * lanes;
+  if (cg < CG) {
+    int off[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int cc = cg * 8 + j;
-      const int kw = s_kw[cc];
-      f[j] = kw == 255 ? 0.f : s_row[s_c[cc] * RW + w + kw];
+      off[j] = s_kw[cc] == 255 ? -1 : s_c[cc] * RW + s_kw[cc];
     }
-    *reinterpret_cast<uint4*>(out + ((((size_t)b * CG + cg) * vox) + rowoff + w) * 8) = pack_bf16x8(f);
+    bf16* orow = out + ((((size_t)b * CG + cg) * vox) + rowoff) * 8;
+    for (int w = wl; w < W; w += lanes) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = off[j] < 0 ? 0.f : s_row[off[j] + w];
+      *reinterpret_cast<uint4*>(orow + (size_t)w * 8) = pack_bf16x8(f);
+    }
   }
 }
 
@@ -424,7 +431,9 @@ int pack_unfold_w(const float* x, int B, int C, int D, int H, int W, int K, Act&
   FTB_CHECK(out.cg() * 8 <= 256 && C <= 255, "pack_unfold_w: at most 256 unfolded channels");
   const size_t smem = (size_t)C * (W + K - 1) * sizeof(float);
   FTB_CHECK(smem <= 40 * 1024, "pack_unfold_w: row too wide for shared memory");
-  pack_unfold_w_kernel<<<(unsigned)((size_t)B * D * H), 256, smem, st>>>(x, C, D, H, W, K, out.cg(), out.p);
+  const int lanes = 256 / out.cg() >= 1 ? 256 / out.cg() : 1;
+  FTB_CHECK(out.cg() <= 256, "pack_unfold_w: too many channel groups");
+  pack_unfold_w_kernel<<<(unsigned)((size_t)B * D * H), out.cg() * lanes, smem, st>>>(x, C, D, H, W, K, out.cg(), out.p);
   FTB_LAUNCH_OK();
   return 0;
 }
