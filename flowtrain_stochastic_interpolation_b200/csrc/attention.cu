@@ -515,6 +515,260 @@ kvctx_kernel(const __grid_constant__ CUtensorMap tm, const KvCtxParams p) {
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------ fused q projection + output
+// The q side of LinearAttention (unet_attn_3d.py:326-341) without writing q: per 128-voxel tile
+//   GEMM1: q = x_tile . Wq^T                                -> TMEM columns [0,128)
+//   pass A (8 warps): q*rs -> softmax over each head's dh, * dh^-0.5 -> shared memory (K-major bf16)
+//   GEMM2: y = q . M_b^T   (M_b = to_out folded with the context, per sample)  -> TMEM [128, 128+C)
+//   pass B (4 warps): + bias -> RMSNorm * g*sqrt(C) -> + x (residual) -> blocked bf16 store
+//   warp 0: TMA producer | warp 1: MMA issuer | warps 2-9: pass A (two head pairs per quadrant) |
+//   warps 10-13: pass B
+constexpr int kQoT = 128;
+constexpr int kQoThreads = 448;
+
+struct QoutParams {
+  int heads, dh;
+  int cg, C;                     // channel groups / padded channels of x (= output channels)
+  int cgtot, cgoff;              // of x
+  int out_cgtot;
+  long long vox;
+  int ntiles, nsplit, nx;
+  uint32_t x_stage, off_wq, off_mb, off_q, off_bar;
+  const bf16* wq;                // packed K-major tiles of the q rows [ks][16][2][8][8]
+  const bf16* mb;                // per sample [8][C/8][2][8][8]
+  long long mb_bstride;
+  const bf16* x;                 // residual (same tensor the TMA reads)
+  const float* ss;               // [B][vox] ||x||^2
+  const float* bias;             // [C]
+  const float* gs;               // [C] g*sqrt(C)
+  bf16* out;
+  float q_scale;
+};
+
+__global__ void __launch_bounds__(kQoThreads, 1)
+qout_kernel(const __grid_constant__ CUtensorMap tm, const QoutParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  constexpr uint32_t kBytesQ = 16 * kQoT * 16;
+  uint8_t* s_wq = smem + p.off_wq;
+  uint8_t* s_mb = smem + p.off_mb;
+  uint8_t* s_q = smem + p.off_q;               // 2 stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint64_t* x_full = bars;            // [4]
+  uint64_t* x_empty = bars + 4;       // [4]
+  uint64_t* q_ready = bars + 8;       // [2] pass A wrote sQ
+  uint64_t* q_empty = bars + 10;      // [2] GEMM2 consumed sQ
+  uint64_t* d1_full = bars + 12;
+  uint64_t* d1_empty = bars + 13;
+  uint64_t* d2_full = bars + 14;
+  uint64_t* d2_empty = bars + 15;
+  uint64_t* w_full = bars + 16;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 17);
+  float* s_bias = reinterpret_cast<float*>(tmem_ptr + 4);   // [128]
+  float* s_gs = s_bias + 128;                               // [128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x, b = blockIdx.y;
+  const int tiles_per = (p.ntiles + p.nsplit - 1) / p.nsplit;
+  const int t_lo = split * tiles_per, t_hi = min(p.ntiles, t_lo + tiles_per);
+  const int nt = max(0, t_hi - t_lo);
+  const int KS = p.cg / 2;
+  const uint32_t wq_bytes = (uint32_t)KS * 4096u;
+  const uint32_t mb_bytes = 8u * (uint32_t)p.C * 32u;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&q_ready[i], 256); mbar_init(&q_empty[i], 1); }
+    mbar_init(d1_full, 1);
+    mbar_init(d1_empty, 256);
+    mbar_init(d2_full, 1);
+    mbar_init(d2_empty, 128);
+    mbar_init(w_full, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tm);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 256);
+    tmem_relinquish();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 128) {
+    const int t = threadIdx.x - 64;
+    s_bias[t] = t < p.C ? __ldg(p.bias + t) : 0.f;
+    s_gs[t] = t < p.C ? __ldg(p.gs + t) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0 && nt > 0) {
+      mbar_expect_tx(w_full, wq_bytes + mb_bytes);
+      bulk_load(s_wq, p.wq, wq_bytes, w_full);
+      bulk_load(s_mb, p.mb + (long long)b * p.mb_bstride, mb_bytes, w_full);
+      for (int i = 0; i < nt; ++i) {
+        const int s = i % p.nx;
+        mbar_wait(&x_empty[s], ((i / p.nx) & 1) ^ 1);
+        mbar_expect_tx(&x_full[s], (uint32_t)p.cg * kQoT * 16);
+        tma_load_3d(smem + s * p.x_stage, &tm, &x_full[s], 0, (t_lo + i) * kQoT, b * p.cgtot + p.cgoff);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one() && nt > 0) {
+      const uint32_t idesc1 = umma_idesc_bf16_f32(128, 128);
+      const uint32_t idesc2 = umma_idesc_bf16_f32(128, p.C);
+      const uint32_t a_hi = (128u >> 4) | (1u << 14);                 // SBO: next 8 voxels
+      const uint32_t a_lbo = ((uint32_t)(kQoT * 16) >> 4) << 16;      // LBO: next channel group
+      const uint32_t b_hi = (256u >> 4) | (1u << 14);
+      const uint32_t b1_lo = (smem_u32(s_wq) >> 4) | ((128u >> 4) << 16);
+      const uint32_t b2_lo = (smem_u32(s_mb) >> 4) | ((128u >> 4) << 16);
+      const uint32_t mb_ks = ((uint32_t)p.C * 32u) >> 4;
+      auto gemm2 = [&](int j) {   // y = q . M_b^T of tile j
+        const int s = j & 1;
+        mbar_wait(&q_ready[s], (j >> 1) & 1);
+        mbar_wait(d2_empty, (j & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t a0 = (smem_u32(s_q + s * kBytesQ) >> 4) | a_lbo;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          umma_bf16_lohi(tmem_base + 128, a0 + ks * ((2u * kQoT * 16u) >> 4), a_hi, b2_lo + ks * mb_ks, b_hi, idesc2, ks != 0);
+        umma_commit(&q_empty[s]);
+        umma_commit(d2_full);
+      };
+      mbar_wait(w_full, 0);
+      for (int i = 0; i < nt; ++i) {
+        const int s = i % p.nx;
+        mbar_wait(&x_full[s], (i / p.nx) & 1);
+        mbar_wait(d1_empty, (i & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t a0 = (smem_u32(smem + s * p.x_stage) >> 4) | a_lbo;
+        for (int ks = 0; ks < KS; ++ks)
+          umma_bf16_lohi(tmem_base, a0 + ks * ((2u * kQoT * 16u) >> 4), a_hi, b1_lo + ks * 256, b_hi, idesc1, ks != 0);
+        umma_commit(&x_empty[s]);
+        umma_commit(d1_full);
+        if (i > 0) gemm2(i - 1);
+      }
+      gemm2(nt - 1);
+    }
+    __syncwarp();
+  } else if (warp < 10) {
+    // ---- pass A: q softmax per head -> sQ (K-major A operand of GEMM2)
+    const int q = warp & 3;
+    const int hsel = (warp - 2) >> 2;              // head pair {2*hsel, 2*hsel+1} (dh = 32) of this row
+    const int row = q * 32 + lane;
+    for (int i = 0; i < nt; ++i) {
+      const long long v = (long long)(t_lo + i) * kQoT + row;
+      const bool in = v < p.vox;
+      float rs = 0.f;
+      if (in) rs = 1.f / fmaxf(sqrtf(__ldg(p.ss + (size_t)b * p.vox + v)), 1e-12f);
+      const int s = i & 1;
+      mbar_wait(d1_full, i & 1);
+      mbar_wait(&q_empty[s], ((i >> 1) & 1) ^ 1);
+      tc_fence_after();
+      uint8_t* dst = s_q + s * kBytesQ;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+      for (int c0 = hsel * 64; c0 < hsel * 64 + 64; c0 += p.dh) {   // one head per iteration (dh 32 or 16)
+        uint32_t r0[16], r1[16];
+        tmem_ld16(trow + c0, r0);
+        if (p.dh == 32) tmem_ld16(trow + c0 + 16, r1);
+        tmem_ld_wait();
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a = __uint_as_float(r0[j]) * rs;
+          r0[j] = __float_as_uint(a);
+          mx = fmaxf(mx, a);
+        }
+        if (p.dh == 32) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a = __uint_as_float(r1[j]) * rs;
+            r1[j] = __float_as_uint(a);
+            mx = fmaxf(mx, a);
+          }
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float e = __expf(__uint_as_float(r0[j]) - mx);
+          r0[j] = __float_as_uint(e);
+          sum += e;
+        }
+        if (p.dh == 32) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float e = __expf(__uint_as_float(r1[j]) - mx);
+            r1[j] = __float_as_uint(e);
+            sum += e;
+          }
+        }
+        const float inv = in ? __fdividef(p.q_scale, sum) : 0.f;
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          if (g8 >= 2 && p.dh != 32) break;
+          const uint32_t* r = g8 < 2 ? r0 + g8 * 8 : r1 + (g8 - 2) * 8;
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[j]) * inv;
+          *reinterpret_cast<uint4*>(dst + ((size_t)((c0 >> 3) + g8) * kQoT + row) * 16) = pack_bf16x8(f);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      mbar_arrive(d1_empty);
+      mbar_arrive(&q_ready[s]);
+    }
+  } else {
+    // ---- pass B: + bias -> RMSNorm * g*sqrt(C) -> + x -> store
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const size_t cgs = (size_t)p.vox;
+    for (int i = 0; i < nt; ++i) {
+      const long long v = (long long)(t_lo + i) * kQoT + row;
+      const bool in = v < p.vox;
+      mbar_wait(d2_full, i & 1);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + 128;
+      float ss[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int c0 = 0; c0 < p.C; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(trow + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a = __uint_as_float(r[j]) + s_bias[c0 + j];
+          ss[j & 3] = fmaf(a, a, ss[j & 3]);
+        }
+      }
+      const float rinv = 1.f / fmaxf(sqrtf((ss[0] + ss[1]) + (ss[2] + ss[3])), 1e-12f);
+      for (int c0 = 0; c0 < p.C; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(trow + c0, r);
+        tmem_ld_wait();
+        if (!in) continue;
+        const bf16* xp = p.x + (((size_t)b * p.cgtot + p.cgoff + (c0 >> 3)) * cgs + (size_t)v) * 8;
+        bf16* op = p.out + (((size_t)b * p.out_cgtot + (c0 >> 3)) * cgs + (size_t)v) * 8;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          float xr[8], f[8];
+          unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(xp + (size_t)hf * cgs * 8)), xr);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int ch = c0 + hf * 8 + j;
+            f[j] = fmaf((__uint_as_float(r[hf * 8 + j]) + s_bias[ch]) * rinv, s_gs[ch], xr[j]);
+          }
+          *reinterpret_cast<uint4*>(op + (size_t)hf * cgs * 8) = pack_bf16x8(f);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(d2_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
 // shift[d] = 1.02 * ||w[d,:] * in_scale||_2 over the k rows of to_qkv (fp32 weights [3*hd][cin])
 __global__ void kshift_kernel(const float* __restrict__ w, const float* __restrict__ in_scale, int hd, int cin,
                               float* __restrict__ shift) {
@@ -792,6 +1046,47 @@ int linattn_kv_context(const Act& x, int cgoff, int cg, const float* ss, const b
   }
   dim3 grid(nsplit, x.B);
   kvctx_kernel<<<grid, kKvThreads, smem, st>>>(tm, p);
+  FTB_LAUNCH_OK();
+  return 0;
+}
+
+int linattn_q_out(const Act& x, const float* ss, const bf16* wq, const bf16* mb, long long mb_bstride,
+                  const float* bias, const float* gs, int heads, int dh, Act& out, cudaStream_t st) {
+  FTB_CHECK(heads * dh == 128 && (dh == 32 || dh == 16), "fused q/out needs heads*dim_head == 128, dim_head 16 or 32");
+  FTB_CHECK(x.C % 16 == 0 && x.C <= 128 && out.C == x.C && out.B == x.B && out.voxels() == x.voxels(),
+            "fused q/out: 16..128 channels, output shaped like the input");
+  CUtensorMap tm;
+  FTB_TRY(make_voxel_tmap(&tm, x, kQoT, x.cg()));
+  QoutParams p;
+  p.heads = heads; p.dh = dh;
+  p.cg = x.cg(); p.C = x.C; p.cgtot = x.cg(); p.cgoff = 0; p.out_cgtot = out.cg();
+  p.vox = (long long)x.voxels();
+  p.ntiles = (int)((p.vox + kQoT - 1) / kQoT);
+  int nsplit = cdiv(2 * num_sms(), x.B);
+  nsplit = nsplit > p.ntiles ? p.ntiles : nsplit;
+  p.nsplit = nsplit < 1 ? 1 : nsplit;
+  p.wq = wq; p.mb = mb; p.mb_bstride = mb_bstride; p.x = x.p; p.ss = ss; p.bias = bias; p.gs = gs; p.out = out.p;
+  p.q_scale = 1.f / sqrtf((float)dh);
+  p.x_stage = (uint32_t)p.cg * kQoT * 16;
+  const uint32_t wq_bytes = (uint32_t)(p.cg / 2) * 4096u, mb_bytes = 8u * (uint32_t)p.C * 32u;
+  const uint32_t qbytes = 2u * 16 * kQoT * 16;
+  const uint32_t fixed = 17 * 8 + 16 + 256 * 4 + 256;
+  const uint32_t limit = 227 * 1024 - 128;
+  p.nx = (int)((limit - fixed - wq_bytes - mb_bytes - qbytes) / p.x_stage);
+  p.nx = p.nx > 4 ? 4 : p.nx;
+  FTB_CHECK(p.nx >= 2, "fused q/out: shared memory budget");
+  p.off_wq = (uint32_t)round_up((int)(p.nx * p.x_stage), 128);
+  p.off_mb = (uint32_t)round_up((int)(p.off_wq + wq_bytes), 128);
+  p.off_q = (uint32_t)round_up((int)(p.off_mb + mb_bytes), 128);
+  p.off_bar = (uint32_t)round_up((int)(p.off_q + qbytes), 16);
+  const int smem = (int)(p.off_bar + 17 * 8 + 16 + 256 * 4 + 128);
+  static bool attr_set = false;
+  if (!attr_set) {
+    FTB_CUDA(cudaFuncSetAttribute(qout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(p.nsplit, x.B);
+  qout_kernel<<<grid, kQoThreads, smem, st>>>(tm, p);
   FTB_LAUNCH_OK();
   return 0;
 }

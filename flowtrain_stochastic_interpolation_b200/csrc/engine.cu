@@ -540,24 +540,15 @@ struct Fwd {
     const int heads = c.attn_heads, dh = c.attn_dim_head, hd = heads * dh;
     // (the dry sizing pass reserves the larger, unfused footprint)
     const bool fused = !dry && !full && x_sumsq != nullptr && U->kshift.count(p) && U->kshift.at(p).ok;
-    // fused path: only q is materialised; k and v live in TMEM / shared memory of kvctx_kernel
-    Act qkv = act(fused ? hd : 3 * hd, x.D, x.H, x.W);
+    // fused path: q, k and v are never materialised (kvctx_kernel, qout_kernel)
+    Act qkv;
+    if (!fused) qkv = act(3 * hd, x.D, x.H, x.W);
     ConvEpilogue eq;
     eq.prenorm = true;
     eq.prenorm_ss = x_sumsq;
     if (!full) { eq.q_softmax_heads = heads; eq.q_dim_head = dh; eq.q_scale = 1.f / sqrtf((float)dh); }
     const ConvLayer& cq = U->convs.at(p + ".to_qkv");
-    if (fused) {
-      if (!dry) {
-        ConvWeights wq;
-        wq.w = cq.packed; wq.ksize = 1; wq.cin = cq.cin_pad; wq.n = cq.n_tile; wq.ntiles = 1;   // q tile only
-        wq.cin_real = cq.cin; wq.cout_real = hd;
-        FTB_TRY(conv_dispatch(ConvSrc{&x, 0, x.cg()}, ConvSrc{}, wq, eq, qkv, 0, st));
-        U->launches += 1;
-      }
-    } else {
-      FTB_TRY(conv(p + ".to_qkv", ConvSrc{&x, 0, x.cg()}, ConvSrc{}, eq, qkv));
-    }
+    if (!fused) FTB_TRY(conv(p + ".to_qkv", ConvSrc{&x, 0, x.cg()}, ConvSrc{}, eq, qkv));
     *out = act(x.C, x.D, x.H, x.W);
     if (full) {
       Act ao = act(hd, x.D, x.H, x.W);
@@ -595,16 +586,22 @@ struct Fwd {
                                   pdev(p + ".to_out.0.weight"), x.C, 1.f, mpack, nullptr, st));
           U->launches += 4;
         }
-        ConvWeights w;
-        w.w = mpack; w.ksize = 1; w.cin = hd; w.n = x.C; w.ntiles = 1;
-        w.batch_stride = (long long)x.C * hd;
-        ConvEpilogue eo;
-        eo.bias = pdev(p + ".to_out.0.bias");
-        eo.norm = true;
-        eo.mul = U->gains.at(p + ".to_out.1.g").gs;
-        eo.resid = &x;
-        FTB_TRY(conv_dispatch(ConvSrc{&qkv, 0, hd / 8}, ConvSrc{}, w, eo, *out, 0, st));
-        U->launches += 1;
+        if (fused) {
+          FTB_TRY(linattn_q_out(x, x_sumsq, cq.packed, mpack, (long long)x.C * hd, pdev(p + ".to_out.0.bias"),
+                                U->gains.at(p + ".to_out.1.g").gs, heads, dh, *out, st));
+          U->launches += 1;
+        } else {
+          ConvWeights w;
+          w.w = mpack; w.ksize = 1; w.cin = hd; w.n = x.C; w.ntiles = 1;
+          w.batch_stride = (long long)x.C * hd;
+          ConvEpilogue eo;
+          eo.bias = pdev(p + ".to_out.0.bias");
+          eo.norm = true;
+          eo.mul = U->gains.at(p + ".to_out.1.g").gs;
+          eo.resid = &x;
+          FTB_TRY(conv_dispatch(ConvSrc{&qkv, 0, hd / 8}, ConvSrc{}, w, eo, *out, 0, st));
+          U->launches += 1;
+        }
       }
     }
     tap(p, *out);
