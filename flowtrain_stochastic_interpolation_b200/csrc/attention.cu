@@ -437,7 +437,7 @@ kvctx_kernel(const __grid_constant__ CUtensorMap tm, const KvCtxParams p) {
     __syncwarp();
   } else {
     const int q = warp & 3;                        // TMEM lane quadrant
-    const int half = (warp - 2) >> 2;              // 0: k columns -> P, 1: v columns -> V
+    const int half = (warp - 2) >> 2;              // which 64 columns of k and of v this warp converts
     const int row = q * 32 + lane;                 // voxel of the tile
     const float log2e = 1.44269504088896340736f;
     for (int i = 0; i < nt; ++i) {
@@ -449,31 +449,35 @@ kvctx_kernel(const __grid_constant__ CUtensorMap tm, const KvCtxParams p) {
       mbar_wait(d1_full, i & 1);
       mbar_wait(&pv_empty[s], ((i / p.npv) & 1) ^ 1);
       tc_fence_after();
-      uint8_t* dst = s_pv + s * kPv + (half ? kBytesP : 0);
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + half * 128;
       const float rs2 = rs * log2e;
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t r0[16], r1[16];
-        tmem_ld16(trow + c0, r0);
-        tmem_ld16(trow + c0 + 16, r1);
-        tmem_ld_wait();
+      // every warp converts 64 k columns (-> P, with the exp) and 64 v columns (-> V): balanced MUFU load
+#pragma unroll 1
+      for (int part = 0; part < 2; ++part) {
+        uint8_t* dst = s_pv + s * kPv + (part ? kBytesP : 0);
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + part * 128;
+        for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
+          uint32_t r0[16], r1[16];
+          tmem_ld16(trow + c0, r0);
+          tmem_ld16(trow + c0 + 16, r1);
+          tmem_ld_wait();
 #pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          float f[8];
-          const uint32_t* r = g8 < 2 ? r0 + g8 * 8 : r1 + (g8 - 2) * 8;
-          if (half == 0) {
-            const float4 m0 = *reinterpret_cast<const float4*>(s_shift + c0 + g8 * 8);
-            const float4 m1 = *reinterpret_cast<const float4*>(s_shift + c0 + g8 * 8 + 4);
-            f[0] = ex2_fast(fmaf(__uint_as_float(r[0]), rs2, -m0.x)); f[1] = ex2_fast(fmaf(__uint_as_float(r[1]), rs2, -m0.y));
-            f[2] = ex2_fast(fmaf(__uint_as_float(r[2]), rs2, -m0.z)); f[3] = ex2_fast(fmaf(__uint_as_float(r[3]), rs2, -m0.w));
-            f[4] = ex2_fast(fmaf(__uint_as_float(r[4]), rs2, -m1.x)); f[5] = ex2_fast(fmaf(__uint_as_float(r[5]), rs2, -m1.y));
-            f[6] = ex2_fast(fmaf(__uint_as_float(r[6]), rs2, -m1.z)); f[7] = ex2_fast(fmaf(__uint_as_float(r[7]), rs2, -m1.w));
-          } else {
+          for (int g8 = 0; g8 < 4; ++g8) {
+            float f[8];
+            const uint32_t* r = g8 < 2 ? r0 + g8 * 8 : r1 + (g8 - 2) * 8;
+            if (part == 0) {
+              const float4 m0 = *reinterpret_cast<const float4*>(s_shift + c0 + g8 * 8);
+              const float4 m1 = *reinterpret_cast<const float4*>(s_shift + c0 + g8 * 8 + 4);
+              f[0] = ex2_fast(fmaf(__uint_as_float(r[0]), rs2, -m0.x)); f[1] = ex2_fast(fmaf(__uint_as_float(r[1]), rs2, -m0.y));
+              f[2] = ex2_fast(fmaf(__uint_as_float(r[2]), rs2, -m0.z)); f[3] = ex2_fast(fmaf(__uint_as_float(r[3]), rs2, -m0.w));
+              f[4] = ex2_fast(fmaf(__uint_as_float(r[4]), rs2, -m1.x)); f[5] = ex2_fast(fmaf(__uint_as_float(r[5]), rs2, -m1.y));
+              f[6] = ex2_fast(fmaf(__uint_as_float(r[6]), rs2, -m1.z)); f[7] = ex2_fast(fmaf(__uint_as_float(r[7]), rs2, -m1.w));
+            } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[j]) * rs;
+              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[j]) * rs;
+            }
+            const uint4 u = in ? pack_bf16x8(f) : make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(dst + ((size_t)((c0 >> 3) + g8) * kKvT + row) * 16) = u;
           }
-          const uint4 u = in ? pack_bf16x8(f) : make_uint4(0u, 0u, 0u, 0u);
-          *reinterpret_cast<uint4*>(dst + ((size_t)((c0 >> 3) + g8) * kKvT + row) * 16) = u;
         }
       }
       tc_fence_before();
@@ -558,12 +562,12 @@ qout_kernel(const __grid_constant__ CUtensorMap tm, const QoutParams p) {
   uint64_t* x_empty = bars + 4;       // [4]
   uint64_t* q_ready = bars + 8;       // [2] pass A wrote sQ
   uint64_t* q_empty = bars + 10;      // [2] GEMM2 consumed sQ
-  uint64_t* d1_full = bars + 12;
-  uint64_t* d1_empty = bars + 13;
-  uint64_t* d2_full = bars + 14;
-  uint64_t* d2_empty = bars + 15;
-  uint64_t* w_full = bars + 16;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* d1_full = bars + 12;      // [2]
+  uint64_t* d1_empty = bars + 14;     // [2]
+  uint64_t* d2_full = bars + 16;
+  uint64_t* d2_empty = bars + 17;
+  uint64_t* w_full = bars + 18;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 19);
   float* s_bias = reinterpret_cast<float*>(tmem_ptr + 4);   // [128]
   float* s_gs = s_bias + 128;                               // [128]
 
@@ -579,8 +583,7 @@ qout_kernel(const __grid_constant__ CUtensorMap tm, const QoutParams p) {
   if (threadIdx.x == 0) {
     for (int i = 0; i < 4; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&q_ready[i], 256); mbar_init(&q_empty[i], 1); }
-    mbar_init(d1_full, 1);
-    mbar_init(d1_empty, 256);
+    for (int i = 0; i < 2; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], 256); }
     mbar_init(d2_full, 1);
     mbar_init(d2_empty, 128);
     mbar_init(w_full, 1);
@@ -588,7 +591,7 @@ qout_kernel(const __grid_constant__ CUtensorMap tm, const QoutParams p) {
     prefetch_tmap(&tm);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr, 256);
+    tmem_alloc(tmem_ptr, 512);   // q accumulators [0,128) and [128,256) (double buffered), y at [256, 256 + C)
     tmem_relinquish();
   }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + 128) {
@@ -631,7 +634,7 @@ qout_kernel(const __grid_constant__ CUtensorMap tm, const QoutParams p) {
         const uint32_t a0 = (smem_u32(s_q + s * kBytesQ) >> 4) | a_lbo;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)
-          umma_bf16_lohi(tmem_base + 128, a0 + ks * ((2u * kQoT * 16u) >> 4), a_hi, b2_lo + ks * mb_ks, b_hi, idesc2, ks != 0);
+          umma_bf16_lohi(tmem_base + 256, a0 + ks * ((2u * kQoT * 16u) >> 4), a_hi, b2_lo + ks * mb_ks, b_hi, idesc2, ks != 0);
         umma_commit(&q_empty[s]);
         umma_commit(d2_full);
       };
@@ -639,13 +642,14 @@ qout_kernel(const __grid_constant__ CUtensorMap tm, const QoutParams p) {
       for (int i = 0; i < nt; ++i) {
         const int s = i % p.nx;
         mbar_wait(&x_full[s], (i / p.nx) & 1);
-        mbar_wait(d1_empty, (i & 1) ^ 1);
+        mbar_wait(&d1_empty[i & 1], ((i >> 1) & 1) ^ 1);   // pass A of tile i-2 has drained this buffer
         tc_fence_after();
         const uint32_t a0 = (smem_u32(smem + s * p.x_stage) >> 4) | a_lbo;
         for (int ks = 0; ks < KS; ++ks)
-          umma_bf16_lohi(tmem_base, a0 + ks * ((2u * kQoT * 16u) >> 4), a_hi, b1_lo + ks * 256, b_hi, idesc1, ks != 0);
+          umma_bf16_lohi(tmem_base + (i & 1) * 128, a0 + ks * ((2u * kQoT * 16u) >> 4), a_hi, b1_lo + ks * 256, b_hi,
+                         idesc1, ks != 0);
         umma_commit(&x_empty[s]);
-        umma_commit(d1_full);
+        umma_commit(&d1_full[i & 1]);
         if (i > 0) gemm2(i - 1);
       }
       gemm2(nt - 1);
@@ -662,11 +666,11 @@ qout_kernel(const __grid_constant__ CUtensorMap tm, const QoutParams p) {
       float rs = 0.f;
       if (in) rs = 1.f / fmaxf(sqrtf(__ldg(p.ss + (size_t)b * p.vox + v)), 1e-12f);
       const int s = i & 1;
-      mbar_wait(d1_full, i & 1);
+      mbar_wait(&d1_full[s], (i >> 1) & 1);
       mbar_wait(&q_empty[s], ((i >> 1) & 1) ^ 1);
       tc_fence_after();
       uint8_t* dst = s_q + s * kBytesQ;
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + s * 128;
       for (int c0 = hsel * 64; c0 < hsel * 64 + 64; c0 += p.dh) {   // one head per iteration (dh 32 or 16)
         uint32_t r0[16], r1[16];
         tmem_ld16(trow + c0, r0);
@@ -715,7 +719,7 @@ qout_kernel(const __grid_constant__ CUtensorMap tm, const QoutParams p) {
       }
       tc_fence_before();
       fence_proxy_async();
-      mbar_arrive(d1_empty);
+      mbar_arrive(&d1_empty[s]);
       mbar_arrive(&q_ready[s]);
     }
   } else {
@@ -728,7 +732,7 @@ qout_kernel(const __grid_constant__ CUtensorMap tm, const QoutParams p) {
       const bool in = v < p.vox;
       mbar_wait(d2_full, i & 1);
       tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + 128;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + 256;
       float ss[4] = {0.f, 0.f, 0.f, 0.f};
       for (int c0 = 0; c0 < p.C; c0 += 16) {
         uint32_t r[16];
@@ -766,7 +770,7 @@ qout_kernel(const __grid_constant__ CUtensorMap tm, const QoutParams p) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // shift[d] = 1.02 * ||w[d,:] * in_scale||_2 over the k rows of to_qkv (fp32 weights [3*hd][cin])
@@ -1070,7 +1074,7 @@ int linattn_q_out(const Act& x, const float* ss, const bf16* wq, const bf16* mb,
   p.x_stage = (uint32_t)p.cg * kQoT * 16;
   const uint32_t wq_bytes = (uint32_t)(p.cg / 2) * 4096u, mb_bytes = 8u * (uint32_t)p.C * 32u;
   const uint32_t qbytes = 2u * 16 * kQoT * 16;
-  const uint32_t fixed = 17 * 8 + 16 + 256 * 4 + 256;
+  const uint32_t fixed = 19 * 8 + 16 + 256 * 4 + 256;
   const uint32_t limit = 227 * 1024 - 128;
   p.nx = (int)((limit - fixed - wq_bytes - mb_bytes - qbytes) / p.x_stage);
   p.nx = p.nx > 4 ? 4 : p.nx;
@@ -1079,7 +1083,7 @@ int linattn_q_out(const Act& x, const float* ss, const bf16* wq, const bf16* mb,
   p.off_mb = (uint32_t)round_up((int)(p.off_wq + wq_bytes), 128);
   p.off_q = (uint32_t)round_up((int)(p.off_mb + mb_bytes), 128);
   p.off_bar = (uint32_t)round_up((int)(p.off_q + qbytes), 16);
-  const int smem = (int)(p.off_bar + 17 * 8 + 16 + 256 * 4 + 128);
+  const int smem = (int)(p.off_bar + 19 * 8 + 16 + 256 * 4 + 128);
   static bool attr_set = false;
   if (!attr_set) {
     FTB_CUDA(cudaFuncSetAttribute(qout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
