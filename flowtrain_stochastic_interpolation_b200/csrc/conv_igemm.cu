@@ -46,7 +46,7 @@ constexpr int kMaxEnt = 96;   // MMA table entries per group (first-chunk pairs 
 constexpr int kMaxKS = 32;    // k-steps (Cin_pad / 16)
 constexpr int kMaxCC = 16;    // channel chunks (passes) per group
 
-enum : int { F_SILU = 1, F_QSOFTMAX = 2, F_NOMMA = 4, F_PLAIN = 8 };
+enum : int { F_SILU = 1, F_QSOFTMAX = 2, F_PLAIN = 8 };
 
 struct IgemmParams {
   int B, D, H, W;
@@ -400,13 +400,6 @@ __device__ __forceinline__ void epi_qsoftmax(const IgemmParams& p, const EpiCtx&
 }
 
 
-__device__ __forceinline__ void umma_fake(uint32_t d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                          uint32_t idesc, uint32_t accum) {   // timing experiments only
-  asm volatile("{\n\t.reg .b32 t;\n\tadd.u32 t, %0, %1;\n\tadd.u32 t, t, %2;\n\tadd.u32 t, t, %3;\n\t"
-               "add.u32 t, t, %4;\n\tadd.u32 t, t, %5;\n\tadd.u32 t, t, %6;\n\t}" ::"r"(d), "r"(a_lo), "r"(a_hi),
-               "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum));
-}
-
 struct IssueCtx {
   uint32_t a_hi, b_hi, planes_enc, slot_enc, nslot, kinc, kstep;
   uint32_t slot_w0, acc0;   // per group: ring slot of window plane 0, TMEM address of accumulator 0
@@ -415,7 +408,7 @@ struct IssueCtx {
 // Issue the MMAs of one weight chunk: table entries [ea, ea_end) x NKS k-steps.  An entry is
 // (window plane q, B row-block offset | accumulate flag, TMEM column offset, instruction
 // descriptor); `overwrite_ok` = this is the first chunk, honour the entry's flag.
-template <int NKS, bool FAKE = false>
+template <int NKS>
 __device__ __forceinline__ void issue_entries(const IssueCtx& ic, uint32_t ea, uint32_t ea_end, uint32_t aoff,
                                               uint32_t wb, bool overwrite_ok) {
   if (ea >= ea_end) return;
@@ -434,15 +427,9 @@ __device__ __forceinline__ void issue_entries(const IssueCtx& ic, uint32_t ea, u
     const uint32_t a = a_base + slot * ic.slot_enc;
     const uint32_t b = (ey & 0x7FFFFFFFu) + wb;
     const uint32_t d = ic.acc0 + ez;
-    if (FAKE) {
-      umma_fake(d, a, ic.a_hi, b, ic.b_hi, ew, overwrite_ok ? (ey >> 31) : 1u);
+    umma_bf16_lohi(d, a, ic.a_hi, b, ic.b_hi, ew, overwrite_ok ? (ey >> 31) : 1u);
 #pragma unroll
-      for (int i = 1; i < NKS; ++i) umma_fake(d, a + i * ic.kinc, ic.a_hi, b + i * ic.kstep, ic.b_hi, ew, 1u);
-    } else {
-      umma_bf16_lohi(d, a, ic.a_hi, b, ic.b_hi, ew, overwrite_ok ? (ey >> 31) : 1u);
-#pragma unroll
-      for (int i = 1; i < NKS; ++i) umma_bf16_lohi(d, a + i * ic.kinc, ic.a_hi, b + i * ic.kstep, ic.b_hi, ew, 1u);
-    }
+    for (int i = 1; i < NKS; ++i) umma_bf16_lohi(d, a + i * ic.kinc, ic.a_hi, b + i * ic.kstep, ic.b_hi, ew, 1u);
     if (!more) break;
     ex = nx; ey = ny; ez = nz; ew = nw;
   }
@@ -579,7 +566,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     const uint32_t nb_enc = (uint32_t)(p.N * 2);                           // one depth tap of B rows, >>4
     const uint32_t tab_addr = smem_u32(tab);
     const bool stream_w = !p.w_resident;
-    const bool fake = (p.flags & F_NOMMA) != 0;
     // ring cursors, advanced incrementally (no divisions on the issue path)
     uint32_t slot_w0 = 0;                  // ring slot of the current window's plane 0
     uint32_t rslot = 0, rphase = 0;        // next plane_full barrier to wait for
@@ -680,18 +666,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
                 const uint32_t ea_end = ea + (uint32_t)(firstc ? n_first : n_main) * 16u;
                 long long ti0 = 0;
                 if (p.dbg) ti0 = clock64();
-                if (fake) {
-                  issue_entries<3, true>(ic, ea, ea_end, aoff, wb, firstc);
-                } else {
-                  switch (nks) {   // straight-line k-step issue for the common chunk lengths
-                    case 1: issue_entries<1>(ic, ea, ea_end, aoff, wb, firstc); break;
-                    case 2: issue_entries<2>(ic, ea, ea_end, aoff, wb, firstc); break;
-                    case 3: issue_entries<3>(ic, ea, ea_end, aoff, wb, firstc); break;
-                    case 4: issue_entries<4>(ic, ea, ea_end, aoff, wb, firstc); break;
-                    default:
-                      for (int i = 0; i < nks; ++i)
-                        issue_entries<1>(ic, ea, ea_end, aoff + i * ic.kinc, wb + i * ic.kstep, firstc && i == 0);
-                  }
+                switch (nks) {   // straight-line k-step issue for the common chunk lengths
+                  case 1: issue_entries<1>(ic, ea, ea_end, aoff, wb, firstc); break;
+                  case 2: issue_entries<2>(ic, ea, ea_end, aoff, wb, firstc); break;
+                  case 3: issue_entries<3>(ic, ea, ea_end, aoff, wb, firstc); break;
+                  case 4: issue_entries<4>(ic, ea, ea_end, aoff, wb, firstc); break;
+                  default:
+                    for (int i = 0; i < nks; ++i)
+                      issue_entries<1>(ic, ea, ea_end, aoff + i * ic.kinc, wb + i * ic.kstep, firstc && i == 0);
                 }
                 if (p.dbg) dbg_issue += clock64() - ti0;
                 if (stream_w) {
@@ -1118,8 +1100,7 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
     q.wpack = w.w + (size_t)nt * w.tile_elems();
     q.bias = e.bias ? e.bias + (size_t)nt * w.n : nullptr;
     q.out_cgoff = out_cgoff + nt * (w.n / 8);
-    q.flags = (e.silu ? F_SILU : 0) | ((e.q_softmax_heads && nt == 0) ? F_QSOFTMAX : 0) |
-              (getenv("FTB_CONV_NOMMA") ? F_NOMMA : 0);
+    q.flags = (e.silu ? F_SILU : 0) | ((e.q_softmax_heads && nt == 0) ? F_QSOFTMAX : 0);
     if (!(q.flags & F_QSOFTMAX) && !q.norm && !q.bias && !q.mul && !q.add && !e.silu && !q.resid && !q.out_f32 && !q.ss_out)
       q.flags |= F_PLAIN;
     int prof = -1;

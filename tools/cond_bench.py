@@ -42,3 +42,12 @@ for (b, s) in ((1, 128), (2, 128), (1, 64)):
         ms = timeit(lambda: net(x, t))
     gf = 872.7 * (s / 64) ** 3 * b
     print(f"Unet3D {s}^3 B={b}: {ms:.2f} ms/eval = {gf/ms:.0f} GF/ms (TFLOP/s)")
+# B=1 latency: eager launch sequence vs one CUDA graph per evaluation
+x = synth.synth_input((1, 18, 64, 64, 64), 3).to(dev)
+t = torch.full((1,), 0.4, device=dev)
+with torch.no_grad():
+    eager = timeit(lambda: net(x, t), 20)
+    net.enable_cuda_graph(True)
+    graphed = timeit(lambda: net(x, t), 20)
+    net.enable_cuda_graph(False)
+print(f"Unet3D 64^3 B=1: eager {eager:.2f} ms/eval, CUDA graph {graphed:.2f} ms/eval")
