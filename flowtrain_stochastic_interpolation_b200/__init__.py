@@ -12,11 +12,12 @@ from .solvers import (ODEFlowSolver, ODEOneSidedDenoisingSolver, SDEOneSidedDeno
                       integrate_fixed, odeSol_RK4)
 from .task import (EMAShadow, Geo3DStochInterp, decode, ema_update_, embed, flow_loss,
                    simplex_embedding)
+from .training import BucketAllReduce, FlowTrainer, flatten_parameters
 from .unet3d import Unet3D, Unet3DCond
 
 __all__ = [
     "Unet3D", "Unet3DCond", "StochasticInterpolator", "BaseInterpolant", "LinearInterpolant", "TrigInterpolant",
     "EncDecInterpolant", "SBDMInterpolant", "MirrorInterpolant", "ODEFlowSolver",
     "ODEOneSidedDenoisingSolver", "SDEOneSidedDenoisingSolver", "odeSol_RK4", "integrate_fixed",
-    "Geo3DStochInterp", "EMAShadow", "embed", "decode", "flow_loss", "ema_update_", "simplex_embedding",
+    "Geo3DStochInterp", "EMAShadow", "FlowTrainer", "BucketAllReduce", "flatten_parameters", "embed", "decode", "flow_loss", "ema_update_", "simplex_embedding",
 ]

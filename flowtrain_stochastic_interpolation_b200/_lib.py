@@ -45,6 +45,7 @@ lib = C.CDLL(LIB_PATH)
 
 _vp, _i, _i64, _f, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
 _ip = C.POINTER(C.c_int)
+BUCKET_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int64)
 
 _SIGS = {
     "ftb_last_error": (C.c_char_p, []),
@@ -76,6 +77,17 @@ _SIGS = {
     "ftb_embed": (_i, [_vp, _vp, _vp, _i, _i, _i, _i64, _i, _vp]),
     "ftb_ema_update": (_i, [_vp, _vp, _i64, _d, _vp]),
     "ftb_mse_ratio_accumulate": (_i, [_vp, _vp, _i64, _vp, _vp]),
+    "ftb_unet3d_param_offset": (_i64, [_vp, _i]),
+    "ftb_unet3d_bind_params": (_i, [_vp, _vp, _vp]),
+    "ftb_unet3d_mark_dirty": (_i, [_vp]),
+    "ftb_unet3d_train_workspace_bytes": (_sz, [_vp, _i, _i, _i, _i]),
+    "ftb_unet3d_forward_train": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "ftb_unet3d_backward": (_i, [_vp, _vp, _vp, _vp, _sz, BUCKET_CB, _vp, _vp]),
+    "ftb_mse_ratio_grad": (_i, [_vp, _vp, _i64, _vp, _f, _vp, _vp]),
+    "ftb_grad_sumsq": (_i, [_vp, _i64, _vp, _vp]),
+    "ftb_adam_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _i, _vp, _f, _f, _vp]),
+    "ftb_test_conv_wgrad": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp]),
+    "ftb_test_conv_dgrad": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ftb_test_conv3d": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "ftb_test_trilinear": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }

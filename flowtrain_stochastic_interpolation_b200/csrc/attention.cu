@@ -792,7 +792,8 @@ __global__ void kshift_kernel(const float* __restrict__ w, const float* __restri
 __global__ void __launch_bounds__(256)
 combine_head_kernel(const float* __restrict__ part, int nsplit, const float* __restrict__ kmax,
                     int kmax_bstride, int heads, int dh, const float* __restrict__ mem_kv, int n_mem, const float* __restrict__ w_out,
-                    int C, float q_scale, bf16* __restrict__ wpack, float* __restrict__ ctx_dbg) {
+                    int C, float q_scale, bf16* __restrict__ wpack, float* __restrict__ ctx_dbg,
+                    float* __restrict__ kstat) {
   __shared__ float sctx[32 * 33];
   __shared__ float ssum[32];
   const int h = blockIdx.x, b = blockIdx.y;
@@ -823,6 +824,10 @@ combine_head_kernel(const float* __restrict__ part, int nsplit, const float* __r
       s += pj;
     }
     const float v = c / s;
+    if (kstat && e == 0) {   // softmax statistics of k over voxels + memory tokens (training backward)
+      kstat[((size_t)b * hd + h * dh + d) * 2] = m;
+      kstat[((size_t)b * hd + h * dh + d) * 2 + 1] = s;
+    }
     sctx[d * 33 + e] = v;   // (d, e) is read and written by this thread only
     if (ctx_dbg) ctx_dbg[((size_t)b * heads + h) * dh * dh + o] = v;
   }
@@ -1097,11 +1102,11 @@ int linattn_q_out(const Act& x, const float* ss, const bf16* wq, const bf16* mb,
 
 int linattn_combine(const float* part, int nsplit, const float* kmax, int kmax_bstride, int B, int heads, int dh,
                     const float* mem_kv, int n_mem, const float* w_out, int C, float q_scale,
-                    bf16* wpack_out, float* ctx_dbg, cudaStream_t st) {
+                    bf16* wpack_out, float* ctx_dbg, cudaStream_t st, float* kstat) {
   FTB_CHECK(C % 16 == 0 && (heads * dh) % 16 == 0, "linattn: C and heads*dim_head must be multiples of 16");
   FTB_CHECK(dh <= 32, "linattn: dim_head must be at most 32");
   combine_head_kernel<<<dim3(heads, B), 256, 0, st>>>(part, nsplit, kmax, kmax_bstride, heads, dh, mem_kv, n_mem, w_out, C,
-                                                      q_scale, wpack_out, ctx_dbg);
+                                                      q_scale, wpack_out, ctx_dbg, kstat);
   FTB_LAUNCH_OK();
   return 0;
 }

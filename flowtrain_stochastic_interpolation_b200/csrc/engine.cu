@@ -128,6 +128,15 @@ struct GainVec {
 using namespace ftb;
 using namespace ftb::eng;
 
+namespace ftb_engine_detail {
+struct DgradPack {
+  int ci0 = 0, cin_sub = 0, n_tile = 0;
+  ftb::bf16* packed = nullptr;
+};
+struct TrainState;
+struct TrainCtx;
+}  // namespace ftb_engine_detail
+
 struct ftb_unet {
   ftb_unet_cfg cfg;
   std::vector<int> dims;
@@ -148,6 +157,11 @@ struct ftb_unet {
   const float** d_film_gs = nullptr;
   int* d_film_off = nullptr;
   bool dirty = true;
+  bool kshift_stale = true;      // the fused-attention shift vectors lag the weights (training skips them)
+  bool dgrad_dirty = true;       // transposed packs for the data gradients lag the weights
+  std::map<std::string, std::vector<ftb_engine_detail::DgradPack>> dgrad;
+  std::shared_ptr<ftb_engine_detail::TrainState> train;
+  std::shared_ptr<ftb_engine_detail::TrainCtx> train_ctx;
   bool on_device = false;
   std::map<std::string, Act> taps;
   bool keep_taps = true;
@@ -250,8 +264,7 @@ void add_attn(ftb_unet* U, const std::string& p, int dim, bool full) {
     // LinearAttention's out projection is folded into per-sample weights (attention.cu), so
     // its weight stays fp32; only the bias/gain are used by the conv epilogue.
     U->kshift[p] = ftb_unet::KShift{};
-    add_param(U, p + ".to_out.0.weight", {dim, hd, 1, 1, 1});
-    add_param(U, p + ".to_out.0.bias", {dim});
+    add_conv(U, p + ".to_out.0", dim, hd, 1, true);   // packed copy is used by the training path only
     add_gain(U, p + ".to_out.1.g", dim);
   }
 }
@@ -410,8 +423,10 @@ __global__ void test_affine_kernel(const float* g, const float* scale, const flo
   add[(size_t)b * stride + c] = shift ? shift[i] : 0.f;
 }
 
-int finalize(ftb_unet* U, cudaStream_t st) {
-  if (!U->dirty) return 0;
+int finalize_kshift(ftb_unet* U, cudaStream_t st);
+
+int finalize(ftb_unet* U, cudaStream_t st, bool for_train = false) {
+  if (!U->dirty) return (for_train || !U->kshift_stale) ? 0 : finalize_kshift(U, st);
   for (const Param& p : U->params)
     FTB_CHECK(p.set, "parameter '" + p.name + "' was never set");
   for (auto& kv : U->gains) {
@@ -434,8 +449,17 @@ int finalize(ftb_unet* U, cudaStream_t st) {
       FTB_CUDA(cudaMemcpyAsync(cl.bias, U->params[U->pindex[cl.bname]].dev, cl.cout * sizeof(float),
                                cudaMemcpyDeviceToDevice, st));
   }
-  // LinearAttention: shift[d] = 1.02*||W_k[d,:] (x) g*sqrt(C)||_2 bounds |k[d,n]| for every voxel, which
-  // lets the fused k/v-context kernel skip the max pass; only trusted while it is far from underflow
+  FTB_CUDA(cudaGetLastError());
+  U->dirty = false;
+  U->dgrad_dirty = true;
+  U->kshift_stale = true;
+  return for_train ? 0 : finalize_kshift(U, st);
+}
+
+// LinearAttention: shift[d] = 1.02*||W_k[d,:] (x) g*sqrt(C)||_2 bounds |k[d,n]| for every voxel, which
+// lets the fused k/v-context kernel skip the max pass; only trusted while it is far from underflow.
+// (Synchronises the stream once per layer, so the training step, which runs the unfused path, skips it.)
+int finalize_kshift(ftb_unet* U, cudaStream_t st) {
   const int hd = U->cfg.attn_heads * U->cfg.attn_dim_head;
   std::vector<float> hshift(hd);
   for (auto& kv : U->kshift) {
@@ -449,7 +473,7 @@ int finalize(ftb_unet* U, cudaStream_t st) {
     kv.second.ok = mx == mx && mx <= 60.f && hd == 128 && cl.cin_pad <= 128 && getenv("FTB_LINATTN_EXACT") == nullptr;
   }
   FTB_CUDA(cudaGetLastError());
-  U->dirty = false;
+  U->kshift_stale = false;
   return 0;
 }
 
@@ -797,6 +821,7 @@ struct Fwd {
 };
 
 }  // namespace ftb_engine_detail
+#include "engine_train.cuh"
 using namespace ftb_engine_detail;
 
 // ====================================================================== C ABI
@@ -993,6 +1018,152 @@ int ftb_mse_ratio_accumulate(const float* v, const float* vhat, int64_t n, doubl
 
 }  // extern "C"
 
+
+// ---------------------------------------------------------------------- training step
+namespace ftb_engine_detail {
+static void ensure_offsets(ftb_unet* h, TrainState* T) {
+  if (!T->poff.empty()) return;
+  int64_t off = 0;
+  for (const Param& p : h->params) {
+    T->poff.push_back(off);
+    off += p.numel;
+  }
+  T->ptotal = off;
+}
+static size_t max_wt_elems(const ftb_unet* h) {
+  size_t m = 16;
+  for (const auto& kv : h->convs) {
+    const ConvLayer& cl = kv.second;
+    const size_t e = (size_t)cl.cout * cl.cin * cl.k * cl.k * cl.k;
+    if (e > m) m = e;
+  }
+  return m;
+}
+// runs (or, dry, only sizes) forward + backward bookkeeping; returns bytes through *total
+static int train_backward_impl(ftb_unet* h, TrainState* T, TrainCtx& c, const float* dout, float* grads) {
+  c.gmap.clear();
+  c.dout = dout;
+  c.grads = grads;
+  c.dfilm = c.f32((size_t)c.B * h->film_rows);
+  c.dts = c.f32((size_t)c.B * h->time_dim);
+  c.wt_tmp = c.f32(max_wt_elems(h));
+  FTB_TRY(c.zero(c.dfilm, (size_t)c.B * h->film_rows * sizeof(float)));
+  FTB_TRY(c.zero(c.dts, (size_t)c.B * h->time_dim * sizeof(float)));
+  if (!c.dry && h->dgrad_dirty) FTB_TRY(pack_dgrad(h, c.wt_tmp, c.st));
+  for (size_t i = T->tape.size(); i-- > 0;) FTB_TRY(T->tape[i](c));
+  return 0;
+}
+}  // namespace ftb_engine_detail
+
+extern "C" {
+
+int64_t ftb_unet3d_param_offset(ftb_unet* h, int i) {
+  if (!h || i < 0 || i > (int)h->params.size()) return -1;
+  int64_t off = 0;
+  for (int k = 0; k < i; ++k) off += h->params[k].numel;
+  return off;
+}
+
+int ftb_unet3d_bind_params(ftb_unet* h, float* flat, void* stream) {
+  FTB_CHECK(h && flat, "null argument");
+  FTB_TRY(ensure_device(h));
+  int64_t off = 0;
+  for (Param& p : h->params) {
+    p.dev = flat + off;
+    p.set = true;
+    off += p.numel;
+  }
+  // the FiLM table holds parameter pointers
+  const int nb = (int)h->film_blocks.size();
+  std::vector<const float*> hw(nb), hb(nb);
+  for (int i = 0; i < nb; ++i) {
+    hw[i] = h->params[h->pindex[h->film_blocks[i] + ".weight"]].dev;
+    hb[i] = h->params[h->pindex[h->film_blocks[i] + ".bias"]].dev;
+  }
+  FTB_CUDA(cudaMemcpyAsync(h->d_film_w, hw.data(), nb * sizeof(float*), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  FTB_CUDA(cudaMemcpyAsync(h->d_film_b, hb.data(), nb * sizeof(float*), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  FTB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  h->dirty = true;
+  return 0;
+}
+
+int ftb_unet3d_mark_dirty(ftb_unet* h) {
+  FTB_CHECK(h, "null handle");
+  h->dirty = true;
+  return 0;
+}
+
+size_t ftb_unet3d_train_workspace_bytes(ftb_unet* h, int B, int X, int Y, int Z) {
+  if (check_dims(h, B, X, Y, Z) != 0 || h->cfg.conditional) return 0;
+  TrainState T;
+  ensure_offsets(h, &T);
+  TrainCtx c{h, &T, nullptr, reinterpret_cast<char*>(uintptr_t(1) << 40), 0, true, B};
+  TrainFwd f{h, &T, c};
+  if (f.run(nullptr, nullptr, nullptr, X, Y, Z) != 0) return 0;
+  if (train_backward_impl(h, &T, c, nullptr, reinterpret_cast<float*>(uintptr_t(1) << 41)) != 0) return 0;
+  return round_up_sz(c.off, 256) + 256;
+}
+
+int ftb_unet3d_forward_train(ftb_unet* h, const float* x, const float* t, float* out, int B, int X, int Y, int Z,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  FTB_TRY(check_dims(h, B, X, Y, Z));
+  FTB_CHECK(!h->cfg.conditional, "training path: only the unconditional Unet3D is implemented");
+  FTB_CHECK(x && t && out && workspace, "null argument");
+  FTB_CHECK(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  FTB_TRY(ensure_device(h));
+  FTB_TRY(finalize(h, st, true));
+  if (!h->train) h->train = std::make_shared<TrainState>();
+  TrainState* T = h->train.get();
+  ensure_offsets(h, T);
+  T->valid = false;
+  h->train_ctx.reset(new TrainCtx{h, T, st, reinterpret_cast<char*>(workspace), 0, false, B});
+  TrainFwd f{h, T, *h->train_ctx};
+  FTB_TRY(f.run(x, t, out, X, Y, Z));
+  FTB_CHECK(h->train_ctx->off <= workspace_bytes, "training workspace too small for the forward");
+  T->fwd_bytes = h->train_ctx->off;
+  T->B = B; T->X = X; T->Y = Y; T->Z = Z;
+  T->valid = true;
+  (void)workspace_bytes;
+  return 0;
+}
+
+int ftb_unet3d_backward(ftb_unet* h, const float* dout, float* grads, void* workspace, size_t workspace_bytes,
+                        void (*bucket_cb)(void*, int64_t, int64_t), void* cb_user, void* stream) {
+  FTB_CHECK(h && dout && grads && workspace, "null argument");
+  FTB_CHECK(h->train && h->train->valid && h->train_ctx, "backward: no matching forward_train");
+  TrainState* T = h->train.get();
+  TrainCtx& c = *h->train_ctx;
+  FTB_CHECK(c.base == reinterpret_cast<char*>(workspace), "backward: workspace differs from the forward's");
+  const size_t need = ftb_unet3d_train_workspace_bytes(h, T->B, T->X, T->Y, T->Z);
+  FTB_CHECK(need > 0 && workspace_bytes >= need, "training workspace too small: need " + std::to_string(need) + " bytes");
+  c.st = (cudaStream_t)stream;
+  c.off = T->fwd_bytes;
+  c.cb = bucket_cb;
+  c.cb_user = cb_user;
+  T->valid = false;   // one backward per forward
+  return train_backward_impl(h, T, c, dout, grads);
+}
+
+int ftb_mse_ratio_grad(const float* v, const float* vhat, int64_t n, const double* acc2, float scale, float* dout,
+                       void* stream) {
+  FTB_CHECK(v && vhat && acc2 && dout, "null argument");
+  return mse_ratio_grad(v, vhat, n, acc2, scale, dout, (cudaStream_t)stream);
+}
+int ftb_grad_sumsq(const float* g, int64_t n, double* acc, void* stream) {
+  FTB_CHECK(g && acc, "null argument");
+  return grad_sumsq(g, n, acc, (cudaStream_t)stream);
+}
+int ftb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int decoupled, int step, const double* sumsq, float grad_scale,
+                  float max_norm, void* stream) {
+  FTB_CHECK(p && g && m && v && step >= 1, "null argument / step < 1");
+  return adam_step(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, decoupled, step, sumsq, grad_scale, max_norm,
+                   (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
 // ---------------------------------------------------------------- test hooks
 namespace ftb_engine_detail {
 struct Scratch {
@@ -1083,6 +1254,69 @@ int ftb_test_conv3d(const float* x, int c1, const float* x2, int c2, const float
   if (impl == 1) FTB_TRY(conv_naive(s0, s1, cw, e, ao, 0, st));   // impl 2: tcgen05 kernel, cubic (no W-unfold)
   else FTB_TRY(conv_igemm(s0, s1, cw, e, ao, 0, st));
   FTB_TRY(unpack_blocked_to_ncdhw(ao, 0, cout, out, st));
+  FTB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// dw [cout][c1+c2][k^3] = conv3d weight gradient from x (|| x2) and dy (NCDHW fp32, rounded to bf16 inside)
+int ftb_test_conv_wgrad(const float* x, int c1, const float* x2, int c2, const float* dy, int cout, int ksize,
+                        float* dw, int B, int X, int Y, int Z, int unfold, void* stream) {
+  FTB_CHECK(x && dy && dw, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  Scratch S;
+  auto mk = [&](int C) {
+    Act a;
+    a.B = B; a.C = round_up(C, 16); a.D = X; a.H = Y; a.W = Z;
+    a.p = S.get<bf16>(a.elems());
+    return a;
+  };
+  Act a0 = mk(unfold ? ksize * c1 : c1), a1, ady = mk(cout);
+  FTB_CHECK(a0.p && ady.p, "scratch allocation failed");
+  if (unfold) FTB_TRY(pack_unfold_w(x, B, c1, X, Y, Z, ksize, a0, st));
+  else FTB_TRY(pack_ncdhw_to_blocked(x, B, c1, X, Y, Z, a0, st));
+  FTB_TRY(pack_ncdhw_to_blocked(dy, B, cout, X, Y, Z, ady, st));
+  const int cin = c1 + (x2 ? c2 : 0);
+  FTB_CUDA(cudaMemsetAsync(dw, 0, (size_t)cout * cin * ksize * ksize * ksize * sizeof(float), st));
+  FTB_TRY(conv_wgrad(a0, 0, a0.cg(), ady, 0, cout, ksize, unfold ? c1 : 0, dw, cin, 0, c1, 0, st));
+  if (x2) {
+    a1 = mk(c2);
+    FTB_CHECK(a1.p, "scratch allocation failed");
+    FTB_TRY(pack_ncdhw_to_blocked(x2, B, c2, X, Y, Z, a1, st));
+    FTB_TRY(conv_wgrad(a1, 0, a1.cg(), ady, 0, cout, ksize, 0, dw, cin, c1, c2, 0, st));
+  }
+  FTB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// dx [B][cin][...] (+ acc) = conv3d input gradient of dy through w [cout][cin][k^3]: the forward kernel on
+// flipped, transposed weights
+int ftb_test_conv_dgrad(const float* dy, const float* w, int cout, int cin, int ksize, const float* acc, float* dx,
+                        int B, int X, int Y, int Z, void* stream) {
+  FTB_CHECK(dy && w && dx, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  Scratch S;
+  auto mk = [&](int C) {
+    Act a;
+    a.B = B; a.C = round_up(C, 16); a.D = X; a.H = Y; a.W = Z;
+    a.p = S.get<bf16>(a.elems());
+    return a;
+  };
+  Act ady = mk(cout), adx = mk(cin);
+  FTB_CHECK(ady.p && adx.p, "scratch allocation failed");
+  FTB_TRY(pack_ncdhw_to_blocked(dy, B, cout, X, Y, Z, ady, st));
+  if (acc) FTB_TRY(pack_ncdhw_to_blocked(acc, B, cin, X, Y, Z, adx, st));
+  const int k3 = ksize * ksize * ksize, n_tile = round_up(cin, 16), kpad = round_up(cout, 16);
+  float* wt = S.get<float>((size_t)cin * cout * k3);
+  bf16* packed = S.get<bf16>((size_t)k3 * kpad * n_tile);
+  FTB_CHECK(wt && packed, "scratch allocation failed");
+  FTB_TRY(transpose_flip(w, cout, cin, ksize, 0, cin, nullptr, wt, st));
+  FTB_TRY(pack_conv_weights(wt, cin, cout, ksize, kpad, n_tile, 1, nullptr, packed, st));
+  ConvWeights cw;
+  cw.w = packed; cw.ksize = ksize; cw.cin = kpad; cw.n = n_tile; cw.ntiles = 1;
+  ConvEpilogue e;
+  if (acc) e.resid = &adx;
+  FTB_TRY(conv_igemm(ConvSrc{&ady, 0, ady.cg()}, ConvSrc{}, cw, e, adx, 0, st));
+  FTB_TRY(unpack_blocked_to_ncdhw(adx, 0, cin, dx, st));
   FTB_CUDA(cudaStreamSynchronize(st));
   return 0;
 }

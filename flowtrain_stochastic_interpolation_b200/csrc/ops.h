@@ -93,8 +93,9 @@ struct TimeMlpParams {
   const float *freqs, *phases, *w1, *b1, *w2, *b2;  // Fourier + Linear(tr->td) + Linear(td->td)
   int time_res, time_dim;
 };
+// save (optional, training): [B][time_res + 2*time_dim] = Fourier features | pre-GELU | GELU
 int time_embed(const TimeMlpParams& p, const float* t, int B, float* temb, float* temb_silu,
-               cudaStream_t st);
+               cudaStream_t st, float* save = nullptr);
 // all per-block FiLM MLPs in one launch: out[b][off_j + o] = W_j[o,:] . silu(temb[b]) + b_j[o]
 // (first half of each block = scale, emitted as (scale+1)*gs_j; second half = shift)
 struct FilmTable {
@@ -126,10 +127,53 @@ int linattn_q_out(const Act& x, const float* ss, const bf16* wq, const bf16* mb,
 // kmax_bstride: elements between samples of `kmax` (0: one shift vector for the whole batch)
 int linattn_combine(const float* part, int nsplit, const float* kmax, int kmax_bstride, int B, int heads, int dh,
                     const float* mem_kv, int n_mem, const float* w_out, int C, float q_scale,
-                    bf16* wpack_out, float* ctx_dbg, cudaStream_t st);
+                    bf16* wpack_out, float* ctx_dbg, cudaStream_t st, float* kstat = nullptr);
 // softmax attention over n tokens (+ n_mem memory kv), one CTA per (b, head, query tile)
 int full_attention(const Act& qkv, int heads, int dh, const float* mem_kv, int n_mem, Act& out,
                    cudaStream_t st);
+
+// ---------------------------------------------------------------- training step (wgrad.cu, train_ops.cu)
+// dw (fp32 [cout][cin_tot][K][K][K]) += weight gradient of source x (channel groups [x_cgoff, x_cgoff+x_cg)),
+// which feeds the weight's input channels [ci_base, ci_base+ci_real).  unfold_cin > 0: x is the W-unfolded
+// stem input (channel kw*unfold_cin + ci).  dw_bstride != 0: one gradient slab per sample.
+int conv_wgrad(const Act& x, int x_cgoff, int x_cg, const Act& dy, int dy_cgoff, int cout_real, int ksize,
+               int unfold_cin, float* dw, int cin_tot, int ci_base, int ci_real, long long dw_bstride,
+               cudaStream_t st);
+// out = act(n * gain[c] * s1[b][c] + sh[b][c]) + resid, n = u / max(||u||_C, 1e-12) when norm
+int normact_fwd(const Act& u, bool norm, const float* gain, const float* s1, const float* sh, int fstride, bool silu,
+                const Act* resid, Act& out, cudaStream_t st);
+// du (may alias dout); R[b][c] += sum_v dz*n, S[b*sstride + c] += sum_v dz, dbias[c] += sum du (each optional)
+int normact_bwd(const Act& dout, const Act& u, bool norm, const float* gain, const float* s1, const float* sh,
+                int fstride, bool silu, Act& du, float* R, float* S, int sstride, float* dbias, cudaStream_t st);
+int normact_finish(const float* R, int B, int C, const float* gain, const float* s1, int fstride, float sqrt_c,
+                   float* ds1, float* dg, cudaStream_t st);
+int bias_grad(const Act& dy, int cgoff, int C, float* db, cudaStream_t st);
+int act_accum(Act& dst, const Act& src, bool add, cudaStream_t st);
+int trilinear_resample_bwd(const Act& dout, Act& din, bool add, cudaStream_t st);
+int transpose_flip(const float* w, int cout, int cin, int ksize, int ci0, int cin_sub, const float* row_scale,
+                   float* wt, cudaStream_t st);
+int fold_gain_bwd(const float* dwp, const float* w, const float* gs, int cout, int cin, float sqrt_c, float* dw,
+                  float* dg, cudaStream_t st);
+int blockdiag(const float* src, int B, int heads, int dh, bool transpose, float mul, float* out, cudaStream_t st);
+int dctx_extract(const float* full, const float* ctx, int B, int heads, int dh, float* dctx, float* ssum,
+                 cudaStream_t st);
+int ksoftmax_apply(Act& qkv, int hd, const float* kstat, cudaStream_t st);
+int ksoftmax_bwd(Act& dqkv, const Act& qkv, int hd, const float* ssum, cudaStream_t st);
+int qsoftmax_bwd(Act& dqkv, const Act& qkv, int heads, int dh, cudaStream_t st);
+int linattn_mem_bwd(const float* mem_kv, int n_mem, const float* kstat, const float* dctx, const float* ssum, int B,
+                    int heads, int dh, float* dmem, cudaStream_t st);
+int full_attention_bwd(const Act& qkv, const Act& ao, const Act& dao, int heads, int dh, const float* mem_kv,
+                       int n_mem, float* scratch, Act& dqkv, float* dmem, cudaStream_t st);
+int linear_bwd(const float* dy, int dy_stride, const float* x, const float* w, int B, int rows, int cols, float* dw,
+               float* db, float* dx, bool dx_add, cudaStream_t st);
+int act_bwd(float* g, const float* pre, size_t n, int mode, cudaStream_t st);   // 0: SiLU', 1: GELU(erf)'
+int fourier_bwd(const float* dy, const float* t, const float* f, const float* phi, int B, int n, float* df, float* dphi,
+                cudaStream_t st);
+int mse_ratio_grad(const float* v, const float* vhat, long long n, const double* acc2, float gscale, float* dout,
+                   cudaStream_t st);
+int grad_sumsq(const float* g, long long n, double* acc, cudaStream_t st);
+int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+              float wd, int decoupled, int step, const double* sumsq, float gscale, float max_norm, cudaStream_t st);
 
 // ---------------------------------------------------------------- sampler / task kernels (fp32, NCDHW flat)
 int interp_xt_bt(int kind, int one_sided, float gamma_a, const float* x0, const float* x1,

@@ -11,7 +11,7 @@ namespace {
 
 __global__ void __launch_bounds__(1024)
 time_embed_kernel(TimeMlpParams p, const float* __restrict__ t, float* __restrict__ temb,
-                  float* __restrict__ temb_silu) {
+                  float* __restrict__ temb_silu, float* __restrict__ save) {
   extern __shared__ float sm[];
   float* y = sm;                 // [time_res]
   float* h1 = sm + p.time_res;   // [time_dim]
@@ -20,6 +20,7 @@ time_embed_kernel(TimeMlpParams p, const float* __restrict__ t, float* __restric
   for (int i = threadIdx.x; i < p.time_res; i += blockDim.x) {
     const float arg = __fadd_rn(__fmul_rn(tv, __ldg(p.freqs + i)), __ldg(p.phases + i));
     y[i] = __fmul_rn(cosf(arg), 1.41421356237309504880f);
+    if (save) save[(size_t)b * (p.time_res + 2 * p.time_dim) + i] = y[i];   // training: y | pre-GELU | GELU
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -31,6 +32,10 @@ time_embed_kernel(TimeMlpParams p, const float* __restrict__ t, float* __restric
     if (lane == 0) {
       const float v = s + __ldg(p.b1 + r);
       h1[r] = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));  // exact GELU
+      if (save) {
+        save[(size_t)b * (p.time_res + 2 * p.time_dim) + p.time_res + r] = v;
+        save[(size_t)b * (p.time_res + 2 * p.time_dim) + p.time_res + p.time_dim + r] = h1[r];
+      }
     }
   }
   __syncthreads();
@@ -77,10 +82,10 @@ film_kernel(FilmTable ft, const float* __restrict__ x, int B, float* __restrict_
 }  // namespace
 
 int time_embed(const TimeMlpParams& p, const float* t, int B, float* temb, float* temb_silu,
-               cudaStream_t st) {
+               cudaStream_t st, float* save) {
   const size_t smem = (size_t)(p.time_res + p.time_dim) * sizeof(float);
   FTB_CHECK(smem <= 48 * 1024, "time_embed: time_resolution + time_dim too large for shared memory");
-  time_embed_kernel<<<B, 1024, smem, st>>>(p, t, temb, temb_silu);   // 32 warps: the row loops are latency-bound
+  time_embed_kernel<<<B, 1024, smem, st>>>(p, t, temb, temb_silu, save);   // 32 warps: the row loops are latency-bound
   FTB_LAUNCH_OK();
   return 0;
 }

@@ -1,0 +1,299 @@
+"""Training step on the B200 path.
+
+Two entry points, both over the same C-ABI calls (``ftb_unet3d_forward_train`` / ``ftb_unet3d_backward``):
+
+* drop-in autograd: a ``Unet3D`` in ``train()`` mode called with grad enabled behaves like the reference
+  module inside ``Geo3DStochInterp.training_step``
+  (project/geodata-3d-unconditional/model_train_inference.py:417-457): ``loss.backward()`` fills ``p.grad``
+  of every parameter, any torch optimiser / Lightning loop works unchanged.
+* ``FlowTrainer``: the whole step of the reference (embed -> noise -> interpolant -> net -> loss -> backward
+  -> clip_grad_norm_ -> Adam -> EMA, :417-473 and callbacks.py:238-268) as kernels on flat fp32 buffers,
+  with the data-parallel gradient all-reduce (NCCL through ``torch.distributed``) started bucket by bucket
+  from inside the backward, as DDP does.
+
+There is no PyTorch implementation of the math here; without libftb.so / a GPU everything raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import torch
+
+from . import _lib
+
+
+# --------------------------------------------------------------------------- flat parameter storage
+def flatten_parameters(net) -> torch.Tensor:
+    """Move every parameter of ``net`` (a B200 ``Unet3D``) into ONE flat fp32 device buffer in state_dict
+    order and bind the engine to it (no per-step copies).  The ``nn.Parameter`` objects stay the same
+    (optimisers, EMA and checkpoints keep working); their storage becomes a view of the flat buffer."""
+    params = list(net.named_parameters())
+    dev = params[0][1].device
+    if dev.type != "cuda":
+        raise RuntimeError("flatten_parameters: move the module to a CUDA device first (no CPU path)")
+    h = net._handle
+    n = _lib.lib.ftb_unet3d_num_params(h)
+    assert n == len(params)
+    total = _lib.lib.ftb_unet3d_param_offset(h, n)
+    flat = torch.empty(total, dtype=torch.float32, device=dev)
+    offs = []
+    with torch.no_grad():
+        for i, (name, p) in enumerate(params):
+            off = _lib.lib.ftb_unet3d_param_offset(h, i)
+            view = flat[off:off + p.numel()].view(p.shape)
+            view.copy_(p.detach().float())
+            p.data = view
+            offs.append(off)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib.ftb_unet3d_bind_params(h, _lib.ptr(flat), _lib.stream_ptr()))
+    net._flat = flat
+    net._flat_offsets = offs
+    net._flat_versions = None
+    net._synced.clear()
+    net._graphs.clear()
+    return flat
+
+
+def _flat_still_bound(net) -> bool:
+    flat = net._flat
+    base = flat.data_ptr()
+    for (name, p), off in zip(net.named_parameters(), net._flat_offsets):
+        if p.data_ptr() != base + 4 * off or p.dtype != torch.float32:
+            return False
+    return True
+
+
+def sync_flat(net):
+    """Called before a forward when the parameters are flat-bound: a changed version counter (in-place
+    optimiser step, load_state_dict) only needs the packed copies rebuilt."""
+    if not _flat_still_bound(net):
+        flatten_parameters(net)   # someone re-assigned .data (e.g. .to()): re-flatten
+    vers = tuple(p._version for p in net.parameters())
+    if vers != net._flat_versions:
+        _lib.check(_lib.lib.ftb_unet3d_mark_dirty(net._handle))
+        net._flat_versions = vers
+        net._graphs.clear()
+
+
+def train_workspace(net, device, B, X, Y, Z):
+    key = ("train", str(device), B, X, Y, Z)
+    ws = net._workspace.get(key)
+    if ws is None:
+        nbytes = _lib.lib.ftb_unet3d_train_workspace_bytes(net._handle, B, X, Y, Z)
+        if nbytes == 0:
+            raise _lib.FtbError(_lib.last_error() or "training workspace sizing failed")
+        net._workspace.clear()
+        net._graphs.clear()
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+        net._workspace[key] = ws
+    base = (ws.data_ptr() + 255) // 256 * 256
+    return ws, base, ws.numel() - (base - ws.data_ptr())
+
+
+def forward_train(net, xin, tin):
+    """Train-mode forward: keeps the intermediates in the workspace and records the backward."""
+    B, _, X, Y, Z = xin.shape
+    if getattr(net, "_flat", None) is None:
+        flatten_parameters(net)
+    sync_flat(net)
+    ws, base, nbytes = train_workspace(net, xin.device, B, X, Y, Z)
+    out = torch.empty_like(xin)
+    _lib.check(_lib.lib.ftb_unet3d_forward_train(net._handle, _lib.ptr(xin), _lib.ptr(tin), _lib.ptr(out), B, X, Y, Z,
+                                                 C.c_void_p(base), nbytes, _lib.stream_ptr()))
+    return out
+
+
+def backward_into(net, dout, gflat, bucket_cb=None):
+    """Adds the parameter gradients of the last ``forward_train`` into ``gflat`` (flat, state_dict order)."""
+    B, _, X, Y, Z = dout.shape
+    ws, base, nbytes = train_workspace(net, dout.device, B, X, Y, Z)
+    cb = _lib.BUCKET_CB(bucket_cb) if bucket_cb is not None else None
+    _lib.check(_lib.lib.ftb_unet3d_backward(net._handle, _lib.ptr(dout), _lib.ptr(gflat), C.c_void_p(base), nbytes,
+                                            cb if cb is not None else None, None, _lib.stream_ptr()))
+
+
+class UnetTrainFn(torch.autograd.Function):
+    """autograd bridge: forward = ftb_unet3d_forward_train, backward = ftb_unet3d_backward.  The gradient
+    w.r.t. the network INPUT is not computed (the training step never needs it: XT is data)."""
+
+    @staticmethod
+    def forward(ctx, net, x, t, *params):
+        ctx.net = net
+        with torch.cuda.device(x.device):
+            out = forward_train(net, x, t)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        net = ctx.net
+        dout = dout.detach().float().contiguous()
+        gflat = torch.zeros_like(net._flat)
+        with torch.cuda.device(dout.device):
+            backward_into(net, dout, gflat)
+        grads = []
+        for (name, p), off in zip(net.named_parameters(), net._flat_offsets):
+            grads.append(gflat[off:off + p.numel()].view(p.shape) if p.requires_grad else None)
+        return (None, None, None, *grads)
+
+
+# --------------------------------------------------------------------------- fused training step
+class BucketAllReduce:
+    """Starts ``all_reduce(sum)`` of gradient ranges on a side stream as the backward completes them
+    (the engine calls ``__call__(user, offset, count)`` from inside ``ftb_unet3d_backward``), so the
+    NCCL traffic overlaps the rest of the backward like DDP's bucketed reducer.  ``min_elems`` coalesces
+    adjacent ranges.  Works on any backend (gloo on CPU tensors in the tests)."""
+
+    def __init__(self, gflat: torch.Tensor, group=None, min_elems: int = 1 << 20):
+        import torch.distributed as dist
+        self.dist = dist
+        self.gflat = gflat
+        self.group = group
+        self.min_elems = min_elems
+        self.cuda = gflat.is_cuda
+        self.side = torch.cuda.Stream(device=gflat.device) if self.cuda else None
+        self.pending = None     # (lo, hi) contiguous range not yet sent
+        self.works = []
+        self.launched = []      # ranges actually reduced (for tests)
+
+    def _launch(self, lo, hi):
+        view = self.gflat[lo:hi]
+        if self.cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.gflat.device))
+            self.side.wait_event(ev)
+            with torch.cuda.stream(self.side):
+                self.works.append(self.dist.all_reduce(view, group=self.group, async_op=True))
+        else:
+            self.works.append(self.dist.all_reduce(view, group=self.group, async_op=True))
+        self.launched.append((lo, hi))
+
+    def __call__(self, user, offset, count):
+        lo, hi = int(offset), int(offset) + int(count)
+        if self.pending is not None and self.pending[0] == hi:        # ranges arrive back to front
+            self.pending = (lo, self.pending[1])
+        elif self.pending is not None and self.pending[1] == lo:
+            self.pending = (self.pending[0], hi)
+        else:
+            if self.pending is not None:
+                self._launch(*self.pending)
+            self.pending = (lo, hi)
+        if self.pending[1] - self.pending[0] >= self.min_elems:
+            self._launch(*self.pending)
+            self.pending = None
+
+    def finish(self):
+        if self.pending is not None:
+            self._launch(*self.pending)
+            self.pending = None
+        for w in self.works:
+            w.wait()
+        self.works = []
+        if self.cuda:
+            torch.cuda.current_stream(self.gflat.device).wait_stream(self.side)
+
+
+class FlowTrainer:
+    """One optimiser step of ``Geo3DStochInterp`` (training_step :417-457, configure_optimizers :465-473,
+    Lightning's ``gradient_clip_val``, EMACallback.on_train_batch_end callbacks.py:238-268) entirely in
+    kernels: no autograd graph, flat fp32 parameter / gradient / Adam-moment / EMA buffers.
+
+    ``module`` is the B200 ``Geo3DStochInterp``.  Data parallelism: one process per GPU, identical initial
+    weights (``broadcast_parameters``), per-rank batches; gradients are summed with NCCL bucket by bucket
+    while the backward is still running and scaled by 1/world inside the Adam kernel."""
+
+    def __init__(self, module, lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False,
+                 max_grad_norm: Optional[float] = 1.0, ema_decay: Optional[float] = 0.9995, ema_start_step=0,
+                 lr_decay: Optional[float] = None, process_group=None, distributed: Optional[bool] = None):
+        import torch.distributed as dist
+        self.module = module
+        self.net = module.net
+        if self.net.dropout_p != 0.0:
+            raise NotImplementedError("FlowTrainer: dropout > 0 is not implemented on the B200 training path")
+        self.flat = flatten_parameters(self.net)
+        self.gflat = torch.zeros_like(self.flat)
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.lr, self.betas, self.eps = float(lr), betas, float(eps)
+        self.weight_decay, self.decoupled = float(weight_decay), bool(decoupled)
+        self.max_grad_norm = float(max_grad_norm) if max_grad_norm else 0.0
+        self.ema_decay, self.ema_start_step = ema_decay, ema_start_step
+        self.ema_flat = None
+        self.lr_decay = lr_decay
+        self.step_count = 0
+        self.group = process_group
+        self.distributed = dist.is_available() and dist.is_initialized() if distributed is None else distributed
+        self.world = dist.get_world_size(process_group) if self.distributed else 1
+        self.sumsq = torch.zeros(1, dtype=torch.float64, device=self.flat.device)
+        self.acc = torch.zeros(2, dtype=torch.float64, device=self.flat.device)
+        self.last_grad_norm = None
+        # parameters the reference keeps frozen get a zero gradient (freqs / phases when not learned)
+        self.frozen = [(off, p.numel()) for (n, p), off in zip(self.net.named_parameters(), self.net._flat_offsets)
+                       if not p.requires_grad]
+
+    def broadcast_parameters(self, src=0):
+        if self.distributed:
+            import torch.distributed as dist
+            dist.broadcast(self.flat, src=src, group=self.group)
+            _lib.check(_lib.lib.ftb_unet3d_mark_dirty(self.net._handle))
+
+    def step(self, batch, noise1=None, X0=None, T=None):
+        """batch: [B,1,X,Y,Z] integer categories.  Returns the (per-rank) loss as a 0-d device tensor."""
+        mod, net, lib = self.module, self.net, _lib.lib
+        dev = self.flat.device
+        with torch.cuda.device(dev), torch.no_grad():
+            st = _lib.stream_ptr()
+            X1 = mod.embed(batch)                                            # :428
+            if noise1 is None:
+                noise1 = torch.randn_like(X1)
+            _lib.check(lib.ftb_ode_axpy(_lib.ptr(X1), _lib.ptr(X1), _lib.ptr(noise1), 1e-3, X1.numel(), None, 1, st))  # :429
+            if X0 is None:
+                X0 = torch.randn_like(X1)                                    # :431
+            if T is None:
+                T = torch.empty(X1.size(0), device=dev).uniform_(mod.time_range[0], mod.time_range[1])  # :434-436
+            XT, VT = mod.interpolator.flow_objective(T, X0, X1)              # :439
+            XT = XT.contiguous()
+            VT = VT.contiguous()
+            Tin = T.to(device=dev, dtype=torch.float32).contiguous()
+            vhat = forward_train(net, XT, Tin)                               # :440
+            self.acc.zero_()
+            _lib.check(lib.ftb_mse_ratio_accumulate(_lib.ptr(VT), _lib.ptr(vhat), VT.numel(), _lib.ptr(self.acc), st))  # :443
+            dout = torch.empty_like(vhat)
+            _lib.check(lib.ftb_mse_ratio_grad(_lib.ptr(VT), _lib.ptr(vhat), VT.numel(), _lib.ptr(self.acc), 1.0,
+                                              _lib.ptr(dout), st))
+            self.gflat.zero_()
+            reducer = BucketAllReduce(self.gflat, self.group) if self.world > 1 else None
+            backward_into(net, dout, self.gflat, reducer)
+            if reducer is not None:
+                reducer.finish()
+            for off, n in self.frozen:
+                self.gflat[off:off + n].zero_()
+            self.step_count += 1
+            self.sumsq.zero_()
+            _lib.check(lib.ftb_grad_sumsq(_lib.ptr(self.gflat), self.gflat.numel(), _lib.ptr(self.sumsq), st))
+            _lib.check(lib.ftb_adam_step(_lib.ptr(self.flat), _lib.ptr(self.gflat), _lib.ptr(self.m), _lib.ptr(self.v),
+                                         self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
+                                         self.weight_decay, 1 if self.decoupled else 0, self.step_count,
+                                         _lib.ptr(self.sumsq), 1.0 / self.world, self.max_grad_norm, st))
+            _lib.check(lib.ftb_unet3d_mark_dirty(net._handle))
+            net._flat_versions = None
+            if self.ema_decay is not None and self.step_count >= self.ema_start_step:   # callbacks.py:243-266
+                if self.ema_flat is None:
+                    self.ema_flat = self.flat.clone()
+                else:
+                    _lib.check(lib.ftb_ema_update(_lib.ptr(self.ema_flat), _lib.ptr(self.flat), self.flat.numel(),
+                                                  float(self.ema_decay), st))
+            self.last_grad_norm = self.sumsq   # squared norm of the summed gradient (device)
+            return (self.acc[0] / self.acc[1]).float()
+
+    def epoch_end(self):
+        """ExponentialLR(gamma=lr_decay) per epoch (:465-473)."""
+        if self.lr_decay:
+            self.lr *= self.lr_decay
+
+    def ema_state_dict(self):
+        """EMA shadow under the parameter names (checkpoint['ema_shadow'], callbacks.py:295-317)."""
+        if self.ema_flat is None:
+            return {}
+        return {n: self.ema_flat[off:off + p.numel()].view(p.shape).clone()
+                for (n, p), off in zip(self.net.named_parameters(), self.net._flat_offsets) if p.requires_grad}

@@ -112,6 +112,7 @@ class Unet3D(nn.Module):
         self._graphs = {}      # (device, B, X, Y, Z) -> (CUDAGraph, static x, static t, static out)
         self._use_graph = False
         self.last_launches = 0
+        self._flat = None      # flat fp32 parameter buffer once training.flatten_parameters() bound it
 
     # ------------------------------------------------------------------ parameter tree
     def _plan(self):
@@ -169,6 +170,10 @@ class Unet3D(nn.Module):
 
     # ------------------------------------------------------------------ engine plumbing
     def _sync_params(self, device):
+        if self._flat is not None:      # parameters live in the flat buffer the engine is bound to
+            from .training import sync_flat
+            sync_flat(self)
+            return
         st = _lib.stream_ptr()
         for name, p in self.named_parameters():
             if p.device != device:
@@ -203,11 +208,14 @@ class Unet3D(nn.Module):
         if not x.is_cuda:
             raise RuntimeError(f"flowtrain_stochastic_interpolation_b200.{type(self).__name__} runs on CUDA "
                                "(sm_100a) only; there is no CPU fallback")
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            if x.requires_grad or self.training:
-                raise NotImplementedError(
-                    "backward through the B200 UNet is not implemented yet (sampling / no_grad only); "
-                    "wrap the call in torch.no_grad()")
+        if self._needs_grad(x):
+            if x.requires_grad:
+                raise NotImplementedError("the gradient w.r.t. the network input is not computed on the B200 path")
+            if self._conditional:
+                raise NotImplementedError("backward through Unet3DCond is not implemented (sampling / no_grad only)")
+            if self.dropout_p != 0.0:
+                raise NotImplementedError("training with dropout > 0 is not implemented on the B200 path "
+                                          "(construct the module with dropout=0.0)")
         if x.dim() != 5 or x.shape[1] != self.channels:
             raise ValueError(f"expected x of shape [B,{self.channels},X,Y,Z], got {tuple(x.shape)}")
         B, _, X, Y, Z = x.shape
@@ -268,9 +276,21 @@ class Unet3D(nn.Module):
         self.last_launches = _lib.lib.ftb_unet3d_last_launches(self._handle)
         return out
 
+    def _needs_grad(self, x):
+        return torch.is_grad_enabled() and self.training and (
+            x.requires_grad or any(p.requires_grad for p in self.parameters()))
+
     def forward(self, x, time, x_self_cond=None):
         self._check_inputs(x, time, x_self_cond)
         B, _, X, Y, Z = x.shape
+        if self._needs_grad(x):
+            # training step (model_train_inference.py:440): forward with saved activations, autograd bridge
+            from .training import UnetTrainFn, flatten_parameters
+            if self._flat is None:
+                flatten_parameters(self)
+            xin = self._f32c(x)
+            tin = time.detach().to(device=x.device, dtype=torch.float32).contiguous()
+            return UnetTrainFn.apply(self, xin, tin, *self.parameters())
         if self._use_graph and not self._conditional:
             with torch.cuda.device(x.device):
                 xin = self._f32c(x)

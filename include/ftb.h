@@ -121,6 +121,39 @@ int ftb_ema_update(float* shadow, const float* param, int64_t n, double decay, v
 /* acc2[0] += sum (v-vhat)^2, acc2[1] += sum v^2 (device doubles; loss = acc2[0]/acc2[1]) */
 int ftb_mse_ratio_accumulate(const float* v, const float* vhat, int64_t n, double* acc2, void* stream);
 
+/* ---- training step: replaces autograd through Unet3D.forward inside Geo3DStochInterp.training_step
+ *      (project/geodata-3d-unconditional/model_train_inference.py:417-457) and the optimiser of
+ *      configure_optimizers (:465-473).  Unconditional model, dropout 0.
+ * Parameters may live in ONE caller-owned flat fp32 buffer in state_dict order (bind_params; offsets
+ * from param_offset, param_offset(h, num_params) = total); after changing it (optimiser step) call
+ * mark_dirty so the packed copies are rebuilt before the next forward.
+ * forward_train keeps every intermediate in the workspace and records the backward; backward (once per
+ * forward_train, same workspace) ADDS the parameter gradients into grads_flat (state_dict order, fp32).
+ * bucket_cb(user, offset, count), optional, is called on the host right after the launches that complete
+ * the gradient range [offset, offset+count) were enqueued, last layers first, so a data-parallel caller
+ * can start an all-reduce of that range while the rest of the backward runs (DDP-style overlap). */
+int64_t ftb_unet3d_param_offset(ftb_unet* h, int i);
+int ftb_unet3d_bind_params(ftb_unet* h, float* flat_params, void* stream);
+int ftb_unet3d_mark_dirty(ftb_unet* h);
+size_t ftb_unet3d_train_workspace_bytes(ftb_unet* h, int B, int X, int Y, int Z);
+int ftb_unet3d_forward_train(ftb_unet* h, const float* x, const float* t, float* out, int B, int X, int Y, int Z,
+                             void* workspace, size_t workspace_bytes, void* stream);
+int ftb_unet3d_backward(ftb_unet* h, const float* dout, float* grads_flat, void* workspace, size_t workspace_bytes,
+                        void (*bucket_cb)(void* user, int64_t offset, int64_t count), void* cb_user, void* stream);
+/* gradient of the flow loss (model_train_inference.py:443) w.r.t. vhat, from the sums ftb_mse_ratio_accumulate
+ * produced: dout = scale * 2 (vhat - v) / acc2[1] */
+int ftb_mse_ratio_grad(const float* v, const float* vhat, int64_t n, const double* acc2, float scale, float* dout,
+                       void* stream);
+/* acc[0] += sum g^2 (device double) */
+int ftb_grad_sumsq(const float* g, int64_t n, double* acc, void* stream);
+/* torch.nn.utils.clip_grad_norm_(max_norm) + torch.optim.Adam (decoupled = 0, weight_decay as L2) or AdamW
+ * (decoupled = 1) on flat buffers.  The gradient is first multiplied by grad_scale (1/world_size after a
+ * sum all-reduce); sumsq (device double, may be NULL) is the squared norm of the UNSCALED gradient and
+ * max_norm <= 0 disables clipping.  step counts from 1. */
+int ftb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int decoupled, int step, const double* sumsq, float grad_scale,
+                  float max_norm, void* stream);
+
 /* ---- single-op test hooks (allocate scratch internally; not for hot paths) */
 /* conv3d "same", stride 1, on NCDHW fp32 tensors through the blocked bf16 kernels.
  * impl: 0 = tcgen05 implicit GEMM, 1 = direct CUDA-core kernel.  x2/resid/bias/g/scale/shift may
@@ -130,6 +163,11 @@ int ftb_test_conv3d(const float* x, int c1, const float* x2, int c2, const float
                     int cout, int ksize, const float* g, const float* scale, const float* shift,
                     const float* resid, int flags, float* out, int B, int X, int Y, int Z, int impl,
                     void* stream);
+/* conv3d weight / input gradients through the tcgen05 kernels (operands rounded to bf16 inside) */
+int ftb_test_conv_wgrad(const float* x, int c1, const float* x2, int c2, const float* dy, int cout, int ksize,
+                        float* dw, int B, int X, int Y, int Z, int unfold, void* stream);
+int ftb_test_conv_dgrad(const float* dy, const float* w, int cout, int cin, int ksize, const float* acc, float* dx,
+                        int B, int X, int Y, int Z, void* stream);
 int ftb_test_trilinear(const float* x, int B, int C, int X, int Y, int Z, int Xo, int Yo, int Zo,
                        float* out, void* stream);
 

@@ -90,6 +90,29 @@ def training_step_loss(net, weight, batch, noise1, X0, T, kind="linear", one_sid
     return flow_loss(VT, VT_hat), (XT, VT, VT_hat)
 
 
+def training_grads(params, cfg, XT, T, VT):
+    """Autograd gradients of the training-step loss (:440-443) w.r.t. every parameter of the functional
+    oracle Unet3D (oracle/unet3d.py), dropout 0.  Returns (loss, vhat, {name: grad})."""
+    from . import unet3d
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+    vhat = unet3d.unet3d_forward(p, cfg, XT, T)
+    loss = flow_loss(VT, vhat)
+    names = list(p.keys())
+    grads = torch.autograd.grad(loss, [p[k] for k in names], allow_unused=True)
+    return loss.detach(), vhat.detach(), {k: (g if g is not None else torch.zeros_like(p[k])) for k, g in zip(names, grads)}
+
+
+def adam_reference(p, g, m, v, step, lr=2e-4, b1=0.9, b2=0.999, eps=1e-8, max_norm=1.0, total_norm=None):
+    """clip_grad_norm_(max_norm) + one torch.optim.Adam step (configure_optimizers :465-473, Lightning
+    gradient_clip_val), restated on flat tensors.  Returns (p, m, v)."""
+    if max_norm and total_norm is not None:
+        g = g * min(1.0, max_norm / (float(total_norm) + 1e-6))
+    m = b1 * m + (1 - b1) * g
+    v = b2 * v + (1 - b2) * g * g
+    denom = v.sqrt() / (1 - b2 ** step) ** 0.5 + eps
+    return p - (lr / (1 - b1 ** step)) * m / denom, m, v
+
+
 def ema_update(shadow: torch.Tensor, param: torch.Tensor, decay: float) -> torch.Tensor:
     """EMACallback.on_train_batch_end :263-266 — shadow = a*shadow + (1-a)*param."""
     return decay * shadow + (1.0 - decay) * param

@@ -57,6 +57,41 @@ def gen_unet():
     np.savez_compressed(os.path.join(OUT, "unet3d_small_seed3.npz"), y=y.numpy(), t=t.numpy())
 
 
+TRAIN_CFGS = {
+    # name -> (cfg overrides, param seed, input shape)
+    "small": (dict(dim=32, dim_mults=(1, 2), data_channels=18, time_resolution=64, time_bandwidth=100.0,
+                   attn_heads=2, attn_dim_head=16), 3, (2, 18, 16, 16, 16)),
+    "full": (dict(), 0, (1, 18, 16, 16, 16)),
+}
+# parameters whose complete gradient is stored (the others: L2 norm + 16 sampled entries)
+TRAIN_FULL_GRADS = ("init_conv.bias", "time_mlp.0.freqs", "time_mlp.3.bias", "downs.0.2.mem_kv", "mid_attn.mem_kv",
+                    "downs.0.0.block1.norm.g", "downs.0.2.norm.g", "final_conv.weight", "final_conv.bias")
+
+
+def gen_train():
+    """Gradients of the training-step loss (model_train_inference.py:443, mse(V, Vhat)/mse(V, 0)) through the
+    REFERENCE Unet3D (autograd), dropout 0, for fixed XT / T / VT."""
+    for name, (over, pseed, shape) in TRAIN_CFGS.items():
+        cfg = synth.make_cfg(**over)
+        p = synth.synth_unet3d_params(cfg, pseed)
+        m = ref_loader.build_reference_unet(cfg, p)   # eval(): dropout is the identity (p = 0 parity runs)
+        xt = synth.synth_input(shape, 11, "xt")
+        vt = synth.synth_input(shape, 12, "vt")
+        t = synth.synth_times(shape[0], 13)
+        vhat = m(xt, t)
+        loss = task.flow_loss(vt, vhat)
+        loss.backward()
+        out = {"loss": np.float64(loss.item()), "t": t.numpy(), "vhat": vhat.detach().numpy()}
+        for k, prm in m.named_parameters():
+            g = prm.grad.detach().reshape(-1)
+            out[f"norm/{k}"] = np.float64(g.double().norm().item())
+            idx = torch.linspace(0, g.numel() - 1, min(16, g.numel())).long()
+            out[f"sample/{k}"] = g[idx].numpy()
+            if k in TRAIN_FULL_GRADS:
+                out[f"full/{k}"] = prm.grad.detach().numpy()
+        np.savez_compressed(os.path.join(OUT, f"train_{name}.npz"), **out)
+
+
 def gen_unet_cond():
     """Unet3DCond v3 (the conditional project's model: 15-d embedding, mults 1,2,2,3,4)."""
     cfg = synth.make_cfg(data_channels=15)
@@ -166,10 +201,14 @@ def gen_decode():
 if __name__ == "__main__":
     assert ref_loader.available(), "reference tree not found"
     torch.set_num_threads(os.cpu_count())
+    if len(sys.argv) > 1 and sys.argv[1] == "train":   # only the training fixtures
+        gen_train()
+        sys.exit(0)
     gen_interp()
     gen_solvers()
     gen_decode()
     gen_unet()
     gen_unet_cond()
+    gen_train()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

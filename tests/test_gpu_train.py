@@ -1,0 +1,341 @@
+"""GPU parity tests of the training step (run with ``-m gpu`` on the B200 box): weight / data gradients of
+the tcgen05 conv kernels against fp64 autograd, the parameter gradients of the whole Unet3D against the
+oracle's autograd (pinned to the reference by tests/test_oracle_golden.py) and the committed reference
+goldens, the fused clip + Adam + EMA kernels against their torch restatement.
+
+Tolerances: single conv gradient with bf16-rounded operands <= 6e-3 rel-L2 (same bar as the forward conv);
+whole-network parameter gradients in bf16 <= 5e-2 rel-L2 per tensor and <= 3e-2 over all parameters
+(the bf16 velocity field itself is allowed 2e-2, north_star); optimiser kernels <= 1e-6.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BAR_CONV = 6e-3
+BAR_GRAD_TENSOR = 5e-2
+BAR_GRAD_ALL = 3e-2
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def ftb():
+    assert torch.cuda.is_available(), "-m gpu tests need a B200"
+    import flowtrain_stochastic_interpolation_b200 as m
+    return m
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def _golden(name):
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", name))
+
+
+bf = lambda t: t.to(torch.bfloat16).float()
+
+
+# ------------------------------------------------------------------ conv weight gradient (wgrad.cu)
+def wgrad_case(B, c1, c2, cout, k, dims, unfold=0, seed=0):
+    import torch.nn.functional as F
+    from flowtrain_stochastic_interpolation_b200 import _lib
+    dev = torch.device("cuda")
+    g = torch.Generator("cpu").manual_seed(seed)
+    X, Y, Z = dims
+    x = bf(torch.randn(B, c1, X, Y, Z, generator=g)).to(dev)
+    x2 = bf(torch.randn(B, c2, X, Y, Z, generator=g)).to(dev) if c2 else None
+    dy = bf(torch.randn(B, cout, X, Y, Z, generator=g)).to(dev)
+    cin = c1 + c2
+    xin = x if x2 is None else torch.cat((x, x2), 1)
+    w = torch.zeros(cout, cin, k, k, k, dtype=torch.float64, device=dev, requires_grad=True)
+    y = F.conv3d(xin.double(), w, None, padding=k // 2)
+    (ref,) = torch.autograd.grad(y, w, dy.double())
+    dw = torch.full((cout, cin, k, k, k), float("nan"), device=dev)
+    _lib.check(_lib.lib.ftb_test_conv_wgrad(_lib.ptr(x), c1, _lib.ptr(x2), c2, _lib.ptr(dy), cout, k, _lib.ptr(dw),
+                                            B, X, Y, Z, unfold, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert not torch.isnan(dw).any()
+    return rel(dw, ref)
+
+
+WGRAD_CASES = [
+    dict(B=1, c1=48, c2=0, cout=48, k=3, dims=(4, 16, 16)),
+    dict(B=2, c1=48, c2=0, cout=48, k=3, dims=(16, 32, 32)),
+    dict(B=1, c1=48, c2=48, cout=48, k=3, dims=(8, 32, 16)),
+    dict(B=1, c1=96, c2=0, cout=96, k=3, dims=(8, 16, 16)),
+    dict(B=1, c1=144, c2=96, cout=144, k=3, dims=(4, 4, 4)),
+    dict(B=2, c1=192, c2=144, cout=192, k=3, dims=(4, 4, 4)),
+    dict(B=1, c1=144, c2=0, cout=192, k=3, dims=(2, 2, 2)),
+    dict(B=1, c1=32, c2=0, cout=64, k=3, dims=(8, 8, 8)),
+    dict(B=2, c1=18, c2=0, cout=48, k=7, dims=(16, 16, 16), unfold=1),
+    dict(B=1, c1=18, c2=0, cout=32, k=7, dims=(8, 8, 24), unfold=1),
+    dict(B=1, c1=48, c2=0, cout=384, k=1, dims=(8, 16, 16)),
+    dict(B=1, c1=48, c2=0, cout=18, k=1, dims=(8, 16, 16)),
+    dict(B=1, c1=96, c2=48, cout=48, k=1, dims=(4, 8, 8)),
+    dict(B=1, c1=128, c2=0, cout=128, k=1, dims=(8, 8, 8)),
+    dict(B=1, c1=48, c2=0, cout=48, k=3, dims=(3, 5, 7)),        # ragged
+    dict(B=3, c1=48, c2=0, cout=96, k=3, dims=(5, 20, 12)),
+    dict(B=1, c1=48, c2=0, cout=48, k=5, dims=(8, 8, 8)),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()).replace(" ", ""))
+def test_conv_wgrad_vs_autograd(ftb, case):
+    assert wgrad_case(**case) <= BAR_CONV
+
+
+def test_conv_wgrad_unstacked_layout(ftb, monkeypatch):
+    """FTB_WGRAD_NOSTACK=1: natural [cg][h][w] halo layout, one MMA per (kh, kw) tap."""
+    monkeypatch.setenv("FTB_WGRAD_NOSTACK", "1")
+    assert wgrad_case(B=1, c1=48, c2=0, cout=48, k=3, dims=(4, 16, 16)) <= BAR_CONV
+    assert wgrad_case(B=1, c1=96, c2=0, cout=96, k=3, dims=(8, 16, 16)) <= BAR_CONV
+
+
+# ------------------------------------------------------------------ conv data gradient (forward kernel, flipped W^T)
+def dgrad_case(B, cin, cout, k, dims, acc=False, seed=0):
+    import torch.nn.functional as F
+    from flowtrain_stochastic_interpolation_b200 import _lib
+    dev = torch.device("cuda")
+    g = torch.Generator("cpu").manual_seed(seed)
+    X, Y, Z = dims
+    dy = bf(torch.randn(B, cout, X, Y, Z, generator=g)).to(dev)
+    w = bf(torch.randn(cout, cin, k, k, k, generator=g) / (cout * k ** 3) ** 0.5).to(dev)
+    a = bf(torch.randn(B, cin, X, Y, Z, generator=g)).to(dev) if acc else None
+    x = torch.zeros(B, cin, X, Y, Z, dtype=torch.float64, device=dev, requires_grad=True)
+    y = F.conv3d(x, w.double(), None, padding=k // 2)
+    (ref,) = torch.autograd.grad(y, x, dy.double())
+    if acc:
+        ref = ref + a.double()
+    dx = torch.full((B, cin, X, Y, Z), float("nan"), device=dev)
+    _lib.check(_lib.lib.ftb_test_conv_dgrad(_lib.ptr(dy), _lib.ptr(w), cout, cin, k, _lib.ptr(a), _lib.ptr(dx),
+                                            B, X, Y, Z, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert not torch.isnan(dx).any()
+    return rel(dx, ref)
+
+
+@pytest.mark.parametrize("case", [
+    dict(B=1, cin=48, cout=48, k=3, dims=(8, 16, 16)),
+    dict(B=2, cin=96, cout=48, k=3, dims=(8, 16, 16), acc=True),
+    dict(B=1, cin=48, cout=384, k=1, dims=(8, 16, 16)),
+    dict(B=1, cin=48, cout=18, k=1, dims=(4, 8, 8), acc=True),
+    dict(B=1, cin=144, cout=192, k=3, dims=(4, 4, 4)),
+], ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()).replace(" ", ""))
+def test_conv_dgrad_vs_autograd(ftb, case):
+    assert dgrad_case(**case) <= BAR_CONV
+
+
+# ------------------------------------------------------------------ whole-network gradients
+def _setup(ftb, dev, name):
+    import importlib.util
+    from oracle import synth
+    gd = os.path.join(os.path.dirname(__file__), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(gd, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    over, pseed, shape = mg.TRAIN_CFGS[name]
+    cfg = synth.make_cfg(**over)
+    cfg["dropout"] = 0.0
+    params = synth.synth_unet3d_params(cfg, pseed)
+    net = ftb.Unet3D(**cfg).to(dev)
+    net.load_state_dict(params)
+    return cfg, params, net, shape, mg
+
+
+def _unet_grads(ftb, dev, name, shape=None):
+    from flowtrain_stochastic_interpolation_b200 import training
+    from oracle import synth, task
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg, params, net, gshape, mg = _setup(ftb, dev, name)
+    shape = shape or gshape
+    xt = synth.synth_input(shape, 11, "xt").to(dev)
+    vt = synth.synth_input(shape, 12, "vt").to(dev)
+    t = synth.synth_times(shape[0], 13).to(dev)
+    # oracle autograd on the same GPU, fp32, TF32 off
+    loss_o, vhat_o, grads_o = task.training_grads({k: v.to(dev) for k, v in params.items()}, cfg, xt, t, vt)
+    # product: train forward, loss gradient kernel, backward
+    net.train()
+    vhat = net(xt, t)
+    loss = ftb.flow_loss(vt, vhat.detach())
+    lo = torch.nn.functional.mse_loss(vt, vhat) / torch.nn.functional.mse_loss(vt, torch.zeros_like(vt))
+    lo.backward()   # torch only differentiates the scalar loss; the network backward is ftb_unet3d_backward
+    got = {k: p.grad.detach() for k, p in net.named_parameters()}
+    return cfg, loss_o, vhat_o, grads_o, loss, vhat.detach(), got, mg
+
+
+def _check_grads(grads_o, got, label):
+    num = den = 0.0
+    worst = ("", 0.0)
+    total = sum(float(g.double().norm() ** 2) for g in grads_o.values()) ** 0.5
+    for k, want in grads_o.items():
+        e = rel(got[k], want)
+        n = float(want.double().norm())
+        num += float((got[k].double().cpu() - want.double().cpu()).norm() ** 2)
+        den += n ** 2
+        if n > 1e-3 * total / len(grads_o) ** 0.5 and e > worst[1]:
+            worst = (k, e)
+        if n > 1e-3 * total / len(grads_o) ** 0.5:   # tensors carrying a non-negligible share of the gradient
+            assert e <= BAR_GRAD_TENSOR, f"{label}: grad {k}: rel-L2 {e:.3e} (norm {n:.3e})"
+    allrel = (num / den) ** 0.5
+    print(f"{label}: all-parameter grad rel-L2 {allrel:.3e}; worst tensor {worst[0]} {worst[1]:.3e}")
+    assert allrel <= BAR_GRAD_ALL
+    return allrel
+
+
+def test_unet3d_small_arch_grads_vs_oracle(ftb, dev):
+    cfg, loss_o, vhat_o, grads_o, loss, vhat, got, mg = _unet_grads(ftb, dev, "small")
+    assert rel(vhat, vhat_o) <= 2e-2
+    assert abs(loss.item() - loss_o.item()) <= 2e-2 * abs(loss_o.item())
+    _check_grads(grads_o, got, "small arch 16^3")
+    g = _golden("train_small.npz")   # and the REFERENCE's autograd (committed fixture)
+    for k in mg.TRAIN_FULL_GRADS:
+        assert rel(got[k], g[f"full/{k}"]) <= BAR_GRAD_TENSOR, k
+
+
+def test_unet3d_full_arch_grads_vs_oracle_and_golden(ftb, dev):
+    cfg, loss_o, vhat_o, grads_o, loss, vhat, got, mg = _unet_grads(ftb, dev, "full")
+    assert rel(vhat, vhat_o) <= 2e-2
+    _check_grads(grads_o, got, "full arch 16^3")
+    g = _golden("train_full.npz")
+    assert rel(vhat, g["vhat"]) <= 2e-2
+    for k in mg.TRAIN_FULL_GRADS:
+        assert rel(got[k], g[f"full/{k}"]) <= BAR_GRAD_TENSOR, k
+    for k, gr in got.items():
+        want = float(g[f"norm/{k}"])
+        if want > 1e-6:
+            assert abs(float(gr.double().norm()) - want) <= 5e-2 * want, k
+
+
+def test_unet3d_full_arch_grads_32_batch2(ftb, dev):
+    """Larger volume, batch 2 (multi-tile wgrad splits, linear attention at 32^3 / 16^3 / 8^3)."""
+    cfg, loss_o, vhat_o, grads_o, loss, vhat, got, mg = _unet_grads(ftb, dev, "full", shape=(2, 18, 32, 32, 32))
+    assert rel(vhat, vhat_o) <= 2e-2
+    _check_grads(grads_o, got, "full arch 32^3 B=2")
+
+
+def test_train_forward_matches_inference_forward(ftb, dev):
+    """The unfused train-mode forward and the fused inference forward are the same function."""
+    cfg, params, net, shape, mg = _setup(ftb, dev, "full")
+    from oracle import synth
+    x = synth.synth_input(shape, 5).to(dev)
+    t = synth.synth_times(shape[0], 6).to(dev)
+    net.eval()
+    with torch.no_grad():
+        y_inf = net(x, t)
+    net.train()
+    y_tr = net(x, t).detach()
+    net.eval()
+    with torch.no_grad():
+        y_inf2 = net(x, t)   # flat-bound parameters now; same result
+    assert rel(y_tr, y_inf) <= 1e-2
+    assert torch.equal(y_inf, y_inf2)
+
+
+# ------------------------------------------------------------------ optimiser kernels + fused step
+def test_adam_clip_ema_kernels_vs_torch(ftb, dev):
+    from flowtrain_stochastic_interpolation_b200 import _lib
+    from oracle import task
+    g = torch.Generator("cpu").manual_seed(1)
+    n = 1_000_003
+    p = torch.randn(n, generator=g)
+    m = torch.zeros(n)
+    v = torch.zeros(n)
+    pd, md, vd = p.to(dev), m.to(dev), v.to(dev)
+    ss = torch.zeros(1, dtype=torch.float64, device=dev)
+    for step in range(1, 4):
+        gr = torch.randn(n, generator=g) * (0.01 if step == 2 else 3.0)   # step 2: norm < max_norm, no clipping
+        gd = gr.to(dev)
+        ss.zero_()
+        _lib.check(_lib.lib.ftb_grad_sumsq(_lib.ptr(gd), n, _lib.ptr(ss), _lib.stream_ptr()))
+        _lib.check(_lib.lib.ftb_adam_step(_lib.ptr(pd), _lib.ptr(gd), _lib.ptr(md), _lib.ptr(vd), n, 2e-4, 0.9, 0.999,
+                                          1e-8, 0.0, 0, step, _lib.ptr(ss), 1.0, 1.0, _lib.stream_ptr()))
+        tn = gr.double().norm().item()
+        assert abs(ss.item() ** 0.5 - tn) <= 1e-9 * tn
+        p, m, v = task.adam_reference(p, gr, m, v, step, total_norm=tn)
+        assert torch.allclose(pd.cpu(), p, rtol=1e-5, atol=1e-7)
+        assert torch.allclose(md.cpu(), m, rtol=1e-5, atol=1e-9)
+    # AdamW, world-size scaling of a summed gradient
+    p2 = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([p2], lr=1e-3, weight_decay=0.01)
+    gr = torch.randn(n, generator=g)
+    p2.grad = gr.clone()
+    opt.step()
+    pd2, md2, vd2 = p.to(dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    gd = (gr * 4).to(dev)   # "sum over 4 ranks"
+    _lib.check(_lib.lib.ftb_adam_step(_lib.ptr(pd2), _lib.ptr(gd), _lib.ptr(md2), _lib.ptr(vd2), n, 1e-3, 0.9, 0.999,
+                                      1e-8, 0.01, 1, 1, None, 0.25, 0.0, _lib.stream_ptr()))
+    assert torch.allclose(pd2.cpu(), p2.detach(), rtol=1e-5, atol=1e-7)
+
+
+def test_flow_trainer_step_vs_oracle(ftb, dev):
+    """FlowTrainer.step == training_step + clip + Adam + EMA of the reference, on fixed draws: the loss, the
+    gradient the optimiser saw, and the parameter update given that gradient."""
+    from oracle import synth, task
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = synth.make_cfg(dim=32, dim_mults=(1, 2), data_channels=18, time_resolution=64, time_bandwidth=100.0,
+                         attn_heads=2, attn_dim_head=16, dropout=0.0)
+    params = synth.synth_unet3d_params(cfg, 3)
+    kw = {k: v for k, v in cfg.items() if k != "data_channels"}
+    mod = ftb.Geo3DStochInterp(data_shape=(16, 16, 16), embedding_dim=18, **kw).to(dev)
+    mod.net.load_state_dict(params)
+    tr = ftb.FlowTrainer(mod, lr=2e-4, max_grad_norm=1.0, ema_decay=0.9, ema_start_step=0)
+    g = torch.Generator("cpu").manual_seed(5)
+    batch = torch.randint(-1, 14, (2, 1, 16, 16, 16), generator=g).to(dev)
+    n1 = synth.synth_input((2, 18, 16, 16, 16), 21, "n1").to(dev)
+    x0 = synth.synth_input((2, 18, 16, 16, 16), 22, "x0").to(dev)
+    T = synth.synth_times(2, 23).to(dev)
+    p_before = tr.flat.clone()
+    loss = tr.step(batch, noise1=n1, X0=x0, T=T)
+    # oracle: same draws
+    W = task.simplex_embedding(15, 18).to(dev)
+    dparams = {k: v.to(dev) for k, v in params.items()}
+    X1 = task.embed(W, batch) + 1e-3 * n1
+    XT, VT = (1 - T.view(-1, 1, 1, 1, 1)) * x0 + T.view(-1, 1, 1, 1, 1) * X1, X1 - x0
+    loss_o, _, grads_o = task.training_grads(dparams, cfg, XT, T, VT)
+    assert abs(loss.item() - loss_o.item()) <= 2e-2 * abs(loss_o.item())
+    gflat_o = torch.cat([grads_o[k].reshape(-1) for k in params.keys()])
+    e = rel(tr.gflat, gflat_o)
+    print(f"FlowTrainer gradient vs oracle rel-L2 {e:.3e}")
+    assert e <= BAR_GRAD_ALL
+    # the update, given the gradient the kernels produced
+    tn = tr.gflat.double().norm().item()
+    want_p, _, _ = task.adam_reference(p_before.cpu(), tr.gflat.cpu(), torch.zeros_like(p_before).cpu(),
+                                       torch.zeros_like(p_before).cpu(), 1, total_norm=tn)
+    assert torch.allclose(tr.flat.cpu(), want_p, rtol=1e-5, atol=1e-7)
+    assert torch.equal(tr.ema_flat, tr.flat)           # first eligible step clones (callbacks.py:259-262)
+    loss2 = tr.step(batch, noise1=n1, X0=x0, T=T)
+    assert torch.isfinite(loss2)
+    want_ema = 0.9 * want_p.to(dev) + 0.1 * tr.flat    # blend after the second step
+    assert torch.allclose(tr.ema_flat, want_ema, rtol=1e-5, atol=1e-7)
+    # the parameters the module exposes are the flat buffer (views), so sampling sees the new weights
+    assert next(mod.net.parameters()).data_ptr() == tr.flat.data_ptr()
+
+
+def test_training_reduces_loss(ftb, dev):
+    """A few fused steps on one fixed batch drive the loss down (end-to-end sanity of sign and scale)."""
+    from oracle import synth
+    cfg = synth.make_cfg(dim=32, dim_mults=(1, 2), data_channels=18, time_resolution=64, time_bandwidth=100.0,
+                         attn_heads=2, attn_dim_head=16, dropout=0.0)
+    kw = {k: v for k, v in cfg.items() if k != "data_channels"}
+    mod = ftb.Geo3DStochInterp(data_shape=(16, 16, 16), embedding_dim=18, **kw).to(dev)
+    mod.net.load_state_dict(synth.synth_unet3d_params(cfg, 3))
+    tr = ftb.FlowTrainer(mod, lr=1e-3, max_grad_norm=1.0, ema_decay=None)
+    g = torch.Generator("cpu").manual_seed(9)
+    batch = torch.randint(-1, 14, (2, 1, 16, 16, 16), generator=g).to(dev)
+    n1 = synth.synth_input((2, 18, 16, 16, 16), 31, "n1").to(dev)
+    x0 = synth.synth_input((2, 18, 16, 16, 16), 32, "x0").to(dev)
+    T = synth.synth_times(2, 33).to(dev)
+    losses = [tr.step(batch, noise1=n1, X0=x0, T=T).item() for _ in range(12)]
+    print("losses", [f"{v:.4f}" for v in losses])
+    assert losses[-1] < 0.9 * losses[0]

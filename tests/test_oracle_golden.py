@@ -202,3 +202,50 @@ def test_ema_and_loss():
     v = torch.randn(2, 3, 4, 4, 4)
     assert task.flow_loss(v, torch.zeros_like(v)).item() == pytest.approx(1.0)
     assert task.flow_loss(v, v).item() == 0.0
+
+
+# ------------------------------------------------------------------ training step (autograd of the oracle)
+@pytest.mark.parametrize("name", ["small", "full"])
+def test_training_grads_vs_reference_golden(golden_dir, name):
+    """Gradients of the training loss through the oracle Unet3D == the reference module's autograd
+    (tests/golden/make_golden.py gen_train): loss, output, every parameter's gradient norm and sampled
+    entries, a handful of complete gradients."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(golden_dir, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    over, pseed, shape = mg.TRAIN_CFGS[name]
+    g = _load(golden_dir, f"train_{name}.npz")
+    cfg = synth.make_cfg(**over)
+    params = synth.synth_unet3d_params(cfg, pseed)
+    xt, vt = synth.synth_input(shape, 11, "xt"), synth.synth_input(shape, 12, "vt")
+    t = torch.from_numpy(g["t"])
+    loss, vhat, grads = task.training_grads(params, cfg, xt, t, vt)
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    assert rel_l2(vhat, g["vhat"]) <= 1e-5
+    for k, gr in grads.items():
+        want = float(g[f"norm/{k}"])
+        got = gr.double().norm().item()
+        assert abs(got - want) <= 2e-3 * want + 1e-9, (k, got, want)
+        flat = gr.reshape(-1)
+        idx = torch.linspace(0, flat.numel() - 1, min(16, flat.numel())).long()
+        assert np.allclose(flat[idx].numpy(), g[f"sample/{k}"], rtol=5e-3, atol=2e-3 * want / max(1.0, flat.numel() ** 0.5))
+    for k in mg.TRAIN_FULL_GRADS:
+        assert rel_l2(grads[k], g[f"full/{k}"]) <= 1e-3, k
+
+
+def test_adam_reference_matches_torch():
+    torch.manual_seed(0)
+    p0 = torch.randn(1000)
+    p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([p], lr=2e-4)
+    m = torch.zeros(1000)
+    v = torch.zeros(1000)
+    q = p0.clone()
+    for step in range(1, 4):
+        gr = torch.randn(1000) * 3
+        p.grad = gr.clone()
+        tn = torch.nn.utils.clip_grad_norm_([p], 1.0)
+        opt.step()
+        q, m, v = task.adam_reference(q, gr, m, v, step, total_norm=tn)
+        assert torch.allclose(q, p.detach(), rtol=1e-5, atol=1e-7)
