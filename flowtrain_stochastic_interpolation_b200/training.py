@@ -108,9 +108,9 @@ def backward_into(net, dout, gflat, bucket_cb=None):
     """Adds the parameter gradients of the last ``forward_train`` into ``gflat`` (flat, state_dict order)."""
     B, _, X, Y, Z = dout.shape
     ws, base, nbytes = train_workspace(net, dout.device, B, X, Y, Z)
-    cb = _lib.BUCKET_CB(bucket_cb) if bucket_cb is not None else None
+    cb = _lib.BUCKET_CB(bucket_cb) if bucket_cb is not None else C.cast(None, _lib.BUCKET_CB)
     _lib.check(_lib.lib.ftb_unet3d_backward(net._handle, _lib.ptr(dout), _lib.ptr(gflat), C.c_void_p(base), nbytes,
-                                            cb if cb is not None else None, None, _lib.stream_ptr()))
+                                            cb, None, _lib.stream_ptr()))
 
 
 class UnetTrainFn(torch.autograd.Function):
