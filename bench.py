@@ -58,6 +58,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-evals", type=int, default=2, help="timed CPU velocity evaluations in the cpu_baseline leg")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (train voxels/s)")
+    ap.add_argument("--train-only", action="store_true", help="only the training-step leg (development)")
+    ap.add_argument("--train-batch", type=int, default=8)
     return ap.parse_args()
 
 
@@ -195,6 +198,91 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------- training-step leg
+TRAIN_GF_PER_SAMPLE = 3 * GF_PER_EVAL - 155.4   # fwd + dgrad + wgrad; the stem has no data gradient
+
+
+def run_train_leg(a, ftb, _lib, dev, rank, world, dist):
+    """BASELINE configs[3]: unconditional 64^3 interpolant training step, batch 8 per GPU, Adam lr 2e-4,
+    clip 1.0, EMA 0.9995 every batch, data-parallel NCCL all-reduce overlapped with the backward.
+    One step = FlowTrainer.step on a fresh synthetic category batch (embed, noise, interpolant, forward,
+    loss, backward, all-reduce, clip + Adam, EMA).  value = world*B*V / step time (max over ranks)."""
+    import ctypes as C
+    import torch
+    from oracle import synth
+    cfg = synth.make_cfg(dropout=0.0)
+    kw = {k: v for k, v in cfg.items() if k != "data_channels"}
+    S, B = a.size, a.train_batch
+    mod = ftb.Geo3DStochInterp(data_shape=(S, S, S), embedding_dim=18, **kw).to(dev)
+    mod.net.load_state_dict(synth.synth_unet3d_params(cfg, 0))
+    tr = ftb.FlowTrainer(mod, lr=2e-4, max_grad_norm=1.0, ema_decay=0.9995, ema_start_step=0)
+    tr.broadcast_parameters(0)
+    g = torch.Generator("cpu").manual_seed(1000 + rank)
+    nb = 4
+    host_batches = [torch.randint(-1, 14, (B, 1, S, S, S), generator=g, dtype=torch.int64).pin_memory() for _ in range(nb)]
+    dev_batches = [b.to(dev) for b in host_batches]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(a.warmup, 1)):
+        tr.step(dev_batches[i % nb])
+    barrier()
+    l0 = _lib.lib.ftb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(a.steps):
+        loss = tr.step(dev_batches[i % nb])
+    e1.record()
+    barrier()
+    step_ms = e0.elapsed_time(e1) / a.steps
+    launches = (_lib.lib.ftb_launch_count() - l0) / a.steps
+    # e2e: host batch in (pinned, H2D inside the timed region), loss scalar back on the host, every step
+    barrier()
+    w0 = time.perf_counter()
+    for i in range(a.steps):
+        loss_host = tr.step(host_batches[i % nb].to(dev, non_blocking=True)).item()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - w0) * 1e3 / a.steps
+    # per-kernel-class times of one more step (CUDA events around every conv / wgrad launch)
+    _lib.lib.ftb_profile_enable(1)
+    tr.step(dev_batches[0])
+    torch.cuda.synchronize()
+    nk = 3
+    fl, by, ms = (C.c_double * nk)(), (C.c_double * nk)(), (C.c_double * nk)()
+    ln = (C.c_int * nk)()
+    _lib.check(_lib.lib.ftb_profile_collect(fl, by, ms, ln, nk))
+    _lib.lib.ftb_profile_enable(0)
+    stats = torch.tensor([step_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    step_ms, e2e_ms = stats.tolist()
+    peaks = measured_peaks()
+    V = S ** 3
+    tf = TRAIN_GF_PER_SAMPLE * B / step_ms
+    del tr, mod
+    torch.cuda.empty_cache()
+    return {
+        "metric": "train_voxels_per_sec_64cubed", "value": world * B * V / (step_ms * 1e-3), "unit": "voxels/s",
+        "ms_per_step": step_ms, "scaling": "weak", "dtype": "bf16 tensor cores, fp32 master weights / Adam / EMA",
+        "config": {"workload": f"configs[3]: unconditional {S}^3 interpolant training step, batch {B}/GPU, Adam 2e-4, "
+                               f"clip 1.0, EMA 0.9995 every batch, dropout 0, {world} rank(s)"
+                               + (", NCCL all-reduce bucketed from inside the backward" if world > 1 else ""),
+                   "global_batch": world * B},
+        "loss": loss_host, "gpu_launches_per_step": launches,
+        "e2e": {"value": world * B * V / (e2e_ms * 1e-3), "unit": "voxels/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": B * V * 8, "d2h_bytes_per_step": 4,
+                "what": "FlowTrainer.step from a pinned host int64 batch to the loss scalar on the host"},
+        "roofline": {"bound": "tensor", "algorithmic_gflop_per_step": TRAIN_GF_PER_SAMPLE * B,
+                     "achieved": tf, "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": tf / peaks["bf16"],
+                     "conv_fwd_dgrad": {"ms": ms[0], "launches": int(ln[0]), "tflops": fl[0] / (ms[0] * 1e-3) / 1e12 if ms[0] > 0 else None},
+                     "conv1x1": {"ms": ms[1], "launches": int(ln[1])},
+                     "wgrad": {"ms": ms[2], "launches": int(ln[2]), "tflops": fl[2] / (ms[2] * 1e-3) / 1e12 if ms[2] > 0 else None}},
+    }
+
+
 # ---------------------------------------------------------------------------- B200 arm
 def run_b200(a):
     import torch
@@ -214,6 +302,13 @@ def run_b200(a):
     from flowtrain_stochastic_interpolation_b200 import _lib
     from oracle import synth  # synthetic weights/inputs only (no oracle compute on this arm's timed path)
 
+    if a.train_only:
+        tl = run_train_leg(a, ftb, _lib, dev, rank, world, dist)
+        if rank == 0:
+            print(json.dumps(tl), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     cfg = synth.make_cfg()
     net = ftb.Unet3D(**cfg).to(dev).eval()
     net.load_state_dict(synth.synth_unet3d_params(cfg, 0))
@@ -290,6 +385,12 @@ def run_b200(a):
             e2e_s = time.perf_counter() - w0
             e2e = (e2e_s, x_host.numel() * 4, out_host.numel() * 8)
 
+    train_leg = None
+    if not a.no_train:
+        del solver, net
+        torch.cuda.empty_cache()
+        train_leg = run_train_leg(a, ftb, _lib, dev, rank, world, dist)
+
     tot_s = (N_ODE_STEPS * step_ms + decode_ms) / 1e3
     stats = torch.tensor([step_ms, decode_ms, tot_s, e2e[0] if e2e else 0.0, float(launches)], device=dev, dtype=torch.float64)
     if world > 1:
@@ -326,6 +427,8 @@ def run_b200(a):
                    "weights": "synthetic random-init (oracle/synth.py seed 0)"},
         "clocks": clk, "gpu_launches": int(launches), "roofline": roof,
     }
+    if train_leg:
+        line["train"] = train_leg
     if e2e:
         line["e2e"] = {"value": world * B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": e2e[1], "d2h_bytes_per_step": e2e[2],
                        "seconds_per_solve": e2e_s,

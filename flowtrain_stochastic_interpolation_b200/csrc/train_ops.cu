@@ -169,6 +169,111 @@ normact_bwd_kernel(const NormActP p) {
   }
 }
 
+// Same backward for C <= 64 channels (every 64^3 layer of the UNet): the voxel's u and dout rows are read from
+// HBM exactly once and held in registers (12 x 16 B for C = 48), the per-channel sums live in registers across
+// the thread's voxels and are reduced once per block.  dbias is not produced here.
+template <int CG, bool kS>
+__global__ void __launch_bounds__(256)
+normact_bwd_small_kernel(const NormActP p, int vpt) {
+  constexpr int C = CG * 8;
+  __shared__ float s_m[C], s_sh[C], s_red[2 * C];
+  const int b = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float m = p.gain ? p.gain[c] : 1.f;
+    if (p.s1) m *= p.s1[(size_t)b * p.fstride + c];
+    s_m[c] = m;
+    s_sh[c] = p.s1 ? p.sh[(size_t)b * p.fstride + c] : 0.f;
+  }
+  for (int c = threadIdx.x; c < 2 * C; c += 256) s_red[c] = 0.f;
+  __syncthreads();
+  const size_t cgs = p.vox * 8;
+  const size_t bbase = (size_t)b * CG * p.vox * 8;
+  float accR[C], accS[kS ? C : 1];
+#pragma unroll
+  for (int c = 0; c < C; ++c) { accR[c] = 0.f; if (kS) accS[c] = 0.f; }
+  for (int it = 0; it < vpt; ++it) {
+    const size_t v = ((size_t)blockIdx.x * vpt + it) * 256 + threadIdx.x;
+    if (v >= p.vox) break;
+    const size_t base = bbase + v * 8;
+    uint4 U[CG], G[CG];
+#pragma unroll
+    for (int cg = 0; cg < CG; ++cg) {
+      U[cg] = __ldg(reinterpret_cast<const uint4*>(p.u + base + cg * cgs));
+      G[cg] = __ldg(reinterpret_cast<const uint4*>(p.dout + base + cg * cgs));
+    }
+    float rinv = 1.f;
+    if (p.norm) {
+      float ss = 0.f;
+#pragma unroll
+      for (int cg = 0; cg < CG; ++cg) {
+        float f[8];
+        unpack_bf16x8(U[cg], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
+      }
+      rinv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    }
+    float dot = 0.f;
+    // pass 1: channel sums and dot = sum_c n*dn (dz is recomputed in pass 2 rather than kept: 48 more registers)
+#pragma unroll
+    for (int cg = 0; cg < CG; ++cg) {
+      float f[8], g[8];
+      unpack_bf16x8(U[cg], f);
+      unpack_bf16x8(G[cg], g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = cg * 8 + j;
+        const float n = f[j] * rinv, m = s_m[c];
+        float dz = g[j];
+        if (p.silu) {
+          const float z = fmaf(n, m, s_sh[c]);
+          const float sg = sigm(z);
+          dz *= sg * (1.f + z * (1.f - sg));
+        }
+        accR[c] = fmaf(dz, n, accR[c]);
+        if (kS) accS[c] += dz;
+        dot = fmaf(n, dz * m, dot);
+        g[j] = dz;
+      }
+    }
+#pragma unroll
+    for (int cg = 0; cg < CG; ++cg) {
+      float f[8], g[8];
+      unpack_bf16x8(U[cg], f);
+      unpack_bf16x8(G[cg], g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = cg * 8 + j;
+        const float n = f[j] * rinv, m = s_m[c];
+        float dz = g[j];
+        if (p.silu) {
+          const float z = fmaf(n, m, s_sh[c]);
+          const float sg = sigm(z);
+          dz *= sg * (1.f + z * (1.f - sg));
+        }
+        const float dn = dz * m;
+        g[j] = p.norm ? rinv * (dn - n * dot) : dn;
+      }
+      *reinterpret_cast<uint4*>(p.du + base + cg * cgs) = pack_bf16x8(g);
+    }
+  }
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float r = warp_sum(accR[c]);
+    if (lane == 0) atomicAdd(&s_red[c], r);
+    if (kS) {
+      const float sm = warp_sum(accS[c]);
+      if (lane == 0) atomicAdd(&s_red[C + c], sm);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += 256) {
+    if (c < C) { if (p.R) atomicAdd(p.R + (size_t)b * C + c, s_red[c]); }
+    else if (p.S) atomicAdd(p.S + (size_t)b * p.sstride + (c - C), s_red[c]);
+  }
+}
+
 // ds1[b][c] = gain[c] * R[b][c];  dg[c] += sqrt_c * sum_b s1[b][c] * R[b][c]   (gain = g*sqrt_c)
 __global__ void normact_finish_kernel(const float* __restrict__ R, int B, int C, const float* __restrict__ gain,
                                       const float* __restrict__ s1, int fstride, float sqrt_c,
@@ -304,18 +409,22 @@ __global__ void transpose_flip_kernel(const float* __restrict__ w, int cout, int
 }
 
 // to_qkv with the pre-norm gain folded in (W' = W diag(gs)): dW = dW' diag(gs), dg[ci] += sqrt_c sum_co dW'[co][ci] W[co][ci]
-__global__ void fold_gain_bwd_kernel(const float* __restrict__ dwp, const float* __restrict__ w, const float* __restrict__ gs,
-                                     int cout, int cin, float sqrt_c, float* __restrict__ dw, float* __restrict__ dg) {
-  const int ci = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ci >= cin) return;
+__global__ void __launch_bounds__(128)
+fold_gain_bwd_kernel(const float* __restrict__ dwp, const float* __restrict__ w, const float* __restrict__ gs,
+                     int cout, int cin, float sqrt_c, float* __restrict__ dw, float* __restrict__ dg) {
+  __shared__ float red[4];
+  const int ci = blockIdx.x;
   float a = 0.f;
   const float g = gs[ci];
-  for (int co = 0; co < cout; ++co) {
+  for (int co = threadIdx.x; co < cout; co += 128) {
     const float d = dwp[(size_t)co * cin + ci];
     dw[(size_t)co * cin + ci] += d * g;
     a = fmaf(d, w[(size_t)co * cin + ci], a);
   }
-  dg[ci] += a * sqrt_c;
+  a = warp_sum(a);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) dg[ci] += (red[0] + red[1] + red[2] + red[3]) * sqrt_c;
 }
 
 // ---------------------------------------------------------------- LinearAttention (train path)
@@ -671,6 +780,24 @@ int normact_bwd(const Act& dout, const Act& u, bool norm, const float* gain, con
   p.CG = u.cg(); p.vox = u.voxels(); p.norm = norm; p.silu = silu;
   p.gain = gain; p.s1 = s1; p.sh = sh; p.fstride = fstride;
   p.R = R; p.S = S; p.sstride = sstride; p.dbias = dbias;
+  if (dbias == nullptr && (p.CG == 6 || p.CG == 4 || p.CG == 2 || p.CG == 8)) {
+    const size_t vblocks = (p.vox + 255) / 256;
+    int vpt = (int)(vblocks * u.B / (4 * (size_t)num_sms()));   // ~4 blocks per SM over the batch
+    vpt = vpt < 1 ? 1 : (vpt > 16 ? 16 : vpt);
+    dim3 grid((unsigned)((vblocks + vpt - 1) / vpt), u.B);
+#define FTB_NA_SMALL(CGV)                                                                   \
+    do {                                                                                     \
+      if (S) normact_bwd_small_kernel<CGV, true><<<grid, 256, 0, st>>>(p, vpt);              \
+      else normact_bwd_small_kernel<CGV, false><<<grid, 256, 0, st>>>(p, vpt);               \
+    } while (0)
+    if (p.CG == 6) FTB_NA_SMALL(6);
+    else if (p.CG == 4) FTB_NA_SMALL(4);
+    else if (p.CG == 2) FTB_NA_SMALL(2);
+    else FTB_NA_SMALL(8);
+#undef FTB_NA_SMALL
+    FTB_LAUNCH_OK();
+    return 0;
+  }
   dim3 grid((unsigned)((p.vox + 256 * kNaVPT - 1) / (256 * kNaVPT)), u.B);
   normact_bwd_kernel<<<grid, 256, 0, st>>>(p);
   FTB_LAUNCH_OK();
@@ -726,7 +853,7 @@ int transpose_flip(const float* w, int cout, int cin, int ksize, int ci0, int ci
 
 int fold_gain_bwd(const float* dwp, const float* w, const float* gs, int cout, int cin, float sqrt_c, float* dw,
                   float* dg, cudaStream_t st) {
-  fold_gain_bwd_kernel<<<cdiv(cin, 128), 128, 0, st>>>(dwp, w, gs, cout, cin, sqrt_c, dw, dg);
+  fold_gain_bwd_kernel<<<cin, 128, 0, st>>>(dwp, w, gs, cout, cin, sqrt_c, dw, dg);
   FTB_LAUNCH_OK();
   return 0;
 }

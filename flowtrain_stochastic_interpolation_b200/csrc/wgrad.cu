@@ -334,7 +334,7 @@ int conv_wgrad(const Act& x, int x_cgoff, int x_cg, const Act& dy, int dy_cgoff,
   p.cout_real = cout_real; p.cin_tot = cin_tot; p.ci_base = ci_base; p.ci_real = ci_real;
   // split the item range so that the grid is about one wave
   const int fixed = p.ncls * p.K * p.nchunk * p.nmb * (p.per_batch ? p.B : 1);
-  int nsplit = cdiv(num_sms(), fixed);
+  int nsplit = num_sms() / fixed;   // one wave: a CTA holds its accumulators for its whole life
   const long long max_split = (p.items + 3) / 4;   // at least ~4 tiles per CTA
   if (nsplit > max_split) nsplit = (int)max_split;
   if (nsplit < 1) nsplit = 1;

@@ -339,3 +339,20 @@ def test_training_reduces_loss(ftb, dev):
     losses = [tr.step(batch, noise1=n1, X0=x0, T=T).item() for _ in range(12)]
     print("losses", [f"{v:.4f}" for v in losses])
     assert losses[-1] < 0.9 * losses[0]
+
+
+def test_flow_trainer_data_parallel_nccl(ftb):
+    """N > 1: one rank per GPU, NCCL all-reduce bucketed from inside the backward (needs >= 2 GPUs; the
+    single-GPU driver run skips it, `gpurun --gpus 2` runs it)."""
+    import subprocess
+    import sys
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29631",
+                        os.path.join(root, "tests", "_ddp_train_worker.py")],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "DDP_OK" in r.stdout

@@ -125,3 +125,24 @@ def test_sharded_ensemble_gloo_world2():
                        capture_output=True, text=True, timeout=240, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "GLOO_OK" in r.stdout
+
+
+def test_bucketed_gradient_allreduce_gloo_world2():
+    """Data-parallel training exchange: the gradient ranges the backward reports are coalesced and
+    all-reduced exactly once each; world_size-2 gloo group on CPU tensors."""
+    script = os.path.join(ROOT, "tests", "_gloo_bucket_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29617")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29617", script],
+                       capture_output=True, text=True, timeout=240, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "BUCKET_OK" in r.stdout
+
+
+def test_training_plan_sizes_without_gpu():
+    """The train-mode tape (forward + backward bookkeeping) is consistent: sizing it needs no GPU."""
+    net = ftb.Unet3D(**synth.make_cfg(dropout=0.0))
+    n = _lib.lib.ftb_unet3d_train_workspace_bytes(net._handle, 1, 16, 16, 16)
+    assert n > _lib.lib.ftb_unet3d_workspace_bytes(net._handle, 1, 16, 16, 16) > 0
+    total = _lib.lib.ftb_unet3d_param_offset(net._handle, _lib.lib.ftb_unet3d_num_params(net._handle))
+    assert total == 25_193_410
