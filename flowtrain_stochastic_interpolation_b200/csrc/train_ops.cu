@@ -169,37 +169,57 @@ normact_bwd_kernel(const NormActP p) {
   }
 }
 
-// Same backward for C <= 64 channels (every 64^3 layer of the UNet): the voxel's u and dout rows are read from
-// HBM exactly once and held in registers (12 x 16 B for C = 48), the per-channel sums live in registers across
-// the thread's voxels and are reduced once per block.  dbias is not produced here.
+// Same backward for C <= 96 channels (every 64^3 / 32^3 layer of the UNet): the voxel's u and dout rows are read
+// from HBM exactly once and held in registers (12 x 16 B for C = 48).  The per-channel sums over voxels use a
+// warp reduce-scatter (31 shuffles per 32 channels instead of 160): afterwards lane l holds the warp's sum of
+// channel 32*g + l, which it accumulates in ONE register per group across its voxels; blocks finish through
+// shared memory and one global atomic per channel.  dbias is not produced here.
+__device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int step = 16; step >= 1; step >>= 1) {
+    const bool up = (lane & step) != 0;
+#pragma unroll
+    for (int i = 0; i < step; ++i) {
+      const float send = up ? v[i] : v[i + step];
+      const float keep = up ? v[i + step] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+    }
+  }
+  return v[0];   // sum over the warp of element `lane`
+}
+
 template <int CG, bool kS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, CG <= 8 ? 2 : 1)
 normact_bwd_small_kernel(const NormActP p, int vpt) {
   constexpr int C = CG * 8;
-  __shared__ float s_m[C], s_sh[C], s_red[2 * C];
+  constexpr int NG = (C + 31) / 32;          // groups of 32 channels
+  __shared__ float s_m[C], s_sh[C], s_red[2 * NG * 32];
   const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31;
   for (int c = threadIdx.x; c < C; c += 256) {
     float m = p.gain ? p.gain[c] : 1.f;
     if (p.s1) m *= p.s1[(size_t)b * p.fstride + c];
     s_m[c] = m;
     s_sh[c] = p.s1 ? p.sh[(size_t)b * p.fstride + c] : 0.f;
   }
-  for (int c = threadIdx.x; c < 2 * C; c += 256) s_red[c] = 0.f;
+  for (int c = threadIdx.x; c < 2 * NG * 32; c += 256) s_red[c] = 0.f;
   __syncthreads();
   const size_t cgs = p.vox * 8;
   const size_t bbase = (size_t)b * CG * p.vox * 8;
-  float accR[C], accS[kS ? C : 1];
+  float accR[NG], accS[NG];
 #pragma unroll
-  for (int c = 0; c < C; ++c) { accR[c] = 0.f; if (kS) accS[c] = 0.f; }
+  for (int g = 0; g < NG; ++g) { accR[g] = 0.f; accS[g] = 0.f; }
   for (int it = 0; it < vpt; ++it) {
+    // whole warps stay in the loop (the reduce-scatter is a warp collective); out-of-range voxels contribute 0
     const size_t v = ((size_t)blockIdx.x * vpt + it) * 256 + threadIdx.x;
-    if (v >= p.vox) break;
-    const size_t base = bbase + v * 8;
+    const bool in = v < p.vox;
+    if (__all_sync(0xffffffffu, !in)) break;
+    const size_t base = bbase + (in ? v : 0) * 8;
     uint4 U[CG], G[CG];
 #pragma unroll
     for (int cg = 0; cg < CG; ++cg) {
-      U[cg] = __ldg(reinterpret_cast<const uint4*>(p.u + base + cg * cgs));
-      G[cg] = __ldg(reinterpret_cast<const uint4*>(p.dout + base + cg * cgs));
+      U[cg] = in ? __ldg(reinterpret_cast<const uint4*>(p.u + base + cg * cgs)) : make_uint4(0u, 0u, 0u, 0u);
+      G[cg] = in ? __ldg(reinterpret_cast<const uint4*>(p.dout + base + cg * cgs)) : make_uint4(0u, 0u, 0u, 0u);
     }
     float rinv = 1.f;
     if (p.norm) {
@@ -214,63 +234,73 @@ normact_bwd_small_kernel(const NormActP p, int vpt) {
       rinv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
     }
     float dot = 0.f;
-    // pass 1: channel sums and dot = sum_c n*dn (dz is recomputed in pass 2 rather than kept: 48 more registers)
+    // pass 1, per group of 32 channels: dz, dot += n*dn, channel sums through the reduce-scatter
 #pragma unroll
-    for (int cg = 0; cg < CG; ++cg) {
-      float f[8], g[8];
-      unpack_bf16x8(U[cg], f);
-      unpack_bf16x8(G[cg], g);
+    for (int g = 0; g < NG; ++g) {
+      float vr[32], vs[32];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = cg * 8 + j;
-        const float n = f[j] * rinv, m = s_m[c];
-        float dz = g[j];
-        if (p.silu) {
-          const float z = fmaf(n, m, s_sh[c]);
-          const float sg = sigm(z);
-          dz *= sg * (1.f + z * (1.f - sg));
+      for (int q = 0; q < 4; ++q) {
+        const int cg = g * 4 + q;
+        if (cg < CG) {
+          float f[8], d[8];
+          unpack_bf16x8(U[cg], f);
+          unpack_bf16x8(G[cg], d);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = cg * 8 + j;
+            const float n = f[j] * rinv, m = s_m[c];
+            float dz = d[j];
+            if (p.silu) {
+              const float z = fmaf(n, m, s_sh[c]);
+              const float sg = sigm(z);
+              dz *= sg * (1.f + z * (1.f - sg));
+            }
+            dot = fmaf(n, dz * m, dot);
+            vr[q * 8 + j] = dz * n;
+            vs[q * 8 + j] = dz;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { vr[q * 8 + j] = 0.f; vs[q * 8 + j] = 0.f; }
         }
-        accR[c] = fmaf(dz, n, accR[c]);
-        if (kS) accS[c] += dz;
-        dot = fmaf(n, dz * m, dot);
-        g[j] = dz;
       }
+      accR[g] += warp_reduce_scatter32(vr, lane);
+      if (kS) accS[g] += warp_reduce_scatter32(vs, lane);
     }
+    if (in) {
 #pragma unroll
-    for (int cg = 0; cg < CG; ++cg) {
-      float f[8], g[8];
-      unpack_bf16x8(U[cg], f);
-      unpack_bf16x8(G[cg], g);
+      for (int cg = 0; cg < CG; ++cg) {
+        float f[8], d[8];
+        unpack_bf16x8(U[cg], f);
+        unpack_bf16x8(G[cg], d);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = cg * 8 + j;
-        const float n = f[j] * rinv, m = s_m[c];
-        float dz = g[j];
-        if (p.silu) {
-          const float z = fmaf(n, m, s_sh[c]);
-          const float sg = sigm(z);
-          dz *= sg * (1.f + z * (1.f - sg));
+        for (int j = 0; j < 8; ++j) {
+          const int c = cg * 8 + j;
+          const float n = f[j] * rinv, m = s_m[c];
+          float dz = d[j];
+          if (p.silu) {
+            const float z = fmaf(n, m, s_sh[c]);
+            const float sg = sigm(z);
+            dz *= sg * (1.f + z * (1.f - sg));
+          }
+          const float dn = dz * m;
+          d[j] = p.norm ? rinv * (dn - n * dot) : dn;
         }
-        const float dn = dz * m;
-        g[j] = p.norm ? rinv * (dn - n * dot) : dn;
+        *reinterpret_cast<uint4*>(p.du + base + cg * cgs) = pack_bf16x8(d);
       }
-      *reinterpret_cast<uint4*>(p.du + base + cg * cgs) = pack_bf16x8(g);
     }
   }
-  const int lane = threadIdx.x & 31;
 #pragma unroll
-  for (int c = 0; c < C; ++c) {
-    const float r = warp_sum(accR[c]);
-    if (lane == 0) atomicAdd(&s_red[c], r);
-    if (kS) {
-      const float sm = warp_sum(accS[c]);
-      if (lane == 0) atomicAdd(&s_red[C + c], sm);
-    }
+  for (int g = 0; g < NG; ++g) {
+    atomicAdd(&s_red[g * 32 + lane], accR[g]);
+    if (kS) atomicAdd(&s_red[(NG + g) * 32 + lane], accS[g]);
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < 2 * C; c += 256) {
-    if (c < C) { if (p.R) atomicAdd(p.R + (size_t)b * C + c, s_red[c]); }
-    else if (p.S) atomicAdd(p.S + (size_t)b * p.sstride + (c - C), s_red[c]);
+  for (int i = threadIdx.x; i < 2 * NG * 32; i += 256) {
+    const int c = i % (NG * 32);
+    if (c >= C) continue;
+    if (i < NG * 32) { if (p.R) atomicAdd(p.R + (size_t)b * C + c, s_red[i]); }
+    else if (kS && p.S) atomicAdd(p.S + (size_t)b * p.sstride + c, s_red[i]);
   }
 }
 
@@ -780,10 +810,10 @@ int normact_bwd(const Act& dout, const Act& u, bool norm, const float* gain, con
   p.CG = u.cg(); p.vox = u.voxels(); p.norm = norm; p.silu = silu;
   p.gain = gain; p.s1 = s1; p.sh = sh; p.fstride = fstride;
   p.R = R; p.S = S; p.sstride = sstride; p.dbias = dbias;
-  if (dbias == nullptr && (p.CG == 6 || p.CG == 4 || p.CG == 2 || p.CG == 8)) {
+  if (dbias == nullptr && (p.CG == 6 || p.CG == 4 || p.CG == 2 || p.CG == 8 || p.CG == 12)) {
     const size_t vblocks = (p.vox + 255) / 256;
-    int vpt = (int)(vblocks * u.B / (4 * (size_t)num_sms()));   // ~4 blocks per SM over the batch
-    vpt = vpt < 1 ? 1 : (vpt > 16 ? 16 : vpt);
+    int vpt = (int)(vblocks * u.B / (8 * (size_t)num_sms()));   // ~8 blocks per SM over the batch
+    vpt = vpt < 1 ? 1 : (vpt > 8 ? 8 : vpt);
     dim3 grid((unsigned)((vblocks + vpt - 1) / vpt), u.B);
 #define FTB_NA_SMALL(CGV)                                                                   \
     do {                                                                                     \
@@ -793,6 +823,7 @@ int normact_bwd(const Act& dout, const Act& u, bool norm, const float* gain, con
     if (p.CG == 6) FTB_NA_SMALL(6);
     else if (p.CG == 4) FTB_NA_SMALL(4);
     else if (p.CG == 2) FTB_NA_SMALL(2);
+    else if (p.CG == 12) FTB_NA_SMALL(12);
     else FTB_NA_SMALL(8);
 #undef FTB_NA_SMALL
     FTB_LAUNCH_OK();

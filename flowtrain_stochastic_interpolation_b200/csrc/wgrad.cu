@@ -43,6 +43,8 @@ struct WgradParams {
   int ngrp;             // accumulator groups per kd = (K / stack) * Kw
   int ncls;             // classes per kd
   int nchunk, nmb, nsplit, per_batch;
+  int kdp, nkg;         // depth taps per CTA (2: the dY tiles of kd0 and kd0+1 share the M = 128 rows), kd groups
+  uint32_t du_box_bytes;
   int nHt, nWt;
   long long items;      // items per sample (per_batch) or over the whole batch
   int x_cgtot, x_cgoff, du_cgtot, du_cgoff;
@@ -73,7 +75,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
   int r = blockIdx.x;
   const int split = r % p.nsplit; r /= p.nsplit;
   const int cls = r % p.ncls; r /= p.ncls;
-  const int kd = r % p.K; r /= p.K;
+  const int kd = (r % p.nkg) * p.kdp; r /= p.nkg;   // first depth tap of this CTA
   const int chunk = r % p.nchunk; r /= p.nchunk;
   const int mb = r % p.nmb; r /= p.nmb;
   const int bfix = r;   // per_batch: sample index
@@ -109,16 +111,22 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
       for (long long it = i_lo; it < i_hi; ++it) {
         int t = (int)(it % tiles_pp);
         long long q = it / tiles_pp;
-        const int d = (int)(q % p.D);
+        const int xd = (int)(q % p.D);     // items walk the X planes; the dY plane of depth tap kd is xd - kd + pad
         const int b = p.per_batch ? bfix : (int)(q / p.D);
-        const int xd = d + kd - p.pad;
-        if (xd < 0 || xd >= p.D) continue;   // this depth tap reads only zero padding
+        const int d0 = xd - kd + p.pad, d1 = d0 - 1;
+        const bool use0 = d0 >= 0 && d0 < p.D;
+        const bool use1 = p.kdp == 2 && kd + 1 < p.K && d1 >= 0 && d1 < p.D;
+        if (!use0 && !use1) continue;      // only zero padding under these taps
         const int h0 = (t / p.nWt) * 16, w0 = (t % p.nWt) * 8;
         const int s = n % p.nstage;
         mbar_wait(&empty[s], ((n / p.nstage) & 1) ^ 1);
-        mbar_expect_tx(&full[s], p.du_bytes + p.x_bytes);
-        tma_load_4d(smem + (size_t)s * p.du_bytes, &tm_du, &full[s], w0 * 8, h0, d,
+        mbar_expect_tx(&full[s], p.du_box_bytes * (p.kdp == 2 ? 2u : 1u) + p.x_bytes);
+        // out-of-range dY planes are zero-filled by TMA (they multiply real X data)
+        tma_load_4d(smem + (size_t)s * p.du_bytes, &tm_du, &full[s], w0 * 8, h0, d0,
                     b * p.du_cgtot + p.du_cgoff + mb * 16);
+        if (p.kdp == 2)
+          tma_load_4d(smem + (size_t)s * p.du_bytes + 16384, &tm_du, &full[s], w0 * 8, h0, kd + 1 < p.K ? d1 : -1,
+                      b * p.du_cgtot + p.du_cgoff);
         if (p.stack > 1)
           tma_load_4d(smem + p.off_x + (size_t)s * p.x_bytes, &tm_x, &full[s], (w0 - p.padw) * 8,
                       b * p.x_cgtot + p.x_cgoff + chunk * p.ncg, h0 - p.pad, xd);
@@ -141,9 +149,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
       const uint32_t b_kstep = p.b_kstep >> 4;   // two h rows per k-step of 16 voxels
       int n = 0;
       for (long long it = i_lo; it < i_hi; ++it) {
-        const int d = (int)((it / tiles_pp) % p.D);
-        const int xd = d + kd - p.pad;
-        if (xd < 0 || xd >= p.D) continue;
+        const int xd = (int)((it / tiles_pp) % p.D);
+        const int d0 = xd - kd + p.pad, d1 = d0 - 1;
+        if (!(d0 >= 0 && d0 < p.D) && !(p.kdp == 2 && kd + 1 < p.K && d1 >= 0 && d1 < p.D)) continue;
         const int s = n % p.nstage;
         mbar_wait(&full[s], (n / p.nstage) & 1);
         tc_fence_after();
@@ -167,12 +175,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
   } else {
     // ---- TMEM -> fp32 gradient (atomicAdd): thread = accumulator row = output channel
     const int q = warp & 3;
-    const int co = mb * 128 + q * 32 + lane;
+    const int row = q * 32 + lane;
+    const int co = p.kdp == 2 ? (row & 63) : mb * 128 + row;
+    const int kd_row = p.kdp == 2 ? kd + (row >> 6) : kd;
     // any item with an in-range depth tap?  (same predicate as the producer / issuer loops)
     bool any = false;
     for (long long it = i_lo; it < i_hi && !any; ++it) {
-      const int xd = (int)((it / tiles_pp) % p.D) + kd - p.pad;
-      any = xd >= 0 && xd < p.D;
+      const int d0 = (int)((it / tiles_pp) % p.D) - kd + p.pad, d1 = d0 - 1;
+      any = (d0 >= 0 && d0 < p.D) || (p.kdp == 2 && kd + 1 < p.K && d1 >= 0 && d1 < p.D);
     }
     if (any) {
       mbar_wait(done, 0);
@@ -187,7 +197,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
           uint32_t v[16];
           tmem_ld16(trow + a * p.Nacc + c0, v);
           tmem_ld_wait();
-          if (co < p.cout_real) {
+          if (co < p.cout_real && kd_row < p.K) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int n = c0 + j;
@@ -202,7 +212,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
                 ok = ci < p.ci_real;
               }
               if (ok) {
-                const size_t idx = ((((size_t)co * p.cin_tot + p.ci_base + ci) * p.K + kd) * p.K + kh) * p.Kww + kww;
+                const size_t idx = ((((size_t)co * p.cin_tot + p.ci_base + ci) * p.K + kd_row) * p.K + kh) * p.Kww + kww;
                 atomicAdd(dwb + idx, __uint_as_float(v[j]));
               }
             }
@@ -316,24 +326,29 @@ int conv_wgrad(const Act& x, int x_cgoff, int x_cg, const Act& dy, int dy_cgoff,
   } else {             // [ncg][BH][BW][8]
     p.b_sbo = BH * P; p.b_lbo = P; p.b_kh = P; p.b_kstep = 2 * P;
   }
-  p.du_bytes = du_box_cg * 2048;
+  // Cout <= 64: two depth taps per CTA share the 128 accumulator rows (rows 0-63: kd0, rows 64-127: kd0+1)
+  p.kdp = (p.K > 1 && p.nmb == 1 && cout_cg <= 8 && getenv("FTB_WGRAD_NOPAIR") == nullptr) ? 2 : 1;
+  p.nkg = cdiv(p.K, p.kdp);
+  p.du_box_bytes = du_box_cg * 2048;
+  p.du_bytes = p.kdp == 2 ? 32768 : du_box_cg * 2048;
   p.x_bytes = (uint32_t)BH * p.ncg * P;
   FTB_CHECK(p.x_bytes % 128 == 0, "wgrad: X box bytes must be a multiple of 128");
   // stages: all dY tiles first, then all X tiles, then 32 KB of readable slack for the M=128 over-read
   int ns = kWgMaxStages;
-  auto total = [&](int n) { return (size_t)n * p.du_bytes + (size_t)n * p.x_bytes + 32768 + 256 + 128; };
+  const size_t slack = p.kdp == 2 ? 0 : 32768;   // paired taps: the 128 rows are exactly the stage
+  auto total = [&](int n) { return (size_t)n * p.du_bytes + (size_t)n * p.x_bytes + slack + 256 + 128; };
   while (ns > 2 && total(ns) > kWgSmemLimit) --ns;
   FTB_CHECK(total(ns) <= kWgSmemLimit, "wgrad: stage does not fit shared memory");
   p.nstage = ns;
   p.off_x = (uint32_t)ns * p.du_bytes;
-  p.off_bar = (uint32_t)round_up((int)(p.off_x + ns * p.x_bytes + 32768), 16);
+  p.off_bar = (uint32_t)round_up((int)(p.off_x + ns * p.x_bytes + slack), 16);
   const uint32_t smem_bytes = p.off_bar + 256 + 128;
   p.x_cgtot = x.cg(); p.x_cgoff = x_cgoff;
   p.du_cgtot = dy.cg(); p.du_cgoff = dy_cgoff;
   p.dw = dw; p.dw_bstride = dw_bstride;
   p.cout_real = cout_real; p.cin_tot = cin_tot; p.ci_base = ci_base; p.ci_real = ci_real;
   // split the item range so that the grid is about one wave
-  const int fixed = p.ncls * p.K * p.nchunk * p.nmb * (p.per_batch ? p.B : 1);
+  const int fixed = p.ncls * p.nkg * p.nchunk * p.nmb * (p.per_batch ? p.B : 1);
   int nsplit = num_sms() / fixed;   // one wave: a CTA holds its accumulators for its whole life
   const long long max_split = (p.items + 3) / 4;   // at least ~4 tiles per CTA
   if (nsplit > max_split) nsplit = (int)max_split;
@@ -349,8 +364,8 @@ int conv_wgrad(const Act& x, int x_cgoff, int x_cg, const Act& dy, int dy_cgoff,
     attr_set = true;
   }
   if (getenv("FTB_CONV_PLAN"))
-    fprintf(stderr, "wgrad plan: K%d cin %d cout %d @%dx%dx%d B%d -> stack %d ncg %d N %d nacc %d cls %d chunks %d mb %d split %d stages %d smem %u\n",
-            p.K, x_cg * 8, cout_real, p.D, p.H, p.W, p.B, p.stack, p.ncg, p.Nacc, p.nacc, p.ncls, p.nchunk, p.nmb,
+    fprintf(stderr, "wgrad plan: K%d cin %d cout %d @%dx%dx%d B%d -> kdp %d stack %d ncg %d N %d nacc %d cls %d chunks %d mb %d split %d stages %d smem %u\n",
+            p.K, x_cg * 8, cout_real, p.D, p.H, p.W, p.B, p.kdp, p.stack, p.ncg, p.Nacc, p.nacc, p.ncls, p.nchunk, p.nmb,
             p.nsplit, p.nstage, smem_bytes);
   int prof = -1;
   if (prof_enabled()) {
