@@ -210,7 +210,7 @@ def run_train_leg(a, ftb, _lib, dev, rank, world, dist):
     import ctypes as C
     import torch
     from oracle import synth
-    cfg = synth.make_cfg(dropout=0.0)
+    cfg = synth.make_cfg(dropout=0.1)   # get_config() of the reference (model_train_inference.py:40-127)
     kw = {k: v for k, v in cfg.items() if k != "data_channels"}
     S, B = a.size, a.train_batch
     mod = ftb.Geo3DStochInterp(data_shape=(S, S, S), embedding_dim=18, **kw).to(dev)
@@ -270,7 +270,7 @@ def run_train_leg(a, ftb, _lib, dev, rank, world, dist):
         "metric": "train_voxels_per_sec_64cubed", "value": world * B * V / (step_ms * 1e-3), "unit": "voxels/s",
         "ms_per_step": step_ms, "scaling": "weak", "dtype": "bf16 tensor cores, fp32 master weights / Adam / EMA",
         "config": {"workload": f"configs[3]: unconditional {S}^3 interpolant training step, batch {B}/GPU, Adam 2e-4, "
-                               f"clip 1.0, EMA 0.9995 every batch, dropout 0, {world} rank(s)"
+                               f"clip 1.0, EMA 0.9995 every batch, dropout 0.1, {world} rank(s)"
                                + (", NCCL all-reduce bucketed from inside the backward" if world > 1 else ""),
                    "global_batch": world * B},
         "loss": loss_host, "gpu_launches_per_step": launches,

@@ -80,6 +80,7 @@ _SIGS = {
     "ftb_unet3d_param_offset": (_i64, [_vp, _i]),
     "ftb_unet3d_bind_params": (_i, [_vp, _vp, _vp]),
     "ftb_unet3d_mark_dirty": (_i, [_vp]),
+    "ftb_unet3d_set_dropout": (_i, [_vp, _f, C.c_uint64]),
     "ftb_unet3d_train_workspace_bytes": (_sz, [_vp, _i, _i, _i, _i]),
     "ftb_unet3d_forward_train": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "ftb_unet3d_backward": (_i, [_vp, _vp, _vp, _vp, _sz, BUCKET_CB, _vp, _vp]),

@@ -156,6 +156,8 @@ struct ftb_unet {
   const float** d_film_b = nullptr;
   const float** d_film_gs = nullptr;
   int* d_film_off = nullptr;
+  float drop_p = 0.f;            // training: nn.Dropout probability of Block1 (0 = off)
+  unsigned long long drop_seed = 0;
   bool dirty = true;
   bool kshift_stale = true;      // the fused-attention shift vectors lag the weights (training skips them)
   bool dgrad_dirty = true;       // transposed packs for the data gradients lag the weights
@@ -1084,6 +1086,14 @@ int ftb_unet3d_bind_params(ftb_unet* h, float* flat, void* stream) {
   FTB_CUDA(cudaMemcpyAsync(h->d_film_b, hb.data(), nb * sizeof(float*), cudaMemcpyHostToDevice, (cudaStream_t)stream));
   FTB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   h->dirty = true;
+  return 0;
+}
+
+int ftb_unet3d_set_dropout(ftb_unet* h, float p, uint64_t seed) {
+  FTB_CHECK(h, "null handle");
+  FTB_CHECK(p >= 0.f && p < 1.f, "dropout probability must be in [0, 1)");
+  h->drop_p = p;
+  h->drop_seed = seed;
   return 0;
 }
 

@@ -218,7 +218,10 @@ struct TrainFwd {
     const float* s1 = foff >= 0 ? c.film_raw + foff : nullptr;
     const float* sh = foff >= 0 ? c.film_raw + foff + C : nullptr;
     const int fstride = U->film_rows;
-    TRUN(normact_fwd(u, norm, gain, s1, sh, fstride, silu, resid, out, c.st));
+    // nn.Dropout sits at the end of Block.forward (:244) and only block1 gets p > 0 (:261): the FiLM'd block
+    const float dp = foff >= 0 ? U->drop_p : 0.f;
+    const unsigned long long dkey = U->drop_seed * 0x9E3779B97F4A7C15ull + ((unsigned long long)(foff + 1) << 40);
+    TRUN(normact_fwd(u, norm, gain, s1, sh, fstride, silu, resid, out, c.st, dp, dkey));
     const Act Uu = u, O = out, R = resid ? *resid : Act();
     const bool hasr = resid != nullptr;
     T->tape.push_back([=](TrainCtx& c) -> int {
@@ -231,10 +234,10 @@ struct TrainFwd {
       float* S = foff >= 0 ? c.dfilm + foff + C : nullptr;
       if (gu.init) {   // the input also feeds a residual path: add to its gradient
         Act tmp = c.like(Uu);
-        TRUN(normact_bwd(dO, Uu, norm, gain, s1, sh, fstride, silu, tmp, Rb, S, fstride, nullptr, c.st));
+        TRUN(normact_bwd(dO, Uu, norm, gain, s1, sh, fstride, silu, tmp, Rb, S, fstride, nullptr, c.st, dp, dkey));
         TRUN(act_accum(gu.g, tmp, true, c.st));
       } else {
-        TRUN(normact_bwd(dO, Uu, norm, gain, s1, sh, fstride, silu, gu.g, Rb, S, fstride, nullptr, c.st));
+        TRUN(normact_bwd(dO, Uu, norm, gain, s1, sh, fstride, silu, gu.g, Rb, S, fstride, nullptr, c.st, dp, dkey));
       }
       gu.init = true;
       float* ds1 = foff >= 0 ? c.dfilm + foff : nullptr;

@@ -140,11 +140,13 @@ int conv_wgrad(const Act& x, int x_cgoff, int x_cg, const Act& dy, int dy_cgoff,
                int unfold_cin, float* dw, int cin_tot, int ci_base, int ci_real, long long dw_bstride,
                cudaStream_t st);
 // out = act(n * gain[c] * s1[b][c] + sh[b][c]) + resid, n = u / max(||u||_C, 1e-12) when norm
+// drop_p > 0: dropout after the activation with a counter-based mask keyed by drop_key (regenerated in the backward)
 int normact_fwd(const Act& u, bool norm, const float* gain, const float* s1, const float* sh, int fstride, bool silu,
-                const Act* resid, Act& out, cudaStream_t st);
+                const Act* resid, Act& out, cudaStream_t st, float drop_p = 0.f, unsigned long long drop_key = 0);
 // du (may alias dout); R[b][c] += sum_v dz*n, S[b*sstride + c] += sum_v dz, dbias[c] += sum du (each optional)
 int normact_bwd(const Act& dout, const Act& u, bool norm, const float* gain, const float* s1, const float* sh,
-                int fstride, bool silu, Act& du, float* R, float* S, int sstride, float* dbias, cudaStream_t st);
+                int fstride, bool silu, Act& du, float* R, float* S, int sstride, float* dbias, cudaStream_t st,
+                float drop_p = 0.f, unsigned long long drop_key = 0);
 int normact_finish(const float* R, int B, int C, const float* gain, const float* s1, int fstride, float sqrt_c,
                    float* ds1, float* dg, cudaStream_t st);
 int bias_grad(const Act& dy, int cgoff, int C, float* db, cudaStream_t st);

@@ -29,7 +29,22 @@ struct NormActP {
   int fstride;
   float *R, *S, *dbias;         // backward sums: R[b][c] = sum dz*n, S[b][c] = sum dz, dbias[c] = sum du
   int sstride;                  // row stride of S
+  float drop_p;                 // nn.Dropout after the activation (Block.forward :244), 0 = off
+  unsigned long long drop_key;  // per-(step, block) key of the counter-based mask
 };
+
+// Dropout keep-mask of element (b, c, v): counter-based (splitmix64 of the element index xor the key), so the
+// backward regenerates it instead of storing it.  Returns 0 or 1/(1-p).  The stream differs from torch's Philox
+// dropout by construction (SURVEY 7 "Hard parts"): parity runs use p = 0.
+__device__ __forceinline__ float drop_scale(const NormActP& p, size_t elem) {
+  unsigned long long z = (unsigned long long)elem + p.drop_key;
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const float u = (float)(unsigned)(z >> 40) * (1.0f / 16777216.0f);
+  return u < p.drop_p ? 0.f : 1.f / (1.f - p.drop_p);
+}
 
 // out = act(n * gain * s1 + sh) + resid,  n = u / max(||u||_C, 1e-12) (norm) or u
 __global__ void __launch_bounds__(256)
@@ -61,6 +76,7 @@ normact_fwd_kernel(const NormActP p) {
       if (p.gain) y *= __ldg(p.gain + c);
       if (p.s1) y = fmaf(y, __ldg(p.s1 + (size_t)b * p.fstride + c), __ldg(p.sh + (size_t)b * p.fstride + c));
       if (p.silu) y = y * sigm(y);
+      if (p.drop_p > 0.f) y *= drop_scale(p, base + cg * cgs + j);
       if (p.resid) y += r[j];
       f[j] = y;
     }
@@ -106,6 +122,7 @@ normact_bwd_kernel(const NormActP p) {
         float m = p.gain ? __ldg(p.gain + c) : 1.f;
         if (p.s1) m *= __ldg(p.s1 + (size_t)b * p.fstride + c);
         float dz = g[j];
+        if (p.drop_p > 0.f) dz *= drop_scale(p, base + cg * cgs + j);
         if (p.silu) {
           const float z = fmaf(n, m, p.s1 ? __ldg(p.sh + (size_t)b * p.fstride + c) : 0.f);
           const float s = sigm(z);
@@ -136,6 +153,7 @@ normact_bwd_kernel(const NormActP p) {
         float m = p.gain ? __ldg(p.gain + c) : 1.f;
         if (p.s1) m *= __ldg(p.s1 + (size_t)b * p.fstride + c);
         float dz = g[j];
+        if (p.drop_p > 0.f) dz *= drop_scale(p, off + j);
         if (p.silu) {
           const float z = fmaf(n, m, p.s1 ? __ldg(p.sh + (size_t)b * p.fstride + c) : 0.f);
           const float s = sigm(z);
@@ -250,6 +268,7 @@ normact_bwd_small_kernel(const NormActP p, int vpt) {
             const int c = cg * 8 + j;
             const float n = f[j] * rinv, m = s_m[c];
             float dz = d[j];
+            if (p.drop_p > 0.f) dz *= drop_scale(p, base + cg * cgs + j);
             if (p.silu) {
               const float z = fmaf(n, m, s_sh[c]);
               const float sg = sigm(z);
@@ -278,6 +297,7 @@ normact_bwd_small_kernel(const NormActP p, int vpt) {
           const int c = cg * 8 + j;
           const float n = f[j] * rinv, m = s_m[c];
           float dz = d[j];
+          if (p.drop_p > 0.f) dz *= drop_scale(p, base + cg * cgs + j);
           if (p.silu) {
             const float z = fmaf(n, m, s_sh[c]);
             const float sg = sigm(z);
@@ -789,13 +809,14 @@ inline int grid1(size_t n, int threads) {
 }  // namespace
 
 int normact_fwd(const Act& u, bool norm, const float* gain, const float* s1, const float* sh, int fstride, bool silu,
-                const Act* resid, Act& out, cudaStream_t st) {
+                const Act* resid, Act& out, cudaStream_t st, float drop_p, unsigned long long drop_key) {
   FTB_CHECK(out.B == u.B && out.C == u.C && out.voxels() == u.voxels(), "normact: shapes");
   if (resid) FTB_CHECK(resid->C == u.C && resid->voxels() == u.voxels(), "normact: residual shape");
   NormActP p{};
   p.u = u.p; p.out = out.p; p.resid = resid ? resid->p : nullptr;
   p.CG = u.cg(); p.vox = u.voxels(); p.norm = norm; p.silu = silu;
   p.gain = gain; p.s1 = s1; p.sh = sh; p.fstride = fstride;
+  p.drop_p = drop_p; p.drop_key = drop_key;
   dim3 grid((unsigned)((p.vox + 255) / 256), u.B);
   normact_fwd_kernel<<<grid, 256, 0, st>>>(p);
   FTB_LAUNCH_OK();
@@ -803,13 +824,15 @@ int normact_fwd(const Act& u, bool norm, const float* gain, const float* s1, con
 }
 
 int normact_bwd(const Act& dout, const Act& u, bool norm, const float* gain, const float* s1, const float* sh,
-                int fstride, bool silu, Act& du, float* R, float* S, int sstride, float* dbias, cudaStream_t st) {
+                int fstride, bool silu, Act& du, float* R, float* S, int sstride, float* dbias, cudaStream_t st,
+                float drop_p, unsigned long long drop_key) {
   FTB_CHECK(dout.C == u.C && du.C == u.C && dout.voxels() == u.voxels(), "normact_bwd: shapes");
   NormActP p{};
   p.u = u.p; p.dout = dout.p; p.du = du.p;
   p.CG = u.cg(); p.vox = u.voxels(); p.norm = norm; p.silu = silu;
   p.gain = gain; p.s1 = s1; p.sh = sh; p.fstride = fstride;
   p.R = R; p.S = S; p.sstride = sstride; p.dbias = dbias;
+  p.drop_p = drop_p; p.drop_key = drop_key;
   if (dbias == nullptr && (p.CG == 6 || p.CG == 4 || p.CG == 2 || p.CG == 8 || p.CG == 12)) {
     const size_t vblocks = (p.vox + 255) / 256;
     int vpt = (int)(vblocks * u.B / (8 * (size_t)num_sms()));   // ~8 blocks per SM over the batch

@@ -99,6 +99,14 @@ def forward_train(net, xin, tin):
     sync_flat(net)
     ws, base, nbytes = train_workspace(net, xin.device, B, X, Y, Z)
     out = torch.empty_like(xin)
+    # nn.Dropout(p) of every ResnetBlock.block1 (unet_attn_3d.py:244, :261): fresh counter-based mask per forward
+    p_drop = net.dropout_p if net.training else 0.0
+    if net._drop_seed is not None:
+        seed = net._drop_seed
+    else:
+        net._drop_count += 1
+        seed = (torch.initial_seed() * 0x9E3779B1 + net._drop_count) & 0xFFFFFFFFFFFFFFFF
+    _lib.check(_lib.lib.ftb_unet3d_set_dropout(net._handle, float(p_drop), seed))
     _lib.check(_lib.lib.ftb_unet3d_forward_train(net._handle, _lib.ptr(xin), _lib.ptr(tin), _lib.ptr(out), B, X, Y, Z,
                                                  C.c_void_p(base), nbytes, _lib.stream_ptr()))
     return out
@@ -208,8 +216,7 @@ class FlowTrainer:
         import torch.distributed as dist
         self.module = module
         self.net = module.net
-        if self.net.dropout_p != 0.0:
-            raise NotImplementedError("FlowTrainer: dropout > 0 is not implemented on the B200 training path")
+        self.net.train()   # Block1 dropout (if the module was built with dropout > 0) is active, as in Lightning's fit
         self.flat = flatten_parameters(self.net)
         self.gflat = torch.zeros_like(self.flat)
         self.m = torch.zeros_like(self.flat)

@@ -113,6 +113,8 @@ class Unet3D(nn.Module):
         self._use_graph = False
         self.last_launches = 0
         self._flat = None      # flat fp32 parameter buffer once training.flatten_parameters() bound it
+        self._drop_seed = None  # explicit dropout seed for the next train-mode forward (tests); else a counter
+        self._drop_count = 0
 
     # ------------------------------------------------------------------ parameter tree
     def _plan(self):
@@ -213,9 +215,6 @@ class Unet3D(nn.Module):
                 raise NotImplementedError("the gradient w.r.t. the network input is not computed on the B200 path")
             if self._conditional:
                 raise NotImplementedError("backward through Unet3DCond is not implemented (sampling / no_grad only)")
-            if self.dropout_p != 0.0:
-                raise NotImplementedError("training with dropout > 0 is not implemented on the B200 path "
-                                          "(construct the module with dropout=0.0)")
         if x.dim() != 5 or x.shape[1] != self.channels:
             raise ValueError(f"expected x of shape [B,{self.channels},X,Y,Z], got {tuple(x.shape)}")
         B, _, X, Y, Z = x.shape
@@ -275,6 +274,11 @@ class Unet3D(nn.Module):
             C.c_void_p(base), ws.numel() - (base - ws.data_ptr()), _lib.stream_ptr()))
         self.last_launches = _lib.lib.ftb_unet3d_last_launches(self._handle)
         return out
+
+    def set_dropout_seed(self, seed):
+        """Pin the dropout mask of the following train-mode forwards (None: a fresh mask per forward)."""
+        self._drop_seed = None if seed is None else int(seed)
+        return self
 
     def _needs_grad(self, x):
         return torch.is_grad_enabled() and self.training and (

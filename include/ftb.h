@@ -135,6 +135,10 @@ int ftb_mse_ratio_accumulate(const float* v, const float* vhat, int64_t n, doubl
 int64_t ftb_unet3d_param_offset(ftb_unet* h, int i);
 int ftb_unet3d_bind_params(ftb_unet* h, float* flat_params, void* stream);
 int ftb_unet3d_mark_dirty(ftb_unet* h);
+/* nn.Dropout(p) at the end of every ResnetBlock.block1 (unet_attn_3d.py:244, :261) for the NEXT forward_train:
+ * counter-based keep mask keyed by `seed` (pass a fresh seed per step), regenerated by the backward, scale 1/(1-p).
+ * The random stream is this library's own (torch's Philox dropout stream cannot be matched); p = 0 turns it off. */
+int ftb_unet3d_set_dropout(ftb_unet* h, float p, uint64_t seed);
 size_t ftb_unet3d_train_workspace_bytes(ftb_unet* h, int B, int X, int Y, int Z);
 int ftb_unet3d_forward_train(ftb_unet* h, const float* x, const float* t, float* out, int B, int X, int Y, int Z,
                              void* workspace, size_t workspace_bytes, void* stream);

@@ -356,3 +356,60 @@ def test_flow_trainer_data_parallel_nccl(ftb):
                        capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "DDP_OK" in r.stdout
+
+
+def test_dropout_mask_is_consistent_between_forward_and_backward(ftb, dev):
+    """dropout 0.1 (the reference's training default): the counter-based mask is regenerated by the backward.
+    Pinned seed -> identical forwards; fresh seed -> different; and the directional derivative along the gradient,
+    measured by central differences of the (mask-pinned) loss, matches |g| — it would not if forward and
+    backward disagreed on which activations were dropped."""
+    from flowtrain_stochastic_interpolation_b200 import training
+    from oracle import synth
+    cfg = synth.make_cfg(dim=32, dim_mults=(1, 2), data_channels=18, time_resolution=64, time_bandwidth=100.0,
+                         attn_heads=2, attn_dim_head=16, dropout=0.1)
+    net = ftb.Unet3D(**cfg).to(dev)
+    net.load_state_dict(synth.synth_unet3d_params(cfg, 3))
+    net.train()
+    shape = (2, 18, 16, 16, 16)
+    xt, vt = synth.synth_input(shape, 11, "xt").to(dev), synth.synth_input(shape, 12, "vt").to(dev)
+    t = synth.synth_times(2, 13).to(dev)
+
+    def loss_of(out):
+        return torch.nn.functional.mse_loss(vt, out) / torch.nn.functional.mse_loss(vt, torch.zeros_like(vt))
+
+    net.set_dropout_seed(1234)
+    y1 = net(xt, t)
+    l1 = loss_of(y1)
+    l1.backward()
+    g = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).clone()
+    with torch.no_grad():
+        y1b = training.forward_train(net, xt, t)
+        net.set_dropout_seed(99)
+        y2 = training.forward_train(net, xt, t)
+        net.eval()
+        y0 = net(xt, t)
+        net.train()
+    assert torch.equal(y1.detach(), y1b)
+    d12 = rel(y2, y1.detach())
+    d10 = rel(y1.detach(), y0)
+    print(f"dropout: other mask differs by {d12:.3f}, eval vs train {d10:.3f}")
+    assert 1e-3 < d12 < 1.0 and 1e-3 < d10 < 1.0
+    # central difference along the gradient direction with the mask pinned
+    net.set_dropout_seed(1234)
+    gn = g.double().norm().item()
+    eps = 0.05
+    flat = net._flat
+    p0 = flat.clone()
+    with torch.no_grad():
+        vals = []
+        for sgn in (+1, -1):
+            flat.copy_(p0 + sgn * eps * g / gn)
+            for p in net.parameters():
+                p._version  # noqa: B018  (flat-bound views: mark dirty explicitly)
+            from flowtrain_stochastic_interpolation_b200 import _lib
+            _lib.check(_lib.lib.ftb_unet3d_mark_dirty(net._handle))
+            vals.append(loss_of(training.forward_train(net, xt, t)).item())
+        flat.copy_(p0)
+    fd = (vals[0] - vals[1]) / (2 * eps)
+    print(f"dropout: directional derivative {fd:.4f} vs |g| {gn:.4f}")
+    assert abs(fd - gn) <= 0.15 * gn
