@@ -33,17 +33,31 @@ struct NormActP {
   unsigned long long drop_key;  // per-(step, block) key of the counter-based mask
 };
 
-// Dropout keep-mask of element (b, c, v): counter-based (splitmix64 of the element index xor the key), so the
-// backward regenerates it instead of storing it.  Returns 0 or 1/(1-p).  The stream differs from torch's Philox
-// dropout by construction (SURVEY 7 "Hard parts"): parity runs use p = 0.
-__device__ __forceinline__ float drop_scale(const NormActP& p, size_t elem) {
-  unsigned long long z = (unsigned long long)elem + p.drop_key;
-  z += 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  const float u = (float)(unsigned)(z >> 40) * (1.0f / 16777216.0f);
-  return u < p.drop_p ? 0.f : 1.f / (1.f - p.drop_p);
+// Dropout keep-mask, counter-based so the backward regenerates it instead of storing it: one 64-bit hash per
+// (voxel, 8-channel group) gives 8 bits per element; element j is dropped when its byte < t = round(256 p), and
+// kept values are scaled by 256/(256 - t) (the exact inverse keep probability of this mask).  The stream differs
+// from torch's Philox dropout by construction (SURVEY 7 "Hard parts"): parity runs use p = 0.
+struct DropMask {
+  unsigned long long bits;
+  unsigned t;
+  float scale;
+  __device__ __forceinline__ float operator()(int j) const {
+    return ((unsigned)(bits >> (8 * j)) & 255u) < t ? 0.f : scale;
+  }
+};
+__device__ __forceinline__ unsigned mix32(unsigned x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ DropMask drop_mask8(const NormActP& p, size_t group) {
+  DropMask m;
+  m.t = (unsigned)(p.drop_p * 256.f + 0.5f);
+  m.scale = 256.f / (256.f - (float)m.t);
+  const unsigned g = (unsigned)group ^ ((unsigned)(group >> 32) * 0x85ebca6bu);
+  const unsigned k0 = (unsigned)p.drop_key, k1 = (unsigned)(p.drop_key >> 32);
+  const unsigned h0 = mix32(g ^ k0), h1 = mix32((g + 0x9E3779B9u) ^ k1 ^ h0);
+  m.bits = ((unsigned long long)h1 << 32) | h0;
+  return m;
 }
 
 // out = act(n * gain * s1 + sh) + resid,  n = u / max(||u||_C, 1e-12) (norm) or u
@@ -69,6 +83,8 @@ normact_fwd_kernel(const NormActP p) {
     float f[8], r[8];
     unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.u + base + cg * cgs)), f);
     if (p.resid) unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.resid + base + cg * cgs)), r);
+    DropMask dm;
+    if (p.drop_p > 0.f) dm = drop_mask8(p, (base + cg * cgs) >> 3);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = cg * 8 + j;
@@ -76,7 +92,7 @@ normact_fwd_kernel(const NormActP p) {
       if (p.gain) y *= __ldg(p.gain + c);
       if (p.s1) y = fmaf(y, __ldg(p.s1 + (size_t)b * p.fstride + c), __ldg(p.sh + (size_t)b * p.fstride + c));
       if (p.silu) y = y * sigm(y);
-      if (p.drop_p > 0.f) y *= drop_scale(p, base + cg * cgs + j);
+      if (p.drop_p > 0.f) y *= dm(j);
       if (p.resid) y += r[j];
       f[j] = y;
     }
@@ -115,6 +131,8 @@ normact_bwd_kernel(const NormActP p) {
       float f[8], g[8];
       unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.u + base + cg * cgs)), f);
       unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.dout + base + cg * cgs)), g);
+      DropMask dm;
+      if (p.drop_p > 0.f) dm = drop_mask8(p, (base + cg * cgs) >> 3);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int c = cg * 8 + j;
@@ -122,7 +140,7 @@ normact_bwd_kernel(const NormActP p) {
         float m = p.gain ? __ldg(p.gain + c) : 1.f;
         if (p.s1) m *= __ldg(p.s1 + (size_t)b * p.fstride + c);
         float dz = g[j];
-        if (p.drop_p > 0.f) dz *= drop_scale(p, base + cg * cgs + j);
+        if (p.drop_p > 0.f) dz *= dm(j);
         if (p.silu) {
           const float z = fmaf(n, m, p.s1 ? __ldg(p.sh + (size_t)b * p.fstride + c) : 0.f);
           const float s = sigm(z);
@@ -146,6 +164,8 @@ normact_bwd_kernel(const NormActP p) {
       float f[8], g[8];
       unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.u + off)), f);
       unpack_bf16x8(*reinterpret_cast<const uint4*>(p.dout + off), g);
+      DropMask dm;
+      if (p.drop_p > 0.f) dm = drop_mask8(p, off >> 3);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int c = cg * 8 + j;
@@ -153,7 +173,7 @@ normact_bwd_kernel(const NormActP p) {
         float m = p.gain ? __ldg(p.gain + c) : 1.f;
         if (p.s1) m *= __ldg(p.s1 + (size_t)b * p.fstride + c);
         float dz = g[j];
-        if (p.drop_p > 0.f) dz *= drop_scale(p, off + j);
+        if (p.drop_p > 0.f) dz *= dm(j);
         if (p.silu) {
           const float z = fmaf(n, m, p.s1 ? __ldg(p.sh + (size_t)b * p.fstride + c) : 0.f);
           const float s = sigm(z);
@@ -263,12 +283,14 @@ normact_bwd_small_kernel(const NormActP p, int vpt) {
           float f[8], d[8];
           unpack_bf16x8(U[cg], f);
           unpack_bf16x8(G[cg], d);
+          DropMask dm;
+          if (p.drop_p > 0.f) dm = drop_mask8(p, (base + cg * cgs) >> 3);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int c = cg * 8 + j;
             const float n = f[j] * rinv, m = s_m[c];
             float dz = d[j];
-            if (p.drop_p > 0.f) dz *= drop_scale(p, base + cg * cgs + j);
+            if (p.drop_p > 0.f) dz *= dm(j);
             if (p.silu) {
               const float z = fmaf(n, m, s_sh[c]);
               const float sg = sigm(z);
@@ -292,12 +314,14 @@ normact_bwd_small_kernel(const NormActP p, int vpt) {
         float f[8], d[8];
         unpack_bf16x8(U[cg], f);
         unpack_bf16x8(G[cg], d);
+        DropMask dm;
+        if (p.drop_p > 0.f) dm = drop_mask8(p, (base + cg * cgs) >> 3);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int c = cg * 8 + j;
           const float n = f[j] * rinv, m = s_m[c];
           float dz = d[j];
-          if (p.drop_p > 0.f) dz *= drop_scale(p, base + cg * cgs + j);
+          if (p.drop_p > 0.f) dz *= dm(j);
           if (p.silu) {
             const float z = fmaf(n, m, s_sh[c]);
             const float sg = sigm(z);
