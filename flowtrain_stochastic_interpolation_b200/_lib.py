@@ -10,7 +10,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libftb.so")
+LIB_PATH = os.environ.get("FTB_LIB_PATH") or os.path.join(_HERE, "csrc", "libftb.so")   # override: A/B builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "ftb.h")
 
 FTB_MAX_STAGES = 8

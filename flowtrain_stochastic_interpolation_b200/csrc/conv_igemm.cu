@@ -88,6 +88,9 @@ struct IgemmParams {
   int pre_cgtot, pre_cgoff, pre_cg;
   int flags, q_dh;
   float q_scale;
+  bf16* u_out;                 // training: pre-norm output (same channel layout as `out`), or null
+  float drop_p;                // training: dropout after the activation
+  unsigned long long drop_key;
 };
 
 struct ItemCoord {
@@ -114,6 +117,8 @@ __device__ __forceinline__ ItemCoord decode_item(const IgemmParams& p, int item)
 struct EpiCtx {
   const float *bias, *mul, *add;   // shared memory, this half's copy for the current sample
   bf16* out_b;                     // output base of sample b
+  bf16* u_b;                       // pre-norm output base of sample b (or null)
+  int b;                           // sample index (dropout mask key)
   const bf16* res_b;               // residual base of sample b (or null)
   float* f32_b;                    // NCDHW fp32 output base of sample b (or null)
   size_t cgs;                      // voxels per channel-group plane (D*H*W)
@@ -128,6 +133,7 @@ __device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f 
 
 // finish 16 consecutive channels [c0, c0+16) of one voxel: SiLU, + residual, store.
 // `pre` (optional) holds the residual's two 16-byte groups, loaded by the caller ahead of time.
+template <bool kTrain = false>
 __device__ __forceinline__ void epi_store16(const IgemmParams& p, EpiCtx& ec, int c0, size_t vox,
                                             float (&v)[16], uint4 pre0 = uint4(), uint4 pre1 = uint4(),
                                             bool use_pre = false) {
@@ -136,6 +142,12 @@ __device__ __forceinline__ void epi_store16(const IgemmParams& p, EpiCtx& ec, in
     for (int j = 0; j < 16; ++j) v[j] = silu_fast(v[j]);
   }
   if (!ec.valid) return;
+  if (kTrain && p.drop_p > 0.f) {   // nn.Dropout after the activation (training only)
+    const size_t grp = ((size_t)ec.b * p.out_cgtot + p.out_cgoff + (c0 >> 3)) * ec.cgs + vox;
+    const DropMask d0 = drop_mask8(p.drop_p, p.drop_key, grp), d1 = drop_mask8(p.drop_p, p.drop_key, grp + ec.cgs);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { v[j] *= d0(j); v[8 + j] *= d1(j); }
+  }
   if (ec.res_b) {
     uint4 u0, u1;
     if (use_pre) {
@@ -249,7 +261,7 @@ __device__ __forceinline__ void epi_plain(const IgemmParams& p, EpiCtx& ec, uint
 
 // channel RMSNorm (unet_attn_3d.py:127-128) with the whole voxel row held in registers:
 // v = acc*rs + bias; y = v / max(||v||, 1e-12) * mul + add
-template <int NCH>
+template <int NCH, bool kTrain>
 __device__ __forceinline__ void epi_norm_regs(const IgemmParams& p, EpiCtx& ec, uint32_t trow,
                                               size_t vox, float rs) {
   constexpr bool kPre = NCH <= 3;   // residual row preloaded into registers (else L1 prefetch)
@@ -284,6 +296,17 @@ __device__ __forceinline__ void epi_norm_regs(const IgemmParams& p, EpiCtx& ec, 
       r[ch][j4 + 2] = __float_as_uint(a2); r[ch][j4 + 3] = __float_as_uint(a3);
     }
   const float rinv = 1.f / fmaxf(sqrtf((ss[0] + ss[1]) + (ss[2] + ss[3])), 1e-12f);
+  if (kTrain && ec.u_b && ec.valid) {   // training: the pre-norm row
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[ch][hf * 8 + j]);
+        *reinterpret_cast<uint4*>(ec.u_b + ((size_t)(p.out_cgoff + ch * 2 + hf) * ec.cgs + vox) * 8) = pack_bf16x8(f);
+      }
+  }
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
     float v[16];
@@ -296,12 +319,13 @@ __device__ __forceinline__ void epi_norm_regs(const IgemmParams& p, EpiCtx& ec, 
       v[j4 + 2] = fmaf(__uint_as_float(r[ch][j4 + 2]) * rinv, mu.z, ad.z);
       v[j4 + 3] = fmaf(__uint_as_float(r[ch][j4 + 3]) * rinv, mu.w, ad.w);
     }
-    if (kPre) epi_store16(p, ec, ch * 16, vox, v, pre[2 * ch], pre[2 * ch + 1], true);
-    else epi_store16(p, ec, ch * 16, vox, v);
+    if (kPre) epi_store16<kTrain>(p, ec, ch * 16, vox, v, pre[2 * ch], pre[2 * ch + 1], true);
+    else epi_store16<kTrain>(p, ec, ch * 16, vox, v);
   }
 }
 
 // same, any N: one TMEM pass for the norm, a second for the output
+template <bool kTrain>
 __device__ __forceinline__ void epi_norm_2pass(const IgemmParams& p, EpiCtx& ec, uint32_t trow,
                                                size_t vox, float rs) {
   epi_prefetch_resid(p, ec, vox);
@@ -346,12 +370,25 @@ __device__ __forceinline__ void epi_norm_2pass(const IgemmParams& p, EpiCtx& ec,
       const float4 bi = *reinterpret_cast<const float4*>(ec.bias + c0 + j4);
       const float4 mu = *reinterpret_cast<const float4*>(ec.mul + c0 + j4);
       const float4 ad = *reinterpret_cast<const float4*>(ec.add + c0 + j4);
-      v[j4 + 0] = fmaf(fmaf(__uint_as_float(r0[j4 + 0]), rs, bi.x) * rinv, mu.x, ad.x);
-      v[j4 + 1] = fmaf(fmaf(__uint_as_float(r0[j4 + 1]), rs, bi.y) * rinv, mu.y, ad.y);
-      v[j4 + 2] = fmaf(fmaf(__uint_as_float(r0[j4 + 2]), rs, bi.z) * rinv, mu.z, ad.z);
-      v[j4 + 3] = fmaf(fmaf(__uint_as_float(r0[j4 + 3]), rs, bi.w) * rinv, mu.w, ad.w);
+      const float a0 = fmaf(__uint_as_float(r0[j4 + 0]), rs, bi.x), a1 = fmaf(__uint_as_float(r0[j4 + 1]), rs, bi.y);
+      const float a2 = fmaf(__uint_as_float(r0[j4 + 2]), rs, bi.z), a3 = fmaf(__uint_as_float(r0[j4 + 3]), rs, bi.w);
+      r0[j4 + 0] = __float_as_uint(a0); r0[j4 + 1] = __float_as_uint(a1);
+      r0[j4 + 2] = __float_as_uint(a2); r0[j4 + 3] = __float_as_uint(a3);
+      v[j4 + 0] = fmaf(a0 * rinv, mu.x, ad.x);
+      v[j4 + 1] = fmaf(a1 * rinv, mu.y, ad.y);
+      v[j4 + 2] = fmaf(a2 * rinv, mu.z, ad.z);
+      v[j4 + 3] = fmaf(a3 * rinv, mu.w, ad.w);
     }
-    epi_store16(p, ec, c0, vox, v);
+    if (kTrain && ec.u_b && ec.valid) {   // training: the pre-norm row
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r0[hf * 8 + j]);
+        *reinterpret_cast<uint4*>(ec.u_b + ((size_t)(p.out_cgoff + (c0 >> 3) + hf) * ec.cgs + vox) * 8) = pack_bf16x8(f);
+      }
+    }
+    epi_store16<kTrain>(p, ec, c0, vox, v);
   }
 }
 
@@ -435,6 +472,7 @@ __device__ __forceinline__ void issue_entries(const IssueCtx& ic, uint32_t ea, u
   }
 }
 
+template <bool kTrain>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                   const IgemmParams p) {
@@ -746,6 +784,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
         cur_b = c.b;
       }
       ec.out_b = p.out + (size_t)c.b * p.out_cgtot * cgs * 8;
+      ec.u_b = p.u_out ? p.u_out + (size_t)c.b * p.out_cgtot * cgs * 8 : nullptr;
+      ec.b = c.b;
       ec.res_b = p.resid ? p.resid + (size_t)c.b * p.resid_cgtot * cgs * 8 : nullptr;
       ec.f32_b = p.out_f32 ? p.out_f32 + (size_t)c.b * p.out_f32_c * cgs : nullptr;
       for (int g = 0; g < ngroups; ++g, ++gctr) {
@@ -785,8 +825,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
             if (p.q_dh == 32) epi_qsoftmax<32>(p, ec, trow, vox, rs);
             else epi_qsoftmax<16>(p, ec, trow, vox, rs);
           } else if (p.norm) {
-            if (p.N == 48) epi_norm_regs<3>(p, ec, trow, vox, rs);
-            else epi_norm_2pass(p, ec, trow, vox, rs);
+            if (p.N == 48) epi_norm_regs<3, kTrain>(p, ec, trow, vox, rs);
+            else epi_norm_2pass<kTrain>(p, ec, trow, vox, rs);
           } else if (p.flags & F_PLAIN) {
             epi_plain(p, ec, trow, vox, rs);
           } else {
@@ -1073,6 +1113,14 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   p.ss_out = e.sumsq_out;
   if (e.prenorm) { p.pre_src = a0.p; p.pre_cgtot = a0.cg(); p.pre_cgoff = s0.cgoff; p.pre_cg = s0.cg; }
   p.q_dh = e.q_dim_head; p.q_scale = e.q_scale;
+  p.u_out = nullptr;
+  if (e.pre_out) {
+    FTB_CHECK(e.norm && w.ntiles == 1, "conv: the pre-norm side output needs the norm epilogue and a single N tile");
+    FTB_CHECK(e.pre_out->C == out.C && e.pre_out->voxels() == out.voxels() && e.pre_out->B == out.B,
+              "conv: pre-norm output must be shaped like the output");
+    p.u_out = e.pre_out->p;
+  }
+  p.drop_p = e.drop_p; p.drop_key = e.drop_key;
 
   CUtensorMap tm0, tm1;
   const int box0 = pick(p.cg0), box1 = s1.t ? pick(p.cg1) : 0;   // TMA box = one channel chunk
@@ -1086,7 +1134,9 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
 
   static bool attr_set = false;
   if (!attr_set) {
-    FTB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FTB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(kSmemLimit + 128)));
+    FTB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(kSmemLimit + 128)));
     attr_set = true;
   }
@@ -1114,7 +1164,10 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
       const double bytes = vox * (cin + cout) * 2.0;  // read input once, write output once (bf16)
       prof = prof_begin(st, flops, bytes, w.ksize > 1 ? 0 : 1);
     }
-    conv_igemm_kernel<<<grid, kThreads, smem_bytes, st>>>(tm0, tm1, q);
+    // the training epilogue (pre-norm side output, dropout) is a separate instantiation: the inference kernel
+    // carries none of its code
+    if (q.u_out || q.drop_p > 0.f) conv_igemm_kernel<true><<<grid, kThreads, smem_bytes, st>>>(tm0, tm1, q);
+    else conv_igemm_kernel<false><<<grid, kThreads, smem_bytes, st>>>(tm0, tm1, q);
     prof_end(prof, st);
     FTB_LAUNCH_OK();
   }

@@ -213,6 +213,7 @@ int conv_naive(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
                Act& out, int out_cgoff, cudaStream_t st) {
   const Act& a0 = *s0.t;
   FTB_CHECK((s0.cg + s1.cg) * 8 == w.cin, "conv_naive: weight K extent does not match the sources");
+  FTB_CHECK(!e.pre_out && e.drop_p == 0.f, "conv_naive: the training epilogue (pre-norm output, dropout) is tcgen05-only");
   NaiveParams p{};
   p.B = a0.B; p.D = a0.D; p.H = a0.H; p.W = a0.W; p.K = w.ksize; p.pad = (w.ksize - 1) / 2;
   p.Kw = w.kw(); p.padw = (p.Kw - 1) / 2;

@@ -42,6 +42,7 @@ struct TrainCtx {
   float* grads = nullptr;          // flat parameter gradients (state_dict order)
   const float* dout = nullptr;     // dL/d(output) NCDHW fp32
   float* film_raw = nullptr;       // [B][film_rows]: (scale+1 | shift) per block
+  float* film_fold = nullptr;      // [B][film_rows]: ((scale+1)*g*sqrt(C) | shift), the fused conv epilogue's operands
   float* dfilm = nullptr;          // [B][film_rows]
   float* temb_silu = nullptr;      // [B][time_dim]
   float* dts = nullptr;            // [B][time_dim] gradient w.r.t. silu(temb)
@@ -102,7 +103,7 @@ struct TrainFwd {
   ftb_unet* U;
   TrainState* T;
   TrainCtx& c;       // allocator shared with the backward
-  bool leaf_next = false;
+  bool fuse = getenv("FTB_TRAIN_NOFUSE") == nullptr;   // norm/FiLM/SiLU in the conv epilogue (pre-norm side output)
 
   ConvWeights weights(const ConvLayer& cl) {
     ConvWeights w;
@@ -135,7 +136,8 @@ struct TrainFwd {
 
   // out = conv(x0 [|| x1]) + bias (+ resid) (q softmax on the first N tile when qsm); out_f32: NCDHW fp32 output
   int conv(const std::string& name, const Act& x0, const Act* x1, int c0_real, int c1_real, const Act* resid, bool qsm,
-           float* out_f32, Act& out, bool leaf, bool f32out = false) {
+           float* out_f32, Act& out, bool leaf, bool f32out = false, bool bias_by_consumer = false,
+           const ConvEpilogue* fused = nullptr, Act* fused_out = nullptr) {
     const ConvLayer& cl = U->convs.at(name);
     ConvWeights w = weights(cl);
     ConvEpilogue e;
@@ -153,7 +155,16 @@ struct TrainFwd {
       if (x1) split.push_back(c1_real);
       FTB_TRY(ensure_dgrad(name, split));
     }
-    TRUN(conv_dispatch(s0, s1, w, e, out, 0, c.st));
+    if (fused) {
+      // norm / FiLM / SiLU / dropout / residual fused into this conv's epilogue (as on the inference path); the
+      // pre-norm tensor `out` that the backward needs is a side output of the same launch
+      ConvEpilogue ef = *fused;
+      ef.bias = e.bias;
+      ef.pre_out = &out;
+      TRUN(conv_dispatch(s0, s1, w, ef, *fused_out, 0, c.st));
+    } else {
+      TRUN(conv_dispatch(s0, s1, w, e, out, 0, c.st));
+    }
     // ---- backward closure
     const Act X0 = x0, X1 = x1 ? *x1 : Act(), R = resid ? *resid : Act(), O = out;
     const bool has1 = x1 != nullptr, hasr = resid != nullptr;
@@ -168,7 +179,8 @@ struct TrainFwd {
         FTB_TRY(c.need(O, &dY, name.c_str()));
       }
       if (hasr) FTB_TRY(c.accumulate(R, dY));
-      if (!cl.bname.empty()) TRUN(bias_grad(dY, 0, cl.cout, c.gptr(cl.bname), c.st));
+      // (when a norm/activation pass consumes this conv's output, its backward already summed dY per channel)
+      if (!cl.bname.empty() && !bias_by_consumer) TRUN(bias_grad(dY, 0, cl.cout, c.gptr(cl.bname), c.st));
       // weight gradient
       const int cin_tot = cl.cin;
       float* dw = c.gptr(cl.wname);
@@ -211,7 +223,7 @@ struct TrainFwd {
 
   // out = act(norm(u) * gain * s1 + sh) + resid
   int normact(const Act& u, bool norm, const std::string& gain_name, const std::string& film_block, bool silu,
-              const Act* resid, Act& out) {
+              const Act* resid, Act& out, const std::string& bias_of_u = "", bool forward_done = false) {
     const int C = u.C;
     const float* gain = gain_name.empty() ? nullptr : U->gains.at(gain_name).gs;
     const int foff = film_block.empty() ? -1 : U->film_off.at(film_block);
@@ -221,7 +233,7 @@ struct TrainFwd {
     // nn.Dropout sits at the end of Block.forward (:244) and only block1 gets p > 0 (:261): the FiLM'd block
     const float dp = foff >= 0 ? U->drop_p : 0.f;
     const unsigned long long dkey = U->drop_seed * 0x9E3779B97F4A7C15ull + ((unsigned long long)(foff + 1) << 40);
-    TRUN(normact_fwd(u, norm, gain, s1, sh, fstride, silu, resid, out, c.st, dp, dkey));
+    if (!forward_done) TRUN(normact_fwd(u, norm, gain, s1, sh, fstride, silu, resid, out, c.st, dp, dkey));
     const Act Uu = u, O = out, R = resid ? *resid : Act();
     const bool hasr = resid != nullptr;
     T->tape.push_back([=](TrainCtx& c) -> int {
@@ -232,12 +244,13 @@ struct TrainFwd {
       FTB_TRY(c.zero(Rb, (size_t)c.B * C * sizeof(float)));
       TrainCtx::GradSlot& gu = c.grad(Uu);
       float* S = foff >= 0 ? c.dfilm + foff + C : nullptr;
+      float* dbias = bias_of_u.empty() ? nullptr : c.gptr(bias_of_u);   // bias gradient of the conv that produced u
       if (gu.init) {   // the input also feeds a residual path: add to its gradient
         Act tmp = c.like(Uu);
-        TRUN(normact_bwd(dO, Uu, norm, gain, s1, sh, fstride, silu, tmp, Rb, S, fstride, nullptr, c.st, dp, dkey));
+        TRUN(normact_bwd(dO, Uu, norm, gain, s1, sh, fstride, silu, tmp, Rb, S, fstride, dbias, c.st, dp, dkey));
         TRUN(act_accum(gu.g, tmp, true, c.st));
       } else {
-        TRUN(normact_bwd(dO, Uu, norm, gain, s1, sh, fstride, silu, gu.g, Rb, S, fstride, nullptr, c.st, dp, dkey));
+        TRUN(normact_bwd(dO, Uu, norm, gain, s1, sh, fstride, silu, gu.g, Rb, S, fstride, dbias, c.st, dp, dkey));
       }
       gu.init = true;
       float* ds1 = foff >= 0 ? c.dfilm + foff : nullptr;
@@ -269,12 +282,34 @@ struct TrainFwd {
     return 0;
   }
 
+  // epilogue equivalent of normact(norm, gain, film, silu, resid) for the fused train-mode conv
+  ConvEpilogue fused_epilogue(const std::string& gain_name, const std::string& film_block, int C, bool silu,
+                              const Act* resid) {
+    ConvEpilogue e;
+    e.norm = true;
+    if (!film_block.empty()) {
+      const int foff = U->film_off.at(film_block);
+      e.mul = c.film_fold + foff; e.mul_stride = U->film_rows;           // (scale + 1) * g * sqrt(C)
+      e.add = c.film_fold + foff + C; e.add_stride = U->film_rows;
+      e.drop_p = U->drop_p;
+      e.drop_key = U->drop_seed * 0x9E3779B97F4A7C15ull + ((unsigned long long)(foff + 1) << 40);
+    } else {
+      e.mul = U->gains.at(gain_name).gs;
+    }
+    e.silu = silu;
+    e.resid = resid;
+    return e;
+  }
+  bool fuse_ok(int cout) const { return fuse && round_up(cout, 16) <= 256; }
+
   // ResnetBlock (:265-278)
   int resnet(const std::string& p, const Act& x0, const Act* x1, int c0, int c1, int cout, Act* out) {
     const std::string film = resnet_mlp(U, p);
     Act u1 = c.act(cout, x0.D, x0.H, x0.W), h1 = c.like(u1);
-    FTB_TRY(conv(p + ".block1.proj", x0, x1, c0, c1, nullptr, false, nullptr, u1, false));
-    FTB_TRY(normact(u1, true, p + ".block1.norm.g", film, true, nullptr, h1));
+    const bool fz = fuse_ok(cout);
+    ConvEpilogue f1 = fused_epilogue(p + ".block1.norm.g", film, cout, true, nullptr);
+    FTB_TRY(conv(p + ".block1.proj", x0, x1, c0, c1, nullptr, false, nullptr, u1, false, false, true, fz ? &f1 : nullptr, &h1));
+    FTB_TRY(normact(u1, true, p + ".block1.norm.g", film, true, nullptr, h1, p + ".block1.proj.bias", fz));
     Act res = x0;
     const int cin = c0 + (x1 ? c1 : 0);
     if (cin != cout) {
@@ -283,8 +318,9 @@ struct TrainFwd {
     }
     Act u2 = c.like(u1);
     *out = c.like(u1);
-    FTB_TRY(conv(p + ".block2.proj", h1, nullptr, cout, 0, nullptr, false, nullptr, u2, false));
-    FTB_TRY(normact(u2, true, p + ".block2.norm.g", "", true, &res, *out));
+    ConvEpilogue f2 = fused_epilogue(p + ".block2.norm.g", "", cout, true, &res);
+    FTB_TRY(conv(p + ".block2.proj", h1, nullptr, cout, 0, nullptr, false, nullptr, u2, false, false, true, fz ? &f2 : nullptr, out));
+    FTB_TRY(normact(u2, true, p + ".block2.norm.g", "", true, &res, *out, p + ".block2.proj.bias", fz));
     return 0;
   }
 
@@ -384,8 +420,10 @@ struct TrainFwd {
       return 0;
     });
     Act uo = c.like(x);
-    FTB_TRY(conv(p + ".to_out.0", o, nullptr, hd, 0, nullptr, false, nullptr, uo, false));
-    FTB_TRY(normact(uo, true, p + ".to_out.1.g", "", false, &x, *out));
+    const bool fz = fuse_ok(C);
+    ConvEpilogue fo = fused_epilogue(p + ".to_out.1.g", "", C, false, &x);
+    FTB_TRY(conv(p + ".to_out.0", o, nullptr, hd, 0, nullptr, false, nullptr, uo, false, false, true, fz ? &fo : nullptr, out));
+    FTB_TRY(normact(uo, true, p + ".to_out.1.g", "", false, &x, *out, p + ".to_out.0.bias", fz));
     return 0;
   }
 
@@ -422,6 +460,7 @@ struct TrainFwd {
     c.temb_silu = c.f32((size_t)c.B * td);
     float* tsave = c.f32((size_t)c.B * (tr + 2 * td));
     c.film_raw = c.f32((size_t)c.B * U->film_rows);
+    c.film_fold = c.f32((size_t)c.B * U->film_rows);
     float* tcopy = c.f32((size_t)c.B);
     if (!c.dry) FTB_CUDA(cudaMemcpyAsync(tcopy, t, c.B * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
     T->t_dev = tcopy;
@@ -432,6 +471,9 @@ struct TrainFwd {
       TRUN(time_embed(tp, tcopy, c.B, temb, c.temb_silu, c.st, tsave));
       FilmTable ft{U->d_film_w, U->d_film_b, nullptr, U->d_film_off, (int)U->film_blocks.size(), U->film_rows, td};
       TRUN(film_mlps(ft, c.temb_silu, c.B, c.film_raw, c.st));
+      FilmTable ftf = ft;
+      ftf.gs = U->d_film_gs;
+      TRUN(film_mlps(ftf, c.temb_silu, c.B, c.film_fold, c.st));
       T->tape.push_back([=](TrainCtx& c) -> int {
         // d silu(temb) -> time_mlp.3 -> GELU -> time_mlp.1 -> Fourier features
         const int B = c.B;

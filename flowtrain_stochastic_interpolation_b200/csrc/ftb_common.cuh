@@ -246,6 +246,33 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16_f32(int M, int N) {
   return d;
 }
 
+// Dropout keep-mask, counter-based so the backward regenerates it instead of storing it: one 64-bit hash per
+// (voxel, 8-channel group) gives 8 bits per element; element j is dropped when its byte < t = round(256 p), and
+// kept values are scaled by 256/(256 - t) (the exact inverse keep probability of this mask).  `group` is the index
+// of the 16-byte unit inside the blocked tensor: (b*CG + cg)*voxels + v.
+struct DropMask {
+  unsigned long long bits;
+  unsigned t;
+  float scale;
+  __device__ __forceinline__ float operator()(int j) const {
+    return ((unsigned)(bits >> (8 * j)) & 255u) < t ? 0.f : scale;
+  }
+};
+__device__ __forceinline__ unsigned mix32(unsigned x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ DropMask drop_mask8(float drop_p, unsigned long long key, size_t group) {
+  DropMask m;
+  m.t = (unsigned)(drop_p * 256.f + 0.5f);
+  m.scale = 256.f / (256.f - (float)m.t);
+  const unsigned g = (unsigned)group ^ ((unsigned)(group >> 32) * 0x85ebca6bu);
+  const unsigned k0 = (unsigned)key, k1 = (unsigned)(key >> 32);
+  const unsigned h0 = mix32(g ^ k0), h1 = mix32((g + 0x9E3779B9u) ^ k1 ^ h0);
+  m.bits = ((unsigned long long)h1 << 32) | h0;
+  return m;
+}
+
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {

@@ -48,6 +48,11 @@ struct ConvEpilogue {
   float q_scale = 1.f;
   float* out_f32 = nullptr;      // NCDHW fp32 output (final conv) instead of blocked bf16
   int out_f32_c = 0;
+  // training: also store the pre-norm tensor (acc*rs + bias, shaped like `out`) that the backward of the
+  // RMSNorm / FiLM / SiLU needs, and apply nn.Dropout after the activation (mask: ftb_common.cuh drop_mask8)
+  const Act* pre_out = nullptr;
+  float drop_p = 0.f;
+  unsigned long long drop_key = 0;
 };
 
 struct ConvSrc {

@@ -13,7 +13,7 @@ namespace ftb {
 
 namespace {
 
-__device__ __forceinline__ float sigm(float z) { return 1.f / (1.f + __expf(-z)); }
+__device__ __forceinline__ float sigm(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
 
 struct NormActP {
   const bf16* u;
@@ -33,318 +33,188 @@ struct NormActP {
   unsigned long long drop_key;  // per-(step, block) key of the counter-based mask
 };
 
-// Dropout keep-mask, counter-based so the backward regenerates it instead of storing it: one 64-bit hash per
-// (voxel, 8-channel group) gives 8 bits per element; element j is dropped when its byte < t = round(256 p), and
-// kept values are scaled by 256/(256 - t) (the exact inverse keep probability of this mask).  The stream differs
-// from torch's Philox dropout by construction (SURVEY 7 "Hard parts"): parity runs use p = 0.
-struct DropMask {
-  unsigned long long bits;
-  unsigned t;
-  float scale;
-  __device__ __forceinline__ float operator()(int j) const {
-    return ((unsigned)(bits >> (8 * j)) & 255u) < t ? 0.f : scale;
-  }
-};
-__device__ __forceinline__ unsigned mix32(unsigned x) {
-  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-  return x;
-}
 __device__ __forceinline__ DropMask drop_mask8(const NormActP& p, size_t group) {
-  DropMask m;
-  m.t = (unsigned)(p.drop_p * 256.f + 0.5f);
-  m.scale = 256.f / (256.f - (float)m.t);
-  const unsigned g = (unsigned)group ^ ((unsigned)(group >> 32) * 0x85ebca6bu);
-  const unsigned k0 = (unsigned)p.drop_key, k1 = (unsigned)(p.drop_key >> 32);
-  const unsigned h0 = mix32(g ^ k0), h1 = mix32((g + 0x9E3779B9u) ^ k1 ^ h0);
-  m.bits = ((unsigned long long)h1 << 32) | h0;
-  return m;
+  return ::ftb::drop_mask8(p.drop_p, p.drop_key, group);
 }
 
-// out = act(n * gain * s1 + sh) + resid,  n = u / max(||u||_C, 1e-12) (norm) or u
+// Thread mapping of both passes: LPV lanes per voxel (8, 16 or 32 >= C/8), lane = one 8-channel group (one 16-byte
+// unit of the blocked layout).  A thread therefore holds its 8 channels of u / dY / dz in registers for the whole
+// computation (every tensor is read ONCE), the channel reductions of the RMSNorm (sum of squares, n.dn) are
+// log2(LPV) xor-shuffles, and the per-channel sums over voxels needed by the FiLM / gain gradients accumulate in 8
+// registers per thread with no cross-lane traffic until the block ends.  Lanes of a warp with the same channel
+// group read consecutive voxels (64-byte runs at LPV = 8).
+constexpr int kNaUnr = 4;   // voxels in flight per thread
+
+template <int LPV>
+__device__ __forceinline__ float lanes_sum(float v) {
+#pragma unroll
+  for (int o = 1; o < LPV; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// out = act(n * gain * s1 + sh) * dropout + resid,  n = u / max(||u||_C, 1e-12) (norm) or u
+template <int LPV>
 __global__ void __launch_bounds__(256)
-normact_fwd_kernel(const NormActP p) {
+normact_fwd_kernel(const NormActP p, int iters) {
+  constexpr int VPB = 256 / LPV;
   const int b = blockIdx.y;
-  const size_t v = (size_t)blockIdx.x * 256 + threadIdx.x;
-  if (v >= p.vox) return;
-  const size_t base = ((size_t)b * p.CG * p.vox + v) * 8;
-  const size_t cgs = p.vox * 8;
-  float rinv = 1.f;
-  if (p.norm) {
-    float ss = 0.f;
-    for (int cg = 0; cg < p.CG; ++cg) {
-      float f[8];
-      unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.u + base + cg * cgs)), f);
+  const int cgi = threadIdx.x % LPV, vi = threadIdx.x / LPV;
+  const bool act = cgi < p.CG;
+  float m[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cgi * 8 + j;
+    m[j] = 1.f; sh[j] = 0.f;
+    if (act) {
+      if (p.gain) m[j] = __ldg(p.gain + c);
+      if (p.s1) { m[j] *= __ldg(p.s1 + (size_t)b * p.fstride + c); sh[j] = __ldg(p.sh + (size_t)b * p.fstride + c); }
+    }
+  }
+  const size_t cbase = ((size_t)b * p.CG + (act ? cgi : 0)) * p.vox * 8;
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  for (int it0 = 0; it0 < iters; it0 += kNaUnr) {
+    // all loads of kNaUnr voxels first: enough bytes in flight per SM to cover the HBM latency
+    uint4 Uq[kNaUnr], Rq[kNaUnr];
+#pragma unroll
+    for (int k = 0; k < kNaUnr; ++k) {
+      const size_t v = ((size_t)blockIdx.x * iters + it0 + k) * VPB + vi;
+      const bool in = act && it0 + k < iters && v < p.vox;
+      const size_t off = cbase + (in ? v : 0) * 8;
+      Uq[k] = in ? __ldg(reinterpret_cast<const uint4*>(p.u + off)) : zero4;
+      Rq[k] = (in && p.resid) ? __ldg(reinterpret_cast<const uint4*>(p.resid + off)) : zero4;
+    }
+#pragma unroll
+    for (int k = 0; k < kNaUnr; ++k) {
+    const size_t v = ((size_t)blockIdx.x * iters + it0 + k) * VPB + vi;
+    const bool in = act && it0 + k < iters && v < p.vox;
+    const size_t off = cbase + (in ? v : 0) * 8;
+    float f[8], r[8];
+    unpack_bf16x8(Uq[k], f);
+    unpack_bf16x8(Rq[k], r);
+    float rinv = 1.f;
+    if (p.norm) {
+      float ss = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
+      rinv = 1.f / fmaxf(sqrtf(lanes_sum<LPV>(ss)), 1e-12f);
     }
-    rinv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-  }
-  for (int cg = 0; cg < p.CG; ++cg) {
-    float f[8], r[8];
-    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.u + base + cg * cgs)), f);
-    if (p.resid) unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.resid + base + cg * cgs)), r);
     DropMask dm;
-    if (p.drop_p > 0.f) dm = drop_mask8(p, (base + cg * cgs) >> 3);
+    if (p.drop_p > 0.f) dm = drop_mask8(p, off >> 3);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int c = cg * 8 + j;
-      float y = f[j] * rinv;
-      if (p.gain) y *= __ldg(p.gain + c);
-      if (p.s1) y = fmaf(y, __ldg(p.s1 + (size_t)b * p.fstride + c), __ldg(p.sh + (size_t)b * p.fstride + c));
+      float y = fmaf(f[j] * rinv, m[j], sh[j]);
       if (p.silu) y = y * sigm(y);
       if (p.drop_p > 0.f) y *= dm(j);
       if (p.resid) y += r[j];
       f[j] = y;
     }
-    *reinterpret_cast<uint4*>(p.out + base + cg * cgs) = pack_bf16x8(f);
+    if (in) *reinterpret_cast<uint4*>(p.out + off) = pack_bf16x8(f);
+    }
   }
 }
 
-constexpr int kNaVPT = 4;
-// backward of the above: du (may alias dout), R, S, dbias
+// backward of the above: du (may alias dout), R[b][c] += sum_v dz*n, S += sum_v dz, dbias[c] += sum du
+template <int LPV>
 __global__ void __launch_bounds__(256)
-normact_bwd_kernel(const NormActP p) {
-  __shared__ float red[8][24];
-  const int b = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t v0 = (size_t)blockIdx.x * (256 * kNaVPT) + threadIdx.x;
-  const size_t cgs = p.vox * 8;
-  const size_t bbase = (size_t)b * p.CG * p.vox * 8;
-  float rinv[kNaVPT], dot[kNaVPT];
-#pragma unroll
-  for (int i = 0; i < kNaVPT; ++i) {
-    rinv[i] = 1.f;
-    dot[i] = 0.f;
-    const size_t v = v0 + (size_t)i * 256;
-    if (v >= p.vox || !p.norm) continue;
-    const size_t base = bbase + v * 8;
-    float ss = 0.f;
-    for (int cg = 0; cg < p.CG; ++cg) {
-      float f[8];
-      unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.u + base + cg * cgs)), f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
-    }
-    const float ri = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-    float dt = 0.f;
-    for (int cg = 0; cg < p.CG; ++cg) {
-      float f[8], g[8];
-      unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.u + base + cg * cgs)), f);
-      unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.dout + base + cg * cgs)), g);
-      DropMask dm;
-      if (p.drop_p > 0.f) dm = drop_mask8(p, (base + cg * cgs) >> 3);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = cg * 8 + j;
-        const float n = f[j] * ri;
-        float m = p.gain ? __ldg(p.gain + c) : 1.f;
-        if (p.s1) m *= __ldg(p.s1 + (size_t)b * p.fstride + c);
-        float dz = g[j];
-        if (p.drop_p > 0.f) dz *= dm(j);
-        if (p.silu) {
-          const float z = fmaf(n, m, p.s1 ? __ldg(p.sh + (size_t)b * p.fstride + c) : 0.f);
-          const float s = sigm(z);
-          dz *= s * (1.f + z * (1.f - s));
-        }
-        dt = fmaf(n, dz * m, dt);
-      }
-    }
-    rinv[i] = ri;
-    dot[i] = dt;
-  }
-  for (int cg = 0; cg < p.CG; ++cg) {
-    float acc[24];
-#pragma unroll
-    for (int k = 0; k < 24; ++k) acc[k] = 0.f;
-#pragma unroll
-    for (int i = 0; i < kNaVPT; ++i) {
-      const size_t v = v0 + (size_t)i * 256;
-      if (v >= p.vox) continue;
-      const size_t off = bbase + v * 8 + cg * cgs;
-      float f[8], g[8];
-      unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(p.u + off)), f);
-      unpack_bf16x8(*reinterpret_cast<const uint4*>(p.dout + off), g);
-      DropMask dm;
-      if (p.drop_p > 0.f) dm = drop_mask8(p, off >> 3);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = cg * 8 + j;
-        const float n = f[j] * rinv[i];
-        float m = p.gain ? __ldg(p.gain + c) : 1.f;
-        if (p.s1) m *= __ldg(p.s1 + (size_t)b * p.fstride + c);
-        float dz = g[j];
-        if (p.drop_p > 0.f) dz *= dm(j);
-        if (p.silu) {
-          const float z = fmaf(n, m, p.s1 ? __ldg(p.sh + (size_t)b * p.fstride + c) : 0.f);
-          const float s = sigm(z);
-          dz *= s * (1.f + z * (1.f - s));
-        }
-        const float dn = dz * m;
-        const float d = p.norm ? rinv[i] * (dn - n * dot[i]) : dn;
-        acc[j] += dz * n;
-        acc[8 + j] += dz;
-        acc[16 + j] += d;
-        g[j] = d;
-      }
-      *reinterpret_cast<uint4*>(p.du + off) = pack_bf16x8(g);
-    }
-#pragma unroll
-    for (int k = 0; k < 24; ++k) acc[k] = warp_sum(acc[k]);
-    __syncthreads();
-    if (lane == 0) {
-#pragma unroll
-      for (int k = 0; k < 24; ++k) red[warp][k] = acc[k];
-    }
-    __syncthreads();
-    if (threadIdx.x < 24) {
-      float s = 0.f;
-      for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-      const int k = threadIdx.x >> 3, c = cg * 8 + (threadIdx.x & 7);
-      if (k == 0 && p.R) atomicAdd(p.R + (size_t)b * p.CG * 8 + c, s);
-      if (k == 1 && p.S) atomicAdd(p.S + (size_t)b * p.sstride + c, s);
-      if (k == 2 && p.dbias) atomicAdd(p.dbias + c, s);
-    }
-  }
-}
-
-// Same backward for C <= 96 channels (every 64^3 / 32^3 layer of the UNet): the voxel's u and dout rows are read
-// from HBM exactly once and held in registers (12 x 16 B for C = 48).  The per-channel sums over voxels use a
-// warp reduce-scatter (31 shuffles per 32 channels instead of 160): afterwards lane l holds the warp's sum of
-// channel 32*g + l, which it accumulates in ONE register per group across its voxels; blocks finish through
-// shared memory and one global atomic per channel.  dbias is not produced here.
-__device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int step = 16; step >= 1; step >>= 1) {
-    const bool up = (lane & step) != 0;
-#pragma unroll
-    for (int i = 0; i < step; ++i) {
-      const float send = up ? v[i] : v[i + step];
-      const float keep = up ? v[i + step] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
-    }
-  }
-  return v[0];   // sum over the warp of element `lane`
-}
-
-template <int CG, bool kS>
-__global__ void __launch_bounds__(256, CG <= 8 ? 2 : 1)
-normact_bwd_small_kernel(const NormActP p, int vpt) {
-  constexpr int C = CG * 8;
-  constexpr int NG = (C + 31) / 32;          // groups of 32 channels
-  __shared__ float s_m[C], s_sh[C], s_red[2 * NG * 32];
+normact_bwd_kernel(const NormActP p, int iters) {
+  constexpr int VPB = 256 / LPV;
+  __shared__ float s_red[3 * 256];
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31;
-  for (int c = threadIdx.x; c < C; c += 256) {
-    float m = p.gain ? p.gain[c] : 1.f;
-    if (p.s1) m *= p.s1[(size_t)b * p.fstride + c];
-    s_m[c] = m;
-    s_sh[c] = p.s1 ? p.sh[(size_t)b * p.fstride + c] : 0.f;
-  }
-  for (int c = threadIdx.x; c < 2 * NG * 32; c += 256) s_red[c] = 0.f;
+  const int cgi = threadIdx.x % LPV, vi = threadIdx.x / LPV;
+  const bool act = cgi < p.CG;
+  for (int i = threadIdx.x; i < 3 * 256; i += 256) s_red[i] = 0.f;
   __syncthreads();
-  const size_t cgs = p.vox * 8;
-  const size_t bbase = (size_t)b * CG * p.vox * 8;
-  float accR[NG], accS[NG];
+  float m[8], sh[8], accR[8], accS[8], accB[8];
 #pragma unroll
-  for (int g = 0; g < NG; ++g) { accR[g] = 0.f; accS[g] = 0.f; }
-  for (int it = 0; it < vpt; ++it) {
-    // whole warps stay in the loop (the reduce-scatter is a warp collective); out-of-range voxels contribute 0
-    const size_t v = ((size_t)blockIdx.x * vpt + it) * 256 + threadIdx.x;
-    const bool in = v < p.vox;
-    if (__all_sync(0xffffffffu, !in)) break;
-    const size_t base = bbase + (in ? v : 0) * 8;
-    uint4 U[CG], G[CG];
-#pragma unroll
-    for (int cg = 0; cg < CG; ++cg) {
-      U[cg] = in ? __ldg(reinterpret_cast<const uint4*>(p.u + base + cg * cgs)) : make_uint4(0u, 0u, 0u, 0u);
-      G[cg] = in ? __ldg(reinterpret_cast<const uint4*>(p.dout + base + cg * cgs)) : make_uint4(0u, 0u, 0u, 0u);
+  for (int j = 0; j < 8; ++j) {
+    const int c = cgi * 8 + j;
+    m[j] = 1.f; sh[j] = 0.f; accR[j] = 0.f; accS[j] = 0.f; accB[j] = 0.f;
+    if (act) {
+      if (p.gain) m[j] = __ldg(p.gain + c);
+      if (p.s1) { m[j] *= __ldg(p.s1 + (size_t)b * p.fstride + c); sh[j] = __ldg(p.sh + (size_t)b * p.fstride + c); }
     }
+  }
+  const size_t cbase = ((size_t)b * p.CG + (act ? cgi : 0)) * p.vox * 8;
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  for (int it0 = 0; it0 < iters; it0 += kNaUnr) {
+    uint4 Uq[kNaUnr], Gq[kNaUnr];
+#pragma unroll
+    for (int k = 0; k < kNaUnr; ++k) {
+      const size_t v = ((size_t)blockIdx.x * iters + it0 + k) * VPB + vi;
+      const bool in = act && it0 + k < iters && v < p.vox;
+      const size_t off = cbase + (in ? v : 0) * 8;
+      Uq[k] = in ? __ldg(reinterpret_cast<const uint4*>(p.u + off)) : zero4;
+      Gq[k] = in ? *reinterpret_cast<const uint4*>(p.dout + off) : zero4;
+    }
+#pragma unroll
+    for (int k = 0; k < kNaUnr; ++k) {
+    const size_t v = ((size_t)blockIdx.x * iters + it0 + k) * VPB + vi;
+    const bool in = act && it0 + k < iters && v < p.vox;
+    const size_t off = cbase + (in ? v : 0) * 8;
+    float f[8], g[8];
+    unpack_bf16x8(Uq[k], f);
+    unpack_bf16x8(Gq[k], g);
     float rinv = 1.f;
     if (p.norm) {
       float ss = 0.f;
 #pragma unroll
-      for (int cg = 0; cg < CG; ++cg) {
-        float f[8];
-        unpack_bf16x8(U[cg], f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
-      }
-      rinv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+      for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
+      rinv = 1.f / fmaxf(sqrtf(lanes_sum<LPV>(ss)), 1e-12f);
     }
-    float dot = 0.f;
-    // pass 1, per group of 32 channels: dz, dot += n*dn, channel sums through the reduce-scatter
+    DropMask dm;
+    if (p.drop_p > 0.f) dm = drop_mask8(p, off >> 3);
+    float dotp = 0.f;
 #pragma unroll
-    for (int g = 0; g < NG; ++g) {
-      float vr[32], vs[32];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int cg = g * 4 + q;
-        if (cg < CG) {
-          float f[8], d[8];
-          unpack_bf16x8(U[cg], f);
-          unpack_bf16x8(G[cg], d);
-          DropMask dm;
-          if (p.drop_p > 0.f) dm = drop_mask8(p, (base + cg * cgs) >> 3);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int c = cg * 8 + j;
-            const float n = f[j] * rinv, m = s_m[c];
-            float dz = d[j];
-            if (p.drop_p > 0.f) dz *= dm(j);
-            if (p.silu) {
-              const float z = fmaf(n, m, s_sh[c]);
-              const float sg = sigm(z);
-              dz *= sg * (1.f + z * (1.f - sg));
-            }
-            dot = fmaf(n, dz * m, dot);
-            vr[q * 8 + j] = dz * n;
-            vs[q * 8 + j] = dz;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { vr[q * 8 + j] = 0.f; vs[q * 8 + j] = 0.f; }
-        }
+    for (int j = 0; j < 8; ++j) {
+      const float n = f[j] * rinv;
+      float dz = g[j];
+      if (p.drop_p > 0.f) dz *= dm(j);
+      if (p.silu) {
+        const float z = fmaf(n, m[j], sh[j]);
+        const float sg = sigm(z);
+        dz *= sg * (1.f + z * (1.f - sg));
       }
-      accR[g] += warp_reduce_scatter32(vr, lane);
-      if (kS) accS[g] += warp_reduce_scatter32(vs, lane);
+      accR[j] = fmaf(dz, n, accR[j]);
+      accS[j] += dz;
+      f[j] = n;
+      g[j] = dz * m[j];          // dn
+      dotp = fmaf(n, g[j], dotp);
     }
-    if (in) {
+    if (p.norm) {
+      const float dot = lanes_sum<LPV>(dotp);
 #pragma unroll
-      for (int cg = 0; cg < CG; ++cg) {
-        float f[8], d[8];
-        unpack_bf16x8(U[cg], f);
-        unpack_bf16x8(G[cg], d);
-        DropMask dm;
-        if (p.drop_p > 0.f) dm = drop_mask8(p, (base + cg * cgs) >> 3);
+      for (int j = 0; j < 8; ++j) g[j] = rinv * (g[j] - f[j] * dot);
+    }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int c = cg * 8 + j;
-          const float n = f[j] * rinv, m = s_m[c];
-          float dz = d[j];
-          if (p.drop_p > 0.f) dz *= dm(j);
-          if (p.silu) {
-            const float z = fmaf(n, m, s_sh[c]);
-            const float sg = sigm(z);
-            dz *= sg * (1.f + z * (1.f - sg));
-          }
-          const float dn = dz * m;
-          d[j] = p.norm ? rinv * (dn - n * dot) : dn;
-        }
-        *reinterpret_cast<uint4*>(p.du + base + cg * cgs) = pack_bf16x8(d);
-      }
+    for (int j = 0; j < 8; ++j) accB[j] += g[j];
+    if (in) *reinterpret_cast<uint4*>(p.du + off) = pack_bf16x8(g);
     }
   }
+  // lanes of the warp that share a channel group: combine, then one shared-memory add per warp and channel
 #pragma unroll
-  for (int g = 0; g < NG; ++g) {
-    atomicAdd(&s_red[g * 32 + lane], accR[g]);
-    if (kS) atomicAdd(&s_red[(NG + g) * 32 + lane], accS[g]);
+  for (int j = 0; j < 8; ++j) {
+#pragma unroll
+    for (int o = LPV; o < 32; o <<= 1) {
+      accR[j] += __shfl_xor_sync(0xffffffffu, accR[j], o);
+      accS[j] += __shfl_xor_sync(0xffffffffu, accS[j], o);
+      accB[j] += __shfl_xor_sync(0xffffffffu, accB[j], o);
+    }
+  }
+  if (lane < LPV && act) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&s_red[cgi * 8 + j], accR[j]);
+      atomicAdd(&s_red[256 + cgi * 8 + j], accS[j]);
+      atomicAdd(&s_red[512 + cgi * 8 + j], accB[j]);
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * NG * 32; i += 256) {
-    const int c = i % (NG * 32);
-    if (c >= C) continue;
-    if (i < NG * 32) { if (p.R) atomicAdd(p.R + (size_t)b * C + c, s_red[i]); }
-    else if (kS && p.S) atomicAdd(p.S + (size_t)b * p.sstride + c, s_red[i]);
+  const int C = p.CG * 8;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    if (p.R) atomicAdd(p.R + (size_t)b * C + c, s_red[c]);
+    if (p.S) atomicAdd(p.S + (size_t)b * p.sstride + c, s_red[256 + c]);
+    if (p.dbias) atomicAdd(p.dbias + c, s_red[512 + c]);
   }
 }
 
@@ -832,17 +702,36 @@ inline int grid1(size_t n, int threads) {
 
 }  // namespace
 
+template <typename F8, typename F16, typename F32>
+static inline void normact_dispatch(int CG, F8 f8, F16 f16, F32 f32) {
+  if (CG <= 8) f8(); else if (CG <= 16) f16(); else f32();
+}
+static inline void normact_grid(const Act& u, int CG, dim3* grid, int* iters) {
+  const int lpv = CG <= 8 ? 8 : (CG <= 16 ? 16 : 32);
+  const size_t vpb = 256 / lpv;
+  const size_t vblocks = (u.voxels() + vpb - 1) / vpb;
+  int it = (int)(vblocks * u.B / (16 * (size_t)num_sms()));   // ~16 blocks per SM over the batch
+  it = it < 1 ? 1 : (it > 32 ? 32 : it);
+  *iters = it;
+  *grid = dim3((unsigned)((vblocks + it - 1) / it), u.B);
+}
+
 int normact_fwd(const Act& u, bool norm, const float* gain, const float* s1, const float* sh, int fstride, bool silu,
                 const Act* resid, Act& out, cudaStream_t st, float drop_p, unsigned long long drop_key) {
   FTB_CHECK(out.B == u.B && out.C == u.C && out.voxels() == u.voxels(), "normact: shapes");
+  FTB_CHECK(u.cg() <= 32, "normact: at most 256 channels");
   if (resid) FTB_CHECK(resid->C == u.C && resid->voxels() == u.voxels(), "normact: residual shape");
   NormActP p{};
   p.u = u.p; p.out = out.p; p.resid = resid ? resid->p : nullptr;
   p.CG = u.cg(); p.vox = u.voxels(); p.norm = norm; p.silu = silu;
   p.gain = gain; p.s1 = s1; p.sh = sh; p.fstride = fstride;
   p.drop_p = drop_p; p.drop_key = drop_key;
-  dim3 grid((unsigned)((p.vox + 255) / 256), u.B);
-  normact_fwd_kernel<<<grid, 256, 0, st>>>(p);
+  dim3 grid;
+  int iters;
+  normact_grid(u, p.CG, &grid, &iters);
+  normact_dispatch(p.CG, [&] { normact_fwd_kernel<8><<<grid, 256, 0, st>>>(p, iters); },
+                   [&] { normact_fwd_kernel<16><<<grid, 256, 0, st>>>(p, iters); },
+                   [&] { normact_fwd_kernel<32><<<grid, 256, 0, st>>>(p, iters); });
   FTB_LAUNCH_OK();
   return 0;
 }
@@ -851,33 +740,19 @@ int normact_bwd(const Act& dout, const Act& u, bool norm, const float* gain, con
                 int fstride, bool silu, Act& du, float* R, float* S, int sstride, float* dbias, cudaStream_t st,
                 float drop_p, unsigned long long drop_key) {
   FTB_CHECK(dout.C == u.C && du.C == u.C && dout.voxels() == u.voxels(), "normact_bwd: shapes");
+  FTB_CHECK(u.cg() <= 32, "normact_bwd: at most 256 channels");
   NormActP p{};
   p.u = u.p; p.dout = dout.p; p.du = du.p;
   p.CG = u.cg(); p.vox = u.voxels(); p.norm = norm; p.silu = silu;
   p.gain = gain; p.s1 = s1; p.sh = sh; p.fstride = fstride;
   p.R = R; p.S = S; p.sstride = sstride; p.dbias = dbias;
   p.drop_p = drop_p; p.drop_key = drop_key;
-  if (dbias == nullptr && (p.CG == 6 || p.CG == 4 || p.CG == 2 || p.CG == 8 || p.CG == 12)) {
-    const size_t vblocks = (p.vox + 255) / 256;
-    int vpt = (int)(vblocks * u.B / (8 * (size_t)num_sms()));   // ~8 blocks per SM over the batch
-    vpt = vpt < 1 ? 1 : (vpt > 8 ? 8 : vpt);
-    dim3 grid((unsigned)((vblocks + vpt - 1) / vpt), u.B);
-#define FTB_NA_SMALL(CGV)                                                                   \
-    do {                                                                                     \
-      if (S) normact_bwd_small_kernel<CGV, true><<<grid, 256, 0, st>>>(p, vpt);              \
-      else normact_bwd_small_kernel<CGV, false><<<grid, 256, 0, st>>>(p, vpt);               \
-    } while (0)
-    if (p.CG == 6) FTB_NA_SMALL(6);
-    else if (p.CG == 4) FTB_NA_SMALL(4);
-    else if (p.CG == 2) FTB_NA_SMALL(2);
-    else if (p.CG == 12) FTB_NA_SMALL(12);
-    else FTB_NA_SMALL(8);
-#undef FTB_NA_SMALL
-    FTB_LAUNCH_OK();
-    return 0;
-  }
-  dim3 grid((unsigned)((p.vox + 256 * kNaVPT - 1) / (256 * kNaVPT)), u.B);
-  normact_bwd_kernel<<<grid, 256, 0, st>>>(p);
+  dim3 grid;
+  int iters;
+  normact_grid(u, p.CG, &grid, &iters);
+  normact_dispatch(p.CG, [&] { normact_bwd_kernel<8><<<grid, 256, 0, st>>>(p, iters); },
+                   [&] { normact_bwd_kernel<16><<<grid, 256, 0, st>>>(p, iters); },
+                   [&] { normact_bwd_kernel<32><<<grid, 256, 0, st>>>(p, iters); });
   FTB_LAUNCH_OK();
   return 0;
 }
