@@ -194,7 +194,56 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int c
   }
 }
 
+// every weight tensor of the network in ONE launch (the training step repacks after each optimiser update):
+// blockIdx.y = job.  transposed jobs build the data-gradient operand: output channel = input channel ci0 + co' of
+// the forward weight, K index = forward output channel, taps flipped, optional per-row scale (folded pre-norm gain).
+__global__ void pack_jobs_kernel(const PackJob* __restrict__ jobs) {
+  const PackJob jb = jobs[blockIdx.y];
+  const int K = jb.ksize, taps = K * K * K;
+  const int Kw = jb.unfold_w ? 1 : K;
+  const size_t total = (size_t)jb.ntiles * K * K * Kw * jb.cin_pad * jb.n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t r = i;
+    const int k8 = r % 8; r /= 8;
+    const int n8 = r % 8; r /= 8;
+    const int kc = r % 2; r /= 2;
+    const int ng = r % (jb.n / 8); r /= (jb.n / 8);
+    const int j = r % K; r /= K;
+    const int ks = r % (jb.cin_pad / 16); r /= (jb.cin_pad / 16);
+    const int khw = r % (K * Kw); r /= (K * Kw);
+    const int nt = (int)r;
+    const int co = nt * jb.n + ng * 8 + n8;
+    int ci = ks * 16 + kc * 8 + k8;
+    int t = (K - 1 - j) * K * K + khw;
+    bool ok = co < jb.cout && ci < jb.cin_real;
+    if (jb.unfold_w) {
+      const int kw = ci / jb.cin_real;
+      ci -= kw * jb.cin_real;
+      ok = co < jb.cout && kw < K;
+      t = (K - 1 - j) * K * K + khw * K + kw;
+    }
+    float v = 0.f;
+    if (ok) {
+      if (jb.transposed) {
+        v = jb.w[((size_t)ci * jb.src_cin + jb.ci0 + co) * taps + (taps - 1 - t)];
+        if (jb.in_scale) v *= jb.in_scale[jb.ci0 + co];
+      } else {
+        v = jb.w[((size_t)co * jb.cin_real + ci) * taps + t];
+        if (jb.in_scale) v *= jb.in_scale[ci];
+      }
+    }
+    jb.dst[i] = __float2bfloat16(v);
+  }
+}
+
 }  // namespace
+
+int pack_conv_weights_batched(const PackJob* d_jobs, int njobs, cudaStream_t st) {
+  if (njobs <= 0) return 0;
+  pack_jobs_kernel<<<dim3(48, njobs), 256, 0, st>>>(d_jobs);
+  FTB_LAUNCH_OK();
+  return 0;
+}
 
 int pack_conv_weights(const float* w, int cout, int cin_real, int ksize, int cin_pad, int ntile_n,
                       int ntiles, const float* in_scale, bf16* dst, cudaStream_t st, bool unfold_w) {

@@ -161,6 +161,12 @@ struct ftb_unet {
   bool dirty = true;
   bool kshift_stale = true;      // the fused-attention shift vectors lag the weights (training skips them)
   bool dgrad_dirty = true;       // transposed packs for the data gradients lag the weights
+  ftb::PackJob* d_jobs = nullptr;        // device table: forward packs of every conv
+  int n_jobs = 0;
+  const float* jobs_base = nullptr;      // parameter storage the table was built for
+  ftb::PackJob* d_djobs = nullptr;       // device table: transposed packs (data gradients)
+  int n_djobs = 0, cap_djobs = 0;
+  const float* djobs_base = nullptr;
   std::map<std::string, std::vector<ftb_engine_detail::DgradPack>> dgrad;
   std::shared_ptr<ftb_engine_detail::TrainState> train;
   std::shared_ptr<ftb_engine_detail::TrainCtx> train_ctx;
@@ -436,21 +442,37 @@ int finalize(ftb_unet* U, cudaStream_t st, bool for_train = false) {
     const float* src = U->params[U->pindex[g.gname]].dev;
     scale_vec_kernel<<<cdiv(g.c, 128), 128, 0, st>>>(src, sqrtf((float)g.c), g.gs, g.c);
   }
+  // weight packs: one table-driven launch for all convs (the table holds parameter pointers: rebuilt when they move)
+  const float* base0 = U->params.empty() ? nullptr : U->params[0].dev;
+  if (!U->d_jobs || U->jobs_base != base0) {
+    std::vector<PackJob> jobs;
+    for (auto& kv : U->convs) {
+      ConvLayer& cl = kv.second;
+      PackJob jb{};
+      jb.w = U->params[U->pindex[cl.wname]].dev;
+      jb.in_scale = cl.in_scale.empty() ? nullptr : cl.scale_tmp;
+      jb.dst = cl.packed;
+      jb.cout = cl.cout; jb.cin_real = cl.cin; jb.ksize = cl.k; jb.cin_pad = cl.cin_pad; jb.n = cl.n_tile;
+      jb.ntiles = cl.ntiles; jb.unfold_w = cl.unfold_w ? 1 : 0;
+      jobs.push_back(jb);
+    }
+    if (!U->d_jobs) FTB_TRY(dev_alloc(U, &U->d_jobs, jobs.size()));
+    FTB_CUDA(cudaMemcpyAsync(U->d_jobs, jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice, st));
+    FTB_CUDA(cudaStreamSynchronize(st));   // `jobs` is pageable host memory
+    U->n_jobs = (int)jobs.size();
+    U->jobs_base = base0;
+  }
   for (auto& kv : U->convs) {
     ConvLayer& cl = kv.second;
-    const float* w = U->params[U->pindex[cl.wname]].dev;
-    const float* in_scale = nullptr;
     if (!cl.in_scale.empty()) {
       const float* g = U->params[U->pindex[cl.in_scale]].dev;
       scale_vec_kernel<<<cdiv(cl.cin, 128), 128, 0, st>>>(g, cl.in_scale_mul, cl.scale_tmp, cl.cin);
-      in_scale = cl.scale_tmp;
     }
-    FTB_TRY(pack_conv_weights(w, cl.cout, cl.cin, cl.k, cl.cin_pad, cl.n_tile, cl.ntiles, in_scale,
-                              cl.packed, st, cl.unfold_w));
     if (!cl.bname.empty())
       FTB_CUDA(cudaMemcpyAsync(cl.bias, U->params[U->pindex[cl.bname]].dev, cl.cout * sizeof(float),
                                cudaMemcpyDeviceToDevice, st));
   }
+  FTB_TRY(pack_conv_weights_batched(U->d_jobs, U->n_jobs, st));
   FTB_CUDA(cudaGetLastError());
   U->dirty = false;
   U->dgrad_dirty = true;
@@ -1127,6 +1149,10 @@ int ftb_unet3d_forward_train(ftb_unet* h, const float* x, const float* t, float*
   TrainState* T = h->train.get();
   ensure_offsets(h, T);
   T->valid = false;
+  if (T->need_bytes == 0 || T->B != B || T->X != X || T->Y != Y || T->Z != Z)   // sized once per shape (a dry tape run)
+    T->need_bytes = ftb_unet3d_train_workspace_bytes(h, B, X, Y, Z);
+  FTB_CHECK(T->need_bytes > 0 && workspace_bytes >= T->need_bytes,
+            "training workspace too small: need " + std::to_string(T->need_bytes) + " bytes");
   h->train_ctx.reset(new TrainCtx{h, T, st, reinterpret_cast<char*>(workspace), 0, false, B});
   TrainFwd f{h, T, *h->train_ctx};
   FTB_TRY(f.run(x, t, out, X, Y, Z));
@@ -1145,8 +1171,7 @@ int ftb_unet3d_backward(ftb_unet* h, const float* dout, float* grads, void* work
   TrainState* T = h->train.get();
   TrainCtx& c = *h->train_ctx;
   FTB_CHECK(c.base == reinterpret_cast<char*>(workspace), "backward: workspace differs from the forward's");
-  const size_t need = ftb_unet3d_train_workspace_bytes(h, T->B, T->X, T->Y, T->Z);
-  FTB_CHECK(need > 0 && workspace_bytes >= need, "training workspace too small: need " + std::to_string(need) + " bytes");
+  FTB_CHECK(workspace_bytes >= T->need_bytes, "training workspace too small: need " + std::to_string(T->need_bytes) + " bytes");
   c.st = (cudaStream_t)stream;
   c.off = T->fwd_bytes;
   c.cb = bucket_cb;

@@ -24,6 +24,7 @@ struct TrainState {
   std::vector<int64_t> poff;                              // flat offset of each parameter
   int64_t ptotal = 0;
   size_t fwd_bytes = 0;      // workspace consumed by the forward (the backward continues after it)
+  size_t need_bytes = 0;     // forward + backward footprint of the current shape
   int B = 0, X = 0, Y = 0, Z = 0;
   bool valid = false;        // a forward_train has run and its tape matches the workspace
   const float* t_dev = nullptr;
@@ -570,18 +571,36 @@ struct TrainFwd {
   }
 };
 
-// (re)pack the transposed weights of every conv that has a data gradient
-inline int pack_dgrad(ftb_unet* U, float* wt_tmp, cudaStream_t st) {
-  for (auto& kv : U->dgrad) {
-    const ConvLayer& cl = U->convs.at(kv.first);
-    const float* w = U->params[U->pindex.at(cl.wname)].dev;
-    for (DgradPack& d : kv.second) {
-      // wT[ci][co][flipped taps] (* pre-norm gain of the input channel when it was folded into the forward pack)
-      FTB_TRY(transpose_flip(w, cl.cout, cl.cin, cl.k, d.ci0, d.cin_sub, cl.in_scale.empty() ? nullptr : cl.scale_tmp,
-                             wt_tmp, st));
-      FTB_TRY(pack_conv_weights(wt_tmp, d.cin_sub, cl.cout, cl.k, round_up(cl.cout, 16), d.n_tile, 1, nullptr, d.packed, st));
+// (re)pack the transposed weights of every conv that has a data gradient: one table-driven launch
+inline int pack_dgrad(ftb_unet* U, float* /*wt_tmp*/, cudaStream_t st) {
+  int n = 0;
+  for (auto& kv : U->dgrad) n += (int)kv.second.size();
+  const float* base0 = U->params.empty() ? nullptr : U->params[0].dev;
+  if (n != U->n_djobs || U->djobs_base != base0) {
+    std::vector<PackJob> jobs;
+    for (auto& kv : U->dgrad) {
+      const ConvLayer& cl = U->convs.at(kv.first);
+      for (DgradPack& d : kv.second) {
+        PackJob jb{};
+        jb.w = U->params[U->pindex.at(cl.wname)].dev;
+        jb.in_scale = cl.in_scale.empty() ? nullptr : cl.scale_tmp;   // pre-norm gain folded into the forward pack
+        jb.dst = d.packed;
+        jb.cout = d.cin_sub; jb.cin_real = cl.cout; jb.ksize = cl.k; jb.cin_pad = round_up(cl.cout, 16);
+        jb.n = d.n_tile; jb.ntiles = 1; jb.unfold_w = 0;
+        jb.transposed = 1; jb.ci0 = d.ci0; jb.src_cin = cl.cin;
+        jobs.push_back(jb);
+      }
     }
+    if (n > U->cap_djobs) {
+      FTB_TRY(dev_alloc(U, &U->d_djobs, (size_t)n + 64));
+      U->cap_djobs = n + 64;
+    }
+    FTB_CUDA(cudaMemcpyAsync(U->d_djobs, jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice, st));
+    FTB_CUDA(cudaStreamSynchronize(st));
+    U->n_djobs = n;
+    U->djobs_base = base0;
   }
+  FTB_TRY(pack_conv_weights_batched(U->d_djobs, U->n_djobs, st));
   U->dgrad_dirty = false;
   return 0;
 }

@@ -83,6 +83,18 @@ int make_voxel_tmap(CUtensorMap* tm, const Act& a, int box_vox, int box_cg);
 int pack_conv_weights(const float* w, int cout, int cin_real, int ksize, int cin_pad, int ntile_n,
                       int ntiles, const float* in_scale, bf16* dst, cudaStream_t st, bool unfold_w = false);
 
+// batched form: a device table of jobs, one launch.  Plain job: as pack_conv_weights.  Transposed job (data
+// gradient): dst = pack of wT[co'][ci'][flipped taps] = w[ci'][ci0 + co'] * in_scale[ci0 + co'], with cout = number
+// of source channels, cin_real = forward Cout, src_cin = forward Cin.
+struct PackJob {
+  const float* w;
+  const float* in_scale;
+  bf16* dst;
+  int cout, cin_real, ksize, cin_pad, n, ntiles, unfold_w;
+  int transposed, ci0, src_cin;
+};
+int pack_conv_weights_batched(const PackJob* d_jobs, int njobs, cudaStream_t st);
+
 // ---------------------------------------------------------------- layout / resample
 int pack_ncdhw_to_blocked(const float* x, int B, int C, int D, int H, int W, Act& out, cudaStream_t st);
 // W-unfolded pack: out channel kw*C + c of voxel (d,h,w) = x[c][d][h][w + kw - K/2] (zero outside)
