@@ -53,7 +53,7 @@ __device__ __forceinline__ float lanes_sum(float v) {
 }
 
 // out = act(n * gain * s1 + sh) * dropout + resid,  n = u / max(||u||_C, 1e-12) (norm) or u
-template <int LPV>
+template <int LPV, bool kNorm, bool kSilu, bool kDrop>
 __global__ void __launch_bounds__(256)
 normact_fwd_kernel(const NormActP p, int iters) {
   constexpr int VPB = 256 / LPV;
@@ -92,21 +92,20 @@ normact_fwd_kernel(const NormActP p, int iters) {
     unpack_bf16x8(Uq[k], f);
     unpack_bf16x8(Rq[k], r);
     float rinv = 1.f;
-    if (p.norm) {
+    if (kNorm) {
       float ss = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
       rinv = 1.f / fmaxf(sqrtf(lanes_sum<LPV>(ss)), 1e-12f);
     }
     DropMask dm;
-    if (p.drop_p > 0.f) dm = drop_mask8(p, off >> 3);
+    if (kDrop) dm = drop_mask8(p, off >> 3);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float y = fmaf(f[j] * rinv, m[j], sh[j]);
-      if (p.silu) y = y * sigm(y);
-      if (p.drop_p > 0.f) y *= dm(j);
-      if (p.resid) y += r[j];
-      f[j] = y;
+      if (kSilu) y = y * sigm(y);
+      if (kDrop) y *= dm(j);
+      f[j] = y + r[j];   // r is zero without a residual
     }
     if (in) *reinterpret_cast<uint4*>(p.out + off) = pack_bf16x8(f);
     }
@@ -114,7 +113,7 @@ normact_fwd_kernel(const NormActP p, int iters) {
 }
 
 // backward of the above: du (may alias dout), R[b][c] += sum_v dz*n, S += sum_v dz, dbias[c] += sum du
-template <int LPV>
+template <int LPV, bool kNorm, bool kSilu, bool kDrop>
 __global__ void __launch_bounds__(256)
 normact_bwd_kernel(const NormActP p, int iters) {
   constexpr int VPB = 256 / LPV;
@@ -156,21 +155,21 @@ normact_bwd_kernel(const NormActP p, int iters) {
     unpack_bf16x8(Uq[k], f);
     unpack_bf16x8(Gq[k], g);
     float rinv = 1.f;
-    if (p.norm) {
+    if (kNorm) {
       float ss = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
       rinv = 1.f / fmaxf(sqrtf(lanes_sum<LPV>(ss)), 1e-12f);
     }
     DropMask dm;
-    if (p.drop_p > 0.f) dm = drop_mask8(p, off >> 3);
+    if (kDrop) dm = drop_mask8(p, off >> 3);
     float dotp = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float n = f[j] * rinv;
       float dz = g[j];
-      if (p.drop_p > 0.f) dz *= dm(j);
-      if (p.silu) {
+      if (kDrop) dz *= dm(j);
+      if (kSilu) {
         const float z = fmaf(n, m[j], sh[j]);
         const float sg = sigm(z);
         dz *= sg * (1.f + z * (1.f - sg));
@@ -181,7 +180,7 @@ normact_bwd_kernel(const NormActP p, int iters) {
       g[j] = dz * m[j];          // dn
       dotp = fmaf(n, g[j], dotp);
     }
-    if (p.norm) {
+    if (kNorm) {
       const float dot = lanes_sum<LPV>(dotp);
 #pragma unroll
       for (int j = 0; j < 8; ++j) g[j] = rinv * (g[j] - f[j] * dot);
@@ -702,6 +701,21 @@ inline int grid1(size_t n, int threads) {
 
 }  // namespace
 
+#define FTB_NA_FLAGS(KERNEL, LPVV)                                                              \
+  do {                                                                                          \
+    const int code = (norm ? 4 : 0) | (silu ? 2 : 0) | (dr ? 1 : 0);                            \
+    switch (code) {                                                                             \
+      case 0: KERNEL<LPVV, false, false, false><<<grid, 256, 0, st>>>(p, iters); break;         \
+      case 1: KERNEL<LPVV, false, false, true><<<grid, 256, 0, st>>>(p, iters); break;          \
+      case 2: KERNEL<LPVV, false, true, false><<<grid, 256, 0, st>>>(p, iters); break;          \
+      case 3: KERNEL<LPVV, false, true, true><<<grid, 256, 0, st>>>(p, iters); break;           \
+      case 4: KERNEL<LPVV, true, false, false><<<grid, 256, 0, st>>>(p, iters); break;          \
+      case 5: KERNEL<LPVV, true, false, true><<<grid, 256, 0, st>>>(p, iters); break;           \
+      case 6: KERNEL<LPVV, true, true, false><<<grid, 256, 0, st>>>(p, iters); break;           \
+      default: KERNEL<LPVV, true, true, true><<<grid, 256, 0, st>>>(p, iters); break;           \
+    }                                                                                           \
+  } while (0)
+
 template <typename F8, typename F16, typename F32>
 static inline void normact_dispatch(int CG, F8 f8, F16 f16, F32 f32) {
   if (CG <= 8) f8(); else if (CG <= 16) f16(); else f32();
@@ -729,9 +743,9 @@ int normact_fwd(const Act& u, bool norm, const float* gain, const float* s1, con
   dim3 grid;
   int iters;
   normact_grid(u, p.CG, &grid, &iters);
-  normact_dispatch(p.CG, [&] { normact_fwd_kernel<8><<<grid, 256, 0, st>>>(p, iters); },
-                   [&] { normact_fwd_kernel<16><<<grid, 256, 0, st>>>(p, iters); },
-                   [&] { normact_fwd_kernel<32><<<grid, 256, 0, st>>>(p, iters); });
+  const bool dr = drop_p > 0.f;
+  normact_dispatch(p.CG, [&] { FTB_NA_FLAGS(normact_fwd_kernel, 8); }, [&] { FTB_NA_FLAGS(normact_fwd_kernel, 16); },
+                   [&] { FTB_NA_FLAGS(normact_fwd_kernel, 32); });
   FTB_LAUNCH_OK();
   return 0;
 }
@@ -750,9 +764,9 @@ int normact_bwd(const Act& dout, const Act& u, bool norm, const float* gain, con
   dim3 grid;
   int iters;
   normact_grid(u, p.CG, &grid, &iters);
-  normact_dispatch(p.CG, [&] { normact_bwd_kernel<8><<<grid, 256, 0, st>>>(p, iters); },
-                   [&] { normact_bwd_kernel<16><<<grid, 256, 0, st>>>(p, iters); },
-                   [&] { normact_bwd_kernel<32><<<grid, 256, 0, st>>>(p, iters); });
+  const bool dr = drop_p > 0.f;
+  normact_dispatch(p.CG, [&] { FTB_NA_FLAGS(normact_bwd_kernel, 8); }, [&] { FTB_NA_FLAGS(normact_bwd_kernel, 16); },
+                   [&] { FTB_NA_FLAGS(normact_bwd_kernel, 32); });
   FTB_LAUNCH_OK();
   return 0;
 }
