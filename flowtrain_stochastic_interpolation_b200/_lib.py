@@ -63,6 +63,9 @@ _SIGS = {
     "ftb_unet3d_set_param": (_i, [_vp, C.c_char_p, _vp, _i64, _vp]),
     "ftb_unet3d_workspace_bytes": (_sz, [_vp, _i, _i, _i, _i]),
     "ftb_unet3d_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "ftb_unet3d_f32_workspace_bytes": (_sz, [_vp, _i, _i, _i, _i]),
+    "ftb_unet3d_forward_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "ftb_unet3d_get_tap_f32": (_i, [_vp, C.c_char_p, _vp, _ip, _vp]),
     "ftb_unet3d_cond_workspace_bytes": (_sz, [_vp, _i, _i, _i, _i, _i]),
     "ftb_unet3d_cond_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _i, _vp]),
     "ftb_unet3d_tap_channels": (_i, [_vp, C.c_char_p, _ip, _ip, _ip, _ip]),

@@ -76,7 +76,8 @@ struct IgemmParams {
   bf16* out;
   int out_cgtot, out_cgoff;
   float* out_f32;
-  int out_f32_c;
+  int out_f32_c;               // channels of this N tile that exist in the fp32 output
+  int out_f32_cs;              // channels per sample of the fp32 output (sample stride)
   const float *bias, *mul, *add;
   int mul_stride, add_stride, norm;
   const bf16* resid;
@@ -91,6 +92,7 @@ struct IgemmParams {
   bf16* u_out;                 // training: pre-norm output (same channel layout as `out`), or null
   float drop_p;                // training: dropout after the activation
   unsigned long long drop_key;
+  int f32_accum;               // fp32 mode: out_f32 += instead of = (the hi/lo operand products of one conv)
 };
 
 struct ItemCoord {
@@ -174,7 +176,10 @@ __device__ __forceinline__ void epi_store16(const IgemmParams& p, EpiCtx& ec, in
   if (ec.f32_b) {
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-      if (c0 + j < p.out_f32_c) ec.f32_b[(size_t)(c0 + j) * ec.cgs + vox] = v[j];
+      if (c0 + j < p.out_f32_c) {
+        float* o = ec.f32_b + (size_t)(c0 + j) * ec.cgs + vox;
+        *o = (kTrain && p.f32_accum) ? *o + v[j] : v[j];
+      }
     return;
   }
   bf16* dst = ec.out_b + ((size_t)(p.out_cgoff + (c0 >> 3)) * ec.cgs + vox) * 8;
@@ -196,6 +201,7 @@ __device__ __forceinline__ void epi_prefetch_resid(const IgemmParams& p, const E
 }
 
 // y = (acc * rs) * mul + add'   (no norm; bias already folded into add')
+template <bool kTrain>
 __device__ __forceinline__ void epi_affine(const IgemmParams& p, EpiCtx& ec, uint32_t trow,
                                            size_t vox, float rs) {
   epi_prefetch_resid(p, ec, vox);
@@ -215,7 +221,7 @@ __device__ __forceinline__ void epi_affine(const IgemmParams& p, EpiCtx& ec, uin
       v[j4 + 2] = fmaf(__uint_as_float(r0[j4 + 2]) * rs, mu.z, ad.z);
       v[j4 + 3] = fmaf(__uint_as_float(r0[j4 + 3]) * rs, mu.w, ad.w);
     }
-    epi_store16(p, ec, c0, vox, v);
+    epi_store16<kTrain>(p, ec, c0, vox, v);
     if (two) {
 #pragma unroll
       for (int j4 = 0; j4 < 16; j4 += 4) {
@@ -226,7 +232,7 @@ __device__ __forceinline__ void epi_affine(const IgemmParams& p, EpiCtx& ec, uin
         v[j4 + 2] = fmaf(__uint_as_float(r1[j4 + 2]) * rs, mu.z, ad.z);
         v[j4 + 3] = fmaf(__uint_as_float(r1[j4 + 3]) * rs, mu.w, ad.w);
       }
-      epi_store16(p, ec, c0 + 16, vox, v);
+      epi_store16<kTrain>(p, ec, c0 + 16, vox, v);
     }
   }
 }
@@ -787,7 +793,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
       ec.u_b = p.u_out ? p.u_out + (size_t)c.b * p.out_cgtot * cgs * 8 : nullptr;
       ec.b = c.b;
       ec.res_b = p.resid ? p.resid + (size_t)c.b * p.resid_cgtot * cgs * 8 : nullptr;
-      ec.f32_b = p.out_f32 ? p.out_f32 + (size_t)c.b * p.out_f32_c * cgs : nullptr;
+      ec.f32_b = p.out_f32 ? p.out_f32 + (size_t)c.b * p.out_f32_cs * cgs : nullptr;
       for (int g = 0; g < ngroups; ++g, ++gctr) {
         const int nze = min(p.NZ, c.lz - g * p.NZ);
         const uint32_t ab = gctr & 1;
@@ -830,7 +836,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
           } else if (p.flags & F_PLAIN) {
             epi_plain(p, ec, trow, vox, rs);
           } else {
-            epi_affine(p, ec, trow, vox, rs);
+            epi_affine<kTrain>(p, ec, trow, vox, rs);
           }
           if (p.ss_out && ec.valid) p.ss_out[(size_t)c.b * cgs + vox] = ec.ssq;
         }
@@ -1104,7 +1110,7 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   p.wpack = w.w;
   p.w_batch_stride = w.batch_stride;
   p.out = out.p; p.out_cgtot = out.cg();
-  p.out_f32 = e.out_f32; p.out_f32_c = e.out_f32_c;
+  p.out_f32 = e.out_f32; p.out_f32_c = e.out_f32_c; p.out_f32_cs = e.out_f32_c;
   p.norm = e.norm ? 1 : 0;
   p.mul = e.mul; p.add = e.add; p.mul_stride = e.mul_stride; p.add_stride = e.add_stride;
   p.resid = e.resid ? e.resid->p : nullptr;
@@ -1121,6 +1127,7 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
     p.u_out = e.pre_out->p;
   }
   p.drop_p = e.drop_p; p.drop_key = e.drop_key;
+  p.f32_accum = (e.out_f32 && e.out_f32_accum) ? 1 : 0;
 
   CUtensorMap tm0, tm1;
   const int box0 = pick(p.cg0), box1 = s1.t ? pick(p.cg1) : 0;   // TMA box = one channel chunk
@@ -1150,6 +1157,10 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
     q.wpack = w.w + (size_t)nt * w.tile_elems();
     q.bias = e.bias ? e.bias + (size_t)nt * w.n : nullptr;
     q.out_cgoff = out_cgoff + nt * (w.n / 8);
+    if (q.out_f32) {   // N tile nt of an fp32 output: channels [nt*n, ...) of every sample
+      q.out_f32 = p.out_f32 + (size_t)nt * w.n * a0.voxels();
+      q.out_f32_c = p.out_f32_c - nt * w.n;
+    }
     q.flags = (e.silu ? F_SILU : 0) | ((e.q_softmax_heads && nt == 0) ? F_QSOFTMAX : 0);
     if (!(q.flags & F_QSOFTMAX) && !q.norm && !q.bias && !q.mul && !q.add && !e.silu && !q.resid && !q.out_f32 && !q.ss_out)
       q.flags |= F_PLAIN;
@@ -1166,7 +1177,7 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
     }
     // the training epilogue (pre-norm side output, dropout) is a separate instantiation: the inference kernel
     // carries none of its code
-    if (q.u_out || q.drop_p > 0.f) conv_igemm_kernel<true><<<grid, kThreads, smem_bytes, st>>>(tm0, tm1, q);
+    if (q.u_out || q.drop_p > 0.f || q.f32_accum) conv_igemm_kernel<true><<<grid, kThreads, smem_bytes, st>>>(tm0, tm1, q);
     else conv_igemm_kernel<false><<<grid, kThreads, smem_bytes, st>>>(tm0, tm1, q);
     prof_end(prof, st);
     FTB_LAUNCH_OK();

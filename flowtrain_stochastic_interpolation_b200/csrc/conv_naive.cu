@@ -232,6 +232,7 @@ __global__ void pack_jobs_kernel(const PackJob* __restrict__ jobs) {
         if (jb.in_scale) v *= jb.in_scale[ci];
       }
     }
+    if (jb.part == 2) v -= __bfloat162float(__float2bfloat16(v));   // low part of the 3 x bf16 split
     jb.dst[i] = __float2bfloat16(v);
   }
 }

@@ -168,6 +168,12 @@ struct ftb_unet {
   int n_djobs = 0, cap_djobs = 0;
   const float* djobs_base = nullptr;
   std::map<std::string, std::vector<ftb_engine_detail::DgradPack>> dgrad;
+  std::map<std::string, std::pair<ftb::bf16*, ftb::bf16*>> f32packs;   // fp32 mode: (hi, lo) weight packs per conv
+  ftb::PackJob* d_f32jobs = nullptr;
+  int n_f32jobs = 0;
+  const float* f32jobs_base = nullptr;
+  bool f32_stale = true;
+  std::map<std::string, std::vector<long long>> taps32;   // fp32 mode: name -> (pointer, B, C, D, H, W)
   std::shared_ptr<ftb_engine_detail::TrainState> train;
   std::shared_ptr<ftb_engine_detail::TrainCtx> train_ctx;
   bool on_device = false;
@@ -477,6 +483,7 @@ int finalize(ftb_unet* U, cudaStream_t st, bool for_train = false) {
   U->dirty = false;
   U->dgrad_dirty = true;
   U->kshift_stale = true;
+  U->f32_stale = true;
   return for_train ? 0 : finalize_kshift(U, st);
 }
 
@@ -846,6 +853,7 @@ struct Fwd {
 
 }  // namespace ftb_engine_detail
 #include "engine_train.cuh"
+#include "engine_f32.cuh"
 using namespace ftb_engine_detail;
 
 // ====================================================================== C ABI
@@ -952,6 +960,29 @@ int ftb_unet3d_forward(ftb_unet* h, const float* x, const float* t, float* out, 
   return f.run(x, t, out, X, Y, Z);
 }
 
+size_t ftb_unet3d_f32_workspace_bytes(ftb_unet* h, int B, int X, int Y, int Z) {
+  if (check_dims(h, B, X, Y, Z) != 0) return 0;
+  if (h->cfg.conditional) { set_error("fp32 mode: unconditional Unet3D only"); return 0; }
+  FwdF32 f{h, nullptr, nullptr, true, B};
+  return f.run(nullptr, nullptr, nullptr, X, Y, Z) == 0 ? round_up_sz(f.peak, 256) + 256 : 0;
+}
+
+int ftb_unet3d_forward_f32(ftb_unet* h, const float* x, const float* t, float* out, int B, int X, int Y, int Z,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  FTB_TRY(check_dims(h, B, X, Y, Z));
+  FTB_CHECK(!h->cfg.conditional, "fp32 mode: unconditional Unet3D only");
+  FTB_CHECK(x && t && out && workspace, "null argument");
+  FTB_CHECK(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+  const size_t need = ftb_unet3d_f32_workspace_bytes(h, B, X, Y, Z);
+  FTB_CHECK(need > 0 && workspace_bytes >= need, "workspace too small: need " + std::to_string(need) + " bytes");
+  cudaStream_t st = (cudaStream_t)stream;
+  FTB_TRY(ensure_device(h));
+  FTB_TRY(finalize(h, st, true));
+  FTB_TRY(finalize_f32(h, st));
+  FwdF32 f{h, st, reinterpret_cast<char*>(workspace), false, B};
+  return f.run(x, t, out, X, Y, Z);
+}
+
 int ftb_unet3d_cond_forward(ftb_unet* h, const float* x, const float* atb, int atb_B, const float* t, float* out,
                             int B, int X, int Y, int Z, void* workspace, size_t workspace_bytes, int reuse_atb,
                             void* stream) {
@@ -990,6 +1021,20 @@ int ftb_unet3d_get_tap(ftb_unet* h, const char* name, float* out, void* stream) 
   auto it = h->taps.find(name);
   FTB_CHECK(it != h->taps.end(), std::string("no tap named '") + name + "'");
   return unpack_blocked_to_ncdhw(it->second, 0, it->second.C, out, (cudaStream_t)stream);
+}
+
+/* fp32 mode: copy a named fp32 intermediate of the last ftb_unet3d_forward_f32 (dims: B, C, X, Y, Z) */
+int ftb_unet3d_get_tap_f32(ftb_unet* h, const char* name, float* out, int* dims, void* stream) {
+  FTB_CHECK(h && name, "null argument");
+  auto it = h->taps32.find(name);
+  FTB_CHECK(it != h->taps32.end(), std::string("no fp32 tap named '") + name + "'");
+  const std::vector<long long>& v = it->second;
+  if (dims) for (int i = 0; i < 5; ++i) dims[i] = (int)v[1 + i];
+  if (out)
+    FTB_CUDA(cudaMemcpyAsync(out, reinterpret_cast<const float*>((uintptr_t)v[0]),
+                             (size_t)(v[1] * v[2] * v[3] * v[4] * v[5]) * sizeof(float), cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)stream));
+  return 0;
 }
 
 int ftb_unet3d_last_launches(const ftb_unet* h) { return h ? h->launches : 0; }

@@ -48,6 +48,7 @@ struct ConvEpilogue {
   float q_scale = 1.f;
   float* out_f32 = nullptr;      // NCDHW fp32 output (final conv) instead of blocked bf16
   int out_f32_c = 0;
+  bool out_f32_accum = false;    // fp32 mode: add to out_f32 instead of overwriting it
   // training: also store the pre-norm tensor (acc*rs + bias, shaped like `out`) that the backward of the
   // RMSNorm / FiLM / SiLU needs, and apply nn.Dropout after the activation (mask: ftb_common.cuh drop_mask8)
   const Act* pre_out = nullptr;
@@ -92,6 +93,7 @@ struct PackJob {
   bf16* dst;
   int cout, cin_real, ksize, cin_pad, n, ntiles, unfold_w;
   int transposed, ci0, src_cin;
+  int part;   // 0: bf16(w);  1: hi = bf16(w) again (fp32 mode);  2: lo = bf16(w - hi) (fp32 mode, 3 x bf16 split)
 };
 int pack_conv_weights_batched(const PackJob* d_jobs, int njobs, cudaStream_t st);
 
@@ -193,6 +195,20 @@ int mse_ratio_grad(const float* v, const float* vhat, long long n, const double*
 int grad_sumsq(const float* g, long long n, double* acc, cudaStream_t st);
 int adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
               float wd, int decoupled, int step, const double* sumsq, float gscale, float max_norm, cudaStream_t st);
+
+// ---------------------------------------------------------------- fp32 mode (f32_ops.cu): NCDHW fp32 tensors
+// x0 (|| x1) [B][C][vox] fp32 -> blocked bf16 with 2*CP channels: [hi(CP) | lo(CP)], hi = bf16(x), lo = bf16(x - hi)
+int f32_pack_split(const float* x0, int c0, const float* x1, int c1, int B, size_t vox, Act& out, cudaStream_t st);
+// out = act(n * gain[c] * s1[b][c] + sh[b][c]) + resid on NCDHW fp32, n = u / max(||u||_C, 1e-12) when norm
+int f32_normact(const float* u, int B, int C, size_t vox, bool norm, const float* gain, const float* s1, const float* sh,
+                int fstride, bool silu, const float* resid, float* out, cudaStream_t st);
+int f32_trilinear(const float* in, int B, int C, int Di, int Hi, int Wi, int Do, int Ho, int Wo, float* out, cudaStream_t st);
+// LinearAttention on qkv [B][3*hd][n] fp32 (q | k | v): out [B][hd][n]; scratch: B*hd*2 + B*heads*dh*dh floats
+int f32_linear_attention(float* qkv, int B, int heads, int dh, size_t n, const float* mem_kv, int n_mem, float* scratch,
+                         float* out, cudaStream_t st);
+// softmax attention, qkv [B][3*hd][n] fp32, mem_kv [2][heads][n_mem][dh]: out [B][hd][n]
+int f32_full_attention(const float* qkv, int B, int heads, int dh, int n, const float* mem_kv, int n_mem, float* out,
+                       cudaStream_t st);
 
 // ---------------------------------------------------------------- sampler / task kernels (fp32, NCDHW flat)
 int interp_xt_bt(int kind, int one_sided, float gamma_a, const float* x0, const float* x1,

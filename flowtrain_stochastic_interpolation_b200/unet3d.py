@@ -115,6 +115,38 @@ class Unet3D(nn.Module):
         self._flat = None      # flat fp32 parameter buffer once training.flatten_parameters() bound it
         self._drop_seed = None  # explicit dropout seed for the next train-mode forward (tests); else a counter
         self._drop_count = 0
+        self.precision = "bf16"  # "bf16": tensor-core operands in bf16; "fp32": 3 x bf16 split convs, fp32 elsewhere
+        self._workspace_f32 = {}
+
+    def set_precision(self, precision: str):
+        """``"bf16"`` (default: bf16 operands, fp32 accumulation, <= 2e-2 rel-L2 of the fp32 reference) or
+        ``"fp32"`` (accuracy mode: every Conv3d as three bf16 tensor-core products accumulated in fp32, everything
+        else in fp32; <= 1e-4 rel-L2 of the reference with ``cudnn.allow_tf32=False``).  Inference only."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        if precision == "fp32" and self._conditional:
+            raise NotImplementedError("the fp32 accuracy mode is implemented for the unconditional Unet3D only")
+        self.precision = precision
+        return self
+
+    def _forward_f32(self, xin, tin):
+        B, _, X, Y, Z = xin.shape
+        key = (str(xin.device), B, X, Y, Z)
+        ws = self._workspace_f32.get(key)
+        if ws is None:
+            nbytes = _lib.lib.ftb_unet3d_f32_workspace_bytes(self._handle, B, X, Y, Z)
+            if nbytes == 0:
+                raise _lib.FtbError(_lib.last_error())
+            self._workspace_f32.clear()
+            ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=xin.device)
+            self._workspace_f32[key] = ws
+        base = (ws.data_ptr() + 255) // 256 * 256
+        out = torch.empty_like(xin)
+        _lib.check(_lib.lib.ftb_unet3d_forward_f32(
+            self._handle, _lib.ptr(xin), _lib.ptr(tin), _lib.ptr(out), B, X, Y, Z,
+            C.c_void_p(base), ws.numel() - (base - ws.data_ptr()), _lib.stream_ptr()))
+        self.last_launches = _lib.lib.ftb_unet3d_last_launches(self._handle)
+        return out
 
     # ------------------------------------------------------------------ parameter tree
     def _plan(self):
@@ -290,11 +322,20 @@ class Unet3D(nn.Module):
         if self._needs_grad(x):
             # training step (model_train_inference.py:440): forward with saved activations, autograd bridge
             from .training import UnetTrainFn, flatten_parameters
+            if self.precision != "bf16":
+                raise NotImplementedError("the training step runs in bf16 (precision='fp32' is inference only)")
             if self._flat is None:
                 flatten_parameters(self)
             xin = self._f32c(x)
             tin = time.detach().to(device=x.device, dtype=torch.float32).contiguous()
             return UnetTrainFn.apply(self, xin, tin, *self.parameters())
+        if self.precision == "fp32":
+            with torch.cuda.device(x.device):
+                xin = self._f32c(x)
+                tin = time.detach().to(device=x.device, dtype=torch.float32).contiguous()
+                self._sync_params(x.device)
+                out = self._forward_f32(xin, tin)
+            return out if x.dtype == torch.float32 else out.to(x.dtype)
         if self._use_graph and not self._conditional:
             with torch.cuda.device(x.device):
                 xin = self._f32c(x)
@@ -325,6 +366,18 @@ class Unet3D(nn.Module):
         out = torch.empty((B, c.value, x.value, y.value, z.value), dtype=torch.float32, device=ws.device)
         with torch.cuda.device(ws.device):
             _lib.check(_lib.lib.ftb_unet3d_get_tap(self._handle, name.encode(), _lib.ptr(out), _lib.stream_ptr()))
+        return out
+
+    def get_tap_f32(self, name: str) -> torch.Tensor:
+        """fp32 mode: copy of a named intermediate of the LAST fp32 forward.  Stage outputs always survive; block
+        internals only when the process runs with FTB_F32_KEEP=1 (no workspace reuse)."""
+        dims = (C.c_int * 5)()
+        _lib.check(_lib.lib.ftb_unet3d_get_tap_f32(self._handle, name.encode(), None, dims, None))
+        ws = next(iter(self._workspace_f32.values()))
+        out = torch.empty(tuple(dims), dtype=torch.float32, device=ws.device)
+        with torch.cuda.device(ws.device):
+            _lib.check(_lib.lib.ftb_unet3d_get_tap_f32(self._handle, name.encode(), _lib.ptr(out), dims,
+                                                       _lib.stream_ptr()))
         return out
 
     def __del__(self):

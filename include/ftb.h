@@ -70,6 +70,14 @@ size_t ftb_unet3d_workspace_bytes(ftb_unet* h, int B, int X, int Y, int Z);
 /* x [B,C,X,Y,Z] fp32, t [B] fp32 -> out [B,C,X,Y,Z] fp32.  bf16 tensor-core path. */
 int ftb_unet3d_forward(ftb_unet* h, const float* x, const float* t, float* out, int B, int X, int Y,
                        int Z, void* workspace, size_t workspace_bytes, void* stream);
+/* fp32 accuracy mode of the same call (BASELINE: fp32 velocity field within 1e-4 relative L2 of the reference,
+ * src/flowtrain/models/unet_attn_3d.py:673-719): NCDHW fp32 activations, every Conv3d as three bf16 tcgen05
+ * products (W_hi x_hi + W_hi x_lo + W_lo x_hi) accumulated in fp32.  About 3-4x the cost of the bf16 path. */
+size_t ftb_unet3d_f32_workspace_bytes(ftb_unet* h, int B, int X, int Y, int Z);
+int ftb_unet3d_forward_f32(ftb_unet* h, const float* x, const float* t, float* out, int B, int X, int Y, int Z,
+                           void* workspace, size_t workspace_bytes, void* stream);
+/* after ftb_unet3d_forward_f32: dims[5] = (B, C, X, Y, Z) of a named intermediate; out (may be NULL) receives it */
+int ftb_unet3d_get_tap_f32(ftb_unet* h, const char* name, float* out, int* dims, void* stream);
 /* ---- conditional velocity field: replaces Unet3DCond.forward(x, ATb, time)
  *      (src/flowtrain/models/unet_attn_3d_cond_v3.py:769-828; handle created with cfg.conditional = 1).
  * atb is [atb_B, C, X, Y, Z] fp32 with atb_B = B, or 1 when one conditioning volume is shared by the
