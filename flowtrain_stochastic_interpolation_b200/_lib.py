@@ -86,6 +86,7 @@ _SIGS = {
     "ftb_unet3d_set_dropout": (_i, [_vp, _f, C.c_uint64]),
     "ftb_unet3d_train_workspace_bytes": (_sz, [_vp, _i, _i, _i, _i]),
     "ftb_unet3d_forward_train": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "ftb_unet3d_cond_forward_train": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "ftb_unet3d_backward": (_i, [_vp, _vp, _vp, _vp, _sz, BUCKET_CB, _vp, _vp]),
     "ftb_mse_ratio_grad": (_i, [_vp, _vp, _i64, _vp, _f, _vp, _vp]),
     "ftb_grad_sumsq": (_i, [_vp, _i64, _vp, _vp]),

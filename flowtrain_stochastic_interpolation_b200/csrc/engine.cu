@@ -1171,7 +1171,7 @@ int ftb_unet3d_mark_dirty(ftb_unet* h) {
 }
 
 size_t ftb_unet3d_train_workspace_bytes(ftb_unet* h, int B, int X, int Y, int Z) {
-  if (check_dims(h, B, X, Y, Z) != 0 || h->cfg.conditional) return 0;
+  if (check_dims(h, B, X, Y, Z) != 0) return 0;
   TrainState T;
   ensure_offsets(h, &T);
   TrainCtx c{h, &T, nullptr, reinterpret_cast<char*>(uintptr_t(1) << 40), 0, true, B};
@@ -1181,10 +1181,9 @@ size_t ftb_unet3d_train_workspace_bytes(ftb_unet* h, int B, int X, int Y, int Z)
   return round_up_sz(c.off, 256) + 256;
 }
 
-int ftb_unet3d_forward_train(ftb_unet* h, const float* x, const float* t, float* out, int B, int X, int Y, int Z,
-                             void* workspace, size_t workspace_bytes, void* stream) {
+static int forward_train_impl(ftb_unet* h, const float* x, const float* atb, const float* t, float* out, int B, int X,
+                              int Y, int Z, void* workspace, size_t workspace_bytes, void* stream) {
   FTB_TRY(check_dims(h, B, X, Y, Z));
-  FTB_CHECK(!h->cfg.conditional, "training path: only the unconditional Unet3D is implemented");
   FTB_CHECK(x && t && out && workspace, "null argument");
   FTB_CHECK(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1200,13 +1199,26 @@ int ftb_unet3d_forward_train(ftb_unet* h, const float* x, const float* t, float*
             "training workspace too small: need " + std::to_string(T->need_bytes) + " bytes");
   h->train_ctx.reset(new TrainCtx{h, T, st, reinterpret_cast<char*>(workspace), 0, false, B});
   TrainFwd f{h, T, *h->train_ctx};
-  FTB_TRY(f.run(x, t, out, X, Y, Z));
+  FTB_TRY(f.run(x, t, out, X, Y, Z, atb));
   FTB_CHECK(h->train_ctx->off <= workspace_bytes, "training workspace too small for the forward");
   T->fwd_bytes = h->train_ctx->off;
   T->B = B; T->X = X; T->Y = Y; T->Z = Z;
   T->valid = true;
-  (void)workspace_bytes;
   return 0;
+}
+
+int ftb_unet3d_forward_train(ftb_unet* h, const float* x, const float* t, float* out, int B, int X, int Y, int Z,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  FTB_CHECK(h, "null handle");
+  FTB_CHECK(!h->cfg.conditional, "conditional model: call ftb_unet3d_cond_forward_train (ATb is required)");
+  return forward_train_impl(h, x, nullptr, t, out, B, X, Y, Z, workspace, workspace_bytes, stream);
+}
+
+int ftb_unet3d_cond_forward_train(ftb_unet* h, const float* x, const float* atb, const float* t, float* out, int B,
+                                  int X, int Y, int Z, void* workspace, size_t workspace_bytes, void* stream) {
+  FTB_CHECK(h && atb, "null argument");
+  FTB_CHECK(h->cfg.conditional, "unconditional model: call ftb_unet3d_forward_train");
+  return forward_train_impl(h, x, atb, t, out, B, X, Y, Z, workspace, workspace_bytes, stream);
 }
 
 int ftb_unet3d_backward(ftb_unet* h, const float* dout, float* grads, void* workspace, size_t workspace_bytes,

@@ -222,17 +222,24 @@ struct TrainFwd {
     return 0;
   }
 
+  // explicit rows of the FiLM table (MixATb: the (scale | shift) halves of x and of the ATb embedding); the caller
+  // pushes the backward of the block's Linear itself
+  struct FilmSlice { int s1 = -1, sh = -1; };
+
   // out = act(norm(u) * gain * s1 + sh) + resid
   int normact(const Act& u, bool norm, const std::string& gain_name, const std::string& film_block, bool silu,
-              const Act* resid, Act& out, const std::string& bias_of_u = "", bool forward_done = false) {
+              const Act* resid, Act& out, const std::string& bias_of_u = "", bool forward_done = false,
+              const FilmSlice* fs = nullptr) {
     const int C = u.C;
     const float* gain = gain_name.empty() ? nullptr : U->gains.at(gain_name).gs;
-    const int foff = film_block.empty() ? -1 : U->film_off.at(film_block);
+    const int foff = fs ? fs->s1 : (film_block.empty() ? -1 : U->film_off.at(film_block));
+    const int shoff = fs ? fs->sh : foff + C;
+    const bool own_linear = foff >= 0 && fs == nullptr;
     const float* s1 = foff >= 0 ? c.film_raw + foff : nullptr;
-    const float* sh = foff >= 0 ? c.film_raw + foff + C : nullptr;
+    const float* sh = foff >= 0 ? c.film_raw + shoff : nullptr;
     const int fstride = U->film_rows;
     // nn.Dropout sits at the end of Block.forward (:244) and only block1 gets p > 0 (:261): the FiLM'd block
-    const float dp = foff >= 0 ? U->drop_p : 0.f;
+    const float dp = own_linear ? U->drop_p : 0.f;
     const unsigned long long dkey = U->drop_seed * 0x9E3779B97F4A7C15ull + ((unsigned long long)(foff + 1) << 40);
     if (!forward_done) TRUN(normact_fwd(u, norm, gain, s1, sh, fstride, silu, resid, out, c.st, dp, dkey));
     const Act Uu = u, O = out, R = resid ? *resid : Act();
@@ -244,7 +251,7 @@ struct TrainFwd {
       float* Rb = c.f32((size_t)c.B * C);
       FTB_TRY(c.zero(Rb, (size_t)c.B * C * sizeof(float)));
       TrainCtx::GradSlot& gu = c.grad(Uu);
-      float* S = foff >= 0 ? c.dfilm + foff + C : nullptr;
+      float* S = foff >= 0 ? c.dfilm + shoff : nullptr;
       float* dbias = bias_of_u.empty() ? nullptr : c.gptr(bias_of_u);   // bias gradient of the conv that produced u
       if (gu.init) {   // the input also feeds a residual path: add to its gradient
         Act tmp = c.like(Uu);
@@ -257,7 +264,7 @@ struct TrainFwd {
       float* ds1 = foff >= 0 ? c.dfilm + foff : nullptr;
       float* dg = gain_name.empty() ? nullptr : c.gptr(gain_name);
       if (ds1 || dg) TRUN(normact_finish(Rb, c.B, C, gain, s1, fstride, sqrtf((float)C), ds1, dg, c.st));
-      if (foff >= 0) {
+      if (own_linear) {
         // this block's FiLM Linear (SiLU -> Linear(time_dim -> 2C)): dW, db now, d silu(temb) accumulated
         const int td = c.U->time_dim;
         TRUN(linear_bwd(c.dfilm + foff, fstride, c.temb_silu, c.pdev(film_block + ".weight"), c.B, 2 * C, td,
@@ -428,6 +435,45 @@ struct TrainFwd {
     return 0;
   }
 
+  // EmbedATb.forward (unet_attn_3d_cond_v3.py:131-139): trilinear(opened ATb) -> conv 5^3 -> SiLU -> conv 5^3
+  int embed_atb(const std::string& p, const Act& opened, int cin_real, int C, int D, int H, int W, Act* out) {
+    Act src = opened;
+    if (opened.D != D || opened.H != H || opened.W != W) FTB_TRY(resample(opened, D, H, W, &src));
+    Act u1 = c.act(C, D, H, W), e1 = c.like(u1);
+    FTB_TRY(conv(p + ".conv1", src, nullptr, cin_real, 0, nullptr, false, nullptr, u1, false));
+    FTB_TRY(normact(u1, false, "", "", true, nullptr, e1));
+    *out = c.like(u1);
+    FTB_TRY(conv(p + ".conv2", e1, nullptr, C, 0, nullptr, false, nullptr, *out, false));
+    return 0;
+  }
+
+  // MixATb.forward (unet_attn_3d_cond_v3.py:175-190): FiLM(cat(x, emb)) -> conv 3^3 -> RMSNorm -> SiLU -> conv 3^3, + x.
+  // The FiLM of the concat is applied to its two halves separately (rows [0,C) | [C,2C) of scale and shift) and the
+  // conv reads them as its two sources, so the concatenated tensor is never formed.
+  int mix_atb(const std::string& p, const Act& x, const Act& emb, Act* out) {
+    const int C = x.C;
+    const std::string lin = p + ".time_mlp.1";
+    const int foff = U->film_off.at(lin);
+    // (pushed first: in the backward it runs after both FiLM halves have written their rows of dfilm)
+    T->tape.push_back([=](TrainCtx& c) -> int {
+      TRUN(linear_bwd(c.dfilm + foff, c.U->film_rows, c.temb_silu, c.pdev(lin + ".weight"), c.B, 4 * C, c.U->time_dim,
+                      c.gptr(lin + ".weight"), c.gptr(lin + ".bias"), c.dts, true, c.st));
+      return 0;
+    });
+    Act xf = c.like(x), ef = c.like(emb);
+    const FilmSlice fx{foff, foff + 2 * C}, fe{foff + C, foff + 3 * C};
+    FTB_TRY(normact(x, false, "", "", false, nullptr, xf, "", false, &fx));
+    FTB_TRY(normact(emb, false, "", "", false, nullptr, ef, "", false, &fe));
+    Act u1 = c.like(x), h1 = c.like(x);
+    const bool fz = fuse_ok(C);
+    ConvEpilogue f1 = fused_epilogue(p + ".norm.g", "", C, true, nullptr);
+    FTB_TRY(conv(p + ".conv1", xf, &ef, C, C, nullptr, false, nullptr, u1, false, false, true, fz ? &f1 : nullptr, &h1));
+    FTB_TRY(normact(u1, true, p + ".norm.g", "", true, nullptr, h1, p + ".conv1.bias", fz));
+    *out = c.like(x);
+    FTB_TRY(conv(p + ".conv2", h1, nullptr, C, 0, &x, false, nullptr, *out, false));
+    return 0;
+  }
+
   // a contiguous range of parameters [first, last] is complete once the backward passes this point
   void marker(const std::string& first, const std::string& last) {
     const int i0 = U->pindex.at(first), i1 = U->pindex.at(last);
@@ -438,9 +484,10 @@ struct TrainFwd {
     });
   }
 
-  int run(const float* x, const float* t, float* y, int X, int Y, int Z) {
+  int run(const float* x, const float* t, float* y, int X, int Y, int Z, const float* atb = nullptr) {
     const ftb_unet_cfg& cf = U->cfg;
-    FTB_CHECK(!cf.conditional, "training path: only the unconditional Unet3D is implemented");
+    const bool cond = cf.conditional != 0;
+    const int o = cond ? 2 : 0;   // module index of the first ResnetBlock inside a stage (after EmbedATb, MixATb)
     const int n = cf.n_stages;
     auto sub = [&](const std::string& p, int k) { return p + "." + std::to_string(k); };
     auto last_param = [&](const std::string& prefix) {   // last parameter whose name starts with prefix
@@ -465,7 +512,7 @@ struct TrainFwd {
     float* tcopy = c.f32((size_t)c.B);
     if (!c.dry) FTB_CUDA(cudaMemcpyAsync(tcopy, t, c.B * sizeof(float), cudaMemcpyDeviceToDevice, c.st));
     T->t_dev = tcopy;
-    marker("init_conv.weight", "time_mlp.3.bias");
+    marker(U->params[0].name, "time_mlp.3.bias");
     {
       TimeMlpParams tp{c.pdev("time_mlp.0.freqs"), c.pdev("time_mlp.0.phases"), c.pdev("time_mlp.1.weight"),
                        c.pdev("time_mlp.1.bias"), c.pdev("time_mlp.3.weight"), c.pdev("time_mlp.3.bias"), tr, td};
@@ -502,13 +549,19 @@ struct TrainFwd {
         return 0;
       });
     }
-    // ---- stem
-    const ConvLayer& stem = U->convs.at("init_conv");
-    Act xin = c.act(stem.unfold_w ? stem.k * stem.cin : stem.cin, X, Y, Z);
-    if (stem.unfold_w) TRUN(pack_unfold_w(x, c.B, stem.cin, X, Y, Z, stem.k, xin, c.st));
-    else TRUN(pack_ncdhw_to_blocked(x, c.B, stem.cin, X, Y, Z, xin, c.st));
-    Act r = c.act(cf.dim, X, Y, Z);
-    FTB_TRY(conv("init_conv", xin, nullptr, stem.cin, 0, nullptr, false, nullptr, r, true));
+    // ---- stem(s): NCDHW fp32 -> blocked bf16 (W-unfolded when the conv was planned that way) -> 7^3 conv
+    auto stem_conv = [&](const std::string& name, const float* src, int cout, Act* out) -> int {
+      const ConvLayer& stem = U->convs.at(name);
+      Act xin = c.act(stem.unfold_w ? stem.k * stem.cin : stem.cin, X, Y, Z);
+      if (stem.unfold_w) TRUN(pack_unfold_w(src, c.B, stem.cin, X, Y, Z, stem.k, xin, c.st));
+      else TRUN(pack_ncdhw_to_blocked(src, c.B, stem.cin, X, Y, Z, xin, c.st));
+      *out = c.act(cout, X, Y, Z);
+      return conv(name, xin, nullptr, stem.cin, 0, nullptr, false, nullptr, *out, true);
+    };
+    Act opened;   // init_conv_ATb(ATb) (:778): its gradient collects from the EmbedATb of every stage
+    if (cond) FTB_TRY(stem_conv("init_conv_ATb", atb, cf.data_channels, &opened));
+    Act r;
+    FTB_TRY(stem_conv(cond ? "init_conv_x" : "init_conv", x, cf.dim, &r));
     Act cur = r;
     std::vector<Act> skips;
     for (int i = 0; i < n; ++i) {
@@ -516,19 +569,25 @@ struct TrainFwd {
       const int din = U->in_out[i].first, dout = U->in_out[i].second;
       marker(first_param(p + "."), last_param(p + "."));
       Act a1, a2, a3, a4;
-      FTB_TRY(resnet(sub(p, 0), cur, nullptr, din, 0, din, &a1));
+      if (cond) {
+        Act emb, mixed;
+        FTB_TRY(embed_atb(sub(p, 0), opened, cf.data_channels, din, cur.D, cur.H, cur.W, &emb));
+        FTB_TRY(mix_atb(sub(p, 1), cur, emb, &mixed));
+        cur = mixed;
+      }
+      FTB_TRY(resnet(sub(p, o), cur, nullptr, din, 0, din, &a1));
       skips.push_back(a1);
-      FTB_TRY(resnet(sub(p, 1), a1, nullptr, din, 0, din, &a2));
-      FTB_TRY(attention(sub(p, 2), a2, cf.full_attn[i] != 0, &a3));
+      FTB_TRY(resnet(sub(p, o + 1), a1, nullptr, din, 0, din, &a2));
+      FTB_TRY(attention(sub(p, o + 2), a2, cf.full_attn[i] != 0, &a3));
       skips.push_back(a3);
       if (i >= n - 1) {
         a4 = c.act(dout, a3.D, a3.H, a3.W);
-        FTB_TRY(conv(sub(p, 3), a3, nullptr, din, 0, nullptr, false, nullptr, a4, false));
+        FTB_TRY(conv(sub(p, o + 3), a3, nullptr, din, 0, nullptr, false, nullptr, a4, false));
       } else {
         Act ds;
         FTB_TRY(resample(a3, a3.D / 2, a3.H / 2, a3.W / 2, &ds));
         a4 = c.act(dout, ds.D, ds.H, ds.W);
-        FTB_TRY(conv(sub(p, 3) + ".conv", ds, nullptr, din, 0, nullptr, false, nullptr, a4, false));
+        FTB_TRY(conv(sub(p, o + 3) + ".conv", ds, nullptr, din, 0, nullptr, false, nullptr, a4, false));
       }
       cur = a4;
     }
@@ -546,19 +605,25 @@ struct TrainFwd {
       const int din = U->in_out[n - 1 - i].first, dout = U->in_out[n - 1 - i].second;
       marker(first_param(p + "."), last_param(p + "."));
       Act a1, a2, a3, a4;
+      if (cond) {
+        Act emb, mixed;
+        FTB_TRY(embed_atb(sub(p, 0), opened, cf.data_channels, dout, cur.D, cur.H, cur.W, &emb));
+        FTB_TRY(mix_atb(sub(p, 1), cur, emb, &mixed));
+        cur = mixed;
+      }
       Act s = skips.back(); skips.pop_back();
-      FTB_TRY(resnet(sub(p, 0), cur, &s, dout, din, dout, &a1));
+      FTB_TRY(resnet(sub(p, o), cur, &s, dout, din, dout, &a1));
       s = skips.back(); skips.pop_back();
-      FTB_TRY(resnet(sub(p, 1), a1, &s, dout, din, dout, &a2));
-      FTB_TRY(attention(sub(p, 2), a2, cf.full_attn[n - 1 - i] != 0, &a3));
+      FTB_TRY(resnet(sub(p, o + 1), a1, &s, dout, din, dout, &a2));
+      FTB_TRY(attention(sub(p, o + 2), a2, cf.full_attn[n - 1 - i] != 0, &a3));
       if (i == n - 1) {
         a4 = c.act(din, a3.D, a3.H, a3.W);
-        FTB_TRY(conv(sub(p, 3), a3, nullptr, dout, 0, nullptr, false, nullptr, a4, false));
+        FTB_TRY(conv(sub(p, o + 3), a3, nullptr, dout, 0, nullptr, false, nullptr, a4, false));
       } else {
         Act us;
         FTB_TRY(resample(a3, a3.D * 2, a3.H * 2, a3.W * 2, &us));
         a4 = c.act(din, us.D, us.H, us.W);
-        FTB_TRY(conv(sub(p, 3) + ".conv", us, nullptr, dout, 0, nullptr, false, nullptr, a4, false));
+        FTB_TRY(conv(sub(p, o + 3) + ".conv", us, nullptr, dout, 0, nullptr, false, nullptr, a4, false));
       }
       cur = a4;
     }

@@ -91,8 +91,9 @@ def train_workspace(net, device, B, X, Y, Z):
     return ws, base, ws.numel() - (base - ws.data_ptr())
 
 
-def forward_train(net, xin, tin):
-    """Train-mode forward: keeps the intermediates in the workspace and records the backward."""
+def forward_train(net, xin, tin, ain=None):
+    """Train-mode forward: keeps the intermediates in the workspace and records the backward.
+    ``ain``: the conditioning volume ATb [B,C,X,Y,Z] of a ``Unet3DCond``."""
     B, _, X, Y, Z = xin.shape
     if getattr(net, "_flat", None) is None:
         flatten_parameters(net)
@@ -107,8 +108,13 @@ def forward_train(net, xin, tin):
         net._drop_count += 1
         seed = (torch.initial_seed() * 0x9E3779B1 + net._drop_count) & 0xFFFFFFFFFFFFFFFF
     _lib.check(_lib.lib.ftb_unet3d_set_dropout(net._handle, float(p_drop), seed))
-    _lib.check(_lib.lib.ftb_unet3d_forward_train(net._handle, _lib.ptr(xin), _lib.ptr(tin), _lib.ptr(out), B, X, Y, Z,
-                                                 C.c_void_p(base), nbytes, _lib.stream_ptr()))
+    if ain is not None:
+        _lib.check(_lib.lib.ftb_unet3d_cond_forward_train(net._handle, _lib.ptr(xin), _lib.ptr(ain), _lib.ptr(tin),
+                                                          _lib.ptr(out), B, X, Y, Z, C.c_void_p(base), nbytes,
+                                                          _lib.stream_ptr()))
+    else:
+        _lib.check(_lib.lib.ftb_unet3d_forward_train(net._handle, _lib.ptr(xin), _lib.ptr(tin), _lib.ptr(out), B, X, Y,
+                                                     Z, C.c_void_p(base), nbytes, _lib.stream_ptr()))
     return out
 
 
@@ -122,14 +128,15 @@ def backward_into(net, dout, gflat, bucket_cb=None):
 
 
 class UnetTrainFn(torch.autograd.Function):
-    """autograd bridge: forward = ftb_unet3d_forward_train, backward = ftb_unet3d_backward.  The gradient
-    w.r.t. the network INPUT is not computed (the training step never needs it: XT is data)."""
+    """autograd bridge: forward = ftb_unet3d_(cond_)forward_train, backward = ftb_unet3d_backward.  The gradient
+    w.r.t. the network INPUTS (x, ATb) is not computed: the training steps never need it, XT and ATb are data
+    (the conditional project freezes its embedding, model_train_sh_inference_cond.py:302)."""
 
     @staticmethod
-    def forward(ctx, net, x, t, *params):
+    def forward(ctx, net, x, t, atb, *params):
         ctx.net = net
         with torch.cuda.device(x.device):
-            out = forward_train(net, x, t)
+            out = forward_train(net, x, t, atb)
         return out
 
     @staticmethod
@@ -142,7 +149,7 @@ class UnetTrainFn(torch.autograd.Function):
         grads = []
         for (name, p), off in zip(net.named_parameters(), net._flat_offsets):
             grads.append(gflat[off:off + p.numel()].view(p.shape) if p.requires_grad else None)
-        return (None, None, None, *grads)
+        return (None, None, None, None, *grads)
 
 
 # --------------------------------------------------------------------------- fused training step

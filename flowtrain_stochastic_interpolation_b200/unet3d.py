@@ -245,8 +245,6 @@ class Unet3D(nn.Module):
         if self._needs_grad(x):
             if x.requires_grad:
                 raise NotImplementedError("the gradient w.r.t. the network input is not computed on the B200 path")
-            if self._conditional:
-                raise NotImplementedError("backward through Unet3DCond is not implemented (sampling / no_grad only)")
         if x.dim() != 5 or x.shape[1] != self.channels:
             raise ValueError(f"expected x of shape [B,{self.channels},X,Y,Z], got {tuple(x.shape)}")
         B, _, X, Y, Z = x.shape
@@ -328,7 +326,7 @@ class Unet3D(nn.Module):
                 flatten_parameters(self)
             xin = self._f32c(x)
             tin = time.detach().to(device=x.device, dtype=torch.float32).contiguous()
-            return UnetTrainFn.apply(self, xin, tin, *self.parameters())
+            return UnetTrainFn.apply(self, xin, tin, None, *self.parameters())
         if self.precision == "fp32":
             with torch.cuda.device(x.device):
                 xin = self._f32c(x)
@@ -426,6 +424,18 @@ class Unet3DCond(Unet3D):
             raise AssertionError(f"Input and ATb shapes do not match: {tuple(x.shape)} and {tuple(ATb.shape)}")
         if ATb.device != x.device:
             raise RuntimeError("x and ATb must be on the same device")
+        if self._needs_grad(x):
+            # conditional training step (model_train_sh_inference_cond.py:431): autograd bridge, one ATb per sample
+            from .training import UnetTrainFn, flatten_parameters
+            if ATb.requires_grad:
+                raise NotImplementedError("the gradient w.r.t. ATb is not computed on the B200 path")
+            if ATb.shape[0] != B:
+                raise AssertionError(f"Input and ATb shapes do not match: {tuple(x.shape)} and {tuple(ATb.shape)}")
+            if self._flat is None:
+                flatten_parameters(self)
+            self._atb_key = None   # the training workspace replaces the sampling one
+            tin = time.detach().to(device=x.device, dtype=torch.float32).contiguous()
+            return UnetTrainFn.apply(self, self._f32c(x), tin, self._f32c(ATb), *self.parameters())
         with torch.cuda.device(x.device):
             xin = self._f32c(x)
             ain = self._f32c(ATb)

@@ -150,6 +150,11 @@ int ftb_unet3d_set_dropout(ftb_unet* h, float p, uint64_t seed);
 size_t ftb_unet3d_train_workspace_bytes(ftb_unet* h, int B, int X, int Y, int Z);
 int ftb_unet3d_forward_train(ftb_unet* h, const float* x, const float* t, float* out, int B, int X, int Y, int Z,
                              void* workspace, size_t workspace_bytes, void* stream);
+/* conditional model (Unet3DCond.forward(x, ATb, time) under autograd, model_train_sh_inference_cond.py:431):
+ * atb [B,C,X,Y,Z] fp32 (one conditioning volume per sample, ATb = X1 * mask, :414-420).  The backward is the same
+ * ftb_unet3d_backward; ATb and x are data, so no input gradient is produced. */
+int ftb_unet3d_cond_forward_train(ftb_unet* h, const float* x, const float* atb, const float* t, float* out, int B,
+                                  int X, int Y, int Z, void* workspace, size_t workspace_bytes, void* stream);
 int ftb_unet3d_backward(ftb_unet* h, const float* dout, float* grads_flat, void* workspace, size_t workspace_bytes,
                         void (*bucket_cb)(void* user, int64_t offset, int64_t count), void* cb_user, void* stream);
 /* gradient of the flow loss (model_train_inference.py:443) w.r.t. vhat, from the sums ftb_mse_ratio_accumulate

@@ -102,6 +102,29 @@ def training_grads(params, cfg, XT, T, VT):
     return loss.detach(), vhat.detach(), {k: (g if g is not None else torch.zeros_like(p[k])) for k, g in zip(names, grads)}
 
 
+def cond_training_grads(params, cfg, XT, ATb, T, VT):
+    """Conditional counterpart of ``training_grads``: autograd gradients of the flow loss through the functional
+    oracle Unet3DCond v3 (oracle/unet3d_cond.py; reference call site model_train_sh_inference_cond.py:431), dropout 0."""
+    from . import unet3d_cond
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in params.items()}
+    vhat = unet3d_cond.unet3d_cond_forward(p, cfg, XT, ATb, T)
+    loss = flow_loss(VT, vhat)
+    names = list(p.keys())
+    grads = torch.autograd.grad(loss, [p[k] for k in names], allow_unused=True)
+    return loss.detach(), vhat.detach(), {k: (g if g is not None else torch.zeros_like(p[k])) for k, g in zip(names, grads)}
+
+
+def cond_training_loss(VT, VT_hat, XT, X1, T, mask, lambda_reconstruct):
+    """Loss of the conditional training_step (model_train_sh_inference_cond.py:432-452): flow loss with the 1e-6
+    guard plus the T-weighted reconstruction of the observed voxels, b_hat = XT + (1 - T) VT_hat on the mask."""
+    Tb = T.view(-1, 1, 1, 1, 1)
+    b = X1[mask]
+    b_hat = XT[mask] + ((1 - Tb) * VT_hat)[mask]
+    mse = F.mse_loss(VT, VT_hat) / (F.mse_loss(VT, torch.zeros_like(VT)) + 1e-6)
+    rec = (Tb.squeeze() * F.mse_loss(b, b_hat)) / (F.mse_loss(X1, torch.zeros_like(X1)) + 1e-6)
+    return mse + lambda_reconstruct * rec.mean()
+
+
 def adam_reference(p, g, m, v, step, lr=2e-4, b1=0.9, b2=0.999, eps=1e-8, max_norm=1.0, total_norm=None):
     """clip_grad_norm_(max_norm) + one torch.optim.Adam step (configure_optimizers :465-473, Lightning
     gradient_clip_val), restated on flat tensors.  Returns (p, m, v)."""

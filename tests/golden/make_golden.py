@@ -92,6 +92,42 @@ def gen_train():
         np.savez_compressed(os.path.join(OUT, f"train_{name}.npz"), **out)
 
 
+TRAIN_COND_CFGS = {
+    "small": (dict(dim=32, dim_mults=(1, 2), data_channels=15, time_resolution=64, time_bandwidth=100.0,
+                   attn_heads=2, attn_dim_head=16), 8, (2, 15, 16, 16, 16)),
+    "full": (dict(data_channels=15), 5, (1, 15, 16, 16, 16)),
+}
+TRAIN_COND_FULL_GRADS = ("init_conv_ATb.weight", "init_conv_ATb.bias", "init_conv_x.bias", "downs.0.0.conv1.bias",
+                         "downs.0.0.conv2.bias", "downs.0.1.time_mlp.1.weight", "downs.0.1.time_mlp.1.bias",
+                         "downs.0.1.norm.g", "downs.1.1.conv2.bias", "ups.0.0.conv1.bias", "ups.1.1.conv1.bias",
+                         "final_conv.weight")
+
+
+def gen_train_cond():
+    """Gradients of the flow loss through the REFERENCE Unet3DCond v3 (autograd; call site
+    model_train_sh_inference_cond.py:431), dropout 0, for fixed XT / ATb / T / VT."""
+    for name, (over, pseed, shape) in TRAIN_COND_CFGS.items():
+        cfg = synth.make_cfg(**over)
+        p = synth.synth_unet3d_cond_params(cfg, pseed)
+        m = ref_loader.build_reference_unet_cond(cfg, p)
+        xt = synth.synth_input(shape, 11, "xt")
+        vt = synth.synth_input(shape, 12, "vt")
+        atb = synth.synth_atb(shape, 14)
+        t = synth.synth_times(shape[0], 13)
+        vhat = m(xt, atb, t)
+        loss = task.flow_loss(vt, vhat)
+        loss.backward()
+        out = {"loss": np.float64(loss.item()), "t": t.numpy(), "vhat": vhat.detach().numpy()}
+        for k, prm in m.named_parameters():
+            g = prm.grad.detach().reshape(-1)
+            out[f"norm/{k}"] = np.float64(g.double().norm().item())
+            idx = torch.linspace(0, g.numel() - 1, min(16, g.numel())).long()
+            out[f"sample/{k}"] = g[idx].numpy()
+            if k in TRAIN_COND_FULL_GRADS:
+                out[f"full/{k}"] = prm.grad.detach().numpy()
+        np.savez_compressed(os.path.join(OUT, f"train_cond_{name}.npz"), **out)
+
+
 def gen_unet_cond():
     """Unet3DCond v3 (the conditional project's model: 15-d embedding, mults 1,2,2,3,4)."""
     cfg = synth.make_cfg(data_channels=15)
@@ -204,11 +240,15 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "train":   # only the training fixtures
         gen_train()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "train_cond":
+        gen_train_cond()
+        sys.exit(0)
     gen_interp()
     gen_solvers()
     gen_decode()
     gen_unet()
     gen_unet_cond()
     gen_train()
+    gen_train_cond()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -85,6 +85,11 @@ WGRAD_CASES = [
     dict(B=1, c1=48, c2=0, cout=48, k=3, dims=(3, 5, 7)),        # ragged
     dict(B=3, c1=48, c2=0, cout=96, k=3, dims=(5, 20, 12)),
     dict(B=1, c1=48, c2=0, cout=48, k=5, dims=(8, 8, 8)),
+    # conditional model: EmbedATb 5^3 convs from the 15-channel opened ATb and at the widest stage, cubic 7^3 stems
+    dict(B=2, c1=15, c2=0, cout=48, k=5, dims=(8, 16, 16)),
+    dict(B=1, c1=192, c2=0, cout=192, k=5, dims=(4, 4, 4)),
+    dict(B=1, c1=15, c2=0, cout=15, k=7, dims=(8, 16, 16)),
+    dict(B=1, c1=15, c2=0, cout=48, k=7, dims=(8, 8, 16)),
 ]
 
 
@@ -129,6 +134,8 @@ def dgrad_case(B, cin, cout, k, dims, acc=False, seed=0):
     dict(B=1, cin=48, cout=384, k=1, dims=(8, 16, 16)),
     dict(B=1, cin=48, cout=18, k=1, dims=(4, 8, 8), acc=True),
     dict(B=1, cin=144, cout=192, k=3, dims=(4, 4, 4)),
+    dict(B=1, cin=15, cout=48, k=5, dims=(8, 16, 16), acc=True),   # EmbedATb conv1 -> opened ATb
+    dict(B=1, cin=96, cout=96, k=5, dims=(8, 8, 8)),
 ], ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()).replace(" ", ""))
 def test_conv_dgrad_vs_autograd(ftb, case):
     assert dgrad_case(**case) <= BAR_CONV
@@ -221,6 +228,58 @@ def test_unet3d_full_arch_grads_32_batch2(ftb, dev):
     cfg, loss_o, vhat_o, grads_o, loss, vhat, got, mg = _unet_grads(ftb, dev, "full", shape=(2, 18, 32, 32, 32))
     assert rel(vhat, vhat_o) <= 2e-2
     _check_grads(grads_o, got, "full arch 32^3 B=2")
+
+
+# ------------------------------------------------------------------ conditional model (Unet3DCond v3) gradients
+def _cond_grads(ftb, dev, name):
+    import importlib.util
+    from oracle import synth, task
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    gd = os.path.join(os.path.dirname(__file__), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(gd, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    over, pseed, shape = mg.TRAIN_COND_CFGS[name]
+    cfg = synth.make_cfg(**over)
+    cfg["dropout"] = 0.0
+    params = synth.synth_unet3d_cond_params(cfg, pseed)
+    net = ftb.Unet3DCond(**cfg).to(dev)
+    net.load_state_dict(params)
+    xt = synth.synth_input(shape, 11, "xt").to(dev)
+    vt = synth.synth_input(shape, 12, "vt").to(dev)
+    atb = synth.synth_atb(shape, 14).to(dev)
+    t = synth.synth_times(shape[0], 13).to(dev)
+    loss_o, vhat_o, grads_o = task.cond_training_grads({k: v.to(dev) for k, v in params.items()}, cfg, xt, atb, t, vt)
+    net.train()
+    vhat = net(xt, atb, t)     # the reference call site: self.net(XT, ATb, T), model_train_sh_inference_cond.py:431
+    lo = torch.nn.functional.mse_loss(vt, vhat) / torch.nn.functional.mse_loss(vt, torch.zeros_like(vt))
+    lo.backward()
+    got = {k: p.grad.detach() for k, p in net.named_parameters()}
+    # the same module still samples (inference path, cached ATb branch) after a training step
+    net.eval()
+    with torch.no_grad():
+        y = net(xt, atb, t)
+    assert rel(y, vhat_o) <= 2e-2
+    return loss_o, vhat_o, grads_o, lo.detach(), vhat.detach(), got, mg
+
+
+@pytest.mark.parametrize("name", ["small", "full"])
+def test_unet3d_cond_grads_vs_oracle_and_golden(ftb, dev, name):
+    """Backward of the conditional model (EmbedATb 5^3 convs + trilinear of the opened ATb, MixATb FiLM of the concat,
+    init_conv_ATb collecting from all ten embeddings) vs the oracle's autograd and the REFERENCE's (golden)."""
+    loss_o, vhat_o, grads_o, loss, vhat, got, mg = _cond_grads(ftb, dev, name)
+    assert rel(vhat, vhat_o) <= 2e-2
+    assert abs(loss.item() - loss_o.item()) <= 2e-2 * abs(loss_o.item())
+    _check_grads(grads_o, got, f"cond {name} arch 16^3")
+    g = _golden(f"train_cond_{name}.npz")
+    assert rel(vhat, g["vhat"]) <= 2e-2
+    for k in mg.TRAIN_COND_FULL_GRADS:
+        assert rel(got[k], g[f"full/{k}"]) <= BAR_GRAD_TENSOR, k
+    for k, gr in got.items():
+        want = float(g[f"norm/{k}"])
+        if want > 1e-6:
+            assert abs(float(gr.double().norm()) - want) <= 5e-2 * want, k
 
 
 def test_train_forward_matches_inference_forward(ftb, dev):

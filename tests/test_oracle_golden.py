@@ -234,6 +234,35 @@ def test_training_grads_vs_reference_golden(golden_dir, name):
         assert rel_l2(grads[k], g[f"full/{k}"]) <= 1e-3, k
 
 
+@pytest.mark.parametrize("name", ["small", "full"])
+def test_cond_training_grads_vs_reference_golden(golden_dir, name):
+    """Same for the conditional model: autograd through the oracle Unet3DCond v3 == the reference module's
+    (tests/golden/make_golden.py gen_train_cond)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(golden_dir, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    over, pseed, shape = mg.TRAIN_COND_CFGS[name]
+    g = _load(golden_dir, f"train_cond_{name}.npz")
+    cfg = synth.make_cfg(**over)
+    params = synth.synth_unet3d_cond_params(cfg, pseed)
+    xt, vt = synth.synth_input(shape, 11, "xt"), synth.synth_input(shape, 12, "vt")
+    atb = synth.synth_atb(shape, 14)
+    t = torch.from_numpy(g["t"])
+    loss, vhat, grads = task.cond_training_grads(params, cfg, xt, atb, t, vt)
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    assert rel_l2(vhat, g["vhat"]) <= 1e-5
+    for k, gr in grads.items():
+        want = float(g[f"norm/{k}"])
+        got = gr.double().norm().item()
+        assert abs(got - want) <= 2e-3 * want + 1e-9, (k, got, want)
+        flat = gr.reshape(-1)
+        idx = torch.linspace(0, flat.numel() - 1, min(16, flat.numel())).long()
+        assert np.allclose(flat[idx].numpy(), g[f"sample/{k}"], rtol=5e-3, atol=2e-3 * want / max(1.0, flat.numel() ** 0.5))
+    for k in mg.TRAIN_COND_FULL_GRADS:
+        assert rel_l2(grads[k], g[f"full/{k}"]) <= 1e-3, k
+
+
 def test_adam_reference_matches_torch():
     torch.manual_seed(0)
     p0 = torch.randn(1000)
