@@ -10,14 +10,19 @@ from .interpolation import (BaseInterpolant, EncDecInterpolant, LinearInterpolan
                             SBDMInterpolant, StochasticInterpolator, TrigInterpolant)
 from .solvers import (ODEFlowSolver, ODEOneSidedDenoisingSolver, SDEOneSidedDenoisingSolver,
                       integrate_fixed, odeSol_RK4)
-from .task import (EMAShadow, Geo3DStochInterp, decode, ema_update_, embed, flow_loss,
+from .boreholes import (conditioning_frontend, draw_boreholes, jittered_grid_points, make_boreholes_mask,
+                        make_combined_mask, make_surface_mask)
+from .ensemble import EnsembleVotes
+from .task import (EMAShadow, Geo3DStochInterp, Geo3DStochInterpCond, decode, ema_update_, embed, flow_loss,
                    simplex_embedding)
-from .training import BucketAllReduce, FlowTrainer, flatten_parameters
+from .training import BucketAllReduce, CondFlowTrainer, FlowTrainer, flatten_parameters
 from .unet3d import Unet3D, Unet3DCond
 
 __all__ = [
     "Unet3D", "Unet3DCond", "StochasticInterpolator", "BaseInterpolant", "LinearInterpolant", "TrigInterpolant",
     "EncDecInterpolant", "SBDMInterpolant", "MirrorInterpolant", "ODEFlowSolver",
     "ODEOneSidedDenoisingSolver", "SDEOneSidedDenoisingSolver", "odeSol_RK4", "integrate_fixed",
-    "Geo3DStochInterp", "EMAShadow", "FlowTrainer", "BucketAllReduce", "flatten_parameters", "embed", "decode", "flow_loss", "ema_update_", "simplex_embedding",
+    "Geo3DStochInterp", "Geo3DStochInterpCond", "EMAShadow", "FlowTrainer", "CondFlowTrainer", "EnsembleVotes",
+    "make_boreholes_mask", "make_surface_mask", "make_combined_mask", "conditioning_frontend", "draw_boreholes",
+    "jittered_grid_points", "BucketAllReduce", "flatten_parameters", "embed", "decode", "flow_loss", "ema_update_", "simplex_embedding",
 ]

@@ -342,6 +342,26 @@ __global__ void drift_kernel(float* __restrict__ out, const float* __restrict__ 
 // ------------------------------------------------------------------ decode (model_train_inference.py:373-404)
 // One thread per voxel; fp32 op ORDER fixed (no FMA contraction): sequential sum of squares,
 // sqrt, clamp 1e-12, divide, ncat sequential dot products, first-max argmax -> int64.
+__device__ __forceinline__ int decode_voxel(const float* __restrict__ xp, size_t n, const float* s_en, int E, int ncat) {
+  float xv[32];
+  float ss = 0.f;
+  for (int e = 0; e < E; ++e) {
+    xv[e] = __ldg(xp + (size_t)e * n);
+    ss = __fadd_rn(ss, __fmul_rn(xv[e], xv[e]));
+  }
+  const float nrm = fmaxf(__fsqrt_rn(ss), 1e-12f);
+  for (int e = 0; e < E; ++e) xv[e] = __fdiv_rn(xv[e], nrm);
+  float best = -INFINITY;
+  int arg = 0;
+  for (int c = 0; c < ncat; ++c) {
+    float acc = 0.f;
+    for (int e = 0; e < E; ++e) acc = __fadd_rn(acc, __fmul_rn(xv[e], s_en[c * E + e]));
+    // strictly-greater keeps the FIRST maximum; a NaN logit wins like torch.argmax
+    if (c == 0 || acc > best || (acc != acc && best == best)) { best = acc; arg = c; }
+  }
+  return arg;
+}
+
 __global__ void decode_kernel(const float* __restrict__ x, const float* __restrict__ en,
                               long long* __restrict__ out, int B, int E, int ncat, size_t n) {
   extern __shared__ float s_en[];
@@ -352,24 +372,29 @@ __global__ void decode_kernel(const float* __restrict__ x, const float* __restri
        i += (size_t)gridDim.x * blockDim.x) {
     const int b = (int)(i / n);
     const size_t v = i % n;
-    const float* xp = x + (size_t)b * E * n + v;
-    float xv[32];
-    float ss = 0.f;
-    for (int e = 0; e < E; ++e) {
-      xv[e] = __ldg(xp + (size_t)e * n);
-      ss = __fadd_rn(ss, __fmul_rn(xv[e], xv[e]));
+    out[i] = decode_voxel(x + (size_t)b * E * n + v, n, s_en, E, ncat);
+  }
+}
+
+// Ensemble vote (model_inference_experiments.py:442-447): decode S samples of one voxel and add them to the per-voxel
+// category histogram counts[ncat][n] (int32, +=, so several launches / ranks accumulate).  Thread = voxel; the
+// histogram of the voxel lives in shared memory ([ncat][128] ints) while the samples stream by, so the decoded
+// volumes never have to reach HBM (`decoded` is optional).
+__global__ void __launch_bounds__(128)
+decode_vote_kernel(const float* __restrict__ x, const float* __restrict__ en, int S, int E, int ncat, size_t n,
+                   long long* __restrict__ decoded, int* __restrict__ counts) {
+  extern __shared__ float s_en[];
+  int* s_cnt = reinterpret_cast<int*>(s_en + ncat * E);   // [ncat][128]
+  for (int i = threadIdx.x; i < ncat * E; i += blockDim.x) s_en[i] = en[i];
+  __syncthreads();
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (size_t)gridDim.x * blockDim.x) {
+    for (int c = 0; c < ncat; ++c) s_cnt[c * 128 + threadIdx.x] = 0;
+    for (int s = 0; s < S; ++s) {
+      const int arg = decode_voxel(x + (size_t)s * E * n + v, n, s_en, E, ncat);
+      if (decoded) decoded[(size_t)s * n + v] = arg;
+      s_cnt[arg * 128 + threadIdx.x] += 1;
     }
-    const float nrm = fmaxf(__fsqrt_rn(ss), 1e-12f);
-    for (int e = 0; e < E; ++e) xv[e] = __fdiv_rn(xv[e], nrm);
-    float best = -INFINITY;
-    int arg = 0;
-    for (int c = 0; c < ncat; ++c) {
-      float acc = 0.f;
-      for (int e = 0; e < E; ++e) acc = __fadd_rn(acc, __fmul_rn(xv[e], s_en[c * E + e]));
-      // strictly-greater keeps the FIRST maximum; a NaN logit wins like torch.argmax
-      if (c == 0 || acc > best || (acc != acc && best == best)) { best = acc; arg = c; }
-    }
-    out[i] = arg;
+    for (int c = 0; c < ncat; ++c) counts[(size_t)c * n + v] += s_cnt[c * 128 + threadIdx.x];
   }
 }
 
@@ -517,6 +542,15 @@ int decode_argmax(const float* x, const float* en, long long* out, int B, int E,
   FTB_CHECK(E >= 1 && E <= 32, "decode: embedding dim must be in [1,32]");
   FTB_CHECK(ncat >= 1 && ncat <= 256, "decode: category count");
   decode_kernel<<<grid_for((size_t)B * n, 128), 128, (size_t)ncat * E * sizeof(float), st>>>(x, en, out, B, E, ncat, (size_t)n);
+  FTB_LAUNCH_OK();
+  return 0;
+}
+int decode_vote(const float* x, const float* en, int S, int E, int ncat, long long n, long long* decoded, int* counts,
+                cudaStream_t st) {
+  FTB_CHECK(E >= 1 && E <= 32, "decode: embedding dim must be in [1,32]");
+  FTB_CHECK(ncat >= 1 && ncat <= 64, "decode_vote: at most 64 categories");
+  const size_t smem = (size_t)ncat * E * sizeof(float) + (size_t)ncat * 128 * sizeof(int);
+  decode_vote_kernel<<<grid_for((size_t)n, 128), 128, smem, st>>>(x, en, S, E, ncat, (size_t)n, decoded, counts);
   FTB_LAUNCH_OK();
   return 0;
 }

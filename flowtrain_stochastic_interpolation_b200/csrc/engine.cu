@@ -1070,6 +1070,40 @@ int ftb_decode(const float* x, const float* en, int64_t* out, int B, int E, int 
   FTB_CHECK(x && en && out, "null argument");
   return decode_argmax(x, en, reinterpret_cast<long long*>(out), B, E, ncat, n, (cudaStream_t)stream);
 }
+int ftb_cond_frontend(const int64_t* cats, const int32_t* bores, const int32_t* n_bores, int max_bores, const float* w,
+                      int B, int E, int ncat, int shift, int X, int Y, int Z, int surface, uint8_t* mask, float* x1,
+                      float* atb, void* stream) {
+  FTB_CHECK(cats && (mask || x1 || atb), "null argument");
+  FTB_CHECK(w || (!x1 && !atb), "embedding matrix missing");
+  FTB_CHECK(max_bores == 0 || (bores && n_bores), "borehole table missing");
+  FTB_CHECK(B >= 1 && X >= 1 && Y >= 1 && Z >= 1, "non-positive dims");
+  return cond_frontend(reinterpret_cast<const long long*>(cats), bores, n_bores, max_bores, w, B, E, ncat, shift, X, Y, Z,
+                       surface, mask, x1, atb, (cudaStream_t)stream);
+}
+int ftb_cond_loss_accumulate(const float* vt, const float* vhat, const float* xt, const float* x1_clean,
+                             const float* x1_noisy, const uint8_t* mask, const float* t, int B, int E, int64_t n,
+                             double* acc6, void* stream) {
+  FTB_CHECK(vt && vhat && xt && x1_clean && x1_noisy && mask && t && acc6, "null argument");
+  return cond_loss_partial(vt, vhat, xt, x1_clean, x1_noisy, mask, t, B, E, n, acc6, (cudaStream_t)stream);
+}
+int ftb_cond_loss_grad(const float* vt, const float* vhat, const float* xt, const float* x1_clean, const uint8_t* mask,
+                       const float* t, int B, int E, int64_t n, const double* acc6, float lambda_reconstruct, float scale,
+                       float* dout, void* stream) {
+  FTB_CHECK(vt && vhat && xt && x1_clean && mask && t && acc6 && dout, "null argument");
+  return cond_loss_grad(vt, vhat, xt, x1_clean, mask, t, B, E, n, acc6, lambda_reconstruct, scale, dout,
+                        (cudaStream_t)stream);
+}
+int ftb_decode_vote(const float* x, const float* en, int S, int E, int ncat, int64_t n, int64_t* decoded,
+                    int32_t* counts, void* stream) {
+  FTB_CHECK(x && en && counts, "null argument");
+  return decode_vote(x, en, S, E, ncat, n, reinterpret_cast<long long*>(decoded), counts, (cudaStream_t)stream);
+}
+int ftb_vote_finalize(const int32_t* counts, int S, int ncat, int64_t n, int shift, float* probs, float* entropy,
+                      int64_t* most_probable, float* entropy_masked, void* stream) {
+  FTB_CHECK(counts && (probs || entropy || most_probable || entropy_masked), "null argument");
+  return vote_finalize(counts, S, ncat, n, shift, probs, entropy, reinterpret_cast<long long*>(most_probable),
+                       entropy_masked, (cudaStream_t)stream);
+}
 int ftb_embed(const int64_t* cats, const float* w, float* out, int B, int E, int ncat, int64_t n,
               int shift, void* stream) {
   FTB_CHECK(cats && w && out, "null argument");

@@ -224,6 +224,22 @@ int denoise_drift(float* out, const float* x, const float* eta, const float* noi
                   float ad, float bd, float eps, int use_sde, long long n, cudaStream_t st);
 int decode_argmax(const float* x, const float* en, long long* out, int B, int E, int ncat,
                   long long n, cudaStream_t st);
+// ---- conditional project / ensemble kernels (cond_ops.cu, elementwise.cu)
+// surface + borehole mask, X1 = W[cat + shift], ATb = X1 * mask in one pass; bores [B][max_b][2] int32 (x, y),
+// nb [B] counts; mask (u8 [B][X*Y*Z]), x1, atb may each be null
+int cond_frontend(const long long* cats, const int* bores, const int* nb, int max_b, const float* w, int B, int E,
+                  int ncat, int shift, int X, int Y, int Z, int surface, unsigned char* mask, float* x1, float* atb,
+                  cudaStream_t st);
+int cond_loss_partial(const float* vt, const float* vh, const float* xt, const float* x1c, const float* x1n,
+                      const unsigned char* mask, const float* T, int B, int E, long long n, double* acc6, cudaStream_t st);
+int cond_loss_grad(const float* vt, const float* vh, const float* xt, const float* x1c, const unsigned char* mask,
+                   const float* T, int B, int E, long long n, const double* acc6, float lambda, float scale, float* dout,
+                   cudaStream_t st);
+// decode S samples [S][E][n] and add them to counts [ncat][n] (int32); decoded [S][n] int64 optional
+int decode_vote(const float* x, const float* en, int S, int E, int ncat, long long n, long long* decoded, int* counts,
+                cudaStream_t st);
+int vote_finalize(const int* counts, int S, int ncat, long long n, int shift, float* probs, float* entropy,
+                  long long* most, float* entropy_masked, cudaStream_t st);
 int embed_lookup(const long long* cats, const float* w, float* out, int B, int E, int ncat,
                  long long n, int shift, cudaStream_t st);
 int ema_update(float* shadow, const float* param, long long n, double decay, cudaStream_t st);

@@ -14,7 +14,7 @@ from torch import nn
 
 from . import _lib
 from .interpolation import LinearInterpolant, StochasticInterpolator
-from .unet3d import Unet3D
+from .unet3d import Unet3D, Unet3DCond
 
 
 def simplex_embedding(n_cats: int, n_dims: int) -> torch.Tensor:
@@ -164,3 +164,45 @@ class Geo3DStochInterp(nn.Module):
             T = torch.empty(X1.size(0), device=X1.device).uniform_(self.time_range[0], self.time_range[1])
         XT, VT = self.interpolator.flow_objective(T, X0, X1)
         return flow_loss(VT, self.net(XT, T))
+
+
+class Geo3DStochInterpCond(nn.Module):
+    """Hot-path surface of the conditional project's LightningModule
+    (project/geodata-3d-conditional/model_train_sh_inference_cond.py:247-495): ``net`` is the B200 ``Unet3DCond``,
+    the simplex ``embedding`` is frozen (:302), ``forward(x, ATb, t)``; ``conditioning(batch)`` is the fused
+    embed + combined mask + ``ATb = X1 * mask`` front-end of training_step (:413-420)."""
+
+    def __init__(self, data_shape: Tuple[int, int, int] = (32, 32, 32),
+                 time_range: List[float] = [0.0001, 0.9999], num_categories: int = 15, embedding_dim: int = 20,
+                 lambda_reconstruct: float = 1.0, learning_rate: float = 2e-3, lr_decay: float = 0.999,
+                 **model_params: Any):
+        super().__init__()
+        self.data_shape = data_shape
+        self.time_range = time_range
+        self.num_categories = num_categories
+        self.embedding_dim = embedding_dim
+        self.lambda_reconstruct = lambda_reconstruct
+        self.learning_rate, self.lr_decay = learning_rate, lr_decay
+        self.embedding = nn.Embedding(num_categories, embedding_dim)
+        with torch.no_grad():
+            self.embedding.weight.copy_(simplex_embedding(num_categories, embedding_dim))
+        self.embedding.weight.requires_grad = False
+        model_params["data_channels"] = embedding_dim
+        self.net = Unet3DCond(**model_params)
+        self.ema_shadow = {}
+        self.interpolant = LinearInterpolant(one_sided=True)
+        self.interpolator = StochasticInterpolator(self.interpolant)
+
+    def forward(self, x, ATb, t):
+        return self.net(x, ATb, t)
+
+    def embed(self, x):
+        return embed(self.embedding.weight, x)
+
+    def decode(self, x, return_logits=False):
+        return decode(self.embedding.weight, x, return_logits)
+
+    def conditioning(self, batch, bores=None, n_bores=None, generator=None):
+        """(X1, ATb, mask) of a category batch [B,1,X,Y,Z] in one kernel (see boreholes.conditioning_frontend)."""
+        from .boreholes import conditioning_frontend
+        return conditioning_frontend(batch, self.embedding.weight, bores, n_bores, generator)

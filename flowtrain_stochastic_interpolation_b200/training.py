@@ -275,30 +275,35 @@ class FlowTrainer:
             dout = torch.empty_like(vhat)
             _lib.check(lib.ftb_mse_ratio_grad(_lib.ptr(VT), _lib.ptr(vhat), VT.numel(), _lib.ptr(self.acc), 1.0,
                                               _lib.ptr(dout), st))
-            self.gflat.zero_()
-            reducer = BucketAllReduce(self.gflat, self.group) if self.world > 1 else None
-            backward_into(net, dout, self.gflat, reducer)
-            if reducer is not None:
-                reducer.finish()
-            for off, n in self.frozen:
-                self.gflat[off:off + n].zero_()
-            self.step_count += 1
-            self.sumsq.zero_()
-            _lib.check(lib.ftb_grad_sumsq(_lib.ptr(self.gflat), self.gflat.numel(), _lib.ptr(self.sumsq), st))
-            _lib.check(lib.ftb_adam_step(_lib.ptr(self.flat), _lib.ptr(self.gflat), _lib.ptr(self.m), _lib.ptr(self.v),
-                                         self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
-                                         self.weight_decay, 1 if self.decoupled else 0, self.step_count,
-                                         _lib.ptr(self.sumsq), 1.0 / self.world, self.max_grad_norm, st))
-            _lib.check(lib.ftb_unet3d_mark_dirty(net._handle))
-            net._flat_versions = None
-            if self.ema_decay is not None and self.step_count >= self.ema_start_step:   # callbacks.py:243-266
-                if self.ema_flat is None:
-                    self.ema_flat = self.flat.clone()
-                else:
-                    _lib.check(lib.ftb_ema_update(_lib.ptr(self.ema_flat), _lib.ptr(self.flat), self.flat.numel(),
-                                                  float(self.ema_decay), st))
-            self.last_grad_norm = self.sumsq   # squared norm of the summed gradient (device)
+            self._optimizer_tail(dout)
             return (self.acc[0] / self.acc[1]).float()
+
+    def _optimizer_tail(self, dout):
+        """backward -> (bucketed all-reduce) -> clip + Adam(W) -> EMA, shared by both training steps."""
+        net, lib, st = self.net, _lib.lib, _lib.stream_ptr()
+        self.gflat.zero_()
+        reducer = BucketAllReduce(self.gflat, self.group) if self.world > 1 else None
+        backward_into(net, dout, self.gflat, reducer)
+        if reducer is not None:
+            reducer.finish()
+        for off, n in self.frozen:
+            self.gflat[off:off + n].zero_()
+        self.step_count += 1
+        self.sumsq.zero_()
+        _lib.check(lib.ftb_grad_sumsq(_lib.ptr(self.gflat), self.gflat.numel(), _lib.ptr(self.sumsq), st))
+        _lib.check(lib.ftb_adam_step(_lib.ptr(self.flat), _lib.ptr(self.gflat), _lib.ptr(self.m), _lib.ptr(self.v),
+                                     self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
+                                     self.weight_decay, 1 if self.decoupled else 0, self.step_count,
+                                     _lib.ptr(self.sumsq), 1.0 / self.world, self.max_grad_norm, st))
+        _lib.check(lib.ftb_unet3d_mark_dirty(net._handle))
+        net._flat_versions = None
+        if self.ema_decay is not None and self.step_count >= self.ema_start_step:   # callbacks.py:243-266
+            if self.ema_flat is None:
+                self.ema_flat = self.flat.clone()
+            else:
+                _lib.check(lib.ftb_ema_update(_lib.ptr(self.ema_flat), _lib.ptr(self.flat), self.flat.numel(),
+                                              float(self.ema_decay), st))
+        self.last_grad_norm = self.sumsq   # squared norm of the summed gradient (device)
 
     def epoch_end(self):
         """ExponentialLR(gamma=lr_decay) per epoch (:465-473)."""
@@ -311,3 +316,61 @@ class FlowTrainer:
             return {}
         return {n: self.ema_flat[off:off + p.numel()].view(p.shape).clone()
                 for (n, p), off in zip(self.net.named_parameters(), self.net._flat_offsets) if p.requires_grad}
+
+
+class CondFlowTrainer(FlowTrainer):
+    """One optimiser step of the conditional project (training_step
+    project/geodata-3d-conditional/model_train_sh_inference_cond.py:401-467; AdamW lr 1e-3 :487-495, Lightning
+    ``gradient_clip_val`` 0.3, EMA 0.9995 every batch) in kernels: fused conditioning front-end (embed + surface /
+    borehole mask + ATb), interpolant, ``Unet3DCond`` forward/backward, the flow + T-weighted reconstruction loss
+    and its gradient without a host sync, clip + AdamW, EMA.  ``module`` is the B200 ``Geo3DStochInterpCond``."""
+
+    def __init__(self, module, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, decoupled=True,
+                 max_grad_norm: Optional[float] = 0.3, ema_decay: Optional[float] = 0.9995, ema_start_step=0,
+                 lr_decay: Optional[float] = None, process_group=None, distributed: Optional[bool] = None,
+                 generator: Optional[torch.Generator] = None):
+        super().__init__(module, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, decoupled=decoupled,
+                         max_grad_norm=max_grad_norm, ema_decay=ema_decay, ema_start_step=ema_start_step,
+                         lr_decay=lr_decay, process_group=process_group, distributed=distributed)
+        self.acc6 = torch.zeros(6, dtype=torch.float64, device=self.flat.device)
+        self.generator = generator   # CPU generator of the borehole draw
+        self.last_terms = None
+
+    def step(self, batch, noise1=None, X0=None, T=None, bores=None, n_bores=None):
+        """batch: [B,1,X,Y,Z] integer categories.  Returns the (per-rank) loss as a 0-d device tensor; the random
+        draws (noise1 = randn for X1, X0, T, borehole columns) can be passed in for parity runs."""
+        mod, net, lib = self.module, self.net, _lib.lib
+        dev = self.flat.device
+        with torch.cuda.device(dev), torch.no_grad():
+            st = _lib.stream_ptr()
+            X1c, ATb, mask = mod.conditioning(batch, bores, n_bores, self.generator)       # :413-420
+            if noise1 is None:
+                noise1 = torch.randn_like(X1c)
+            X1 = torch.empty_like(X1c)
+            _lib.check(lib.ftb_ode_axpy(_lib.ptr(X1), _lib.ptr(X1c), _lib.ptr(noise1), 1e-4, X1.numel(), None, 1, st))  # :421
+            if X0 is None:
+                X0 = torch.randn_like(X1)                                                  # :423
+            if T is None:
+                T = torch.empty(X1.size(0), device=dev).uniform_(mod.time_range[0], mod.time_range[1])   # :426-428
+            XT, VT = mod.interpolator.flow_objective(T, X0, X1)                            # :431
+            XT, VT = XT.contiguous(), VT.contiguous()
+            Tin = T.to(device=dev, dtype=torch.float32).contiguous()
+            vhat = forward_train(net, XT, Tin, ATb)                                        # :432
+            B, E = X1.shape[0], X1.shape[1]
+            n = X1[0, 0].numel()
+            m8 = mask.view(torch.uint8)
+            self.acc6.zero_()
+            _lib.check(lib.ftb_cond_loss_accumulate(_lib.ptr(VT), _lib.ptr(vhat), _lib.ptr(XT), _lib.ptr(X1c),
+                                                    _lib.ptr(X1), _lib.ptr(m8), _lib.ptr(Tin), B, E, n,
+                                                    _lib.ptr(self.acc6), st))              # :434-451
+            dout = torch.empty_like(vhat)
+            _lib.check(lib.ftb_cond_loss_grad(_lib.ptr(VT), _lib.ptr(vhat), _lib.ptr(XT), _lib.ptr(X1c), _lib.ptr(m8),
+                                              _lib.ptr(Tin), B, E, n, _lib.ptr(self.acc6),
+                                              float(mod.lambda_reconstruct), 1.0, _lib.ptr(dout), st))
+            self._optimizer_tail(dout)
+            a = self.acc6
+            N = float(VT.numel())
+            flow = (a[0] / N) / (a[1] / N + 1e-6)
+            rec = (a[5] / B) * (a[2] / a[3]) / (a[4] / N + 1e-6)
+            self.last_terms = (flow.float(), rec.float())          # "flow_loss", "reconstruct_loss" of log_dict :454-465
+            return (flow + mod.lambda_reconstruct * rec).float()

@@ -124,6 +124,39 @@ int ftb_decode(const float* x, const float* en, int64_t* out, int B, int E, int 
 int ftb_embed(const int64_t* cats, const float* w, float* out, int B, int E, int ncat, int64_t n,
               int shift, void* stream);
 
+/* ---- conditioning front-end: replaces make_combined_mask + embed + ATb = X1 * mask
+ *      (project/geodata-3d-conditional/boreholes.py:45-126; model_train_sh_inference_cond.py:413-420).
+ * cats [B,X,Y,Z] int64 (-1 = air); bores [B,max_bores,2] int32 borehole (x, y) columns, n_bores [B] how many of
+ * them are valid (the random draw stays with the caller); w [ncat,E].  Outputs (each may be NULL):
+ * mask [B,X,Y,Z] uint8 = (surface != 0: top slice | air | voxel below air) | borehole column;  w may be NULL when
+ * only the mask is wanted;  x1 [B,E,X,Y,Z] = w[cat + shift];
+ * atb [B,E,X,Y,Z] = x1 * mask. */
+int ftb_cond_frontend(const int64_t* cats, const int32_t* bores, const int32_t* n_bores, int max_bores, const float* w,
+                      int B, int E, int ncat, int shift, int X, int Y, int Z, int surface, uint8_t* mask, float* x1,
+                      float* atb, void* stream);
+/* ---- loss of the conditional training step (model_train_sh_inference_cond.py:432-452):
+ *      loss = mse(VT, VThat) / (mse(VT, 0) + 1e-6) + lambda * mean(T) * mse(b, b_hat) / (mse(X1, 0) + 1e-6),
+ *      b = X1_clean[mask], b_hat = (XT + (1 - T) VThat)[mask].  accumulate adds the six partial sums
+ *      (sum (v-vh)^2, sum v^2, sum_mask (b-b_hat)^2, #masked elements, sum X1_noisy^2, sum T) to acc6 (device doubles);
+ *      grad writes dout = scale * d loss / d VThat from them (no host sync in between). */
+int ftb_cond_loss_accumulate(const float* vt, const float* vhat, const float* xt, const float* x1_clean,
+                             const float* x1_noisy, const uint8_t* mask, const float* t, int B, int E, int64_t n,
+                             double* acc6, void* stream);
+int ftb_cond_loss_grad(const float* vt, const float* vhat, const float* xt, const float* x1_clean, const uint8_t* mask,
+                       const float* t, int B, int E, int64_t n, const double* acc6, float lambda_reconstruct, float scale,
+                       float* dout, void* stream);
+/* ---- ensemble statistics: replaces decode -> one_hot -> mean / entropy / argmax
+ *      (project/geodata-3d-conditional/model_inference_experiments.py:442-459; inference_demo.ipynb cell 21).
+ * decode_vote: x [S,E,n] fp32 samples, en [ncat,E] normalised embedding -> counts [ncat,n] int32 += votes (bit-exact
+ * decode order as ftb_decode); decoded [S,n] int64 optional.  Counts of several launches / ranks add up (one
+ * all-reduce(sum) of counts across GPUs).  vote_finalize: S = total samples; probs [ncat,n] = counts / S,
+ * entropy [n] = -sum p log(p + 1e-8), most_probable [n] = first argmax + shift (-1: air),
+ * entropy_masked [n] = entropy, -1 where most_probable == -1.  Each output may be NULL. */
+int ftb_decode_vote(const float* x, const float* en, int S, int E, int ncat, int64_t n, int64_t* decoded,
+                    int32_t* counts, void* stream);
+int ftb_vote_finalize(const int32_t* counts, int S, int ncat, int64_t n, int shift, float* probs, float* entropy,
+                      int64_t* most_probable, float* entropy_masked, void* stream);
+
 /* ---- training-step pieces (model_train_inference.py:443; callbacks.py:263-266) */
 int ftb_ema_update(float* shadow, const float* param, int64_t n, double decay, void* stream);
 /* acc2[0] += sum (v-vhat)^2, acc2[1] += sum v^2 (device doubles; loss = acc2[0]/acc2[1]) */

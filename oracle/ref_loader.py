@@ -43,6 +43,10 @@ def unet3d_cond_module():
     return _load("ref_unet_attn_3d_cond_v3", "src/flowtrain/models/unet_attn_3d_cond_v3.py")
 
 
+def boreholes_module():
+    return _load("ref_boreholes", "project/geodata-3d-conditional/boreholes.py")
+
+
 def interpolation_module():
     return _load("ref_interpolation", "src/flowtrain/interpolation/interpolation.py")
 

@@ -145,3 +145,90 @@ def vote_probabilities(decoded: torch.Tensor, n_cat: int) -> torch.Tensor:
     """inference_demo.ipynb cell 21 — one-hot vote over the ensemble axis (dim 0)."""
     oh = F.one_hot(decoded.long(), n_cat).float()
     return oh.mean(dim=0).movedim(-1, 0)
+
+
+# ---------------------------------------------------------------------------------- conditioning masks
+def make_boreholes_mask(X: torch.Tensor, bores: torch.Tensor, n_bores: torch.Tensor) -> torch.Tensor:
+    """make_boreholes_mask — project/geodata-3d-conditional/boreholes.py:45-75 with the random borehole columns passed
+    in (bores [B, max, 2] (x, y), n_bores [B]) so that parity is definable: the whole z column at each (x, y)."""
+    B, C, sx, sy, sz = X.shape
+    mask = torch.zeros((B, 1, sx, sy, sz), dtype=torch.bool)
+    for b in range(B):
+        pts = bores[b, : int(n_bores[b])].long()
+        mask[b, 0, pts[:, 0], pts[:, 1], :] = True
+    return mask
+
+
+def make_surface_mask(X: torch.Tensor) -> torch.Tensor:
+    """make_surface_mask — boreholes.py:77-111: top z slice; every air voxel (value -1) and the voxel at z-1 below it
+    (clamped at 0)."""
+    B, C, sx, sy, sz = X.shape
+    mask = torch.zeros((B, 1, sx, sy, sz), dtype=torch.bool)
+    mask[:, 0, :, :, sz - 1] = True
+    for b in range(B):
+        positions = (X[b, 0] == -1).nonzero(as_tuple=True)
+        if positions[0].numel() > 0:
+            xc, yc, zc = positions
+            mask[b, 0, xc, yc, zc] = True
+            mask[b, 0, xc, yc, torch.clamp(zc - 1, min=0)] = True
+    return mask
+
+
+def make_combined_mask(X: torch.Tensor, bores: torch.Tensor, n_bores: torch.Tensor) -> torch.Tensor:
+    """make_combined_mask — boreholes.py:114-129."""
+    return make_boreholes_mask(X, bores, n_bores) | make_surface_mask(X)
+
+
+def jittered_grid_points(X: int, Y: int, n_bores: int, rand: torch.Tensor) -> torch.Tensor:
+    """_jittered_grid_points — boreholes.py:9-42, with the 2 * n_x * n_y uniform draws passed in as ``rand`` [n_x*n_y, 2]
+    (the reference calls torch.rand(1) twice per cell, x first, cells in (i, j) order)."""
+    import math
+    n_x = int(math.floor(math.sqrt(n_bores)))
+    n_y = int(math.ceil(n_bores / n_x))
+    cwx, cwy = X / n_x, Y / n_y
+    points = []
+    k = 0
+    for i in range(n_x):
+        for j in range(n_y):
+            cx, cy = (i + 0.5) * cwx, (j + 0.5) * cwy
+            rx = rand[k, 0:1] * cwx - cwx / 2
+            ry = rand[k, 1:2] * cwy - cwy / 2
+            k += 1
+            px = torch.clamp(cx + rx, min=0, max=X - 1)
+            py = torch.clamp(cy + ry, min=0, max=Y - 1)
+            points.append((px.item(), py.item()))
+    points = points[:n_bores]
+    return torch.tensor(points, dtype=torch.long)
+
+
+def replay_reference_borehole_draws(seed, B, X, Y):
+    """The reference's call sequence on the global CPU generator (boreholes.py:66-68, :27-28): per sample one
+    randint(8, 32), then rand(1) twice per grid cell."""
+    import math
+    torch.manual_seed(seed)
+    bores = torch.zeros(B, 64, 2, dtype=torch.long)
+    nb = torch.zeros(B, dtype=torch.long)
+    for b in range(B):
+        n = torch.randint(8, 32, (1,)).item()
+        n_x = int(math.floor(math.sqrt(n)))
+        n_y = int(math.ceil(n / n_x))
+        rand = torch.stack([torch.cat((torch.rand(1), torch.rand(1))) for _ in range(n_x * n_y)])
+        pts = jittered_grid_points(X, Y, n, rand)
+        bores[b, : pts.shape[0]] = pts
+        nb[b] = pts.shape[0]
+    return bores, nb
+
+
+# ---------------------------------------------------------------------------------- ensemble statistics
+def ensemble_statistics(sols_decoded: torch.Tensor, num_categories: int = 15):
+    """ensemble_analysis — project/geodata-3d-conditional/model_inference_experiments.py:442-459.  sols_decoded:
+    [S, 1, X, Y, Z] categories in -1 .. num_categories-2.  Returns (probability_vector [1,C,X,Y,Z], entropy [X,Y,Z],
+    most_probable [X,Y,Z] (air = -1), entropy_masked)."""
+    oh = F.one_hot(sols_decoded.squeeze(1) + 1, num_categories).permute(0, 4, 1, 2, 3).float()
+    pv = oh.mean(dim=0, keepdim=True)
+    eps = 1e-8
+    entropy = -torch.sum(pv * torch.log(pv + eps), dim=1).squeeze(0)
+    most = torch.argmax(pv, dim=1).squeeze(0) - 1
+    em = entropy.clone()
+    em[most == -1] = -1
+    return pv, entropy, most, em

@@ -128,6 +128,34 @@ def gen_train_cond():
         np.savez_compressed(os.path.join(OUT, f"train_cond_{name}.npz"), **out)
 
 
+def synth_categories(shape, seed):
+    """Layered synthetic category volume [B,1,X,Y,Z] in -1..13 with air (-1) on top of an uneven surface."""
+    g = torch.Generator().manual_seed(seed)
+    B, _, X, Y, Z = shape
+    cats = torch.randint(0, 14, shape, generator=g)
+    height = torch.randint(Z // 2, Z + 1, (B, 1, X, Y, 1), generator=g)      # first air index per column (Z = no air)
+    z = torch.arange(Z).view(1, 1, 1, 1, Z)
+    return torch.where(z >= height, torch.full_like(cats, -1), cats)
+
+
+def gen_cond_frontend():
+    """Masks of the REFERENCE boreholes.py (make_surface_mask, make_boreholes_mask, make_combined_mask) on synthetic
+    category volumes.  The borehole draw uses the global CPU generator: the fixture stores the seed, and the oracle
+    test replays the same torch.randint / torch.rand(1) call sequence to recover the coordinates."""
+    bm = ref_loader.boreholes_module()
+    out = {}
+    for name, shape, seed in (("a", (2, 1, 16, 16, 8), 40), ("b", (3, 1, 12, 20, 10), 41)):
+        cats = synth_categories(shape, seed)
+        out[f"{name}.cats"] = cats.to(torch.int8).numpy()
+        out[f"{name}.surface"] = np.packbits(bm.make_surface_mask(cats).numpy())
+        torch.manual_seed(seed + 100)
+        out[f"{name}.boreholes"] = np.packbits(bm.make_boreholes_mask(cats).numpy())
+        torch.manual_seed(seed + 100)
+        out[f"{name}.combined"] = np.packbits(bm.make_combined_mask(cats).numpy())
+        out[f"{name}.seed"] = np.int64(seed + 100)
+    np.savez_compressed(os.path.join(OUT, "cond_frontend.npz"), **out)
+
+
 def gen_unet_cond():
     """Unet3DCond v3 (the conditional project's model: 15-d embedding, mults 1,2,2,3,4)."""
     cfg = synth.make_cfg(data_channels=15)
@@ -240,6 +268,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "train":   # only the training fixtures
         gen_train()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "cond_frontend":
+        gen_cond_frontend()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "train_cond":
         gen_train_cond()
         sys.exit(0)
@@ -250,5 +281,6 @@ if __name__ == "__main__":
     gen_unet_cond()
     gen_train()
     gen_train_cond()
+    gen_cond_frontend()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -381,6 +381,63 @@ def test_flow_trainer_step_vs_oracle(ftb, dev):
     assert next(mod.net.parameters()).data_ptr() == tr.flat.data_ptr()
 
 
+def test_cond_flow_trainer_step_vs_oracle(ftb, dev):
+    """CondFlowTrainer.step == the conditional training_step (model_train_sh_inference_cond.py:401-467) + clip 0.3 +
+    AdamW on fixed draws: loss (flow + T-weighted masked reconstruction), gradient seen by the optimiser, update."""
+    from oracle import synth, task, unet3d_cond
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = synth.make_cfg(dim=32, dim_mults=(1, 2), data_channels=15, time_resolution=64, time_bandwidth=100.0,
+                         attn_heads=2, attn_dim_head=16, dropout=0.0)
+    params = synth.synth_unet3d_cond_params(cfg, 8)
+    kw = {k: v for k, v in cfg.items() if k != "data_channels"}
+    mod = ftb.Geo3DStochInterpCond(data_shape=(16, 16, 16), embedding_dim=15, lambda_reconstruct=1.0, **kw).to(dev)
+    mod.net.load_state_dict(params)
+    tr = ftb.CondFlowTrainer(mod, lr=1e-3, max_grad_norm=0.3, ema_decay=0.9, ema_start_step=0)
+    g = torch.Generator("cpu").manual_seed(5)
+    shape = (2, 15, 16, 16, 16)
+    batch = torch.randint(-1, 14, (2, 1, 16, 16, 16), generator=g)
+    bores, nb = ftb.draw_boreholes(2, 16, 16, torch.Generator().manual_seed(9))
+    n1 = synth.synth_input(shape, 21, "n1").to(dev)
+    x0 = synth.synth_input(shape, 22, "x0").to(dev)
+    T = synth.synth_times(2, 23, 1e-4, 0.9999).to(dev)
+    p_before = tr.flat.clone()
+    loss = tr.step(batch.to(dev), noise1=n1, X0=x0, T=T, bores=bores, n_bores=nb)
+    # oracle: the reference's op sequence on the same draws, autograd through the functional Unet3DCond
+    W = task.simplex_embedding(15, 15)
+    mask = task.make_combined_mask(batch, bores, nb).expand(-1, 15, -1, -1, -1).to(dev)
+    X1 = task.embed(W, batch).to(dev)
+    ATb = X1 * mask
+    X1 = X1 + 1e-4 * n1
+    Tb = T.view(-1, 1, 1, 1, 1)
+    XT, VT = (1 - Tb) * x0 + Tb * X1, X1 - x0
+    p = {k: v.to(dev).clone().requires_grad_(True) for k, v in params.items()}
+    vhat = unet3d_cond.unet3d_cond_forward(p, cfg, XT, ATb, T)
+    b_clean = (ATb)[mask]   # X1_clean[mask] == ATb[mask]
+    b_hat = XT[mask] + ((1 - Tb) * vhat)[mask]
+    F = torch.nn.functional
+    mse = F.mse_loss(VT, vhat) / (F.mse_loss(VT, torch.zeros_like(VT)) + 1e-6)
+    rec = ((Tb.squeeze() * F.mse_loss(b_clean, b_hat)) / (F.mse_loss(X1, torch.zeros_like(X1)) + 1e-6)).mean()
+    loss_o = mse + 1.0 * rec
+    grads = torch.autograd.grad(loss_o, [p[k] for k in params.keys()], allow_unused=True)
+    gflat_o = torch.cat([(gr if gr is not None else torch.zeros_like(p[k])).reshape(-1) for k, gr in zip(params.keys(), grads)])
+    print(f"cond loss {loss.item():.6f} (oracle {loss_o.item():.6f}); flow {tr.last_terms[0].item():.6f} rec {tr.last_terms[1].item():.6f}")
+    assert abs(loss.item() - loss_o.item()) <= 2e-2 * abs(loss_o.item())
+    assert abs(tr.last_terms[1].item() - rec.item()) <= 3e-2 * abs(rec.item())
+    e = rel(tr.gflat, gflat_o)
+    print(f"CondFlowTrainer gradient vs oracle rel-L2 {e:.3e}")
+    assert e <= BAR_GRAD_ALL
+    # AdamW (decoupled weight decay 0.01) + clip 0.3, given the gradient the kernels produced
+    gcl = tr.gflat.cpu() * min(1.0, 0.3 / (tr.gflat.double().norm().item() + 1e-6))
+    pt = torch.nn.Parameter(p_before.cpu().clone())
+    opt = torch.optim.AdamW([pt], lr=1e-3)
+    pt.grad = gcl
+    opt.step()
+    assert torch.allclose(tr.flat.cpu(), pt.detach(), rtol=1e-5, atol=1e-7)
+    loss2 = tr.step(batch.to(dev), noise1=n1, X0=x0, T=T, bores=bores, n_bores=nb)
+    assert torch.isfinite(loss2)
+
+
 def test_training_reduces_loss(ftb, dev):
     """A few fused steps on one fixed batch drive the loss down (end-to-end sanity of sign and scale)."""
     from oracle import synth

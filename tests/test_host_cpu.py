@@ -146,3 +146,28 @@ def test_training_plan_sizes_without_gpu():
     assert n > _lib.lib.ftb_unet3d_workspace_bytes(net._handle, 1, 16, 16, 16) > 0
     total = _lib.lib.ftb_unet3d_param_offset(net._handle, _lib.lib.ftb_unet3d_num_params(net._handle))
     assert total == 25_193_410
+
+
+def test_host_jittered_grid_points_match_oracle():
+    """The host borehole draw (boreholes.jittered_grid_points, vectorised) equals the reference's per-cell loop
+    (oracle restatement of boreholes.py:9-42) on the same uniform numbers."""
+    import math
+    for (X, Y, n) in ((64, 64, 8), (64, 64, 17), (32, 48, 31), (16, 16, 10)):
+        g = torch.Generator().manual_seed(n)
+        got = ftb.jittered_grid_points(X, Y, n, g)
+        n_x = int(math.floor(math.sqrt(n)))
+        n_y = int(math.ceil(n / n_x))
+        rand = torch.rand(n_x * n_y, 2, generator=torch.Generator().manual_seed(n))
+        want = task.jittered_grid_points(X, Y, n, rand)
+        assert torch.equal(got, want), (X, Y, n)
+        assert got.shape == (n, 2) and got.min() >= 0 and got[:, 0].max() <= X - 1 and got[:, 1].max() <= Y - 1
+    bores, nb = ftb.draw_boreholes(3, 64, 64, torch.Generator().manual_seed(1))
+    assert bores.shape == (3, 64, 2) and bores.dtype == torch.int32 and all(8 <= int(v) < 32 for v in nb)
+
+
+def test_conditioning_frontend_has_no_cpu_path():
+    cats = torch.zeros(1, 1, 4, 4, 4, dtype=torch.long)
+    with pytest.raises(RuntimeError):
+        ftb.make_surface_mask(cats)
+    with pytest.raises(RuntimeError):
+        ftb.EnsembleVotes(ftb.simplex_embedding(15, 18), (4, 4, 4), "cpu")

@@ -263,6 +263,31 @@ def test_cond_training_grads_vs_reference_golden(golden_dir, name):
         assert rel_l2(grads[k], g[f"full/{k}"]) <= 1e-3, k
 
 
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_conditioning_masks_vs_reference_golden(golden_dir, name):
+    """oracle make_surface_mask / make_boreholes_mask / make_combined_mask == the reference's boreholes.py
+    (tests/golden/make_golden.py gen_cond_frontend), borehole draws replayed from the stored seed."""
+    g = _load(golden_dir, "cond_frontend.npz")
+    cats = torch.from_numpy(g[f"{name}.cats"]).long()
+    B, _, X, Y, Z = cats.shape
+    unpack = lambda k: torch.from_numpy(np.unpackbits(g[f"{name}.{k}"])[: cats.numel()].astype(bool)).view(cats.shape)
+    assert torch.equal(task.make_surface_mask(cats), unpack("surface"))
+    bores, nb = task.replay_reference_borehole_draws(int(g[f"{name}.seed"]), B, X, Y)
+    assert torch.equal(task.make_boreholes_mask(cats, bores, nb), unpack("boreholes"))
+    assert torch.equal(task.make_combined_mask(cats, bores, nb), unpack("combined"))
+
+
+def test_ensemble_statistics_closed_form():
+    """ensemble_statistics (model_inference_experiments.py:442-459) on a hand-made ensemble."""
+    dec = torch.tensor([[-1, 0, 3, 3], [-1, 1, 3, 2], [-1, 0, 2, 2], [0, 0, 3, 13]]).view(4, 1, 1, 1, 4)
+    pv, ent, most, em = task.ensemble_statistics(dec, 15)
+    assert pv.shape == (1, 15, 1, 1, 4)
+    assert torch.allclose(pv[0, :, 0, 0, 0], torch.tensor([0.75, 0.25] + [0.0] * 13))
+    assert most.view(-1).tolist() == [-1, 0, 3, 2]          # ties -> first maximum
+    assert abs(ent.view(-1)[1].item() - (-(0.75 * np.log(0.75) + 0.25 * np.log(0.25)))) < 1e-6
+    assert em.view(-1)[0].item() == -1 and em.view(-1)[1].item() == ent.view(-1)[1].item()
+
+
 def test_adam_reference_matches_torch():
     torch.manual_seed(0)
     p0 = torch.randn(1000)
