@@ -174,12 +174,17 @@ __device__ __forceinline__ void epi_store16(const IgemmParams& p, EpiCtx& ec, in
     ec.ssq += s0 + s1;
   }
   if (ec.f32_b) {
+    float* o = ec.f32_b + (size_t)c0 * ec.cgs + vox;
+    if (kTrain && p.f32_accum) {   // all 16 loads in flight before the first store
+      float old[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) old[j] = (c0 + j < p.out_f32_c) ? __ldcg(o + (size_t)j * ec.cgs) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] += old[j];
+    }
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-      if (c0 + j < p.out_f32_c) {
-        float* o = ec.f32_b + (size_t)(c0 + j) * ec.cgs + vox;
-        *o = (kTrain && p.f32_accum) ? *o + v[j] : v[j];
-      }
+      if (c0 + j < p.out_f32_c) o[(size_t)j * ec.cgs] = v[j];
     return;
   }
   bf16* dst = ec.out_b + ((size_t)(p.out_cgoff + (c0 >> 3)) * ec.cgs + vox) * 8;
@@ -525,6 +530,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // Programmatic dependent launch: the prologue above (barrier init, TMEM allocation, descriptor prefetch) ran while
+  // the previous kernel of the stream was still draining; its results are only read below this point.  The
+  // trigger lets the NEXT kernel's CTAs take an SM as soon as this kernel's CTA there exits.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -1177,8 +1187,17 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
     }
     // the training epilogue (pre-norm side output, dropout) is a separate instantiation: the inference kernel
     // carries none of its code
-    if (q.u_out || q.drop_p > 0.f || q.f32_accum) conv_igemm_kernel<true><<<grid, kThreads, smem_bytes, st>>>(tm0, tm1, q);
-    else conv_igemm_kernel<false><<<grid, kThreads, smem_bytes, st>>>(tm0, tm1, q);
+    {
+      static const bool pdl = getenv("FTB_NO_PDL") == nullptr;
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+      if (q.u_out || q.drop_p > 0.f || q.f32_accum) FTB_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true>, tm0, tm1, q));
+      else FTB_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false>, tm0, tm1, q));
+    }
     prof_end(prof, st);
     FTB_LAUNCH_OK();
   }

@@ -215,6 +215,12 @@ __global__ void pack_jobs_kernel(const PackJob* __restrict__ jobs) {
     const int co = nt * jb.n + ng * 8 + n8;
     int ci = ks * 16 + kc * 8 + k8;
     int t = (K - 1 - j) * K * K + khw;
+    int seg = 0;   // fp32 mode: K extent = 2 or 3 copies of the padded channels ([hi | hi] or [hi | hi | lo] weights)
+    if (jb.part >= 3) {
+      const int cp = jb.cin_pad / (jb.part == 3 ? 3 : 2);
+      seg = ci / cp;
+      ci -= seg * cp;
+    }
     bool ok = co < jb.cout && ci < jb.cin_real;
     if (jb.unfold_w) {
       const int kw = ci / jb.cin_real;
@@ -232,7 +238,7 @@ __global__ void pack_jobs_kernel(const PackJob* __restrict__ jobs) {
         if (jb.in_scale) v *= jb.in_scale[ci];
       }
     }
-    if (jb.part == 2) v -= __bfloat162float(__float2bfloat16(v));   // low part of the 3 x bf16 split
+    if (jb.part == 2 || (jb.part == 3 && seg == 2)) v -= __bfloat162float(__float2bfloat16(v));   // low part of the 3 x bf16 split
     jb.dst[i] = __float2bfloat16(v);
   }
 }

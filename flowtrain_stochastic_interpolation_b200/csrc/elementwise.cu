@@ -116,9 +116,10 @@ __device__ __forceinline__ Lerp lerp_idx(int o, int in, float scale) {
   return r;
 }
 
-// One block per (b*cg, d, group of RH output rows): the depth/height lerp parameters are computed
-// from block-uniform values, each thread only does the W lerp of its voxel (no per-thread div/mod).
-constexpr int kTriRH = 4;
+// One block per (b*cg, d, group of RH output rows): the depth lerp parameters are block-uniform.  A thread produces
+// up to RH*Wo/256 voxels in an unrolled loop (8 independent 16-byte loads each, so a few dozen loads in flight per
+// thread): with 4 rows per block the 64^3 upsample was 98 304 one-voxel-per-thread blocks and ran at 1.1 TB/s.
+constexpr int kTriRH = 16;
 __global__ void __launch_bounds__(256)
 trilinear_kernel(const bf16* __restrict__ in, int CG, int Di, int Hi, int Wi, int Do, int Ho, int Wo,
                  int hgroups, float sd, float sh, float sw, bf16* __restrict__ out) {
@@ -129,10 +130,11 @@ trilinear_kernel(const bf16* __restrict__ in, int CG, int Di, int Hi, int Wi, in
   const Lerp ld = lerp_idx(d, Di, sd);
   const bf16* base = in + bc * (size_t)Di * Hi * Wi * 8;
   bf16* obase = out + (bc * (size_t)Do + d) * Ho * Wo * 8;
+#pragma unroll 2
   for (int idx = threadIdx.x; idx < kTriRH * Wo; idx += blockDim.x) {
     const int hr = idx / Wo, w = idx - hr * Wo;
     const int h = hg * kTriRH + hr;
-    if (h >= Ho) break;
+    if (h >= Ho) continue;
     const Lerp lh = lerp_idx(h, Hi, sh), lw = lerp_idx(w, Wi, sw);
     float acc[8];
 #pragma unroll

@@ -8,28 +8,37 @@
 
 namespace ftb_engine_detail {
 
-// hi / lo weight packs of every conv (no folded gains, no W-unfolding), rebuilt when the parameters change
+// Weight packs of every conv (no folded gains, no W-unfolding), rebuilt when the parameters change.  With CP = pad16(Cin):
+//   3*CP <= 512: ONE launch, sources (x_hi | x_lo) and x_hi again, weights [W_hi | W_hi | W_lo] along K — the three
+//                products share the TMEM accumulator and the fp32 output is written once;
+//   2*CP <= 512: (x_hi | x_lo) x [W_hi | W_hi], then x_hi x W_lo accumulated in place by the epilogue;
+//   else       : three launches of CP channels each.
+inline int f32_mode(int cp) { return 3 * cp <= 512 ? 3 : (2 * cp <= 512 ? 2 : 1); }
+
 int finalize_f32(ftb_unet* U, cudaStream_t st) {
   const float* base0 = U->params.empty() ? nullptr : U->params[0].dev;
   if (!U->d_f32jobs || U->f32jobs_base != base0) {
     std::vector<PackJob> jobs;
     for (auto& kv : U->convs) {
       const ConvLayer& cl = kv.second;
-      const int cp = round_up(cl.cin, 16);
+      const int cp = round_up(cl.cin, 16), mode = f32_mode(cp);
       const size_t elems = (size_t)cl.ntiles * cl.k * cl.k * cl.k * cp * cl.n_tile;
       std::pair<bf16*, bf16*>& pk = U->f32packs[kv.first];
       if (!pk.first) {
-        FTB_TRY(dev_alloc(U, &pk.first, elems));
-        FTB_TRY(dev_alloc(U, &pk.second, elems));
+        FTB_TRY(dev_alloc(U, &pk.first, elems * (mode == 1 ? 1 : mode)));
+        if (mode != 3) FTB_TRY(dev_alloc(U, &pk.second, elems));
       }
-      for (int part = 1; part <= 2; ++part) {
+      for (int which = 0; which < (mode == 3 ? 1 : 2); ++which) {
         PackJob jb{};
         jb.w = U->params[U->pindex[cl.wname]].dev;
         jb.in_scale = nullptr;
-        jb.dst = part == 1 ? pk.first : pk.second;
-        jb.cout = cl.cout; jb.cin_real = cl.cin; jb.ksize = cl.k; jb.cin_pad = cp; jb.n = cl.n_tile;
+        jb.dst = which == 0 ? pk.first : pk.second;
+        jb.cout = cl.cout; jb.cin_real = cl.cin; jb.ksize = cl.k; jb.n = cl.n_tile;
         jb.ntiles = cl.ntiles; jb.unfold_w = 0;
-        jb.part = part;
+        if (which == 1) { jb.cin_pad = cp; jb.part = 2; }               // W_lo
+        else if (mode == 3) { jb.cin_pad = 3 * cp; jb.part = 3; }       // [W_hi | W_hi | W_lo]
+        else if (mode == 2) { jb.cin_pad = 2 * cp; jb.part = 4; }       // [W_hi | W_hi]
+        else { jb.cin_pad = cp; jb.part = 1; }                          // W_hi
         jobs.push_back(jb);
       }
     }
@@ -111,16 +120,30 @@ struct FwdF32 {
       e.out_f32 = out.p;
       e.out_f32_c = cl.cout;
       Act dummy = sp;   // spatial dims only: the epilogue writes NCDHW fp32
-      const ConvSrc hi{&sp, 0, cp / 8}, lo{&sp, cp / 8, cp / 8};
-      w.w = pk.first;
+      const ConvSrc hi{&sp, 0, cp / 8}, lo{&sp, cp / 8, cp / 8}, hilo{&sp, 0, 2 * cp / 8};
+      const int mode = f32_mode(cp);
       e.bias = cl.bname.empty() ? nullptr : cl.bias;
-      FTB_TRY(conv_igemm(hi, ConvSrc{}, w, e, dummy, 0, st));      // W_hi x_hi + bias
-      e.bias = nullptr;
-      e.out_f32_accum = true;
-      FTB_TRY(conv_igemm(lo, ConvSrc{}, w, e, dummy, 0, st));      // += W_hi x_lo
-      w.w = pk.second;
-      FTB_TRY(conv_igemm(hi, ConvSrc{}, w, e, dummy, 0, st));      // += W_lo x_hi
-      U->launches += 1 + 3 * cl.ntiles;
+      w.w = pk.first;
+      if (mode == 3) {
+        w.cin = 3 * cp;
+        FTB_TRY(conv_igemm(hilo, hi, w, e, dummy, 0, st));           // W_hi x_hi + W_hi x_lo + W_lo x_hi + bias
+      } else if (mode == 2) {
+        w.cin = 2 * cp;
+        FTB_TRY(conv_igemm(hilo, ConvSrc{}, w, e, dummy, 0, st));    // W_hi (x_hi + x_lo) + bias
+      } else {
+        FTB_TRY(conv_igemm(hi, ConvSrc{}, w, e, dummy, 0, st));      // W_hi x_hi + bias
+        e.bias = nullptr;
+        e.out_f32_accum = true;
+        FTB_TRY(conv_igemm(lo, ConvSrc{}, w, e, dummy, 0, st));      // += W_hi x_lo
+      }
+      if (mode != 3) {
+        e.bias = nullptr;
+        e.out_f32_accum = true;
+        w.cin = cp;
+        w.w = pk.second;
+        FTB_TRY(conv_igemm(hi, ConvSrc{}, w, e, dummy, 0, st));      // += W_lo x_hi
+      }
+      U->launches += 1 + (mode == 3 ? 1 : (mode == 2 ? 2 : 3)) * cl.ntiles;
     }
     off = mark;   // the split operand is dead once the three launches are enqueued (stream order)
     return 0;
@@ -180,10 +203,10 @@ struct FwdF32 {
       FTB_TRY(conv(p + ".to_out", ao, nullptr, o));
       FTB_TRY(normact(o, false, nullptr, nullptr, nullptr, 0, false, x.p, out));
     } else {
-      float* scratch = f32((size_t)B * hd * 2 + (size_t)B * heads * dh * dh);
+      float* scratch = f32(f32_linattn_scratch(B, heads, dh, x.vox()));
       if (!dry) {
         FTB_TRY(f32_linear_attention(qkv.p, B, heads, dh, x.vox(), pdev(p + ".mem_kv"), c.num_mem_kv, scratch, ao.p, st));
-        U->launches += 4;
+        U->launches += 5;
       }
       FTB_TRY(conv(p + ".to_out.0", ao, nullptr, o));
       FTB_TRY(normact(o, true, U->gains.at(p + ".to_out.1.g").gs, nullptr, nullptr, 0, false, x.p, out));

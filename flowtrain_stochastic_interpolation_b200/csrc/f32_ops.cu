@@ -2,8 +2,8 @@
 // reference's own layout), the convolutions on the tcgen05 kernel with the 3 x bf16 split
 //     W x  ~=  W_hi x_hi + W_hi x_lo + W_lo x_hi        (hi = bf16(.), lo = bf16(. - hi); fp32 accumulation),
 // which keeps 16 mantissa bits of both operands: the bar is <= 1e-4 relative L2 against the fp32 reference
-// (BASELINE north_star; plain bf16 operands give 5.6e-3, TF32 7e-4 — SURVEY §6).  This is the accuracy mode, about
-// 3.5x the cost of the bf16 path; the kernels here are simple coalesced fp32 passes (thread = voxel, channel stride =
+// (BASELINE north_star; plain bf16 operands give 5.6e-3, TF32 7e-4 — SURVEY §6).  This is the accuracy mode, measured at
+// 3.8x the cost of the bf16 path (14.3 vs 3.8 ms per 64^3 evaluation at B=1); the kernels here are simple coalesced fp32 passes (thread = voxel, channel stride =
 // voxels).  Reference: unet_attn_3d.py RMSNorm :111-128, Block :232-244, LinearAttention :308-341, Attention
 // :357-373 / :436-465, Upsample / Downsample :85-88, :105-108.
 #include "ops.h"
@@ -126,30 +126,60 @@ linattn_kstat_f32_kernel(const float* __restrict__ qkv, int hd, size_t n, const 
     stat[((size_t)b * hd + ch) * 2 + 1] = t;
   }
 }
-// block per (b, h, d): ctx[b][h][d][e] = sum_n softmax_n(k)[d,n] v[e,n] (+ memory tokens); 256 threads = 32 e x 8 lanes
+// Context of one (sample, head): ctx[d][e] = sum_n softmax_n(k)[d,n] v[e,n].  Block = (voxel chunk, head, sample):
+// the chunk's P = exp(k - max) [dh][TN] and V [dh][TN] tiles are staged in shared memory (k and v are read from HBM
+// exactly once, one expf per element) and each of the 256 threads accumulates a 2 x 2 patch of the dh x dh result;
+// per-chunk partials go to `part` and are summed in a fixed order by linattn_ctx_finish_f32_kernel (deterministic).
+constexpr int kCtxTN = 128;    // voxels per staged tile
+constexpr int kCtxChunk = 2048;  // voxels per block
 __global__ void __launch_bounds__(256)
-linattn_ctx_f32_kernel(const float* __restrict__ qkv, int heads, int dh, size_t n, const float* __restrict__ mem_kv,
-                       int n_mem, const float* __restrict__ stat, float* __restrict__ ctx) {
-  __shared__ float red[256];
-  const int d = blockIdx.x, h = blockIdx.y, b = blockIdx.z, hd = heads * dh;
-  const int e = threadIdx.x / 8, l = threadIdx.x % 8;
+linattn_ctx_part_f32_kernel(const float* __restrict__ qkv, int heads, int dh, size_t n, const float* __restrict__ stat,
+                            float* __restrict__ part, int nchunk) {
+  __shared__ float sp[32][kCtxTN + 1], sv[32][kCtxTN + 1];
+  const int chunk = blockIdx.x, h = blockIdx.y, b = blockIdx.z, hd = heads * dh;
+  const float* kb = qkv + ((size_t)b * 3 * hd + hd + (size_t)h * dh) * n;
+  const float* vb = qkv + ((size_t)b * 3 * hd + 2 * hd + (size_t)h * dh) * n;
+  const int d0 = (threadIdx.x >> 4) * 2, e0 = (threadIdx.x & 15) * 2;   // 16 x 16 threads, 2 x 2 outputs each
+  float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+  const size_t v_lo = (size_t)chunk * kCtxChunk;
+  const size_t v_hi = v_lo + kCtxChunk < n ? v_lo + kCtxChunk : n;
+  for (size_t t0 = v_lo; t0 < v_hi; t0 += kCtxTN) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * kCtxTN; i += 256) {
+      const int r = i / kCtxTN, c = i - r * kCtxTN;
+      const size_t v = t0 + c;
+      const bool in = r < dh && v < v_hi;
+      sp[r][c] = in ? expf(kb[(size_t)r * n + v] - stat[((size_t)b * hd + h * dh + r) * 2]) : 0.f;
+      sv[r][c] = in ? vb[(size_t)r * n + v] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int c = 0; c < kCtxTN; ++c) {
+      const float p0 = sp[d0][c], p1 = sp[d0 + 1][c], v0 = sv[e0][c], v1 = sv[e0 + 1][c];
+      a00 = fmaf(p0, v0, a00); a01 = fmaf(p0, v1, a01);
+      a10 = fmaf(p1, v0, a10); a11 = fmaf(p1, v1, a11);
+    }
+  }
+  float* o = part + (((size_t)b * heads + h) * nchunk + chunk) * 1024;
+  o[d0 * 32 + e0] = a00; o[d0 * 32 + e0 + 1] = a01;
+  o[(d0 + 1) * 32 + e0] = a10; o[(d0 + 1) * 32 + e0 + 1] = a11;
+}
+// ctx[b][h][d][e] = (sum_chunks part + memory tokens) / den[d]; block per (h, b), thread per (d, e)
+__global__ void __launch_bounds__(1024)
+linattn_ctx_finish_f32_kernel(const float* __restrict__ part, int nchunk, int heads, int dh,
+                              const float* __restrict__ mem_kv, int n_mem, const float* __restrict__ stat,
+                              float* __restrict__ ctx) {
+  const int h = blockIdx.x, b = blockIdx.y, hd = heads * dh;
+  const int d = threadIdx.x >> 5, e = threadIdx.x & 31;
+  if (d >= dh || e >= dh) return;
+  const float* pp = part + ((size_t)b * heads + h) * nchunk * 1024 + d * 32 + e;
+  float t = 0.f;
+  for (int c = 0; c < nchunk; ++c) t += pp[(size_t)c * 1024];
   const float mx = stat[((size_t)b * hd + h * dh + d) * 2], den = stat[((size_t)b * hd + h * dh + d) * 2 + 1];
-  float a = 0.f;
-  if (e < dh) {
-    const float* k = qkv + ((size_t)b * 3 * hd + hd + h * dh + d) * n;
-    const float* vv = qkv + ((size_t)b * 3 * hd + 2 * hd + h * dh + e) * n;
-    for (size_t i = l; i < n; i += 8) a += expf(k[i] - mx) * vv[i];
-  }
-  red[threadIdx.x] = a;
-  __syncthreads();
-  if (l == 0 && e < dh) {
-    float t = 0.f;
-    for (int i = 0; i < 8; ++i) t += red[e * 8 + i];
-    const float* mk = mem_kv + ((size_t)h * dh + d) * n_mem;
-    const float* mv = mem_kv + ((size_t)hd + h * dh + e) * n_mem;
-    for (int j = 0; j < n_mem; ++j) t += expf(mk[j] - mx) * mv[j];
-    ctx[(((size_t)b * heads + h) * dh + d) * dh + e] = t / den;
-  }
+  const float* mk = mem_kv + ((size_t)h * dh + d) * n_mem;
+  const float* mv = mem_kv + ((size_t)hd + h * dh + e) * n_mem;
+  for (int j = 0; j < n_mem; ++j) t += expf(mk[j] - mx) * mv[j];
+  ctx[(((size_t)b * heads + h) * dh + d) * dh + e] = t / den;
 }
 // out[b][(h,e)][n] = sum_d ctx[b][h][d][e] q~[(h,d)][n]; thread = (b, h, voxel)
 __global__ void __launch_bounds__(256)
@@ -234,17 +264,27 @@ int f32_trilinear(const float* in, int B, int C, int Di, int Hi, int Wi, int Do,
   return 0;
 }
 
+int f32_linattn_chunks(size_t n) { return (int)((n + kCtxChunk - 1) / kCtxChunk); }
+// scratch floats f32_linear_attention needs: stat [B][hd][2] + ctx [B][heads][dh][dh] + per-chunk partials
+size_t f32_linattn_scratch(int B, int heads, int dh, size_t n) {
+  return (size_t)B * heads * dh * 2 + (size_t)B * heads * dh * dh + (size_t)B * heads * f32_linattn_chunks(n) * 1024;
+}
+
 int f32_linear_attention(float* qkv, int B, int heads, int dh, size_t n, const float* mem_kv, int n_mem, float* scratch,
                          float* out, cudaStream_t st) {
   FTB_CHECK(dh <= 32, "f32 linear attention: dim_head <= 32");
   const int hd = heads * dh;
   float* stat = scratch;
   float* ctx = scratch + (size_t)B * hd * 2;
+  float* part = ctx + (size_t)B * heads * dh * dh;
+  const int nchunk = f32_linattn_chunks(n);
   linattn_q_f32_kernel<<<dim3((unsigned)((n + 255) / 256), heads, B), 256, 0, st>>>(qkv, heads, dh, n, 1.f / sqrtf((float)dh));
   FTB_LAUNCH_OK();
   linattn_kstat_f32_kernel<<<dim3(hd, B), 1024, 0, st>>>(qkv, hd, n, mem_kv, n_mem, stat);
   FTB_LAUNCH_OK();
-  linattn_ctx_f32_kernel<<<dim3(dh, heads, B), 256, 0, st>>>(qkv, heads, dh, n, mem_kv, n_mem, stat, ctx);
+  linattn_ctx_part_f32_kernel<<<dim3(nchunk, heads, B), 256, 0, st>>>(qkv, heads, dh, n, stat, part, nchunk);
+  FTB_LAUNCH_OK();
+  linattn_ctx_finish_f32_kernel<<<dim3(heads, B), 1024, 0, st>>>(part, nchunk, heads, dh, mem_kv, n_mem, stat, ctx);
   FTB_LAUNCH_OK();
   linattn_out_f32_kernel<<<dim3((unsigned)((n + 255) / 256), heads, B), 256, 0, st>>>(qkv, heads, dh, n, ctx, out);
   FTB_LAUNCH_OK();

@@ -93,7 +93,8 @@ struct PackJob {
   bf16* dst;
   int cout, cin_real, ksize, cin_pad, n, ntiles, unfold_w;
   int transposed, ci0, src_cin;
-  int part;   // 0: bf16(w);  1: hi = bf16(w) again (fp32 mode);  2: lo = bf16(w - hi) (fp32 mode, 3 x bf16 split)
+  int part;   // 0 / 1: bf16(w);  2: lo = bf16(w - bf16(w));  fp32 mode (3 x bf16 split) with the K extent repeated:
+              // 3: cin_pad = 3 x pad16(cin), weights [hi | hi | lo];  4: cin_pad = 2 x pad16(cin), weights [hi | hi]
 };
 int pack_conv_weights_batched(const PackJob* d_jobs, int njobs, cudaStream_t st);
 
@@ -203,7 +204,8 @@ int f32_pack_split(const float* x0, int c0, const float* x1, int c1, int B, size
 int f32_normact(const float* u, int B, int C, size_t vox, bool norm, const float* gain, const float* s1, const float* sh,
                 int fstride, bool silu, const float* resid, float* out, cudaStream_t st);
 int f32_trilinear(const float* in, int B, int C, int Di, int Hi, int Wi, int Do, int Ho, int Wo, float* out, cudaStream_t st);
-// LinearAttention on qkv [B][3*hd][n] fp32 (q | k | v): out [B][hd][n]; scratch: B*hd*2 + B*heads*dh*dh floats
+// LinearAttention on qkv [B][3*hd][n] fp32 (q | k | v): out [B][hd][n]; scratch: f32_linattn_scratch() floats
+size_t f32_linattn_scratch(int B, int heads, int dh, size_t n);
 int f32_linear_attention(float* qkv, int B, int heads, int dh, size_t n, const float* mem_kv, int n_mem, float* scratch,
                          float* out, cudaStream_t st);
 // softmax attention, qkv [B][3*hd][n] fp32, mem_kv [2][heads][n_mem][dh]: out [B][hd][n]
