@@ -61,6 +61,8 @@ def parse():
     ap.add_argument("--no-train", action="store_true", help="skip the training-step leg (train voxels/s)")
     ap.add_argument("--train-only", action="store_true", help="only the training-step leg (development)")
     ap.add_argument("--train-batch", type=int, default=8)
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the side measurements (fp32 accuracy mode, conditional training step)")
     return ap.parse_args()
 
 
@@ -285,6 +287,53 @@ def run_train_leg(a, ftb, _lib, dev, rank, world, dist):
     }
 
 
+def run_extras(a, ftb, dev):
+    """Side measurements carried in the JSON line under "extras" (never the headline): one velocity evaluation in
+    the fp32 accuracy mode vs bf16 at B=1, and one optimiser step of the conditional project (BASELINE configs[2]'s
+    model: Unet3DCond v3, 15-d embedding; CondFlowTrainer: AdamW 1e-3, clip 0.3, EMA, dropout 0.1)."""
+    import torch
+    from oracle import synth
+    S = a.size
+    out = {}
+
+    def timed(fn, n):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    cfg = synth.make_cfg()
+    net = ftb.Unet3D(**cfg).to(dev).eval()
+    net.load_state_dict(synth.synth_unet3d_params(cfg, 0))
+    x = synth.synth_input((1, 18, S, S, S), 100).to(dev)
+    t = torch.full((1,), 0.5, device=dev)
+    with torch.no_grad():
+        bf = timed(lambda: net(x, t), 5)
+        net.set_precision("fp32")
+        f32 = timed(lambda: net(x, t), 5)
+    out["fp32_mode"] = {"ms_per_eval_b1": f32, "bf16_ms_per_eval_b1": bf, "ratio": f32 / bf,
+                        "what": "Unet3D.set_precision('fp32'): 3 x bf16 split convs, fp32 elsewhere (<= 1e-4 rel-L2)"}
+    del net, x
+    torch.cuda.empty_cache()
+    B = a.train_batch
+    cfg = synth.make_cfg(data_channels=15, dropout=0.1)
+    kw = {k: v for k, v in cfg.items() if k != "data_channels"}
+    mod = ftb.Geo3DStochInterpCond(data_shape=(S, S, S), embedding_dim=15, **kw).to(dev)
+    mod.net.load_state_dict(synth.synth_unet3d_cond_params(cfg, 5))
+    tr = ftb.CondFlowTrainer(mod, lr=1e-3, max_grad_norm=0.3, ema_decay=0.9995)
+    cats = torch.randint(-1, 14, (B, 1, S, S, S), generator=torch.Generator().manual_seed(7)).to(dev)
+    ms = timed(lambda: tr.step(cats), 3)
+    out["cond_train"] = {"ms_per_step": ms, "voxels_per_s": B * S ** 3 / (ms * 1e-3), "batch": B,
+                         "what": "CondFlowTrainer.step: conditioning front-end kernel, Unet3DCond v3 fwd/bwd, "
+                                 "flow + reconstruction loss, clip 0.3 + AdamW, EMA (1 GPU)"}
+    del tr, mod
+    torch.cuda.empty_cache()
+    return out
+
+
 # ---------------------------------------------------------------------------- B200 arm
 def run_b200(a):
     import torch
@@ -394,6 +443,16 @@ def run_b200(a):
         torch.cuda.empty_cache()
         train_leg = run_train_leg(a, ftb, _lib, dev, rank, world, dist)
 
+    extras = None
+    if not a.no_extras and world == 1 and not os.environ.get("FTB_BENCH_MINIMAL"):
+        try:
+            if train_leg is None:
+                del solver, net
+                torch.cuda.empty_cache()
+            extras = run_extras(a, ftb, dev)
+        except Exception as exc:   # side measurements never break the headline line
+            extras = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     tot_s = (N_ODE_STEPS * step_ms + decode_ms) / 1e3
     stats = torch.tensor([step_ms, decode_ms, tot_s, e2e[0] if e2e else 0.0, float(launches)], device=dev, dtype=torch.float64)
     if world > 1:
@@ -432,6 +491,8 @@ def run_b200(a):
     }
     if train_leg:
         line["train"] = train_leg
+    if extras:
+        line["extras"] = extras
     if e2e:
         line["e2e"] = {"value": world * B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": e2e[1], "d2h_bytes_per_step": e2e[2],
                        "seconds_per_solve": e2e_s,

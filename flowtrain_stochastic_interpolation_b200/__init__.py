@@ -13,7 +13,8 @@ from .solvers import (ODEFlowSolver, ODEOneSidedDenoisingSolver, SDEOneSidedDeno
 from .boreholes import (conditioning_frontend, draw_boreholes, jittered_grid_points, make_boreholes_mask,
                         make_combined_mask, make_surface_mask)
 from .ensemble import EnsembleVotes
-from .task import (EMAShadow, Geo3DStochInterp, Geo3DStochInterpCond, decode, ema_update_, embed, flow_loss,
+from .task import (EMAShadow, Geo3DStochInterp, Geo3DStochInterpCond, lightning_checkpoint,
+                   load_model_with_ema_option, decode, ema_update_, embed, flow_loss,
                    simplex_embedding)
 from .training import BucketAllReduce, CondFlowTrainer, FlowTrainer, flatten_parameters
 from .unet3d import Unet3D, Unet3DCond
@@ -24,5 +25,5 @@ __all__ = [
     "ODEOneSidedDenoisingSolver", "SDEOneSidedDenoisingSolver", "odeSol_RK4", "integrate_fixed",
     "Geo3DStochInterp", "Geo3DStochInterpCond", "EMAShadow", "FlowTrainer", "CondFlowTrainer", "EnsembleVotes",
     "make_boreholes_mask", "make_surface_mask", "make_combined_mask", "conditioning_frontend", "draw_boreholes",
-    "jittered_grid_points", "BucketAllReduce", "flatten_parameters", "embed", "decode", "flow_loss", "ema_update_", "simplex_embedding",
+    "jittered_grid_points", "load_model_with_ema_option", "lightning_checkpoint", "BucketAllReduce", "flatten_parameters", "embed", "decode", "flow_loss", "ema_update_", "simplex_embedding",
 ]

@@ -206,3 +206,37 @@ class Geo3DStochInterpCond(nn.Module):
         """(X1, ATb, mask) of a category batch [B,1,X,Y,Z] in one kernel (see boreholes.conditioning_frontend)."""
         from .boreholes import conditioning_frontend
         return conditioning_frontend(batch, self.embedding.weight, bores, n_bores, generator)
+
+
+# --------------------------------------------------------------------------------------- checkpoint interop
+def load_model_with_ema_option(module: nn.Module, ckpt, map_location="cpu", use_ema: bool = False, strict: bool = True):
+    """Counterpart of ``load_model_with_ema_option`` (project/geodata-3d-conditional/model_inference_experiments.py:
+    387-403) for the B200 modules: ``ckpt`` is a Lightning ``.ckpt`` path or an already loaded dict with
+    ``"state_dict"`` (keys ``net.*``, ``embedding.weight``: the reference LightningModule's own names, which
+    ``Geo3DStochInterp`` / ``Geo3DStochInterpCond`` share) and optionally ``"ema_shadow"`` (EMACallback.on_save_checkpoint,
+    callbacks.py:295-303: name -> tensor over ``pl_module.named_parameters()``).  With ``use_ema`` the shadow replaces the
+    parameters it covers, as the reference does.  Pure host-side plumbing (no math): returns ``module``."""
+    if isinstance(ckpt, (str, bytes)) or hasattr(ckpt, "__fspath__"):
+        ckpt = torch.load(ckpt, map_location=map_location, weights_only=False)
+    sd = ckpt["state_dict"] if "state_dict" in ckpt else ckpt
+    module.load_state_dict(sd, strict=strict)
+    if use_ema and "ema_shadow" in ckpt:
+        shadow = ckpt["ema_shadow"]
+        with torch.no_grad():
+            for name, param in module.named_parameters():
+                if name in shadow:
+                    param.data.copy_(shadow[name].to(param.device))
+    elif use_ema:
+        print("WARNING: 'ema_shadow' not found in checkpoint. Using regular weights.")
+    return module
+
+
+def lightning_checkpoint(module: nn.Module, trainer=None, update_on_cpu: bool = True) -> dict:
+    """The two entries of a Lightning ``.ckpt`` the reference's loaders read (``state_dict``, ``ema_shadow`` keyed like
+    ``pl_module.named_parameters()``, ``ema_update_on_cpu``; callbacks.py:295-303), from a B200 module and, when given,
+    the EMA buffer of a ``FlowTrainer`` / ``CondFlowTrainer`` — so weights trained here load into the reference."""
+    ck = {"state_dict": {k: v.detach().cpu().clone() for k, v in module.state_dict().items()}}
+    if trainer is not None:
+        ck["ema_shadow"] = {f"net.{k}": (v.cpu() if update_on_cpu else v) for k, v in trainer.ema_state_dict().items()}
+        ck["ema_update_on_cpu"] = update_on_cpu
+    return ck

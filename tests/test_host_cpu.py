@@ -171,3 +171,26 @@ def test_conditioning_frontend_has_no_cpu_path():
         ftb.make_surface_mask(cats)
     with pytest.raises(RuntimeError):
         ftb.EnsembleVotes(ftb.simplex_embedding(15, 18), (4, 4, 4), "cpu")
+
+
+def test_lightning_checkpoint_round_trip(tmp_path):
+    """A Lightning-style .ckpt (state_dict with net.* / embedding.weight keys + ema_shadow, callbacks.py:295-303) loads
+    into the B200 module exactly as model_inference_experiments.py:387-403 does, with and without the EMA shadow."""
+    cfg = dict(dim=32, dim_mults=(1, 2), time_resolution=64, time_bandwidth=100.0, time_learned_emb=True,
+               attn_heads=2, attn_dim_head=16)
+    src = ftb.Geo3DStochInterp(data_shape=(16, 16, 16), embedding_dim=18, **cfg)
+    sd = {k: v.clone() for k, v in src.state_dict().items()}
+    shadow = {n: p.detach() + 1.0 for n, p in src.named_parameters() if p.requires_grad}
+    path = tmp_path / "epoch=1.ckpt"
+    torch.save({"state_dict": sd, "ema_shadow": shadow, "ema_update_on_cpu": True, "epoch": 1}, path)
+    dst = ftb.Geo3DStochInterp(data_shape=(16, 16, 16), embedding_dim=18, **cfg)
+    ftb.load_model_with_ema_option(dst, str(path), use_ema=False)
+    for k, v in dst.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    ftb.load_model_with_ema_option(dst, str(path), use_ema=True)
+    for n, p in dst.named_parameters():
+        want = shadow[n] if n in shadow else sd[n]
+        assert torch.equal(p.detach(), want), n
+    assert "embedding.weight" not in shadow and torch.equal(dst.embedding.weight, sd["embedding.weight"])
+    ck = ftb.lightning_checkpoint(dst)
+    assert set(ck["state_dict"].keys()) == set(sd.keys())

@@ -14,7 +14,7 @@ if [[ $what == all || $what == bench ]]; then
   echo "bench rc=$?"; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 fi
 if [[ $what == all || $what == ncu ]]; then
-  CMD="python bench.py --steps 1 --warmup 1 --batch $nb --no-e2e --no-cpu-baseline"
+  CMD="python bench.py --steps 1 --warmup 1 --batch $nb --no-e2e --no-cpu-baseline --no-train --no-extras"
   timeout 300 $CMD > gpurun_out/plain.log 2>&1 &&
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv \
       --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
