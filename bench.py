@@ -197,7 +197,7 @@ def run_reference(a):
                                    f"Unet3D.forward on torch CPU ops); samples/s = 1/({N_ODE_STEPS}*{per}*s_per_eval)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------- training-step leg
@@ -357,7 +357,7 @@ def run_b200(a):
     if a.train_only:
         tl = run_train_leg(a, ftb, _lib, dev, rank, world, dist)
         if rank == 0:
-            print(json.dumps(tl), flush=True)
+            emit(tl)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -504,13 +504,29 @@ def run_b200(a):
             "value": 1.0 / (N_ODE_STEPS * per * s_per_eval), "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{a.cpu_evals} velocity evaluations at B=1 {S}^3 fp32 on the host ({s_per_eval:.2f} s each, oracle "
                       f"port of the reference CPU path); samples/s = 1/({N_ODE_STEPS}*{per}*s_per_eval)"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
     a = parse()
+    # stdout carries exactly one JSON line: anything a library prints to file descriptor 1 (e.g. NCCL's version
+    # banner under NCCL_DEBUG=VERSION) is sent to stderr instead
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -65,6 +65,7 @@ _SIGS = {
     "ftb_unet3d_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "ftb_unet3d_f32_workspace_bytes": (_sz, [_vp, _i, _i, _i, _i]),
     "ftb_unet3d_forward_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "ftb_unet3d_cond_forward_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
     "ftb_unet3d_get_tap_f32": (_i, [_vp, C.c_char_p, _vp, _ip, _vp]),
     "ftb_unet3d_cond_workspace_bytes": (_sz, [_vp, _i, _i, _i, _i, _i]),
     "ftb_unet3d_cond_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _sz, _i, _vp]),

@@ -962,15 +962,13 @@ int ftb_unet3d_forward(ftb_unet* h, const float* x, const float* t, float* out, 
 
 size_t ftb_unet3d_f32_workspace_bytes(ftb_unet* h, int B, int X, int Y, int Z) {
   if (check_dims(h, B, X, Y, Z) != 0) return 0;
-  if (h->cfg.conditional) { set_error("fp32 mode: unconditional Unet3D only"); return 0; }
   FwdF32 f{h, nullptr, nullptr, true, B};
   return f.run(nullptr, nullptr, nullptr, X, Y, Z) == 0 ? round_up_sz(f.peak, 256) + 256 : 0;
 }
 
-int ftb_unet3d_forward_f32(ftb_unet* h, const float* x, const float* t, float* out, int B, int X, int Y, int Z,
-                           void* workspace, size_t workspace_bytes, void* stream) {
+static int forward_f32_impl(ftb_unet* h, const float* x, const float* atb, const float* t, float* out, int B, int X,
+                            int Y, int Z, void* workspace, size_t workspace_bytes, void* stream) {
   FTB_TRY(check_dims(h, B, X, Y, Z));
-  FTB_CHECK(!h->cfg.conditional, "fp32 mode: unconditional Unet3D only");
   FTB_CHECK(x && t && out && workspace, "null argument");
   FTB_CHECK(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
   const size_t need = ftb_unet3d_f32_workspace_bytes(h, B, X, Y, Z);
@@ -980,7 +978,21 @@ int ftb_unet3d_forward_f32(ftb_unet* h, const float* x, const float* t, float* o
   FTB_TRY(finalize(h, st, true));
   FTB_TRY(finalize_f32(h, st));
   FwdF32 f{h, st, reinterpret_cast<char*>(workspace), false, B};
-  return f.run(x, t, out, X, Y, Z);
+  return f.run(x, t, out, X, Y, Z, atb);
+}
+
+int ftb_unet3d_forward_f32(ftb_unet* h, const float* x, const float* t, float* out, int B, int X, int Y, int Z,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  FTB_CHECK(h, "null handle");
+  FTB_CHECK(!h->cfg.conditional, "conditional model: call ftb_unet3d_cond_forward_f32 (ATb is required)");
+  return forward_f32_impl(h, x, nullptr, t, out, B, X, Y, Z, workspace, workspace_bytes, stream);
+}
+
+int ftb_unet3d_cond_forward_f32(ftb_unet* h, const float* x, const float* atb, const float* t, float* out, int B,
+                                int X, int Y, int Z, void* workspace, size_t workspace_bytes, void* stream) {
+  FTB_CHECK(h && atb, "null argument");
+  FTB_CHECK(h->cfg.conditional, "unconditional model: call ftb_unet3d_forward_f32");
+  return forward_f32_impl(h, x, atb, t, out, B, X, Y, Z, workspace, workspace_bytes, stream);
 }
 
 int ftb_unet3d_cond_forward(ftb_unet* h, const float* x, const float* atb, int atb_B, const float* t, float* out,

@@ -217,15 +217,51 @@ struct FwdF32 {
     return 0;
   }
 
+  // EmbedATb.forward (unet_attn_3d_cond_v3.py:131-139); `out` allocated by the caller
+  int embed_atb(const std::string& p, const T32& opened, const T32& out) {
+    const size_t mark = off;
+    T32 src = opened;
+    if (opened.D != out.D || opened.H != out.H || opened.W != out.W) {
+      src = like(out, opened.C);
+      FTB_TRY(resample(opened, src));
+    }
+    T32 e1 = like(out, out.C);
+    FTB_TRY(conv(p + ".conv1", src, nullptr, e1));
+    FTB_TRY(normact(e1, false, nullptr, nullptr, nullptr, 0, true, nullptr, e1));   // SiLU
+    FTB_TRY(conv(p + ".conv2", e1, nullptr, out));
+    release(mark);
+    return 0;
+  }
+
+  // MixATb.forward (unet_attn_3d_cond_v3.py:175-190): FiLM on cat(x, emb) (applied to the two halves), conv, norm, SiLU,
+  // conv, + x
+  int mix_atb(const std::string& p, const T32& x, const T32& emb, const T32& out) {
+    const int C = x.C;
+    const float* fp = film + U->film_off.at(p + ".time_mlp.1");   // (scale + 1)[2C] | shift[2C]
+    const size_t mark = off;
+    T32 xf = like(x, C), ef = like(x, C), h = like(x, C), h2 = like(x, C);
+    FTB_TRY(normact(x, false, nullptr, fp, fp + 2 * C, U->film_rows, false, nullptr, xf));
+    FTB_TRY(normact(emb, false, nullptr, fp + C, fp + 3 * C, U->film_rows, false, nullptr, ef));
+    FTB_TRY(conv(p + ".conv1", xf, &ef, h));
+    FTB_TRY(normact(h, true, U->gains.at(p + ".norm.g").gs, nullptr, nullptr, 0, true, nullptr, h));
+    FTB_TRY(conv(p + ".conv2", h, nullptr, h2));
+    FTB_TRY(normact(h2, false, nullptr, nullptr, nullptr, 0, false, x.p, out));
+    tap(p, out);
+    release(mark);
+    return 0;
+  }
+
   int resample(const T32& in, const T32& out) {
     if (dry) return 0;
     U->launches += 1;
     return f32_trilinear(in.p, B, in.C, in.D, in.H, in.W, out.D, out.H, out.W, out.p, st);
   }
 
-  int run(const float* x, const float* t, float* y, int X, int Y, int Z) {
+  int run(const float* x, const float* t, float* y, int X, int Y, int Z, const float* atb = nullptr) {
     const ftb_unet_cfg& c = U->cfg;
     const int n = c.n_stages;
+    const bool cond = c.conditional != 0;
+    const int o = cond ? 2 : 0;
     auto sub = [&](const std::string& p, int k) { return p + "." + std::to_string(k); };
     U->taps32.clear();
     U->launches = 0;
@@ -244,37 +280,52 @@ struct FwdF32 {
     }
     T32 xin;
     xin.p = const_cast<float*>(x); xin.C = c.data_channels; xin.D = X; xin.H = Y; xin.W = Z;
+    T32 opened;
+    if (cond) {   // init_conv_ATb (:778); one conditioning volume per sample in this mode
+      T32 ain;
+      ain.p = const_cast<float*>(atb); ain.C = c.data_channels; ain.D = X; ain.H = Y; ain.W = Z;
+      opened = t32(c.data_channels, X, Y, Z);
+      FTB_TRY(conv("init_conv_ATb", ain, nullptr, opened));
+      tap("init_conv_ATb", opened);
+    }
+    const std::string init_name = cond ? "init_conv_x" : "init_conv";
     T32 r = t32(c.dim, X, Y, Z);
-    FTB_TRY(conv("init_conv", xin, nullptr, r));
-    tap("init_conv", r);
+    FTB_TRY(conv(init_name, xin, nullptr, r));
+    tap(init_name, r);
     T32 cur = r;
     std::vector<T32> skips;
     for (int i = 0; i < n; ++i) {
       const std::string p = "downs." + std::to_string(i);
       const int din = U->in_out[i].first, dout = U->in_out[i].second;
       T32 a1 = like(cur, din);
-      FTB_TRY(resnet(sub(p, 0), cur, nullptr, a1));
-      skips.push_back(a1);
-      T32 a3 = like(cur, din);          // second skip; a2 and the stage output live above it
+      T32 a3 = like(cur, din);          // second skip; temporaries and the stage output live above the two skips
       const size_t mark = off;
+      if (cond) {
+        T32 emb = like(cur, din), mixed = like(cur, din);
+        FTB_TRY(embed_atb(sub(p, 0), opened, emb));
+        FTB_TRY(mix_atb(sub(p, 1), cur, emb, mixed));
+        cur = mixed;
+      }
+      FTB_TRY(resnet(sub(p, o), cur, nullptr, a1));
+      skips.push_back(a1);
       T32 a2 = like(cur, din);
-      FTB_TRY(resnet(sub(p, 1), a1, nullptr, a2));
-      FTB_TRY(attention(sub(p, 2), a2, c.full_attn[i] != 0, a3));
+      FTB_TRY(resnet(sub(p, o + 1), a1, nullptr, a2));
+      FTB_TRY(attention(sub(p, o + 2), a2, c.full_attn[i] != 0, a3));
       skips.push_back(a3);
       release(mark);
       T32 a4;
       if (i >= n - 1) {
         a4 = like(a3, dout);
-        FTB_TRY(conv(sub(p, 3), a3, nullptr, a4));
+        FTB_TRY(conv(sub(p, o + 3), a3, nullptr, a4));
       } else {
         a4 = t32(dout, a3.D / 2, a3.H / 2, a3.W / 2);
         const size_t m2 = off;
         T32 ds = t32(din, a3.D / 2, a3.H / 2, a3.W / 2);
         FTB_TRY(resample(a3, ds));
-        FTB_TRY(conv(sub(p, 3) + ".conv", ds, nullptr, a4));
+        FTB_TRY(conv(sub(p, o + 3) + ".conv", ds, nullptr, a4));
         release(m2);
       }
-      tap(sub(p, 3), a4);
+      tap(sub(p, o + 3), a4);
       cur = a4;
     }
     {
@@ -294,20 +345,26 @@ struct FwdF32 {
       // stage output first (it outlives the stage's temporaries)
       T32 a4 = (i == n - 1) ? like(cur, din) : t32(din, cur.D * 2, cur.H * 2, cur.W * 2);
       const size_t mark = off;
+      if (cond) {
+        T32 emb = like(cur, dout), mixed = like(cur, dout);
+        FTB_TRY(embed_atb(sub(p, 0), opened, emb));
+        FTB_TRY(mix_atb(sub(p, 1), cur, emb, mixed));
+        cur = mixed;
+      }
       T32 a1 = like(cur, dout), a2 = like(cur, dout), a3 = like(cur, dout);
       T32 s = skips.back(); skips.pop_back();
-      FTB_TRY(resnet(sub(p, 0), cur, &s, a1));
+      FTB_TRY(resnet(sub(p, o), cur, &s, a1));
       s = skips.back(); skips.pop_back();
-      FTB_TRY(resnet(sub(p, 1), a1, &s, a2));
-      FTB_TRY(attention(sub(p, 2), a2, c.full_attn[n - 1 - i] != 0, a3));
+      FTB_TRY(resnet(sub(p, o + 1), a1, &s, a2));
+      FTB_TRY(attention(sub(p, o + 2), a2, c.full_attn[n - 1 - i] != 0, a3));
       if (i == n - 1) {
-        FTB_TRY(conv(sub(p, 3), a3, nullptr, a4));
+        FTB_TRY(conv(sub(p, o + 3), a3, nullptr, a4));
       } else {
         T32 us = t32(dout, a4.D, a4.H, a4.W);
         FTB_TRY(resample(a3, us));
-        FTB_TRY(conv(sub(p, 3) + ".conv", us, nullptr, a4));
+        FTB_TRY(conv(sub(p, o + 3) + ".conv", us, nullptr, a4));
       }
-      tap(sub(p, 3), a4);
+      tap(sub(p, o + 3), a4);
       release(mark);
       cur = a4;
     }

@@ -124,12 +124,10 @@ class Unet3D(nn.Module):
         else in fp32; <= 1e-4 rel-L2 of the reference with ``cudnn.allow_tf32=False``).  Inference only."""
         if precision not in ("bf16", "fp32"):
             raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
-        if precision == "fp32" and self._conditional:
-            raise NotImplementedError("the fp32 accuracy mode is implemented for the unconditional Unet3D only")
         self.precision = precision
         return self
 
-    def _forward_f32(self, xin, tin):
+    def _forward_f32(self, xin, tin, ain=None):
         B, _, X, Y, Z = xin.shape
         key = (str(xin.device), B, X, Y, Z)
         ws = self._workspace_f32.get(key)
@@ -142,9 +140,14 @@ class Unet3D(nn.Module):
             self._workspace_f32[key] = ws
         base = (ws.data_ptr() + 255) // 256 * 256
         out = torch.empty_like(xin)
-        _lib.check(_lib.lib.ftb_unet3d_forward_f32(
-            self._handle, _lib.ptr(xin), _lib.ptr(tin), _lib.ptr(out), B, X, Y, Z,
-            C.c_void_p(base), ws.numel() - (base - ws.data_ptr()), _lib.stream_ptr()))
+        if ain is not None:
+            _lib.check(_lib.lib.ftb_unet3d_cond_forward_f32(
+                self._handle, _lib.ptr(xin), _lib.ptr(ain), _lib.ptr(tin), _lib.ptr(out), B, X, Y, Z,
+                C.c_void_p(base), ws.numel() - (base - ws.data_ptr()), _lib.stream_ptr()))
+        else:
+            _lib.check(_lib.lib.ftb_unet3d_forward_f32(
+                self._handle, _lib.ptr(xin), _lib.ptr(tin), _lib.ptr(out), B, X, Y, Z,
+                C.c_void_p(base), ws.numel() - (base - ws.data_ptr()), _lib.stream_ptr()))
         self.last_launches = _lib.lib.ftb_unet3d_last_launches(self._handle)
         return out
 
@@ -436,6 +439,15 @@ class Unet3DCond(Unet3D):
             self._atb_key = None   # the training workspace replaces the sampling one
             tin = time.detach().to(device=x.device, dtype=torch.float32).contiguous()
             return UnetTrainFn.apply(self, self._f32c(x), tin, self._f32c(ATb), *self.parameters())
+        if self.precision == "fp32":
+            with torch.cuda.device(x.device):
+                ain = self._f32c(ATb)
+                if ain.shape[0] != B:     # the fp32 mode keeps one conditioning volume per sample
+                    ain = ain.expand(B, -1, -1, -1, -1).contiguous()
+                tin = time.detach().to(device=x.device, dtype=torch.float32).contiguous()
+                self._sync_params(x.device)
+                out = self._forward_f32(self._f32c(x), tin, ain)
+            return out if x.dtype == torch.float32 else out.to(x.dtype)
         with torch.cuda.device(x.device):
             xin = self._f32c(x)
             ain = self._f32c(ATb)

@@ -76,6 +76,9 @@ int ftb_unet3d_forward(ftb_unet* h, const float* x, const float* t, float* out, 
 size_t ftb_unet3d_f32_workspace_bytes(ftb_unet* h, int B, int X, int Y, int Z);
 int ftb_unet3d_forward_f32(ftb_unet* h, const float* x, const float* t, float* out, int B, int X, int Y, int Z,
                            void* workspace, size_t workspace_bytes, void* stream);
+/* conditional model in the fp32 mode: atb [B,C,X,Y,Z] (one conditioning volume per sample; nothing is cached) */
+int ftb_unet3d_cond_forward_f32(ftb_unet* h, const float* x, const float* atb, const float* t, float* out, int B,
+                                int X, int Y, int Z, void* workspace, size_t workspace_bytes, void* stream);
 /* after ftb_unet3d_forward_f32: dims[5] = (B, C, X, Y, Z) of a named intermediate; out (may be NULL) receives it */
 int ftb_unet3d_get_tap_f32(ftb_unet* h, const char* name, float* out, int* dims, void* stream);
 /* ---- conditional velocity field: replaces Unet3DCond.forward(x, ATb, time)
