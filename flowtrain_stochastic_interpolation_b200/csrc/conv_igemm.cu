@@ -930,6 +930,18 @@ int make_voxel_tmap(CUtensorMap* tm, const Act& a, int box_vox, int box_cg) {
   return 0;
 }
 
+// number of channel chunks (passes) one source of `cg` channel groups is cut into for a K^3 conv with N-wide tiles
+// (same rule as the planner below: equal chunks of an even divisor <= 8 groups (16 for K = 1) whose weight chunk of
+// one (kh, kw) position stays <= 56 KB); the planner accepts at most kMaxCC chunks over both sources
+int conv_chunk_count(int cg, int K, int N) {
+  const int cg_cap = K == 1 ? 16 : 8;
+  const uint32_t kstep_bytes = (uint32_t)K * N * 32;
+  for (int d = cg < cg_cap ? cg : cg_cap; d > 2; d -= 2)
+    if (cg % d == 0 && (uint32_t)(d / 2) * kstep_bytes <= 56u * 1024u) return cg / d;
+  return cg / 2;
+}
+int conv_max_chunks() { return kMaxCC; }
+
 int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const ConvEpilogue& e,
                Act& out, int out_cgoff, cudaStream_t st) {
   const Act& a0 = *s0.t;

@@ -12,8 +12,14 @@ namespace ftb_engine_detail {
 //   3*CP <= 512: ONE launch, sources (x_hi | x_lo) and x_hi again, weights [W_hi | W_hi | W_lo] along K — the three
 //                products share the TMEM accumulator and the fp32 output is written once;
 //   2*CP <= 512: (x_hi | x_lo) x [W_hi | W_hi], then x_hi x W_lo accumulated in place by the epilogue;
-//   else       : three launches of CP channels each.
-inline int f32_mode(int cp) { return 3 * cp <= 512 ? 3 : (2 * cp <= 512 ? 2 : 1); }
+//   else       : three launches of CP channels each (also when the K-extended input would need more channel-chunk
+//                passes than the conv planner accepts, e.g. the 5^3 192 -> 192 EmbedATb conv).
+inline int f32_mode(int cp, int k, int n) {
+  const int cg = cp / 8, lim = conv_max_chunks();
+  if (3 * cp <= 512 && conv_chunk_count(2 * cg, k, n) + conv_chunk_count(cg, k, n) <= lim) return 3;
+  if (2 * cp <= 512 && conv_chunk_count(2 * cg, k, n) <= lim) return 2;
+  return 1;
+}
 
 int finalize_f32(ftb_unet* U, cudaStream_t st) {
   const float* base0 = U->params.empty() ? nullptr : U->params[0].dev;
@@ -21,7 +27,7 @@ int finalize_f32(ftb_unet* U, cudaStream_t st) {
     std::vector<PackJob> jobs;
     for (auto& kv : U->convs) {
       const ConvLayer& cl = kv.second;
-      const int cp = round_up(cl.cin, 16), mode = f32_mode(cp);
+      const int cp = round_up(cl.cin, 16), mode = f32_mode(cp, cl.k, cl.n_tile);
       const size_t elems = (size_t)cl.ntiles * cl.k * cl.k * cl.k * cp * cl.n_tile;
       std::pair<bf16*, bf16*>& pk = U->f32packs[kv.first];
       if (!pk.first) {
@@ -121,7 +127,7 @@ struct FwdF32 {
       e.out_f32_c = cl.cout;
       Act dummy = sp;   // spatial dims only: the epilogue writes NCDHW fp32
       const ConvSrc hi{&sp, 0, cp / 8}, lo{&sp, cp / 8, cp / 8}, hilo{&sp, 0, 2 * cp / 8};
-      const int mode = f32_mode(cp);
+      const int mode = f32_mode(cp, cl.k, cl.n_tile);
       e.bias = cl.bname.empty() ? nullptr : cl.bias;
       w.w = pk.first;
       if (mode == 3) {

@@ -72,6 +72,9 @@ int conv_dispatch(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, co
                   Act& out, int out_cgoff, cudaStream_t st);
 
 int conv_debug_read(long long* host, int n);
+// planner facts the fp32 mode needs to choose its launch variant
+int conv_chunk_count(int cg, int K, int N);
+int conv_max_chunks();
 
 // 3-D TMA view of a blocked activation as (8 channels, voxels, B*CG); box = (8, box_vox, box_cg):
 // lands in shared memory as [cg][voxel][8], the no-swizzle MN-major UMMA operand layout.
