@@ -1,10 +1,10 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "unet3d or trilinear or conv" 2>&1 | tail -5 > gpurun_out/pytest_ab.log
-tail -5 gpurun_out/pytest_ab.log
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_train.py -m gpu -x -q -k "trilinear or unet3d_matches or full_arch_grads_32 or 64_full" 2>&1 | tail -4
 for v in 0 1; do
-  if [ $v = 1 ]; then export FTB_NO_PDL=1; else unset FTB_NO_PDL; fi
-  timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline --no-train > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
-  echo "NO_PDL=$v rc=$?"; cut -c1-400 gpurun_out/ab_$v.json; tail -2 gpurun_out/ab_$v.err
+  if [ $v = 1 ]; then export FTB_TRILINEAR_DIRECT=1; else unset FTB_TRILINEAR_DIRECT; fi
+  timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline --no-extras > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
+  echo "DIRECT=$v rc=$?"; python -c "
+import json; d=json.load(open('gpurun_out/ab_$v.json')); print(d['value'], d['ms_per_step'], d['train']['ms_per_step'])"
 done
