@@ -282,6 +282,30 @@ def test_unet3d_cond_grads_vs_oracle_and_golden(ftb, dev, name):
             assert abs(float(gr.double().norm()) - want) <= 5e-2 * want, k
 
 
+def test_cond_grads_ragged_volume_batch3(ftb, dev):
+    """Conditional backward on a non-cubic volume (8 x 24 x 16, B = 3: EmbedATb trilinear to a ragged half scale, 5^3
+    weight gradients over partial tiles) vs the oracle's autograd."""
+    from oracle import synth, task
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = synth.make_cfg(dim=32, dim_mults=(1, 2), data_channels=15, time_resolution=64, time_bandwidth=100.0,
+                         attn_heads=2, attn_dim_head=16, dropout=0.0)
+    params = synth.synth_unet3d_cond_params(cfg, 31)
+    net = ftb.Unet3DCond(**cfg).to(dev)
+    net.load_state_dict(params)
+    shape = (3, 15, 8, 24, 16)
+    xt, vt = synth.synth_input(shape, 41, "xt").to(dev), synth.synth_input(shape, 42, "vt").to(dev)
+    atb = synth.synth_atb(shape, 44).to(dev)
+    t = synth.synth_times(3, 43).to(dev)
+    loss_o, vhat_o, grads_o = task.cond_training_grads({k: v.to(dev) for k, v in params.items()}, cfg, xt, atb, t, vt)
+    net.train()
+    vhat = net(xt, atb, t)
+    lo = torch.nn.functional.mse_loss(vt, vhat) / torch.nn.functional.mse_loss(vt, torch.zeros_like(vt))
+    lo.backward()
+    assert rel(vhat.detach(), vhat_o) <= 2e-2
+    _check_grads(grads_o, {k: p.grad.detach() for k, p in net.named_parameters()}, "cond small arch 8x24x16 B=3")
+
+
 def test_train_forward_matches_inference_forward(ftb, dev):
     """The unfused train-mode forward and the fused inference forward are the same function."""
     cfg, params, net, shape, mg = _setup(ftb, dev, "full")
