@@ -72,6 +72,10 @@ _SIGS = {
     "ftb_unet3d_tap_channels": (_i, [_vp, C.c_char_p, _ip, _ip, _ip, _ip]),
     "ftb_unet3d_get_tap": (_i, [_vp, C.c_char_p, _vp, _vp]),
     "ftb_unet3d_last_launches": (_i, [_vp]),
+    "ftb_ode_lincomb": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _vp]),
+    "ftb_ode_error_ratio": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _i64, _vp, _vp]),
+    "ftb_ode_scaled_sumsq": (_i, [_vp, _vp, _vp, _f, _f, _i64, _vp, _vp]),
+    "ftb_ode_dense_eval": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i64, _vp]),
     "ftb_cond_frontend": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "ftb_cond_loss_accumulate": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp, _vp]),
     "ftb_cond_loss_grad": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp, _f, _f, _vp, _vp]),

@@ -1082,6 +1082,26 @@ int ftb_decode(const float* x, const float* en, int64_t* out, int B, int E, int 
   FTB_CHECK(x && en && out, "null argument");
   return decode_argmax(x, en, reinterpret_cast<long long*>(out), B, E, ncat, n, (cudaStream_t)stream);
 }
+int ftb_ode_lincomb(float* out, const float* y0, const float* const* k, const double* coef, int nk, int64_t n,
+                    void* stream) {
+  FTB_CHECK(out && y0, "null argument");
+  return ode_lincomb(out, y0, k, coef, nk, n, (cudaStream_t)stream);
+}
+int ftb_ode_error_ratio(const float* y0, const float* y1, const float* const* k, const double* coef, int nk, float rtol,
+                        float atol, int64_t n, double* acc, void* stream) {
+  FTB_CHECK(y0 && y1 && acc, "null argument");
+  return ode_error_ratio(y0, y1, k, coef, nk, rtol, atol, n, acc, (cudaStream_t)stream);
+}
+int ftb_ode_scaled_sumsq(const float* a1, const float* a2, const float* y, float rtol, float atol, int64_t n,
+                         double* acc, void* stream) {
+  FTB_CHECK(a1 && y && acc, "null argument");
+  return ode_scaled_sumsq(a1, a2, y, rtol, atol, n, acc, (cudaStream_t)stream);
+}
+int ftb_ode_dense_eval(float* out, const float* y0, const float* y1, const float* ymid, const float* f0,
+                       const float* f1, double dt, double x, int64_t n, void* stream) {
+  FTB_CHECK(out && y0 && y1 && ymid && f0 && f1, "null argument");
+  return ode_dense_eval(out, y0, y1, ymid, f0, f1, dt, x, n, (cudaStream_t)stream);
+}
 int ftb_cond_frontend(const int64_t* cats, const int32_t* bores, const int32_t* n_bores, int max_bores, const float* w,
                       int B, int E, int ncat, int shift, int X, int Y, int Z, int surface, uint8_t* mask, float* x1,
                       float* atb, void* stream) {

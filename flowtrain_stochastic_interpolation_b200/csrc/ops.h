@@ -229,6 +229,15 @@ int denoise_drift(float* out, const float* x, const float* eta, const float* noi
                   float ad, float bd, float eps, int use_sde, long long n, cudaStream_t st);
 int decode_argmax(const float* x, const float* en, long long* out, int B, int E, int ncat,
                   long long n, cudaStream_t st);
+// ---- adaptive-step Runge-Kutta passes (ode_adaptive.cu); k: nk device pointers, coef: nk host doubles (already * dt)
+int ode_lincomb(float* out, const float* y0, const float* const* k, const double* coef, int nk, long long n,
+                cudaStream_t st);
+int ode_error_ratio(const float* y0, const float* y1, const float* const* k, const double* coef, int nk, float rtol,
+                    float atol, long long n, double* acc, cudaStream_t st);
+int ode_scaled_sumsq(const float* a1, const float* a2, const float* y, float rtol, float atol, long long n, double* acc,
+                     cudaStream_t st);
+int ode_dense_eval(float* out, const float* y0, const float* y1, const float* ymid, const float* f0, const float* f1,
+                   double dt, double x, long long n, cudaStream_t st);
 // ---- conditional project / ensemble kernels (cond_ops.cu, elementwise.cu)
 // surface + borehole mask, X1 = W[cat + shift], ATb = X1 * mask in one pass; bores [B][max_b][2] int32 (x, y),
 // nb [B] counts; mask (u8 [B][X*Y*Z]), x1, atb may each be null

@@ -7,8 +7,10 @@ zeroes the velocity on the masked trailing dims (:71-73), and the eq-6.7 drift /
 :138-143 / :205-216.
 
 Difference, stated once: the reference hands ``ode_func`` to torchdiffeq's ADAPTIVE dopri5 /
-adaptive_heun.  This build integrates on the FIXED grid above with ``method`` in
-{"euler", "heun", "rk4"} (torchdiffeq fixed-grid convention, one step per grid interval); the
+adaptive_heun.  The default here integrates on the FIXED grid above with ``method`` in
+{"euler", "heun", "rk4"} (torchdiffeq fixed-grid convention, one step per grid interval);
+``method="dopri5"`` / ``"adaptive_heun"`` run a restatement of torchdiffeq's adaptive loop
+(``integrate_adaptive``: one host round trip per attempted step for the error ratio).  The
 stage combinations run as single fused kernels (ftb_ode_axpy / heun_combine / rk4_combine) on the
 fp32 state, and no host synchronisation happens inside the loop (the reference does one
 ``t.item()`` device->host sync per evaluation).  ``return_trajectory=False`` keeps only the end
@@ -22,6 +24,25 @@ from . import _lib
 from .interpolation import BaseInterpolant
 
 METHODS = ("euler", "heun", "rk4")
+ADAPTIVE_METHODS = ("dopri5", "adaptive_heun")
+
+# Butcher tableaus as torchdiffeq defines them (dopri5.py, adaptive_heun.py): alpha, beta rows, c_sol, c_error, c_mid
+_DOPRI5 = dict(
+    order=5,
+    alpha=[1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0, 1.0],
+    beta=[[1 / 5],
+          [3 / 40, 9 / 40],
+          [44 / 45, -56 / 15, 32 / 9],
+          [19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729],
+          [9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656],
+          [35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84]],
+    c_sol=[35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84, 0],
+    c_error=[35 / 384 - 1951 / 21600, 0, 500 / 1113 - 22642 / 50085, 125 / 192 - 451 / 720,
+             -2187 / 6784 - -12231 / 42400, 11 / 84 - 649 / 6300, -1.0 / 60.0],
+    c_mid=[6025192743 / 30085553152 / 2, 0, 51252292925 / 65400821598 / 2, -2691868925 / 45128329728 / 2,
+           187940372067 / 1594534317056 / 2, -1776094331 / 19743644256 / 2, 11237099 / 235043384 / 2],
+)
+_ADAPTIVE_HEUN = dict(order=2, alpha=[1.0], beta=[[1.0]], c_sol=[0.5, 0.5], c_error=[0.5, -0.5], c_mid=[0.5, 0.0])
 
 
 def _flat(x):
@@ -108,9 +129,132 @@ def integrate_fixed(func, X0, t0, tf, n_steps, method="euler", return_trajectory
     return traj if traj is not None else x
 
 
+def _ptr_array(tensors):
+    import ctypes as C
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+def _dbl_array(vals):
+    import ctypes as C
+    return (C.c_double * len(vals))(*[float(v) for v in vals])
+
+
+def _lincomb(out, y0, ks, coefs):
+    with torch.cuda.device(y0.device):
+        _lib.check(_lib.lib.ftb_ode_lincomb(_lib.ptr(out), _lib.ptr(y0), _ptr_array(ks), _dbl_array(coefs), len(ks),
+                                            y0.numel(), _lib.stream_ptr()))
+    return out
+
+
+def integrate_adaptive(func, X0, t0, tf, n_steps, method="dopri5", rtol=1e-6, atol=1e-6, return_trajectory=True,
+                       max_num_steps=100000, stats=None):
+    """torchdiffeq's adaptive Runge-Kutta loop (rk_common.RKAdaptiveStepsizeODESolver of torchdiffeq 0.2.x, the
+    un-vendored dependency behind solvers.py:77, :148, :220-222) restated: initial step from ``_select_initial_step``,
+    steps accepted when the RMS of error / (atol + rtol max(|y0|, |y1|)) is <= 1, step factor
+    ``min(10, max(0.9 / ratio^(1/order), 0.2))`` (dfactor 1 after an accepted step), first-same-as-last reuse of the last
+    stage, and the output grid ``linspace(t0, tf, n_steps)`` evaluated with the quartic dense-output interpolant.
+    Time-like values are host doubles (torchdiffeq keeps them in float64); the state passes are CUDA kernels
+    (ftb_ode_lincomb / error_ratio / dense_eval) and ONE scalar (the error ratio) returns to the host per attempted
+    step.  ``func(t, x, eval_index) -> dx/dt``.  Parity unpinned (torchdiffeq is not installed here)."""
+    if method not in ADAPTIVE_METHODS:
+        raise ValueError(f"method must be one of {ADAPTIVE_METHODS}, got {method!r}")
+    if not X0.is_cuda:
+        raise RuntimeError("the samplers run on CUDA only (no CPU fallback)")
+    tab = _DOPRI5 if method == "dopri5" else _ADAPTIVE_HEUN
+    order = tab["order"]
+    y0 = _flat(X0).clone()
+    n = y0.numel()
+    dev = y0.device
+    lib = _lib.lib
+    # the reference builds the output grid in fp32 (solvers.py:59); torchdiffeq then carries time in float64
+    grid = [float(v) for v in torch.linspace(t0, tf, n_steps)] if n_steps > 1 else [float(t0)]
+    acc = torch.zeros(1, dtype=torch.float64, device=dev)
+    n_eval = 0
+
+    def norm_of(a1, a2, y):   # rms_norm((a1 - a2) / (atol + rtol |y|))
+        acc.zero_()
+        with torch.cuda.device(dev):
+            _lib.check(lib.ftb_ode_scaled_sumsq(_lib.ptr(a1), _lib.ptr(a2), _lib.ptr(y), float(rtol), float(atol), n,
+                                                _lib.ptr(acc), _lib.stream_ptr()))
+        return (acc.item() / n) ** 0.5
+
+    # ---- _before_integrate: f0 and the first step (_select_initial_step with order - 1)
+    f0 = func(grid[0], y0, n_eval); n_eval += 1
+    d0, d1 = norm_of(y0, None, y0), norm_of(f0, None, y0)
+    h0 = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
+    y1 = _lincomb(torch.empty_like(y0), y0, [f0], [h0])
+    f1 = func(grid[0] + h0, y1, n_eval); n_eval += 1
+    d2 = norm_of(f1, f0, y0) / h0
+    h1 = max(1e-6, h0 * 1e-3) if (d1 <= 1e-15 and d2 <= 1e-15) else (0.01 / max(d1, d2)) ** (1.0 / float(order))
+    dt = min(100 * h0, h1)
+    t_cur = grid[0]
+    traj = torch.empty((len(grid),) + tuple(y0.shape), dtype=torch.float32, device=dev) if return_trajectory else None
+    if traj is not None:
+        traj[0].copy_(y0)
+    interp = None   # (t0, t1, y0, y1, ymid, f0, f1) of the last accepted step
+    accepted = rejected = 0
+    nstage = len(tab["alpha"])
+    for gi in range(1, len(grid)):
+        t_out = grid[gi]
+        while t_out > t_cur:
+            if accepted + rejected >= max_num_steps:
+                raise RuntimeError(f"max_num_steps exceeded ({max_num_steps})")
+            # ---- _runge_kutta_step
+            t1 = t_cur + dt
+            ks = [f0]
+            for i in range(nstage):
+                ti = t1 if tab["alpha"][i] == 1.0 else t_cur + tab["alpha"][i] * dt
+                yi = _lincomb(torch.empty_like(y0), y0, ks, [b * dt for b in tab["beta"][i]])
+                ks.append(func(ti, yi, n_eval)); n_eval += 1
+            fsal = tab["c_sol"][-1] == 0 and list(tab["c_sol"][:-1]) == list(tab["beta"][-1])
+            y1 = yi if fsal else _lincomb(torch.empty_like(y0), y0, ks, [c * dt for c in tab["c_sol"]])
+            f1 = ks[-1]
+            acc.zero_()
+            with torch.cuda.device(dev):
+                _lib.check(lib.ftb_ode_error_ratio(_lib.ptr(y0), _lib.ptr(y1), _ptr_array(ks),
+                                                   _dbl_array([c * dt for c in tab["c_error"]]), len(ks), float(rtol),
+                                                   float(atol), n, _lib.ptr(acc), _lib.stream_ptr()))
+            ratio = (acc.item() / n) ** 0.5
+            if ratio != ratio:
+                raise FloatingPointError("adaptive solver: non-finite error estimate")
+            if ratio <= 1.0:   # accept
+                ymid = _lincomb(torch.empty_like(y0), y0, ks, [c * dt for c in tab["c_mid"]])
+                interp = (t_cur, t1, y0, y1, ymid, f0, f1, dt)
+                y0, f0, t_cur = y1, f1, t1
+                accepted += 1
+            else:
+                rejected += 1
+            # ---- _optimal_step_size
+            if ratio == 0.0:
+                dt = dt * 10.0
+            else:
+                dfactor = 1.0 if ratio < 1.0 else 0.2
+                dt = dt * min(10.0, max(0.9 / ratio ** (1.0 / order), dfactor))
+        ta, tb, ya, yb, ym, fa, fb, hdt = interp
+        out = traj[gi] if traj is not None else torch.empty_like(y0)
+        with torch.cuda.device(dev):
+            _lib.check(lib.ftb_ode_dense_eval(_lib.ptr(out), _lib.ptr(ya), _lib.ptr(yb), _lib.ptr(ym), _lib.ptr(fa),
+                                              _lib.ptr(fb), hdt, (t_out - ta) / (tb - ta), n, _lib.stream_ptr()))
+        last = out
+    if stats is not None:
+        stats.update(accepted=accepted, rejected=rejected, evals=n_eval)
+    return traj if traj is not None else (last if len(grid) > 1 else y0)
+
+
+def _integrate(func, X0, t0, tf, n_steps, method, return_trajectory, rtol, atol, stats=None):
+    if method in ADAPTIVE_METHODS:
+        return integrate_adaptive(func, X0, t0, tf, n_steps, method, rtol, atol, return_trajectory, stats=stats)
+    return integrate_fixed(func, X0, t0, tf, n_steps, method, return_trajectory)
+
+
 class ODEFlowSolver:
-    """Flow ODE dx/dt = model(x, t) — reference ODEFlowSolver (:14-77); fixed grid, see module doc.
-    ``atol``/``rtol`` are accepted for signature compatibility and ignored by the fixed-grid methods."""
+    """Flow ODE dx/dt = model(x, t) — reference ODEFlowSolver (:14-77).  ``method`` "euler" | "heun" | "rk4" integrate
+    on the fixed output grid (see module doc); "dopri5" / "adaptive_heun" are the reference's adaptive steppers
+    (``atol`` / ``rtol`` as in :35) — use them with ``model.set_precision("fp32")``: the bf16 velocity field's own noise
+    (~5e-3) is far above the reference's 1e-6 tolerances and would drive the step size to the floor."""
 
     def __init__(self, model, atol=1e-6, rtol=1e-6, method="euler"):
         self.model = model
@@ -130,7 +274,8 @@ class ODEFlowSolver:
                 dxdt = _flat(self.model(XT, tbuf))
                 return _zero_frozen(dxdt, mask)
 
-        return integrate_fixed(ode_func, X0, t0, tf, n_steps, self.method, return_trajectory)
+        return _integrate(ode_func, X0, t0, tf, n_steps, self.method, return_trajectory, self.rtol, self.atol,
+                          getattr(self, "stats", None))
 
 
 class ODEOneSidedDenoisingSolver:
@@ -167,7 +312,7 @@ class ODEOneSidedDenoisingSolver:
                 eta = _flat(self.model(XT, tbuf))
                 return self._drift(t, XT, eta)
 
-        return integrate_fixed(ode_func, X0, t0, tf, n_steps, self.method, return_trajectory)
+        return _integrate(ode_func, X0, t0, tf, n_steps, self.method, return_trajectory, self.rtol, self.atol)
 
 
 class SDEOneSidedDenoisingSolver(ODEOneSidedDenoisingSolver):
@@ -199,7 +344,7 @@ class SDEOneSidedDenoisingSolver(ODEOneSidedDenoisingSolver):
                 z = self.noise(i) if self.noise is not None else torch.randn_like(XT)
                 return self._drift(t, XT, eta, _flat(z).to(XT.device), eps)
 
-        return integrate_fixed(ode_func, X0, t0, tf, n_steps, self.method, return_trajectory)
+        return _integrate(ode_func, X0, t0, tf, n_steps, self.method, return_trajectory, self.rtol, self.atol)
 
 
 def odeSol_RK4(x0, model, nsteps=100, Tf=1.0):
@@ -225,4 +370,4 @@ def odeSol_RK4(x0, model, nsteps=100, Tf=1.0):
 
 
 __all__ = ["ODEFlowSolver", "ODEOneSidedDenoisingSolver", "SDEOneSidedDenoisingSolver", "odeSol_RK4",
-           "integrate_fixed"]
+           "integrate_fixed", "integrate_adaptive"]

@@ -114,6 +114,23 @@ int ftb_ode_heun_combine(float* out, const float* x, const float* k1, const floa
                          int64_t n, void* stream);
 int ftb_ode_rk4_combine(float* out, const float* x, const float* k1, const float* k2, const float* k3,
                         const float* k4, double h, int64_t n, void* stream);
+/* ---- adaptive-step Runge-Kutta (torchdiffeq's dopri5 / adaptive_heun behind ODEFlowSolver & co, solvers.py:77, :148,
+ *      :220-222; torchdiffeq >=0.2.5,<0.3 is an un-vendored dependency: restated from its published algorithm, parity
+ *      unpinned).  The step controller is host code; these are the passes over the fp32 state.  k: nk host-array of
+ *      device pointers (stage derivatives; a pointer may be NULL where its weight is 0), coef: nk host doubles
+ *      (tableau weight * dt).  n must be a multiple of 4.
+ *   lincomb:      out = y0 + sum_j coef[j] k[j]
+ *   error_ratio:  acc[0] += sum ((sum_j coef[j] k[j]) / (atol + rtol max(|y0|, |y1|)))^2      (device double)
+ *   scaled_sumsq: acc[0] += sum ((a1 - a2) / (atol + rtol |y|))^2   (a2 may be NULL; initial-step heuristic)
+ *   dense_eval:   out = quartic interpolant through (y0, ymid, y1) with end slopes (f0, f1) at x in [0, 1] */
+int ftb_ode_lincomb(float* out, const float* y0, const float* const* k, const double* coef, int nk, int64_t n,
+                    void* stream);
+int ftb_ode_error_ratio(const float* y0, const float* y1, const float* const* k, const double* coef, int nk, float rtol,
+                        float atol, int64_t n, double* acc, void* stream);
+int ftb_ode_scaled_sumsq(const float* a1, const float* a2, const float* y, float rtol, float atol, int64_t n,
+                         double* acc, void* stream);
+int ftb_ode_dense_eval(float* out, const float* y0, const float* y1, const float* ymid, const float* f0,
+                       const float* f1, double dt, double x, int64_t n, void* stream);
 /* eq. 6.7 drift from a denoiser eta (solvers.py:130-143); SDE term (:205-216) when use_sde */
 int ftb_denoise_drift(float* out, const float* x, const float* eta, const float* noise, float alpha,
                       float beta, float alpha_dot, float beta_dot, float eps, int use_sde, int64_t n,

@@ -288,6 +288,30 @@ def test_ensemble_statistics_closed_form():
     assert em.view(-1)[0].item() == -1 and em.view(-1)[1].item() == ent.view(-1)[1].item()
 
 
+def test_adaptive_rk_restatement_against_scipy_and_closed_form():
+    """The restated torchdiffeq loop (oracle/solvers.odeint_adaptive; parity unpinned: torchdiffeq is not installed) on
+    problems with known answers: linear decay (closed form), a nonlinear system against scipy's independent
+    Dormand-Prince implementation, dense output on a non-uniform grid, and the adaptive_heun tableau."""
+    from scipy.integrate import solve_ivp
+    from oracle import solvers as osolv
+    y0 = torch.tensor([1.0, -2.0, 0.5], dtype=torch.float64)
+    t = torch.tensor([0.0, 0.13, 0.5, 0.51, 1.0], dtype=torch.float64)
+    st = {}
+    y = osolv.odeint_adaptive(lambda tt, yy: -2.0 * yy, y0, t, "dopri5", rtol=1e-8, atol=1e-10, stats=st)
+    want = y0[None] * torch.exp(-2.0 * t)[:, None]
+    assert (y - want).abs().max().item() < 1e-7
+    assert st["accepted"] >= 3
+
+    def f(tt, yy):   # a stiff-ish nonlinear oscillator
+        return torch.stack((yy[1], -yy[0] - 0.3 * yy[1] * (yy[0] ** 2 - 1.0), torch.sin(3.0 * tt + yy[2])))
+    y = osolv.odeint_adaptive(f, y0, t, "dopri5", rtol=1e-8, atol=1e-10)
+    ref = solve_ivp(lambda tt, yy: f(tt, torch.from_numpy(yy)).numpy(), (0.0, 1.0), y0.numpy(), method="DOP853",
+                    t_eval=t.numpy(), rtol=1e-12, atol=1e-13).y.T
+    assert np.abs(y.numpy() - ref).max() < 5e-7
+    y2 = osolv.odeint_adaptive(f, y0, t, "adaptive_heun", rtol=1e-6, atol=1e-8)
+    assert np.abs(y2.numpy() - ref).max() < 2e-4
+
+
 def test_adam_reference_matches_torch():
     torch.manual_seed(0)
     p0 = torch.randn(1000)
