@@ -93,6 +93,7 @@ struct IgemmParams {
   float drop_p;                // training: dropout after the activation
   unsigned long long drop_key;
   int f32_accum;               // fp32 mode: out_f32 += instead of = (the hi/lo operand products of one conv)
+  long long w_tile_stride;     // elements between the packed weights of consecutive N tiles (blockIdx.y = tile)
 };
 
 struct ItemCoord {
@@ -123,6 +124,7 @@ struct EpiCtx {
   int b;                           // sample index (dropout mask key)
   const bf16* res_b;               // residual base of sample b (or null)
   float* f32_b;                    // NCDHW fp32 output base of sample b (or null)
+  int f32_lim;                     // channels of this N tile that exist in the fp32 output
   size_t cgs;                      // voxels per channel-group plane (D*H*W)
   float ssq;                       // running sum of squares of this voxel's stored outputs
   bool valid;
@@ -178,13 +180,13 @@ __device__ __forceinline__ void epi_store16(const IgemmParams& p, EpiCtx& ec, in
     if (kTrain && p.f32_accum) {   // all 16 loads in flight before the first store
       float old[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) old[j] = (c0 + j < p.out_f32_c) ? __ldcg(o + (size_t)j * ec.cgs) : 0.f;
+      for (int j = 0; j < 16; ++j) old[j] = (c0 + j < ec.f32_lim) ? __ldcg(o + (size_t)j * ec.cgs) : 0.f;
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] += old[j];
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j)
-      if (c0 + j < p.out_f32_c) o[(size_t)j * ec.cgs] = v[j];
+      if (c0 + j < ec.f32_lim) o[(size_t)j * ec.cgs] = v[j];
     return;
   }
   bf16* dst = ec.out_b + ((size_t)(p.out_cgoff + (c0 >> 3)) * ec.cgs + vox) * 8;
@@ -568,7 +570,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
               if (++pslot == (uint32_t)p.nslot) { pslot = 0; pphase ^= 1; }
             }
             if (!p.w_resident || !w_loaded) {
-              const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack + (long long)c.b * p.w_batch_stride) +
+              const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack + (long long)blockIdx.y * p.w_tile_stride +
+                                                                   (long long)c.b * p.w_batch_stride) +
                                     (size_t)p.cc_ks0[cc] * p.kstep_bytes;
               const uint32_t wbytes = (uint32_t)p.cc_ks[cc] * p.kstep_bytes;
               for (int t = 0; t < p.taps; ++t) {
@@ -778,6 +781,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     EpiCtx ec;
     ec.bias = par; ec.mul = par + kMaxN; ec.add = par + 2 * kMaxN;
     ec.cgs = cgs;
+    const int tile_c0 = (int)blockIdx.y * p.N;
     uint32_t gctr = 0;
     int cur_b = -1;
     long long e_wait = 0, e_t0 = clock64();
@@ -790,20 +794,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
         // (bias, mul, add) of sample b; without a norm the bias folds into the affine part
         named_bar_sync(1 + half, 128);
         for (int ch = tid_h; ch < p.N; ch += 128) {
-          float bi = p.bias ? __ldg(p.bias + ch) : 0.f;
-          const float mu = p.mul ? __ldg(p.mul + (size_t)c.b * p.mul_stride + ch) : 1.f;
-          float ad = p.add ? __ldg(p.add + (size_t)c.b * p.add_stride + ch) : 0.f;
+          const int cht = tile_c0 + ch;   // channel within the whole layer (blockIdx.y = N tile)
+          float bi = p.bias ? __ldg(p.bias + cht) : 0.f;
+          const float mu = p.mul ? __ldg(p.mul + (size_t)c.b * p.mul_stride + cht) : 1.f;
+          float ad = p.add ? __ldg(p.add + (size_t)c.b * p.add_stride + cht) : 0.f;
           if (!p.norm) { ad = fmaf(bi, mu, ad); bi = 0.f; }
           par[ch] = bi; par[kMaxN + ch] = mu; par[2 * kMaxN + ch] = ad;
         }
         named_bar_sync(1 + half, 128);
         cur_b = c.b;
       }
-      ec.out_b = p.out + (size_t)c.b * p.out_cgtot * cgs * 8;
-      ec.u_b = p.u_out ? p.u_out + (size_t)c.b * p.out_cgtot * cgs * 8 : nullptr;
+      // the N tile's channel-group offset is folded into the per-sample base pointers
+      const size_t tile_cg = (size_t)(tile_c0 >> 3) * cgs * 8;
+      ec.out_b = p.out + (size_t)c.b * p.out_cgtot * cgs * 8 + tile_cg;
+      ec.u_b = p.u_out ? p.u_out + (size_t)c.b * p.out_cgtot * cgs * 8 + tile_cg : nullptr;
       ec.b = c.b;
-      ec.res_b = p.resid ? p.resid + (size_t)c.b * p.resid_cgtot * cgs * 8 : nullptr;
-      ec.f32_b = p.out_f32 ? p.out_f32 + (size_t)c.b * p.out_f32_cs * cgs : nullptr;
+      ec.res_b = p.resid ? p.resid + (size_t)c.b * p.resid_cgtot * cgs * 8 + tile_cg : nullptr;
+      ec.f32_b = p.out_f32 ? p.out_f32 + ((size_t)c.b * p.out_f32_cs + tile_c0) * cgs : nullptr;
+      ec.f32_lim = p.out_f32_c - tile_c0;
       for (int g = 0; g < ngroups; ++g, ++gctr) {
         const int nze = min(p.NZ, c.lz - g * p.NZ);
         const uint32_t ab = gctr & 1;
@@ -837,7 +845,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
             rs = 1.f / fmaxf(sqrtf(ss0 + ss1), 1e-12f);
           }
           ec.ssq = 0.f;
-          if (p.flags & F_QSOFTMAX) {
+          if ((p.flags & F_QSOFTMAX) && blockIdx.y == 0) {   // q softmax on the first N tile (q | k | v)
             if (p.q_dh == 32) epi_qsoftmax<32>(p, ec, trow, vox, rs);
             else epi_qsoftmax<16>(p, ec, trow, vox, rs);
           } else if (p.norm) {
@@ -1091,6 +1099,10 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   FTB_CHECK(fits, "conv: one plane window + weights exceed shared memory (Cin too large)");
   w_region = (size_t)p.wslot * p.wchunk_bytes;
   const int cols = a0.B * p.nHt * p.nWt;
+  // Tiny volumes (4^3, 8^3 per sample): with NZ planes per group there are fewer work items than half the SMs and each
+  // CTA runs a long serial MMA chain; trade depth-tap stacking for parallelism until the launch fills half the GPU.
+  if (getenv("FTB_NO_NZ_SPREAD") == nullptr)
+    while (p.NZ > 1 && (long long)cols * cdiv(p.Dext, p.NZ) * w.ntiles < sms / 2) --p.NZ;
   int nslot = (int)((kSmemLimit - fixed - w_region) / p.slot_stride);
   nslot = nslot > kMaxSlots ? kMaxSlots : nslot;
   p.nslot = nslot;
@@ -1174,45 +1186,43 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
     fprintf(stderr, "conv plan: K%d cin %d(+%d) N%d @%dx%dx%d B%d -> ncc %d NZ %d iss %d wslot %d%s nslot %d LZ %d TH %d items %d smem %u\n",
             p.K, p.cg0 * 8, p.cg1 * 8, p.N, p.D, p.H, p.W, p.B, p.ncc, p.NZ, p.n_iss, p.wslot,
             p.w_resident ? "(resident)" : "", p.nslot, p.LZ, p.TH, p.n_items, smem_bytes);
-  for (int nt = 0; nt < w.ntiles; ++nt) {
-    IgemmParams q = p;
-    q.wpack = w.w + (size_t)nt * w.tile_elems();
-    q.bias = e.bias ? e.bias + (size_t)nt * w.n : nullptr;
-    q.out_cgoff = out_cgoff + nt * (w.n / 8);
-    if (q.out_f32) {   // N tile nt of an fp32 output: channels [nt*n, ...) of every sample
-      q.out_f32 = p.out_f32 + (size_t)nt * w.n * a0.voxels();
-      q.out_f32_c = p.out_f32_c - nt * w.n;
-    }
-    q.flags = (e.silu ? F_SILU : 0) | ((e.q_softmax_heads && nt == 0) ? F_QSOFTMAX : 0);
-    if (!(q.flags & F_QSOFTMAX) && !q.norm && !q.bias && !q.mul && !q.add && !e.silu && !q.resid && !q.out_f32 && !q.ss_out)
-      q.flags |= F_PLAIN;
-    int prof = -1;
-    if (prof_enabled()) {
-      // algorithmic work of this launch: real (unpadded) channel counts
-      const double vox = (double)a0.B * a0.voxels();
-      const double cin = w.cin_real > 0 ? w.cin_real : w.cin;
-      const double cout_all = w.cout_real > 0 ? w.cout_real : (double)w.n * w.ntiles;
-      const double cout = cout_all / w.ntiles;
-      const double flops = 2.0 * vox * cin * cout * p.K * p.K * (w.ksize_w == 1 && p.K > 1 ? 1 : p.K);   // cin_real of an unfolded conv already counts the W taps
-      const double bytes = vox * (cin + cout) * 2.0;  // read input once, write output once (bf16)
-      prof = prof_begin(st, flops, bytes, w.ksize > 1 ? 0 : 1);
-    }
-    // the training epilogue (pre-norm side output, dropout) is a separate instantiation: the inference kernel
-    // carries none of its code
-    {
-      static const bool pdl = getenv("FTB_NO_PDL") == nullptr;
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      at[0].val.programmaticStreamSerializationAllowed = 1;
-      cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-      if (q.u_out || q.drop_p > 0.f || q.f32_accum) FTB_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true>, tm0, tm1, q));
-      else FTB_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false>, tm0, tm1, q));
-    }
-    prof_end(prof, st);
-    FTB_LAUNCH_OK();
+  // every N tile of the layer in ONE launch (blockIdx.y = tile): a wide layer on a small volume (192 channels at
+  // 4^3: 8-32 items) is bound by each CTA streaming the whole weight tensor through its shared memory, so splitting
+  // N over more CTAs divides both that traffic and the MMA width per CTA
+  FTB_CHECK(w.ntiles == 1 || (!e.norm && !e.sumsq_out), "conv: channel norm / sum-of-squares epilogues need a single N tile");
+  IgemmParams q = p;
+  q.wpack = w.w;
+  q.w_tile_stride = (long long)w.tile_elems();
+  q.bias = e.bias;
+  q.out_cgoff = out_cgoff;
+  q.flags = (e.silu ? F_SILU : 0) | (e.q_softmax_heads ? F_QSOFTMAX : 0);
+  if (!(q.flags & F_QSOFTMAX) && !q.norm && !q.bias && !q.mul && !q.add && !e.silu && !q.resid && !q.out_f32 && !q.ss_out)
+    q.flags |= F_PLAIN;
+  int prof = -1;
+  if (prof_enabled()) {
+    // algorithmic work of this launch: real (unpadded) channel counts
+    const double vox = (double)a0.B * a0.voxels();
+    const double cin = w.cin_real > 0 ? w.cin_real : w.cin;
+    const double cout = w.cout_real > 0 ? w.cout_real : (double)w.n * w.ntiles;
+    const double flops = 2.0 * vox * cin * cout * p.K * p.K * (w.ksize_w == 1 && p.K > 1 ? 1 : p.K);   // cin_real of an unfolded conv already counts the W taps
+    const double bytes = vox * (cin + cout) * 2.0;  // read input once, write output once (bf16)
+    prof = prof_begin(st, flops, bytes, w.ksize > 1 ? 0 : 1);
   }
+  // the training epilogue (pre-norm side output, dropout) is a separate instantiation: the inference kernel
+  // carries none of its code
+  {
+    static const bool pdl = getenv("FTB_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid, w.ntiles); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    if (q.u_out || q.drop_p > 0.f || q.f32_accum) FTB_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true>, tm0, tm1, q));
+    else FTB_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false>, tm0, tm1, q));
+  }
+  prof_end(prof, st);
+  FTB_LAUNCH_OK();
   return 0;
 }
 

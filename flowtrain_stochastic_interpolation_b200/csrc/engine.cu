@@ -243,12 +243,23 @@ std::string resnet_mlp(const ftb_unet* U, const std::string& p) {
   return p + (U->cfg.conditional ? ".time_mlp.1" : ".mlp.1");
 }
 
-void add_resnet(ftb_unet* U, const std::string& p, int cin, int cout) {
+// N tile of a conv at the coarsest level (downs[n-1], mid, ups[0]: 4^3 voxels per sample at 64^3): there a launch has
+// only 8-32 work items and every CTA streams the whole weight tensor through shared memory, so a wide layer
+// (>= 128 output channels) is cut into <= 48-channel N tiles that run as blockIdx.y of the same launch; the channel
+// norm then runs as its own pass (normact_fwd).  0 = one tile.
+int deep_n_tile(int cout) {
+  if (cout < 128 || getenv("FTB_NO_NSPLIT") != nullptr) return 0;
+  for (int n = 48; n >= 16; n -= 16)
+    if (cout % n == 0) return n;
+  return 0;
+}
+
+void add_resnet(ftb_unet* U, const std::string& p, int cin, int cout, bool deep = false) {
   add_param(U, resnet_mlp(U, p) + ".weight", {2 * cout, U->time_dim});
   add_param(U, resnet_mlp(U, p) + ".bias", {2 * cout});
-  add_conv(U, p + ".block1.proj", cout, cin, 3, true);
+  add_conv(U, p + ".block1.proj", cout, cin, 3, true, "", deep ? deep_n_tile(cout) : 0);
   add_gain(U, p + ".block1.norm.g", cout);
-  add_conv(U, p + ".block2.proj", cout, cout, 3, true);
+  add_conv(U, p + ".block2.proj", cout, cout, 3, true, "", deep ? deep_n_tile(cout) : 0);
   add_gain(U, p + ".block2.norm.g", cout);
   if (cin != cout) add_conv(U, p + ".res_conv", cout, cin, 1, true);
 }
@@ -322,26 +333,26 @@ int build_plan(ftb_unet* U) {
     const int din = U->in_out[i].first, dout = U->in_out[i].second;
     const std::string p = "downs." + std::to_string(i);
     if (cond) add_embed_mix(U, p, din);
-    add_resnet(U, sub(p, o), din, din);
-    add_resnet(U, sub(p, o + 1), din, din);
+    add_resnet(U, sub(p, o), din, din, i == n - 1 && n > 1);
+    add_resnet(U, sub(p, o + 1), din, din, i == n - 1 && n > 1);
     add_attn(U, sub(p, o + 2), din, c.full_attn[i] != 0);
-    if (i >= n - 1) add_conv(U, sub(p, o + 3), dout, din, 3, true);
+    if (i >= n - 1) add_conv(U, sub(p, o + 3), dout, din, 3, true, "", n > 1 ? deep_n_tile(dout) : 0);
     else add_conv(U, sub(p, o + 3) + ".conv", dout, din, 1, true);
   }
   for (int i = 0; i < n; ++i) {
     const int din = U->in_out[n - 1 - i].first, dout = U->in_out[n - 1 - i].second;
     const std::string p = "ups." + std::to_string(i);
     if (cond) add_embed_mix(U, p, dout);
-    add_resnet(U, sub(p, o), dout + din, dout);
-    add_resnet(U, sub(p, o + 1), dout + din, dout);
+    add_resnet(U, sub(p, o), dout + din, dout, i == 0 && n > 1);
+    add_resnet(U, sub(p, o + 1), dout + din, dout, i == 0 && n > 1);
     add_attn(U, sub(p, o + 2), dout, c.full_attn[n - 1 - i] != 0);
     if (i == n - 1) add_conv(U, sub(p, o + 3), din, dout, 3, true);
     else add_conv(U, sub(p, o + 3) + ".conv", din, dout, 3, true);
   }
   const int mid = U->dims.back();
-  add_resnet(U, "mid_block1", mid, mid);
+  add_resnet(U, "mid_block1", mid, mid, n > 1);
   add_attn(U, "mid_attn", mid, true);
-  add_resnet(U, "mid_block2", mid, mid);
+  add_resnet(U, "mid_block2", mid, mid, n > 1);
   add_resnet(U, "final_res_block", c.dim * 2, c.dim);
   add_conv(U, "final_conv", c.data_channels, c.dim, 1, true);
 
@@ -549,13 +560,26 @@ struct Fwd {
     w.cin_real = cl.unfold_w ? cl.k * cl.cin : cl.cin; w.cout_real = cl.cout;
     if (!cl.bname.empty()) e.bias = cl.bias;
     if (dry || skip) return 0;
-    U->launches += cl.ntiles;
+    U->launches += 1;
     return conv_dispatch(s0, s1, w, e, out, out_cgoff, st);
   }
 
   // ResnetBlock.forward (:265-278); input may be the channel concat of (x0, x1)
   // `sumsq` (optional, [B][voxels]) receives ||out voxel||^2 for a following attention's pre-norm
-  int resnet(const std::string& p, const Act& x0, const Act* x1, int cout, Act* out, float* sumsq = nullptr) {
+  // conv -> (RMSNorm * mul + add -> SiLU -> + resid): fused into the conv epilogue, or, for a layer cut into several
+  // N tiles (deep_n_tile), a bias-only conv followed by the norm/activation pass
+  int conv_norm_act(const std::string& name, const ConvSrc& s0, const ConvSrc& s1, ConvEpilogue e, Act& out) {
+    const ConvLayer& cl = U->convs.at(name);
+    if (cl.ntiles == 1) return conv(name, s0, s1, e, out);
+    Act u = act(cl.cout, out.D, out.H, out.W);
+    FTB_TRY(conv(name, s0, s1, ConvEpilogue{}, u));
+    if (dry) return 0;
+    U->launches += 1;
+    return normact_fwd(u, e.norm, e.mul_stride ? nullptr : e.mul, e.mul_stride ? e.mul : nullptr, e.add, e.mul_stride,
+                       e.silu, e.resid, out, st);
+  }
+
+  int resnet(const std::string& p, const Act& x0, const Act* x1, int cout, Act* out, float** sumsq = nullptr) {
     const Act& a = x0;
     ConvSrc s0{&x0, 0, x0.cg()}, s1{};
     if (x1) s1 = ConvSrc{x1, 0, x1->cg()};
@@ -568,7 +592,7 @@ struct Fwd {
     e1.mul = film_p; e1.mul_stride = U->film_rows;
     e1.add = film_p ? film_p + cout : nullptr; e1.add_stride = U->film_rows;
     e1.silu = true;
-    FTB_TRY(conv(p + ".block1.proj", s0, s1, e1, h1));
+    FTB_TRY(conv_norm_act(p + ".block1.proj", s0, s1, e1, h1));
     tap(p + ".block1", h1);
     Act res;
     const Act* resp = &x0;
@@ -583,8 +607,10 @@ struct Fwd {
     e2.mul = U->gains.at(p + ".block2.norm.g").gs;
     e2.silu = true;
     e2.resid = resp;
-    e2.sumsq_out = sumsq;
-    FTB_TRY(conv(p + ".block2.proj", ConvSrc{&h1, 0, h1.cg()}, ConvSrc{}, e2, *out));
+    // ||out voxel||^2 for a following attention's pre-norm comes from the fused epilogue only
+    if (sumsq && U->convs.at(p + ".block2.proj").ntiles > 1) *sumsq = nullptr;
+    e2.sumsq_out = sumsq ? *sumsq : nullptr;
+    FTB_TRY(conv_norm_act(p + ".block2.proj", ConvSrc{&h1, 0, h1.cg()}, ConvSrc{}, e2, *out));
     tap(p, *out);
     return 0;
   }
@@ -789,7 +815,7 @@ struct Fwd {
       FTB_TRY(resnet(sub(p, o), cur, nullptr, din, &a1));
       skips.push_back(a1);
       float* ss = f32((size_t)B * a1.voxels());
-      FTB_TRY(resnet(sub(p, o + 1), a1, nullptr, din, &a2, ss));
+      FTB_TRY(resnet(sub(p, o + 1), a1, nullptr, din, &a2, &ss));
       FTB_TRY(attention(sub(p, o + 2), a2, ss, c.full_attn[i] != 0, &a3));
       skips.push_back(a3);
       if (i >= n - 1) {
@@ -808,7 +834,7 @@ struct Fwd {
       Act m1, m2, m3;
       const int mid = U->dims.back();
       float* ss = f32((size_t)B * cur.voxels());
-      FTB_TRY(resnet("mid_block1", cur, nullptr, mid, &m1, ss));
+      FTB_TRY(resnet("mid_block1", cur, nullptr, mid, &m1, &ss));
       FTB_TRY(attention("mid_attn", m1, ss, true, &m2));
       FTB_TRY(resnet("mid_block2", m2, nullptr, mid, &m3));
       cur = m3;
@@ -826,7 +852,7 @@ struct Fwd {
       FTB_TRY(resnet(sub(p, o), cur, &s, dout, &a1));
       s = skips.back(); skips.pop_back();
       float* ss = f32((size_t)B * a1.voxels());
-      FTB_TRY(resnet(sub(p, o + 1), a1, &s, dout, &a2, ss));
+      FTB_TRY(resnet(sub(p, o + 1), a1, &s, dout, &a2, &ss));
       FTB_TRY(attention(sub(p, o + 2), a2, ss, c.full_attn[n - 1 - i] != 0, &a3));
       if (i == n - 1) {
         a4 = act(din, a3.D, a3.H, a3.W);

@@ -149,7 +149,7 @@ struct FwdF32 {
         w.w = pk.second;
         FTB_TRY(conv_igemm(hi, ConvSrc{}, w, e, dummy, 0, st));      // += W_lo x_hi
       }
-      U->launches += 1 + (mode == 3 ? 1 : (mode == 2 ? 2 : 3)) * cl.ntiles;
+      U->launches += 1 + (mode == 3 ? 1 : (mode == 2 ? 2 : 3));
     }
     off = mark;   // the split operand is dead once the three launches are enqueued (stream order)
     return 0;

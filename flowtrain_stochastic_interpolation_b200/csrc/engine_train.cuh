@@ -308,13 +308,16 @@ struct TrainFwd {
     e.resid = resid;
     return e;
   }
-  bool fuse_ok(int cout) const { return fuse && round_up(cout, 16) <= 256; }
+  // (a layer cut into several N tiles cannot norm over all channels in its epilogue)
+  bool fuse_ok(const std::string& conv_name, int cout) const {
+    return fuse && round_up(cout, 16) <= 256 && U->convs.at(conv_name).ntiles == 1;
+  }
 
   // ResnetBlock (:265-278)
   int resnet(const std::string& p, const Act& x0, const Act* x1, int c0, int c1, int cout, Act* out) {
     const std::string film = resnet_mlp(U, p);
     Act u1 = c.act(cout, x0.D, x0.H, x0.W), h1 = c.like(u1);
-    const bool fz = fuse_ok(cout);
+    const bool fz = fuse_ok(p + ".block1.proj", cout);
     ConvEpilogue f1 = fused_epilogue(p + ".block1.norm.g", film, cout, true, nullptr);
     FTB_TRY(conv(p + ".block1.proj", x0, x1, c0, c1, nullptr, false, nullptr, u1, false, false, true, fz ? &f1 : nullptr, &h1));
     FTB_TRY(normact(u1, true, p + ".block1.norm.g", film, true, nullptr, h1, p + ".block1.proj.bias", fz));
@@ -428,7 +431,7 @@ struct TrainFwd {
       return 0;
     });
     Act uo = c.like(x);
-    const bool fz = fuse_ok(C);
+    const bool fz = fuse_ok(p + ".to_out.0", C);
     ConvEpilogue fo = fused_epilogue(p + ".to_out.1.g", "", C, false, &x);
     FTB_TRY(conv(p + ".to_out.0", o, nullptr, hd, 0, nullptr, false, nullptr, uo, false, false, true, fz ? &fo : nullptr, out));
     FTB_TRY(normact(uo, true, p + ".to_out.1.g", "", false, &x, *out, p + ".to_out.0.bias", fz));
@@ -465,7 +468,7 @@ struct TrainFwd {
     FTB_TRY(normact(x, false, "", "", false, nullptr, xf, "", false, &fx));
     FTB_TRY(normact(emb, false, "", "", false, nullptr, ef, "", false, &fe));
     Act u1 = c.like(x), h1 = c.like(x);
-    const bool fz = fuse_ok(C);
+    const bool fz = fuse_ok(p + ".conv1", C);
     ConvEpilogue f1 = fused_epilogue(p + ".norm.g", "", C, true, nullptr);
     FTB_TRY(conv(p + ".conv1", xf, &ef, C, C, nullptr, false, nullptr, u1, false, false, true, fz ? &f1 : nullptr, &h1));
     FTB_TRY(normact(u1, true, p + ".norm.g", "", true, nullptr, h1, p + ".conv1.bias", fz));

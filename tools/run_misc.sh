@@ -2,5 +2,6 @@
 set -u
 mkdir -p gpurun_out
 CMD="python bench.py --steps 1 --warmup 1 --batch 8 --no-e2e --no-cpu-baseline --no-train --no-extras"
-timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active,launch__occupancy_limit_shared_mem,launch__registers_per_thread --clock-control none -k regex:trilinear -c 24 --csv --log-file gpurun_out/tri.csv $CMD > gpurun_out/ncu_tri.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_split.csv $CMD > gpurun_out/ncu_list.log 2>&1
 echo rc=$?
+FTB_CONV_PLAN=1 timeout 300 python bench.py --steps 1 --warmup 1 --batch 8 --no-e2e --no-cpu-baseline --no-train --no-extras 2>&1 | grep "conv plan" | sort | uniq -c | sort -rn | head -60 > gpurun_out/conv_plans.txt
