@@ -866,10 +866,12 @@ full_attn_kernel(const bf16* __restrict__ qkv, int cgtot, int heads, int n,
   const bf16* kb = qkv + ((size_t)b * cgtot + (hd + h * DH) / 8) * (size_t)n * 8;
   const bf16* vb = qkv + ((size_t)b * cgtot + (2 * hd + h * DH) / 8) * (size_t)n * 8;
   const int nk = n + n_mem;
-  const int q0 = blockIdx.y * 64;
   // each warp walks queries q0+warp, q0+warp+4, ...; all warps share the key tiles, so the
-  // loops are organised tile-outer and the per-query state lives in registers (16 queries/warp).
-  constexpr int QPW = 16;
+  // loops are organised tile-outer and the per-query state lives in registers.  4 queries per warp = 16 per block:
+  // the kernel only ever sees <= 516 keys and a few hundred queries per (sample, head), so it is latency-bound and
+  // wants many small blocks (with 16 per warp the 64-token case ran as 32 blocks for 56 us).
+  constexpr int QPW = 4;
+  const int q0 = blockIdx.y * (4 * QPW);
   float m_run[QPW], l_run[QPW], o_run[QPW][DPL];
 #pragma unroll
   for (int i = 0; i < QPW; ++i) {
@@ -1116,7 +1118,7 @@ int full_attention(const Act& qkv, int heads, int dh, const float* mem_kv, int n
   const int n = (int)qkv.voxels();
   FTB_CHECK(qkv.C == 3 * heads * dh && out.C == heads * dh, "attention: channel counts");
   FTB_CHECK(n_mem <= 128, "attention: too many memory kv");
-  dim3 grid(qkv.B * heads, cdiv(n, 64));
+  dim3 grid(qkv.B * heads, cdiv(n, 16));
   const float scale = 1.0f / sqrtf((float)dh);
   if (dh == 32)
     full_attn_kernel<32><<<grid, 128, 0, st>>>(qkv.p, qkv.cg(), heads, n, mem_kv, n_mem, out.p, out.cg(), scale);
