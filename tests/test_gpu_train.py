@@ -498,6 +498,21 @@ def test_flow_trainer_data_parallel_nccl(ftb):
     assert "DDP_OK" in r.stdout
 
 
+def test_sharded_ensemble_votes_nccl(ftb):
+    """N > 1: ensemble samples sharded over the ranks, one NCCL all-reduce of the vote histogram (needs >= 2 GPUs)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29641",
+                        os.path.join(root, "tests", "_ensemble_worker.py")],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "ENSEMBLE_OK" in r.stdout
+
+
 def test_dropout_mask_is_consistent_between_forward_and_backward(ftb, dev):
     """dropout 0.1 (the reference's training default): the counter-based mask is regenerated by the backward.
     Pinned seed -> identical forwards; fresh seed -> different; and the directional derivative along the gradient,

@@ -1,7 +1,6 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err
-echo "bench n2 rc=$?"; wc -l gpurun_out/bench_n2.json; head -c 200 gpurun_out/bench_n2.json; echo
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 > gpurun_out/bench_ref_n2.json 2> gpurun_out/bench_ref_n2.err
-echo "ref n2 rc=$?"; wc -l gpurun_out/bench_ref_n2.json; head -c 200 gpurun_out/bench_ref_n2.json; echo
+timeout 900 python -m pytest tests/test_gpu_train.py -m gpu -x -q -s -k "nccl" 2>&1 | tail -6
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29535 tools/ensemble_bench.py 64 8 100 euler > gpurun_out/ensemble_n2.json 2> gpurun_out/ensemble_n2.err
+echo "ens n2 rc=$?"; tail -2 gpurun_out/ensemble_n2.json; tail -3 gpurun_out/ensemble_n2.err
