@@ -78,11 +78,14 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.rows = []
+        self.rows = []          # (arrival time, csv line)
         self.proc = None
         self.index = index
+        self.t_begin = self.t_end = None
 
     def start(self):
+        """Started BEFORE the warm-up: nvidia-smi needs a few hundred ms to deliver its first sample, longer than a short
+        timed region; only samples that arrive between mark_begin() and mark_end() are reported."""
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
@@ -92,9 +95,21 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def wait_ready(self, timeout=4.0):
+        """Block until nvidia-smi has delivered its first sample (so the short timed region is covered)."""
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
     def stop(self):
         if not self.proc:
@@ -104,9 +119,16 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        t1 = self.t_end if self.t_end is not None else float("inf")
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.02]
+        window = "timed region"
+        if len(rows) < 2:   # very short timed region: fall back to every sample taken under load (warm-up included)
+            rows = [r for (_, r) in self.rows]
+            window = "warm-up + timed region (fewer than 2 samples arrived inside the timed region)"
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -121,7 +143,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw),
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def measured_peaks():
@@ -383,18 +405,21 @@ def run_b200(a):
         torch.cuda.synchronize()
 
     with torch.no_grad():
-        run_steps(max(a.warmup, 1), x_dev)
-        barrier()
         clocks = ClockSampler(local_rank)
         if rank == 0:
             clocks.start()
+            clocks.wait_ready()
+        run_steps(max(a.warmup, 1), x_dev)
+        barrier()
         l0 = _lib.lib.ftb_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        clocks.mark_begin()
         e0.record()
         x_end = run_steps(a.steps, x_dev)
         e1.record()
         barrier()
+        clocks.mark_end()
         step_ms = e0.elapsed_time(e1) / a.steps
         launches = _lib.lib.ftb_launch_count() - l0
         clk = clocks.stop() if rank == 0 else None
