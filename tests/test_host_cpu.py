@@ -194,3 +194,31 @@ def test_lightning_checkpoint_round_trip(tmp_path):
     assert "embedding.weight" not in shadow and torch.equal(dst.embedding.weight, sd["embedding.weight"])
     ck = ftb.lightning_checkpoint(dst)
     assert set(ck["state_dict"].keys()) == set(sd.keys())
+
+
+def test_precision_switch_and_solver_method_validation():
+    """Host-side argument checks of the additions that need no GPU: precision names, adaptive-method names, the
+    conditional module's signature and the training bridge's refusal to produce input gradients."""
+    net = ftb.Unet3D(dim=32, dim_mults=(1, 2), data_channels=18, time_resolution=64, time_learned_emb=True,
+                     attn_heads=2, attn_dim_head=16)
+    assert net.precision == "bf16" and net.set_precision("fp32") is net and net.precision == "fp32"
+    with pytest.raises(ValueError):
+        net.set_precision("fp16")
+    with pytest.raises(RuntimeError):          # no CPU fallback, also in the fp32 mode
+        net(torch.zeros(1, 18, 8, 8, 8), torch.zeros(1))
+    from flowtrain_stochastic_interpolation_b200 import solvers
+    assert set(solvers.ADAPTIVE_METHODS) == {"dopri5", "adaptive_heun"}
+    with pytest.raises(ValueError):
+        solvers.integrate_adaptive(lambda t, x, i: x, torch.zeros(4), 0.0, 1.0, 3, method="rk45")
+    with pytest.raises(RuntimeError):
+        solvers.integrate_adaptive(lambda t, x, i: x, torch.zeros(4), 0.0, 1.0, 3, method="dopri5")
+    # tableau consistency: rows of beta sum to alpha, the 5th-order weights sum to 1, error weights to 0
+    d = solvers._DOPRI5
+    for a, row in zip(d["alpha"], d["beta"]):
+        assert abs(sum(row) - a) < 1e-12
+    assert abs(sum(d["c_sol"]) - 1.0) < 1e-12 and abs(sum(d["c_error"])) < 1e-12
+    cnet = ftb.Unet3DCond(dim=32, dim_mults=(1, 2), data_channels=15, time_resolution=64, time_learned_emb=True,
+                          attn_heads=2, attn_dim_head=16)
+    assert cnet.set_precision("fp32").precision == "fp32"
+    names = [n for n, _ in cnet.named_parameters()]
+    assert names[0] == "init_conv_x.weight" and "downs.0.0.conv1.weight" in names and "downs.0.1.time_mlp.1.weight" in names
