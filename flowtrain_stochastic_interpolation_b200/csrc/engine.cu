@@ -265,14 +265,14 @@ void add_resnet(ftb_unet* U, const std::string& p, int cin, int cout, bool deep 
 }
 
 // EmbedATb (unet_attn_3d_cond_v3.py:120-129) + MixATb (:156-173) of one stage
-void add_embed_mix(ftb_unet* U, const std::string& p, int d) {
-  add_conv(U, p + ".0.conv1", d, U->cfg.data_channels, 5, true);
-  add_conv(U, p + ".0.conv2", d, d, 5, true);
+void add_embed_mix(ftb_unet* U, const std::string& p, int d, bool deep = false) {
+  add_conv(U, p + ".0.conv1", d, U->cfg.data_channels, 5, true, "", deep ? deep_n_tile(d) : 0);
+  add_conv(U, p + ".0.conv2", d, d, 5, true, "", deep ? deep_n_tile(d) : 0);
   add_param(U, p + ".1.time_mlp.1.weight", {4 * d, U->time_dim});
   add_param(U, p + ".1.time_mlp.1.bias", {4 * d});
   add_conv(U, p + ".1.conv1", d, 2 * d, 3, true);
   add_gain(U, p + ".1.norm.g", d);
-  add_conv(U, p + ".1.conv2", d, d, 3, true);
+  add_conv(U, p + ".1.conv2", d, d, 3, true, "", deep ? deep_n_tile(d) : 0);
 }
 
 void add_attn(ftb_unet* U, const std::string& p, int dim, bool full) {
@@ -332,7 +332,7 @@ int build_plan(ftb_unet* U) {
   for (int i = 0; i < n; ++i) {
     const int din = U->in_out[i].first, dout = U->in_out[i].second;
     const std::string p = "downs." + std::to_string(i);
-    if (cond) add_embed_mix(U, p, din);
+    if (cond) add_embed_mix(U, p, din, i == n - 1 && n > 1);
     add_resnet(U, sub(p, o), din, din, i == n - 1 && n > 1);
     add_resnet(U, sub(p, o + 1), din, din, i == n - 1 && n > 1);
     add_attn(U, sub(p, o + 2), din, c.full_attn[i] != 0);
@@ -342,7 +342,7 @@ int build_plan(ftb_unet* U) {
   for (int i = 0; i < n; ++i) {
     const int din = U->in_out[n - 1 - i].first, dout = U->in_out[n - 1 - i].second;
     const std::string p = "ups." + std::to_string(i);
-    if (cond) add_embed_mix(U, p, dout);
+    if (cond) add_embed_mix(U, p, dout, i == 0 && n > 1);
     add_resnet(U, sub(p, o), dout + din, dout, i == 0 && n > 1);
     add_resnet(U, sub(p, o + 1), dout + din, dout, i == 0 && n > 1);
     add_attn(U, sub(p, o + 2), dout, c.full_attn[n - 1 - i] != 0);

@@ -1,7 +1,7 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-CMD="python bench.py --steps 1 --warmup 1 --batch 8 --no-e2e --no-cpu-baseline --no-train --no-extras"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_split.csv $CMD > gpurun_out/ncu_list.log 2>&1
-echo rc=$?
-FTB_CONV_PLAN=1 timeout 300 python bench.py --steps 1 --warmup 1 --batch 8 --no-e2e --no-cpu-baseline --no-train --no-extras 2>&1 | grep "conv plan" | sort | uniq -c | sort -rn | head -60 > gpurun_out/conv_plans.txt
+timeout 900 python -m pytest tests -m gpu -x -q -k "cond" 2>&1 | tail -4
+timeout 600 python tools/cond_train_bench.py 8 2>/dev/null | python -c "
+import json,sys; d=json.load(sys.stdin); print(d['cond_train_step'])"
+timeout 300 python tools/cond_bench.py 8 2>&1 | head -2
