@@ -15,7 +15,13 @@ The oracle is therefore pinned against OUTPUTS OF THE REFERENCE ITSELF, generate
 build container by importing the reference modules by file path
 (``tests/golden/make_golden.py``) and committed under ``tests/golden/``.  The one part
 that stays "parity unpinned" is the adaptive dopri5 / adaptive_heun stepping of the
-un-vendored ``torchdiffeq`` dependency (>=0.2.5,<0.3): the fixed-grid Euler / Heun / RK4
-integrators here are this build's own contract (torchdiffeq fixed-grid convention); only
-``odeSol_RK4`` is a restatement of reference code (solvers.py:225-245).
+un-vendored ``torchdiffeq`` dependency (>=0.2.5,<0.3): ``solvers.odeint_adaptive`` restates
+its published algorithm and is checked against closed forms and scipy's independent
+Dormand-Prince integrator, but no reference test or fixture holds an adaptive-solver result.
+The fixed-grid Euler / Heun / RK4 integrators are this build's own contract (torchdiffeq
+fixed-grid convention); ``odeSol_RK4`` is a restatement of reference code (solvers.py:225-245).
+Also restated here: the conditioning masks (boreholes.py, pinned by the reference's own masks in
+``tests/golden/cond_frontend.npz``), the conditional training loss and the ensemble statistics
+(project/geodata-3d-conditional scripts), and autograd through both functional networks (pinned by
+the reference modules' gradients in ``tests/golden/train*.npz``).
 """
