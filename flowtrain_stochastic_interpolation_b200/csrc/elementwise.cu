@@ -164,14 +164,16 @@ trilinear_kernel(const bf16* __restrict__ in, int CG, int Di, int Hi, int Wi, in
   }
 }
 
-// Same result (same lerp order), input rows staged in shared memory: an upsample reads every input voxel from 8
-// outputs, and with direct global loads that 8x gather traffic made the 32^3 -> 64^3 resample L2-bound (353 us for
+// Upsampling variant: an upsample reads every input voxel from ~8 outputs; with direct global loads that gather
+// traffic and the 8 x (unpack + lerp) per output made the 32^3 -> 64^3 resample instruction- and L2-bound (353 us for
 // 453 MB).  Block = (b*cg, d, group of RH output rows): the two source planes' rows [r0, r0 + nrows) are loaded once
-// (coalesced 16-byte units), then every output is 8 LDS.128.
+// (coalesced 16-byte units) and blended along D (block-uniform weights) into fp32 shared-memory rows, then every
+// output is a 4-tap bilinear blend of those rows.  (fp32 throughout; the association D-then-HW differs from ATen's in
+// the last bit, far below the bf16 output rounding.)
 __global__ void __launch_bounds__(256)
 trilinear_smem_kernel(const bf16* __restrict__ in, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int hgroups,
                       int RH, int max_rows, float sd, float sh, float sw, bf16* __restrict__ out) {
-  extern __shared__ uint4 s_in[];   // [2 planes][max_rows][Wi]
+  extern __shared__ float4 s_t[];   // [max_rows][Wi][2]: the two source planes already blended along D (fp32, 8 channels)
   int blk = blockIdx.x;
   const int hg = blk % hgroups; blk /= hgroups;
   const int d = blk % Do;
@@ -181,10 +183,15 @@ trilinear_smem_kernel(const bf16* __restrict__ in, int Di, int Hi, int Wi, int D
   const int r0 = lerp_idx(h_lo, Hi, sh).i0;
   const int nrows = lerp_idx(h_hi, Hi, sh).i1 - r0 + 1;
   const uint4* base = reinterpret_cast<const uint4*>(in) + bc * (size_t)Di * Hi * Wi;
-  for (int i = threadIdx.x; i < 2 * nrows * Wi; i += blockDim.x) {
-    const int pl = i / (nrows * Wi), rem = i - pl * nrows * Wi;
-    const int dd = pl ? ld.i1 : ld.i0;
-    s_in[pl * max_rows * Wi + rem] = __ldg(base + ((size_t)dd * Hi + r0) * Wi + rem);
+  // the depth weights are block-uniform: blend the two planes once per staged voxel instead of once per output
+  for (int i = threadIdx.x; i < nrows * Wi; i += blockDim.x) {
+    float f0[8], f1[8];
+    unpack_bf16x8(__ldg(base + ((size_t)ld.i0 * Hi + r0) * Wi + i), f0);
+    unpack_bf16x8(__ldg(base + ((size_t)ld.i1 * Hi + r0) * Wi + i), f1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f0[k] = ld.l0 * f0[k] + ld.l1 * f1[k];
+    s_t[2 * i] = make_float4(f0[0], f0[1], f0[2], f0[3]);
+    s_t[2 * i + 1] = make_float4(f0[4], f0[5], f0[6], f0[7]);
   }
   __syncthreads();
   bf16* obase = out + (bc * (size_t)Do + d) * Ho * Wo * 8;
@@ -193,28 +200,17 @@ trilinear_smem_kernel(const bf16* __restrict__ in, int Di, int Hi, int Wi, int D
     const int h = h_lo + hr;
     if (h >= Ho) continue;
     const Lerp lh = lerp_idx(h, Hi, sh), lw = lerp_idx(w, Wi, sw);
+    const float4* ra = s_t + (size_t)(lh.i0 - r0) * Wi * 2;
+    const float4* rb = s_t + (size_t)(lh.i1 - r0) * Wi * 2;
+    const float w00 = lh.l0 * lw.l0, w01 = lh.l0 * lw.l1, w10 = lh.l1 * lw.l0, w11 = lh.l1 * lw.l1;
     float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
-    for (int a = 0; a < 2; ++a) {
-      const float wd = a ? ld.l1 : ld.l0;
-      float accd[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) accd[j] = 0.f;
-#pragma unroll
-      for (int bb = 0; bb < 2; ++bb) {
-        const int hh = (bb ? lh.i1 : lh.i0) - r0;
-        const float wh = bb ? lh.l1 : lh.l0;
-        float f0[8], f1[8];
-        const uint4* row = s_in + (a * max_rows + hh) * Wi;
-        unpack_bf16x8(row[lw.i0], f0);
-        unpack_bf16x8(row[lw.i1], f1);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) accd[j] += wh * (lw.l0 * f0[j] + lw.l1 * f1[j]);
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += wd * accd[j];
+    for (int hf = 0; hf < 2; ++hf) {
+      const float4 a0 = ra[2 * lw.i0 + hf], a1 = ra[2 * lw.i1 + hf], b0 = rb[2 * lw.i0 + hf], b1 = rb[2 * lw.i1 + hf];
+      acc[4 * hf + 0] = w00 * a0.x + w01 * a1.x + w10 * b0.x + w11 * b1.x;
+      acc[4 * hf + 1] = w00 * a0.y + w01 * a1.y + w10 * b0.y + w11 * b1.y;
+      acc[4 * hf + 2] = w00 * a0.z + w01 * a1.z + w10 * b0.z + w11 * b1.z;
+      acc[4 * hf + 3] = w00 * a0.w + w01 * a1.w + w10 * b0.w + w11 * b1.w;
     }
     *reinterpret_cast<uint4*>(obase + ((size_t)h * Wo + w) * 8) = pack_bf16x8(acc);
   }
@@ -538,7 +534,7 @@ int trilinear_resample(const Act& in, Act& out, cudaStream_t st) {
   if (out.H > in.H && out.W >= 16 && getenv("FTB_TRILINEAR_DIRECT") == nullptr) {
     const float shf = scale(in.H, out.H);
     const int max_rows = (int)ceilf(shf * (kTriRH - 1)) + 3;
-    const size_t smem = (size_t)2 * max_rows * in.W * sizeof(uint4);
+    const size_t smem = (size_t)max_rows * in.W * 2 * sizeof(float4);   // D-blended fp32 rows
     if (smem <= 48 * 1024) {
       trilinear_smem_kernel<<<(unsigned)blocks, 256, smem, st>>>(in.p, in.D, in.H, in.W, out.D, out.H, out.W, hgroups,
                                                                 kTriRH, max_rows, scale(in.D, out.D), shf,
