@@ -105,6 +105,7 @@ _SIGS = {
     "ftb_test_conv_dgrad": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ftb_test_conv3d": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "ftb_test_trilinear": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "ftb_test_trilinear_bwd": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
 }
 
 for _name, (_res, _args) in _SIGS.items():

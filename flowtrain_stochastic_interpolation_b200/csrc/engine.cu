@@ -1525,4 +1525,24 @@ int ftb_test_trilinear(const float* x, int B, int C, int X, int Y, int Z, int Xo
   return 0;
 }
 
+/* adjoint of the trilinear resample: dout [B,C,Xo,Yo,Zo] -> din [B,C,X,Y,Z] (+= acc when given) */
+int ftb_test_trilinear_bwd(const float* dout, int B, int C, int X, int Y, int Z, int Xo, int Yo, int Zo,
+                           const float* acc, float* din, void* stream) {
+  FTB_CHECK(dout && din, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  Scratch S;
+  Act a, o;
+  a.B = o.B = B; a.C = o.C = round_up(C, 16);
+  a.D = X; a.H = Y; a.W = Z; o.D = Xo; o.H = Yo; o.W = Zo;
+  a.p = S.get<bf16>(a.elems());
+  o.p = S.get<bf16>(o.elems());
+  FTB_CHECK(a.p && o.p, "scratch allocation failed");
+  FTB_TRY(pack_ncdhw_to_blocked(dout, B, C, Xo, Yo, Zo, o, st));
+  if (acc) FTB_TRY(pack_ncdhw_to_blocked(acc, B, C, X, Y, Z, a, st));
+  FTB_TRY(trilinear_resample_bwd(o, a, acc != nullptr, st));
+  FTB_TRY(unpack_blocked_to_ncdhw(a, 0, C, din, st));
+  FTB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
 }  // extern "C"

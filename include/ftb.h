@@ -240,6 +240,8 @@ int ftb_test_conv_dgrad(const float* dy, const float* w, int cout, int cin, int 
                         int B, int X, int Y, int Z, void* stream);
 int ftb_test_trilinear(const float* x, int B, int C, int X, int Y, int Z, int Xo, int Yo, int Zo,
                        float* out, void* stream);
+int ftb_test_trilinear_bwd(const float* dout, int B, int C, int X, int Y, int Z, int Xo, int Yo, int Zo,
+                           const float* acc, float* din, void* stream);
 
 #ifdef __cplusplus
 }

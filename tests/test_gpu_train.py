@@ -141,6 +141,32 @@ def test_conv_dgrad_vs_autograd(ftb, case):
     assert dgrad_case(**case) <= BAR_CONV
 
 
+# ------------------------------------------------------------------ trilinear adjoint
+@pytest.mark.parametrize("di,do,acc", [((8, 8, 8), (4, 4, 4), False), ((4, 4, 4), (8, 8, 8), True),
+                                       ((16, 16, 16), (32, 32, 32), False), ((32, 32, 32), (16, 16, 16), True),
+                                       ((6, 10, 4), (3, 5, 2), False), ((3, 5, 7), (6, 10, 14), False),
+                                       ((64, 64, 64), (4, 4, 4), False), ((16, 24, 8), (2, 3, 1), True)])
+def test_trilinear_adjoint_vs_autograd(ftb, di, do, acc):
+    """trilinear_resample_bwd == autograd of F.interpolate(mode="trilinear", align_corners=True) for 2x up / down,
+    ragged sizes and the large down-scales of EmbedATb (64 -> 4); bf16 gradient storage."""
+    import torch.nn.functional as F
+    from flowtrain_stochastic_interpolation_b200 import _lib
+    g = torch.Generator("cpu").manual_seed(1)
+    B, C = 2, 24
+    dout = bf(torch.randn(B, C, *do, generator=g)).cuda()
+    a = bf(torch.randn(B, C, *di, generator=g)).cuda() if acc else None
+    x = torch.zeros(B, C, *di, dtype=torch.float64, device="cuda", requires_grad=True)
+    y = F.interpolate(x, size=do, mode="trilinear", align_corners=True)
+    (ref,) = torch.autograd.grad(y, x, dout.double())
+    if acc:
+        ref = ref + a.double()
+    din = torch.full((B, C) + tuple(di), float("nan"), device="cuda")
+    _lib.check(_lib.lib.ftb_test_trilinear_bwd(_lib.ptr(dout), B, C, *di, *do, _lib.ptr(a), _lib.ptr(din),
+                                               _lib.stream_ptr()))
+    assert not torch.isnan(din).any()
+    assert rel(din, ref) <= 4e-3   # bf16 output rounding
+
+
 # ------------------------------------------------------------------ whole-network gradients
 def _setup(ftb, dev, name):
     import importlib.util
