@@ -82,13 +82,20 @@ struct TrainCtx {
     }
     return it->second;
   }
-  // G(x) (+)= src
+  // G(x) (+)= src.  `src` is always the gradient of the calling closure's own output, which nobody reads after that
+  // closure: when it is the FIRST contribution to G(x) the slot simply takes over that buffer (no copy pass); later
+  // contributions add into it in place, after (stream order) the kernels that read it as `src`.
   int accumulate(const Act& x, const Act& src) {
     GradSlot& s = grad(x);
-    if (!dry) FTB_TRY(act_accum(s.g, src, s.init, st));
+    if (!s.init && alias_ok) {
+      s.g = src;
+    } else if (!dry) {
+      FTB_TRY(act_accum(s.g, src, s.init, st));
+    }
     s.init = true;
     return 0;
   }
+  bool alias_ok = getenv("FTB_TRAIN_NO_ALIAS") == nullptr;
   int need(const Act& x, Act* g, const char* what) {
     auto it = gmap.find(x.p);
     FTB_CHECK(it != gmap.end() && it->second.init, std::string("backward: no gradient reached ") + what);
