@@ -1,7 +1,7 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q -k "cond" 2>&1 | tail -4
-timeout 600 python tools/cond_train_bench.py 8 2>/dev/null | python -c "
-import json,sys; d=json.load(sys.stdin); print(d['cond_train_step'])"
-timeout 300 python tools/cond_bench.py 8 2>&1 | head -2
+export FTB_BENCH_MINIMAL=1
+CMD="python bench.py --train-only --steps 1 --warmup 1"
+timeout 300 $CMD > gpurun_out/train_plain.log 2>&1 && timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 860 -c 900 --csv --log-file gpurun_out/train_launches.csv $CMD > gpurun_out/ncu_train.log 2>&1
+echo rc=$?; cat gpurun_out/train_plain.log | tail -1
