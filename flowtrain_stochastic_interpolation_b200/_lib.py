@@ -87,6 +87,7 @@ _SIGS = {
     "ftb_ode_rk4_combine": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _d, _i64, _vp]),
     "ftb_denoise_drift": (_i, [_vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _i, _i64, _vp]),
     "ftb_decode": (_i, [_vp, _vp, _vp, _i, _i, _i, _i64, _vp]),
+    "ftb_decode_logits": (_i, [_vp, _vp, _vp, _i, _i, _i, _i64, _vp]),
     "ftb_embed": (_i, [_vp, _vp, _vp, _i, _i, _i, _i64, _i, _vp]),
     "ftb_ema_update": (_i, [_vp, _vp, _i64, _d, _vp]),
     "ftb_mse_ratio_accumulate": (_i, [_vp, _vp, _i64, _vp, _vp]),

@@ -416,6 +416,33 @@ __device__ __forceinline__ int decode_voxel(const float* __restrict__ xp, size_t
   return arg;
 }
 
+// decode(x, return_logits=True) (:398-399): the cosine logits [B, ncat, n] themselves, same fp32 op order
+__global__ void decode_logits_kernel(const float* __restrict__ x, const float* __restrict__ en,
+                                     float* __restrict__ logits, int B, int E, int ncat, size_t n) {
+  extern __shared__ float s_en[];
+  for (int i = threadIdx.x; i < ncat * E; i += blockDim.x) s_en[i] = en[i];
+  __syncthreads();
+  const size_t total = (size_t)B * n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / n);
+    const size_t v = i % n;
+    const float* xp = x + (size_t)b * E * n + v;
+    float xv[32];
+    float ss = 0.f;
+    for (int e = 0; e < E; ++e) {
+      xv[e] = __ldg(xp + (size_t)e * n);
+      ss = __fadd_rn(ss, __fmul_rn(xv[e], xv[e]));
+    }
+    const float nrm = fmaxf(__fsqrt_rn(ss), 1e-12f);
+    for (int e = 0; e < E; ++e) xv[e] = __fdiv_rn(xv[e], nrm);
+    for (int c = 0; c < ncat; ++c) {
+      float acc = 0.f;
+      for (int e = 0; e < E; ++e) acc = __fadd_rn(acc, __fmul_rn(xv[e], s_en[c * E + e]));
+      logits[((size_t)b * ncat + c) * n + v] = acc;
+    }
+  }
+}
+
 __global__ void decode_kernel(const float* __restrict__ x, const float* __restrict__ en,
                               long long* __restrict__ out, int B, int E, int ncat, size_t n) {
   extern __shared__ float s_en[];
@@ -609,6 +636,14 @@ int decode_argmax(const float* x, const float* en, long long* out, int B, int E,
   FTB_CHECK(E >= 1 && E <= 32, "decode: embedding dim must be in [1,32]");
   FTB_CHECK(ncat >= 1 && ncat <= 256, "decode: category count");
   decode_kernel<<<grid_for((size_t)B * n, 128), 128, (size_t)ncat * E * sizeof(float), st>>>(x, en, out, B, E, ncat, (size_t)n);
+  FTB_LAUNCH_OK();
+  return 0;
+}
+int decode_logits(const float* x, const float* en, float* logits, int B, int E, int ncat, long long n, cudaStream_t st) {
+  FTB_CHECK(E >= 1 && E <= 32, "decode: embedding dim must be in [1,32]");
+  FTB_CHECK(ncat >= 1 && ncat <= 256, "decode: category count");
+  decode_logits_kernel<<<grid_for((size_t)B * n, 128), 128, (size_t)ncat * E * sizeof(float), st>>>(x, en, logits, B, E, ncat,
+                                                                                                  (size_t)n);
   FTB_LAUNCH_OK();
   return 0;
 }

@@ -1162,6 +1162,10 @@ int ftb_vote_finalize(const int32_t* counts, int S, int ncat, int64_t n, int shi
   return vote_finalize(counts, S, ncat, n, shift, probs, entropy, reinterpret_cast<long long*>(most_probable),
                        entropy_masked, (cudaStream_t)stream);
 }
+int ftb_decode_logits(const float* x, const float* en, float* logits, int B, int E, int ncat, int64_t n, void* stream) {
+  FTB_CHECK(x && en && logits, "null argument");
+  return decode_logits(x, en, logits, B, E, ncat, n, (cudaStream_t)stream);
+}
 int ftb_embed(const int64_t* cats, const float* w, float* out, int B, int E, int ncat, int64_t n,
               int shift, void* stream) {
   FTB_CHECK(cats && w && out, "null argument");

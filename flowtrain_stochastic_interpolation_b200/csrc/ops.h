@@ -229,6 +229,7 @@ int denoise_drift(float* out, const float* x, const float* eta, const float* noi
                   float ad, float bd, float eps, int use_sde, long long n, cudaStream_t st);
 int decode_argmax(const float* x, const float* en, long long* out, int B, int E, int ncat,
                   long long n, cudaStream_t st);
+int decode_logits(const float* x, const float* en, float* logits, int B, int E, int ncat, long long n, cudaStream_t st);
 // ---- adaptive-step Runge-Kutta passes (ode_adaptive.cu); k: nk device pointers, coef: nk host doubles (already * dt)
 int ode_lincomb(float* out, const float* y0, const float* const* k, const double* coef, int nk, long long n,
                 cudaStream_t st);

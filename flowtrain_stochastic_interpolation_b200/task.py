@@ -46,8 +46,6 @@ def decode(weight: torch.Tensor, x: torch.Tensor, return_logits: bool = False) -
     """[B,E,X,Y,Z] -> [B,X,Y,Z] int64 nearest category by cosine similarity (decode, :373-404).
     One kernel, no [B,ncat,E,X,Y,Z] temporary; integer output bit-exact w.r.t. the reference's
     CPU op order.  The 15x18 embedding matrix is row-normalised on the host (F.normalize, :384)."""
-    if return_logits:
-        raise NotImplementedError("return_logits=True is not on the hot path (the fused kernel emits categories)")
     if not x.is_cuda:
         raise RuntimeError("decode runs on CUDA only (no CPU fallback)")
     en = F.normalize(weight.detach().float().cpu(), dim=1).to(x.device).contiguous()
@@ -57,6 +55,12 @@ def decode(weight: torch.Tensor, x: torch.Tensor, return_logits: bool = False) -
     xin = x.detach().float().contiguous()
     B = xin.shape[0]
     n = xin[0, 0].numel()
+    if return_logits:   # :398-399: the [B, ncat, X, Y, Z] cosine logits instead of their argmax
+        logits = torch.empty((B, ncat) + tuple(xin.shape[2:]), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib.ftb_decode_logits(_lib.ptr(xin), _lib.ptr(en), _lib.ptr(logits), B, E, ncat, n,
+                                                  _lib.stream_ptr()))
+        return logits
     out = torch.empty((B,) + tuple(xin.shape[2:]), dtype=torch.int64, device=x.device)
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib.ftb_decode(_lib.ptr(xin), _lib.ptr(en), _lib.ptr(out), B, E, ncat, n,

@@ -140,6 +140,8 @@ int ftb_denoise_drift(float* out, const float* x, const float* eta, const float*
 /* x [B,E,n] fp32, en [ncat,E] = F.normalize(embedding.weight) -> out [B,n] int64, bit-exact order */
 int ftb_decode(const float* x, const float* en, int64_t* out, int B, int E, int ncat, int64_t n,
                void* stream);
+/* decode(x, return_logits=True) (:398-399): logits [B,ncat,n] fp32, same op order as ftb_decode */
+int ftb_decode_logits(const float* x, const float* en, float* logits, int B, int E, int ncat, int64_t n, void* stream);
 /* cats [B,n] int64 (+shift, :366) , w [ncat,E] -> out [B,E,n] */
 int ftb_embed(const int64_t* cats, const float* w, float* out, int B, int E, int ncat, int64_t n,
               int shift, void* stream);
