@@ -1033,7 +1033,12 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   int nz_cap = 512 / (2 * p.N);
   if (nz_cap > 8) nz_cap = 8;
   if (nz_cap > p.Dext) nz_cap = p.Dext;
-  if (p.K == 1 && nz_cap > 2) nz_cap = 2;
+  {
+    // 1x1x1 convs: up to 4 flat 128-voxel tiles per accumulator group (fewer producer/issuer/epilogue hand-offs per
+    // byte moved; 2 -> 4 took the 1^3 launches of a Heun step from 2.35 to 2.16 ms)
+    static const int k1cap = getenv("FTB_K1_NZ") ? atoi(getenv("FTB_K1_NZ")) : 4;
+    if (p.K == 1 && nz_cap > k1cap) nz_cap = k1cap < 1 ? 1 : k1cap;
+  }
   if (const char* env = getenv("FTB_NZ")) {   // planner override for experiments
     const int v = atoi(env);
     if (v >= 1 && v < nz_cap) nz_cap = v;

@@ -1,7 +1,6 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-export FTB_BENCH_MINIMAL=1
-CMD="python bench.py --train-only --steps 1 --warmup 1"
-timeout 300 $CMD > gpurun_out/train_plain.log 2>&1 && timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 860 -c 900 --csv --log-file gpurun_out/train_launches.csv $CMD > gpurun_out/ncu_train.log 2>&1
-echo rc=$?; cat gpurun_out/train_plain.log | tail -1
+CMD="python bench.py --steps 1 --warmup 1 --batch 8 --no-e2e --no-cpu-baseline --no-train --no-extras"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_igemm -s 141 -c 14 -f -o gpurun_out/prof_k1up $CMD > gpurun_out/ncu_k1up.log 2>&1
+echo rc=$?
