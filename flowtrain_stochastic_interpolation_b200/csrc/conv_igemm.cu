@@ -1107,7 +1107,10 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   // Tiny volumes (4^3, 8^3 per sample): with NZ planes per group there are fewer work items than half the SMs and each
   // CTA runs a long serial MMA chain; trade depth-tap stacking for parallelism until the launch fills half the GPU.
   if (getenv("FTB_NO_NZ_SPREAD") == nullptr)
-    while (p.NZ > 1 && (long long)cols * cdiv(p.Dext, p.NZ) * w.ntiles < sms / 2) --p.NZ;
+  {
+    static const int spread_pct = getenv("FTB_SPREAD_PCT") ? atoi(getenv("FTB_SPREAD_PCT")) : 50;
+    while (p.NZ > 1 && (long long)cols * cdiv(p.Dext, p.NZ) * w.ntiles * 100 < (long long)sms * spread_pct) --p.NZ;
+  }
   int nslot = (int)((kSmemLimit - fixed - w_region) / p.slot_stride);
   nslot = nslot > kMaxSlots ? kMaxSlots : nslot;
   p.nslot = nslot;

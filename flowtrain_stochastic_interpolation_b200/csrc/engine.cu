@@ -644,7 +644,8 @@ struct Fwd {
       const size_t vox = x.voxels();
       // voxel slices per sample for the context GEMM: about two CTAs per SM over the batch, each
       // with at least a few 128-voxel tiles
-      int nsplit = cdiv(2 * num_sms(), B);
+      static const int kv_mult = getenv("FTB_KV_SPLIT") ? atoi(getenv("FTB_KV_SPLIT")) : 2;
+      int nsplit = cdiv(kv_mult * num_sms(), B);
       const int max_split = (int)((vox + 511) / 512);
       nsplit = nsplit > max_split ? max_split : nsplit;
       nsplit = nsplit < 1 ? 1 : (nsplit > 256 ? 256 : nsplit);
