@@ -1,5 +1,5 @@
 import os, sys, time, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import flowtrain_stochastic_interpolation_b200 as ftb
 from oracle import synth
 dev = torch.device("cuda:0")
