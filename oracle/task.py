@@ -114,14 +114,16 @@ def cond_training_grads(params, cfg, XT, ATb, T, VT):
     return loss.detach(), vhat.detach(), {k: (g if g is not None else torch.zeros_like(p[k])) for k, g in zip(names, grads)}
 
 
-def cond_training_loss(VT, VT_hat, XT, X1, T, mask, lambda_reconstruct):
+def cond_training_loss(VT, VT_hat, XT, X1_clean, T, mask, lambda_reconstruct, X1_noisy=None):
     """Loss of the conditional training_step (model_train_sh_inference_cond.py:432-452): flow loss with the 1e-6
-    guard plus the T-weighted reconstruction of the observed voxels, b_hat = XT + (1 - T) VT_hat on the mask."""
+    guard plus the T-weighted reconstruction of the observed voxels, b = X1[mask] taken BEFORE the 1e-4 noise is added
+    (:418), b_hat = XT + (1 - T) VT_hat on the mask (:434-436), normalised by mse(X1, 0) of the NOISY X1 (:446)."""
     Tb = T.view(-1, 1, 1, 1, 1)
-    b = X1[mask]
+    X1n = X1_clean if X1_noisy is None else X1_noisy
+    b = X1_clean[mask]
     b_hat = XT[mask] + ((1 - Tb) * VT_hat)[mask]
     mse = F.mse_loss(VT, VT_hat) / (F.mse_loss(VT, torch.zeros_like(VT)) + 1e-6)
-    rec = (Tb.squeeze() * F.mse_loss(b, b_hat)) / (F.mse_loss(X1, torch.zeros_like(X1)) + 1e-6)
+    rec = (Tb.squeeze() * F.mse_loss(b, b_hat)) / (F.mse_loss(X1n, torch.zeros_like(X1n)) + 1e-6)
     return mse + lambda_reconstruct * rec.mean()
 
 

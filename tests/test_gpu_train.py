@@ -463,12 +463,11 @@ def test_cond_flow_trainer_step_vs_oracle(ftb, dev):
     XT, VT = (1 - Tb) * x0 + Tb * X1, X1 - x0
     p = {k: v.to(dev).clone().requires_grad_(True) for k, v in params.items()}
     vhat = unet3d_cond.unet3d_cond_forward(p, cfg, XT, ATb, T)
-    b_clean = (ATb)[mask]   # X1_clean[mask] == ATb[mask]
-    b_hat = XT[mask] + ((1 - Tb) * vhat)[mask]
+    X1_clean = task.embed(W, batch).to(dev)                          # b = X1[mask] is taken before the noise (:418)
     F = torch.nn.functional
-    mse = F.mse_loss(VT, vhat) / (F.mse_loss(VT, torch.zeros_like(VT)) + 1e-6)
-    rec = ((Tb.squeeze() * F.mse_loss(b_clean, b_hat)) / (F.mse_loss(X1, torch.zeros_like(X1)) + 1e-6)).mean()
-    loss_o = mse + 1.0 * rec
+    loss_o = task.cond_training_loss(VT, vhat, XT, X1_clean, T, mask, 1.0, X1_noisy=X1)   # oracle: :432-452
+    rec = ((Tb.squeeze() * F.mse_loss(X1_clean[mask], XT[mask] + ((1 - Tb) * vhat)[mask]))
+           / (F.mse_loss(X1, torch.zeros_like(X1)) + 1e-6)).mean()
     grads = torch.autograd.grad(loss_o, [p[k] for k in params.keys()], allow_unused=True)
     gflat_o = torch.cat([(gr if gr is not None else torch.zeros_like(p[k])).reshape(-1) for k, gr in zip(params.keys(), grads)])
     print(f"cond loss {loss.item():.6f} (oracle {loss_o.item():.6f}); flow {tr.last_terms[0].item():.6f} rec {tr.last_terms[1].item():.6f}")
