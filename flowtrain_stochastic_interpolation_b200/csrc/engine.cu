@@ -971,6 +971,13 @@ size_t ftb_unet3d_cond_workspace_bytes(ftb_unet* h, int B, int atb_B, int X, int
   return workspace_bytes_impl(h, B, atb_B, X, Y, Z);
 }
 
+// A sampling / fp32 forward on the handle ends the life of a recorded training tape: the host keeps ONE resident
+// workspace per module, so the tape's activations are about to be freed or overwritten (a later backward would
+// otherwise pass the base-pointer check on a recycled block and read clobbered activations).
+static void invalidate_tape(ftb_unet* h) {
+  if (h->train) h->train->valid = false;
+}
+
 int ftb_unet3d_forward(ftb_unet* h, const float* x, const float* t, float* out, int B, int X, int Y,
                        int Z, void* workspace, size_t workspace_bytes, void* stream) {
   FTB_TRY(check_dims(h, B, X, Y, Z));
@@ -983,6 +990,7 @@ int ftb_unet3d_forward(ftb_unet* h, const float* x, const float* t, float* out, 
   cudaStream_t st = (cudaStream_t)stream;
   FTB_TRY(ensure_device(h));
   FTB_TRY(finalize(h, st));
+  invalidate_tape(h);
   Fwd f{h, st, reinterpret_cast<char*>(workspace), 0, workspace_bytes, false, B};
   return f.run(x, t, out, X, Y, Z);
 }
@@ -1004,6 +1012,7 @@ static int forward_f32_impl(ftb_unet* h, const float* x, const float* atb, const
   FTB_TRY(ensure_device(h));
   FTB_TRY(finalize(h, st, true));
   FTB_TRY(finalize_f32(h, st));
+  invalidate_tape(h);
   FwdF32 f{h, st, reinterpret_cast<char*>(workspace), false, B};
   return f.run(x, t, out, X, Y, Z, atb);
 }
@@ -1037,6 +1046,7 @@ int ftb_unet3d_cond_forward(ftb_unet* h, const float* x, const float* atb, int a
   FTB_TRY(ensure_device(h));
   const bool was_dirty = h->dirty;
   FTB_TRY(finalize(h, st));
+  invalidate_tape(h);
   Fwd f{h, st, reinterpret_cast<char*>(workspace), 0, workspace_bytes, false, B};
   f.atb = atb;
   f.atb_B = atb_B;

@@ -48,8 +48,9 @@ class EnsembleVotes:
     def all_reduce(self, group=None):
         """Sum the histograms (and sample counts) of all ranks: the only collective of ensemble sampling."""
         import torch.distributed as dist
+        from .sharding import reduce_votes
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.counts, group=group)
+            reduce_votes(self.counts, dist.get_world_size(group), group=group)
             tot = torch.tensor([self.samples], dtype=torch.int64, device=self.device)
             dist.all_reduce(tot, group=group)
             self.samples = int(tot.item())

@@ -53,11 +53,13 @@ def gather_samples(local: torch.Tensor, n_samples: int, rank: int, world: int, d
     return out
 
 
-def vote_histogram(decoded_local: torch.Tensor, n_cat: int, world: int, dst: int = 0):
-    """Per-voxel category counts over the whole ensemble: local one-hot sum, then one reduce."""
-    hist = torch.zeros((n_cat,) + tuple(decoded_local.shape[1:]), dtype=torch.int32, device=decoded_local.device)
-    hist.scatter_add_(0, decoded_local.long().clamp(0, n_cat - 1),
-                      torch.ones_like(decoded_local, dtype=torch.int32))
+def reduce_votes(counts: torch.Tensor, world: int, dst: int = None, group=None):
+    """The one collective of ensemble sampling: sum the per-rank int32 vote histograms [n_cat, X, Y, Z] that
+    ``EnsembleVotes.add`` (decode -> histogram kernel) accumulated.  ``dst=None``: all-reduce (every rank gets the
+    ensemble statistics); otherwise a reduce onto ``dst``.  In place; no-op for world 1."""
     if world > 1:
-        dist.reduce(hist, dst=dst, op=dist.ReduceOp.SUM)
-    return hist
+        if dst is None:
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+        else:
+            dist.reduce(counts, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    return counts

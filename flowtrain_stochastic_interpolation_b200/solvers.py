@@ -6,17 +6,23 @@ model is called as ``model(XT, T)`` with ``T = full((B,), t_k)`` fp32 (:68-70), 
 zeroes the velocity on the masked trailing dims (:71-73), and the eq-6.7 drift / SDE term follow
 :138-143 / :205-216.
 
-Difference, stated once: the reference hands ``ode_func`` to torchdiffeq's ADAPTIVE dopri5 /
-adaptive_heun.  The default here integrates on the FIXED grid above with ``method`` in
-{"euler", "heun", "rk4"} (torchdiffeq fixed-grid convention, one step per grid interval);
-``method="dopri5"`` / ``"adaptive_heun"`` run a restatement of torchdiffeq's adaptive loop
-(``integrate_adaptive``: one host round trip per attempted step for the error ratio).  The
-stage combinations run as single fused kernels (ftb_ode_axpy / heun_combine / rk4_combine) on the
-fp32 state, and no host synchronisation happens inside the loop (the reference does one
-``t.item()`` device->host sync per evaluation).  ``return_trajectory=False`` keeps only the end
-state (the 16-point trajectory at 64^3 is 1.2 GB per sample batch of 4).
+The reference hands ``ode_func`` to torchdiffeq's ADAPTIVE dopri5 (ODE solvers, :77, :148) /
+adaptive_heun (SDE solver, :220-222) with ``atol`` / ``rtol``, and ``n_steps`` is the number of OUTPUT
+points.  Called with the reference signature — ``ODEFlowSolver(model, rtol=1e-6).solve(X0, t0=t0, tf=tf,
+n_steps=16)``, model_train_inference.py:615-619 — the classes here do the same: ``method=None`` selects
+the adaptive stepper the reference uses (``integrate_adaptive``, a restatement of torchdiffeq's loop;
+the step controller lives on the device, see ``ode_adaptive.cu``).  The fixed-grid integrators are an
+explicit opt-in, ``method`` in {"euler", "heun", "rk4"} (torchdiffeq's fixed-grid convention: one step
+per grid interval, so ``n_steps`` points = ``n_steps - 1`` steps); ``atol`` / ``rtol`` have no meaning
+there and passing non-default values with a fixed-grid method raises.  The stage combinations run as
+single fused kernels (ftb_ode_axpy / heun_combine / rk4_combine / ftb_ode_lincomb) on the fp32 state,
+and the fixed-grid loop has no host synchronisation (the reference does one ``t.item()`` device->host
+sync per evaluation).  ``return_trajectory=False`` keeps only the end state (the 16-point trajectory at
+64^3 is 1.2 GB per sample batch of 4).
 """
 from __future__ import annotations
+
+import warnings
 
 import torch
 
@@ -25,6 +31,27 @@ from .interpolation import BaseInterpolant
 
 METHODS = ("euler", "heun", "rk4")
 ADAPTIVE_METHODS = ("dopri5", "adaptive_heun")
+_DEFAULT_TOL = 1e-6   # reference defaults (:35, :105, :170)
+
+
+def _resolve_method(method, default, atol, rtol, model):
+    """``method=None`` -> the reference's adaptive stepper.  Fixed-grid methods ignore atol / rtol, so a caller who
+    passes tolerances AND a fixed grid is told instead of silently losing the accuracy they asked for."""
+    if method is None:
+        method = default
+    if method not in METHODS + ADAPTIVE_METHODS:
+        raise ValueError(f"method must be one of {METHODS + ADAPTIVE_METHODS}, got {method!r}")
+    if method in METHODS and (atol != _DEFAULT_TOL or rtol != _DEFAULT_TOL):
+        raise ValueError(f"atol / rtol were given together with the fixed-grid method {method!r}, which ignores them; "
+                         f"drop them or use method={default!r}")
+    if method in ADAPTIVE_METHODS and getattr(model, "precision", None) == "bf16" and min(atol, rtol) < 1e-3:
+        warnings.warn(
+            f"adaptive {method} at atol={atol:g} / rtol={rtol:g} around a bf16 velocity field: the field's own rounding "
+            "noise (~5e-3 relative) is far above the tolerance, so the controller will shrink the step until the "
+            "error estimate resolves that noise.  Use model.set_precision('fp32') for the reference's accuracy, loosen "
+            "the tolerances, or pass an explicit fixed-grid method ('euler' | 'heun' | 'rk4').", RuntimeWarning,
+            stacklevel=3)
+    return method
 
 # Butcher tableaus as torchdiffeq defines them (dopri5.py, adaptive_heun.py): alpha, beta rows, c_sol, c_error, c_mid
 _DOPRI5 = dict(
@@ -89,15 +116,16 @@ def _prep_mask(frozen_mask, x):
     return m.to(torch.uint8).contiguous()
 
 
-def integrate_fixed(func, X0, t0, tf, n_steps, method="euler", return_trajectory=True):
-    """Fixed-grid integration of dx/dt = func(t_k (python float), x, eval_index)."""
+def integrate_fixed(func, X0, t0, tf, n_steps, method="euler", return_trajectory=True, grid_dtype=torch.float32):
+    """Fixed-grid integration of dx/dt = func(t_k (python float), x, eval_index).  ``grid_dtype``: dtype of the
+    reference's ``linspace`` (fp32 at :59 / :187, float64 at :126)."""
     if method not in METHODS:
         raise ValueError(f"method must be one of {METHODS}")
     if not X0.is_cuda:
         raise RuntimeError("the samplers run on CUDA only (no CPU fallback)")
     if len(X0.shape) == 3:  # solvers.py:62-63
         X0 = X0.unsqueeze(0)
-    grid = torch.linspace(t0, tf, n_steps)  # fp32 on the host, as :59
+    grid = torch.linspace(t0, tf, n_steps, dtype=grid_dtype)  # on the host
     x = _flat(X0).clone()
     traj = torch.empty((n_steps,) + tuple(x.shape), dtype=torch.float32, device=x.device) if return_trajectory else None
     if traj is not None:
@@ -150,7 +178,7 @@ def _lincomb(out, y0, ks, coefs):
 
 
 def integrate_adaptive(func, X0, t0, tf, n_steps, method="dopri5", rtol=1e-6, atol=1e-6, return_trajectory=True,
-                       max_num_steps=100000, stats=None):
+                       max_num_steps=100000, stats=None, grid_dtype=torch.float32):
     """torchdiffeq's adaptive Runge-Kutta loop (rk_common.RKAdaptiveStepsizeODESolver of torchdiffeq 0.2.x, the
     un-vendored dependency behind solvers.py:77, :148, :220-222) restated: initial step from ``_select_initial_step``,
     steps accepted when the RMS of error / (atol + rtol max(|y0|, |y1|)) is <= 1, step factor
@@ -170,7 +198,7 @@ def integrate_adaptive(func, X0, t0, tf, n_steps, method="dopri5", rtol=1e-6, at
     dev = y0.device
     lib = _lib.lib
     # the reference builds the output grid in fp32 (solvers.py:59); torchdiffeq then carries time in float64
-    grid = [float(v) for v in torch.linspace(t0, tf, n_steps)] if n_steps > 1 else [float(t0)]
+    grid = [float(v) for v in torch.linspace(t0, tf, n_steps, dtype=grid_dtype)] if n_steps > 1 else [float(t0)]
     acc = torch.zeros(1, dtype=torch.float64, device=dev)
     n_eval = 0
 
@@ -244,23 +272,24 @@ def integrate_adaptive(func, X0, t0, tf, n_steps, method="dopri5", rtol=1e-6, at
     return traj if traj is not None else (last if len(grid) > 1 else y0)
 
 
-def _integrate(func, X0, t0, tf, n_steps, method, return_trajectory, rtol, atol, stats=None):
+def _integrate(func, X0, t0, tf, n_steps, method, return_trajectory, rtol, atol, stats=None, grid_dtype=torch.float32):
     if method in ADAPTIVE_METHODS:
-        return integrate_adaptive(func, X0, t0, tf, n_steps, method, rtol, atol, return_trajectory, stats=stats)
-    return integrate_fixed(func, X0, t0, tf, n_steps, method, return_trajectory)
+        return integrate_adaptive(func, X0, t0, tf, n_steps, method, rtol, atol, return_trajectory, stats=stats,
+                                  grid_dtype=grid_dtype)
+    return integrate_fixed(func, X0, t0, tf, n_steps, method, return_trajectory, grid_dtype)
 
 
 class ODEFlowSolver:
-    """Flow ODE dx/dt = model(x, t) — reference ODEFlowSolver (:14-77).  ``method`` "euler" | "heun" | "rk4" integrate
-    on the fixed output grid (see module doc); "dopri5" / "adaptive_heun" are the reference's adaptive steppers
-    (``atol`` / ``rtol`` as in :35) — use them with ``model.set_precision("fp32")``: the bf16 velocity field's own noise
-    (~5e-3) is far above the reference's 1e-6 tolerances and would drive the step size to the floor."""
+    """Flow ODE dx/dt = model(x, t) — reference ODEFlowSolver (:14-77).  Default (``method=None``): the reference's
+    adaptive dopri5 with ``atol`` / ``rtol`` (:35, :77) — use it with ``model.set_precision("fp32")``: the bf16
+    velocity field's own noise (~5e-3) is far above the reference's 1e-6 tolerances (a RuntimeWarning says so).
+    ``method`` "euler" | "heun" | "rk4" integrate on the fixed output grid instead (see module doc)."""
 
-    def __init__(self, model, atol=1e-6, rtol=1e-6, method="euler"):
+    def __init__(self, model, atol=1e-6, rtol=1e-6, method=None):
         self.model = model
         self.atol = atol
         self.rtol = rtol
-        self.method = method
+        self.method = _resolve_method(method, "dopri5", atol, rtol, model)
 
     def solve(self, X0, frozen_mask=None, t0=0.0, tf=1.0, n_steps=32, return_trajectory=True):
         if len(X0.shape) == 3:
@@ -281,12 +310,12 @@ class ODEFlowSolver:
 class ODEOneSidedDenoisingSolver:
     """Eq. (6.7) ODE from a learned denoiser — reference :80-148."""
 
-    def __init__(self, model, interpolant: BaseInterpolant, atol=1e-6, rtol=1e-6, method="euler"):
+    def __init__(self, model, interpolant: BaseInterpolant, atol=1e-6, rtol=1e-6, method=None):
         self.model = model
         self.interp = interpolant
         self.atol = atol
         self.rtol = rtol
-        self.method = method
+        self.method = _resolve_method(method, "dopri5", atol, rtol, model)   # :148
         assert isinstance(interpolant, BaseInterpolant), "ODEOneSidedDenoisingSolver requires a BaseInterpolant"
         assert self.interp.is_one_sided(), "ODEOneSidedDenoisingSolver requires a one-sided interpolant"
 
@@ -312,7 +341,8 @@ class ODEOneSidedDenoisingSolver:
                 eta = _flat(self.model(XT, tbuf))
                 return self._drift(t, XT, eta)
 
-        return _integrate(ode_func, X0, t0, tf, n_steps, self.method, return_trajectory, self.rtol, self.atol)
+        return _integrate(ode_func, X0, t0, tf, n_steps, self.method, return_trajectory, self.rtol, self.atol,
+                          getattr(self, "stats", None), grid_dtype=torch.float64)   # float64 linspace, :126
 
 
 class SDEOneSidedDenoisingSolver(ODEOneSidedDenoisingSolver):
@@ -321,17 +351,22 @@ class SDEOneSidedDenoisingSolver(ODEOneSidedDenoisingSolver):
     ``eval_index -> tensor``) makes the draws explicit for parity tests; by default
     ``torch.randn_like`` is drawn once per evaluation like the reference (:212)."""
 
-    def __init__(self, model, interpolant, epsilon, atol=1e-6, rtol=1e-6, method="heun", noise=None):
+    def __init__(self, model, interpolant, epsilon, atol=1e-6, rtol=1e-6, method=None, noise=None):
         self.model = model
         self.interp = interpolant
         self.epsilon = epsilon if callable(epsilon) else (lambda t: epsilon)
         self.atol = atol
         self.rtol = rtol
-        self.method = method
+        self.method = _resolve_method(method, "adaptive_heun", atol, rtol, model)   # :220-222
         self.noise = noise
 
     def solve(self, X0, t0=0.0, tf=1.0, n_steps=32, return_trajectory=True):
         assert self.interp.one_sided, "ODEOneSidedDenoisingSolver requires a one-sided interpolant"
+        if self.method in ADAPTIVE_METHODS and self.noise is None:
+            warnings.warn("SDEOneSidedDenoisingSolver with the reference's adaptive_heun draws fresh noise in every "
+                          "evaluation, so the embedded error estimate never falls below atol / rtol and the step size "
+                          "collapses (the reference behaves the same, solvers.py:212-222); pass method='heun' for a "
+                          "fixed-grid solve.", RuntimeWarning, stacklevel=2)
         if len(X0.shape) == 3:
             X0 = X0.unsqueeze(0)
         tbuf = torch.empty(X0.shape[0], dtype=torch.float32, device=X0.device)

@@ -152,6 +152,52 @@ class UnetTrainFn(torch.autograd.Function):
         return (None, None, None, None, *grads)
 
 
+class _CondLossFn(torch.autograd.Function):
+    """Flow + T-weighted masked reconstruction loss of the conditional training_step
+    (model_train_sh_inference_cond.py:434-452) and its gradient w.r.t. VT_hat: ftb_cond_loss_accumulate / _grad."""
+
+    @staticmethod
+    def forward(ctx, VT, VT_hat, XT, X1c, X1, mask, T, lam):
+        f = lambda t: t.detach().float().contiguous()
+        VT, vhat, XT, X1c, X1, T = f(VT), f(VT_hat), f(XT), f(X1c), f(X1), f(T)
+        m8 = mask.contiguous().view(torch.uint8)
+        B, E = X1.shape[0], X1.shape[1]
+        n = X1[0, 0].numel()
+        acc6 = torch.zeros(6, dtype=torch.float64, device=VT.device)
+        with torch.cuda.device(VT.device):
+            _lib.check(_lib.lib.ftb_cond_loss_accumulate(_lib.ptr(VT), _lib.ptr(vhat), _lib.ptr(XT), _lib.ptr(X1c),
+                                                         _lib.ptr(X1), _lib.ptr(m8), _lib.ptr(T), B, E, n,
+                                                         _lib.ptr(acc6), _lib.stream_ptr()))
+        ctx.save_for_backward(VT, vhat, XT, X1c, m8, T, acc6)
+        ctx.lam = float(lam)
+        N = float(VT.numel())
+        flow = (acc6[0] / N) / (acc6[1] / N + 1e-6)
+        rec = (acc6[5] / B) * (acc6[2] / acc6[3]) / (acc6[4] / N + 1e-6)
+        ctx.mark_non_differentiable(flow, rec)
+        return (flow + ctx.lam * rec).float(), flow.float(), rec.float()
+
+    @staticmethod
+    def backward(ctx, gout, _gf, _gr):
+        VT, vhat, XT, X1c, m8, T, acc6 = ctx.saved_tensors
+        B, E = X1c.shape[0], X1c.shape[1]
+        n = X1c[0, 0].numel()
+        dout = torch.empty_like(vhat)
+        with torch.cuda.device(VT.device):
+            _lib.check(_lib.lib.ftb_cond_loss_grad(_lib.ptr(VT), _lib.ptr(vhat), _lib.ptr(XT), _lib.ptr(X1c),
+                                                   _lib.ptr(m8), _lib.ptr(T), B, E, n, _lib.ptr(acc6), ctx.lam, 1.0,
+                                                   _lib.ptr(dout), _lib.stream_ptr()))
+        return None, dout.mul_(gout.to(dout.dtype)), None, None, None, None, None, None
+
+
+def cond_loss(VT, VT_hat, XT, X1_clean, X1, mask, T, lambda_reconstruct=1.0):
+    """(loss, flow_loss, reconstruct_loss) of the conditional training_step (:434-452); ``loss`` is differentiable
+    w.r.t. ``VT_hat``.  ``mask``: the bool [B,1,X,Y,Z] conditioning mask, ``X1_clean`` the embedding before the 1e-4
+    noise (``b`` is gathered from it, :417)."""
+    if not VT.is_cuda:
+        raise RuntimeError("cond_loss runs on CUDA only (no CPU fallback)")
+    return _CondLossFn.apply(VT, VT_hat, XT, X1_clean, X1, mask, T, lambda_reconstruct)
+
+
 # --------------------------------------------------------------------------- fused training step
 class BucketAllReduce:
     """Starts ``all_reduce(sum)`` of gradient ranges on a side stream as the backward completes them
@@ -241,9 +287,19 @@ class FlowTrainer:
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=self.flat.device)
         self.acc = torch.zeros(2, dtype=torch.float64, device=self.flat.device)
         self.last_grad_norm = None
-        # parameters the reference keeps frozen get a zero gradient (freqs / phases when not learned)
+        # parameters the reference keeps frozen (freqs / phases when not learned) get a zero gradient and are left
+        # out of the optimiser launches: torch's Adam / AdamW skip parameters without a gradient, so decoupled weight
+        # decay must not touch them either
         self.frozen = [(off, p.numel()) for (n, p), off in zip(self.net.named_parameters(), self.net._flat_offsets)
                        if not p.requires_grad]
+        self.trainable = []
+        for (n, p), off in zip(self.net.named_parameters(), self.net._flat_offsets):
+            if not p.requires_grad:
+                continue
+            if self.trainable and self.trainable[-1][0] + self.trainable[-1][1] == off:
+                self.trainable[-1] = (self.trainable[-1][0], self.trainable[-1][1] + p.numel())
+            else:
+                self.trainable.append((off, p.numel()))
 
     def broadcast_parameters(self, src=0):
         if self.distributed:
@@ -291,10 +347,11 @@ class FlowTrainer:
         self.step_count += 1
         self.sumsq.zero_()
         _lib.check(lib.ftb_grad_sumsq(_lib.ptr(self.gflat), self.gflat.numel(), _lib.ptr(self.sumsq), st))
-        _lib.check(lib.ftb_adam_step(_lib.ptr(self.flat), _lib.ptr(self.gflat), _lib.ptr(self.m), _lib.ptr(self.v),
-                                     self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps,
-                                     self.weight_decay, 1 if self.decoupled else 0, self.step_count,
-                                     _lib.ptr(self.sumsq), 1.0 / self.world, self.max_grad_norm, st))
+        for off, cnt in self.trainable:     # one launch when nothing is frozen (contiguous ranges are merged)
+            _lib.check(lib.ftb_adam_step(_lib.ptr(self.flat[off:]), _lib.ptr(self.gflat[off:]), _lib.ptr(self.m[off:]),
+                                         _lib.ptr(self.v[off:]), cnt, self.lr, self.betas[0], self.betas[1], self.eps,
+                                         self.weight_decay, 1 if self.decoupled else 0, self.step_count,
+                                         _lib.ptr(self.sumsq), 1.0 / self.world, self.max_grad_norm, st))
         _lib.check(lib.ftb_unet3d_mark_dirty(net._handle))
         net._flat_versions = None
         if self.ema_decay is not None and self.step_count >= self.ema_start_step:   # callbacks.py:243-266

@@ -113,6 +113,7 @@ class Unet3D(nn.Module):
         self._use_graph = False
         self.last_launches = 0
         self._flat = None      # flat fp32 parameter buffer once training.flatten_parameters() bound it
+        self._flat_versions = None
         self._drop_seed = None  # explicit dropout seed for the next train-mode forward (tests); else a counter
         self._drop_count = 0
         self.precision = "bf16"  # "bf16": tensor-core operands in bf16; "fp32": 3 x bf16 split convs, fp32 elsewhere
@@ -225,6 +226,20 @@ class Unet3D(nn.Module):
                                                      d.numel(), st))
             self._synced[name] = key
             self._graphs.clear()   # new weights are re-packed by launches outside any captured graph
+
+    def mark_dirty(self):
+        """Tell the engine that parameter VALUES changed behind autograd's back.  Weight changes are normally
+        detected through each parameter's ``(data_ptr, _version)``; ``param.data.copy_(...)`` (what the reference's
+        ``EMACallback.apply_ema_weights`` / ``restore_original_weights`` do, callbacks.py) changes the values without
+        bumping the version counter, so call this after such a swap: every parameter is re-sent, packed weights are
+        rebuilt on the next forward, captured graphs and the cached ATb branch are dropped."""
+        self._synced.clear()
+        self._flat_versions = None
+        self._graphs.clear()
+        if hasattr(self, "_atb_key"):
+            self.invalidate_conditioning()
+        _lib.check(_lib.lib.ftb_unet3d_mark_dirty(self._handle))
+        return self
 
     def _get_workspace(self, device, B, X, Y, Z):
         key = (str(device), B, X, Y, Z)
@@ -405,6 +420,15 @@ class Unet3DCond(Unet3D):
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
         self._atb_key = None
+        self._atb_keepalive = None
+
+    def invalidate_conditioning(self):
+        """Drop the cached ATb-only branch: the next forward recomputes ``init_conv_ATb`` and every ``EmbedATb``.
+        Needed only after writing into the conditioning volume through ``.data`` (no version bump); any other change
+        of ATb (new tensor, in-place op, new shape) or of the weights is detected."""
+        self._atb_key = None
+        self._atb_keepalive = None
+        return self
 
     def _get_workspace_cond(self, device, B, atb_B, X, Y, Z):
         key = (str(device), B, X, Y, Z, atb_B)
@@ -414,7 +438,7 @@ class Unet3DCond(Unet3D):
             if nbytes == 0:
                 raise _lib.FtbError(_lib.last_error())
             self._workspace.clear()
-            self._atb_key = None
+            self.invalidate_conditioning()
             ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
             self._workspace[key] = ws
         return ws
@@ -436,7 +460,7 @@ class Unet3DCond(Unet3D):
                 raise AssertionError(f"Input and ATb shapes do not match: {tuple(x.shape)} and {tuple(ATb.shape)}")
             if self._flat is None:
                 flatten_parameters(self)
-            self._atb_key = None   # the training workspace replaces the sampling one
+            self.invalidate_conditioning()   # the training workspace replaces the sampling one
             tin = time.detach().to(device=x.device, dtype=torch.float32).contiguous()
             return UnetTrainFn.apply(self, self._f32c(x), tin, self._f32c(ATb), *self.parameters())
         if self.precision == "fp32":
@@ -450,13 +474,18 @@ class Unet3DCond(Unet3D):
             return out if x.dtype == torch.float32 else out.to(x.dtype)
         with torch.cuda.device(x.device):
             xin = self._f32c(x)
-            ain = self._f32c(ATb)
+            # ``ATb.expand(n_samples, ...)`` (model_inference_experiments.py:230-232) is one volume seen B times:
+            # run the ATb-only branch once for the whole batch instead of materialising B copies
+            ain = self._f32c(ATb[:1] if (B > 1 and ATb.shape[0] == B and ATb.stride(0) == 0) else ATb)
             tin = time.detach().to(device=x.device, dtype=torch.float32).contiguous()
             synced_before = dict(self._synced)
             self._sync_params(x.device)
             ws = self._get_workspace_cond(x.device, B, ain.shape[0], X, Y, Z)
             base = (ws.data_ptr() + 255) // 256 * 256
-            key = (ATb.data_ptr(), ATb._version, tuple(ATb.shape), ws.data_ptr())
+            # The cache key names the CALLER's tensor, and that tensor is kept alive below: while it lives, the
+            # caching allocator cannot hand its address to a different conditioning volume (an expanded / converted
+            # ATb that was freed and replaced by a fresh one of the same shape used to alias the old key).
+            key = (ATb.data_ptr(), ATb._version, tuple(ATb.shape), tuple(ATb.stride()), ATb.dtype, ws.data_ptr())
             reuse = self._atb_key == key and synced_before == self._synced
             out = torch.empty_like(xin)
             _lib.check(_lib.lib.ftb_unet3d_cond_forward(
@@ -464,6 +493,6 @@ class Unet3DCond(Unet3D):
                 B, X, Y, Z, C.c_void_p(base), ws.numel() - (base - ws.data_ptr()), 1 if reuse else 0,
                 _lib.stream_ptr()))
             self._atb_key = key
-            self._ain_keepalive = ain
+            self._atb_keepalive = (ATb, ain)
             self.last_launches = _lib.lib.ftb_unet3d_last_launches(self._handle)
         return out if x.dtype == torch.float32 else out.to(x.dtype)

@@ -20,7 +20,10 @@ def main():
     mine = list(sharding.shard_indices(n, rank, world))
     local = torch.stack([fake_sample(i) for i in mine])
     full = sharding.gather_samples(local, n, rank, world)
-    hist = sharding.vote_histogram(local, 15, world)
+    # stand-in for the per-rank histogram the decode -> vote kernel accumulates (EnsembleVotes.counts)
+    hist = torch.zeros(15, 4, 4, 4, dtype=torch.int32)
+    hist.scatter_add_(0, local, torch.ones_like(local, dtype=torch.int32))
+    hist = sharding.reduce_votes(hist, world, dst=0)
     # max-over-ranks timing reduction used by bench.py
     t = torch.tensor([1.0 + rank])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -222,3 +222,87 @@ def test_precision_switch_and_solver_method_validation():
     assert cnet.set_precision("fp32").precision == "fp32"
     names = [n for n, _ in cnet.named_parameters()]
     assert names[0] == "init_conv_x.weight" and "downs.0.0.conv1.weight" in names and "downs.0.1.time_mlp.1.weight" in names
+
+
+def test_solver_defaults_follow_the_reference_call():
+    """``ODEFlowSolver(model, rtol=1e-6).solve(X0, t0, tf, n_steps=16)`` (model_train_inference.py:615-619) is an
+    ADAPTIVE dopri5 solve with 16 output points in the reference (solvers.py:77); the drop-in must not silently turn it
+    into 15 Euler steps.  The SDE solver defaults to adaptive_heun (solvers.py:220-222); fixed grids are explicit."""
+    import warnings
+    ip = ftb.LinearInterpolant(one_sided=True)
+    toy = lambda x, t: x
+    assert ftb.ODEFlowSolver(toy, rtol=1e-6).method == "dopri5"
+    assert ftb.ODEOneSidedDenoisingSolver(toy, ip).method == "dopri5"
+    assert ftb.SDEOneSidedDenoisingSolver(toy, ip, epsilon=torch.tensor(0.1)).method == "adaptive_heun"
+    assert ftb.ODEFlowSolver(toy, method="heun").method == "heun"
+    with pytest.raises(ValueError, match="fixed-grid"):      # tolerances + fixed grid: refuse, do not ignore
+        ftb.ODEFlowSolver(toy, rtol=1e-4, method="euler")
+    with pytest.raises(ValueError, match="method must be"):
+        ftb.ODEFlowSolver(toy, method="rk45")
+    with pytest.raises(AssertionError, match="one-sided"):
+        ftb.ODEOneSidedDenoisingSolver(toy, ftb.LinearInterpolant(one_sided=False))
+    net = ftb.Unet3D(**synth.make_cfg(dim=32, dim_mults=(1, 2), attn_heads=2, attn_dim_head=16, time_resolution=64))
+    with warnings.catch_warnings(record=True) as w:          # bf16 field + 1e-6 tolerances: say so
+        warnings.simplefilter("always")
+        ftb.ODEFlowSolver(net)
+        assert any("bf16" in str(x.message) for x in w)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        ftb.ODEFlowSolver(net.set_precision("fp32"))
+        ftb.ODEFlowSolver(net.set_precision("bf16"), method="heun")
+        assert not w
+
+
+def test_task_modules_have_the_lightning_surface():
+    """training_step / configure_optimizers / checkpoint hooks of the reference LightningModules
+    (model_train_inference.py:417-484, model_train_sh_inference_cond.py:401-495): present, same optimiser classes,
+    same hyper-parameter plumbing.  (The compute inside training_step is covered by the -m gpu tests.)"""
+    small = dict(dim=32, dim_mults=(1, 2), attn_heads=2, attn_dim_head=16, time_resolution=64)
+    m = ftb.Geo3DStochInterp(embedding_dim=18, learning_rate=2e-4, lr_decay=0.997, **small)
+    for hook in ("training_step", "configure_optimizers", "on_save_checkpoint", "on_load_checkpoint",
+                 "on_train_epoch_end", "embed", "decode", "forward"):
+        assert callable(getattr(m, hook)), hook
+    o = m.configure_optimizers()
+    assert type(o["optimizer"]) is torch.optim.Adam and o["optimizer"].param_groups[0]["lr"] == 2e-4
+    assert isinstance(o["lr_scheduler"], torch.optim.lr_scheduler.ExponentialLR) and o["lr_scheduler"].gamma == 0.997
+    # the optimiser sees exactly the trainable parameters of net (the simplex embedding is frozen, :316)
+    n_opt = sum(p.numel() for g in o["optimizer"].param_groups for p in g["params"] if p.requires_grad)
+    assert n_opt == sum(p.numel() for p in m.net.parameters() if p.requires_grad)
+    ck = {}
+    m.ema_shadow = {"net.final_conv.bias": torch.ones(18)}
+    m.on_save_checkpoint(ck)
+    assert ck["ema_shadow"] is m.ema_shadow
+    m2 = ftb.Geo3DStochInterp(embedding_dim=18, **small)
+    m2.on_load_checkpoint(ck)
+    assert m2.ema_shadow is ck["ema_shadow"]
+    c = ftb.Geo3DStochInterpCond(embedding_dim=15, time_learned_emb=True, **small)
+    assert c.hparams.learning_rate == 2e-3 and c.hparams.lr_decay == 0.997     # reference defaults :284-285
+    oc = c.configure_optimizers()
+    assert type(oc["optimizer"]) is torch.optim.AdamW and oc["optimizer"].param_groups[0]["lr"] == 2e-3
+    assert callable(c.training_step) and callable(c.on_after_backward)
+    with pytest.raises(RuntimeError, match="CUDA"):           # no CPU fallback inside the step either
+        m.training_step(torch.zeros(1, 1, 8, 8, 8, dtype=torch.long))
+
+
+def test_mark_dirty_and_ema_swap_plumbing():
+    """``param.data.copy_`` (the reference EMACallback's weight swap) does not bump the version counter the weight
+    sync watches; ``mark_dirty`` clears the sync state so the next forward re-reads every parameter, and
+    ``load_model_with_ema_option`` calls it."""
+    small = dict(dim=32, dim_mults=(1, 2), attn_heads=2, attn_dim_head=16, time_resolution=64)
+    m = ftb.Geo3DStochInterp(embedding_dim=18, **small)
+    net = m.net
+    net._synced = {n: (p.data_ptr(), p._version) for n, p in net.named_parameters()}   # as after a forward
+    p = net.final_conv.bias
+    v0 = p._version
+    p.data.copy_(torch.ones_like(p))
+    assert p._version == v0                      # the hazard: invisible to the (data_ptr, _version) key
+    net.mark_dirty()
+    assert net._synced == {}
+    shadow = {f"net.{n}": torch.full_like(q, 0.25) for n, q in net.named_parameters() if q.requires_grad}
+    net._synced = {n: (q.data_ptr(), q._version) for n, q in net.named_parameters()}
+    ftb.load_model_with_ema_option(m, {"state_dict": m.state_dict(), "ema_shadow": shadow}, use_ema=True)
+    assert net._synced == {} and torch.all(net.final_conv.bias == 0.25)
+    cnet = ftb.Unet3DCond(data_channels=15, time_learned_emb=True, **small)
+    cnet._atb_key = ("stale",)
+    cnet.mark_dirty()
+    assert cnet._atb_key is None
