@@ -313,6 +313,64 @@ def run_train_leg(a, ftb, _lib, dev, rank, world, dist):
     }
 
 
+
+def run_ensemble_leg(a, ftb, dev, rank, world, dist, n_samples=64):
+    """BASELINE configs[2]: conditional 64^3 model (Unet3DCond v3, 15-d embedding, surface + borehole ATb at every
+    resolution), ensemble of 64 samples sharded over the ranks (sample i -> rank i % world, no data-path collective),
+    100-step Euler ODE per sample (seeds 42 + i, model_inference_experiments.py:307), then the ensemble statistics:
+    decode -> vote histogram (one kernel per batch), ONE all-reduce(sum) of the int32 histogram, probabilities /
+    entropy / most-probable map.  STRONG scaling: the ensemble size is fixed as N grows.  Timed with CUDA events from
+    the first H2D copy of pinned host noise to the finalised statistics (all-reduce inside), max over ranks."""
+    import torch
+    from flowtrain_stochastic_interpolation_b200 import sharding
+    from oracle import synth
+    S, batch, steps = a.size, a.batch, N_ODE_STEPS
+    cfg = synth.make_cfg(data_channels=15)
+    kw = {k: v for k, v in cfg.items() if k != "data_channels"}
+    mod = ftb.Geo3DStochInterpCond(data_shape=(S, S, S), embedding_dim=15, **kw).to(dev).eval()
+    mod.net.load_state_dict(synth.synth_unet3d_cond_params(cfg, 5))
+    cats = torch.randint(-1, 14, (1, 1, S, S, S), generator=torch.Generator().manual_seed(3)).to(dev)
+    bores, nb = ftb.draw_boreholes(1, S, S, torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        _, atb, _ = mod.conditioning(cats, bores, nb)     # one conditioning volume shared by the ensemble (:228-232)
+        mine = list(sharding.shard_indices(n_samples, rank, world))
+        host = [torch.stack([torch.randn(15, S, S, S, generator=torch.Generator().manual_seed(42 + j)) for j in mine[i:i + batch]]).pin_memory()
+                for i in range(0, len(mine), batch)]
+        solver = ftb.ODEFlowSolver(lambda x, t: mod.net(x, atb.expand(x.shape[0], -1, -1, -1, -1), t), method="euler")
+        solver.solve(host[0].to(dev), t0=T0, tf=T0 + 3 * (TF - T0) / steps, n_steps=4, return_trajectory=False)   # warm-up
+        votes = ftb.EnsembleVotes(mod.embedding.weight, (S, S, S), dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        for hb in host:
+            xe = solver.solve(hb.to(dev, non_blocking=True), t0=T0, tf=TF, n_steps=steps + 1, return_trajectory=False)
+            votes.add(xe)
+        e1.record()
+        votes.all_reduce()
+        stats = votes.finalize()
+        most_host = stats["most_probable"].cpu()            # D2H of the ensemble's result map
+        e2.record()
+        torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1), e1.elapsed_time(e2), e0.elapsed_time(e2)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    solve_ms, stats_ms, tot_ms = t.tolist()
+    ok = bool(int(votes.counts.sum()) == n_samples * S ** 3)
+    n_local_batches = len(host)
+    del mod, solver, votes
+    torch.cuda.empty_cache()
+    return {"metric": "ensemble_samples_per_sec_cond_64cubed_100step_ode", "value": n_samples / (tot_ms * 1e-3),
+            "unit": "samples/s", "scaling": "strong", "n_gpus": world,
+            "config": {"workload": f"configs[2]: Unet3DCond v3 {S}^3 (15 ch), ensemble of {n_samples} sharded over {world} "
+                                   f"rank(s), batch {batch}/GPU, {steps}-step euler, one shared ATb (ATb-only branch "
+                                   "computed once per trajectory), decode -> vote histogram, one all-reduce"},
+            "solve_ms": solve_ms, "ensemble_stats_ms": stats_ms, "total_ms": tot_ms,
+            "ms_per_eval": solve_ms / (steps * n_local_batches), "votes_ok": ok,
+            "h2d_bytes": len(mine) * 15 * S ** 3 * 4, "d2h_bytes": int(most_host.numel()) * 8,
+            "collective": "all_reduce(sum) of the [15, 64^3] int32 vote histogram" if world > 1 else "none (1 rank)"}
+
 def run_extras(a, ftb, dev):
     """Side measurements carried in the JSON line under "extras" (never the headline): one velocity evaluation in
     the fp32 accuracy mode vs bf16 at B=1, and one optimiser step of the conditional project (BASELINE configs[2]'s
@@ -356,6 +414,55 @@ def run_extras(a, ftb, dev):
                          "what": "CondFlowTrainer.step: conditioning front-end kernel, Unet3DCond v3 fwd/bwd, "
                                  "flow + reconstruction loss, clip 0.3 + AdamW, EMA (1 GPU)"}
     del tr, mod
+    torch.cuda.empty_cache()
+
+    # ---- north_star's target line names 100 EULER steps: the same sampler, one evaluation per step
+    cfg = synth.make_cfg()
+    net = ftb.Unet3D(**cfg).to(dev).eval()
+    net.load_state_dict(synth.synth_unet3d_params(cfg, 0))
+    xb = torch.randn(a.batch, 18, S, S, S, generator=torch.Generator().manual_seed(100)).to(dev)
+    h = (TF - T0) / N_ODE_STEPS
+    eul = ftb.ODEFlowSolver(net, method="euler")
+    with torch.no_grad():
+        k = 10
+        ms = timed(lambda: eul.solve(xb, t0=T0, tf=T0 + k * h, n_steps=k + 1, return_trajectory=False), 2) / k
+    out["euler"] = {"ms_per_step": ms, "samples_per_s": a.batch / (N_ODE_STEPS * ms * 1e-3), "batch": a.batch,
+                    "tflops": GF_PER_EVAL * a.batch / ms, "what": "configs[1] with the Euler integrator (north_star target: "
+                    "100 Euler steps): one velocity evaluation + one fused axpy per step"}
+    # ---- configs[4]: one-sided denoising SDE at 128^3 (eps = 0.1, fresh noise per evaluation, fixed-grid Heun)
+    del xb
+    torch.cuda.empty_cache()
+    x128 = torch.randn(1, 18, 128, 128, 128, generator=torch.Generator().manual_seed(101)).to(dev)
+    sde = ftb.SDEOneSidedDenoisingSolver(net, ftb.LinearInterpolant(one_sided=True), epsilon=torch.tensor(0.1), method="heun")
+    with torch.no_grad():
+        k = 5
+        ms = timed(lambda: sde.solve(x128, t0=0.05, tf=0.05 + k * 0.009, n_steps=k + 1, return_trajectory=False), 2) / k
+    out["sde128"] = {"ms_per_heun_step": ms, "ms_per_eval": ms / 2, "batch": 1, "tflops": GF_PER_EVAL * 8 * 2 / ms,
+                     "samples_per_s_100_steps": 1.0 / (100 * ms * 1e-3),
+                     "what": "configs[4]: SDEOneSidedDenoisingSolver, 128^3, B=1, eps=0.1, Heun (2 evaluations + drift/noise "
+                             "kernels + randn per step)"}
+    del x128, sde, eul, net
+    torch.cuda.empty_cache()
+    # ---- the GPU bar to beat: the reference's own ATen / cuDNN op sequence (the oracle's functional
+    # restatement of Unet3D.forward, eager PyTorch) on this same B200 -- a reported baseline, never the product path
+    from oracle import unet3d as oracle_unet3d
+    params = {k2: v.to(dev) for k2, v in synth.synth_unet3d_params(cfg, 0).items()}
+    xg = synth.synth_input((a.batch, 18, S, S, S), 100).to(dev)
+    tg = torch.full((a.batch,), 0.5, device=dev)
+    ref = {}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    for name, tf32, n in (("tf32_on_default", True, 3), ("tf32_off_true_fp32", False, 1)):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        with torch.no_grad():
+            ms = timed(lambda: oracle_unet3d.unet3d_forward(params, cfg, xg, tg), n)
+        ref[name] = {"ms_per_eval": ms, "samples_per_s_heun100": a.batch / (2 * N_ODE_STEPS * ms * 1e-3),
+                     "samples_per_s_euler100": a.batch / (N_ODE_STEPS * ms * 1e-3)}
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    ref["what"] = (f"eager PyTorch (cuDNN / ATen) running the reference's op sequence on the same GPU, B={a.batch} {S}^3, one "
+                   "velocity evaluation; tf32_on_default is what the unmodified reference gets on a GPU")
+    out["gpu_reference"] = ref
+    del params, xg
     torch.cuda.empty_cache()
     return out
 
@@ -472,12 +579,19 @@ def run_b200(a):
         torch.cuda.empty_cache()
         train_leg = run_train_leg(a, ftb, _lib, dev, rank, world, dist)
 
-    extras = None
-    if not a.no_extras and world == 1 and not os.environ.get("FTB_BENCH_MINIMAL"):
+    ensemble = None
+    if not a.no_extras and not os.environ.get("FTB_BENCH_MINIMAL"):
         try:
             if train_leg is None:
                 del solver, net
                 torch.cuda.empty_cache()
+            ensemble = run_ensemble_leg(a, ftb, dev, rank, world, dist)
+        except Exception as exc:   # side measurements never break the headline line
+            ensemble = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
+    extras = None
+    if not a.no_extras and world == 1 and not os.environ.get("FTB_BENCH_MINIMAL"):
+        try:
             extras = run_extras(a, ftb, dev)
         except Exception as exc:   # side measurements never break the headline line
             extras = {"error": f"{type(exc).__name__}: {exc}"[:300]}
@@ -520,6 +634,8 @@ def run_b200(a):
     }
     if train_leg:
         line["train"] = train_leg
+    if ensemble:
+        line["ensemble"] = ensemble
     if extras:
         line["extras"] = extras
     if e2e:
@@ -533,6 +649,19 @@ def run_b200(a):
             "value": 1.0 / (N_ODE_STEPS * per * s_per_eval), "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{a.cpu_evals} velocity evaluations at B=1 {S}^3 fp32 on the host ({s_per_eval:.2f} s each, oracle "
                       f"port of the reference CPU path); samples/s = 1/({N_ODE_STEPS}*{per}*s_per_eval)"}
+    # the numbers of every leg once more, compact, as the LAST key (log tails keep the end of the line)
+    line["summary"] = {
+        "n_gpus": world, "sampling_samples_per_s": line["value"], "sampling_e2e_samples_per_s": line.get("e2e", {}).get("value"),
+        "sampling_ms_per_heun_step": step_ms, "whole_step_frac_of_bf16_peak": roof["whole_step_frac"],
+        "conv_kernel_frac_of_bf16_peak": roof["frac"],
+        "train_voxels_per_s": train_leg.get("value") if train_leg else None,
+        "train_ms_per_step": train_leg.get("ms_per_step") if train_leg else None,
+        "ensemble64_cond_samples_per_s": ensemble.get("value") if ensemble else None,
+        "ensemble64_total_ms": ensemble.get("total_ms") if ensemble else None,
+        "euler_samples_per_s": (extras or {}).get("euler", {}).get("samples_per_s"),
+        "sde128_ms_per_heun_step": (extras or {}).get("sde128", {}).get("ms_per_heun_step"),
+        "gpu_reference_tf32_ms_per_eval": (extras or {}).get("gpu_reference", {}).get("tf32_on_default", {}).get("ms_per_eval"),
+    }
     emit(line)
     if world > 1:
         dist.destroy_process_group()

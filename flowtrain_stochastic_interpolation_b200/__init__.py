@@ -12,6 +12,7 @@ from .solvers import (ODEFlowSolver, ODEOneSidedDenoisingSolver, SDEOneSidedDeno
                       integrate_fixed, odeSol_RK4)
 from .boreholes import (conditioning_frontend, draw_boreholes, jittered_grid_points, make_boreholes_mask,
                         make_combined_mask, make_surface_mask)
+from .data import DevicePrefetcher, SyntheticGeoStreamingDataset, get_data_loader
 from .ensemble import EnsembleVotes
 from .task import (EMAShadow, Geo3DStochInterp, Geo3DStochInterpCond, lightning_checkpoint,
                    load_model_with_ema_option, decode, ema_update_, embed, flow_loss,
@@ -25,5 +26,6 @@ __all__ = [
     "ODEOneSidedDenoisingSolver", "SDEOneSidedDenoisingSolver", "odeSol_RK4", "integrate_fixed",
     "Geo3DStochInterp", "Geo3DStochInterpCond", "EMAShadow", "FlowTrainer", "CondFlowTrainer", "EnsembleVotes",
     "make_boreholes_mask", "make_surface_mask", "make_combined_mask", "conditioning_frontend", "draw_boreholes",
+    "SyntheticGeoStreamingDataset", "DevicePrefetcher", "get_data_loader",
     "jittered_grid_points", "load_model_with_ema_option", "lightning_checkpoint", "BucketAllReduce", "flatten_parameters", "embed", "decode", "flow_loss", "ema_update_", "simplex_embedding",
 ]

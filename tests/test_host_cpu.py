@@ -306,3 +306,31 @@ def test_mark_dirty_and_ema_swap_plumbing():
     cnet._atb_key = ("stale",)
     cnet.mark_dirty()
     assert cnet._atb_key is None
+
+
+def test_streaming_dataset_stand_in_contract():
+    """the stand-in for geogen's GeoData3DStreamingDataset keeps the item contract the training step
+    relies on (model_train_inference.py:249-260, :428): int64 [1, X, Y, Z], categories -1 .. 13, deterministic per
+    index, fresh per epoch, usable behind a shuffling multi-worker DataLoader."""
+    from torch.utils.data import DataLoader
+    ds = ftb.SyntheticGeoStreamingDataset(model_resolution=[1, 16, 12, 20], model_bounds=((-1, 1), (-1, 1), (-1, 1)),
+                                          dataset_size=6, device="cpu")
+    assert len(ds) == 6
+    a = ds[3]
+    assert a.shape == (1, 16, 12, 20) and a.dtype == torch.int64
+    assert -1 <= int(a.min()) and int(a.max()) <= 13
+    assert (a == -1).any() and a.unique().numel() >= 3          # air + several rock units
+    assert torch.equal(a, ds[3]) and not torch.equal(a, ds[4])
+    ds.set_epoch(1)
+    assert not torch.equal(a, ds[3])
+    with pytest.raises(IndexError):
+        ds[6]
+    dl = DataLoader(ds, batch_size=4, shuffle=True, num_workers=2)
+    shapes = [tuple(b.shape) for b in dl]
+    assert shapes == [(4, 1, 16, 12, 20), (2, 1, 16, 12, 20)]
+    loader = ftb.get_data_loader({"data": {"shape": [1, 8, 8, 8], "bounds": None, "epoch_size": 5, "batch_size": 2}})
+    assert sum(b.shape[0] for b in loader) == 5
+    # embed()'s index rule: cat + 1 must be a valid row of the 15-row embedding
+    assert int((a + 1).min()) >= 0 and int((a + 1).max()) <= 14
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ftb.DevicePrefetcher(loader, "cpu")
