@@ -76,6 +76,14 @@ _SIGS = {
     "ftb_ode_error_ratio": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _i64, _vp, _vp]),
     "ftb_ode_scaled_sumsq": (_i, [_vp, _vp, _vp, _f, _f, _i64, _vp, _vp]),
     "ftb_ode_dense_eval": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i64, _vp]),
+    "ftb_ode_ctl_init": (_i, [_vp, _d, _vp]),
+    "ftb_ode_ctl_first_step": (_i, [_vp, _i, _i64, _i, _vp]),
+    "ftb_ode_ctl_stage_time": (_i, [_vp, _vp, _d, _i, _vp]),
+    "ftb_ode_lincomb_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _vp, _vp]),
+    "ftb_ode_error_ratio_dev": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _i64, _vp, _vp]),
+    "ftb_ode_ctl_step": (_i, [_vp, _vp, _i, _i64, _i, _i64, _vp]),
+    "ftb_ode_advance": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i64, _vp]),
+    "ftb_denoise_drift_dev": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
     "ftb_cond_frontend": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "ftb_cond_loss_accumulate": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp, _vp]),
     "ftb_cond_loss_grad": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i64, _vp, _f, _f, _vp, _vp]),

@@ -393,6 +393,24 @@ __global__ void drift_kernel(float* __restrict__ out, const float* __restrict__ 
   }
 }
 
+// same drift with (alpha, beta, alpha_dot, beta_dot, eps) read from device memory: the adaptive solvers keep time on the
+// device, so the schedule values of an evaluation are computed there too (no host round trip)
+__global__ void drift_dev_kernel(float* __restrict__ out, const float* __restrict__ x, const float* __restrict__ eta,
+                                 const float* __restrict__ noise, const float* __restrict__ coef, int use_sde, size_t n) {
+  const float a = coef[0], b = coef[1], ad = coef[2], bd = coef[3], eps = use_sde ? coef[4] : 0.f;
+  const float bdb = bd / b;
+  const float sq = use_sde ? sqrtf(__fmul_rn(2.f, eps)) : 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float e = __ldg(eta + i), xv = __ldg(x + i);
+    float d = __fadd_rn(__fmul_rn(ad, e), __fmul_rn(bdb, __fsub_rn(xv, __fmul_rn(a, e))));
+    if (use_sde) {
+      const float score = -e / a;
+      d = __fadd_rn(d, __fadd_rn(__fmul_rn(eps, score), __fmul_rn(__ldg(noise + i), sq)));
+    }
+    out[i] = d;
+  }
+}
+
 // ------------------------------------------------------------------ decode (model_train_inference.py:373-404)
 // One thread per voxel; fp32 op ORDER fixed (no FMA contraction): sequential sum of squares,
 // sqrt, clamp 1e-12, divide, ncat sequential dot products, first-max argmax -> int64.
@@ -456,6 +474,99 @@ __global__ void decode_kernel(const float* __restrict__ x, const float* __restri
     out[i] = decode_voxel(x + (size_t)b * E * n + v, n, s_en, E, ncat);
   }
 }
+
+// The same arithmetic, 4 consecutive voxels per thread and compile-time (E, NCAT): 16-byte loads of x, the embedding
+// rows read from shared memory as LDS.128 with immediate offsets once per 4 voxels (the generic kernel spends one LDS
+// per multiply), 16-byte stores of the int64 result.  Every voxel still sees exactly the op sequence of decode_voxel
+// (sequential unfused sums, IEEE sqrt / divide, first maximum), so the output is bit-identical.
+template <int E, int NCAT>
+__device__ __forceinline__ void decode_voxel4(const float* __restrict__ xp, size_t n, const float* s_en, int (&arg)[4]) {
+  float xv[4][E];
+  float ss[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(xp + (size_t)e * n));
+    xv[0][e] = q.x; xv[1][e] = q.y; xv[2][e] = q.z; xv[3][e] = q.w;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) ss[v] = __fadd_rn(ss[v], __fmul_rn(xv[v][e], xv[v][e]));
+  }
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    const float nrm = fmaxf(__fsqrt_rn(ss[v]), 1e-12f);
+#pragma unroll
+    for (int e = 0; e < E; ++e) xv[v][e] = __fdiv_rn(xv[v][e], nrm);
+  }
+  float best[4];
+#pragma unroll
+  for (int c = 0; c < NCAT; ++c) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const float w = s_en[c * E + e];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[v] = __fadd_rn(acc[v], __fmul_rn(xv[v][e], w));
+    }
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+      if (c == 0 || acc[v] > best[v] || (acc[v] != acc[v] && best[v] == best[v])) { best[v] = acc[v]; arg[v] = c; }
+  }
+}
+
+template <int E, int NCAT>
+__global__ void __launch_bounds__(128)
+decode4_kernel(const float* __restrict__ x, const float* __restrict__ en, long long* __restrict__ out, int B, size_t n) {
+  __shared__ __align__(16) float s_en[NCAT * E];
+  for (int i = threadIdx.x; i < NCAT * E; i += blockDim.x) s_en[i] = en[i];
+  __syncthreads();
+  const size_t n4 = n >> 2, total = (size_t)B * n4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / n4, v = (i % n4) << 2;
+    int arg[4];
+    decode_voxel4<E, NCAT>(x + b * E * n + v, n, s_en, arg);
+    longlong2* o = reinterpret_cast<longlong2*>(out + b * n + v);
+    o[0] = make_longlong2(arg[0], arg[1]);
+    o[1] = make_longlong2(arg[2], arg[3]);
+  }
+}
+
+template <int E, int NCAT>
+__global__ void __launch_bounds__(128)
+decode_vote4_kernel(const float* __restrict__ x, const float* __restrict__ en, int S, size_t n,
+                    long long* __restrict__ decoded, int* __restrict__ counts) {
+  __shared__ __align__(16) float s_en[NCAT * E];
+  __shared__ int s_cnt[NCAT][4][128];          // histogram of this thread's 4 voxels
+  for (int i = threadIdx.x; i < NCAT * E; i += blockDim.x) s_en[i] = en[i];
+  __syncthreads();
+  const size_t n4 = n >> 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t v = i << 2;
+#pragma unroll
+    for (int c = 0; c < NCAT; ++c)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s_cnt[c][k][threadIdx.x] = 0;
+    for (int s = 0; s < S; ++s) {
+      int arg[4];
+      decode_voxel4<E, NCAT>(x + (size_t)s * E * n + v, n, s_en, arg);
+      if (decoded) {
+        longlong2* o = reinterpret_cast<longlong2*>(decoded + (size_t)s * n + v);
+        o[0] = make_longlong2(arg[0], arg[1]);
+        o[1] = make_longlong2(arg[2], arg[3]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s_cnt[arg[k]][k][threadIdx.x] += 1;
+    }
+#pragma unroll
+    for (int c = 0; c < NCAT; ++c) {
+      int4* cp = reinterpret_cast<int4*>(counts + (size_t)c * n + v);
+      int4 old = *cp;
+      old.x += s_cnt[c][0][threadIdx.x]; old.y += s_cnt[c][1][threadIdx.x];
+      old.z += s_cnt[c][2][threadIdx.x]; old.w += s_cnt[c][3][threadIdx.x];
+      *cp = old;
+    }
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // Ensemble vote (model_inference_experiments.py:442-447): decode S samples of one voxel and add them to the per-voxel
 // category histogram counts[ncat][n] (int32, +=, so several launches / ranks accumulate).  Thread = voxel; the
@@ -631,10 +742,27 @@ int denoise_drift(float* out, const float* x, const float* eta, const float* noi
   FTB_LAUNCH_OK();
   return 0;
 }
+int denoise_drift_dev(float* out, const float* x, const float* eta, const float* noise, const float* coef, int use_sde,
+                      long long n, cudaStream_t st) {
+  FTB_CHECK(!use_sde || noise != nullptr, "drift: SDE term needs a noise tensor");
+  drift_dev_kernel<<<grid_for((size_t)n, 256), 256, 0, st>>>(out, x, eta, noise, coef, use_sde, (size_t)n);
+  FTB_LAUNCH_OK();
+  return 0;
+}
 int decode_argmax(const float* x, const float* en, long long* out, int B, int E, int ncat,
                   long long n, cudaStream_t st) {
   FTB_CHECK(E >= 1 && E <= 32, "decode: embedding dim must be in [1,32]");
   FTB_CHECK(ncat >= 1 && ncat <= 256, "decode: category count");
+  // the shipped shapes (15 categories in an 18- / 15- / 20-d embedding) run 4 voxels per thread; anything else, ragged
+  // or unaligned volumes take the generic one-voxel kernel (same arithmetic, bit-identical output)
+  if (ncat == 15 && (n & 3) == 0 && aligned16(x) && aligned16(out) && (E == 18 || E == 15 || E == 20)) {
+    const int g = grid_for((size_t)B * (n >> 2), 128);
+    if (E == 18) decode4_kernel<18, 15><<<g, 128, 0, st>>>(x, en, out, B, (size_t)n);
+    else if (E == 15) decode4_kernel<15, 15><<<g, 128, 0, st>>>(x, en, out, B, (size_t)n);
+    else decode4_kernel<20, 15><<<g, 128, 0, st>>>(x, en, out, B, (size_t)n);
+    FTB_LAUNCH_OK();
+    return 0;
+  }
   decode_kernel<<<grid_for((size_t)B * n, 128), 128, (size_t)ncat * E * sizeof(float), st>>>(x, en, out, B, E, ncat, (size_t)n);
   FTB_LAUNCH_OK();
   return 0;
@@ -651,6 +779,15 @@ int decode_vote(const float* x, const float* en, int S, int E, int ncat, long lo
                 cudaStream_t st) {
   FTB_CHECK(E >= 1 && E <= 32, "decode: embedding dim must be in [1,32]");
   FTB_CHECK(ncat >= 1 && ncat <= 64, "decode_vote: at most 64 categories");
+  if (ncat == 15 && (n & 3) == 0 && aligned16(x) && aligned16(counts) && (!decoded || aligned16(decoded)) &&
+      (E == 18 || E == 15 || E == 20)) {
+    const int g = grid_for((size_t)(n >> 2), 128);
+    if (E == 18) decode_vote4_kernel<18, 15><<<g, 128, 0, st>>>(x, en, S, (size_t)n, decoded, counts);
+    else if (E == 15) decode_vote4_kernel<15, 15><<<g, 128, 0, st>>>(x, en, S, (size_t)n, decoded, counts);
+    else decode_vote4_kernel<20, 15><<<g, 128, 0, st>>>(x, en, S, (size_t)n, decoded, counts);
+    FTB_LAUNCH_OK();
+    return 0;
+  }
   const size_t smem = (size_t)ncat * E * sizeof(float) + (size_t)ncat * 128 * sizeof(int);
   decode_vote_kernel<<<grid_for((size_t)n, 128), 128, smem, st>>>(x, en, S, E, ncat, (size_t)n, decoded, counts);
   FTB_LAUNCH_OK();

@@ -1139,6 +1139,43 @@ int ftb_ode_dense_eval(float* out, const float* y0, const float* y1, const float
   FTB_CHECK(out && y0 && y1 && ymid && f0 && f1, "null argument");
   return ode_dense_eval(out, y0, y1, ymid, f0, f1, dt, x, n, (cudaStream_t)stream);
 }
+int ftb_ode_ctl_init(double* ctl, double t0, void* stream) {
+  FTB_CHECK(ctl, "null argument");
+  return ode_ctl_init(ctl, t0, (cudaStream_t)stream);
+}
+int ftb_ode_ctl_first_step(double* ctl, int phase, int64_t n, int order, void* stream) {
+  FTB_CHECK(ctl && n > 0 && order >= 1 && (phase == 0 || phase == 1), "bad argument");
+  return ode_ctl_first_step(ctl, phase, n, order, (cudaStream_t)stream);
+}
+int ftb_ode_ctl_stage_time(float* tbuf, const double* ctl, double alpha, int B, void* stream) {
+  FTB_CHECK(tbuf && ctl && B > 0, "bad argument");
+  return ode_ctl_stage_time(tbuf, ctl, alpha, B, (cudaStream_t)stream);
+}
+int ftb_ode_lincomb_dev(float* out, const float* y0, const float* const* k, const double* coef, int nk, int64_t n,
+                        const double* ctl, void* stream) {
+  FTB_CHECK(out && y0 && ctl, "null argument");
+  return ode_lincomb_dev(out, y0, k, coef, nk, n, ctl, (cudaStream_t)stream);
+}
+int ftb_ode_error_ratio_dev(const float* y0, const float* y1, const float* const* k, const double* coef, int nk,
+                            float rtol, float atol, int64_t n, double* ctl, void* stream) {
+  FTB_CHECK(y0 && y1 && ctl, "null argument");
+  return ode_error_ratio_dev(y0, y1, k, coef, nk, rtol, atol, n, ctl, (cudaStream_t)stream);
+}
+int ftb_ode_ctl_step(double* ctl, const double* grid, int n_out, int64_t n, int order, int64_t max_steps, void* stream) {
+  FTB_CHECK(ctl && grid && n_out >= 1 && n > 0, "bad argument");
+  return ode_ctl_step(ctl, grid, n_out, n, order, max_steps, (cudaStream_t)stream);
+}
+int ftb_ode_advance(float* y0, float* f0, const float* y1, const float* f1, const float* const* k, const double* c_mid,
+                    int nk, const double* ctl, const double* grid, int n_out, float* traj, float* last, int64_t n,
+                    void* stream) {
+  FTB_CHECK(y0 && f0 && y1 && f1 && ctl && grid, "null argument");
+  return ode_advance(y0, f0, y1, f1, k, c_mid, nk, ctl, grid, n_out, traj, last, n, (cudaStream_t)stream);
+}
+int ftb_denoise_drift_dev(float* out, const float* x, const float* eta, const float* noise, const float* coef,
+                          int use_sde, int64_t n, void* stream) {
+  FTB_CHECK(out && x && eta && coef, "null argument");
+  return denoise_drift_dev(out, x, eta, noise, coef, use_sde, n, (cudaStream_t)stream);
+}
 int ftb_cond_frontend(const int64_t* cats, const int32_t* bores, const int32_t* n_bores, int max_bores, const float* w,
                       int B, int E, int ncat, int shift, int X, int Y, int Z, int surface, uint8_t* mask, float* x1,
                       float* atb, void* stream) {

@@ -239,6 +239,19 @@ int ode_scaled_sumsq(const float* a1, const float* a2, const float* y, float rto
                      cudaStream_t st);
 int ode_dense_eval(float* out, const float* y0, const float* y1, const float* ymid, const float* f0, const float* f1,
                    double dt, double x, long long n, cudaStream_t st);
+// device-resident step controller (16 doubles, layout in include/ftb.h); coef: tableau weights NOT multiplied by dt
+int ode_ctl_init(double* ctl, double t0, cudaStream_t st);
+int ode_ctl_first_step(double* ctl, int phase, long long n, int order, cudaStream_t st);
+int ode_ctl_stage_time(float* tbuf, const double* ctl, double alpha, int B, cudaStream_t st);
+int ode_lincomb_dev(float* out, const float* y0, const float* const* k, const double* coef, int nk, long long n,
+                    const double* ctl, cudaStream_t st);
+int ode_error_ratio_dev(const float* y0, const float* y1, const float* const* k, const double* coef, int nk, float rtol,
+                        float atol, long long n, double* ctl, cudaStream_t st);
+int ode_ctl_step(double* ctl, const double* grid, int n_out, long long n, int order, long long max_steps, cudaStream_t st);
+int ode_advance(float* y0, float* f0, const float* y1, const float* f1, const float* const* k, const double* c_mid, int nk,
+                const double* ctl, const double* grid, int n_out, float* traj, float* last, long long n, cudaStream_t st);
+int denoise_drift_dev(float* out, const float* x, const float* eta, const float* noise, const float* coef, int use_sde,
+                      long long n, cudaStream_t st);
 // ---- conditional project / ensemble kernels (cond_ops.cu, elementwise.cu)
 // surface + borehole mask, X1 = W[cat + shift], ATb = X1 * mask in one pass; bores [B][max_b][2] int32 (x, y),
 // nb [B] counts; mask (u8 [B][X*Y*Z]), x1, atb may each be null

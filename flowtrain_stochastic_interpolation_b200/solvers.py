@@ -22,6 +22,7 @@ sync per evaluation).  ``return_trajectory=False`` keeps only the end state (the
 """
 from __future__ import annotations
 
+import ctypes as C
 import warnings
 
 import torch
@@ -170,23 +171,22 @@ def _dbl_array(vals):
     return (C.c_double * len(vals))(*[float(v) for v in vals])
 
 
-def _lincomb(out, y0, ks, coefs):
-    with torch.cuda.device(y0.device):
-        _lib.check(_lib.lib.ftb_ode_lincomb(_lib.ptr(out), _lib.ptr(y0), _ptr_array(ks), _dbl_array(coefs), len(ks),
-                                            y0.numel(), _lib.stream_ptr()))
-    return out
-
-
 def integrate_adaptive(func, X0, t0, tf, n_steps, method="dopri5", rtol=1e-6, atol=1e-6, return_trajectory=True,
-                       max_num_steps=100000, stats=None, grid_dtype=torch.float32):
+                       max_num_steps=100000, stats=None, grid_dtype=torch.float32, lag=1):
     """torchdiffeq's adaptive Runge-Kutta loop (rk_common.RKAdaptiveStepsizeODESolver of torchdiffeq 0.2.x, the
     un-vendored dependency behind solvers.py:77, :148, :220-222) restated: initial step from ``_select_initial_step``,
     steps accepted when the RMS of error / (atol + rtol max(|y0|, |y1|)) is <= 1, step factor
     ``min(10, max(0.9 / ratio^(1/order), 0.2))`` (dfactor 1 after an accepted step), first-same-as-last reuse of the last
     stage, and the output grid ``linspace(t0, tf, n_steps)`` evaluated with the quartic dense-output interpolant.
-    Time-like values are host doubles (torchdiffeq keeps them in float64); the state passes are CUDA kernels
-    (ftb_ode_lincomb / error_ratio / dense_eval) and ONE scalar (the error ratio) returns to the host per attempted
-    step.  ``func(t, x, eval_index) -> dx/dt``.  Parity unpinned (torchdiffeq is not installed here)."""
+
+    The step controller is DEVICE-RESIDENT (ode_adaptive.cu): time, step size, the accept / reject decision, the output
+    cursor and the counters live in a 16-double device struct; stage times, stage inputs, the error ratio, the dense
+    output and the in-place state advance are kernels that read it.  The host enqueues attempted steps and never reads
+    the step being computed: after enqueueing step ``s`` it looks at an asynchronous pinned copy of the controller
+    from step ``s - lag`` to learn when the solve has finished (steps enqueued after that are no-ops on the state, at
+    most ``lag`` of them).  No ``.item()`` per step - the reference syncs once per EVALUATION (``t.item()``, :68).
+    Time-like values are doubles (torchdiffeq keeps them in float64).  ``func(T, x, eval_index) -> dx/dt`` receives the
+    evaluation's time as a device fp32 tensor ``T`` of shape [B].  Parity unpinned (torchdiffeq is not installed)."""
     if method not in ADAPTIVE_METHODS:
         raise ValueError(f"method must be one of {ADAPTIVE_METHODS}, got {method!r}")
     if not X0.is_cuda:
@@ -194,82 +194,87 @@ def integrate_adaptive(func, X0, t0, tf, n_steps, method="dopri5", rtol=1e-6, at
     tab = _DOPRI5 if method == "dopri5" else _ADAPTIVE_HEUN
     order = tab["order"]
     y0 = _flat(X0).clone()
-    n = y0.numel()
-    dev = y0.device
-    lib = _lib.lib
-    # the reference builds the output grid in fp32 (solvers.py:59); torchdiffeq then carries time in float64
-    grid = [float(v) for v in torch.linspace(t0, tf, n_steps, dtype=grid_dtype)] if n_steps > 1 else [float(t0)]
-    acc = torch.zeros(1, dtype=torch.float64, device=dev)
+    n, B, dev, lib = y0.numel(), y0.shape[0], y0.device, _lib.lib
+    # the reference builds the output grid in fp32 (solvers.py:59; float64 at :126); torchdiffeq carries time in float64
+    ghost = torch.linspace(t0, tf, n_steps, dtype=grid_dtype).double() if n_steps > 1 else torch.tensor([float(t0)], dtype=torch.float64)
+    n_out = ghost.numel()
+    grid = ghost.to(dev)
+    ctl = torch.empty(16, dtype=torch.float64, device=dev)
+    tbuf = torch.empty(B, dtype=torch.float32, device=dev)
+    cp = lambda k: C.c_void_p(ctl.data_ptr() + 8 * k)
     n_eval = 0
 
-    def norm_of(a1, a2, y):   # rms_norm((a1 - a2) / (atol + rtol |y|))
-        acc.zero_()
-        with torch.cuda.device(dev):
-            _lib.check(lib.ftb_ode_scaled_sumsq(_lib.ptr(a1), _lib.ptr(a2), _lib.ptr(y), float(rtol), float(atol), n,
-                                                _lib.ptr(acc), _lib.stream_ptr()))
-        return (acc.item() / n) ** 0.5
+    def stage_time(alpha):
+        _lib.check(lib.ftb_ode_ctl_stage_time(_lib.ptr(tbuf), _lib.ptr(ctl), float(alpha), B, _lib.stream_ptr()))
+        return tbuf
 
-    # ---- _before_integrate: f0 and the first step (_select_initial_step with order - 1)
-    f0 = func(grid[0], y0, n_eval); n_eval += 1
-    d0, d1 = norm_of(y0, None, y0), norm_of(f0, None, y0)
-    h0 = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
-    y1 = _lincomb(torch.empty_like(y0), y0, [f0], [h0])
-    f1 = func(grid[0] + h0, y1, n_eval); n_eval += 1
-    d2 = norm_of(f1, f0, y0) / h0
-    h1 = max(1e-6, h0 * 1e-3) if (d1 <= 1e-15 and d2 <= 1e-15) else (0.01 / max(d1, d2)) ** (1.0 / float(order))
-    dt = min(100 * h0, h1)
-    t_cur = grid[0]
-    traj = torch.empty((len(grid),) + tuple(y0.shape), dtype=torch.float32, device=dev) if return_trajectory else None
-    if traj is not None:
-        traj[0].copy_(y0)
-    interp = None   # (t0, t1, y0, y1, ymid, f0, f1) of the last accepted step
-    accepted = rejected = 0
-    nstage = len(tab["alpha"])
-    for gi in range(1, len(grid)):
-        t_out = grid[gi]
-        while t_out > t_cur:
-            if accepted + rejected >= max_num_steps:
-                raise RuntimeError(f"max_num_steps exceeded ({max_num_steps})")
-            # ---- _runge_kutta_step
-            t1 = t_cur + dt
+    def lincomb(ks, coefs):
+        out = torch.empty_like(y0)
+        _lib.check(lib.ftb_ode_lincomb_dev(_lib.ptr(out), _lib.ptr(y0), _ptr_array(ks), _dbl_array(coefs), len(ks), n,
+                                           _lib.ptr(ctl), _lib.stream_ptr()))
+        return out
+
+    def sumsq(a1, a2, slot):   # ctl[slot] += sum(((a1 - a2) / (atol + rtol |y0|))^2)
+        _lib.check(lib.ftb_ode_scaled_sumsq(_lib.ptr(a1), _lib.ptr(a2), _lib.ptr(y0), float(rtol), float(atol), n, cp(slot),
+                                            _lib.stream_ptr()))
+
+    with torch.cuda.device(dev):
+        _lib.check(lib.ftb_ode_ctl_init(_lib.ptr(ctl), float(ghost[0]), _lib.stream_ptr()))
+        # ---- _before_integrate: f0 and the first step (_select_initial_step), all on the device
+        f0 = func(stage_time(0.0), y0, n_eval).clone(); n_eval += 1      # owned: advanced in place below
+        sumsq(y0, None, 3)
+        sumsq(f0, None, 4)
+        _lib.check(lib.ftb_ode_ctl_first_step(_lib.ptr(ctl), 0, n, order, _lib.stream_ptr()))
+        y1 = lincomb([f0], [1.0])
+        f1 = func(stage_time(1.0), y1, n_eval); n_eval += 1
+        sumsq(f1, f0, 5)
+        _lib.check(lib.ftb_ode_ctl_first_step(_lib.ptr(ctl), 1, n, order, _lib.stream_ptr()))
+        traj = torch.empty((n_out,) + tuple(y0.shape), dtype=torch.float32, device=dev) if return_trajectory else None
+        last = None if return_trajectory else torch.empty_like(y0)
+        if traj is not None:
+            traj[0].copy_(y0)
+        if n_out == 1:
+            if stats is not None:
+                stats.update(accepted=0, rejected=0, evals=n_eval)
+            return traj if traj is not None else y0
+        nstage = len(tab["alpha"])
+        fsal = tab["c_sol"][-1] == 0 and list(tab["c_sol"][:-1]) == list(tab["beta"][-1])
+        lag = max(1, int(lag))
+        pinned = torch.zeros((lag + 1, 16), dtype=torch.float64).pin_memory()
+        events = [torch.cuda.Event() for _ in range(lag + 1)]
+        step, final = 0, None
+        while final is None:
+            # ---- _runge_kutta_step, enqueued blind: every time-like quantity is read from ctl by the kernels
             ks = [f0]
             for i in range(nstage):
-                ti = t1 if tab["alpha"][i] == 1.0 else t_cur + tab["alpha"][i] * dt
-                yi = _lincomb(torch.empty_like(y0), y0, ks, [b * dt for b in tab["beta"][i]])
-                ks.append(func(ti, yi, n_eval)); n_eval += 1
-            fsal = tab["c_sol"][-1] == 0 and list(tab["c_sol"][:-1]) == list(tab["beta"][-1])
-            y1 = yi if fsal else _lincomb(torch.empty_like(y0), y0, ks, [c * dt for c in tab["c_sol"]])
+                yi = lincomb(ks, tab["beta"][i])
+                ks.append(func(stage_time(tab["alpha"][i]), yi, n_eval)); n_eval += 1
+            y1 = yi if fsal else lincomb(ks, tab["c_sol"])
             f1 = ks[-1]
-            acc.zero_()
-            with torch.cuda.device(dev):
-                _lib.check(lib.ftb_ode_error_ratio(_lib.ptr(y0), _lib.ptr(y1), _ptr_array(ks),
-                                                   _dbl_array([c * dt for c in tab["c_error"]]), len(ks), float(rtol),
-                                                   float(atol), n, _lib.ptr(acc), _lib.stream_ptr()))
-            ratio = (acc.item() / n) ** 0.5
-            if ratio != ratio:
-                raise FloatingPointError("adaptive solver: non-finite error estimate")
-            if ratio <= 1.0:   # accept
-                ymid = _lincomb(torch.empty_like(y0), y0, ks, [c * dt for c in tab["c_mid"]])
-                interp = (t_cur, t1, y0, y1, ymid, f0, f1, dt)
-                y0, f0, t_cur = y1, f1, t1
-                accepted += 1
-            else:
-                rejected += 1
-            # ---- _optimal_step_size
-            if ratio == 0.0:
-                dt = dt * 10.0
-            else:
-                dfactor = 1.0 if ratio < 1.0 else 0.2
-                dt = dt * min(10.0, max(0.9 / ratio ** (1.0 / order), dfactor))
-        ta, tb, ya, yb, ym, fa, fb, hdt = interp
-        out = traj[gi] if traj is not None else torch.empty_like(y0)
-        with torch.cuda.device(dev):
-            _lib.check(lib.ftb_ode_dense_eval(_lib.ptr(out), _lib.ptr(ya), _lib.ptr(yb), _lib.ptr(ym), _lib.ptr(fa),
-                                              _lib.ptr(fb), hdt, (t_out - ta) / (tb - ta), n, _lib.stream_ptr()))
-        last = out
+            _lib.check(lib.ftb_ode_error_ratio_dev(_lib.ptr(y0), _lib.ptr(y1), _ptr_array(ks), _dbl_array(tab["c_error"]),
+                                                   len(ks), float(rtol), float(atol), n, _lib.ptr(ctl), _lib.stream_ptr()))
+            _lib.check(lib.ftb_ode_ctl_step(_lib.ptr(ctl), _lib.ptr(grid), n_out, n, order, int(max_num_steps),
+                                            _lib.stream_ptr()))
+            _lib.check(lib.ftb_ode_advance(_lib.ptr(y0), _lib.ptr(f0), _lib.ptr(y1), _lib.ptr(f1), _ptr_array(ks),
+                                           _dbl_array(tab["c_mid"]), len(ks), _lib.ptr(ctl), _lib.ptr(grid), n_out,
+                                           _lib.ptr(traj), _lib.ptr(last), n, _lib.stream_ptr()))
+            slot = step % (lag + 1)
+            pinned[slot].copy_(ctl, non_blocking=True)
+            events[slot].record()
+            if step >= lag:   # look at a step the GPU finished while this one was being enqueued
+                old = (step - lag) % (lag + 1)
+                events[old].synchronize()
+                flags = int(pinned[old, 13])
+                if flags & 4:
+                    raise FloatingPointError("adaptive solver: non-finite error estimate")
+                if flags & 8:
+                    raise RuntimeError(f"max_num_steps exceeded ({max_num_steps})")
+                if flags & 2:
+                    final = pinned[old].clone()
+            step += 1
     if stats is not None:
-        stats.update(accepted=accepted, rejected=rejected, evals=n_eval)
-    return traj if traj is not None else (last if len(grid) > 1 else y0)
+        stats.update(accepted=int(final[9]), rejected=int(final[10]), evals=n_eval, enqueued_steps=step)
+    return traj if traj is not None else last
 
 
 def _integrate(func, X0, t0, tf, n_steps, method, return_trajectory, rtol, atol, stats=None, grid_dtype=torch.float32):
@@ -299,8 +304,9 @@ class ODEFlowSolver:
 
         def ode_func(t, XT, _i):
             with torch.no_grad():
-                tbuf.fill_(t)  # T = full((B,), t) without a device->host sync
-                dxdt = _flat(self.model(XT, tbuf))
+                # T = full((B,), t) without a device->host sync; the adaptive stepper hands the device tensor itself
+                T = t if isinstance(t, torch.Tensor) else tbuf.fill_(t)
+                dxdt = _flat(self.model(XT, T))
                 return _zero_frozen(dxdt, mask)
 
         return _integrate(ode_func, X0, t0, tf, n_steps, self.method, return_trajectory, self.rtol, self.atol,
@@ -320,10 +326,23 @@ class ODEOneSidedDenoisingSolver:
         assert self.interp.is_one_sided(), "ODEOneSidedDenoisingSolver requires a one-sided interpolant"
 
     def _drift(self, t, XT, eta, noise=None, eps=None):
-        tt = torch.tensor(t, dtype=torch.float32)
         ip = self.interp
-        a, b, ad, bd = (float(f(tt)) for f in (ip.alpha, ip.beta, ip.alpha_dot, ip.beta_dot))
         out = torch.empty_like(XT)
+        if isinstance(t, torch.Tensor):
+            # adaptive stepper: the evaluation's time lives on the device, so do the five schedule values
+            # (alpha, beta, alpha_dot, beta_dot of :138-141, eps of :207) - computed there, no host round trip
+            tt = t[0]
+            vals = [f(tt) for f in (ip.alpha, ip.beta, ip.alpha_dot, ip.beta_dot)]
+            e = self.epsilon(tt) if eps is not None else 0.0
+            vals.append(torch.as_tensor(e, dtype=torch.float32, device=XT.device))
+            coef = torch.stack([v.to(device=XT.device, dtype=torch.float32).reshape(()) for v in vals]).contiguous()
+            with torch.cuda.device(XT.device):
+                _lib.check(_lib.lib.ftb_denoise_drift_dev(_lib.ptr(out), _lib.ptr(XT), _lib.ptr(eta), _lib.ptr(noise),
+                                                          _lib.ptr(coef), 0 if eps is None else 1, XT.numel(),
+                                                          _lib.stream_ptr()))
+            return out
+        tt = torch.tensor(t, dtype=torch.float32)
+        a, b, ad, bd = (float(f(tt)) for f in (ip.alpha, ip.beta, ip.alpha_dot, ip.beta_dot))
         with torch.cuda.device(XT.device):
             _lib.check(_lib.lib.ftb_denoise_drift(
                 _lib.ptr(out), _lib.ptr(XT), _lib.ptr(eta), _lib.ptr(noise), a, b, ad, bd,
@@ -337,8 +356,8 @@ class ODEOneSidedDenoisingSolver:
 
         def ode_func(t, XT, _i):
             with torch.no_grad():
-                tbuf.fill_(t)
-                eta = _flat(self.model(XT, tbuf))
+                T = t if isinstance(t, torch.Tensor) else tbuf.fill_(t)
+                eta = _flat(self.model(XT, T))
                 return self._drift(t, XT, eta)
 
         return _integrate(ode_func, X0, t0, tf, n_steps, self.method, return_trajectory, self.rtol, self.atol,
@@ -373,13 +392,15 @@ class SDEOneSidedDenoisingSolver(ODEOneSidedDenoisingSolver):
 
         def ode_func(t, XT, i):
             with torch.no_grad():
-                tbuf.fill_(t)
-                eta = _flat(self.model(XT, tbuf))
-                eps = float(self.epsilon(torch.tensor(t, dtype=torch.float32)))
+                dev_time = isinstance(t, torch.Tensor)
+                T = t if dev_time else tbuf.fill_(t)
+                eta = _flat(self.model(XT, T))
+                eps = True if dev_time else float(self.epsilon(torch.tensor(t, dtype=torch.float32)))
                 z = self.noise(i) if self.noise is not None else torch.randn_like(XT)
                 return self._drift(t, XT, eta, _flat(z).to(XT.device), eps)
 
-        return _integrate(ode_func, X0, t0, tf, n_steps, self.method, return_trajectory, self.rtol, self.atol)
+        return _integrate(ode_func, X0, t0, tf, n_steps, self.method, return_trajectory, self.rtol, self.atol,
+                          getattr(self, "stats", None))
 
 
 def odeSol_RK4(x0, model, nsteps=100, Tf=1.0):

@@ -131,10 +131,43 @@ int ftb_ode_scaled_sumsq(const float* a1, const float* a2, const float* y, float
                          double* acc, void* stream);
 int ftb_ode_dense_eval(float* out, const float* y0, const float* y1, const float* ymid, const float* f0,
                        const float* f1, double dt, double x, int64_t n, void* stream);
+/* ---- device-resident step controller of the adaptive solvers (replaces torchdiffeq's host-side
+ *      RKAdaptiveStepsizeODESolver loop behind solvers.py:77, :148, :220-222): time, step size, accept / reject, output
+ *      cursor and counters live in `ctl`, 16 device doubles:
+ *        [0] t  [1] dt  [2] error-ratio accumulator  [3..5] first-step norm accumulators  [6] tp0 [7] tp1 [8] dtp
+ *        (interval and size of the last accepted step)  [9] accepted  [10] rejected  [11] out_lo [12] out_hi
+ *        (outputs [out_lo, out_hi) are emitted by this step)  [13] flags: 1 accepted this step, 2 finished,
+ *        4 non-finite error estimate, 8 max_num_steps exceeded  [14] h0  [15] attempted steps
+ *      A whole solve is enqueued without a device->host read; the host polls an asynchronous copy of `ctl` from an
+ *      earlier step to stop enqueueing (steps after `finished` are no-ops on the state).
+ *   ctl_init:        zero the controller, t = t0
+ *   ctl_first_step:  torchdiffeq _select_initial_step; phase 0: dt = h0 from ctl[3], ctl[4] (sums of squares of
+ *                    y0 / scale and f0 / scale, written by ftb_ode_scaled_sumsq); phase 1: dt = min(100 h0, h1), ctl[5]
+ *   ctl_stage_time:  tbuf[b] = float(t + alpha dt), the model's time input of a stage
+ *   lincomb_dev / error_ratio_dev: as lincomb / error_ratio with coef = tableau weights, multiplied by ctl's dt on
+ *                    the device; error_ratio_dev accumulates into ctl[2]
+ *   ctl_step:        ratio = sqrt(ctl[2] / n); accept iff <= 1; t, dt (factor min(10, max(0.9 ratio^(-1/order),
+ *                    accepted ? 1 : 0.2))), counters, which grid points (device doubles, n_out of them) fall in the step
+ *   advance:         if accepted: write those outputs (quartic dense output; traj [n_out, n] or, when NULL, only the
+ *                    final point into `last`) and y0 <- y1, f0 <- f1 in place; otherwise nothing */
+int ftb_ode_ctl_init(double* ctl, double t0, void* stream);
+int ftb_ode_ctl_first_step(double* ctl, int phase, int64_t n, int order, void* stream);
+int ftb_ode_ctl_stage_time(float* tbuf, const double* ctl, double alpha, int B, void* stream);
+int ftb_ode_lincomb_dev(float* out, const float* y0, const float* const* k, const double* coef, int nk, int64_t n,
+                        const double* ctl, void* stream);
+int ftb_ode_error_ratio_dev(const float* y0, const float* y1, const float* const* k, const double* coef, int nk,
+                            float rtol, float atol, int64_t n, double* ctl, void* stream);
+int ftb_ode_ctl_step(double* ctl, const double* grid, int n_out, int64_t n, int order, int64_t max_steps, void* stream);
+int ftb_ode_advance(float* y0, float* f0, const float* y1, const float* f1, const float* const* k, const double* c_mid,
+                    int nk, const double* ctl, const double* grid, int n_out, float* traj, float* last, int64_t n,
+                    void* stream);
 /* eq. 6.7 drift from a denoiser eta (solvers.py:130-143); SDE term (:205-216) when use_sde */
 int ftb_denoise_drift(float* out, const float* x, const float* eta, const float* noise, float alpha,
                       float beta, float alpha_dot, float beta_dot, float eps, int use_sde, int64_t n,
                       void* stream);
+/* the same with coef = device floats (alpha, beta, alpha_dot, beta_dot, eps) of the evaluation's (device-resident) time */
+int ftb_denoise_drift_dev(float* out, const float* x, const float* eta, const float* noise, const float* coef,
+                          int use_sde, int64_t n, void* stream);
 
 /* ---- categorical embedding (model_train_inference.py:361-370, :373-404) */
 /* x [B,E,n] fp32, en [ncat,E] = F.normalize(embedding.weight) -> out [B,n] int64, bit-exact order */
