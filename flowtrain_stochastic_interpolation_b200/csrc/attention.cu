@@ -447,42 +447,53 @@ kvctx_kernel(const __grid_constant__ CUtensorMap tm, const KvCtxParams p) {
       if (in) rs = 1.f / fmaxf(sqrtf(__ldg(p.ss + (size_t)b * p.vox + v)), 1e-12f);
       const int s = i % p.npv;
       mbar_wait(d1_full, i & 1);
-      mbar_wait(&pv_empty[s], ((i / p.npv) & 1) ^ 1);
       tc_fence_after();
       const float rs2 = rs * log2e;
-      // every warp converts 64 k columns (-> P, with the exp) and 64 v columns (-> V): balanced MUFU load
-#pragma unroll 1
-      for (int part = 0; part < 2; ++part) {
-        uint8_t* dst = s_pv + s * kPv + (part ? kBytesP : 0);
-        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + part * 128;
-        for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
-          uint32_t r0[16], r1[16];
-          tmem_ld16(trow + c0, r0);
-          tmem_ld16(trow + c0 + 16, r1);
-          tmem_ld_wait();
+      // every warp converts 64 k columns (-> P, with the exp) and 64 v columns (-> V): balanced MUFU load.  All 128
+      // values are pulled into registers behind ONE tcgen05.wait and the accumulator is handed back before any math,
+      // so GEMM1 of the next tile overlaps the whole conversion (the pass used to be a chain of four load -> wait ->
+      // convert rounds with the tensor pipe idle in between).
+      uint32_t rk[4][16], rv[4][16];
+      {
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + half * 64;
 #pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
-            float f[8];
-            const uint32_t* r = g8 < 2 ? r0 + g8 * 8 : r1 + (g8 - 2) * 8;
-            if (part == 0) {
-              const float4 m0 = *reinterpret_cast<const float4*>(s_shift + c0 + g8 * 8);
-              const float4 m1 = *reinterpret_cast<const float4*>(s_shift + c0 + g8 * 8 + 4);
-              f[0] = ex2_fast(fmaf(__uint_as_float(r[0]), rs2, -m0.x)); f[1] = ex2_fast(fmaf(__uint_as_float(r[1]), rs2, -m0.y));
-              f[2] = ex2_fast(fmaf(__uint_as_float(r[2]), rs2, -m0.z)); f[3] = ex2_fast(fmaf(__uint_as_float(r[3]), rs2, -m0.w));
-              f[4] = ex2_fast(fmaf(__uint_as_float(r[4]), rs2, -m1.x)); f[5] = ex2_fast(fmaf(__uint_as_float(r[5]), rs2, -m1.y));
-              f[6] = ex2_fast(fmaf(__uint_as_float(r[6]), rs2, -m1.z)); f[7] = ex2_fast(fmaf(__uint_as_float(r[7]), rs2, -m1.w));
-            } else {
+        for (int j = 0; j < 4; ++j) tmem_ld16(trow + j * 16, rk[j]);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[j]) * rs;
-            }
-            const uint4 u = in ? pack_bf16x8(f) : make_uint4(0u, 0u, 0u, 0u);
-            *reinterpret_cast<uint4*>(dst + ((size_t)((c0 >> 3) + g8) * kKvT + row) * 16) = u;
-          }
-        }
+        for (int j = 0; j < 4; ++j) tmem_ld16(trow + 128 + j * 16, rv[j]);
+        tmem_ld_wait();
       }
       tc_fence_before();
-      fence_proxy_async();
       mbar_arrive(d1_empty);
+      mbar_wait(&pv_empty[s], ((i / p.npv) & 1) ^ 1);
+      {
+        uint8_t* dst = s_pv + s * kPv;
+#pragma unroll
+        for (int g8 = 0; g8 < 8; ++g8) {
+          const int c = half * 64 + g8 * 8;
+          const uint32_t* r = rk[g8 >> 1] + (g8 & 1) * 8;
+          const float4 m0 = *reinterpret_cast<const float4*>(s_shift + c);
+          const float4 m1 = *reinterpret_cast<const float4*>(s_shift + c + 4);
+          float f[8];
+          f[0] = ex2_fast(fmaf(__uint_as_float(r[0]), rs2, -m0.x)); f[1] = ex2_fast(fmaf(__uint_as_float(r[1]), rs2, -m0.y));
+          f[2] = ex2_fast(fmaf(__uint_as_float(r[2]), rs2, -m0.z)); f[3] = ex2_fast(fmaf(__uint_as_float(r[3]), rs2, -m0.w));
+          f[4] = ex2_fast(fmaf(__uint_as_float(r[4]), rs2, -m1.x)); f[5] = ex2_fast(fmaf(__uint_as_float(r[5]), rs2, -m1.y));
+          f[6] = ex2_fast(fmaf(__uint_as_float(r[6]), rs2, -m1.z)); f[7] = ex2_fast(fmaf(__uint_as_float(r[7]), rs2, -m1.w));
+          const uint4 u = in ? pack_bf16x8(f) : make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(dst + ((size_t)(c >> 3) * kKvT + row) * 16) = u;
+        }
+        dst += kBytesP;
+#pragma unroll
+        for (int g8 = 0; g8 < 8; ++g8) {
+          const int c = half * 64 + g8 * 8;
+          const uint32_t* r = rv[g8 >> 1] + (g8 & 1) * 8;
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[j]) * rs;
+          const uint4 u = in ? pack_bf16x8(f) : make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(dst + ((size_t)(c >> 3) * kKvT + row) * 16) = u;
+        }
+      }
+      fence_proxy_async();
       mbar_arrive(&pv_ready[s]);
     }
     // ---- TMEM -> partials (warps 2-5): row = (head, d); own head's columns + the denominator column
@@ -547,7 +558,85 @@ struct QoutParams {
   const float* gs;               // [C] g*sqrt(C)
   bf16* out;
   float q_scale;
+  int q_bounded;                 // |q| is bounded far below the fp32 exp range: softmax without the max pass
 };
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// pass B of the fused q/out kernel for one voxel row: y + bias -> RMSNorm * g sqrt(C) -> + x -> store.
+// NCH = C / 16 known at compile time: the row lives in registers (one tcgen05.wait, TMEM released at once);
+// NCH = 0: any C, two passes over TMEM, released at the end.
+template <int NCH>
+__device__ __forceinline__ void qout_finish(const QoutParams& p, uint32_t trow, uint64_t* d2_empty, const float* s_bias,
+                                            const float* s_gs, bool in, int b, long long v, size_t cgs) {
+  if (NCH > 0) {
+    uint32_t r[NCH > 0 ? NCH : 1][16];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) tmem_ld16(trow + ch * 16, r[ch]);
+    tmem_ld_wait();
+    tc_fence_before();
+    mbar_arrive(d2_empty);
+    float ss[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float a = __uint_as_float(r[ch][j]) + s_bias[ch * 16 + j];
+        r[ch][j] = __float_as_uint(a);
+        ss[j & 3] = fmaf(a, a, ss[j & 3]);
+      }
+    if (!in) return;
+    const float rinv = 1.f / fmaxf(sqrtf((ss[0] + ss[1]) + (ss[2] + ss[3])), 1e-12f);
+    const bf16* xp = p.x + (((size_t)b * p.cgtot + p.cgoff) * cgs + (size_t)v) * 8;
+    bf16* op = p.out + ((size_t)b * p.out_cgtot * cgs + (size_t)v) * 8;
+#pragma unroll
+    for (int g = 0; g < 2 * NCH; ++g) {
+      float xr[8], f[8];
+      unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(xp + (size_t)g * cgs * 8)), xr);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(__uint_as_float(r[g >> 1][(g & 1) * 8 + j]) * rinv, s_gs[g * 8 + j], xr[j]);
+      *reinterpret_cast<uint4*>(op + (size_t)g * cgs * 8) = pack_bf16x8(f);
+    }
+    return;
+  }
+  float ss[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c0 = 0; c0 < p.C; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld16(trow + c0, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float a = __uint_as_float(r[j]) + s_bias[c0 + j];
+      ss[j & 3] = fmaf(a, a, ss[j & 3]);
+    }
+  }
+  const float rinv = 1.f / fmaxf(sqrtf((ss[0] + ss[1]) + (ss[2] + ss[3])), 1e-12f);
+  for (int c0 = 0; c0 < p.C; c0 += 16) {
+    uint32_t r[16];
+    tmem_ld16(trow + c0, r);
+    tmem_ld_wait();
+    if (!in) continue;
+    const bf16* xp = p.x + (((size_t)b * p.cgtot + p.cgoff + (c0 >> 3)) * cgs + (size_t)v) * 8;
+    bf16* op = p.out + (((size_t)b * p.out_cgtot + (c0 >> 3)) * cgs + (size_t)v) * 8;
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      float xr[8], f[8];
+      unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(xp + (size_t)hf * cgs * 8)), xr);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int ch = c0 + hf * 8 + j;
+        f[j] = fmaf((__uint_as_float(r[hf * 8 + j]) + s_bias[ch]) * rinv, s_gs[ch], xr[j]);
+      }
+      *reinterpret_cast<uint4*>(op + (size_t)hf * cgs * 8) = pack_bf16x8(f);
+    }
+  }
+  tc_fence_before();
+  mbar_arrive(d2_empty);
+}
 
 __global__ void __launch_bounds__(kQoThreads, 1)
 qout_kernel(const __grid_constant__ CUtensorMap tm, const QoutParams p) {
@@ -676,34 +765,54 @@ qout_kernel(const __grid_constant__ CUtensorMap tm, const QoutParams p) {
         tmem_ld16(trow + c0, r0);
         if (p.dh == 32) tmem_ld16(trow + c0 + 16, r1);
         tmem_ld_wait();
-        float mx = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float a = __uint_as_float(r0[j]) * rs;
-          r0[j] = __float_as_uint(a);
-          mx = fmaxf(mx, a);
-        }
-        if (p.dh == 32) {
+        float sum = 0.f;
+        if (p.q_bounded) {
+          // |q[d]| <= ||W_q[d,:] (x) g sqrt(C)|| (the input row has unit norm), checked on the host against the fp32
+          // exp range: exp(q) / sum exp(q) needs no max pass - one multiply, one ex2, one add per element
+          const float rsl = rs * 1.4426950408889634f;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float a = __uint_as_float(r1[j]) * rs;
-            r1[j] = __float_as_uint(a);
+            const float e = ex2_approx(__uint_as_float(r0[j]) * rsl);
+            r0[j] = __float_as_uint(e);
+            sum += e;
+          }
+          if (p.dh == 32) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float e = ex2_approx(__uint_as_float(r1[j]) * rsl);
+              r1[j] = __float_as_uint(e);
+              sum += e;
+            }
+          }
+        } else {
+          float mx = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a = __uint_as_float(r0[j]) * rs;
+            r0[j] = __float_as_uint(a);
             mx = fmaxf(mx, a);
           }
-        }
-        float sum = 0.f;
+          if (p.dh == 32) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float e = __expf(__uint_as_float(r0[j]) - mx);
-          r0[j] = __float_as_uint(e);
-          sum += e;
-        }
-        if (p.dh == 32) {
+            for (int j = 0; j < 16; ++j) {
+              const float a = __uint_as_float(r1[j]) * rs;
+              r1[j] = __float_as_uint(a);
+              mx = fmaxf(mx, a);
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float e = __expf(__uint_as_float(r1[j]) - mx);
-            r1[j] = __float_as_uint(e);
+            const float e = __expf(__uint_as_float(r0[j]) - mx);
+            r0[j] = __float_as_uint(e);
             sum += e;
+          }
+          if (p.dh == 32) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float e = __expf(__uint_as_float(r1[j]) - mx);
+              r1[j] = __float_as_uint(e);
+              sum += e;
+            }
           }
         }
         const float inv = in ? __fdividef(p.q_scale, sum) : 0.f;
@@ -733,39 +842,13 @@ qout_kernel(const __grid_constant__ CUtensorMap tm, const QoutParams p) {
       mbar_wait(d2_full, i & 1);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + 256;
-      float ss[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int c0 = 0; c0 < p.C; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(trow + c0, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float a = __uint_as_float(r[j]) + s_bias[c0 + j];
-          ss[j & 3] = fmaf(a, a, ss[j & 3]);
-        }
+      // whole row into registers behind one wait, accumulator handed back before the math (GEMM2 of the next tile
+      // no longer waits for two load -> wait -> compute passes over TMEM)
+      switch (p.C >> 4) {
+        case 3: qout_finish<3>(p, trow, d2_empty, s_bias, s_gs, in, b, v, cgs); break;
+        case 6: qout_finish<6>(p, trow, d2_empty, s_bias, s_gs, in, b, v, cgs); break;
+        default: qout_finish<0>(p, trow, d2_empty, s_bias, s_gs, in, b, v, cgs); break;
       }
-      const float rinv = 1.f / fmaxf(sqrtf((ss[0] + ss[1]) + (ss[2] + ss[3])), 1e-12f);
-      for (int c0 = 0; c0 < p.C; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(trow + c0, r);
-        tmem_ld_wait();
-        if (!in) continue;
-        const bf16* xp = p.x + (((size_t)b * p.cgtot + p.cgoff + (c0 >> 3)) * cgs + (size_t)v) * 8;
-        bf16* op = p.out + (((size_t)b * p.out_cgtot + (c0 >> 3)) * cgs + (size_t)v) * 8;
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          float xr[8], f[8];
-          unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(xp + (size_t)hf * cgs * 8)), xr);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int ch = c0 + hf * 8 + j;
-            f[j] = fmaf((__uint_as_float(r[hf * 8 + j]) + s_bias[ch]) * rinv, s_gs[ch], xr[j]);
-          }
-          *reinterpret_cast<uint4*>(op + (size_t)hf * cgs * 8) = pack_bf16x8(f);
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(d2_empty);
     }
   }
   tc_fence_before();
@@ -775,10 +858,10 @@ qout_kernel(const __grid_constant__ CUtensorMap tm, const QoutParams p) {
 
 // shift[d] = 1.02 * ||w[d,:] * in_scale||_2 over the k rows of to_qkv (fp32 weights [3*hd][cin])
 __global__ void kshift_kernel(const float* __restrict__ w, const float* __restrict__ in_scale, int hd, int cin,
-                              float* __restrict__ shift) {
+                              float* __restrict__ shift, int row0) {
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= hd) return;
-  const float* wr = w + (size_t)(hd + d) * cin;
+  const float* wr = w + (size_t)(row0 + d) * cin;
   float s = 0.f;
   for (int c = 0; c < cin; ++c) {
     const float v = wr[c] * (in_scale ? in_scale[c] : 1.f);
@@ -801,8 +884,17 @@ combine_head_kernel(const float* __restrict__ part, int nsplit, const float* __r
   const int per = dh * dh + dh;
   const float* pp = part + ((size_t)b * heads + h) * nsplit * per;
   for (int o = threadIdx.x; o < per; o += blockDim.x) {
-    float c = 0.f;
-    for (int sp = 0; sp < nsplit; ++sp) c += pp[(size_t)sp * per + o];
+    // the kernel is one short dependent chain per thread: keep 8 partial loads in flight (4 accumulators, fixed order)
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+    int sp = 0;
+    for (; sp + 8 <= nsplit; sp += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __ldg(pp + (size_t)(sp + j) * per + o);
+      c0 += v[0] + v[4]; c1 += v[1] + v[5]; c2 += v[2] + v[6]; c3 += v[3] + v[7];
+    }
+    for (; sp < nsplit; ++sp) c0 += __ldg(pp + (size_t)sp * per + o);
+    const float c = (c0 + c1) + (c2 + c3);
     if (o < dh * dh) sctx[(o / dh) * 33 + (o % dh)] = c; else ssum[o - dh * dh] = c;
   }
   __syncthreads();
@@ -1018,8 +1110,8 @@ int linattn_context_partial(const Act& qkv, int heads, int dh, int nsplit, const
   return 0;
 }
 
-int linattn_kshift(const float* w_qkv, const float* in_scale, int hd, int cin, float* shift, cudaStream_t st) {
-  kshift_kernel<<<cdiv(hd, 128), 128, 0, st>>>(w_qkv, in_scale, hd, cin, shift);
+int linattn_kshift(const float* w_qkv, const float* in_scale, int hd, int cin, float* shift, cudaStream_t st, int row0) {
+  kshift_kernel<<<cdiv(hd, 128), 128, 0, st>>>(w_qkv, in_scale, hd, cin, shift, row0);
   FTB_LAUNCH_OK();
   return 0;
 }
@@ -1062,7 +1154,7 @@ int linattn_kv_context(const Act& x, int cgoff, int cg, const float* ss, const b
 }
 
 int linattn_q_out(const Act& x, const float* ss, const bf16* wq, const bf16* mb, long long mb_bstride,
-                  const float* bias, const float* gs, int heads, int dh, Act& out, cudaStream_t st) {
+                  const float* bias, const float* gs, int heads, int dh, Act& out, cudaStream_t st, bool q_bounded) {
   FTB_CHECK(heads * dh == 128 && (dh == 32 || dh == 16), "fused q/out needs heads*dim_head == 128, dim_head 16 or 32");
   FTB_CHECK(x.C % 16 == 0 && x.C <= 128 && out.C == x.C && out.B == x.B && out.voxels() == x.voxels(),
             "fused q/out: 16..128 channels, output shaped like the input");
@@ -1078,6 +1170,7 @@ int linattn_q_out(const Act& x, const float* ss, const bf16* wq, const bf16* mb,
   p.nsplit = nsplit < 1 ? 1 : nsplit;
   p.wq = wq; p.mb = mb; p.mb_bstride = mb_bstride; p.x = x.p; p.ss = ss; p.bias = bias; p.gs = gs; p.out = out.p;
   p.q_scale = 1.f / sqrtf((float)dh);
+  p.q_bounded = q_bounded ? 1 : 0;
   p.x_stage = (uint32_t)p.cg * kQoT * 16;
   const uint32_t wq_bytes = (uint32_t)(p.cg / 2) * 4096u, mb_bytes = 8u * (uint32_t)p.C * 32u;
   const uint32_t qbytes = 2u * 16 * kQoT * 16;

@@ -42,7 +42,7 @@ constexpr int kMaxIss = 2;
 constexpr int kMaxN = 256;
 constexpr int kMaxSlots = 12;
 constexpr int kMaxWSlots = 32;
-constexpr int kMaxEnt = 96;   // MMA table entries per group (first-chunk pairs + stacked runs)
+constexpr int kMaxEnt = 128;  // MMA table entries per group and issuer (overwrite table + stacked runs)
 constexpr int kMaxKS = 32;    // k-steps (Cin_pad / 16)
 constexpr int kMaxCC = 16;    // channel chunks (passes) per group
 
@@ -650,24 +650,42 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
           __syncwarp();
           const int z_lo = (iss * nze) / p.n_iss, z_hi = ((iss + 1) * nze) / p.n_iss;
           int cnt = 0, kd_hi = 0, nruns = 0;
+          // "first" table (k-step 0 of the group's first weight chunk, where every accumulator is touched for the first
+          // time and must be overwritten): the issuer's accumulators [z_lo, z_hi) are cut into blocks of c = min(smax, K)
+          // and block [za, za + n) is overwritten by ONE stacked MMA from window plane za + n - 1 (depth taps n-1 .. 0);
+          // all other (plane, tap) pairs follow as accumulating stacked runs.  (Before: one N-wide MMA per pair on all
+          // k-steps of the first chunk - 12 x 44 instead of 372 tensor cycles per k-step for 48 -> 48, NZ 4.)
+          int cnt_ow = 0, rem = 0, nrem = 0;
           if (lane < win && z_hi > z_lo) {
             const int kd_lo = max(0, lane - (z_hi - 1));
             kd_hi = min(2 * p.pad, lane - z_lo);
             cnt = max(0, kd_hi - kd_lo + 1);
             nruns = (cnt + p.smax - 1) / p.smax;
+            const int cblk = min(p.smax, p.K);
+            if (cnt > 0 && kd_lo == 0 && (((lane - z_lo + 1) % cblk) == 0 || lane == z_hi - 1)) cnt_ow = ((lane - z_lo) % cblk) + 1;
+            rem = cnt - cnt_ow;
+            nrem = (rem + p.smax - 1) / p.smax;
           }
-          int sf = cnt, sm = nruns;  // inclusive scans
+          int so = cnt_ow > 0 ? 1 : 0, sr = nrem, sm = nruns;  // inclusive scans
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) {
-            const int tf = __shfl_up_sync(0xffffffffu, sf, o), tm = __shfl_up_sync(0xffffffffu, sm, o);
-            if (lane >= o) { sf += tf; sm += tm; }
+            const int to = __shfl_up_sync(0xffffffffu, so, o), tr = __shfl_up_sync(0xffffffffu, sr, o),
+                      tm = __shfl_up_sync(0xffffffffu, sm, o);
+            if (lane >= o) { so += to; sr += tr; sm += tm; }
           }
-          n_first = __shfl_sync(0xffffffffu, sf, 31);
+          const int n_ow = __shfl_sync(0xffffffffu, so, 31);
+          n_first = n_ow + __shfl_sync(0xffffffffu, sr, 31);
           n_main = __shfl_sync(0xffffffffu, sm, 31);
-          for (int i = 0; i < cnt; ++i) {
-            const int kd = kd_hi - i;
-            tab[sf - cnt + i] = make_uint4((uint32_t)lane, (uint32_t)(p.K - 1 - kd) * nb_enc | (kd > 0 ? 0x80000000u : 0u),
-                                           (uint32_t)((lane - kd) * p.N), idesc0 + idesc_n);
+          if (cnt_ow > 0) {
+            const int kd = cnt_ow - 1;
+            tab[so - 1] = make_uint4((uint32_t)lane, (uint32_t)(p.K - 1 - kd) * nb_enc, (uint32_t)((lane - kd) * p.N),
+                                     idesc0 + (uint32_t)cnt_ow * idesc_n);
+          }
+          for (int r = 0; r < nrem; ++r) {
+            const int kd = kd_hi - r * p.smax;
+            const int ns = min(p.smax, rem - r * p.smax);
+            tab[n_ow + sr - nrem + r] = make_uint4((uint32_t)lane, (uint32_t)(p.K - 1 - kd) * nb_enc | 0x80000000u,
+                                                   (uint32_t)((lane - kd) * p.N), idesc0 + (uint32_t)ns * idesc_n);
           }
           for (int r = 0; r < nruns; ++r) {
             const int kd = kd_hi - r * p.smax;
@@ -719,18 +737,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
                 }
                 const uint32_t wb = w_enc + wslot_i * wchunk_enc;
                 const bool firstc = (cc | t) == 0;
-                const uint32_t ea = tab_addr + (firstc ? 0u : (uint32_t)n_first * 16u);
-                const uint32_t ea_end = ea + (uint32_t)(firstc ? n_first : n_main) * 16u;
+                const uint32_t ea_m = tab_addr + (uint32_t)n_first * 16u, ea_m_end = ea_m + (uint32_t)n_main * 16u;
                 long long ti0 = 0;
                 if (p.dbg) ti0 = clock64();
-                switch (nks) {   // straight-line k-step issue for the common chunk lengths
-                  case 1: issue_entries<1>(ic, ea, ea_end, aoff, wb, firstc); break;
-                  case 2: issue_entries<2>(ic, ea, ea_end, aoff, wb, firstc); break;
-                  case 3: issue_entries<3>(ic, ea, ea_end, aoff, wb, firstc); break;
-                  case 4: issue_entries<4>(ic, ea, ea_end, aoff, wb, firstc); break;
+                int nk = nks;
+                uint32_t ao = aoff, wo = wb;
+                if (firstc) {   // k-step 0 through the overwrite table, the rest of the chunk like any other
+                  issue_entries<1>(ic, tab_addr, tab_addr + (uint32_t)n_first * 16u, ao, wo, true);
+                  --nk; ao += ic.kinc; wo += ic.kstep;
+                }
+                switch (nk) {   // straight-line k-step issue for the common chunk lengths
+                  case 0: break;
+                  case 1: issue_entries<1>(ic, ea_m, ea_m_end, ao, wo, false); break;
+                  case 2: issue_entries<2>(ic, ea_m, ea_m_end, ao, wo, false); break;
+                  case 3: issue_entries<3>(ic, ea_m, ea_m_end, ao, wo, false); break;
+                  case 4: issue_entries<4>(ic, ea_m, ea_m_end, ao, wo, false); break;
                   default:
-                    for (int i = 0; i < nks; ++i)
-                      issue_entries<1>(ic, ea, ea_end, aoff + i * ic.kinc, wb + i * ic.kstep, firstc && i == 0);
+                    for (int i = 0; i < nk; ++i)
+                      issue_entries<1>(ic, ea_m, ea_m_end, ao + i * ic.kinc, wo + i * ic.kstep, false);
                 }
                 if (p.dbg) dbg_issue += clock64() - ti0;
                 if (stream_w) {
@@ -1043,7 +1067,7 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
     const int v = atoi(env);
     if (v >= 1 && v < nz_cap) nz_cap = v;
   }
-  while (nz_cap > 1 && (nz_cap * p.K > kMaxEnt / 2 || nz_cap + 2 * p.pad > 32)) --nz_cap;
+  while (nz_cap > 1 && (nz_cap * p.K > 48 || nz_cap + 2 * p.pad > 32)) --nz_cap;   // tables: <= 8 + 2 * 48 entries
   FTB_CHECK(nz_cap >= 1, "conv: N tile too wide for a double-buffered accumulator");
   // Smaller channel chunks are tried before a shorter tile: a wide kernel (K = 7: window of NZ + 6
   // planes) only fits with 32- or 16-channel chunks, and a full-height tile keeps all 128 MMA rows busy.

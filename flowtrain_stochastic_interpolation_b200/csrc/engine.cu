@@ -146,7 +146,7 @@ struct ftb_unet {
   std::map<std::string, int> pindex;
   std::map<std::string, ConvLayer> convs;
   std::map<std::string, GainVec> gains;
-  struct KShift { float* dev = nullptr; bool ok = false; };
+  struct KShift { float* dev = nullptr; bool ok = false; bool q_ok = false; };
   std::map<std::string, KShift> kshift;   // LinearAttention layers: softmax shift of the fused k/v-context path
   std::vector<std::string> film_blocks;  // FiLM-table rows: prefix of the (SiLU, Linear) time MLP's Linear
   std::map<std::string, std::string> film_gain;   // block -> gain vector folded into its scale half ("" = none)
@@ -507,7 +507,14 @@ int finalize_kshift(ftb_unet* U, cudaStream_t st) {
   for (auto& kv : U->kshift) {
     const ConvLayer& cl = U->convs.at(kv.first + ".to_qkv");
     const float* w = U->params[U->pindex[cl.wname]].dev;
-    FTB_TRY(linattn_kshift(w, cl.scale_tmp, hd, cl.cin, kv.second.dev, st));
+    // the same bound for the q rows: |q[d,n]| <= 60 lets the fused q/out kernel drop the max pass of its softmax
+    FTB_TRY(linattn_kshift(w, cl.scale_tmp, hd, cl.cin, kv.second.dev, st, 0));
+    FTB_CUDA(cudaMemcpyAsync(hshift.data(), kv.second.dev, hd * sizeof(float), cudaMemcpyDeviceToHost, st));
+    FTB_CUDA(cudaStreamSynchronize(st));
+    float mq = 0.f;
+    for (float v : hshift) mq = v > mq || !(v == v) ? v : mq;
+    kv.second.q_ok = mq == mq && mq <= 60.f && getenv("FTB_LINATTN_EXACT") == nullptr;
+    FTB_TRY(linattn_kshift(w, cl.scale_tmp, hd, cl.cin, kv.second.dev, st, hd));
     FTB_CUDA(cudaMemcpyAsync(hshift.data(), kv.second.dev, hd * sizeof(float), cudaMemcpyDeviceToHost, st));
     FTB_CUDA(cudaStreamSynchronize(st));
     float mx = 0.f;
@@ -670,7 +677,7 @@ struct Fwd {
         }
         if (fused) {
           FTB_TRY(linattn_q_out(x, x_sumsq, cq.packed, mpack, (long long)x.C * hd, pdev(p + ".to_out.0.bias"),
-                                U->gains.at(p + ".to_out.1.g").gs, heads, dh, *out, st));
+                                U->gains.at(p + ".to_out.1.g").gs, heads, dh, *out, st, U->kshift.at(p).q_ok));
           U->launches += 1;
         } else {
           ConvWeights w;

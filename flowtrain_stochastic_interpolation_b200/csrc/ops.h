@@ -140,13 +140,15 @@ int linattn_context_partial(const Act& qkv, int heads, int dh, int nsplit, const
 // phase A2: merge partials + memory kv, fold W_out -> per-sample packed 1x1 weights M_b[C][heads*dh]
 // fused k/v projection + context (never writes k, v): x blocked bf16 (channel groups [cgoff, cgoff+cg)),
 // ss = ||x voxel||^2, wk / wv = packed K-major tiles of the k / v rows of to_qkv, shift[hd] >= |k|
-int linattn_kshift(const float* w_qkv, const float* in_scale, int hd, int cin, float* shift, cudaStream_t st);
+// shift[d] = 1.02 ||W[row0 + d, :] (x) in_scale||_2: row0 = hd for the k rows of to_qkv (softmax shift), 0 for the q rows
+int linattn_kshift(const float* w_qkv, const float* in_scale, int hd, int cin, float* shift, cudaStream_t st, int row0);
 int linattn_kv_context(const Act& x, int cgoff, int cg, const float* ss, const bf16* wk, const bf16* wv,
                        const float* shift, int heads, int dh, int nsplit, float* part, cudaStream_t st);
 // fused q projection + q softmax + (context . q) + to_out + bias + RMSNorm + residual (never writes q):
 // wq = packed q rows of to_qkv, mb = per-sample packed folded projection from linattn_combine
 int linattn_q_out(const Act& x, const float* ss, const bf16* wq, const bf16* mb, long long mb_bstride,
-                  const float* bias, const float* gs, int heads, int dh, Act& out, cudaStream_t st);
+                  const float* bias, const float* gs, int heads, int dh, Act& out, cudaStream_t st,
+                  bool q_bounded = false);
 // kmax_bstride: elements between samples of `kmax` (0: one shift vector for the whole batch)
 int linattn_combine(const float* part, int nsplit, const float* kmax, int kmax_bstride, int B, int heads, int dh,
                     const float* mem_kv, int n_mem, const float* w_out, int C, float q_scale,

@@ -516,37 +516,33 @@ __global__ void qsoftmax_bwd_kernel(bf16* __restrict__ dqkv, const bf16* __restr
     }
   }
 }
-// mem_kv [2][heads][dh][n_mem] gradient; grid (heads), block dh*n_mem threads (<= 256)
+// mem_kv [2][heads][dh][n_mem] gradient; grid (heads, B), block dh*n_mem threads (<= 256); samples add atomically
+// (one block per head looping over the batch was a 50 us serial chain per layer)
 __global__ void linattn_mem_bwd_kernel(const float* __restrict__ mem_kv, int n_mem, const float* __restrict__ kstat,
                                        const float* __restrict__ dctx, const float* __restrict__ ssum, int B, int heads,
                                        int dh, float* __restrict__ dmem) {
-  const int h = blockIdx.x, hd = heads * dh;
+  __shared__ float s_kt[32 * 8];   // softmaxed memory keys kt[d][j] of this (head, sample)
+  const int h = blockIdx.x, b = blockIdx.y, hd = heads * dh;
   const int t = threadIdx.x;
-  if (t >= dh * n_mem) return;
-  const int x = t / n_mem, j = t % n_mem;   // x = d for the k gradient, e for the v gradient
-  float gk = 0.f, gv = 0.f;
-  for (int b = 0; b < B; ++b) {
-    const float* dc = dctx + ((size_t)b * heads + h) * dh * dh;
-    const float* ks = kstat + ((size_t)b * hd + h * dh) * 2;
-    // dk: d = x
-    {
-      const float kt = __expf(mem_kv[((size_t)h * dh + x) * n_mem + j] - ks[2 * x]) / ks[2 * x + 1];
-      float a = 0.f;
-      for (int e = 0; e < dh; ++e) a = fmaf(mem_kv[((size_t)hd + h * dh + e) * n_mem + j], dc[x * dh + e], a);
-      gk += kt * (a - ssum[(size_t)b * hd + h * dh + x]);
-    }
-    // dv: e = x
-    {
-      float a = 0.f;
-      for (int d = 0; d < dh; ++d) {
-        const float kt = __expf(mem_kv[((size_t)h * dh + d) * n_mem + j] - ks[2 * d]) / ks[2 * d + 1];
-        a = fmaf(kt, dc[d * dh + x], a);
-      }
-      gv += a;
-    }
+  const bool on = t < dh * n_mem;
+  const int x = on ? t / n_mem : 0, j = on ? t % n_mem : 0;   // x = d for the k gradient, e for the v gradient
+  const float* dc = dctx + ((size_t)b * heads + h) * dh * dh;
+  const float* ks = kstat + ((size_t)b * hd + h * dh) * 2;
+  float kt = 0.f;
+  if (on) {
+    kt = __expf(mem_kv[((size_t)h * dh + x) * n_mem + j] - ks[2 * x]) / ks[2 * x + 1];
+    s_kt[x * n_mem + j] = kt;
   }
-  dmem[((size_t)h * dh + x) * n_mem + j] += gk;
-  dmem[((size_t)hd + h * dh + x) * n_mem + j] += gv;
+  __syncthreads();
+  if (!on) return;
+  float a = 0.f, g = 0.f;
+#pragma unroll 8
+  for (int e = 0; e < dh; ++e) {
+    a = fmaf(__ldg(mem_kv + ((size_t)hd + h * dh + e) * n_mem + j), __ldg(dc + x * dh + e), a);   // dk: d = x
+    g = fmaf(s_kt[e * n_mem + j], __ldg(dc + e * dh + x), g);                                     // dv: e = x
+  }
+  atomicAdd(dmem + ((size_t)h * dh + x) * n_mem + j, kt * (a - ssum[(size_t)b * hd + h * dh + x]));
+  atomicAdd(dmem + ((size_t)hd + h * dh + x) * n_mem + j, g);
 }
 
 // ---------------------------------------------------------------- softmax Attention backward
@@ -914,8 +910,8 @@ int qsoftmax_bwd(Act& dqkv, const Act& qkv, int heads, int dh, cudaStream_t st) 
 }
 int linattn_mem_bwd(const float* mem_kv, int n_mem, const float* kstat, const float* dctx, const float* ssum, int B,
                     int heads, int dh, float* dmem, cudaStream_t st) {
-  FTB_CHECK(dh * n_mem <= 256, "linattn_mem_bwd: dim_head * num_mem_kv must be <= 256");
-  linattn_mem_bwd_kernel<<<heads, 256, 0, st>>>(mem_kv, n_mem, kstat, dctx, ssum, B, heads, dh, dmem);
+  FTB_CHECK(dh * n_mem <= 256 && dh <= 32 && n_mem <= 8, "linattn_mem_bwd: dim_head <= 32, num_mem_kv <= 8");
+  linattn_mem_bwd_kernel<<<dim3(heads, B), 256, 0, st>>>(mem_kv, n_mem, kstat, dctx, ssum, B, heads, dh, dmem);
   FTB_LAUNCH_OK();
   return 0;
 }

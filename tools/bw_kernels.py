@@ -67,20 +67,23 @@ def timed(fn, n=5):
     return e0.elapsed_time(e1) / n * 1e3
 
 
+PART = os.environ.get("FTB_BW_PART", "all")    # "standalone" | "train" | "all": what the profiler window covers
 standalone()                                   # warm-up (weight packing, attribute setting)
 torch.cuda.synchronize()
-torch.cuda.profiler.start()
-standalone()
-torch.cuda.synchronize()
-torch.cuda.profiler.stop()
-net.train()
-tr = ftb.FlowTrainer(mod, lr=2e-4, max_grad_norm=1.0, ema_decay=0.9995)
-train_step(tr); train_step(tr)                 # warm-up (EMA shadow created on the first step)
-torch.cuda.synchronize()
-torch.cuda.profiler.start()
-train_step(tr)
-torch.cuda.synchronize()
-torch.cuda.profiler.stop()
+if PART in ("all", "standalone"):
+    torch.cuda.profiler.start()
+    standalone()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+if PART in ("all", "train"):
+    net.train()
+    tr = ftb.FlowTrainer(mod, lr=2e-4, max_grad_norm=1.0, ema_decay=0.9995)
+    train_step(tr); train_step(tr)             # warm-up (EMA shadow created on the first step)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    train_step(tr)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
 
 if not os.environ.get("FTB_BW_NO_TIMING"):     # CUDA-event timings of the kernels that can be called alone (L2 > inputs)
     n = x.numel()
