@@ -208,72 +208,77 @@ __device__ __forceinline__ void epi_prefetch_resid(const IgemmParams& p, const E
 }
 
 // y = (acc * rs) * mul + add'   (no norm; bias already folded into add')
+// NLD x 16 columns behind ONE tcgen05.wait (the rows of the 1^3 convs are bound by TMEM round trips, not arithmetic)
+template <int NLD, bool kTrain>
+__device__ __forceinline__ void epi_affine_chunk(const IgemmParams& p, EpiCtx& ec, uint32_t trow, int c0, size_t vox,
+                                                 float rs) {
+  uint32_t r[NLD][16];
+#pragma unroll
+  for (int i = 0; i < NLD; ++i) tmem_ld16(trow + c0 + i * 16, r[i]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < NLD; ++i) {
+    float v[16];
+#pragma unroll
+    for (int j4 = 0; j4 < 16; j4 += 4) {
+      const float4 mu = *reinterpret_cast<const float4*>(ec.mul + c0 + i * 16 + j4);
+      const float4 ad = *reinterpret_cast<const float4*>(ec.add + c0 + i * 16 + j4);
+      v[j4 + 0] = fmaf(__uint_as_float(r[i][j4 + 0]) * rs, mu.x, ad.x);
+      v[j4 + 1] = fmaf(__uint_as_float(r[i][j4 + 1]) * rs, mu.y, ad.y);
+      v[j4 + 2] = fmaf(__uint_as_float(r[i][j4 + 2]) * rs, mu.z, ad.z);
+      v[j4 + 3] = fmaf(__uint_as_float(r[i][j4 + 3]) * rs, mu.w, ad.w);
+    }
+    epi_store16<kTrain>(p, ec, c0 + i * 16, vox, v);
+  }
+}
+
 template <bool kTrain>
 __device__ __forceinline__ void epi_affine(const IgemmParams& p, EpiCtx& ec, uint32_t trow,
                                            size_t vox, float rs) {
   epi_prefetch_resid(p, ec, vox);
-  for (int c0 = 0; c0 < p.N; c0 += 32) {
-    uint32_t r0[16], r1[16];
-    const bool two = c0 + 16 < p.N;
-    tmem_ld16(trow + c0, r0);
-    if (two) tmem_ld16(trow + c0 + 16, r1);
-    tmem_ld_wait();
-    float v[16];
-#pragma unroll
-    for (int j4 = 0; j4 < 16; j4 += 4) {
-      const float4 mu = *reinterpret_cast<const float4*>(ec.mul + c0 + j4);
-      const float4 ad = *reinterpret_cast<const float4*>(ec.add + c0 + j4);
-      v[j4 + 0] = fmaf(__uint_as_float(r0[j4 + 0]) * rs, mu.x, ad.x);
-      v[j4 + 1] = fmaf(__uint_as_float(r0[j4 + 1]) * rs, mu.y, ad.y);
-      v[j4 + 2] = fmaf(__uint_as_float(r0[j4 + 2]) * rs, mu.z, ad.z);
-      v[j4 + 3] = fmaf(__uint_as_float(r0[j4 + 3]) * rs, mu.w, ad.w);
-    }
-    epi_store16<kTrain>(p, ec, c0, vox, v);
-    if (two) {
-#pragma unroll
-      for (int j4 = 0; j4 < 16; j4 += 4) {
-        const float4 mu = *reinterpret_cast<const float4*>(ec.mul + c0 + 16 + j4);
-        const float4 ad = *reinterpret_cast<const float4*>(ec.add + c0 + 16 + j4);
-        v[j4 + 0] = fmaf(__uint_as_float(r1[j4 + 0]) * rs, mu.x, ad.x);
-        v[j4 + 1] = fmaf(__uint_as_float(r1[j4 + 1]) * rs, mu.y, ad.y);
-        v[j4 + 2] = fmaf(__uint_as_float(r1[j4 + 2]) * rs, mu.z, ad.z);
-        v[j4 + 3] = fmaf(__uint_as_float(r1[j4 + 3]) * rs, mu.w, ad.w);
-      }
-      epi_store16<kTrain>(p, ec, c0 + 16, vox, v);
-    }
-  }
+  int c0 = 0;
+  for (; c0 + 48 <= p.N; c0 += 48) epi_affine_chunk<3, kTrain>(p, ec, trow, c0, vox, rs);
+  if (c0 + 32 <= p.N) { epi_affine_chunk<2, kTrain>(p, ec, trow, c0, vox, rs); c0 += 32; }
+  if (c0 + 16 <= p.N) epi_affine_chunk<1, kTrain>(p, ec, trow, c0, vox, rs);
 }
 
 // y = acc * rs: no bias, affine, activation or residual (k and v of to_qkv)
-__device__ __forceinline__ void epi_plain(const IgemmParams& p, EpiCtx& ec, uint32_t trow, size_t vox, float rs) {
-  for (int c0 = 0; c0 < p.N; c0 += 32) {
-    uint32_t r0[16], r1[16];
-    const bool two = c0 + 16 < p.N;
-    tmem_ld16(trow + c0, r0);
-    if (two) tmem_ld16(trow + c0 + 16, r1);
-    tmem_ld_wait();
-    if (!ec.valid) continue;
-    bf16* dst = ec.out_b + ((size_t)(p.out_cgoff + (c0 >> 3)) * ec.cgs + vox) * 8;
-    float f[8];
+template <int NLD>
+__device__ __forceinline__ void epi_plain_chunk(const IgemmParams& p, EpiCtx& ec, uint32_t trow, int c0, size_t vox,
+                                                float rs) {
+  uint32_t r[NLD][16];
+#pragma unroll
+  for (int i = 0; i < NLD; ++i) tmem_ld16(trow + c0 + i * 16, r[i]);
+  tmem_ld_wait();
+  if (!ec.valid) return;
+  bf16* dst = ec.out_b + ((size_t)(p.out_cgoff + (c0 >> 3)) * ec.cgs + vox) * 8;
+#pragma unroll
+  for (int i = 0; i < NLD; ++i)
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
+      float f[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r0[hf * 8 + j]) * rs;
-      *reinterpret_cast<uint4*>(dst + (size_t)hf * ec.cgs * 8) = pack_bf16x8(f);
+      for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[i][hf * 8 + j]) * rs;
+      *reinterpret_cast<uint4*>(dst + (size_t)(2 * i + hf) * ec.cgs * 8) = pack_bf16x8(f);
     }
-    if (two) {
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r1[hf * 8 + j]) * rs;
-        *reinterpret_cast<uint4*>(dst + (size_t)(2 + hf) * ec.cgs * 8) = pack_bf16x8(f);
-      }
-    }
-  }
+}
+__device__ __forceinline__ void epi_plain(const IgemmParams& p, EpiCtx& ec, uint32_t trow, size_t vox, float rs) {
+  int c0 = 0;
+  for (; c0 + 64 <= p.N; c0 += 64) epi_plain_chunk<4>(p, ec, trow, c0, vox, rs);
+  if (c0 + 32 <= p.N) { epi_plain_chunk<2>(p, ec, trow, c0, vox, rs); c0 += 32; }
+  if (c0 + 16 <= p.N) epi_plain_chunk<1>(p, ec, trow, c0, vox, rs);
 }
 
 // channel RMSNorm (unet_attn_3d.py:127-128) with the whole voxel row held in registers:
 // v = acc*rs + bias; y = v / max(||v||, 1e-12) * mul + add
+// residual row of voxel `vox` (all channel groups of this N tile) into registers
+template <int NCG>
+__device__ __forceinline__ void epi_load_resid(const IgemmParams& p, const EpiCtx& ec, size_t vox, uint4 (&pre)[NCG]) {
+  const bf16* rp = ec.res_b + ((size_t)p.resid_cgoff * ec.cgs + vox) * 8;
+#pragma unroll
+  for (int i = 0; i < NCG; ++i) pre[i] = __ldg(reinterpret_cast<const uint4*>(rp + (size_t)i * ec.cgs * 8));
+}
+
 template <int NCH, bool kTrain>
 __device__ __forceinline__ void epi_norm_regs(const IgemmParams& p, EpiCtx& ec, uint32_t trow,
                                               size_t vox, float rs) {
@@ -282,9 +287,7 @@ __device__ __forceinline__ void epi_norm_regs(const IgemmParams& p, EpiCtx& ec, 
   const bool has_res = ec.res_b != nullptr && ec.valid;
   if (kPre) {
     if (has_res) {
-      const bf16* rp = ec.res_b + ((size_t)p.resid_cgoff * ec.cgs + vox) * 8;
-#pragma unroll
-      for (int i = 0; i < 2 * NCH; ++i) pre[i] = __ldg(reinterpret_cast<const uint4*>(rp + (size_t)i * ec.cgs * 8));
+      epi_load_resid<2 * NCH>(p, ec, vox, pre);
     }
   } else {
     epi_prefetch_resid(p, ec, vox);
@@ -338,55 +341,47 @@ __device__ __forceinline__ void epi_norm_regs(const IgemmParams& p, EpiCtx& ec, 
 }
 
 // same, any N: one TMEM pass for the norm, a second for the output
-template <bool kTrain>
-__device__ __forceinline__ void epi_norm_2pass(const IgemmParams& p, EpiCtx& ec, uint32_t trow,
-                                               size_t vox, float rs) {
-  epi_prefetch_resid(p, ec, vox);
-  float ss[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int c0 = 0; c0 < p.N; c0 += 32) {
-    uint32_t r0[16], r1[16];
-    const bool two = c0 + 16 < p.N;
-    tmem_ld16(trow + c0, r0);
-    if (two) tmem_ld16(trow + c0 + 16, r1);
-    tmem_ld_wait();
+// pass 1 of the two-pass norm: sum of squares of NLD x 16 columns behind one tcgen05.wait
+template <int NLD>
+__device__ __forceinline__ void epi_norm_ss_chunk(const EpiCtx& ec, uint32_t trow, int c0, float rs, float (&ss)[4]) {
+  uint32_t r[NLD][16];
+#pragma unroll
+  for (int i = 0; i < NLD; ++i) tmem_ld16(trow + c0 + i * 16, r[i]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < NLD; ++i)
 #pragma unroll
     for (int j4 = 0; j4 < 16; j4 += 4) {
-      const float4 bi = *reinterpret_cast<const float4*>(ec.bias + c0 + j4);
-      const float a0 = fmaf(__uint_as_float(r0[j4 + 0]), rs, bi.x);
-      const float a1 = fmaf(__uint_as_float(r0[j4 + 1]), rs, bi.y);
-      const float a2 = fmaf(__uint_as_float(r0[j4 + 2]), rs, bi.z);
-      const float a3 = fmaf(__uint_as_float(r0[j4 + 3]), rs, bi.w);
+      const float4 bi = *reinterpret_cast<const float4*>(ec.bias + c0 + i * 16 + j4);
+      const float a0 = fmaf(__uint_as_float(r[i][j4 + 0]), rs, bi.x);
+      const float a1 = fmaf(__uint_as_float(r[i][j4 + 1]), rs, bi.y);
+      const float a2 = fmaf(__uint_as_float(r[i][j4 + 2]), rs, bi.z);
+      const float a3 = fmaf(__uint_as_float(r[i][j4 + 3]), rs, bi.w);
       ss[0] = fmaf(a0, a0, ss[0]); ss[1] = fmaf(a1, a1, ss[1]);
       ss[2] = fmaf(a2, a2, ss[2]); ss[3] = fmaf(a3, a3, ss[3]);
     }
-    if (two) {
+}
+// pass 2: normalise, affine, finish NLD x 16 columns behind one tcgen05.wait
+template <int NLD, bool kTrain>
+__device__ __forceinline__ void epi_norm_out_chunk(const IgemmParams& p, EpiCtx& ec, uint32_t trow, int c0, size_t vox,
+                                                   float rs, float rinv) {
+  uint32_t r[NLD][16];
 #pragma unroll
-      for (int j4 = 0; j4 < 16; j4 += 4) {
-        const float4 bi = *reinterpret_cast<const float4*>(ec.bias + c0 + 16 + j4);
-        const float a0 = fmaf(__uint_as_float(r1[j4 + 0]), rs, bi.x);
-        const float a1 = fmaf(__uint_as_float(r1[j4 + 1]), rs, bi.y);
-        const float a2 = fmaf(__uint_as_float(r1[j4 + 2]), rs, bi.z);
-        const float a3 = fmaf(__uint_as_float(r1[j4 + 3]), rs, bi.w);
-        ss[0] = fmaf(a0, a0, ss[0]); ss[1] = fmaf(a1, a1, ss[1]);
-        ss[2] = fmaf(a2, a2, ss[2]); ss[3] = fmaf(a3, a3, ss[3]);
-      }
-    }
-  }
-  const float rinv = 1.f / fmaxf(sqrtf((ss[0] + ss[1]) + (ss[2] + ss[3])), 1e-12f);
-  for (int c0 = 0; c0 < p.N; c0 += 16) {
-    uint32_t r0[16];
-    tmem_ld16(trow + c0, r0);
-    tmem_ld_wait();
+  for (int i = 0; i < NLD; ++i) tmem_ld16(trow + c0 + i * 16, r[i]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < NLD; ++i) {
+    const int cc = c0 + i * 16;
     float v[16];
 #pragma unroll
     for (int j4 = 0; j4 < 16; j4 += 4) {
-      const float4 bi = *reinterpret_cast<const float4*>(ec.bias + c0 + j4);
-      const float4 mu = *reinterpret_cast<const float4*>(ec.mul + c0 + j4);
-      const float4 ad = *reinterpret_cast<const float4*>(ec.add + c0 + j4);
-      const float a0 = fmaf(__uint_as_float(r0[j4 + 0]), rs, bi.x), a1 = fmaf(__uint_as_float(r0[j4 + 1]), rs, bi.y);
-      const float a2 = fmaf(__uint_as_float(r0[j4 + 2]), rs, bi.z), a3 = fmaf(__uint_as_float(r0[j4 + 3]), rs, bi.w);
-      r0[j4 + 0] = __float_as_uint(a0); r0[j4 + 1] = __float_as_uint(a1);
-      r0[j4 + 2] = __float_as_uint(a2); r0[j4 + 3] = __float_as_uint(a3);
+      const float4 bi = *reinterpret_cast<const float4*>(ec.bias + cc + j4);
+      const float4 mu = *reinterpret_cast<const float4*>(ec.mul + cc + j4);
+      const float4 ad = *reinterpret_cast<const float4*>(ec.add + cc + j4);
+      const float a0 = fmaf(__uint_as_float(r[i][j4 + 0]), rs, bi.x), a1 = fmaf(__uint_as_float(r[i][j4 + 1]), rs, bi.y);
+      const float a2 = fmaf(__uint_as_float(r[i][j4 + 2]), rs, bi.z), a3 = fmaf(__uint_as_float(r[i][j4 + 3]), rs, bi.w);
+      r[i][j4 + 0] = __float_as_uint(a0); r[i][j4 + 1] = __float_as_uint(a1);
+      r[i][j4 + 2] = __float_as_uint(a2); r[i][j4 + 3] = __float_as_uint(a3);
       v[j4 + 0] = fmaf(a0 * rinv, mu.x, ad.x);
       v[j4 + 1] = fmaf(a1 * rinv, mu.y, ad.y);
       v[j4 + 2] = fmaf(a2 * rinv, mu.z, ad.z);
@@ -397,12 +392,29 @@ __device__ __forceinline__ void epi_norm_2pass(const IgemmParams& p, EpiCtx& ec,
       for (int hf = 0; hf < 2; ++hf) {
         float f[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r0[hf * 8 + j]);
-        *reinterpret_cast<uint4*>(ec.u_b + ((size_t)(p.out_cgoff + (c0 >> 3) + hf) * ec.cgs + vox) * 8) = pack_bf16x8(f);
+        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[i][hf * 8 + j]);
+        *reinterpret_cast<uint4*>(ec.u_b + ((size_t)(p.out_cgoff + (cc >> 3) + hf) * ec.cgs + vox) * 8) = pack_bf16x8(f);
       }
     }
-    epi_store16<kTrain>(p, ec, c0, vox, v);
+    epi_store16<kTrain>(p, ec, cc, vox, v);
   }
+}
+
+// same, any N: one TMEM pass for the norm, a second for the output (64 / 48 columns per tcgen05.wait)
+template <bool kTrain>
+__device__ __forceinline__ void epi_norm_2pass(const IgemmParams& p, EpiCtx& ec, uint32_t trow,
+                                               size_t vox, float rs) {
+  epi_prefetch_resid(p, ec, vox);
+  float ss[4] = {0.f, 0.f, 0.f, 0.f};
+  int c0 = 0;
+  for (; c0 + 64 <= p.N; c0 += 64) epi_norm_ss_chunk<4>(ec, trow, c0, rs, ss);
+  if (c0 + 32 <= p.N) { epi_norm_ss_chunk<2>(ec, trow, c0, rs, ss); c0 += 32; }
+  if (c0 + 16 <= p.N) epi_norm_ss_chunk<1>(ec, trow, c0, rs, ss);
+  const float rinv = 1.f / fmaxf(sqrtf((ss[0] + ss[1]) + (ss[2] + ss[3])), 1e-12f);
+  c0 = 0;
+  for (; c0 + 48 <= p.N; c0 += 48) epi_norm_out_chunk<3, kTrain>(p, ec, trow, c0, vox, rs, rinv);
+  if (c0 + 32 <= p.N) { epi_norm_out_chunk<2, kTrain>(p, ec, trow, c0, vox, rs, rinv); c0 += 32; }
+  if (c0 + 16 <= p.N) epi_norm_out_chunk<1, kTrain>(p, ec, trow, c0, vox, rs, rinv);
 }
 
 // LinearAttention q: softmax over each dim_head group of this voxel, times dim_head^-0.5
@@ -849,6 +861,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
           // voxel index within one (b, cg): flat tiles are 128 consecutive voxels (the last may be ragged)
           const size_t vox = p.flat ? (size_t)d * 128 + m : (size_t)d * plane_vox + (size_t)h * p.W + w;
           if (p.flat) ec.valid = vox < cgs;
+          // The residual row is consumed at the very end of a row's epilogue, yet its HBM latency used to be the longest
+          // stall of the whole epilogue (~4 000 of 9 000 cycles per row, FTB_CONV_DBG): pull the rows of the NEXT plane
+          // this half will finish (in this group or the next) into L2 now, one plane ahead, at no register cost.
+          if (ec.res_b) {
+            long long nv = -1;
+            const size_t vstep = p.flat ? 128 : plane_vox;
+            if (zi + 2 < nze) nv = (long long)(vox + 2 * vstep);
+            else if (g + 1 < ngroups) {
+              const int z2 = (half + g + 1) & 1;
+              if (z2 < min(p.NZ, c.lz - (g + 1) * p.NZ)) nv = (long long)(vox + (size_t)(p.NZ - zi + z2) * vstep);
+            }
+            if (nv >= 0 && (p.flat ? (size_t)nv < cgs : ec.valid)) {
+              const bf16* rp = ec.res_b + ((size_t)p.resid_cgoff * cgs + (size_t)nv) * 8;
+              for (int cg = 0; cg < (p.N >> 3); ++cg)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (size_t)cg * cgs * 8));
+            }
+          }
           const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (ab * p.NZ + zi) * p.N;
           float rs = 1.f;
           if (p.ss_in) {

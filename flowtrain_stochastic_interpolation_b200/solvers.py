@@ -198,7 +198,8 @@ def integrate_adaptive(func, X0, t0, tf, n_steps, method="dopri5", rtol=1e-6, at
     # the reference builds the output grid in fp32 (solvers.py:59; float64 at :126); torchdiffeq carries time in float64
     ghost = torch.linspace(t0, tf, n_steps, dtype=grid_dtype).double() if n_steps > 1 else torch.tensor([float(t0)], dtype=torch.float64)
     n_out = ghost.numel()
-    grid = ghost.to(dev)
+    ghost = ghost.pin_memory()
+    grid = ghost.to(dev, non_blocking=True)    # pinned + asynchronous: setting a solve up does not synchronise either
     ctl = torch.empty(16, dtype=torch.float64, device=dev)
     tbuf = torch.empty(B, dtype=torch.float32, device=dev)
     cp = lambda k: C.c_void_p(ctl.data_ptr() + 8 * k)
