@@ -960,7 +960,7 @@ int make_plane_tmap(CUtensorMap* tm, const Act& a, int BW, int BH, int cg) {
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.p, gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   tma_promo(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FTB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
   return 0;
 }
@@ -986,7 +986,7 @@ int make_voxel_tmap(CUtensorMap* tm, const Act& a, int box_vox, int box_cg) {
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a.p, gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   tma_promo(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FTB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (voxel view) failed (" + std::to_string((int)r) + ")");
   return 0;
 }

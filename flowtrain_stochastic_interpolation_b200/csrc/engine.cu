@@ -1267,6 +1267,8 @@ static int train_backward_impl(ftb_unet* h, TrainState* T, TrainCtx& c, const fl
   c.dfilm = c.f32((size_t)c.B * h->film_rows);
   c.dts = c.f32((size_t)c.B * h->time_dim);
   c.wt_tmp = c.f32(max_wt_elems(h));
+  c.wg_part_bytes = conv_wgrad_partial_bytes();
+  c.wg_part = c.f32(c.wg_part_bytes / sizeof(float));
   FTB_TRY(c.zero(c.dfilm, (size_t)c.B * h->film_rows * sizeof(float)));
   FTB_TRY(c.zero(c.dts, (size_t)c.B * h->time_dim * sizeof(float)));
   if (!c.dry && h->dgrad_dirty) FTB_TRY(pack_dgrad(h, c.wt_tmp, c.st));
@@ -1520,12 +1522,15 @@ int ftb_test_conv_wgrad(const float* x, int c1, const float* x2, int c2, const f
   FTB_TRY(pack_ncdhw_to_blocked(dy, B, cout, X, Y, Z, ady, st));
   const int cin = c1 + (x2 ? c2 : 0);
   FTB_CUDA(cudaMemsetAsync(dw, 0, (size_t)cout * cin * ksize * ksize * ksize * sizeof(float), st));
-  FTB_TRY(conv_wgrad(a0, 0, a0.cg(), ady, 0, cout, ksize, unfold ? c1 : 0, dw, cin, 0, c1, 0, st));
+  const size_t pbytes = conv_wgrad_partial_bytes();
+  float* part = S.get<float>(pbytes / sizeof(float));
+  FTB_CHECK(part, "scratch allocation failed");
+  FTB_TRY(conv_wgrad(a0, 0, a0.cg(), ady, 0, cout, ksize, unfold ? c1 : 0, dw, cin, 0, c1, 0, st, part, pbytes));
   if (x2) {
     a1 = mk(c2);
     FTB_CHECK(a1.p, "scratch allocation failed");
     FTB_TRY(pack_ncdhw_to_blocked(x2, B, c2, X, Y, Z, a1, st));
-    FTB_TRY(conv_wgrad(a1, 0, a1.cg(), ady, 0, cout, ksize, 0, dw, cin, c1, c2, 0, st));
+    FTB_TRY(conv_wgrad(a1, 0, a1.cg(), ady, 0, cout, ksize, 0, dw, cin, c1, c2, 0, st, part, pbytes));
   }
   FTB_CUDA(cudaStreamSynchronize(st));
   return 0;

@@ -48,6 +48,8 @@ struct TrainCtx {
   float* temb_silu = nullptr;      // [B][time_dim]
   float* dts = nullptr;            // [B][time_dim] gradient w.r.t. silu(temb)
   float* wt_tmp = nullptr;         // transposed fp32 weights scratch
+  float* wg_part = nullptr;        // per-CTA partial weight gradients of the running conv_wgrad launch
+  size_t wg_part_bytes = 0;
   ftb_bucket_cb cb = nullptr;
   void* cb_user = nullptr;
   struct GradSlot { Act g; bool init = false; };
@@ -199,10 +201,10 @@ struct TrainFwd {
         FTB_TRY(c.zero(dw_target, wn * sizeof(float)));
       }
       if (cl.unfold_w) {
-        TRUN(conv_wgrad(X0, 0, X0.cg(), dY, 0, cl.cout, cl.k, cl.cin, dw_target, cin_tot, 0, cl.cin, 0, c.st));
+        TRUN(conv_wgrad(X0, 0, X0.cg(), dY, 0, cl.cout, cl.k, cl.cin, dw_target, cin_tot, 0, cl.cin, 0, c.st, c.wg_part, c.wg_part_bytes));
       } else {
-        TRUN(conv_wgrad(X0, 0, X0.cg(), dY, 0, cl.cout, cl.k, 0, dw_target, cin_tot, 0, c0_real, 0, c.st));
-        if (has1) TRUN(conv_wgrad(X1, 0, X1.cg(), dY, 0, cl.cout, cl.k, 0, dw_target, cin_tot, c0_real, c1_real, 0, c.st));
+        TRUN(conv_wgrad(X0, 0, X0.cg(), dY, 0, cl.cout, cl.k, 0, dw_target, cin_tot, 0, c0_real, 0, c.st, c.wg_part, c.wg_part_bytes));
+        if (has1) TRUN(conv_wgrad(X1, 0, X1.cg(), dY, 0, cl.cout, cl.k, 0, dw_target, cin_tot, c0_real, c1_real, 0, c.st, c.wg_part, c.wg_part_bytes));
       }
       if (!cl.in_scale.empty())
         TRUN(fold_gain_bwd(dw_target, c.pdev(cl.wname), cl.scale_tmp, cl.cout, cl.cin, cl.in_scale_mul, dw,
@@ -412,7 +414,7 @@ struct TrainFwd {
       const size_t ws = (size_t)c.B * hd * hd;
       FTB_TRY(c.zero(full, ws * sizeof(float)));
       // dctx[b][(h,d)][(h',e)] = sum_n q~[(h,d),n] do[(h',e),n]  (voxel-contraction GEMM, one slab per sample)
-      TRUN(conv_wgrad(dO, 0, hd / 8, Q, 0, hd, 1, 0, full, hd, 0, hd, (long long)hd * hd, c.st));
+      TRUN(conv_wgrad(dO, 0, hd / 8, Q, 0, hd, 1, 0, full, hd, 0, hd, (long long)hd * hd, c.st, c.wg_part, c.wg_part_bytes));
       TRUN(dctx_extract(full, ctx, c.B, heads, dh, dctx, ssum, c.st));
       ConvWeights w;
       w.ksize = 1; w.cin = hd; w.n = hd; w.ntiles = 1; w.batch_stride = (long long)hd * hd;

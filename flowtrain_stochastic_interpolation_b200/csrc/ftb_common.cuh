@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <string>
 
@@ -59,6 +60,16 @@ static inline size_t round_up_sz(size_t x, size_t m) { return (x + m - 1) / m * 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 int num_sms();
+// L2 promotion of every activation tensor map (FTB_TMA_PROMO = 0 none, 1 64 B, 2 128 B, 3 256 B; default 128 B)
+static inline CUtensorMapL2promotion tma_promo() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FTB_TMA_PROMO");
+    v = e ? atoi(e) : 2;
+  }
+  return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+       : v == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+}
 void count_launch(int n);
 // optional per-launch CUDA-event timing of the conv kernel (bench.py roofline leg)
 bool prof_enabled();
@@ -122,6 +133,16 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* t
       :
       : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)),
         "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar,
+                                            int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)),
+        "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar,

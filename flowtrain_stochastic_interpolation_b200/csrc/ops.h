@@ -161,9 +161,13 @@ int full_attention(const Act& qkv, int heads, int dh, const float* mem_kv, int n
 // dw (fp32 [cout][cin_tot][K][K][K]) += weight gradient of source x (channel groups [x_cgoff, x_cgoff+x_cg)),
 // which feeds the weight's input channels [ci_base, ci_base+ci_real).  unfold_cin > 0: x is the W-unfolded
 // stem input (channel kw*unfold_cin + ci).  dw_bstride != 0: one gradient slab per sample.
+// partials: scratch of conv_wgrad_partial_bytes() (stream-ordered reuse between launches is fine).
 int conv_wgrad(const Act& x, int x_cgoff, int x_cg, const Act& dy, int dy_cgoff, int cout_real, int ksize,
                int unfold_cin, float* dw, int cin_tot, int ci_base, int ci_real, long long dw_bstride,
-               cudaStream_t st);
+               cudaStream_t st, float* partials = nullptr, size_t partial_bytes = 0);
+// scratch for the per-CTA partial gradients of one conv_wgrad launch (one wave of CTAs x 128 rows x 512 columns fp32);
+// without it (or when a launch needs more) the kernel falls back to its atomic epilogue
+size_t conv_wgrad_partial_bytes();
 // out = act(n * gain[c] * s1[b][c] + sh[b][c]) + resid, n = u / max(||u||_C, 1e-12) when norm
 // drop_p > 0: dropout after the activation with a counter-based mask keyed by drop_key (regenerated in the backward)
 int normact_fwd(const Act& u, bool norm, const float* gain, const float* s1, const float* sh, int fstride, bool silu,

@@ -18,9 +18,13 @@
 //     accumulator rows nobody reads (an M=128 MMA costs the same as M=64).
 //   * accumulators stay in TMEM for the CTA's whole life (split-K over voxel tiles); a CTA owns one
 //     "class" = (kd, up to 512/N (kh-group, kw) accumulators, one Cin chunk, one 128-row block of
-//     Cout) and a slice of the (b, d, tile) items; at the end 4 warps add the rows into the fp32
-//     gradient with atomics.
-//   warp 0: TMA producer | warp 1: MMA issuer | warps 2-5: TMEM -> global (atomicAdd)
+//     Cout) and a slice of the (b, d, tile) items; at the end 4 warps store the rows as one fp32
+//     partial per CTA (64 contiguous bytes per thread and tcgen05.ld) and wgrad_reduce_kernel sums
+//     the partials of a class into the gradient, one owner thread per element.  (The first version
+//     added the rows with atomics: thread = output channel means the 32 lanes of every atomic hit
+//     32 different lines 5 KB apart, 8 M single-lane L2 atomics per launch on 62 K addresses, which
+//     cost 80-130 us per launch whatever the layer size; kept as the fallback without a scratch buffer.)
+//   warp 0: TMA producer | warp 1: MMA issuer | warps 2-5: TMEM -> global
 #include <stdlib.h>
 
 #include "ops.h"
@@ -50,12 +54,16 @@ struct WgradParams {
   int x_cgtot, x_cgoff, du_cgtot, du_cgoff;
   int nstage;
   uint32_t du_bytes, x_bytes;
-  uint32_t b_lbo, b_sbo, b_kh, b_kstep;   // X operand: K-direction / N-direction core-matrix strides, bytes per kh row, per k-step
+  uint32_t b_lbo, b_sbo, b_kh, b_kstep;   // X operand: K-direction / N-direction core-matrix strides, bytes per kh row, per k-step row
+  int interleave;
+  int TH, TW, kpr;      // voxel tile (TH x TW = 128), k-steps per tile row (1 when TW == 8: a k-step is two h rows)
   uint32_t off_x, off_bar, tmem_cols;
   float* dw;
   long long dw_bstride;
   int cout_real, cin_tot, ci_base, ci_real;
   int unfold_cin;       // > 0: X is W-unfolded (channel c' = kw * unfold_cin + ci), Kw == 1
+  float* partials;      // [grid][128][pcols] per-CTA accumulators (summed by wgrad_reduce_kernel), or null: atomics
+  int pcols;            // nacc * Nacc
   int Kww;              // W extent of the weight tensor
 };
 
@@ -81,9 +89,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
   const int bfix = r;   // per_batch: sample index
   const int g0 = cls * p.nacc;
   const int na = min(p.nacc, p.ngrp - g0);
+  // contiguous item ranges, or (interleave) CTA s takes items s, s + nsplit, ...: the CTAs of a wave then walk
+  // neighbouring tiles of the same rows at the same time (DRAM page / L2 sector locality)
   const long long per = (p.items + p.nsplit - 1) / p.nsplit;
-  const long long i_lo = (long long)split * per;
-  const long long i_hi = min(p.items, i_lo + per);
+  const long long i_lo = p.interleave ? split : (long long)split * per;
+  const long long i_hi = p.interleave ? p.items : min(p.items, i_lo + per);
+  const long long i_st = p.interleave ? p.nsplit : 1;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.nstage; ++i) {
@@ -108,7 +119,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       int n = 0;
-      for (long long it = i_lo; it < i_hi; ++it) {
+      for (long long it = i_lo; it < i_hi; it += i_st) {
         int t = (int)(it % tiles_pp);
         long long q = it / tiles_pp;
         const int xd = (int)(q % p.D);     // items walk the X planes; the dY plane of depth tap kd is xd - kd + pad
@@ -117,21 +128,21 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
         const bool use0 = d0 >= 0 && d0 < p.D;
         const bool use1 = p.kdp == 2 && kd + 1 < p.K && d1 >= 0 && d1 < p.D;
         if (!use0 && !use1) continue;      // only zero padding under these taps
-        const int h0 = (t / p.nWt) * 16, w0 = (t % p.nWt) * 8;
+        const int h0 = (t / p.nWt) * p.TH, w0 = (t % p.nWt) * p.TW;
         const int s = n % p.nstage;
         mbar_wait(&empty[s], ((n / p.nstage) & 1) ^ 1);
         mbar_expect_tx(&full[s], p.du_box_bytes * (p.kdp == 2 ? 2u : 1u) + p.x_bytes);
         // out-of-range dY planes are zero-filled by TMA (they multiply real X data)
-        tma_load_4d(smem + (size_t)s * p.du_bytes, &tm_du, &full[s], w0 * 8, h0, d0,
+        tma_load_5d(smem + (size_t)s * p.du_bytes, &tm_du, &full[s], 0, w0, h0, d0,
                     b * p.du_cgtot + p.du_cgoff + mb * 16);
         if (p.kdp == 2)
-          tma_load_4d(smem + (size_t)s * p.du_bytes + 16384, &tm_du, &full[s], w0 * 8, h0, kd + 1 < p.K ? d1 : -1,
+          tma_load_5d(smem + (size_t)s * p.du_bytes + 16384, &tm_du, &full[s], 0, w0, h0, kd + 1 < p.K ? d1 : -1,
                       b * p.du_cgtot + p.du_cgoff);
         if (p.stack > 1)
-          tma_load_4d(smem + p.off_x + (size_t)s * p.x_bytes, &tm_x, &full[s], (w0 - p.padw) * 8,
+          tma_load_5d(smem + p.off_x + (size_t)s * p.x_bytes, &tm_x, &full[s], 0, w0 - p.padw,
                       b * p.x_cgtot + p.x_cgoff + chunk * p.ncg, h0 - p.pad, xd);
         else
-          tma_load_4d(smem + p.off_x + (size_t)s * p.x_bytes, &tm_x, &full[s], (w0 - p.padw) * 8, h0 - p.pad, xd,
+          tma_load_5d(smem + p.off_x + (size_t)s * p.x_bytes, &tm_x, &full[s], 0, w0 - p.padw, h0 - p.pad, xd,
                       b * p.x_cgtot + p.x_cgoff + chunk * p.ncg);
         ++n;
       }
@@ -146,9 +157,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
       // B (X halo tile): LBO = halo-row pitch (next 8 voxels along K), SBO = channel-group pitch
       const uint32_t b_hi = (p.b_sbo >> 4) | (1u << 14);
       const uint32_t b_lbo = (p.b_lbo >> 4) << 16;
-      const uint32_t b_kstep = p.b_kstep >> 4;   // two h rows per k-step of 16 voxels
+      const uint32_t b_kstep = p.b_kstep >> 4;   // per tile row of k-steps (TW == 8: two h rows per k-step of 16 voxels)
+      const int kpr = p.kpr;
       int n = 0;
-      for (long long it = i_lo; it < i_hi; ++it) {
+      for (long long it = i_lo; it < i_hi; it += i_st) {
         const int xd = (int)((it / tiles_pp) % p.D);
         const int d0 = xd - kd + p.pad, d1 = d0 - 1;
         if (!(d0 >= 0 && d0 < p.D) && !(p.kdp == 2 && kd + 1 < p.K && d1 >= 0 && d1 < p.D)) continue;
@@ -164,7 +176,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
           const uint32_t dcol = tmem_base + (uint32_t)(a * p.Nacc);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
-            umma_bf16_lohi(dcol, a0 + ks * 16, a_hi, b0 + ks * b_kstep, b_hi, idesc, (n | ks) != 0);
+            umma_bf16_lohi(dcol, a0 + ks * 16, a_hi, b0 + (ks / kpr) * b_kstep + (ks % kpr) * 16, b_hi, idesc, (n | ks) != 0);
         }
         umma_commit(&empty[s]);
         ++n;
@@ -180,10 +192,36 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
     const int kd_row = p.kdp == 2 ? kd + (row >> 6) : kd;
     // any item with an in-range depth tap?  (same predicate as the producer / issuer loops)
     bool any = false;
-    for (long long it = i_lo; it < i_hi && !any; ++it) {
+    for (long long it = i_lo; it < i_hi && !any; it += i_st) {
       const int d0 = (int)((it / tiles_pp) % p.D) - kd + p.pad, d1 = d0 - 1;
       any = (d0 >= 0 && d0 < p.D) || (p.kdp == 2 && kd + 1 < p.K && d1 >= 0 && d1 < p.D);
     }
+    if (p.partials) {
+      // ---- per-CTA partial: [row][pcols] fp32, plain 16-byte stores (zeros when this CTA had no item)
+      float* out = p.partials + ((size_t)blockIdx.x * 128 + row) * p.pcols;
+      const bool row_ok = co < p.cout_real && kd_row < p.K;
+      if (any) {
+        mbar_wait(done, 0);
+        tc_fence_after();
+      }
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+      for (int a = 0; a < na; ++a)
+        for (int c0 = 0; c0 < p.Nacc; c0 += 16) {
+          uint32_t v[16];
+          if (any) {
+            tmem_ld16(trow + a * p.Nacc + c0, v);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0u;
+          }
+          if (row_ok) {
+            uint4* o4 = reinterpret_cast<uint4*>(out + a * p.Nacc + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o4[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        }
+    } else
     if (any) {
       mbar_wait(done, 0);
       tc_fence_after();
@@ -226,6 +264,59 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
+// dw[idx(class, row, col)] += sum over the nsplit partials of the class; one thread per (class, row, col), consecutive
+// threads = consecutive columns (coalesced reads of every partial); the index mapping is the epilogue's.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const WgradParams p, int fixed) {
+  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long per_cls = (long long)128 * p.pcols;
+  if (e >= (long long)fixed * per_cls) return;
+  const int cidx = (int)(e / per_cls);
+  const int rem = (int)(e % per_cls);
+  const int row = rem / p.pcols, col = rem % p.pcols;
+  int r = cidx;
+  const int cls = r % p.ncls; r /= p.ncls;
+  const int kd = (r % p.nkg) * p.kdp; r /= p.nkg;
+  const int chunk = r % p.nchunk; r /= p.nchunk;
+  const int mb = r % p.nmb; r /= p.nmb;
+  const int bfix = r;
+  const int g0 = cls * p.nacc;
+  const int na = min(p.nacc, p.ngrp - g0);
+  const int a = col / p.Nacc, n = col % p.Nacc;
+  if (a >= na) return;
+  const int co = p.kdp == 2 ? (row & 63) : mb * 128 + row;
+  const int kd_row = p.kdp == 2 ? kd + (row >> 6) : kd;
+  if (co >= p.cout_real || kd_row >= p.K) return;
+  const int g = g0 + a;
+  const int kh0 = (g / p.Kw) * p.stack, kw = g % p.Kw;
+  const int nci = p.ncg * 8;
+  const int kh = kh0 + n / nci;
+  int ci = chunk * nci + n % nci, kww = kw;
+  bool ok;
+  if (p.unfold_cin > 0) {
+    kww = ci / p.unfold_cin;
+    ci = ci % p.unfold_cin;
+    ok = kww < p.Kww;
+  } else {
+    ok = ci < p.ci_real;
+  }
+  if (!ok) return;
+  const float* src = p.partials + ((size_t)cidx * p.nsplit * 128 + row) * p.pcols + col;
+  const size_t sstride = (size_t)128 * p.pcols;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int sp = 0;
+  for (; sp + 4 <= p.nsplit; sp += 4) {
+    s0 += __ldcs(src + (size_t)sp * sstride);
+    s1 += __ldcs(src + (size_t)(sp + 1) * sstride);
+    s2 += __ldcs(src + (size_t)(sp + 2) * sstride);
+    s3 += __ldcs(src + (size_t)(sp + 3) * sstride);
+  }
+  for (; sp < p.nsplit; ++sp) s0 += __ldcs(src + (size_t)sp * sstride);
+  float* dwb = p.dw + (p.per_batch ? (long long)bfix * p.dw_bstride : 0);
+  const size_t idx = ((((size_t)co * p.cin_tot + p.ci_base + ci) * p.K + kd_row) * p.K + kh) * p.Kww + kww;
+  dwb[idx] += (s0 + s1) + (s2 + s3);
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -242,52 +333,53 @@ PFN_encodeTiled wg_encode() {
   return fn;
 }
 
-// dims (W*8, H, D, B*CG), box (64, 16, 1, cg): lands as [cg][16][8][8]
-int tmap_du(CUtensorMap* tm, const Act& a, int cg) {
+// dims (8, W, H, D, B*CG), box (8, TW, TH, 1, cg): lands as [cg][TH][TW][8] = [cg][16 blocks of 8 voxels][8]
+int tmap_du(CUtensorMap* tm, const Act& a, int cg, int TH, int TW) {
   PFN_encodeTiled enc = wg_encode();
   FTB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t gdim[4] = {(cuuint64_t)a.W * 8, (cuuint64_t)a.H, (cuuint64_t)a.D, (cuuint64_t)a.B * a.cg()};
-  cuuint64_t gstr[3] = {(cuuint64_t)a.W * 16, (cuuint64_t)a.W * a.H * 16, (cuuint64_t)a.W * a.H * a.D * 16};
-  cuuint32_t box[4] = {64u, 16u, 1u, (cuuint32_t)cg};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.p, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  cuuint64_t gdim[5] = {8, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.D, (cuuint64_t)a.B * a.cg()};
+  cuuint64_t gstr[4] = {16, (cuuint64_t)a.W * 16, (cuuint64_t)a.W * a.H * 16, (cuuint64_t)a.W * a.H * a.D * 16};
+  cuuint32_t box[5] = {8u, (cuuint32_t)TW, (cuuint32_t)TH, 1u, (cuuint32_t)cg};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, a.p, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, tma_promo(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FTB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (wgrad dY) failed (" + std::to_string((int)r) + ")");
   return 0;
 }
-// stacked: dims (W*8, B*CG, H, D), box (BW*8, ncg, BH, 1): lands as [BH][ncg][BW][8]
-// natural: dims (W*8, H, D, B*CG), box (BW*8, BH, 1, ncg): lands as [ncg][BH][BW][8]
+// stacked: dims (8, W, B*CG, H, D), box (8, BW, ncg, BH, 1): lands as [BH][ncg][BW][8]
+// natural: dims (8, W, H, D, B*CG), box (8, BW, BH, 1, ncg): lands as [ncg][BH][BW][8]
 int tmap_x(CUtensorMap* tm, const Act& a, int BW, int BH, int ncg, bool stacked) {
   PFN_encodeTiled enc = wg_encode();
   FTB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   if (!stacked) {
-    cuuint64_t gdim[4] = {(cuuint64_t)a.W * 8, (cuuint64_t)a.H, (cuuint64_t)a.D, (cuuint64_t)a.B * a.cg()};
-    cuuint64_t gstr[3] = {(cuuint64_t)a.W * 16, (cuuint64_t)a.W * a.H * 16, (cuuint64_t)a.W * a.H * a.D * 16};
-    cuuint32_t box[4] = {(cuuint32_t)BW * 8, (cuuint32_t)BH, 1u, (cuuint32_t)ncg};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.p, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    cuuint64_t gdim[5] = {8, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.D, (cuuint64_t)a.B * a.cg()};
+    cuuint64_t gstr[4] = {16, (cuuint64_t)a.W * 16, (cuuint64_t)a.W * a.H * 16, (cuuint64_t)a.W * a.H * a.D * 16};
+    cuuint32_t box[5] = {8u, (cuuint32_t)BW, (cuuint32_t)BH, 1u, (cuuint32_t)ncg};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, a.p, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, tma_promo(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     FTB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (wgrad X, natural) failed (" + std::to_string((int)r) + ")");
     return 0;
   }
-  cuuint64_t gdim[4] = {(cuuint64_t)a.W * 8, (cuuint64_t)a.B * a.cg(), (cuuint64_t)a.H, (cuuint64_t)a.D};
-  cuuint64_t gstr[3] = {(cuuint64_t)a.W * a.H * a.D * 16, (cuuint64_t)a.W * 16, (cuuint64_t)a.W * a.H * 16};
-  cuuint32_t box[4] = {(cuuint32_t)BW * 8, (cuuint32_t)ncg, (cuuint32_t)BH, 1u};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.p, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  cuuint64_t gdim[5] = {8, (cuuint64_t)a.W, (cuuint64_t)a.B * a.cg(), (cuuint64_t)a.H, (cuuint64_t)a.D};
+  cuuint64_t gstr[4] = {16, (cuuint64_t)a.W * a.H * a.D * 16, (cuuint64_t)a.W * 16, (cuuint64_t)a.W * a.H * 16};
+  cuuint32_t box[5] = {8u, (cuuint32_t)BW, (cuuint32_t)ncg, (cuuint32_t)BH, 1u};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, a.p, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, tma_promo(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FTB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (wgrad X) failed (" + std::to_string((int)r) + ")");
   return 0;
 }
 
 }  // namespace
 
+size_t conv_wgrad_partial_bytes() { return (size_t)(num_sms() + 12) * 128 * 512 * sizeof(float); }
+
 // dw (fp32, [cout][cin_tot][K][K][Kww], pre-zeroed or holding a running sum) += the gradient
 // contribution of source `x` (channel groups [x_cgoff, x_cgoff + x_cg)), which occupies the weight's
 // input channels [ci_base, ci_base + ci_real).  per_batch: dw has one slab per sample (dw_bstride).
 int conv_wgrad(const Act& x, int x_cgoff, int x_cg, const Act& dy, int dy_cgoff, int cout_real, int ksize,
                int unfold_cin, float* dw, int cin_tot, int ci_base, int ci_real, long long dw_bstride,
-               cudaStream_t st) {
+               cudaStream_t st, float* partials, size_t partial_bytes) {
   FTB_CHECK(x.B == dy.B && x.D == dy.D && x.H == dy.H && x.W == dy.W, "wgrad: dims");
   FTB_CHECK(ksize == 1 || ksize == 3 || ksize == 5 || ksize == 7, "wgrad: ksize");
   FTB_CHECK(x_cg > 0 && x_cg % 2 == 0, "wgrad: channel groups must be a positive multiple of 2");
@@ -316,16 +408,26 @@ int conv_wgrad(const Act& x, int x_cgoff, int x_cg, const Act& dy, int dy_cgoff,
   const int cout_cg = cdiv(cout_real, 8);
   p.nmb = cdiv(cout_cg, 16);
   const int du_box_cg = cout_cg < 16 ? cout_cg : 16;
-  p.nHt = cdiv(x.H, 16); p.nWt = cdiv(x.W, 8);
+  // voxel tile TH x TW = 128: wider tiles read longer contiguous runs of a W row (FTB_WGRAD_TW = 8 | 16 | 32)
+  static const int tw_env = getenv("FTB_WGRAD_TW") ? atoi(getenv("FTB_WGRAD_TW")) : 8;
+  p.TW = tw_env;
+  while (p.TW > 8 && p.TW / 2 >= x.W) p.TW /= 2;
+  FTB_CHECK(p.TW == 8 || p.TW == 16 || p.TW == 32, "wgrad: tile width");
+  p.TH = 128 / p.TW;
+  p.kpr = p.TW == 8 ? 1 : p.TW / 16;
+  p.nHt = cdiv(x.H, p.TH); p.nWt = cdiv(x.W, p.TW);
   p.per_batch = dw_bstride != 0 ? 1 : 0;
   p.items = (long long)p.D * p.nHt * p.nWt * (p.per_batch ? 1 : p.B);
-  const int BH = 16 + p.K - 1, BW = 8 + p.Kw - 1;
+  const int BH = p.TH + p.K - 1, BW = p.TW + p.Kw - 1;
   const uint32_t P = BW * 16;
   if (p.stack > 1) {   // [BH][ncg][BW][8]
-    p.b_sbo = P; p.b_lbo = p.ncg * P; p.b_kh = p.ncg * P; p.b_kstep = 2 * p.ncg * P;
+    p.b_sbo = P; p.b_kh = p.ncg * P;
   } else {             // [ncg][BH][BW][8]
-    p.b_sbo = BH * P; p.b_lbo = P; p.b_kh = P; p.b_kstep = 2 * P;
+    p.b_sbo = BH * P; p.b_kh = P;
   }
+  // a k-step is 16 voxels = two 8-voxel blocks: h-adjacent rows when TW == 8, w-adjacent blocks otherwise
+  p.b_lbo = p.TW == 8 ? p.b_kh : 128;
+  p.b_kstep = p.TW == 8 ? 2 * p.b_kh : p.b_kh;
   // Cout <= 64: two depth taps per CTA share the 128 accumulator rows (rows 0-63: kd0, rows 64-127: kd0+1)
   p.kdp = (p.K > 1 && p.nmb == 1 && cout_cg <= 8 && getenv("FTB_WGRAD_NOPAIR") == nullptr) ? 2 : 1;
   p.nkg = cdiv(p.K, p.kdp);
@@ -354,9 +456,11 @@ int conv_wgrad(const Act& x, int x_cgoff, int x_cg, const Act& dy, int dy_cgoff,
   if (nsplit > max_split) nsplit = (int)max_split;
   if (nsplit < 1) nsplit = 1;
   p.nsplit = nsplit;
+  static const int il_env = getenv("FTB_WGRAD_INTERLEAVE") ? atoi(getenv("FTB_WGRAD_INTERLEAVE")) : 0;
+  p.interleave = il_env;
 
   CUtensorMap tmd, tmx;
-  FTB_TRY(tmap_du(&tmd, dy, du_box_cg));
+  FTB_TRY(tmap_du(&tmd, dy, du_box_cg, p.TH, p.TW));
   FTB_TRY(tmap_x(&tmx, x, BW, BH, p.ncg, p.stack > 1));
   static bool attr_set = false;
   if (!attr_set) {
@@ -364,17 +468,27 @@ int conv_wgrad(const Act& x, int x_cgoff, int x_cg, const Act& dy, int dy_cgoff,
     attr_set = true;
   }
   if (getenv("FTB_CONV_PLAN"))
-    fprintf(stderr, "wgrad plan: K%d cin %d cout %d @%dx%dx%d B%d -> kdp %d stack %d ncg %d N %d nacc %d cls %d chunks %d mb %d split %d stages %d smem %u\n",
-            p.K, x_cg * 8, cout_real, p.D, p.H, p.W, p.B, p.kdp, p.stack, p.ncg, p.Nacc, p.nacc, p.ncls, p.nchunk, p.nmb,
+    fprintf(stderr, "wgrad plan: K%d cin %d cout %d @%dx%dx%d B%d -> tile %dx%d kdp %d stack %d ncg %d N %d nacc %d cls %d chunks %d mb %d split %d stages %d smem %u\n",
+            p.K, x_cg * 8, cout_real, p.D, p.H, p.W, p.B, p.TH, p.TW, p.kdp, p.stack, p.ncg, p.Nacc, p.nacc, p.ncls, p.nchunk, p.nmb,
             p.nsplit, p.nstage, smem_bytes);
   int prof = -1;
   if (prof_enabled()) {
     const double flops = 2.0 * x.B * (double)x.voxels() * ci_real * cout_real * ksize * ksize * ksize;
     prof = prof_begin(st, flops, (double)x.B * x.voxels() * (ci_real + cout_real) * 2.0, 2);
   }
+  // per-CTA partials + a reduce pass when the caller's scratch holds them; else the atomic epilogue
+  p.pcols = p.nacc * p.Nacc;
+  const size_t need = (size_t)fixed * nsplit * 128 * p.pcols * sizeof(float);
+  static const bool no_partials = getenv("FTB_WGRAD_ATOMIC") != nullptr;
+  p.partials = (partials != nullptr && need <= partial_bytes && !no_partials) ? partials : nullptr;
   wgrad_kernel<<<fixed * nsplit, kWgThreads, smem_bytes, st>>>(tmd, tmx, p);
-  prof_end(prof, st);
   FTB_LAUNCH_OK();
+  if (p.partials) {
+    const long long total = (long long)fixed * 128 * p.pcols;
+    wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(p, fixed);
+    FTB_LAUNCH_OK();
+  }
+  prof_end(prof, st);
   return 0;
 }
 
