@@ -157,12 +157,33 @@ def measured_peaks():
 
 
 def ncu_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
-    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(p):
-        with open(p) as f:
-            return json.load(f)
-    return None
+    """DRAM bytes per launch of the dominant kernel, read from the newest committed `ncu --set full` summary
+    (profiles/rNN_conv_igemm_ncu_full.csv, written by tools/ncu_summary.py from the capture of the same round):
+    dram__bytes_read.sum + dram__bytes_write.sum of every captured conv launch, and their mean."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r[0-9][0-9]_conv_igemm_ncu_full.csv")))
+    if not files:
+        return None
+    with open(files[-1]) as f:
+        rows = list(csv.reader(f))
+    hdr = rows[0]
+
+    def col(prefix):
+        for i, h in enumerate(hdr):
+            if h.startswith(prefix):
+                scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[h.split("[")[1].rstrip("]")]
+                return i, scale
+        return None, 1.0
+
+    (ri, rs), (wi, ws) = col("dram__bytes_read.sum"), col("dram__bytes_write.sum")
+    if ri is None or wi is None:
+        return None
+    per = [float(r[ri]) * rs + float(r[wi]) * ws for r in rows[1:] if len(r) > max(ri, wi)]
+    if not per:
+        return None
+    return {"dram_bytes_per_launch": sum(per) / len(per), "launches": [int(x) for x in per],
+            "source": os.path.relpath(files[-1], ROOT)}
 
 
 # ---------------------------------------------------------------------------- CPU baseline (oracle port)
@@ -612,6 +633,7 @@ def run_b200(a):
     roof = {
         "bound": "tensor", "kernel": "conv_igemm_kernel (k>=3 convs)", "achieved": conv_tf, "peak": peaks["bf16"],
         "unit": "TFLOP/s", "frac": conv_tf / peaks["bf16"], "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+        "traffic_source": traffic if traffic else None,
         "peak_source": peaks["src"], "launches_per_step": int(ln[0]), "avg_launch_ms": ms[0] / max(ln[0], 1),
         "algorithmic_gflop_per_launch": fl[0] / max(ln[0], 1) / 1e9,
         "share_of_step": ms[0] / one_step_ms if one_step_ms > 0 else None,

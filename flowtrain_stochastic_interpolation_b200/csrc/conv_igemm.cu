@@ -94,6 +94,7 @@ struct IgemmParams {
   unsigned long long drop_key;
   int f32_accum;               // fp32 mode: out_f32 += instead of = (the hi/lo operand products of one conv)
   long long w_tile_stride;     // elements between the packed weights of consecutive N tiles (blockIdx.y = tile)
+  int no_fast27;               // FTB_CONV_NO_FAST27: always walk the table tap by tap
 };
 
 struct ItemCoord {
@@ -118,7 +119,7 @@ __device__ __forceinline__ ItemCoord decode_item(const IgemmParams& p, int item)
 
 // ------------------------------------------------------------------------------ epilogue helpers
 struct EpiCtx {
-  const float *bias, *mul, *add;   // shared memory, this half's copy for the current sample
+  uint32_t bias, mul, add;         // shared-memory byte addresses of this half's copy for the current sample (LDS, not generic loads)
   bf16* out_b;                     // output base of sample b
   bf16* u_b;                       // pre-norm output base of sample b (or null)
   int b;                           // sample index (dropout mask key)
@@ -132,6 +133,14 @@ struct EpiCtx {
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// 16-byte load from a shared-memory byte address.  (Through a generic pointer the same load compiles to LD.E.128, which
+// costs two shared-memory wavefronts instead of one: ncu r02 counted 93 % of the kernel's LSU shared wavefronts on the
+// 36 per-row parameter loads of the epilogue, competing with the tensor core's operand fetches for the same banks.)
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ float silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
@@ -221,8 +230,8 @@ __device__ __forceinline__ void epi_affine_chunk(const IgemmParams& p, EpiCtx& e
     float v[16];
 #pragma unroll
     for (int j4 = 0; j4 < 16; j4 += 4) {
-      const float4 mu = *reinterpret_cast<const float4*>(ec.mul + c0 + i * 16 + j4);
-      const float4 ad = *reinterpret_cast<const float4*>(ec.add + c0 + i * 16 + j4);
+      const float4 mu = lds_f4(ec.mul + 4u * (uint32_t)(c0 + i * 16 + j4));
+      const float4 ad = lds_f4(ec.add + 4u * (uint32_t)(c0 + i * 16 + j4));
       v[j4 + 0] = fmaf(__uint_as_float(r[i][j4 + 0]) * rs, mu.x, ad.x);
       v[j4 + 1] = fmaf(__uint_as_float(r[i][j4 + 1]) * rs, mu.y, ad.y);
       v[j4 + 2] = fmaf(__uint_as_float(r[i][j4 + 2]) * rs, mu.z, ad.z);
@@ -301,7 +310,7 @@ __device__ __forceinline__ void epi_norm_regs(const IgemmParams& p, EpiCtx& ec, 
   for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
     for (int j4 = 0; j4 < 16; j4 += 4) {
-      const float4 bi = *reinterpret_cast<const float4*>(ec.bias + ch * 16 + j4);
+      const float4 bi = lds_f4(ec.bias + 4u * (uint32_t)(ch * 16 + j4));
       const float a0 = fmaf(__uint_as_float(r[ch][j4 + 0]), rs, bi.x);
       const float a1 = fmaf(__uint_as_float(r[ch][j4 + 1]), rs, bi.y);
       const float a2 = fmaf(__uint_as_float(r[ch][j4 + 2]), rs, bi.z);
@@ -328,8 +337,8 @@ __device__ __forceinline__ void epi_norm_regs(const IgemmParams& p, EpiCtx& ec, 
     float v[16];
 #pragma unroll
     for (int j4 = 0; j4 < 16; j4 += 4) {
-      const float4 mu = *reinterpret_cast<const float4*>(ec.mul + ch * 16 + j4);
-      const float4 ad = *reinterpret_cast<const float4*>(ec.add + ch * 16 + j4);
+      const float4 mu = lds_f4(ec.mul + 4u * (uint32_t)(ch * 16 + j4));
+      const float4 ad = lds_f4(ec.add + 4u * (uint32_t)(ch * 16 + j4));
       v[j4 + 0] = fmaf(__uint_as_float(r[ch][j4 + 0]) * rinv, mu.x, ad.x);
       v[j4 + 1] = fmaf(__uint_as_float(r[ch][j4 + 1]) * rinv, mu.y, ad.y);
       v[j4 + 2] = fmaf(__uint_as_float(r[ch][j4 + 2]) * rinv, mu.z, ad.z);
@@ -352,7 +361,7 @@ __device__ __forceinline__ void epi_norm_ss_chunk(const EpiCtx& ec, uint32_t tro
   for (int i = 0; i < NLD; ++i)
 #pragma unroll
     for (int j4 = 0; j4 < 16; j4 += 4) {
-      const float4 bi = *reinterpret_cast<const float4*>(ec.bias + c0 + i * 16 + j4);
+      const float4 bi = lds_f4(ec.bias + 4u * (uint32_t)(c0 + i * 16 + j4));
       const float a0 = fmaf(__uint_as_float(r[i][j4 + 0]), rs, bi.x);
       const float a1 = fmaf(__uint_as_float(r[i][j4 + 1]), rs, bi.y);
       const float a2 = fmaf(__uint_as_float(r[i][j4 + 2]), rs, bi.z);
@@ -375,9 +384,9 @@ __device__ __forceinline__ void epi_norm_out_chunk(const IgemmParams& p, EpiCtx&
     float v[16];
 #pragma unroll
     for (int j4 = 0; j4 < 16; j4 += 4) {
-      const float4 bi = *reinterpret_cast<const float4*>(ec.bias + cc + j4);
-      const float4 mu = *reinterpret_cast<const float4*>(ec.mul + cc + j4);
-      const float4 ad = *reinterpret_cast<const float4*>(ec.add + cc + j4);
+      const float4 bi = lds_f4(ec.bias + 4u * (uint32_t)(cc + j4));
+      const float4 mu = lds_f4(ec.mul + 4u * (uint32_t)(cc + j4));
+      const float4 ad = lds_f4(ec.add + 4u * (uint32_t)(cc + j4));
       const float a0 = fmaf(__uint_as_float(r[i][j4 + 0]), rs, bi.x), a1 = fmaf(__uint_as_float(r[i][j4 + 1]), rs, bi.y);
       const float a2 = fmaf(__uint_as_float(r[i][j4 + 2]), rs, bi.z), a3 = fmaf(__uint_as_float(r[i][j4 + 3]), rs, bi.w);
       r[i][j4 + 0] = __float_as_uint(a0); r[i][j4 + 1] = __float_as_uint(a1);
@@ -497,6 +506,47 @@ __device__ __forceinline__ void issue_entries(const IssueCtx& ic, uint32_t ea, u
   }
 }
 
+// The table entries of one (group, channel-chunk) pass decoded ONCE into registers, then k-steps [KS0, NKS) of every
+// entry for one filter tap: two adds per MMA.  The issuer is a single thread and its instruction stream, not the
+// tensor pipe, bounded the kernel (FTB_CONV_DBG + the ncu source page, r02: ~300 instructions at ~6 cycles each per
+// tap for 12 MMAs per issuer = 1 900 cycles per tap against 1 200 cycles of tensor time for both issuers together;
+// the table walk re-read and re-decoded every entry for every tap).
+constexpr int kCache = 8;
+template <int NKS, int KS0>
+__device__ __forceinline__ void issue_cached(const IssueCtx& ic, const uint32_t (&ca)[kCache], const uint32_t (&cb)[kCache],
+                                             const uint32_t (&cd)[kCache], const uint32_t (&ci)[kCache], int ne,
+                                             uint32_t aoff, uint32_t wb) {
+#pragma unroll
+  for (int e = 0; e < kCache; ++e) {
+    if (e < ne) {
+#pragma unroll
+      for (int ks = KS0; ks < NKS; ++ks)
+        umma_bf16_lohi(cd[e], ca[e] + aoff + (uint32_t)ks * ic.kinc, ic.a_hi, cb[e] + wb + (uint32_t)ks * ic.kstep, ic.b_hi,
+                       ci[e], 1u);
+    }
+  }
+}
+
+// Resident 3^3 weights, one channel chunk of three k-steps (the 48 -> 48 layers that hold most of the FLOPs): all
+// 27 (tap, k-step) MMAs of ONE table entry in a straight line.  The issuer is a single thread, and ncu (r02, source
+// page) showed the kernel bound by ITS instruction stream, not by the tensor pipe: with the per-tap walk an entry is
+// re-read and re-decoded for every tap (41 instructions per 3 MMAs plus ~100 per tap around the loop, 287 cycles per
+// 3 MMAs against 216 of tensor time).  Here an entry is decoded once per 27 MMAs: two adds per instruction remain.
+// skip_first: (tap 0, k-step 0) was already issued through the overwrite table.
+__device__ __forceinline__ void issue_entry_27(const IssueCtx& ic, uint32_t a0, uint32_t b0, uint32_t d, uint32_t idesc,
+                                               uint32_t rowp_enc, uint32_t wchunk_enc) {
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+      for (int ks = 0; ks < 3; ++ks) {
+        if ((kh | kw | ks) == 0) continue;
+        umma_bf16_lohi(d, a0 + (uint32_t)kh * rowp_enc + (uint32_t)kw + (uint32_t)ks * ic.kinc, ic.a_hi,
+                       b0 + (uint32_t)(kh * 3 + kw) * wchunk_enc + (uint32_t)ks * ic.kstep, ic.b_hi, idesc, 1u);
+      }
+}
+
 template <bool kTrain>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
@@ -551,11 +601,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
-    // ===================================================================== TMA producer
+    // ===================================================================== TMA producer: activation planes
+    // (The weight chunks have their own producer thread below.  With both in one thread's program order the plane
+    // loads of the next group queued behind 27 weight-chunk loads that each wait for a free ring slot, so the planes
+    // could not be prefetched: FTB_CONV_DBG showed the issuers waiting 10 % of their cycles for planes and 13 % for
+    // weights on 48 -> 48 @64^3.)
     if (lane == 0) {
       uint32_t pslot = 0, pphase = 0;   // plane ring cursor
-      uint32_t wslot = 0, wphase = 0;   // weight ring cursor
-      bool w_loaded = false;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const ItemCoord c = decode_item(p, item);
         const int npl = c.lz + 2 * p.pad;
@@ -573,7 +625,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
             if (p.ncc == 1) { q_lo = issued; q_hi = min(npl, g * p.NZ + win); issued = q_hi; }
             else { q_lo = g * p.NZ; q_hi = q_lo + win; }
             for (int q = q_lo; q < q_hi; ++q) {
-              mbar_wait(&plane_empty[pslot], pphase ^ 1);
+              mbar_wait_backoff(&plane_empty[pslot], pphase ^ 1);
               mbar_expect_tx(&plane_full[pslot], bytes);
               uint8_t* dst = s_planes + (size_t)pslot * p.slot_stride;
               const int dz = c.d0 - p.pad + q;
@@ -581,23 +633,35 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
               else tma_load_4d(dst, tm, &plane_full[pslot], (c.w0 - p.padw) * 8, c.h0 - p.pad, dz, cgc);
               if (++pslot == (uint32_t)p.nslot) { pslot = 0; pphase ^= 1; }
             }
-            if (!p.w_resident || !w_loaded) {
-              const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack + (long long)blockIdx.y * p.w_tile_stride +
-                                                                   (long long)c.b * p.w_batch_stride) +
-                                    (size_t)p.cc_ks0[cc] * p.kstep_bytes;
-              const uint32_t wbytes = (uint32_t)p.cc_ks[cc] * p.kstep_bytes;
-              for (int t = 0; t < p.taps; ++t) {
-                uint32_t slot;
-                if (p.w_resident) {
-                  slot = (uint32_t)(cc * p.taps + t);
-                } else {
-                  slot = wslot;
-                  mbar_wait(&w_empty[slot], wphase ^ 1);
-                  if (++wslot == (uint32_t)p.wslot) { wslot = 0; wphase ^= 1; }
-                }
-                mbar_expect_tx(&w_full[slot], wbytes);
-                bulk_load(s_w + (size_t)slot * p.wchunk_bytes, wsrc + (size_t)t * p.wtap_bytes, wbytes, &w_full[slot]);
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================================================================== bulk-copy producer: weight chunks
+    if (lane == 0) {
+      uint32_t wslot = 0, wphase = 0;   // weight ring cursor
+      bool w_loaded = false;
+      for (int item = blockIdx.x; item < p.n_items && !(p.w_resident && w_loaded); item += gridDim.x) {
+        const ItemCoord c = decode_item(p, item);
+        const int ngroups = (c.lz + p.NZ - 1) / p.NZ;
+        for (int g = 0; g < ngroups && !(p.w_resident && w_loaded); ++g) {
+          for (int cc = 0; cc < p.ncc; ++cc) {
+            const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack + (long long)blockIdx.y * p.w_tile_stride +
+                                                                 (long long)c.b * p.w_batch_stride) +
+                                  (size_t)p.cc_ks0[cc] * p.kstep_bytes;
+            const uint32_t wbytes = (uint32_t)p.cc_ks[cc] * p.kstep_bytes;
+            for (int t = 0; t < p.taps; ++t) {
+              uint32_t slot;
+              if (p.w_resident) {
+                slot = (uint32_t)(cc * p.taps + t);
+              } else {
+                slot = wslot;
+                mbar_wait_backoff(&w_empty[slot], wphase ^ 1);
+                if (++wslot == (uint32_t)p.wslot) { wslot = 0; wphase ^= 1; }
               }
+              mbar_expect_tx(&w_full[slot], wbytes);
+              bulk_load(s_w + (size_t)slot * p.wchunk_bytes, wsrc + (size_t)t * p.wtap_bytes, wbytes, &w_full[slot]);
             }
           }
           w_loaded = true;
@@ -635,6 +699,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     const uint32_t nb_enc = (uint32_t)(p.N * 2);                           // one depth tap of B rows, >>4
     const uint32_t tab_addr = smem_u32(tab);
     const bool stream_w = !p.w_resident;
+    const bool fast27 = !stream_w && p.ncc == 1 && p.K == 3 && p.Kw == 3 && p.cc_ks[0] == 3 && !p.no_fast27;
     // ring cursors, advanced incrementally (no divisions on the issue path)
     uint32_t slot_w0 = 0;                  // ring slot of the current window's plane 0
     uint32_t rslot = 0, rphase = 0;        // next plane_full barrier to wait for
@@ -715,6 +780,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
           mbar_wait(&acc_empty[ab], ((gctr >> 1) & 1) ^ 1);
           if (p.dbg) dbg_acc += clock64() - tq0;
           ic.acc0 = tmem_base + ab * p.NZ * p.N;
+          if (fast27) {
+            const int upto = min(npl, g * p.NZ + win);
+            for (int i = waited; i < upto; ++i) {
+              mbar_wait(&plane_full[rslot], rphase);
+              if (++rslot == ic.nslot) { rslot = 0; rphase ^= 1; }
+            }
+            waited = upto;
+            if (!w_waited)
+              for (int t = 0; t < 9; ++t) mbar_wait(&w_full[t], 0);
+            tc_fence_after();
+            ic.slot_w0 = slot_w0;
+            // first touch of every accumulator: (tap 0, k-step 0) through the overwrite table
+            issue_entries<1>(ic, tab_addr, tab_addr + (uint32_t)n_first * 16u, 0u, w_enc, true);
+            const uint32_t ea_end = tab_addr + (uint32_t)(n_first + n_main) * 16u;
+            for (uint32_t ea = tab_addr + (uint32_t)n_first * 16u; ea < ea_end; ea += 16) {
+              uint32_t ex, ey, ez, ew;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ex), "=r"(ey), "=r"(ez), "=r"(ew) : "r"(ea));
+              uint32_t slot = slot_w0 + ex;
+              if (slot >= ic.nslot) slot -= ic.nslot;
+              issue_entry_27(ic, ic.planes_enc + slot * ic.slot_enc, (ey & 0x7FFFFFFFu) + w_enc, ic.acc0 + ez, ew, rowp_enc,
+                             wchunk_enc);
+            }
+          } else
           for (int cc = 0; cc < p.ncc; ++cc) {
             if (p.dbg) tq0 = clock64();
             int n_new;
@@ -728,6 +816,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
             tc_fence_after();
             ic.slot_w0 = slot_w0;
             const int nks = p.cc_ks[cc];
+            // main-table entries of this pass in registers (window plane -> ring slot resolved here, once)
+            const bool cached = n_main <= kCache && nks <= 4 && !p.no_fast27;
+            uint32_t ca[kCache], cb[kCache], cd[kCache], ci[kCache];
+            if (cached) {
+#pragma unroll
+              for (int e = 0; e < kCache; ++e) {
+                ca[e] = 0; cb[e] = 0; cd[e] = 0; ci[e] = 0;
+                if (e < n_main) {
+                  uint32_t ex, ey, ez, ew;
+                  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ex), "=r"(ey), "=r"(ez), "=r"(ew)
+                               : "r"(tab_addr + (uint32_t)(n_first + e) * 16u));
+                  uint32_t slot = slot_w0 + ex;
+                  if (slot >= ic.nslot) slot -= ic.nslot;
+                  ca[e] = ic.planes_enc + slot * ic.slot_enc;
+                  cb[e] = ey & 0x7FFFFFFFu;
+                  cd[e] = ic.acc0 + ez;
+                  ci[e] = ew;
+                }
+              }
+            }
             int t = 0;
             for (int kh = 0; kh < p.K; ++kh)
               for (int kw = 0; kw < p.Kw; ++kw, ++t) {
@@ -754,6 +862,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
                 if (p.dbg) ti0 = clock64();
                 int nk = nks;
                 uint32_t ao = aoff, wo = wb;
+                if (cached) {
+                  if (firstc) {   // k-step 0 through the overwrite table
+                    issue_entries<1>(ic, tab_addr, tab_addr + (uint32_t)n_first * 16u, ao, wo, true);
+                    switch (nks) {
+                      case 2: issue_cached<2, 1>(ic, ca, cb, cd, ci, n_main, ao, wo); break;
+                      case 3: issue_cached<3, 1>(ic, ca, cb, cd, ci, n_main, ao, wo); break;
+                      case 4: issue_cached<4, 1>(ic, ca, cb, cd, ci, n_main, ao, wo); break;
+                      default: break;
+                    }
+                  } else {
+                    switch (nks) {
+                      case 1: issue_cached<1, 0>(ic, ca, cb, cd, ci, n_main, ao, wo); break;
+                      case 2: issue_cached<2, 0>(ic, ca, cb, cd, ci, n_main, ao, wo); break;
+                      case 3: issue_cached<3, 0>(ic, ca, cb, cd, ci, n_main, ao, wo); break;
+                      default: issue_cached<4, 0>(ic, ca, cb, cd, ci, n_main, ao, wo); break;
+                    }
+                  }
+                  nk = 0;
+                } else
                 if (firstc) {   // k-step 0 through the overwrite table, the rest of the chunk like any other
                   issue_entries<1>(ic, tab_addr, tab_addr + (uint32_t)n_first * 16u, ao, wo, true);
                   --nk; ao += ic.kinc; wo += ic.kstep;
@@ -815,7 +942,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     const size_t cgs = (size_t)p.D * plane_vox;
     float* par = s_par + half * 3 * kMaxN;
     EpiCtx ec;
-    ec.bias = par; ec.mul = par + kMaxN; ec.add = par + 2 * kMaxN;
+    ec.bias = smem_u32(par); ec.mul = smem_u32(par + kMaxN); ec.add = smem_u32(par + 2 * kMaxN);
     ec.cgs = cgs;
     const int tile_c0 = (int)blockIdx.y * p.N;
     uint32_t gctr = 0;
@@ -853,7 +980,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
         const uint32_t ab = gctr & 1;
         long long ew0 = 0;
         if (p.dbg) ew0 = clock64();
-        mbar_wait(&acc_full[ab], (gctr >> 1) & 1);
+        mbar_wait_backoff(&acc_full[ab], (gctr >> 1) & 1);
         if (p.dbg) e_wait += clock64() - ew0;
         tc_fence_after();
         for (int zi = (half + g) & 1; zi < nze; zi += 2) {
@@ -1195,6 +1322,8 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   p.n_iss = p.NZ >= 2 ? kMaxIss : 1;
   if (const char* env = getenv("FTB_NISS")) { const int v = atoi(env); if (v >= 1 && v <= kMaxIss && v <= p.NZ) p.n_iss = v; }
   p.dbg = nullptr;
+  static const int no_fast27 = getenv("FTB_CONV_NO_FAST27") ? 1 : 0;
+  p.no_fast27 = no_fast27;
   if (getenv("FTB_CONV_DBG")) {
     static long long* dbuf = nullptr;
     if (!dbuf) FTB_CUDA(cudaMalloc(&dbuf, 256 * 16 * sizeof(long long)));

@@ -173,7 +173,10 @@ trilinear_kernel(const bf16* __restrict__ in, int CG, int Di, int Hi, int Wi, in
 __global__ void __launch_bounds__(256)
 trilinear_smem_kernel(const bf16* __restrict__ in, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int hgroups,
                       int RH, int max_rows, float sd, float sh, float sw, bf16* __restrict__ out) {
-  extern __shared__ float4 s_t[];   // [max_rows][Wi][2]: the two source planes already blended along D (fp32, 8 channels)
+  // [2 halves][max_rows][Wi]: the two source planes already blended along D (fp32, channels 0-3 | 4-7 of the group in
+  // separate arrays: the taps of neighbouring outputs are then neighbouring 16-byte words, one wavefront per quarter warp)
+  extern __shared__ float4 s_t[];
+  const int half_stride = max_rows * Wi;
   int blk = blockIdx.x;
   const int hg = blk % hgroups; blk /= hgroups;
   const int d = blk % Do;
@@ -190,8 +193,8 @@ trilinear_smem_kernel(const bf16* __restrict__ in, int Di, int Hi, int Wi, int D
     unpack_bf16x8(__ldg(base + ((size_t)ld.i1 * Hi + r0) * Wi + i), f1);
 #pragma unroll
     for (int k = 0; k < 8; ++k) f0[k] = ld.l0 * f0[k] + ld.l1 * f1[k];
-    s_t[2 * i] = make_float4(f0[0], f0[1], f0[2], f0[3]);
-    s_t[2 * i + 1] = make_float4(f0[4], f0[5], f0[6], f0[7]);
+    s_t[i] = make_float4(f0[0], f0[1], f0[2], f0[3]);
+    s_t[half_stride + i] = make_float4(f0[4], f0[5], f0[6], f0[7]);
   }
   __syncthreads();
   bf16* obase = out + (bc * (size_t)Do + d) * Ho * Wo * 8;
@@ -200,13 +203,14 @@ trilinear_smem_kernel(const bf16* __restrict__ in, int Di, int Hi, int Wi, int D
     const int h = h_lo + hr;
     if (h >= Ho) continue;
     const Lerp lh = lerp_idx(h, Hi, sh), lw = lerp_idx(w, Wi, sw);
-    const float4* ra = s_t + (size_t)(lh.i0 - r0) * Wi * 2;
-    const float4* rb = s_t + (size_t)(lh.i1 - r0) * Wi * 2;
+    const float4* ra = s_t + (size_t)(lh.i0 - r0) * Wi;
+    const float4* rb = s_t + (size_t)(lh.i1 - r0) * Wi;
     const float w00 = lh.l0 * lw.l0, w01 = lh.l0 * lw.l1, w10 = lh.l1 * lw.l0, w11 = lh.l1 * lw.l1;
     float acc[8];
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
-      const float4 a0 = ra[2 * lw.i0 + hf], a1 = ra[2 * lw.i1 + hf], b0 = rb[2 * lw.i0 + hf], b1 = rb[2 * lw.i1 + hf];
+      const float4 a0 = ra[hf * half_stride + lw.i0], a1 = ra[hf * half_stride + lw.i1];
+      const float4 b0 = rb[hf * half_stride + lw.i0], b1 = rb[hf * half_stride + lw.i1];
       acc[4 * hf + 0] = w00 * a0.x + w01 * a1.x + w10 * b0.x + w11 * b1.x;
       acc[4 * hf + 1] = w00 * a0.y + w01 * a1.y + w10 * b0.y + w11 * b1.y;
       acc[4 * hf + 2] = w00 * a0.z + w01 * a1.z + w10 * b0.z + w11 * b1.z;

@@ -124,6 +124,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// The same wait for warps that are not on the critical path (producers waiting for a free slot, epilogue warps
+// waiting for an accumulator): sleep between polls, so the polling does not take shared-memory cycles from the
+// tensor core's operand fetches.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (++spins > 20000000u) {
+      printf("ftb: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x,
+             threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+
 // TMA: 4-D tiled tensor load, global -> shared, completion on an mbarrier
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar,
                                             int c0, int c1, int c2, int c3) {

@@ -811,8 +811,8 @@ int normact_bwd(const Act& dout, const Act& u, bool norm, const float* gain, con
   p.drop_p = drop_p; p.drop_key = drop_key;
   dim3 grid;
   int iters;
-  normact_grid(u, p.CG, &grid, &iters);
   const bool dr = drop_p > 0.f;
+  normact_grid(u, p.CG, &grid, &iters);
   normact_dispatch(p.CG, [&] { FTB_NA_FLAGS(normact_bwd_kernel, 8); }, [&] { FTB_NA_FLAGS(normact_bwd_kernel, 16); },
                    [&] { FTB_NA_FLAGS(normact_bwd_kernel, 32); });
   FTB_LAUNCH_OK();

@@ -130,7 +130,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
         if (!use0 && !use1) continue;      // only zero padding under these taps
         const int h0 = (t / p.nWt) * p.TH, w0 = (t % p.nWt) * p.TW;
         const int s = n % p.nstage;
-        mbar_wait(&empty[s], ((n / p.nstage) & 1) ^ 1);
+        mbar_wait_backoff(&empty[s], ((n / p.nstage) & 1) ^ 1);
         mbar_expect_tx(&full[s], p.du_box_bytes * (p.kdp == 2 ? 2u : 1u) + p.x_bytes);
         // out-of-range dY planes are zero-filled by TMA (they multiply real X data)
         tma_load_5d(smem + (size_t)s * p.du_bytes, &tm_du, &full[s], 0, w0, h0, d0,
@@ -182,8 +182,13 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
         ++n;
       }
       umma_commit(done);
+      mbar_wait(done, 0);
     }
     __syncwarp();
+    tc_fence_before();
+    // the epilogue warps sleep on a hardware barrier instead of polling the mbarrier (shared-memory cycles the
+    // tensor core needs for its operand fetches)
+    asm volatile("bar.sync 1, 160;" ::: "memory");
   } else {
     // ---- TMEM -> fp32 gradient (atomicAdd): thread = accumulator row = output channel
     const int q = warp & 3;
@@ -196,14 +201,13 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
       const int d0 = (int)((it / tiles_pp) % p.D) - kd + p.pad, d1 = d0 - 1;
       any = (d0 >= 0 && d0 < p.D) || (p.kdp == 2 && kd + 1 < p.K && d1 >= 0 && d1 < p.D);
     }
+    // all MMAs of this CTA have completed once the issuer warp arrives here
+    asm volatile("bar.sync 1, 160;" ::: "memory");
+    tc_fence_after();
     if (p.partials) {
       // ---- per-CTA partial: [row][pcols] fp32, plain 16-byte stores (zeros when this CTA had no item)
       float* out = p.partials + ((size_t)blockIdx.x * 128 + row) * p.pcols;
       const bool row_ok = co < p.cout_real && kd_row < p.K;
-      if (any) {
-        mbar_wait(done, 0);
-        tc_fence_after();
-      }
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
       for (int a = 0; a < na; ++a)
         for (int c0 = 0; c0 < p.Nacc; c0 += 16) {
@@ -223,8 +227,6 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
         }
     } else
     if (any) {
-      mbar_wait(done, 0);
-      tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
       float* dwb = p.dw + (p.per_batch ? (long long)bfix * p.dw_bstride : 0);
       const int nci = p.ncg * 8;
@@ -265,7 +267,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
 }
 
 // dw[idx(class, row, col)] += sum over the nsplit partials of the class; one thread per (class, row, col), consecutive
-// threads = consecutive columns (coalesced reads of every partial); the index mapping is the epilogue's.
+// threads = consecutive columns (coalesced reads of every partial), 16 independent loads in flight per thread (the
+// pass is latency-bound: a 74-deep chain of dependent adds took 13-15 us whatever the grid); the index mapping is
+// the epilogue's; each element has exactly one owner, so no atomics.
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const WgradParams p, int fixed) {
   const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -301,20 +305,34 @@ wgrad_reduce_kernel(const WgradParams p, int fixed) {
     ok = ci < p.ci_real;
   }
   if (!ok) return;
-  const float* src = p.partials + ((size_t)cidx * p.nsplit * 128 + row) * p.pcols + col;
-  const size_t sstride = (size_t)128 * p.pcols;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int sp = 0;
-  for (; sp + 4 <= p.nsplit; sp += 4) {
-    s0 += __ldcs(src + (size_t)sp * sstride);
-    s1 += __ldcs(src + (size_t)(sp + 1) * sstride);
-    s2 += __ldcs(src + (size_t)(sp + 2) * sstride);
-    s3 += __ldcs(src + (size_t)(sp + 3) * sstride);
-  }
-  for (; sp < p.nsplit; ++sp) s0 += __ldcs(src + (size_t)sp * sstride);
   float* dwb = p.dw + (p.per_batch ? (long long)bfix * p.dw_bstride : 0);
   const size_t idx = ((((size_t)co * p.cin_tot + p.ci_base + ci) * p.K + kd_row) * p.K + kh) * p.Kww + kww;
-  dwb[idx] += (s0 + s1) + (s2 + s3);
+  const float old = dwb[idx];   // in flight with the partial loads
+  const float* src = p.partials + ((size_t)cidx * p.nsplit * 128 + row) * p.pcols + col;
+  const size_t sstride = (size_t)128 * p.pcols;
+  float acc = 0.f;
+  int sp = 0;
+  for (; sp + 16 <= p.nsplit; sp += 16) {
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = __ldcs(src + (size_t)(sp + k) * sstride);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] += v[k + 8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] += v[k + 4];
+    acc += (v[0] + v[2]) + (v[1] + v[3]);
+  }
+  if (sp < p.nsplit) {
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = sp + k < p.nsplit ? __ldcs(src + (size_t)(sp + k) * sstride) : 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] += v[k + 8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] += v[k + 4];
+    acc += (v[0] + v[2]) + (v[1] + v[3]);
+  }
+  dwb[idx] = old + acc;
 }
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
