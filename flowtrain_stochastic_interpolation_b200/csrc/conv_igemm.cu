@@ -527,6 +527,49 @@ __device__ __forceinline__ void issue_cached(const IssueCtx& ic, const uint32_t 
   }
 }
 
+// All filter taps of one (group, channel chunk) pass for cached entries: per tap only the weight-slot hand-shake
+// (wait / commit) and one call of issue_cached remain on the issuing thread.
+struct TapCtx {
+  uint32_t w_enc, wchunk_enc, rowp_enc, first_lo, first_hi;
+  uint64_t *w_full, *w_empty;
+  int K, Kw, nwslot, res_slot0;
+  bool stream_w, w_waited, first_pass;
+};
+template <int NKS>
+__device__ __forceinline__ void run_taps_cached(const IssueCtx& ic, const TapCtx& tc, const uint32_t (&ca)[kCache],
+                                                const uint32_t (&cb)[kCache], const uint32_t (&cd)[kCache],
+                                                const uint32_t (&ci)[kCache], int ne, uint32_t& wslot, uint32_t& wphase) {
+  uint32_t aoff_row = 0;
+  uint32_t res_slot = (uint32_t)tc.res_slot0;
+  for (int kh = 0; kh < tc.K; ++kh, aoff_row += tc.rowp_enc)
+    for (int kw = 0; kw < tc.Kw; ++kw) {
+      uint32_t slot;
+      if (tc.stream_w) {
+        slot = wslot;
+        mbar_wait(&tc.w_full[slot], wphase);
+        tc_fence_after();
+      } else {
+        slot = res_slot++;
+        if (!tc.w_waited) {
+          mbar_wait(&tc.w_full[slot], 0);
+          tc_fence_after();
+        }
+      }
+      const uint32_t wb = tc.w_enc + slot * tc.wchunk_enc;
+      const uint32_t ao = aoff_row + (uint32_t)kw;
+      if (tc.first_pass && (kh | kw) == 0) {   // first touch of every accumulator: k-step 0 through the overwrite table
+        issue_entries<1>(ic, tc.first_lo, tc.first_hi, ao, wb, true);
+        issue_cached<NKS, 1>(ic, ca, cb, cd, ci, ne, ao, wb);
+      } else {
+        issue_cached<NKS, 0>(ic, ca, cb, cd, ci, ne, ao, wb);
+      }
+      if (tc.stream_w) {
+        umma_commit(&tc.w_empty[slot]);
+        if (++wslot == (uint32_t)tc.nwslot) { wslot = 0; wphase ^= 1; }
+      }
+    }
+}
+
 // Resident 3^3 weights, one channel chunk of three k-steps (the 48 -> 48 layers that hold most of the FLOPs): all
 // 27 (tap, k-step) MMAs of ONE table entry in a straight line.  The issuer is a single thread, and ncu (r02, source
 // page) showed the kernel bound by ITS instruction stream, not by the tensor pipe: with the per-tap walk an entry is
@@ -808,9 +851,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
             int n_new;
             if (p.ncc == 1) { const int upto = min(npl, g * p.NZ + win); n_new = upto - waited; waited = upto; }
             else n_new = win;
-            for (int i = 0; i < n_new; ++i) {
-              mbar_wait(&plane_full[rslot], rphase);
-              if (++rslot == ic.nslot) { rslot = 0; rphase ^= 1; }
+            for (int i = 0; i < n_new; i += 4) {   // up to four planes per round trip
+              uint32_t ba[4], bp[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (i + j < n_new) {
+                  ba[j] = smem_u32(&plane_full[rslot]); bp[j] = rphase;
+                  if (++rslot == ic.nslot) { rslot = 0; rphase ^= 1; }
+                } else {
+                  ba[j] = ba[j - 1]; bp[j] = bp[j - 1];
+                }
+              }
+              mbar_wait4(ba[0], bp[0], ba[1], bp[1], ba[2], bp[2], ba[3], bp[3]);
             }
             if (p.dbg) dbg_plane += clock64() - tq0;
             tc_fence_after();
@@ -836,6 +888,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
                 }
               }
             }
+            if (cached) {
+              long long ti0 = 0;
+              if (p.dbg) ti0 = clock64();
+              TapCtx tcx;
+              tcx.w_enc = w_enc; tcx.wchunk_enc = wchunk_enc; tcx.rowp_enc = rowp_enc;
+              tcx.first_lo = tab_addr; tcx.first_hi = tab_addr + (uint32_t)n_first * 16u;
+              tcx.w_full = w_full; tcx.w_empty = w_empty;
+              tcx.K = p.K; tcx.Kw = p.Kw; tcx.nwslot = p.wslot; tcx.res_slot0 = cc * p.taps;
+              tcx.stream_w = stream_w; tcx.w_waited = w_waited; tcx.first_pass = cc == 0;
+              switch (nks) {
+                case 1: run_taps_cached<1>(ic, tcx, ca, cb, cd, ci, n_main, wslot, wphase); break;
+                case 2: run_taps_cached<2>(ic, tcx, ca, cb, cd, ci, n_main, wslot, wphase); break;
+                case 3: run_taps_cached<3>(ic, tcx, ca, cb, cd, ci, n_main, wslot, wphase); break;
+                default: run_taps_cached<4>(ic, tcx, ca, cb, cd, ci, n_main, wslot, wphase); break;
+              }
+              if (p.dbg) dbg_issue += clock64() - ti0;
+            } else {
             int t = 0;
             for (int kh = 0; kh < p.K; ++kh)
               for (int kw = 0; kw < p.Kw; ++kw, ++t) {
@@ -862,25 +931,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
                 if (p.dbg) ti0 = clock64();
                 int nk = nks;
                 uint32_t ao = aoff, wo = wb;
-                if (cached) {
-                  if (firstc) {   // k-step 0 through the overwrite table
-                    issue_entries<1>(ic, tab_addr, tab_addr + (uint32_t)n_first * 16u, ao, wo, true);
-                    switch (nks) {
-                      case 2: issue_cached<2, 1>(ic, ca, cb, cd, ci, n_main, ao, wo); break;
-                      case 3: issue_cached<3, 1>(ic, ca, cb, cd, ci, n_main, ao, wo); break;
-                      case 4: issue_cached<4, 1>(ic, ca, cb, cd, ci, n_main, ao, wo); break;
-                      default: break;
-                    }
-                  } else {
-                    switch (nks) {
-                      case 1: issue_cached<1, 0>(ic, ca, cb, cd, ci, n_main, ao, wo); break;
-                      case 2: issue_cached<2, 0>(ic, ca, cb, cd, ci, n_main, ao, wo); break;
-                      case 3: issue_cached<3, 0>(ic, ca, cb, cd, ci, n_main, ao, wo); break;
-                      default: issue_cached<4, 0>(ic, ca, cb, cd, ci, n_main, ao, wo); break;
-                    }
-                  }
-                  nk = 0;
-                } else
                 if (firstc) {   // k-step 0 through the overwrite table, the rest of the chunk like any other
                   issue_entries<1>(ic, tab_addr, tab_addr + (uint32_t)n_first * 16u, ao, wo, true);
                   --nk; ao += ic.kinc; wo += ic.kstep;
@@ -901,6 +951,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
                   if (++wslot == (uint32_t)p.wslot) { wslot = 0; wphase ^= 1; }
                 }
               }
+            }   // !cached
             if (p.ncc > 1) {   // this pass's window is done: hand all its slots back
               for (int i = 0; i < win; ++i) {
                 umma_commit(&plane_empty[slot_w0]);

@@ -124,6 +124,37 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait for up to four barriers at once: the four try_wait round trips overlap instead of adding up (a satisfied wait
+// still costs its shared-memory latency on the issuing thread's critical path).  Unused entries repeat the last one.
+__device__ __forceinline__ bool mbar_try_wait4(uint32_t a0, uint32_t p0, uint32_t a1, uint32_t p1, uint32_t a2, uint32_t p2,
+                                               uint32_t a3, uint32_t p3) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred q0, q1, q2, q3;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q0, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q1, [%3], %4;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q2, [%5], %6;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 q3, [%7], %8;\n\t"
+      "and.pred q0, q0, q1;\n\t"
+      "and.pred q2, q2, q3;\n\t"
+      "and.pred q0, q0, q2;\n\t"
+      "selp.u32 %0, 1, 0, q0;\n\t}"
+      : "=r"(ok)
+      : "r"(a0), "r"(p0), "r"(a1), "r"(p1), "r"(a2), "r"(p2), "r"(a3), "r"(p3)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait4(uint32_t a0, uint32_t p0, uint32_t a1, uint32_t p1, uint32_t a2, uint32_t p2,
+                                           uint32_t a3, uint32_t p3) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait4(a0, p0, a1, p1, a2, p2, a3, p3)) {
+    if (++spins > 20000000u) {
+      printf("ftb: mbarrier (x4) timeout block %d thread %d bar %u\n", blockIdx.x, threadIdx.x, a0);
+      __trap();
+    }
+  }
+}
+
 // The same wait for warps that are not on the critical path (producers waiting for a free slot, epilogue warps
 // waiting for an accumulator): sleep between polls, so the polling does not take shared-memory cycles from the
 // tensor core's operand fetches.

@@ -1,0 +1,12 @@
+set -u
+mkdir -p gpurun_out
+L=gpurun_out/r2_exp10.log
+: > $L
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_headline.py tests/test_gpu_train.py -m gpu -q -x 2>&1 | tail -3 >> $L
+for v in "" "FTB_CONV_RUNS=0"; do
+  echo "== conv bench [$v]" >> $L
+  env $v timeout 200 python tools/conv_bench.py 8 2>&1 | awk '/^B8/ {print}' >> $L
+  env $v FTB_CONV_DBG=1 timeout 200 python tools/conv_bench.py 8 2>&1 | awk '/issuer0/ {print}' | head -3 >> $L
+done
+timeout 400 python bench.py --no-cpu-baseline --no-extras > gpurun_out/r2_bench10.json 2>> $L; echo "bench rc=$?" >> $L
+tail -40 $L
