@@ -55,7 +55,7 @@ struct WgradParams {
   int nstage;
   uint32_t du_bytes, x_bytes;
   uint32_t b_lbo, b_sbo, b_kh, b_kstep;   // X operand: K-direction / N-direction core-matrix strides, bytes per kh row, per k-step row
-  int interleave;
+  int dbg;              // FTB_WGRAD_DBG: block 0 prints issuer / producer cycle counters
   int TH, TW, kpr;      // voxel tile (TH x TW = 128), k-steps per tile row (1 when TW == 8: a k-step is two h rows)
   uint32_t off_x, off_bar, tmem_cols;
   float* dw;
@@ -89,12 +89,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
   const int bfix = r;   // per_batch: sample index
   const int g0 = cls * p.nacc;
   const int na = min(p.nacc, p.ngrp - g0);
-  // contiguous item ranges, or (interleave) CTA s takes items s, s + nsplit, ...: the CTAs of a wave then walk
-  // neighbouring tiles of the same rows at the same time (DRAM page / L2 sector locality)
-  const long long per = (p.items + p.nsplit - 1) / p.nsplit;
-  const long long i_lo = p.interleave ? split : (long long)split * per;
-  const long long i_hi = p.interleave ? p.items : min(p.items, i_lo + per);
-  const long long i_st = p.interleave ? p.nsplit : 1;
+  // contiguous item range of this CTA; the loops below walk it with (tile, plane, sample) counters, no division
+  const int per = (int)((p.items + p.nsplit - 1) / p.nsplit);
+  const int i_lo = split * per;
+  const int i_hi = min((int)p.items, i_lo + per);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.nstage; ++i) {
@@ -119,18 +117,29 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       int n = 0;
-      for (long long it = i_lo; it < i_hi; it += i_st) {
-        int t = (int)(it % tiles_pp);
-        long long q = it / tiles_pp;
-        const int xd = (int)(q % p.D);     // items walk the X planes; the dY plane of depth tap kd is xd - kd + pad
-        const int b = p.per_batch ? bfix : (int)(q / p.D);
+      uint32_t s = 0, ph = 0;
+      long long pw = 0, pt0 = clock64();
+      // items walk the X planes; the dY plane of depth tap kd is xd - kd + pad
+      int t = i_lo % tiles_pp, xd = (i_lo / tiles_pp) % p.D, bb = (i_lo / tiles_pp) / p.D;
+      for (int it = i_lo; it < i_hi; ++it, ++t) {
+        if (t == tiles_pp) { t = 0; if (++xd == p.D) { xd = 0; ++bb; } }
+        const int b = p.per_batch ? bfix : bb;
         const int d0 = xd - kd + p.pad, d1 = d0 - 1;
         const bool use0 = d0 >= 0 && d0 < p.D;
         const bool use1 = p.kdp == 2 && kd + 1 < p.K && d1 >= 0 && d1 < p.D;
         if (!use0 && !use1) continue;      // only zero padding under these taps
-        const int h0 = (t / p.nWt) * p.TH, w0 = (t % p.nWt) * p.TW;
-        const int s = n % p.nstage;
-        mbar_wait_backoff(&empty[s], ((n / p.nstage) & 1) ^ 1);
+        const int ht = t / p.nWt;
+        const int h0 = ht * p.TH, w0 = (t - ht * p.nWt) * p.TW;
+        long long pq = 0;
+        if (p.dbg) pq = clock64();
+        mbar_wait_backoff(&empty[s], ph ^ 1);
+        if (p.dbg) pw += clock64() - pq;
+        if (p.dbg == 2) {   // timing experiment: no loads at all (results are garbage), the MMA stream alone
+          mbar_arrive(&full[s]);
+          ++n;
+          if (++s == (uint32_t)p.nstage) { s = 0; ph ^= 1; }
+          continue;
+        }
         mbar_expect_tx(&full[s], p.du_box_bytes * (p.kdp == 2 ? 2u : 1u) + p.x_bytes);
         // out-of-range dY planes are zero-filled by TMA (they multiply real X data)
         tma_load_5d(smem + (size_t)s * p.du_bytes, &tm_du, &full[s], 0, w0, h0, d0,
@@ -145,7 +154,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
           tma_load_5d(smem + p.off_x + (size_t)s * p.x_bytes, &tm_x, &full[s], 0, w0 - p.padw, h0 - p.pad, xd,
                       b * p.x_cgtot + p.x_cgoff + chunk * p.ncg);
         ++n;
+        if (++s == (uint32_t)p.nstage) { s = 0; ph ^= 1; }
       }
+      if (p.dbg && blockIdx.x == 0) printf("wgrad dbg producer: total %lld wait_empty %lld stages %d\n", clock64() - pt0, pw, n);
     }
   } else if (warp == 1) {
     if (elect_one()) {
@@ -157,32 +168,71 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
       // B (X halo tile): LBO = halo-row pitch (next 8 voxels along K), SBO = channel-group pitch
       const uint32_t b_hi = (p.b_sbo >> 4) | (1u << 14);
       const uint32_t b_lbo = (p.b_lbo >> 4) << 16;
-      const uint32_t b_kstep = p.b_kstep >> 4;   // per tile row of k-steps (TW == 8: two h rows per k-step of 16 voxels)
-      const int kpr = p.kpr;
+      const uint32_t b_kstep = p.b_kstep >> 4;   // two h rows per k-step of 16 voxels
+      // The issuer is ONE thread and its instruction stream is on the critical path (an M=128 x N=144 MMA takes 72
+      // cycles; a dependent integer instruction of a single warp ~6): everything that does not change between stages
+      // is computed here, once - per accumulator the B start offset of its (kh group, kw) and its TMEM column - and
+      // the stage / phase cursors advance incrementally (no division in the loop).
+      constexpr int kUnrollAcc = 4;
+      uint32_t boff[kUnrollAcc], dcol[kUnrollAcc];
+#pragma unroll
+      for (int a = 0; a < kUnrollAcc; ++a) {
+        const int g = g0 + (a < na ? a : 0);
+        const int kh0 = (g / p.Kw) * p.stack, kw = g % p.Kw;
+        boff[a] = ((uint32_t)kh0 * p.b_kh + (uint32_t)kw * 16u) >> 4;
+        dcol[a] = tmem_base + (uint32_t)(a * p.Nacc);
+      }
+      uint32_t kso[8];   // B offset of k-step ks: tile rows of kpr k-steps (TW == 8: one k-step = two h rows)
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) kso[ks] = (uint32_t)(ks / p.kpr) * b_kstep + (uint32_t)(ks % p.kpr) * 16u;
+      const uint32_t du_enc = p.du_bytes >> 4, x_enc = p.x_bytes >> 4;
+      const uint32_t a_base = (smem_u32(smem) >> 4) | a_lbo;
+      const uint32_t x_base = (smem_u32(smem + p.off_x) >> 4) | b_lbo;
       int n = 0;
-      for (long long it = i_lo; it < i_hi; it += i_st) {
-        const int xd = (int)((it / tiles_pp) % p.D);
+      uint32_t s = 0, ph = 0;
+      long long iw = 0, it0 = clock64();
+      int t = i_lo % tiles_pp, xd = (i_lo / tiles_pp) % p.D;
+      for (int it = i_lo; it < i_hi; ++it, ++t) {
+        if (t == tiles_pp) { t = 0; if (++xd == p.D) xd = 0; }
         const int d0 = xd - kd + p.pad, d1 = d0 - 1;
         if (!(d0 >= 0 && d0 < p.D) && !(p.kdp == 2 && kd + 1 < p.K && d1 >= 0 && d1 < p.D)) continue;
-        const int s = n % p.nstage;
-        mbar_wait(&full[s], (n / p.nstage) & 1);
+        long long iq = 0;
+        if (p.dbg) iq = clock64();
+        mbar_wait(&full[s], ph);
+        if (p.dbg) iw += clock64() - iq;
         tc_fence_after();
-        const uint32_t a0 = (smem_u32(smem + (size_t)s * p.du_bytes) >> 4) | a_lbo;
-        const uint32_t xb = smem_u32(smem + p.off_x + (size_t)s * p.x_bytes);
-        for (int a = 0; a < na; ++a) {
+        const uint32_t a0 = a_base + s * du_enc;
+        const uint32_t xb = x_base + s * x_enc;
+        const uint32_t first = n != 0 ? 1u : 0u;
+#pragma unroll
+        for (int a = 0; a < kUnrollAcc; ++a) {
+          if (a < na) {
+            const uint32_t b0 = xb + boff[a];
+            umma_bf16_lohi(dcol[a], a0, a_hi, b0, b_hi, idesc, first);
+#pragma unroll
+            for (int ks = 1; ks < 8; ++ks)
+              umma_bf16_lohi(dcol[a], a0 + ks * 16, a_hi, b0 + kso[ks], b_hi, idesc, 1u);
+          }
+        }
+        for (int a = kUnrollAcc; a < na; ++a) {
           const int g = g0 + a;
           const int kh0 = (g / p.Kw) * p.stack, kw = g % p.Kw;
-          const uint32_t b0 = ((xb + (uint32_t)kh0 * p.b_kh + (uint32_t)kw * 16u) >> 4) | b_lbo;
-          const uint32_t dcol = tmem_base + (uint32_t)(a * p.Nacc);
+          const uint32_t b0 = xb + (((uint32_t)kh0 * p.b_kh + (uint32_t)kw * 16u) >> 4);
+          const uint32_t dc = tmem_base + (uint32_t)(a * p.Nacc);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
-            umma_bf16_lohi(dcol, a0 + ks * 16, a_hi, b0 + (ks / kpr) * b_kstep + (ks % kpr) * 16, b_hi, idesc, (n | ks) != 0);
+            umma_bf16_lohi(dc, a0 + ks * 16, a_hi, b0 + kso[ks], b_hi, idesc, (n | ks) != 0);
         }
         umma_commit(&empty[s]);
         ++n;
+        if (++s == (uint32_t)p.nstage) { s = 0; ph ^= 1; }
       }
       umma_commit(done);
+      const long long it1 = clock64();
       mbar_wait(done, 0);
+      if (p.dbg && blockIdx.x == 0)
+        printf("wgrad dbg issuer: loop %lld wait_full %lld drain %lld stages %d (MMA time %lld)\n", it1 - it0, iw, clock64() - it1, n,
+               (long long)n * na * 8 * (p.Nacc / 2 > 32 + p.Nacc / 4 ? p.Nacc / 2 : 32 + p.Nacc / 4));
     }
     __syncwarp();
     tc_fence_before();
@@ -197,8 +247,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
     const int kd_row = p.kdp == 2 ? kd + (row >> 6) : kd;
     // any item with an in-range depth tap?  (same predicate as the producer / issuer loops)
     bool any = false;
-    for (long long it = i_lo; it < i_hi && !any; it += i_st) {
-      const int d0 = (int)((it / tiles_pp) % p.D) - kd + p.pad, d1 = d0 - 1;
+    for (int it = i_lo; it < i_hi && !any; ++it) {
+      const int d0 = (it / tiles_pp) % p.D - kd + p.pad, d1 = d0 - 1;
       any = (d0 >= 0 && d0 < p.D) || (p.kdp == 2 && kd + 1 < p.K && d1 >= 0 && d1 < p.D);
     }
     // all MMAs of this CTA have completed once the issuer warp arrives here
@@ -426,7 +476,8 @@ int conv_wgrad(const Act& x, int x_cgoff, int x_cg, const Act& dy, int dy_cgoff,
   const int cout_cg = cdiv(cout_real, 8);
   p.nmb = cdiv(cout_cg, 16);
   const int du_box_cg = cout_cg < 16 ? cout_cg : 16;
-  // voxel tile TH x TW = 128: wider tiles read longer contiguous runs of a W row (FTB_WGRAD_TW = 8 | 16 | 32)
+  // voxel tile TH x TW = 128 voxels: 16 x 8, 8 x 16 or 4 x 32.  Wider tiles mean longer box rows (fewer, larger TMA
+  // requests per stage: 128-byte dY rows and 160-byte X rows at TW = 8 against 512 / 544 bytes at TW = 32).
   static const int tw_env = getenv("FTB_WGRAD_TW") ? atoi(getenv("FTB_WGRAD_TW")) : 8;
   p.TW = tw_env;
   while (p.TW > 8 && p.TW / 2 >= x.W) p.TW /= 2;
@@ -474,8 +525,8 @@ int conv_wgrad(const Act& x, int x_cgoff, int x_cg, const Act& dy, int dy_cgoff,
   if (nsplit > max_split) nsplit = (int)max_split;
   if (nsplit < 1) nsplit = 1;
   p.nsplit = nsplit;
-  static const int il_env = getenv("FTB_WGRAD_INTERLEAVE") ? atoi(getenv("FTB_WGRAD_INTERLEAVE")) : 0;
-  p.interleave = il_env;
+  static const int dbg_env = getenv("FTB_WGRAD_DBG") ? atoi(getenv("FTB_WGRAD_DBG")) : 0;
+  p.dbg = dbg_env;
 
   CUtensorMap tmd, tmx;
   FTB_TRY(tmap_du(&tmd, dy, du_box_cg, p.TH, p.TW));
