@@ -55,6 +55,7 @@ struct WgradParams {
   int nstage;
   uint32_t du_bytes, x_bytes;
   uint32_t b_lbo, b_sbo, b_kh, b_kstep;   // X operand: K-direction / N-direction core-matrix strides, bytes per kh row, per k-step row
+  int map4;             // 4-D tensor maps (inner dimension = a whole box row of TW voxels x 8 channels)
   int dbg;              // FTB_WGRAD_DBG: block 0 prints issuer / producer cycle counters
   int TH, TW, kpr;      // voxel tile (TH x TW = 128), k-steps per tile row (1 when TW == 8: a k-step is two h rows)
   uint32_t off_x, off_bar, tmem_cols;
@@ -142,17 +143,30 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
         }
         mbar_expect_tx(&full[s], p.du_box_bytes * (p.kdp == 2 ? 2u : 1u) + p.x_bytes);
         // out-of-range dY planes are zero-filled by TMA (they multiply real X data)
+        if (p.map4) {
+          tma_load_4d(smem + (size_t)s * p.du_bytes, &tm_du, &full[s], w0 * 8, h0, d0, b * p.du_cgtot + p.du_cgoff + mb * 16);
+          if (p.kdp == 2)
+            tma_load_4d(smem + (size_t)s * p.du_bytes + 16384, &tm_du, &full[s], w0 * 8, h0, kd + 1 < p.K ? d1 : -1,
+                        b * p.du_cgtot + p.du_cgoff);
+          if (p.stack > 1)
+            tma_load_4d(smem + p.off_x + (size_t)s * p.x_bytes, &tm_x, &full[s], (w0 - p.padw) * 8,
+                        b * p.x_cgtot + p.x_cgoff + chunk * p.ncg, h0 - p.pad, xd);
+          else
+            tma_load_4d(smem + p.off_x + (size_t)s * p.x_bytes, &tm_x, &full[s], (w0 - p.padw) * 8, h0 - p.pad, xd,
+                        b * p.x_cgtot + p.x_cgoff + chunk * p.ncg);
+        } else {
         tma_load_5d(smem + (size_t)s * p.du_bytes, &tm_du, &full[s], 0, w0, h0, d0,
-                    b * p.du_cgtot + p.du_cgoff + mb * 16);
-        if (p.kdp == 2)
-          tma_load_5d(smem + (size_t)s * p.du_bytes + 16384, &tm_du, &full[s], 0, w0, h0, kd + 1 < p.K ? d1 : -1,
-                      b * p.du_cgtot + p.du_cgoff);
-        if (p.stack > 1)
-          tma_load_5d(smem + p.off_x + (size_t)s * p.x_bytes, &tm_x, &full[s], 0, w0 - p.padw,
-                      b * p.x_cgtot + p.x_cgoff + chunk * p.ncg, h0 - p.pad, xd);
-        else
-          tma_load_5d(smem + p.off_x + (size_t)s * p.x_bytes, &tm_x, &full[s], 0, w0 - p.padw, h0 - p.pad, xd,
-                      b * p.x_cgtot + p.x_cgoff + chunk * p.ncg);
+                      b * p.du_cgtot + p.du_cgoff + mb * 16);
+          if (p.kdp == 2)
+            tma_load_5d(smem + (size_t)s * p.du_bytes + 16384, &tm_du, &full[s], 0, w0, h0, kd + 1 < p.K ? d1 : -1,
+                        b * p.du_cgtot + p.du_cgoff);
+          if (p.stack > 1)
+            tma_load_5d(smem + p.off_x + (size_t)s * p.x_bytes, &tm_x, &full[s], 0, w0 - p.padw,
+                        b * p.x_cgtot + p.x_cgoff + chunk * p.ncg, h0 - p.pad, xd);
+          else
+            tma_load_5d(smem + p.off_x + (size_t)s * p.x_bytes, &tm_x, &full[s], 0, w0 - p.padw, h0 - p.pad, xd,
+                        b * p.x_cgtot + p.x_cgoff + chunk * p.ncg);
+        }
         ++n;
         if (++s == (uint32_t)p.nstage) { s = 0; ph ^= 1; }
       }
@@ -438,6 +452,41 @@ int tmap_x(CUtensorMap* tm, const Act& a, int BW, int BH, int ncg, bool stacked)
   return 0;
 }
 
+// 4-D variants: dims (W*8, H, D, B*CG) resp. (W*8, B*CG, H, D); the innermost box dimension is a whole tile row
+int tmap_du4(CUtensorMap* tm, const Act& a, int cg, int TH, int TW) {
+  PFN_encodeTiled enc = wg_encode();
+  FTB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[4] = {(cuuint64_t)a.W * 8, (cuuint64_t)a.H, (cuuint64_t)a.D, (cuuint64_t)a.B * a.cg()};
+  cuuint64_t gstr[3] = {(cuuint64_t)a.W * 16, (cuuint64_t)a.W * a.H * 16, (cuuint64_t)a.W * a.H * a.D * 16};
+  cuuint32_t box[4] = {(cuuint32_t)TW * 8, (cuuint32_t)TH, 1u, (cuuint32_t)cg};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.p, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, tma_promo(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FTB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (wgrad dY, 4-D) failed (" + std::to_string((int)r) + ")");
+  return 0;
+}
+int tmap_x4(CUtensorMap* tm, const Act& a, int BW, int BH, int ncg, bool stacked) {
+  PFN_encodeTiled enc = wg_encode();
+  FTB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r;
+  if (!stacked) {
+    cuuint64_t gdim[4] = {(cuuint64_t)a.W * 8, (cuuint64_t)a.H, (cuuint64_t)a.D, (cuuint64_t)a.B * a.cg()};
+    cuuint64_t gstr[3] = {(cuuint64_t)a.W * 16, (cuuint64_t)a.W * a.H * 16, (cuuint64_t)a.W * a.H * a.D * 16};
+    cuuint32_t box[4] = {(cuuint32_t)BW * 8, (cuuint32_t)BH, 1u, (cuuint32_t)ncg};
+    r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.p, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, tma_promo(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    cuuint64_t gdim[4] = {(cuuint64_t)a.W * 8, (cuuint64_t)a.B * a.cg(), (cuuint64_t)a.H, (cuuint64_t)a.D};
+    cuuint64_t gstr[3] = {(cuuint64_t)a.W * a.H * a.D * 16, (cuuint64_t)a.W * 16, (cuuint64_t)a.W * a.H * 16};
+    cuuint32_t box[4] = {(cuuint32_t)BW * 8, (cuuint32_t)ncg, (cuuint32_t)BH, 1u};
+    r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, a.p, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, tma_promo(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  FTB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (wgrad X, 4-D) failed (" + std::to_string((int)r) + ")");
+  return 0;
+}
+
 }  // namespace
 
 size_t conv_wgrad_partial_bytes() { return (size_t)(num_sms() + 12) * 128 * 512 * sizeof(float); }
@@ -476,9 +525,13 @@ int conv_wgrad(const Act& x, int x_cgoff, int x_cg, const Act& dy, int dy_cgoff,
   const int cout_cg = cdiv(cout_real, 8);
   p.nmb = cdiv(cout_cg, 16);
   const int du_box_cg = cout_cg < 16 ? cout_cg : 16;
-  // voxel tile TH x TW = 128 voxels: 16 x 8, 8 x 16 or 4 x 32.  Wider tiles mean longer box rows (fewer, larger TMA
-  // requests per stage: 128-byte dY rows and 160-byte X rows at TW = 8 against 512 / 544 bytes at TW = 32).
-  static const int tw_env = getenv("FTB_WGRAD_TW") ? atoi(getenv("FTB_WGRAD_TW")) : 8;
+  // voxel tile TH x TW = 128 voxels: 16 x 8, 8 x 16 or 4 x 32.  The stage ring is bound by TMA delivery, and TMA works
+  // in units of the box's INNERMOST dimension: with 5-D maps (innermost = 8 channels = 16 bytes) a stage took 2 630
+  // cycles against 1 730 of tensor time; 4-D maps whose innermost dimension is a whole tile row (TW x 8 channels:
+  // 256-byte dY rows and 288-byte X rows at TW = 16) brought 48 -> 48 @64^3 from 397 to 315 us, the 7^3 stem from
+  // 2.27 to 1.43 ms and the 1^3 48 -> 384 layer from 540 to 281 us (profiles/r02_wgrad_tma_maps.log).  TW = 32 needs
+  // the 5-D form (a 34-voxel halo row exceeds the 256-element box limit) and is slower.
+  static const int tw_env = getenv("FTB_WGRAD_TW") ? atoi(getenv("FTB_WGRAD_TW")) : 16;
   p.TW = tw_env;
   while (p.TW > 8 && p.TW / 2 >= x.W) p.TW /= 2;
   FTB_CHECK(p.TW == 8 || p.TW == 16 || p.TW == 32, "wgrad: tile width");
@@ -529,8 +582,16 @@ int conv_wgrad(const Act& x, int x_cgoff, int x_cg, const Act& dy, int dy_cgoff,
   p.dbg = dbg_env;
 
   CUtensorMap tmd, tmx;
-  FTB_TRY(tmap_du(&tmd, dy, du_box_cg, p.TH, p.TW));
-  FTB_TRY(tmap_x(&tmx, x, BW, BH, p.ncg, p.stack > 1));
+  // 4-D maps whenever a box row fits the 256-element limit of a box dimension (TW <= 16 with a W halo)
+  static const int map4_env = getenv("FTB_WGRAD_MAP4") ? atoi(getenv("FTB_WGRAD_MAP4")) : 1;
+  p.map4 = (map4_env && BW * 8 <= 256 && p.TW * 8 <= 256) ? 1 : 0;
+  if (p.map4) {
+    FTB_TRY(tmap_du4(&tmd, dy, du_box_cg, p.TH, p.TW));
+    FTB_TRY(tmap_x4(&tmx, x, BW, BH, p.ncg, p.stack > 1));
+  } else {
+    FTB_TRY(tmap_du(&tmd, dy, du_box_cg, p.TH, p.TW));
+    FTB_TRY(tmap_x(&tmx, x, BW, BH, p.ncg, p.stack > 1));
+  }
   static bool attr_set = false;
   if (!attr_set) {
     FTB_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kWgSmemLimit + 128)));
