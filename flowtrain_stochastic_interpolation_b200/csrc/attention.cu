@@ -131,6 +131,7 @@ constexpr int kCtxStages = 3;
 constexpr int kCtxThreads = 320;   // TMA warp | MMA warp | 8 exp warps
 
 struct CtxParams {
+  int vdiv;   // divisor of the voxel coordinate of the x / qkv tensor map (make_voxel_tmap)
   int heads, dh, hd;             // hd = heads*dh = 128
   int cgtot;                     // channel groups of the qkv tensor
   long long vox;                 // voxels per sample
@@ -199,8 +200,8 @@ ctx_tc_kernel(const __grid_constant__ CUtensorMap tm, const CtxParams p) {
         mbar_expect_tx(&full[s], kBytesK + 16 * kCtxT * 16);
         uint8_t* dst = smem + s * kStage;
         const int v0 = (t_lo + i) * kCtxT;
-        tma_load_3d(dst, &tm, &full[s], 0, v0, b * p.cgtot + p.hd / 8);
-        tma_load_3d(dst + kBytesK, &tm, &full[s], 0, v0, b * p.cgtot + 2 * p.hd / 8);
+        tma_load_3d(dst, &tm, &full[s], 0, v0 / p.vdiv, b * p.cgtot + p.hd / 8);
+        tma_load_3d(dst + kBytesK, &tm, &full[s], 0, v0 / p.vdiv, b * p.cgtot + 2 * p.hd / 8);
       }
     }
   } else if (warp == 1) {
@@ -302,6 +303,7 @@ constexpr int kKvT = 128;
 constexpr int kKvThreads = 320;
 
 struct KvCtxParams {
+  int vdiv;   // divisor of the voxel coordinate of the x / qkv tensor map (make_voxel_tmap)
   int heads, dh, hd;
   int cg;                        // channel groups of x (C/8)
   int cgtot, cgoff;
@@ -391,7 +393,7 @@ kvctx_kernel(const __grid_constant__ CUtensorMap tm, const KvCtxParams p) {
         const int s = i % p.nx;
         mbar_wait(&x_empty[s], ((i / p.nx) & 1) ^ 1);
         mbar_expect_tx(&x_full[s], (uint32_t)p.cg * kKvT * 16);
-        tma_load_3d(smem + s * p.x_stage, &tm, &x_full[s], 0, (t_lo + i) * kKvT, b * p.cgtot + p.cgoff);
+        tma_load_3d(smem + s * p.x_stage, &tm, &x_full[s], 0, (t_lo + i) * kKvT / p.vdiv, b * p.cgtot + p.cgoff);
       }
     }
   } else if (warp == 1) {
@@ -542,6 +544,7 @@ constexpr int kQoT = 128;
 constexpr int kQoThreads = 448;
 
 struct QoutParams {
+  int vdiv;   // divisor of the voxel coordinate of the x / qkv tensor map (make_voxel_tmap)
   int heads, dh;
   int cg, C;                     // channel groups / padded channels of x (= output channels)
   int cgtot, cgoff;              // of x
@@ -702,7 +705,7 @@ qout_kernel(const __grid_constant__ CUtensorMap tm, const QoutParams p) {
         const int s = i % p.nx;
         mbar_wait(&x_empty[s], ((i / p.nx) & 1) ^ 1);
         mbar_expect_tx(&x_full[s], (uint32_t)p.cg * kQoT * 16);
-        tma_load_3d(smem + s * p.x_stage, &tm, &x_full[s], 0, (t_lo + i) * kQoT, b * p.cgtot + p.cgoff);
+        tma_load_3d(smem + s * p.x_stage, &tm, &x_full[s], 0, (t_lo + i) * kQoT / p.vdiv, b * p.cgtot + p.cgoff);
       }
     }
   } else if (warp == 1) {
@@ -1080,8 +1083,10 @@ int linattn_context_partial(const Act& qkv, int heads, int dh, int nsplit, const
   static const bool simt = [] { const char* e = getenv("FTB_LINATTN_IMPL"); return e && !strcmp(e, "simt"); }();
   if (heads * dh == 128 && !simt) {
     CUtensorMap tm;
-    FTB_TRY(make_voxel_tmap(&tm, qkv, kCtxT, 16));
+    int vdiv = 1;
+    FTB_TRY(make_voxel_tmap(&tm, qkv, kCtxT, 16, &vdiv));
     CtxParams p;
+    p.vdiv = vdiv;
     p.heads = heads; p.dh = dh; p.hd = heads * dh;
     p.cgtot = qkv.cg();
     p.vox = (long long)qkv.voxels();
@@ -1121,8 +1126,10 @@ int linattn_kv_context(const Act& x, int cgoff, int cg, const float* ss, const b
   FTB_CHECK(heads * dh == 128, "fused k/v context needs heads*dim_head == 128");
   FTB_CHECK(cg >= 2 && cg % 2 == 0 && cg <= 16, "fused k/v context: 16..128 input channels");
   CUtensorMap tm;
-  FTB_TRY(make_voxel_tmap(&tm, x, kKvT, cg));
+  int vdiv = 1;
+  FTB_TRY(make_voxel_tmap(&tm, x, kKvT, cg, &vdiv));
   KvCtxParams p;
+  p.vdiv = vdiv;
   p.heads = heads; p.dh = dh; p.hd = 128;
   p.cg = cg; p.cgtot = x.cg(); p.cgoff = cgoff;
   p.vox = (long long)x.voxels();
@@ -1159,8 +1166,10 @@ int linattn_q_out(const Act& x, const float* ss, const bf16* wq, const bf16* mb,
   FTB_CHECK(x.C % 16 == 0 && x.C <= 128 && out.C == x.C && out.B == x.B && out.voxels() == x.voxels(),
             "fused q/out: 16..128 channels, output shaped like the input");
   CUtensorMap tm;
-  FTB_TRY(make_voxel_tmap(&tm, x, kQoT, x.cg()));
+  int vdiv = 1;
+  FTB_TRY(make_voxel_tmap(&tm, x, kQoT, x.cg(), &vdiv));
   QoutParams p;
+  p.vdiv = vdiv;
   p.heads = heads; p.dh = dh;
   p.cg = x.cg(); p.C = x.C; p.cgtot = x.cg(); p.cgoff = 0; p.out_cgtot = out.cg();
   p.vox = (long long)x.voxels();

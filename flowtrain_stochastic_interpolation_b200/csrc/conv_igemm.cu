@@ -94,6 +94,7 @@ struct IgemmParams {
   unsigned long long drop_key;
   int f32_accum;               // fp32 mode: out_f32 += instead of = (the hi/lo operand products of one conv)
   long long w_tile_stride;     // elements between the packed weights of consecutive N tiles (blockIdx.y = tile)
+  int vdiv;                    // flat tiles: divisor of the voxel coordinate of the tensor map (32: wide rows, 1)
   int no_fast27;               // FTB_CONV_NO_FAST27: always walk the table tap by tap
 };
 
@@ -672,7 +673,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
               mbar_expect_tx(&plane_full[pslot], bytes);
               uint8_t* dst = s_planes + (size_t)pslot * p.slot_stride;
               const int dz = c.d0 - p.pad + q;
-              if (p.flat) tma_load_3d(dst, tm, &plane_full[pslot], 0, dz * 128, cgc);
+              if (p.flat) tma_load_3d(dst, tm, &plane_full[pslot], 0, dz * 128 / p.vdiv, cgc);
               else tma_load_4d(dst, tm, &plane_full[pslot], (c.w0 - p.padw) * 8, c.h0 - p.pad, dz, cgc);
               if (++pslot == (uint32_t)p.nslot) { pslot = 0; pphase ^= 1; }
             }
@@ -1154,10 +1155,28 @@ int conv_debug_read(long long* host, int n) {
   return cudaMemcpy(host, g_conv_dbg, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
 }
 
-int make_voxel_tmap(CUtensorMap* tm, const Act& a, int box_vox, int box_cg) {
+int make_voxel_tmap(CUtensorMap* tm, const Act& a, int box_vox, int box_cg, int* vdiv) {
   PFN_encodeTiled enc = get_encode();
   FTB_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   const cuuint64_t vox = (cuuint64_t)a.voxels();
+  // TMA works in units of the box's innermost dimension.  Narrow form: (8 channels, voxels, B*CG), innermost = 16 bytes.
+  // Wide form (whenever the voxel count and the box are multiples of 32): (32 voxels x 8 channels, voxels / 32, B*CG),
+  // innermost = 512 contiguous bytes; the box lands in shared memory byte for byte like the narrow one
+  // ([cg][voxel][8]).  *vdiv = divisor of the voxel coordinate (32 or 1).
+  static const bool no_wide = getenv("FTB_TMA_NARROW") != nullptr;
+  if (vdiv != nullptr && !no_wide && vox % 32 == 0 && box_vox % 32 == 0) {
+    *vdiv = 32;
+    cuuint64_t gdim[3] = {256, vox / 32, (cuuint64_t)a.B * a.cg()};
+    cuuint64_t gstr[2] = {512, vox * 16};
+    cuuint32_t box[3] = {256u, (cuuint32_t)(box_vox / 32), (cuuint32_t)box_cg};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, a.p, gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     tma_promo(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FTB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (wide voxel view) failed (" + std::to_string((int)r) + ")");
+    return 0;
+  }
+  if (vdiv != nullptr) *vdiv = 1;
   cuuint64_t gdim[3] = {8, vox, (cuuint64_t)a.B * a.cg()};
   cuuint64_t gstr[2] = {16, vox * 16};
   cuuint32_t box[3] = {8u, (cuuint32_t)box_vox, (cuuint32_t)box_cg};
@@ -1407,8 +1426,11 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   CUtensorMap tm0, tm1;
   const int box0 = pick(p.cg0), box1 = s1.t ? pick(p.cg1) : 0;   // TMA box = one channel chunk
   if (p.flat) {
-    FTB_TRY(make_voxel_tmap(&tm0, a0, 128, box0));
-    if (s1.t) FTB_TRY(make_voxel_tmap(&tm1, *s1.t, 128, box1)); else tm1 = tm0;
+    int vd0 = 1, vd1 = 1;
+    FTB_TRY(make_voxel_tmap(&tm0, a0, 128, box0, &vd0));
+    if (s1.t) FTB_TRY(make_voxel_tmap(&tm1, *s1.t, 128, box1, &vd1)); else { tm1 = tm0; vd1 = vd0; }
+    FTB_CHECK(vd0 == vd1, "conv: the two sources of a 1x1x1 conv must have the same voxel count");
+    p.vdiv = vd0;
   } else {
     FTB_TRY(make_plane_tmap(&tm0, a0, p.BW, p.BH, box0));
     if (s1.t) FTB_TRY(make_plane_tmap(&tm1, *s1.t, p.BW, p.BH, box1)); else tm1 = tm0;

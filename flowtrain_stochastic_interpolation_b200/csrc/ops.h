@@ -78,7 +78,7 @@ int conv_max_chunks();
 
 // 3-D TMA view of a blocked activation as (8 channels, voxels, B*CG); box = (8, box_vox, box_cg):
 // lands in shared memory as [cg][voxel][8], the no-swizzle MN-major UMMA operand layout.
-int make_voxel_tmap(CUtensorMap* tm, const Act& a, int box_vox, int box_cg);
+int make_voxel_tmap(CUtensorMap* tm, const Act& a, int box_vox, int box_cg, int* vdiv = nullptr);
 
 // fp32 [Cout][Cin][k^3] -> packed bf16 tiles.  cin_map: K index -> source Cin index is
 // identity for k < cin_real, zero beyond.  in_scale (optional, [cin_real]) folds a per-input-
