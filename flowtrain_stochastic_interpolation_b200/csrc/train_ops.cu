@@ -488,32 +488,34 @@ __global__ void ksoftmax_bwd_kernel(bf16* __restrict__ dqkv, const bf16* __restr
   }
 }
 // dq third of dqkv, in place: q~ = softmax_d(q)*scale;  dq = q~ * (dq~ - sum_d q~ dq~ / scale)
-__global__ void qsoftmax_bwd_kernel(bf16* __restrict__ dqkv, const bf16* __restrict__ qkv, int cgtot, size_t vox,
-                                    int heads, int dh, float scale) {
-  const int b = blockIdx.y;
+// One thread per (voxel, head); the head's dh <= 32 channels of dq~ and q~ stay in registers between the dot product
+// and the update, so both tensors are read once (the two-pass version read them twice: 2.7 instead of 1.6 GB per
+// 64^3 layer at B=8).
+template <int CGH>
+__global__ void __launch_bounds__(256)
+qsoftmax_bwd_kernel(bf16* __restrict__ dqkv, const bf16* __restrict__ qkv, int cgtot, size_t vox, int heads, float scale) {
+  const int b = blockIdx.z, h = blockIdx.y;
   const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= vox) return;
-  const int cgh = dh / 8;
-  for (int h = 0; h < heads; ++h) {
-    float dot = 0.f;
-    for (int cg = 0; cg < cgh; ++cg) {
-      const size_t off = (((size_t)b * cgtot + h * cgh + cg) * vox + v) * 8;
-      float f[8], q[8];
-      unpack_bf16x8(*reinterpret_cast<const uint4*>(dqkv + off), f);
-      unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(qkv + off)), q);
+  float f[CGH][8], q[CGH][8];
+  float dot = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) dot = fmaf(f[j], q[j], dot);
-    }
-    dot /= scale;
-    for (int cg = 0; cg < cgh; ++cg) {
-      const size_t off = (((size_t)b * cgtot + h * cgh + cg) * vox + v) * 8;
-      float f[8], q[8];
-      unpack_bf16x8(*reinterpret_cast<const uint4*>(dqkv + off), f);
-      unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(qkv + off)), q);
+  for (int cg = 0; cg < CGH; ++cg) {
+    const size_t off = (((size_t)b * cgtot + h * CGH + cg) * vox + v) * 8;
+    unpack_bf16x8(*reinterpret_cast<const uint4*>(dqkv + off), f[cg]);
+    unpack_bf16x8(__ldg(reinterpret_cast<const uint4*>(qkv + off)), q[cg]);
+  }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = q[j] * (f[j] - dot);
-      *reinterpret_cast<uint4*>(dqkv + off) = pack_bf16x8(f);
-    }
+  for (int cg = 0; cg < CGH; ++cg)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dot = fmaf(f[cg][j], q[cg][j], dot);
+  dot /= scale;
+#pragma unroll
+  for (int cg = 0; cg < CGH; ++cg) {
+    const size_t off = (((size_t)b * cgtot + h * CGH + cg) * vox + v) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[cg][j] = q[cg][j] * (f[cg][j] - dot);
+    *reinterpret_cast<uint4*>(dqkv + off) = pack_bf16x8(f[cg]);
   }
 }
 // mem_kv [2][heads][dh][n_mem] gradient; grid (heads, B), block dh*n_mem threads (<= 256); samples add atomically
@@ -650,12 +652,30 @@ __global__ void linear_bwd_w_kernel(const float* __restrict__ dy, int dy_stride,
     if (i == 0 && db) db[r] += s;
   }
 }
-__global__ void linear_bwd_x_kernel(const float* __restrict__ dy, int dy_stride, const float* __restrict__ w, int B,
-                                    int rows, int cols, float* __restrict__ dx, int add) {
+// grid (cols / 32, B), block 256 = 32 columns x 8 row slices (a serial loop over up to 384 rows per thread made each of
+// the 25 launches of a step a 27 us latency chain)
+__global__ void __launch_bounds__(256)
+linear_bwd_x_kernel(const float* __restrict__ dy, int dy_stride, const float* __restrict__ w, int B,
+                    int rows, int cols, float* __restrict__ dx, int add) {
+  __shared__ float s_part[8][32];
   const int b = blockIdx.y;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cols; i += gridDim.x * blockDim.x) {
+  const int ci = threadIdx.x & 31, rs = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + ci;
+  float a0 = 0.f, a1 = 0.f;
+  if (i < cols) {
+    int r = rs;
+    for (; r + 8 < rows; r += 16) {
+      a0 = fmaf(__ldg(dy + (size_t)b * dy_stride + r), __ldg(w + (size_t)r * cols + i), a0);
+      a1 = fmaf(__ldg(dy + (size_t)b * dy_stride + r + 8), __ldg(w + (size_t)(r + 8) * cols + i), a1);
+    }
+    if (r < rows) a0 = fmaf(__ldg(dy + (size_t)b * dy_stride + r), __ldg(w + (size_t)r * cols + i), a0);
+  }
+  s_part[rs][ci] = a0 + a1;
+  __syncthreads();
+  if (rs == 0 && i < cols) {
     float a = 0.f;
-    for (int r = 0; r < rows; ++r) a = fmaf(dy[(size_t)b * dy_stride + r], w[(size_t)r * cols + i], a);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a += s_part[k][ci];
     if (add) dx[(size_t)b * cols + i] += a; else dx[(size_t)b * cols + i] = a;
   }
 }
@@ -903,8 +923,12 @@ int ksoftmax_bwd(Act& dqkv, const Act& qkv, int hd, const float* ssum, cudaStrea
 }
 int qsoftmax_bwd(Act& dqkv, const Act& qkv, int heads, int dh, cudaStream_t st) {
   const size_t vox = qkv.voxels();
-  dim3 grid((unsigned)((vox + 255) / 256), qkv.B);
-  qsoftmax_bwd_kernel<<<grid, 256, 0, st>>>(dqkv.p, qkv.p, qkv.cg(), vox, heads, dh, 1.f / sqrtf((float)dh));
+  FTB_CHECK(dh == 8 || dh == 16 || dh == 32, "qsoftmax_bwd: dim_head must be 8, 16 or 32");
+  dim3 grid((unsigned)((vox + 255) / 256), heads, qkv.B);
+  const float scale = 1.f / sqrtf((float)dh);
+  if (dh == 32) qsoftmax_bwd_kernel<4><<<grid, 256, 0, st>>>(dqkv.p, qkv.p, qkv.cg(), vox, heads, scale);
+  else if (dh == 16) qsoftmax_bwd_kernel<2><<<grid, 256, 0, st>>>(dqkv.p, qkv.p, qkv.cg(), vox, heads, scale);
+  else qsoftmax_bwd_kernel<1><<<grid, 256, 0, st>>>(dqkv.p, qkv.p, qkv.cg(), vox, heads, scale);
   FTB_LAUNCH_OK();
   return 0;
 }
@@ -940,7 +964,7 @@ int linear_bwd(const float* dy, int dy_stride, const float* x, const float* w, i
     FTB_LAUNCH_OK();
   }
   if (dx) {
-    linear_bwd_x_kernel<<<dim3(cdiv(cols, 128), B), 128, 0, st>>>(dy, dy_stride, w, B, rows, cols, dx, dx_add ? 1 : 0);
+    linear_bwd_x_kernel<<<dim3(cdiv(cols, 32), B), 256, 0, st>>>(dy, dy_stride, w, B, rows, cols, dx, dx_add ? 1 : 0);
     FTB_LAUNCH_OK();
   }
   return 0;

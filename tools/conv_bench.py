@@ -15,6 +15,7 @@ dev = torch.device("cuda:0")
 SHAPES = [  # (c1, c2, cout, k, size, norm/silu/resid flags)
     (48, 0, 48, 3, 64, 1), (48, 48, 48, 3, 64, 1), (96, 0, 96, 3, 32, 1), (96, 96, 96, 3, 32, 1),
     (18, 0, 48, 7, 64, 0), (48, 0, 384, 1, 64, 0), (96, 0, 48, 3, 64, 0), (144, 0, 144, 3, 16, 1),
+    (48, 48, 48, 1, 64, 0), (96, 96, 96, 1, 32, 0), (192, 0, 192, 3, 8, 1), (192, 192, 192, 3, 4, 1),
 ]
 
 
