@@ -875,7 +875,8 @@ __global__ void kshift_kernel(const float* __restrict__ w, const float* __restri
 
 // grid (heads, B): merge the split partials + memory kv -> ctx[h]; then this head's 32 columns
 // of the folded projection M_b[c][h*dh + d] = q_scale * sum_e W[c][h*dh+e] ctx[h][d][e]
-__global__ void __launch_bounds__(256)
+// 1024 threads: one partial column (a 37-deep latency chain) per thread in the merge
+__global__ void __launch_bounds__(1024)
 combine_head_kernel(const float* __restrict__ part, int nsplit, const float* __restrict__ kmax,
                     int kmax_bstride, int heads, int dh, const float* __restrict__ mem_kv, int n_mem, const float* __restrict__ w_out,
                     int C, float q_scale, bf16* __restrict__ wpack, float* __restrict__ ctx_dbg,
@@ -1209,7 +1210,7 @@ int linattn_combine(const float* part, int nsplit, const float* kmax, int kmax_b
                     bf16* wpack_out, float* ctx_dbg, cudaStream_t st, float* kstat) {
   FTB_CHECK(C % 16 == 0 && (heads * dh) % 16 == 0, "linattn: C and heads*dim_head must be multiples of 16");
   FTB_CHECK(dh <= 32, "linattn: dim_head must be at most 32");
-  combine_head_kernel<<<dim3(heads, B), 256, 0, st>>>(part, nsplit, kmax, kmax_bstride, heads, dh, mem_kv, n_mem, w_out, C,
+  combine_head_kernel<<<dim3(heads, B), 1024, 0, st>>>(part, nsplit, kmax, kmax_bstride, heads, dh, mem_kv, n_mem, w_out, C,
                                                       q_scale, wpack_out, ctx_dbg, kstat);
   FTB_LAUNCH_OK();
   return 0;
