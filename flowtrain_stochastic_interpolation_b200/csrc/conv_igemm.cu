@@ -95,7 +95,7 @@ struct IgemmParams {
   int f32_accum;               // fp32 mode: out_f32 += instead of = (the hi/lo operand products of one conv)
   long long w_tile_stride;     // elements between the packed weights of consecutive N tiles (blockIdx.y = tile)
   int vdiv;                    // flat tiles: divisor of the voxel coordinate of the tensor map (32: wide rows, 1)
-  int no_fast27;               // FTB_CONV_NO_FAST27: always walk the table tap by tap
+  int no_fast27;               // FTB_CONV_NO_FAST27: always walk the table tap by tap (no register-cached entries)
 };
 
 struct ItemCoord {
@@ -571,26 +571,6 @@ __device__ __forceinline__ void run_taps_cached(const IssueCtx& ic, const TapCtx
     }
 }
 
-// Resident 3^3 weights, one channel chunk of three k-steps (the 48 -> 48 layers that hold most of the FLOPs): all
-// 27 (tap, k-step) MMAs of ONE table entry in a straight line.  The issuer is a single thread, and ncu (r02, source
-// page) showed the kernel bound by ITS instruction stream, not by the tensor pipe: with the per-tap walk an entry is
-// re-read and re-decoded for every tap (41 instructions per 3 MMAs plus ~100 per tap around the loop, 287 cycles per
-// 3 MMAs against 216 of tensor time).  Here an entry is decoded once per 27 MMAs: two adds per instruction remain.
-// skip_first: (tap 0, k-step 0) was already issued through the overwrite table.
-__device__ __forceinline__ void issue_entry_27(const IssueCtx& ic, uint32_t a0, uint32_t b0, uint32_t d, uint32_t idesc,
-                                               uint32_t rowp_enc, uint32_t wchunk_enc) {
-#pragma unroll
-  for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-    for (int kw = 0; kw < 3; ++kw)
-#pragma unroll
-      for (int ks = 0; ks < 3; ++ks) {
-        if ((kh | kw | ks) == 0) continue;
-        umma_bf16_lohi(d, a0 + (uint32_t)kh * rowp_enc + (uint32_t)kw + (uint32_t)ks * ic.kinc, ic.a_hi,
-                       b0 + (uint32_t)(kh * 3 + kw) * wchunk_enc + (uint32_t)ks * ic.kstep, ic.b_hi, idesc, 1u);
-      }
-}
-
 template <bool kTrain>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
@@ -743,7 +723,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     const uint32_t nb_enc = (uint32_t)(p.N * 2);                           // one depth tap of B rows, >>4
     const uint32_t tab_addr = smem_u32(tab);
     const bool stream_w = !p.w_resident;
-    const bool fast27 = !stream_w && p.ncc == 1 && p.K == 3 && p.Kw == 3 && p.cc_ks[0] == 3 && !p.no_fast27;
     // ring cursors, advanced incrementally (no divisions on the issue path)
     uint32_t slot_w0 = 0;                  // ring slot of the current window's plane 0
     uint32_t rslot = 0, rphase = 0;        // next plane_full barrier to wait for
@@ -824,29 +803,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
           mbar_wait(&acc_empty[ab], ((gctr >> 1) & 1) ^ 1);
           if (p.dbg) dbg_acc += clock64() - tq0;
           ic.acc0 = tmem_base + ab * p.NZ * p.N;
-          if (fast27) {
-            const int upto = min(npl, g * p.NZ + win);
-            for (int i = waited; i < upto; ++i) {
-              mbar_wait(&plane_full[rslot], rphase);
-              if (++rslot == ic.nslot) { rslot = 0; rphase ^= 1; }
-            }
-            waited = upto;
-            if (!w_waited)
-              for (int t = 0; t < 9; ++t) mbar_wait(&w_full[t], 0);
-            tc_fence_after();
-            ic.slot_w0 = slot_w0;
-            // first touch of every accumulator: (tap 0, k-step 0) through the overwrite table
-            issue_entries<1>(ic, tab_addr, tab_addr + (uint32_t)n_first * 16u, 0u, w_enc, true);
-            const uint32_t ea_end = tab_addr + (uint32_t)(n_first + n_main) * 16u;
-            for (uint32_t ea = tab_addr + (uint32_t)n_first * 16u; ea < ea_end; ea += 16) {
-              uint32_t ex, ey, ez, ew;
-              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ex), "=r"(ey), "=r"(ez), "=r"(ew) : "r"(ea));
-              uint32_t slot = slot_w0 + ex;
-              if (slot >= ic.nslot) slot -= ic.nslot;
-              issue_entry_27(ic, ic.planes_enc + slot * ic.slot_enc, (ey & 0x7FFFFFFFu) + w_enc, ic.acc0 + ez, ew, rowp_enc,
-                             wchunk_enc);
-            }
-          } else
           for (int cc = 0; cc < p.ncc; ++cc) {
             if (p.dbg) tq0 = clock64();
             int n_new;
