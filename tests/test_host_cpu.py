@@ -334,3 +334,17 @@ def test_streaming_dataset_stand_in_contract():
     assert int((a + 1).min()) >= 0 and int((a + 1).max()) <= 14
     with pytest.raises(RuntimeError, match="CUDA"):
         ftb.DevicePrefetcher(loader, "cpu")
+
+
+def test_bench_reads_roofline_traffic_from_the_ncu_summary():
+    """bench.py computes roofline.traffic from the newest committed `ncu --set full` summary of the conv kernel
+    (profiles/rNN_conv_igemm_ncu_full.csv): read + write DRAM bytes of every captured launch and their mean."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    t = bench.ncu_traffic()
+    assert t is not None and t["source"].startswith("profiles/r") and t["source"].endswith("_conv_igemm_ncu_full.csv")
+    assert len(t["launches"]) >= 1 and all(b > 1e8 for b in t["launches"])   # hundreds of MB per 64^3 launch
+    assert abs(t["dram_bytes_per_launch"] - sum(t["launches"]) / len(t["launches"])) < 1.0
+    # at or below the algorithmic bytes of a 48 -> 48 @64^3 B=8 launch with a residual (604 MB) plus 10 %
+    assert t["dram_bytes_per_launch"] < 1.1 * 604e6
