@@ -35,28 +35,34 @@ __global__ void pack_kernel(const float* __restrict__ x, int B, int C, size_t vo
   }
 }
 
-// One block per (b, d, h) row: the C fp32 rows are staged in shared memory with a zero halo, then
-// every (channel group, w) output reads its 8 (kw, c) taps from there (coalesced both ways).
+// One block per (b, d, group of kUnfRows h rows): the C fp32 rows of every h are staged in shared memory with a zero
+// halo, then every (channel group, w) output reads its 8 (kw, c) taps from there (coalesced both ways).  Several rows
+// per block amortise the per-block set-up (tap tables, barrier): with one row per block the 32 768 small blocks of a
+// 64^3 B=8 input ran at 3.3 TB/s.
+constexpr int kUnfRows = 4;
 __global__ void __launch_bounds__(256)
 pack_unfold_w_kernel(const float* __restrict__ x, int C, int D, int H, int W, int K, int CG,
                      bf16* __restrict__ out) {
-  extern __shared__ float s_row[];                  // [C][W + K - 1]
+  extern __shared__ float s_row[];                  // [kUnfRows][C][W + K - 1]
   __shared__ unsigned char s_kw[256], s_c[256];     // per unfolded channel: tap and source channel
   const int pad = K / 2, RW = W + K - 1;
+  const int hgroups = (H + kUnfRows - 1) / kUnfRows;
   int blk = blockIdx.x;
-  const int h = blk % H; blk /= H;
+  const int hg = blk % hgroups; blk /= hgroups;
   const int d = blk % D;
   const int b = blk / D;
+  const int h0 = hg * kUnfRows;
+  const int nh = min(kUnfRows, H - h0);
   const size_t vox = (size_t)D * H * W;
-  const size_t rowoff = ((size_t)d * H + h) * W;
   for (int i = threadIdx.x; i < CG * 8; i += blockDim.x) {
     const int kw = i / C;
     s_kw[i] = (unsigned char)(kw < K ? kw : 255);
     s_c[i] = (unsigned char)(i - kw * C);
   }
-  for (int i = threadIdx.x; i < C * RW; i += blockDim.x) {
-    const int c = i / RW, wr = i - c * RW, w = wr - pad;
-    s_row[i] = (w >= 0 && w < W) ? __ldg(x + ((size_t)b * C + c) * vox + rowoff + w) : 0.f;
+  for (int i = threadIdx.x; i < nh * C * RW; i += blockDim.x) {
+    const int r = i / (C * RW), j = i - r * (C * RW);
+    const int c = j / RW, wr = j - c * RW, w = wr - pad;
+    s_row[i] = (w >= 0 && w < W) ? __ldg(x + ((size_t)b * C + c) * vox + ((size_t)d * H + h0 + r) * W + w) : 0.f;
   }
   __syncthreads();
   // thread = (channel group, W lane): its 8 (kw, c) taps are loop invariant
@@ -69,12 +75,15 @@ pack_unfold_w_kernel(const float* __restrict__ x, int C, int D, int H, int W, in
       const int cc = cg * 8 + j;
       off[j] = s_kw[cc] == 255 ? -1 : s_c[cc] * RW + s_kw[cc];
     }
-    bf16* orow = out + ((((size_t)b * CG + cg) * vox) + rowoff) * 8;
-    for (int w = wl; w < W; w += lanes) {
-      float f[8];
+    for (int r = 0; r < nh; ++r) {
+      const float* sr = s_row + (size_t)r * C * RW;
+      bf16* orow = out + ((((size_t)b * CG + cg) * vox) + ((size_t)d * H + h0 + r) * W) * 8;
+      for (int w = wl; w < W; w += lanes) {
+        float f[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = off[j] < 0 ? 0.f : s_row[off[j] + w];
-      *reinterpret_cast<uint4*>(orow + (size_t)w * 8) = pack_bf16x8(f);
+        for (int j = 0; j < 8; ++j) f[j] = off[j] < 0 ? 0.f : sr[off[j] + w];
+        *reinterpret_cast<uint4*>(orow + (size_t)w * 8) = pack_bf16x8(f);
+      }
     }
   }
 }
@@ -650,11 +659,11 @@ int pack_unfold_w(const float* x, int B, int C, int D, int H, int W, int K, Act&
   FTB_CHECK(out.B == B && out.D == D && out.H == H && out.W == W && out.C >= K * C && out.C % 16 == 0,
             "pack_unfold_w: output activation shape");
   FTB_CHECK(out.cg() * 8 <= 256 && C <= 255, "pack_unfold_w: at most 256 unfolded channels");
-  const size_t smem = (size_t)C * (W + K - 1) * sizeof(float);
-  FTB_CHECK(smem <= 40 * 1024, "pack_unfold_w: row too wide for shared memory");
+  const size_t smem = (size_t)kUnfRows * C * (W + K - 1) * sizeof(float);
+  FTB_CHECK(smem <= 44 * 1024, "pack_unfold_w: row too wide for shared memory");
   const int lanes = 256 / out.cg() >= 1 ? 256 / out.cg() : 1;
   FTB_CHECK(out.cg() <= 256, "pack_unfold_w: too many channel groups");
-  pack_unfold_w_kernel<<<(unsigned)((size_t)B * D * H), out.cg() * lanes, smem, st>>>(x, C, D, H, W, K, out.cg(), out.p);
+  pack_unfold_w_kernel<<<(unsigned)((size_t)B * D * cdiv(H, kUnfRows)), out.cg() * lanes, smem, st>>>(x, C, D, H, W, K, out.cg(), out.p);
   FTB_LAUNCH_OK();
   return 0;
 }
