@@ -539,7 +539,8 @@ struct TapCtx {
 template <int NKS>
 __device__ __forceinline__ void run_taps_cached(const IssueCtx& ic, const TapCtx& tc, const uint32_t (&ca)[kCache],
                                                 const uint32_t (&cb)[kCache], const uint32_t (&cd)[kCache],
-                                                const uint32_t (&ci)[kCache], int ne, uint32_t& wslot, uint32_t& wphase) {
+                                                const uint32_t (&ci)[kCache], int ne, uint32_t& wslot, uint32_t& wphase,
+                                                bool& w_ready) {
   uint32_t aoff_row = 0;
   uint32_t res_slot = (uint32_t)tc.res_slot0;
   for (int kh = 0; kh < tc.K; ++kh, aoff_row += tc.rowp_enc)
@@ -547,7 +548,13 @@ __device__ __forceinline__ void run_taps_cached(const IssueCtx& ic, const TapCtx
       uint32_t slot;
       if (tc.stream_w) {
         slot = wslot;
-        mbar_wait(&tc.w_full[slot], wphase);
+        if (!w_ready) {   // also tests the next slot: when that is already full, the next tap skips its wait
+          uint32_t ns = slot + 1, np = wphase;
+          if (ns == (uint32_t)tc.nwslot) { ns = 0; np ^= 1; }
+          w_ready = mbar_wait_test_next(&tc.w_full[slot], wphase, &tc.w_full[ns], np);
+        } else {
+          w_ready = false;
+        }
         tc_fence_after();
       } else {
         slot = res_slot++;
@@ -727,6 +734,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
     uint32_t slot_w0 = 0;                  // ring slot of the current window's plane 0
     uint32_t rslot = 0, rphase = 0;        // next plane_full barrier to wait for
     uint32_t wslot = 0, wphase = 0;        // next streamed weight chunk
+    bool w_ready = false;                  // the slot at the cursor was already seen full (tested with the previous wait)
     uint32_t gctr = 0;
     int tab_nze = -1, n_first = 0, n_main = 0;
     bool w_waited = false;
@@ -855,10 +863,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
               tcx.K = p.K; tcx.Kw = p.Kw; tcx.nwslot = p.wslot; tcx.res_slot0 = cc * p.taps;
               tcx.stream_w = stream_w; tcx.w_waited = w_waited; tcx.first_pass = cc == 0;
               switch (nks) {
-                case 1: run_taps_cached<1>(ic, tcx, ca, cb, cd, ci, n_main, wslot, wphase); break;
-                case 2: run_taps_cached<2>(ic, tcx, ca, cb, cd, ci, n_main, wslot, wphase); break;
-                case 3: run_taps_cached<3>(ic, tcx, ca, cb, cd, ci, n_main, wslot, wphase); break;
-                default: run_taps_cached<4>(ic, tcx, ca, cb, cd, ci, n_main, wslot, wphase); break;
+                case 1: run_taps_cached<1>(ic, tcx, ca, cb, cd, ci, n_main, wslot, wphase, w_ready); break;
+                case 2: run_taps_cached<2>(ic, tcx, ca, cb, cd, ci, n_main, wslot, wphase, w_ready); break;
+                case 3: run_taps_cached<3>(ic, tcx, ca, cb, cd, ci, n_main, wslot, wphase, w_ready); break;
+                default: run_taps_cached<4>(ic, tcx, ca, cb, cd, ci, n_main, wslot, wphase, w_ready); break;
               }
               if (p.dbg) dbg_issue += clock64() - ti0;
             } else {
@@ -906,6 +914,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
                 if (stream_w) {
                   umma_commit(&w_empty[wslot_i]);
                   if (++wslot == (uint32_t)p.wslot) { wslot = 0; wphase ^= 1; }
+                  w_ready = false;
                 }
               }
             }   // !cached

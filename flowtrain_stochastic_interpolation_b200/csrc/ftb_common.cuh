@@ -155,6 +155,30 @@ __device__ __forceinline__ void mbar_wait4(uint32_t a0, uint32_t p0, uint32_t a1
   }
 }
 
+// Wait for `bar` and, in the same shared-memory round trip, TEST (non-blocking) whether the barrier the caller will
+// need next has completed too: when it has, the caller skips that wait altogether.  Returns the test's result.
+__device__ __forceinline__ bool mbar_wait_test_next(uint64_t* bar, uint32_t parity, uint64_t* next, uint32_t next_parity) {
+  uint32_t spins = 0;
+  while (true) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred q0, q1;\n\t.reg .u32 r0, r1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q0, [%1], %2;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 q1, [%3], %4;\n\t"
+        "selp.u32 r0, 1, 0, q0;\n\t"
+        "selp.u32 r1, 2, 0, q1;\n\t"
+        "or.b32 %0, r0, r1;\n\t}"
+        : "=r"(r)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(smem_u32(next)), "r"(next_parity)
+        : "memory");
+    if (r & 1u) return (r & 2u) != 0;
+    if (++spins > 20000000u) {
+      printf("ftb: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+
 // The same wait for warps that are not on the critical path (producers waiting for a free slot, epilogue warps
 // waiting for an accumulator): sleep between polls, so the polling does not take shared-memory cycles from the
 // tensor core's operand fetches.

@@ -204,6 +204,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
       const uint32_t x_base = (smem_u32(smem + p.off_x) >> 4) | b_lbo;
       int n = 0;
       uint32_t s = 0, ph = 0;
+      bool ready = false;   // the stage at the cursor was already seen full
       long long iw = 0, it0 = clock64();
       int t = i_lo % tiles_pp, xd = (i_lo / tiles_pp) % p.D;
       for (int it = i_lo; it < i_hi; ++it, ++t) {
@@ -212,7 +213,13 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
         if (!(d0 >= 0 && d0 < p.D) && !(p.kdp == 2 && kd + 1 < p.K && d1 >= 0 && d1 < p.D)) continue;
         long long iq = 0;
         if (p.dbg) iq = clock64();
-        mbar_wait(&full[s], ph);
+        if (!ready) {   // also tests the next stage's barrier: when that is already full its wait is skipped
+          uint32_t s1 = s + 1, ph1 = ph;
+          if (s1 == (uint32_t)p.nstage) { s1 = 0; ph1 ^= 1; }
+          ready = mbar_wait_test_next(&full[s], ph, &full[s1], ph1);
+        } else {
+          ready = false;
+        }
         if (p.dbg) iw += clock64() - iq;
         tc_fence_after();
         const uint32_t a0 = a_base + s * du_enc;
