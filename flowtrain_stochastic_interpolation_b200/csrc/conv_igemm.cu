@@ -95,6 +95,7 @@ struct IgemmParams {
   int f32_accum;               // fp32 mode: out_f32 += instead of = (the hi/lo operand products of one conv)
   long long w_tile_stride;     // elements between the packed weights of consecutive N tiles (blockIdx.y = tile)
   int vdiv;                    // flat tiles: divisor of the voxel coordinate of the tensor map (32: wide rows, 1)
+  int wait_test;               // per-tap slot wait also tests the next slot (FTB_CONV_WAIT_TEST=1; off by default)
   int no_fast27;               // FTB_CONV_NO_FAST27: always walk the table tap by tap (no register-cached entries)
 };
 
@@ -534,7 +535,7 @@ struct TapCtx {
   uint32_t w_enc, wchunk_enc, rowp_enc, first_lo, first_hi;
   uint64_t *w_full, *w_empty;
   int K, Kw, nwslot, res_slot0;
-  bool stream_w, w_waited, first_pass;
+  bool stream_w, w_waited, first_pass, wait_test;
 };
 template <int NKS>
 __device__ __forceinline__ void run_taps_cached(const IssueCtx& ic, const TapCtx& tc, const uint32_t (&ca)[kCache],
@@ -551,7 +552,7 @@ __device__ __forceinline__ void run_taps_cached(const IssueCtx& ic, const TapCtx
         if (!w_ready) {   // also tests the next slot: when that is already full, the next tap skips its wait
           uint32_t ns = slot + 1, np = wphase;
           if (ns == (uint32_t)tc.nwslot) { ns = 0; np ^= 1; }
-          w_ready = mbar_wait_test_next(&tc.w_full[slot], wphase, &tc.w_full[ns], np);
+          w_ready = mbar_wait_test_next(&tc.w_full[slot], wphase, &tc.w_full[ns], np, tc.wait_test);
         } else {
           w_ready = false;
         }
@@ -808,26 +809,31 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
         if (leader) {
           long long tq0 = 0;
           if (p.dbg) tq0 = clock64();
-          mbar_wait(&acc_empty[ab], ((gctr >> 1) & 1) ^ 1);
-          if (p.dbg) dbg_acc += clock64() - tq0;
+          // (the accumulator-buffer barrier rides in the first plane batch: one round trip for the whole group start)
           ic.acc0 = tmem_base + ab * p.NZ * p.N;
           for (int cc = 0; cc < p.ncc; ++cc) {
             if (p.dbg) tq0 = clock64();
             int n_new;
             if (p.ncc == 1) { const int upto = min(npl, g * p.NZ + win); n_new = upto - waited; waited = upto; }
             else n_new = win;
-            for (int i = 0; i < n_new; i += 4) {   // up to four planes per round trip
-              uint32_t ba[4], bp[4];
+            int extra = cc == 0 ? 1 : 0;   // acc_empty still to be waited for
+            for (int i = 0; i < n_new || extra; ) {   // up to six barriers per round trip
+              uint32_t ba[6], bp[6];
+              int j = 0;
+              if (extra) { ba[0] = smem_u32(&acc_empty[ab]); bp[0] = ((gctr >> 1) & 1) ^ 1; j = 1; extra = 0; }
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                if (i + j < n_new) {
-                  ba[j] = smem_u32(&plane_full[rslot]); bp[j] = rphase;
-                  if (++rslot == ic.nslot) { rslot = 0; rphase ^= 1; }
-                } else {
-                  ba[j] = ba[j - 1]; bp[j] = bp[j - 1];
+              for (int k = 0; k < 6; ++k) {
+                if (k >= j) {
+                  if (i < n_new) {
+                    ba[k] = smem_u32(&plane_full[rslot]); bp[k] = rphase;
+                    if (++rslot == ic.nslot) { rslot = 0; rphase ^= 1; }
+                    ++i;
+                  } else {
+                    ba[k] = ba[k > 0 ? k - 1 : 0]; bp[k] = bp[k > 0 ? k - 1 : 0];
+                  }
                 }
               }
-              mbar_wait4(ba[0], bp[0], ba[1], bp[1], ba[2], bp[2], ba[3], bp[3]);
+              mbar_wait6(ba, bp);
             }
             if (p.dbg) dbg_plane += clock64() - tq0;
             tc_fence_after();
@@ -861,7 +867,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
               tcx.first_lo = tab_addr; tcx.first_hi = tab_addr + (uint32_t)n_first * 16u;
               tcx.w_full = w_full; tcx.w_empty = w_empty;
               tcx.K = p.K; tcx.Kw = p.Kw; tcx.nwslot = p.wslot; tcx.res_slot0 = cc * p.taps;
-              tcx.stream_w = stream_w; tcx.w_waited = w_waited; tcx.first_pass = cc == 0;
+              tcx.stream_w = stream_w; tcx.w_waited = w_waited; tcx.first_pass = cc == 0; tcx.wait_test = p.wait_test != 0;
               switch (nks) {
                 case 1: run_taps_cached<1>(ic, tcx, ca, cb, cd, ci, n_main, wslot, wphase, w_ready); break;
                 case 2: run_taps_cached<2>(ic, tcx, ca, cb, cd, ci, n_main, wslot, wphase, w_ready); break;
@@ -1359,6 +1365,8 @@ int conv_igemm(const ConvSrc& s0, const ConvSrc& s1, const ConvWeights& w, const
   p.dbg = nullptr;
   static const int no_fast27 = getenv("FTB_CONV_NO_FAST27") ? 1 : 0;
   p.no_fast27 = no_fast27;
+  static const int wt_env = getenv("FTB_CONV_WAIT_TEST") ? 1 : 0;   // measured 2.7 % slower here (profiles/r02_wait_test_next.log)
+  p.wait_test = wt_env;
   if (getenv("FTB_CONV_DBG")) {
     static long long* dbuf = nullptr;
     if (!dbuf) FTB_CUDA(cudaMalloc(&dbuf, 256 * 16 * sizeof(long long)));

@@ -155,9 +155,42 @@ __device__ __forceinline__ void mbar_wait4(uint32_t a0, uint32_t p0, uint32_t a1
   }
 }
 
+// Six barriers per round trip (the group start of the conv issuer: accumulator buffer + new planes).
+__device__ __forceinline__ void mbar_wait6(const uint32_t (&a)[6], const uint32_t (&p)[6]) {
+  uint32_t spins = 0;
+  while (true) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred q0, q1, q2, q3, q4, q5;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q0, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q1, [%3], %4;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q2, [%5], %6;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q3, [%7], %8;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q4, [%9], %10;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q5, [%11], %12;\n\t"
+        "and.pred q0, q0, q1;\n\t"
+        "and.pred q2, q2, q3;\n\t"
+        "and.pred q4, q4, q5;\n\t"
+        "and.pred q0, q0, q2;\n\t"
+        "and.pred q0, q0, q4;\n\t"
+        "selp.u32 %0, 1, 0, q0;\n\t}"
+        : "=r"(ok)
+        : "r"(a[0]), "r"(p[0]), "r"(a[1]), "r"(p[1]), "r"(a[2]), "r"(p[2]), "r"(a[3]), "r"(p[3]), "r"(a[4]), "r"(p[4]),
+          "r"(a[5]), "r"(p[5])
+        : "memory");
+    if (ok) return;
+    if (++spins > 20000000u) {
+      printf("ftb: mbarrier (x6) timeout block %d thread %d bar %u\n", blockIdx.x, threadIdx.x, a[0]);
+      __trap();
+    }
+  }
+}
+
 // Wait for `bar` and, in the same shared-memory round trip, TEST (non-blocking) whether the barrier the caller will
 // need next has completed too: when it has, the caller skips that wait altogether.  Returns the test's result.
-__device__ __forceinline__ bool mbar_wait_test_next(uint64_t* bar, uint32_t parity, uint64_t* next, uint32_t next_parity) {
+__device__ __forceinline__ bool mbar_wait_test_next(uint64_t* bar, uint32_t parity, uint64_t* next, uint32_t next_parity,
+                                                    bool test = true) {
+  if (!test) { mbar_wait(bar, parity); return false; }
   uint32_t spins = 0;
   while (true) {
     uint32_t r;

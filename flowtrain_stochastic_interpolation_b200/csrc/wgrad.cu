@@ -56,6 +56,7 @@ struct WgradParams {
   uint32_t du_bytes, x_bytes;
   uint32_t b_lbo, b_sbo, b_kh, b_kstep;   // X operand: K-direction / N-direction core-matrix strides, bytes per kh row, per k-step row
   int map4;             // 4-D tensor maps (inner dimension = a whole box row of TW voxels x 8 channels)
+  int wait_test;        // the stage wait also tests the next stage's barrier (FTB_NO_WAIT_TEST=1 turns it off)
   int dbg;              // FTB_WGRAD_DBG: block 0 prints issuer / producer cycle counters
   int TH, TW, kpr;      // voxel tile (TH x TW = 128), k-steps per tile row (1 when TW == 8: a k-step is two h rows)
   uint32_t off_x, off_bar, tmem_cols;
@@ -216,7 +217,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_du, const __grid_constant__ 
         if (!ready) {   // also tests the next stage's barrier: when that is already full its wait is skipped
           uint32_t s1 = s + 1, ph1 = ph;
           if (s1 == (uint32_t)p.nstage) { s1 = 0; ph1 ^= 1; }
-          ready = mbar_wait_test_next(&full[s], ph, &full[s1], ph1);
+          ready = mbar_wait_test_next(&full[s], ph, &full[s1], ph1, p.wait_test != 0);
         } else {
           ready = false;
         }
@@ -587,6 +588,8 @@ int conv_wgrad(const Act& x, int x_cgoff, int x_cg, const Act& dy, int dy_cgoff,
   p.nsplit = nsplit;
   static const int dbg_env = getenv("FTB_WGRAD_DBG") ? atoi(getenv("FTB_WGRAD_DBG")) : 0;
   p.dbg = dbg_env;
+  static const int wt_env = getenv("FTB_NO_WAIT_TEST") ? 0 : 1;
+  p.wait_test = wt_env;
 
   CUtensorMap tmd, tmx;
   // 4-D maps whenever a box row fits the 256-element limit of a box dimension (TW <= 16 with a W halo)
