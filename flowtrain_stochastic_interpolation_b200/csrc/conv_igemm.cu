@@ -7,7 +7,8 @@
 // the residual add (:278, :695), the pre-attention RMSNorm (:311, as a per-row scale) and the
 // q softmax of LinearAttention (:326,:329).
 //
-// Data flow per CTA (persistent, 192 threads = TMA warp | MMA warp | 4 epilogue warps):
+// Data flow per CTA (persistent, 384 threads = plane producer warp | two MMA issuer warps | weight producer warp |
+// 8 epilogue warps):
 //   * activations live in HBM as [B][C/8][D][H][W][8] bf16.  One TMA box = one halo PLANE
 //     (BH x BW voxels x all input channels) and lands in shared memory as [cg][h][w][8], which is
 //     exactly the no-swizzle K-major UMMA operand layout: 8 consecutive voxels along W form a
@@ -27,8 +28,10 @@
 //     small ring, once per group of NZ planes.
 //   * accumulators are double-buffered (the epilogue of group g overlaps the MMAs of g+1); each
 //     epilogue thread owns one voxel row, so the channel reduction of RMSNorm is thread-local.
-//   * the MMA issuer is one elected lane of warp 1 walking a per-group table (built by the whole
-//     warp): chunk -> table entry -> k-step, two adds per instruction.
+//   * an MMA issuer is one elected lane of warp 1 / 2 (disjoint accumulators).  The whole warp builds a per-group
+//     table of stacked MMAs; the lane decodes its entries ONCE per (group, channel chunk) pass into registers
+//     (issue_cached) and then walks tap -> entry -> k-step with two adds per instruction: the issuing thread's own
+//     instruction stream is what bounds the kernel, not the tensor pipe or shared memory.
 #include <stdlib.h>
 
 #include "ops.h"
